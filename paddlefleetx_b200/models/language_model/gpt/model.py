@@ -1,0 +1,359 @@
+"""GPT model family: one implementation for single-card, tensor-parallel, sequence-parallel and MoE runs.
+
+Capabilities mirrored from the reference (single-card ``gpt/dygraph/single_model.py:56-1419`` and hybrid
+``gpt/dygraph/hybrid_model.py:90-1000``):
+  * pre-LN decoder, fused or split QKV, tanh-GELU FFN, learned absolute positions, tied LM head,
+  * ``scale_qk_by_layer_num`` (scores computed as (q/(L*sqrt(d))) k^T then *L — hybrid_model.py:310-315),
+  * flash attention or unfused ``QK^T -> fused causal softmax -> PV`` core attention,
+  * recompute granularities ``full | full_attn | core_attn`` and ``no_recompute_layers``,
+  * Megatron TP (+ sequence parallel in ``[s, b, h]`` layout) through ``parallel/tp_layers.py``,
+  * KV cache for generation, sequence-classification head, masked-mean pre-training criterion,
+  * optional MoE FFN per layer (``moe_configs``).
+
+State-dict keys keep the reference's structured names, e.g.
+``gpt.decoder.layers.3.self_attn.qkv_proj.weight``; linear weights are stored ``[out, in]`` (torch) instead
+of Paddle's ``[in, out]`` — ``utils/ckpt_convert.py`` transposes when importing genuine Paddle checkpoints.
+The fused-QKV output dimension is laid out ``[heads, 3, head_dim]`` like the reference.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from ....ops import attention as ATT
+from ....ops import functional as OF
+from ....parallel import comm_ops as C
+from ....parallel.recompute import recompute
+from ....parallel.rng import get_rng_state_tracker
+from ....parallel.tp_layers import (ColumnParallelLinear, ColumnSequenceParallelLinear, ParallelCrossEntropy,
+                                    RowParallelLinear, RowSequenceParallelLinear, VocabParallelEmbedding,
+                                    mark_as_sequence_parallel_parameter, parallel_matmul)
+
+
+class LayerNorm(nn.Module):
+    def __init__(self, hidden: int, eps: float = 1e-5, sequence_parallel: bool = False, dtype=None, device=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden, dtype=dtype, device=device))
+        self.bias = nn.Parameter(torch.zeros(hidden, dtype=dtype, device=device))
+        self.eps = eps
+        if sequence_parallel:
+            mark_as_sequence_parallel_parameter(self.weight)
+            mark_as_sequence_parallel_parameter(self.bias)
+
+    def forward(self, x):
+        return OF.layer_norm(x, self.weight, self.bias, self.eps)
+
+
+class KVCache:
+    """Pre-allocated static KV cache: in-place writes, no per-step concat/re-allocation (the reference grows
+    its cache with ``concat`` every token, hybrid_model.py:198-214)."""
+
+    def __init__(self, batch: int, max_len: int, heads: int, head_dim: int, dtype, device):
+        self.k = torch.zeros(batch, max_len, heads, head_dim, dtype=dtype, device=device)
+        self.v = torch.zeros_like(self.k)
+        self.length = 0
+
+    def append(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        n = k.shape[1]
+        self.k[:, self.length:self.length + n] = k
+        self.v[:, self.length:self.length + n] = v
+        self.length += n
+        return self.k[:, :self.length], self.v[:, :self.length]
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, hidden: int, num_heads: int, attn_dropout: float = 0.0, fuse_attn_qkv: bool = True, scale_qk_coeff: float = 1.0,
+                 use_flash_attn: bool = True, fused_softmax_with_triangular: bool = True, sequence_parallel: bool = False,
+                 mp_group=None, init_std: float = 0.02, out_init_std: float = 0.02, recompute_core: bool = False,
+                 fused_tp_comm: bool = False, use_rope: bool = False, dtype=None, device=None):
+        super().__init__()
+        self.hidden, self.num_heads = hidden, num_heads
+        self.head_dim = hidden // num_heads
+        assert self.head_dim * num_heads == hidden
+        self.world = C.group_size(mp_group)
+        assert num_heads % self.world == 0, f"heads {num_heads} % mp {self.world}"
+        self.local_heads = num_heads // self.world
+        self.attn_dropout = attn_dropout
+        self.fuse_attn_qkv = fuse_attn_qkv
+        self.scale_qk_coeff = scale_qk_coeff
+        self.use_flash_attn = use_flash_attn
+        self.fused_softmax_with_triangular = fused_softmax_with_triangular
+        self.sequence_parallel = sequence_parallel
+        self.recompute_core = recompute_core
+        self.use_rope = use_rope
+        kw = dict(mp_group=mp_group, dtype=dtype, device=device)
+        Col = ColumnSequenceParallelLinear if sequence_parallel else ColumnParallelLinear
+        Row = RowSequenceParallelLinear if sequence_parallel else RowParallelLinear
+        ckw = dict(kw, gather_output=False, init_std=init_std)
+        rkw = dict(kw, input_is_parallel=True, init_std=out_init_std, skip_bias_add=True)
+        if sequence_parallel:
+            ckw["fused_comm"] = fused_tp_comm
+            rkw["fused_comm"] = fused_tp_comm
+        if fuse_attn_qkv:
+            self.qkv_proj = Col(hidden, 3 * hidden, **ckw)
+        else:
+            self.q_proj = Col(hidden, hidden, **ckw)
+            self.k_proj = Col(hidden, hidden, **ckw)
+            self.v_proj = Col(hidden, hidden, **ckw)
+        self.out_proj = Row(hidden, hidden, **rkw)
+
+    # -- projections -------------------------------------------------------------------------
+    def _qkv(self, x: torch.Tensor):
+        """returns q, k, v as ``[b, s, local_heads, d]``."""
+        if self.fuse_attn_qkv:
+            mix = self.qkv_proj(x)
+            mix = mix.view(*mix.shape[:-1], self.local_heads, 3, self.head_dim)
+            q, k, v = mix.unbind(-2)
+        else:
+            q, k, v = (p(x).view(*x.shape[:-1] if not self.sequence_parallel else (-1, x.shape[1]), self.local_heads, self.head_dim)
+                       for p in (self.q_proj, self.k_proj, self.v_proj))
+        if self.sequence_parallel:      # [s, b, heads, d] -> [b, s, heads, d]
+            q, k, v = (t.transpose(0, 1) for t in (q, k, v))
+        return q, k, v
+
+    def _core(self, q, k, v, attn_mask):
+        scale = 1.0 / math.sqrt(self.head_dim)
+        p = self.attn_dropout if self.training else 0.0
+        if self.use_flash_attn and attn_mask is None:
+            if p > 0:
+                with get_rng_state_tracker().rng_state("local_seed"):
+                    return ATT.attention(q, k, v, causal=True, dropout_p=p, scale=scale)
+            return ATT.attention(q, k, v, causal=q.shape[1] > 1, dropout_p=0.0, scale=scale)
+        if self.scale_qk_coeff != 1.0:
+            # overflow trick for fp16: scores = (q / (coeff * sqrt(d))) k^T, softmax input multiplied back by coeff
+            q = q / self.scale_qk_coeff
+            scale = scale * self.scale_qk_coeff
+        causal = attn_mask is None and self.fused_softmax_with_triangular
+        if attn_mask is None and not causal:
+            sq, sk = q.shape[1], k.shape[1]
+            attn_mask = torch.full((sq, sk), -1e4, device=q.device, dtype=torch.float32).triu(1 + sk - sq)
+        return ATT.core_attention(q, k, v, scale, p, self.training, attn_mask=attn_mask, causal=causal)
+
+    def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, cache: Optional[KVCache] = None,
+                positions: Optional[torch.Tensor] = None):
+        q, k, v = self._qkv(x)
+        if self.use_rope:
+            pos = positions
+            if pos is None and cache is not None and cache.length > 0:
+                pos = torch.arange(cache.length, cache.length + q.shape[1], device=q.device).expand(q.shape[0], -1)
+            q, k = OF.rope(q.contiguous(), pos), OF.rope(k.contiguous(), pos)
+        if cache is not None:
+            k, v = cache.append(k, v)
+        if self.recompute_core and self.training:
+            out = recompute(self._core, q, k, v, attn_mask)
+        else:
+            out = self._core(q, k, v, attn_mask)
+        out = out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim)
+        if self.sequence_parallel:
+            out = out.transpose(0, 1).contiguous()
+        return self.out_proj(out)          # (y, bias): bias is folded into the following dropout+residual kernel
+
+
+class TransformerDecoderLayer(nn.Module):
+    def __init__(self, hidden: int, num_heads: int, ffn_hidden: int, hidden_dropout: float = 0.1, attn_dropout: float = 0.1,
+                 num_layers: int = 1, sequence_parallel: bool = False, mp_group=None, init_std: float = 0.02,
+                 recompute_attn: bool = False, recompute_core: bool = False, moe_layer: Optional[nn.Module] = None,
+                 fused_tp_comm: bool = False, dtype=None, device=None, **attn_kwargs):
+        super().__init__()
+        out_std = init_std / math.sqrt(2.0 * num_layers)
+        self.sequence_parallel = sequence_parallel
+        self.hidden_dropout = hidden_dropout
+        self.recompute_attn = recompute_attn
+        self.norm1 = LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.self_attn = MultiHeadAttention(hidden, num_heads, attn_dropout, sequence_parallel=sequence_parallel, mp_group=mp_group,
+                                            init_std=init_std, out_init_std=out_std, recompute_core=recompute_core,
+                                            fused_tp_comm=fused_tp_comm, dtype=dtype, device=device, **attn_kwargs)
+        self.norm2 = LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.moe_mlp = moe_layer
+        if moe_layer is None:
+            Col = ColumnSequenceParallelLinear if sequence_parallel else ColumnParallelLinear
+            Row = RowSequenceParallelLinear if sequence_parallel else RowParallelLinear
+            kw = dict(mp_group=mp_group, dtype=dtype, device=device)
+            extra = dict(fused_comm=fused_tp_comm) if sequence_parallel else {}
+            self.linear1 = Col(hidden, ffn_hidden, gather_output=False, init_std=init_std, has_bias=True, **kw, **extra)
+            self.linear2 = Row(ffn_hidden, hidden, input_is_parallel=True, init_std=out_std, skip_bias_add=True, **kw, **extra)
+        # hidden dropout stream: identical inside the TP group without SP, distinct under SP
+        self.rng_name = "local_seed" if sequence_parallel else "global_seed"
+
+    def _attn_block(self, x, attn_mask, cache, positions):
+        y, b = self.self_attn(self.norm1(x), attn_mask, cache, positions)
+        return OF.bias_dropout_add(y, b, x, self.hidden_dropout, self.training, self.rng_name)
+
+    def _ffn(self, h):
+        z = self.linear1(h, skip_bias=True)      # GEMM only; bias rides in the fused bias+GELU kernel
+        return self.linear2(OF.bias_gelu(z, self.linear1.bias))
+
+    def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, cache: Optional[KVCache] = None,
+                positions: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.recompute_attn and self.training and cache is None:
+            x = recompute(self._attn_block, x, attn_mask, None, positions)
+        else:
+            x = self._attn_block(x, attn_mask, cache, positions)
+        h = self.norm2(x)
+        if self.moe_mlp is not None:
+            y = self.moe_mlp(h)
+            return OF.bias_dropout_add(y, None, x, self.hidden_dropout, self.training, self.rng_name)
+        y, b = self._ffn(h)
+        return OF.bias_dropout_add(y, b, x, self.hidden_dropout, self.training, self.rng_name)
+
+
+class TransformerDecoder(nn.Module):
+    def __init__(self, layers: List[nn.Module], hidden: int, use_recompute: bool = False, recompute_granularity: str = "full",
+                 no_recompute_layers: Optional[List[int]] = None, sequence_parallel: bool = False, dtype=None, device=None):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.norm = LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.use_recompute = use_recompute
+        self.recompute_granularity = recompute_granularity
+        self.no_recompute_layers = set(no_recompute_layers or [])
+
+    def forward(self, x, attn_mask=None, caches: Optional[List[KVCache]] = None, positions=None):
+        for i, layer in enumerate(self.layers):
+            cache = caches[i] if caches is not None else None
+            if (self.use_recompute and self.recompute_granularity == "full" and self.training and cache is None
+                    and i not in self.no_recompute_layers):
+                x = recompute(layer, x, attn_mask, None, positions)
+            else:
+                x = layer(x, attn_mask, cache, positions)
+        return self.norm(x)
+
+
+class GPTEmbeddings(nn.Module):
+    def __init__(self, vocab_size: int, hidden: int, max_position: int, hidden_dropout: float, init_std: float, sequence_parallel: bool,
+                 mp_group=None, use_rope: bool = False, dtype=None, device=None):
+        super().__init__()
+        self.word_embeddings = VocabParallelEmbedding(vocab_size, hidden, mp_group, init_std, dtype, device)
+        self.use_rope = use_rope
+        if not use_rope:
+            self.position_embeddings = nn.Embedding(max_position, hidden, dtype=dtype, device=device)
+            with torch.no_grad():
+                self.position_embeddings.weight.normal_(0.0, init_std)
+        self.hidden_dropout = hidden_dropout
+        self.sequence_parallel = sequence_parallel
+        self.group = mp_group
+
+    def forward(self, input_ids: torch.Tensor, position_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self.word_embeddings(input_ids)
+        if not self.use_rope:
+            if position_ids is None:
+                position_ids = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0).expand_as(input_ids)
+            x = x + self.position_embeddings(position_ids)
+        if self.sequence_parallel:
+            x = C.scatter_seq(x.transpose(0, 1).contiguous(), self.group)     # [s/n, b, h]
+            return OF.dropout(x, self.hidden_dropout, self.training, "local_seed")
+        return OF.dropout(x, self.hidden_dropout, self.training, "global_seed")
+
+
+class GPTModel(nn.Module):
+    def __init__(self, vocab_size: int = 50304, hidden_size: int = 768, num_layers: int = 12, num_attention_heads: int = 12,
+                 ffn_hidden_size: Optional[int] = None, hidden_dropout_prob: float = 0.1, attention_probs_dropout_prob: float = 0.1,
+                 max_position_embeddings: int = 1024, type_vocab_size: int = 16, initializer_range: float = 0.02,
+                 use_recompute: bool = False, recompute_granularity: Optional[str] = "full", no_recompute_layers=None,
+                 fused_linear: bool = False, fuse_attn_qkv: bool = True, scale_qk_by_layer_num: bool = True,
+                 sequence_parallel: bool = False, use_flash_attn: bool = True, fused_softmax_with_triangular: bool = True,
+                 mp_group=None, moe_configs: Optional[dict] = None, fused_tp_comm: bool = False, use_rope: bool = False,
+                 dtype=None, device=None, **unused):
+        super().__init__()
+        ffn_hidden_size = ffn_hidden_size or 4 * hidden_size
+        recompute_granularity = recompute_granularity or "full"
+        self.hidden_size, self.vocab_size, self.num_layers = hidden_size, vocab_size, num_layers
+        self.initializer_range = initializer_range
+        self.mp_group = mp_group
+        self.sequence_parallel = sequence_parallel and C.group_size(mp_group) > 1
+        sp = self.sequence_parallel
+        self.embeddings = GPTEmbeddings(vocab_size, hidden_size, max_position_embeddings, hidden_dropout_prob, initializer_range,
+                                        sp, mp_group, use_rope, dtype, device)
+        layers = []
+        for i in range(num_layers):
+            moe = None
+            if moe_configs and moe_configs.get("expert_mode", False):
+                from ..moe.moe_layer import build_moe_layer
+
+                moe = build_moe_layer(hidden_size, ffn_hidden_size, moe_configs, num_layers, initializer_range, mp_group, dtype, device, i)
+            layers.append(TransformerDecoderLayer(
+                hidden_size, num_attention_heads, ffn_hidden_size, hidden_dropout_prob, attention_probs_dropout_prob, num_layers,
+                sequence_parallel=sp, mp_group=mp_group, init_std=initializer_range,
+                recompute_attn=use_recompute and recompute_granularity == "full_attn",
+                recompute_core=use_recompute and recompute_granularity == "core_attn", moe_layer=moe, fused_tp_comm=fused_tp_comm,
+                dtype=dtype, device=device, fuse_attn_qkv=fuse_attn_qkv,
+                scale_qk_coeff=float(num_layers) if scale_qk_by_layer_num else 1.0, use_flash_attn=use_flash_attn,
+                fused_softmax_with_triangular=fused_softmax_with_triangular, use_rope=use_rope))
+        self.decoder = TransformerDecoder(layers, hidden_size, use_recompute, recompute_granularity, no_recompute_layers, sp, dtype, device)
+
+    def new_caches(self, batch: int, max_len: int) -> List[KVCache]:
+        p = self.decoder.norm.weight
+        lh, hd = self.decoder.layers[0].self_attn.local_heads, self.decoder.layers[0].self_attn.head_dim
+        return [KVCache(batch, max_len, lh, hd, p.dtype, p.device) for _ in self.decoder.layers]
+
+    def forward(self, input_ids, position_ids=None, attention_mask=None, caches: Optional[List[KVCache]] = None):
+        if position_ids is None and caches is not None and caches[0].length > 0:
+            past = caches[0].length
+            position_ids = torch.arange(past, past + input_ids.shape[1], device=input_ids.device).unsqueeze(0).expand_as(input_ids)
+        x = self.embeddings(input_ids, position_ids)
+        x = self.decoder(x, attention_mask, caches, position_ids)
+        if self.sequence_parallel:
+            x = C.gather_seq(x, self.mp_group).transpose(0, 1).contiguous()      # back to [b, s, h]
+        return x
+
+
+GPTModelHybrid = GPTModel
+
+
+class GPTForPretraining(nn.Module):
+    """LM head tied to the (vocab-parallel) word embedding."""
+
+    def __init__(self, gpt: GPTModel, parallel_output: bool = True):
+        super().__init__()
+        self.gpt = gpt
+        self.parallel_output = parallel_output
+
+    def forward(self, input_ids, position_ids=None, attention_mask=None, caches=None):
+        h = self.gpt(input_ids, position_ids, attention_mask, caches)
+        return parallel_matmul(h, self.gpt.embeddings.word_embeddings.weight, self.gpt.mp_group, self.parallel_output)
+
+
+GPTForPretrainingHybrid = GPTForPretraining
+
+
+class GPTPretrainingCriterion(nn.Module):
+    """loss = sum(CE * mask) / sum(mask) (reference hybrid_model.py:955-996)."""
+
+    def __init__(self, mp_group=None):
+        super().__init__()
+        self.ce = ParallelCrossEntropy(mp_group)
+
+    def forward(self, logits: torch.Tensor, labels: torch.Tensor, loss_mask: torch.Tensor) -> torch.Tensor:
+        per_tok = self.ce(logits, labels)
+        mask = loss_mask.reshape(-1).float()
+        return (per_tok.reshape(-1) * mask).sum() / mask.sum()
+
+
+GPTPretrainingCriterionHybird = GPTPretrainingCriterion  # (sic) name used by the reference module layer
+
+
+class GPTForSequenceClassification(nn.Module):
+    """Pooled logit = hidden state of the last non-pad token -> ``score`` (reference single_model.py:856-895)."""
+
+    def __init__(self, gpt: GPTModel, num_classes: int = 2, pad_token_id: int = 0):
+        super().__init__()
+        self.gpt = gpt
+        p = gpt.decoder.norm.weight
+        self.score = nn.Linear(gpt.hidden_size, num_classes, bias=False, dtype=p.dtype, device=p.device)
+        with torch.no_grad():
+            self.score.weight.normal_(0.0, gpt.initializer_range)
+        self.pad_token_id = pad_token_id
+
+    def forward(self, input_ids, position_ids=None, attention_mask=None):
+        h = self.gpt(input_ids, position_ids, attention_mask)
+        logits = self.score(h)
+        eos = (input_ids != self.pad_token_id).to(torch.int64).sum(-1) - 1
+        return logits[torch.arange(input_ids.shape[0], device=input_ids.device), eos.clamp_min(0)]
+
+
+def vocab_size_with_padding(vocab_size: int, div_unit: int, mp_degree: int) -> int:
+    """Pad the vocabulary to a multiple of ``div_unit * mp`` (reference language_module.py:62-70)."""
+    mult = div_unit * mp_degree
+    return ((vocab_size + mult - 1) // mult) * mult

@@ -1,0 +1,358 @@
+// pybind11 / torch glue for the sm_100a kernel library.  All kernels run on the current CUDA stream.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <string>
+#include <vector>
+
+#include "pfx_gemm.h"
+#include "pfx_kernels.h"
+
+namespace {
+
+inline int dtype_code(const at::Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kHalf: return 0;
+    case at::kBFloat16: return 1;
+    case at::kFloat: return 3;
+    default: TORCH_CHECK(false, "pfx: unsupported dtype ", t.scalar_type());
+  }
+}
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline int num_sms() {
+  static int n = 0;
+  if (!n) n = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  return n;
+}
+#define PFX_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    TORCH_CHECK(_e == cudaSuccess, "pfx CUDA error: ", cudaGetErrorString(_e), " at ", #expr); \
+  } while (0)
+#define PFX_CHECK_CUDA_CONTIG(t) TORCH_CHECK((t).is_cuda() && (t).is_contiguous(), #t " must be a contiguous CUDA tensor")
+
+// ------------------------------------------------------------------------------- GEMM
+// d[M,N] (+)= op(a) * op(b)^T.  a: [M,K] if a_kmajor else [K,M]; b: [N,K] if b_kmajor else [K,N].
+at::Tensor gemm(const at::Tensor& a, const at::Tensor& b, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> out, bool a_kmajor,
+                bool b_kmajor, int64_t epilogue, int64_t out_mode, int64_t config) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2, "gemm: 2-D CUDA tensors expected");
+  TORCH_CHECK(a.scalar_type() == b.scalar_type() && (a.scalar_type() == at::kBFloat16 || a.scalar_type() == at::kHalf),
+              "gemm: bf16/fp16 operands expected");
+  TORCH_CHECK(a.stride(1) == 1 && b.stride(1) == 1, "gemm: innermost dim must be contiguous");
+  const c10::cuda::CUDAGuard guard(a.device());
+  const int64_t M = a_kmajor ? a.size(0) : a.size(1);
+  const int64_t K = a_kmajor ? a.size(1) : a.size(0);
+  const int64_t N = b_kmajor ? b.size(0) : b.size(1);
+  const int64_t Kb = b_kmajor ? b.size(1) : b.size(0);
+  TORCH_CHECK(K == Kb, "gemm: K mismatch ", K, " vs ", Kb);
+  TORCH_CHECK(a.stride(0) % 8 == 0 && b.stride(0) % 8 == 0, "gemm: row strides must be multiples of 8 elements (16 B)");
+  TORCH_CHECK((reinterpret_cast<uintptr_t>(a.data_ptr()) % 16) == 0 && (reinterpret_cast<uintptr_t>(b.data_ptr()) % 16) == 0,
+              "gemm: operands must be 16-byte aligned");
+  at::Tensor d;
+  if (out.has_value()) {
+    d = *out;
+    TORCH_CHECK(d.is_cuda() && d.dim() == 2 && d.size(0) == M && d.size(1) == N && d.stride(1) == 1, "gemm: bad out tensor");
+  } else {
+    TORCH_CHECK(out_mode != 2, "gemm: accumulate mode needs an out tensor");
+    d = at::empty({M, N}, a.options().dtype(out_mode == 0 ? a.scalar_type() : at::kFloat));
+  }
+  if (out_mode == 0) {
+    TORCH_CHECK(d.scalar_type() == a.scalar_type() && N % 8 == 0 && d.stride(0) % 8 == 0, "gemm: bf16 out needs N % 8 == 0");
+  } else {
+    TORCH_CHECK(d.scalar_type() == at::kFloat && N % 4 == 0 && d.stride(0) % 4 == 0, "gemm: fp32 out needs N % 4 == 0");
+  }
+  pfx::GemmArgs g{};
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr();
+  g.bias = nullptr;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N && bias->is_contiguous(), "gemm: bias must be bf16 [N]");
+    TORCH_CHECK(N % 8 == 0, "gemm: bias epilogue needs N % 8 == 0");
+    g.bias = bias->data_ptr();
+  } else {
+    TORCH_CHECK(epilogue == pfx::EPI_NONE || epilogue == pfx::EPI_GELU, "gemm: bias epilogue without bias");
+  }
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.lda = (int)a.stride(0); g.ldb = (int)b.stride(0); g.ldd = (int)d.stride(0);
+  g.a_kmajor = a_kmajor; g.b_kmajor = b_kmajor;
+  g.out_mode = (int)out_mode; g.epilogue = (int)epilogue;
+  g.ab_format = a.scalar_type() == at::kBFloat16 ? 1 : 0;
+  g.num_sms = num_sms(); g.config = (int)config;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+  return d;
+}
+
+// ------------------------------------------------------------------------------- norms
+std::vector<at::Tensor> norm_fwd(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> b, double eps, bool rms) {
+  PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(w);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t cols = x.size(-1), rows = x.numel() / cols;
+  auto y = at::empty_like(x);
+  auto fopt = x.options().dtype(at::kFloat);
+  auto mean = rms ? at::empty({0}, fopt) : at::empty({rows}, fopt);
+  auto rstd = at::empty({rows}, fopt);
+  PFX_CUDA_CHECK(pfx::norm_fwd(x.data_ptr(), w.data_ptr(), (b.has_value() && b->defined()) ? b->data_ptr() : nullptr, y.data_ptr(),
+                               rms ? nullptr : mean.data_ptr<float>(), rstd.data_ptr<float>(), (int)rows, (int)cols, (float)eps,
+                               dtype_code(x), rms, cur_stream()));
+  return {y, mean, rstd};
+}
+
+std::vector<at::Tensor> norm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& mean,
+                                 const at::Tensor& rstd, bool rms, bool has_bias) {
+  PFX_CHECK_CUDA_CONTIG(dy); PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t cols = x.size(-1), rows = x.numel() / cols;
+  auto dx = at::empty_like(x);
+  auto dw = at::empty_like(w);
+  auto db = (has_bias && !rms) ? at::empty_like(w) : at::empty({0}, w.options());
+  const int parts = pfx::norm_bwd_num_parts((int)rows, num_sms());
+  auto ws = at::empty({2 * (int64_t)parts * cols}, x.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::norm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rms ? nullptr : mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                               dx.data_ptr(), dw.data_ptr(), (has_bias && !rms) ? db.data_ptr() : nullptr, ws.data_ptr<float>(), (int)rows,
+                               (int)cols, dtype_code(x), rms, num_sms(), cur_stream()));
+  return {dx, dw, db};
+}
+
+// ------------------------------------------------------------------------------- activations / dropout
+at::Tensor bias_gelu_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty_like(x);
+  const int64_t cols = x.size(-1);
+  PFX_CUDA_CHECK(pfx::bias_gelu(x.data_ptr(), (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr, nullptr, y.data_ptr(),
+                                x.numel() / cols, (int)cols, dtype_code(x), false, num_sms(), cur_stream()));
+  return y;
+}
+at::Tensor bias_gelu_bwd(const at::Tensor& dy, const at::Tensor& x, c10::optional<at::Tensor> bias) {
+  PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(dy);
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto dx = at::empty_like(x);
+  const int64_t cols = x.size(-1);
+  PFX_CUDA_CHECK(pfx::bias_gelu(x.data_ptr(), (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr, dy.data_ptr(),
+                                dx.data_ptr(), x.numel() / cols, (int)cols, dtype_code(x), true, num_sms(), cur_stream()));
+  return dx;
+}
+at::Tensor bias_dropout_add_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> residual, double p,
+                                int64_t seed, int64_t offset) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto y = at::empty_like(x);
+  const int64_t cols = x.size(-1);
+  if (residual.has_value() && residual->defined()) PFX_CHECK_CUDA_CONTIG(*residual);
+  PFX_CUDA_CHECK(pfx::bias_dropout_add(x.data_ptr(), (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr,
+                                       (residual.has_value() && residual->defined()) ? residual->data_ptr() : nullptr, y.data_ptr(),
+                                       x.numel() / cols, (int)cols, (float)p, (uint64_t)seed, (uint64_t)offset, dtype_code(x), false,
+                                       num_sms(), cur_stream()));
+  return y;
+}
+at::Tensor dropout_bwd(const at::Tensor& dy, double p, int64_t seed, int64_t offset) {
+  PFX_CHECK_CUDA_CONTIG(dy);
+  const c10::cuda::CUDAGuard guard(dy.device());
+  auto dx = at::empty_like(dy);
+  const int64_t cols = dy.size(-1);
+  PFX_CUDA_CHECK(pfx::bias_dropout_add(dy.data_ptr(), nullptr, nullptr, dx.data_ptr(), dy.numel() / cols, (int)cols, (float)p,
+                                       (uint64_t)seed, (uint64_t)offset, dtype_code(dy), true, num_sms(), cur_stream()));
+  return dx;
+}
+at::Tensor colsum(const at::Tensor& x, bool out_fp32) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t cols = x.size(-1), rows = x.numel() / cols;
+  auto out = at::empty({cols}, x.options().dtype(out_fp32 ? at::kFloat : x.scalar_type()));
+  auto ws = at::empty({(int64_t)pfx::colsum_num_parts((int)rows) * cols}, x.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::colsum(x.data_ptr(), out.data_ptr(), ws.data_ptr<float>(), (int)rows, (int)cols, dtype_code(x), out_fp32, cur_stream()));
+  return out;
+}
+
+// ------------------------------------------------------------------------------- loss
+std::vector<at::Tensor> ce_stats(const at::Tensor& logits, const at::Tensor& labels, int64_t vocab_start) {
+  PFX_CHECK_CUDA_CONTIG(logits); PFX_CHECK_CUDA_CONTIG(labels);
+  TORCH_CHECK(labels.scalar_type() == at::kLong, "labels must be int64");
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t cols = logits.size(-1), rows = logits.numel() / cols;
+  auto fopt = logits.options().dtype(at::kFloat);
+  auto mx = at::empty({rows}, fopt), sm = at::empty({rows}, fopt), tg = at::empty({rows}, fopt);
+  PFX_CUDA_CHECK(pfx::ce_stats(logits.data_ptr(), labels.data_ptr<int64_t>(), mx.data_ptr<float>(), sm.data_ptr<float>(),
+                               tg.data_ptr<float>(), (int)rows, (int)cols, vocab_start, dtype_code(logits), cur_stream()));
+  return {mx, sm, tg};
+}
+void ce_bwd_(at::Tensor& logits, const at::Tensor& labels, const at::Tensor& lse, const at::Tensor& gscale, int64_t vocab_start) {
+  PFX_CHECK_CUDA_CONTIG(logits);
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int64_t cols = logits.size(-1), rows = logits.numel() / cols;
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && gscale.scalar_type() == at::kFloat && lse.numel() == rows && gscale.numel() == rows);
+  PFX_CUDA_CHECK(pfx::ce_bwd(logits.data_ptr(), labels.data_ptr<int64_t>(), lse.data_ptr<float>(), gscale.data_ptr<float>(), (int)rows,
+                             (int)cols, vocab_start, dtype_code(logits), cur_stream()));
+}
+
+// ------------------------------------------------------------------------------- optimizer
+void sumsq_(const at::Tensor& x, at::Tensor& out, bool accumulate) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto ws = at::empty({1024}, x.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::sumsq(x.data_ptr(), (size_t)x.numel(), out.data_ptr<float>(), ws.data_ptr<float>(), dtype_code(x), accumulate,
+                            num_sms(), cur_stream()));
+}
+void clip_coef_(const at::Tensor& sq, double inv_loss_scale, double clip_norm, at::Tensor& gscale, at::Tensor& found_inf, at::Tensor& gnorm) {
+  const c10::cuda::CUDAGuard guard(sq.device());
+  PFX_CUDA_CHECK(pfx::clip_coef(sq.data_ptr<float>(), (float)inv_loss_scale, (float)clip_norm, gscale.data_ptr<float>(),
+                                found_inf.data_ptr<float>(), gnorm.data_ptr<float>(), cur_stream()));
+}
+void adamw_flat_(c10::optional<at::Tensor> p_lp, at::Tensor& master, const at::Tensor& grad, at::Tensor& m, at::Tensor& v, double lr,
+                 double beta1, double beta2, double eps, double wd, int64_t step, c10::optional<at::Tensor> gscale,
+                 c10::optional<at::Tensor> found_inf) {
+  PFX_CHECK_CUDA_CONTIG(master); PFX_CHECK_CUDA_CONTIG(grad);
+  const c10::cuda::CUDAGuard guard(master.device());
+  const size_t n = master.numel();
+  TORCH_CHECK((size_t)grad.numel() == n && (size_t)m.numel() == n && (size_t)v.numel() == n, "adamw: size mismatch");
+  const float bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  const bool has_lp = p_lp.has_value() && p_lp->defined();
+  PFX_CUDA_CHECK(pfx::adamw_flat(has_lp ? p_lp->data_ptr() : nullptr, master.data_ptr<float>(), grad.data_ptr(), m.data_ptr<float>(),
+                                 v.data_ptr<float>(), n, (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, bc1, bc2,
+                                 (gscale.has_value() && gscale->defined()) ? gscale->data_ptr<float>() : nullptr,
+                                 (found_inf.has_value() && found_inf->defined()) ? found_inf->data_ptr<float>() : nullptr,
+                                 dtype_code(grad), has_lp ? dtype_code(*p_lp) : 3, num_sms(), cur_stream()));
+}
+void accumulate_f32_(at::Tensor& dst, const at::Tensor& src, double scale) {
+  const c10::cuda::CUDAGuard guard(dst.device());
+  TORCH_CHECK(dst.scalar_type() == at::kFloat && dst.numel() == src.numel() && dst.is_contiguous() && src.is_contiguous());
+  PFX_CUDA_CHECK(pfx::accumulate_f32(dst.data_ptr<float>(), src.data_ptr(), (size_t)src.numel(), (float)scale, dtype_code(src), num_sms(),
+                                     cur_stream()));
+}
+
+// ------------------------------------------------------------------------------- sampling / rope / softmax
+std::vector<at::Tensor> topp_sampling(const at::Tensor& probs, const at::Tensor& top_ps, int64_t seed, int64_t offset) {
+  PFX_CHECK_CUDA_CONTIG(probs);
+  const c10::cuda::CUDAGuard guard(probs.device());
+  const int64_t V = probs.size(-1), rows = probs.numel() / V;
+  auto tp = top_ps.to(at::kFloat).contiguous();
+  TORCH_CHECK(tp.numel() == rows, "top_ps must have one entry per row");
+  auto out_p = at::empty({rows, 1}, probs.options().dtype(at::kFloat));
+  auto out_i = at::empty({rows, 1}, probs.options().dtype(at::kLong));
+  PFX_CUDA_CHECK(pfx::topp_sampling(probs.data_ptr(), tp.data_ptr<float>(), out_p.data_ptr<float>(), out_i.data_ptr<int64_t>(), (int)rows,
+                                    (int)V, (uint64_t)seed, (uint64_t)offset, dtype_code(probs), cur_stream()));
+  return {out_p.to(probs.scalar_type()), out_i};
+}
+at::Tensor rope(const at::Tensor& x, c10::optional<at::Tensor> positions, int64_t seq_len, double base, bool bwd) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  TORCH_CHECK(x.dim() >= 3, "rope: [..., heads, d]");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t d = x.size(-1), heads = x.size(-2), tokens = x.numel() / (d * heads);
+  auto y = at::empty_like(x);
+  const int64_t* pos = nullptr;
+  at::Tensor pc;
+  if (positions.has_value() && positions->defined()) { pc = positions->to(at::kLong).contiguous(); pos = pc.data_ptr<int64_t>(); }
+  PFX_CUDA_CHECK(pfx::rope(x.data_ptr(), y.data_ptr(), pos, (size_t)tokens, (int)heads, (int)d, (int)seq_len, (float)base, bwd,
+                           dtype_code(x), num_sms(), cur_stream()));
+  return y;
+}
+at::Tensor causal_softmax_fwd(const at::Tensor& x, double scale) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t sk = x.size(-1), sq = x.size(-2), batch = x.numel() / (sk * sq);
+  auto y = at::empty_like(x);
+  PFX_CUDA_CHECK(pfx::causal_softmax(x.data_ptr(), nullptr, y.data_ptr(), (size_t)batch, (int)sq, (int)sk, (float)scale, false,
+                                     dtype_code(x), cur_stream()));
+  return y;
+}
+at::Tensor causal_softmax_bwd(const at::Tensor& dy, const at::Tensor& y, double scale) {
+  PFX_CHECK_CUDA_CONTIG(dy); PFX_CHECK_CUDA_CONTIG(y);
+  const c10::cuda::CUDAGuard guard(y.device());
+  const int64_t sk = y.size(-1), sq = y.size(-2), batch = y.numel() / (sk * sq);
+  auto dx = at::empty_like(y);
+  PFX_CUDA_CHECK(pfx::causal_softmax(dy.data_ptr(), y.data_ptr(), dx.data_ptr(), (size_t)batch, (int)sq, (int)sk, (float)scale, true,
+                                     dtype_code(y), cur_stream()));
+  return dx;
+}
+
+// ------------------------------------------------------------------------------- symmetric memory (CUDA IPC)
+// Buffers are raw cudaMalloc allocations (the caching allocator's blocks cannot be IPC-exported piecewise).
+py::tuple ipc_alloc(int64_t nbytes) {
+  void* p = nullptr;
+  PFX_CUDA_CHECK(cudaMalloc(&p, (size_t)nbytes));
+  PFX_CUDA_CHECK(cudaMemset(p, 0, (size_t)nbytes));
+  cudaIpcMemHandle_t h;
+  PFX_CUDA_CHECK(cudaIpcGetMemHandle(&h, p));
+  return py::make_tuple((int64_t) reinterpret_cast<uintptr_t>(p), py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)));
+}
+int64_t ipc_open(const std::string& handle) {
+  TORCH_CHECK(handle.size() == sizeof(cudaIpcMemHandle_t), "bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle.data(), sizeof(h));
+  void* p = nullptr;
+  PFX_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return (int64_t) reinterpret_cast<uintptr_t>(p);
+}
+void ipc_close(int64_t ptr) { cudaIpcCloseMemHandle(reinterpret_cast<void*>((uintptr_t)ptr)); }
+void ipc_free(int64_t ptr) { cudaFree(reinterpret_cast<void*>((uintptr_t)ptr)); }
+at::Tensor tensor_from_ptr(int64_t ptr, std::vector<int64_t> sizes, at::ScalarType dtype, int64_t device) {
+  auto opts = at::TensorOptions().dtype(dtype).device(at::kCUDA, (c10::DeviceIndex)device);
+  return at::from_blob(reinterpret_cast<void*>((uintptr_t)ptr), sizes, [](void*) {}, opts);
+}
+
+static std::vector<void*> to_ptrs(const std::vector<int64_t>& v) {
+  std::vector<void*> out;
+  for (auto x : v) out.push_back(reinterpret_cast<void*>((uintptr_t)x));
+  return out;
+}
+void p2p_barrier(const std::vector<int64_t>& pads, int64_t rank, int64_t slot) {
+  auto pp = to_ptrs(pads);
+  PFX_CUDA_CHECK(pfx::p2p_barrier(reinterpret_cast<uint32_t**>(pp.data()), (int)rank, (int)pads.size(), (uint32_t)slot, cur_stream()));
+}
+void p2p_reduce_scatter(const std::vector<int64_t>& peer_bufs, at::Tensor& out, int64_t rank, int64_t in_dtype, bool accumulate,
+                        double scale, int64_t num_ctas) {
+  auto pp = to_ptrs(peer_bufs);
+  PFX_CUDA_CHECK(pfx::p2p_reduce_scatter(pp.data(), out.data_ptr(), (size_t)out.numel(), (int)rank, (int)peer_bufs.size(), (int)in_dtype,
+                                         dtype_code(out), accumulate, (float)scale, (int)num_ctas, cur_stream()));
+}
+void p2p_all_gather(const std::vector<int64_t>& peer_bufs, const at::Tensor& src, int64_t rank, int64_t num_ctas) {
+  auto pp = to_ptrs(peer_bufs);
+  PFX_CUDA_CHECK(pfx::p2p_all_gather(pp.data(), src.data_ptr(), (size_t)src.numel(), (int)rank, (int)peer_bufs.size(), dtype_code(src),
+                                     (int)num_ctas, cur_stream()));
+}
+void adamw_p2p_broadcast_(const std::vector<int64_t>& peer_param_bufs, int64_t shard_offset, at::Tensor& master, const at::Tensor& grad,
+                          at::Tensor& m, at::Tensor& v, double lr, double beta1, double beta2, double eps, double wd, int64_t step,
+                          c10::optional<at::Tensor> gscale, c10::optional<at::Tensor> found_inf, int64_t lp_dtype, int64_t num_ctas) {
+  auto pp = to_ptrs(peer_param_bufs);
+  const float bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  PFX_CUDA_CHECK(pfx::adamw_p2p_broadcast(pp.data(), (size_t)shard_offset, master.data_ptr<float>(), grad.data_ptr(), m.data_ptr<float>(),
+                                          v.data_ptr<float>(), (size_t)master.numel(), (float)lr, (float)beta1, (float)beta2, (float)eps,
+                                          (float)wd, bc1, bc2,
+                                          (gscale.has_value() && gscale->defined()) ? gscale->data_ptr<float>() : nullptr,
+                                          (found_inf.has_value() && found_inf->defined()) ? found_inf->data_ptr<float>() : nullptr,
+                                          dtype_code(grad), (int)lp_dtype, (int)peer_param_bufs.size(), (int)num_ctas, cur_stream()));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "paddlefleetx_b200 sm_100a kernel library";
+  m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("out") = py::none(), py::arg("a_kmajor") = true,
+        py::arg("b_kmajor") = true, py::arg("epilogue") = 0, py::arg("out_mode") = 0, py::arg("config") = 0);
+  m.def("norm_fwd", &norm_fwd);
+  m.def("norm_bwd", &norm_bwd);
+  m.def("bias_gelu_fwd", &bias_gelu_fwd);
+  m.def("bias_gelu_bwd", &bias_gelu_bwd);
+  m.def("bias_dropout_add_fwd", &bias_dropout_add_fwd);
+  m.def("dropout_bwd", &dropout_bwd);
+  m.def("colsum", &colsum);
+  m.def("ce_stats", &ce_stats);
+  m.def("ce_bwd_", &ce_bwd_);
+  m.def("sumsq_", &sumsq_);
+  m.def("clip_coef_", &clip_coef_);
+  m.def("adamw_flat_", &adamw_flat_);
+  m.def("accumulate_f32_", &accumulate_f32_);
+  m.def("topp_sampling", &topp_sampling);
+  m.def("rope", &rope);
+  m.def("causal_softmax_fwd", &causal_softmax_fwd);
+  m.def("causal_softmax_bwd", &causal_softmax_bwd);
+  m.def("ipc_alloc", &ipc_alloc);
+  m.def("ipc_open", &ipc_open);
+  m.def("ipc_close", &ipc_close);
+  m.def("ipc_free", &ipc_free);
+  m.def("tensor_from_ptr", &tensor_from_ptr);
+  m.def("p2p_barrier", &p2p_barrier);
+  m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
+  m.def("p2p_all_gather", &p2p_all_gather);
+  m.def("adamw_p2p_broadcast_", &adamw_p2p_broadcast_);
+}

@@ -1,0 +1,400 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] (+)= A[M,K] * B[N,K]^T  (+ bias[N]) (-> GELU)
+//
+//   * operands bf16 (or fp16), fp32 accumulation in TMEM, output bf16 (TMA store) or fp32 (direct,
+//     optionally accumulating into the destination = fused main-grad accumulation for wgrad).
+//   * A and B may each be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]) so the
+//     forward (X W^T), dgrad (dY W) and wgrad (dY^T X) GEMMs of a Linear layer all run without a
+//     transpose pass.
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (single elected thread), warp2 = TMEM
+//     allocator, warps4-7 = epilogue (TMEM -> regs -> swizzled smem -> TMA store).
+//   * kCG = 2 pairs two CTAs (cta_group::2): UMMA 256 x BLOCK_N x 16, each CTA stages half of B.
+//   * TMEM holds two accumulator buffers so the epilogue of tile i overlaps the mainloop of i+1.
+//
+// This is the kernel every Linear layer of the framework runs on (reference call sites L1-L5 in
+// QKV / out-proj / FFN1 / FFN2 / LM head use cuBLAS(Lt) in the reference).
+#include "pfx_ptx.cuh"
+#include "pfx_gemm.h"
+#include <cudaTypedefs.h>
+
+namespace pfx {
+
+constexpr int kBlockM = 128;   // rows of A per CTA
+constexpr int kBlockK = 64;    // 64 x 2 B = one 128-byte swizzle span
+constexpr int kUmmaK = 16;
+constexpr int kNumEpiWarps = 4;
+constexpr int kNumThreads = 256;
+constexpr int kGroupM = 16;    // tile-raster group height (L2 reuse)
+constexpr int kStoreCols = 64; // columns per TMA-store box (128 B of bf16)
+
+template <int kCG, int kBlockN>
+struct GemmSmem {
+  static constexpr int kLoadN = kBlockN / kCG;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = kLoadN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiBytes = kBlockM * kStoreCols * 2;   // one store box
+  static constexpr int kNumEpiBufs = 2;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes - kNumEpiBufs * kEpiBytes;
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kTotal = 1024 + kStages * kStageBytes + kNumEpiBufs * kEpiBytes + kBarrierBytes;
+};
+
+struct TileCoord { int m_blk, n_blk; };
+
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks) {
+  const int tiles_per_group = kGroupM * num_n_blocks;
+  const int group = tile / tiles_per_group;
+  const int first_m = group * kGroupM;
+  const int group_m = min(kGroupM, num_m_blocks - first_m);
+  const int in_group = tile - group * tiles_per_group;
+  return {first_m + in_group % group_m, in_group / group_m};
+}
+
+// kOutMode: 0 = bf16/fp16 via TMA store, 1 = fp32 direct store, 2 = fp32 direct accumulate (D += acc)
+template <int kCG, int kBlockN, bool kAK, bool kBK, int kOutMode>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_d, float* __restrict__ out_f32, const __nv_bfloat16* __restrict__ bias,
+                    int M, int N, int K, int ldd, int epilogue, uint32_t ab_format) {
+  using S = GemmSmem<kCG, kBlockN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kLoadN = S::kLoadN;
+  constexpr int kUmmaM = kBlockM * kCG;
+  constexpr int kTmemCols = 2 * kBlockN;
+  static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM columns must be a power of two");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_ab = smem_base;
+  const uint32_t smem_epi = smem_base + kStages * S::kStageBytes;
+  const uint32_t smem_bar = smem_epi + S::kNumEpiBufs * S::kEpiBytes;
+  auto full_bar = [&](int s) { return smem_bar + 8u * s; };
+  auto empty_bar = [&](int s) { return smem_bar + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return smem_bar + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return smem_bar + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = smem_bar + 8u * (2 * kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+
+  const int num_m_blocks = (M + kUmmaM - 1) / kUmmaM;
+  const int num_n_blocks = (N + kBlockN - 1) / kBlockN;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int num_clusters = gridDim.x / kCG;
+  const int cluster_id = blockIdx.x / kCG;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    if (kOutMode == 0) tma_prefetch_desc(&tmap_d);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kNumEpiWarps * kCG); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kCG>(tmem_slot, kTmemCols);
+    tmem_relinquish<kCG>();
+  }
+  tcgen05_fence_before();
+  if (kCG == 2) cluster_sync(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks);
+        const int m_idx = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
+        const int n_idx = tc.n_blk * kBlockN + (int)cta_rank * kLoadN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_ab + stage * S::kStageBytes;
+          const uint32_t sb = sa + S::kABytes;
+          const uint32_t fb = full_bar(stage);
+          const int k_idx = kb * kBlockK;
+          if (kCG == 1 || is_leader) mbar_arrive_expect_tx(fb, S::kStageBytes * kCG);
+          if constexpr (kAK) {
+            if (kCG == 2) tma_load_2d_2sm(&tmap_a, fb, sa, k_idx, m_idx); else tma_load_2d(&tmap_a, fb, sa, k_idx, m_idx);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kBlockM / 64; ++j) {
+              if (kCG == 2) tma_load_2d_2sm(&tmap_a, fb, sa + j * 8192, m_idx + j * 64, k_idx);
+              else tma_load_2d(&tmap_a, fb, sa + j * 8192, m_idx + j * 64, k_idx);
+            }
+          }
+          if constexpr (kBK) {
+            if (kCG == 2) tma_load_2d_2sm(&tmap_b, fb, sb, k_idx, n_idx); else tma_load_2d(&tmap_b, fb, sb, k_idx, n_idx);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kLoadN / 64; ++j) {
+              if (kCG == 2) tma_load_2d_2sm(&tmap_b, fb, sb + j * 8192, n_idx + j * 64, k_idx);
+              else tma_load_2d(&tmap_b, fb, sb + j * 8192, n_idx + j * 64, k_idx);
+            }
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (is_leader && elect_one()) {
+      const uint32_t idesc = umma_idesc(/*c=f32*/ 1, ab_format, ab_format, !kAK, !kBK, kUmmaM, kBlockN);
+      // K-major SW128: 8-row groups 1024 B apart.  MN-major SW128: 8-k groups 1024 B apart, 64-element
+      // MN chunks (one TMA box of 64 k-rows x 128 B) 8192 B apart.
+      constexpr uint64_t kDescA = kAK ? umma_desc_hi_lo(16, 1024) : umma_desc_hi_lo(8192, 1024);
+      constexpr uint64_t kDescB = kBK ? umma_desc_hi_lo(16, 1024) : umma_desc_hi_lo(8192, 1024);
+      constexpr uint32_t kAdvA = kAK ? (kUmmaK * 2) : (kUmmaK * 128);   // bytes per UMMA_K step
+      constexpr uint32_t kAdvB = kBK ? (kUmmaK * 2) : (kUmmaK * 128);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_ab + stage * S::kStageBytes;
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = umma_desc(sa + k * kAdvA, kDescA);
+            const uint64_t db = umma_desc(sb + k * kAdvB, kDescB);
+            umma_f16<kCG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<kCG>(empty_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit<kCG>(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    const uint32_t q = warp & 3u;                 // TMEM lane quarter this warp may access
+    const uint32_t row_in_cta = q * 32 + lane;
+    const bool is_store_thread = (warp == 4) && (lane == 0);
+    const uint32_t tempty_leader = mapa(tempty_bar(0), 0);
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t store_iter = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks);
+      const int row0 = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
+      const int col_tile = tc.n_blk * kBlockN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / kStoreCols; ++c) {
+        const int col0 = col_tile + c * kStoreCols;
+        uint32_t r[2][32];
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * kBlockN + c * kStoreCols;
+        tmem_ld_32x32b_x32(taddr, r[0]);
+        tmem_ld_32x32b_x32(taddr + 32, r[1]);
+        tmem_ld_wait();
+        if (c == kBlockN / kStoreCols - 1) {
+          // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * acc);
+        }
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i >> 5][i & 31]);
+        if (epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int i = 0; i < 64; i += 8) {
+            if (col0 + i < N) {   // N % 8 == 0 is required by the host wrapper
+              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + col0 + i));
+              const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bv);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(b2[j]);
+                v[i + 2 * j] += f.x; v[i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+        }
+        if (epilogue == EPI_BIAS_GELU || epilogue == EPI_GELU) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
+        }
+        if constexpr (kOutMode == 0) {
+          const uint32_t buf = store_iter & 1u;
+          if (store_iter >= 2) {
+            if (is_store_thread) tma_store_wait_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+          const uint32_t sbase = smem_epi + buf * S::kEpiBytes + row_in_cta * 128u;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t dst = sbase + (((uint32_t)ch ^ (row_in_cta & 7u)) << 4);
+            uint32_t p0, p1, p2, p3;
+            if (ab_format == 1) {
+              p0 = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]); p1 = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+              p2 = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]); p3 = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+            } else {
+              __half2 h0 = __floats2half2_rn(v[ch * 8 + 0], v[ch * 8 + 1]), h1 = __floats2half2_rn(v[ch * 8 + 2], v[ch * 8 + 3]);
+              __half2 h2 = __floats2half2_rn(v[ch * 8 + 4], v[ch * 8 + 5]), h3 = __floats2half2_rn(v[ch * 8 + 6], v[ch * 8 + 7]);
+              p0 = *reinterpret_cast<uint32_t*>(&h0); p1 = *reinterpret_cast<uint32_t*>(&h1);
+              p2 = *reinterpret_cast<uint32_t*>(&h2); p3 = *reinterpret_cast<uint32_t*>(&h3);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (is_store_thread) {
+            if (col0 < N && row0 < M) tma_store_2d(&tmap_d, smem_epi + buf * S::kEpiBytes, col0, row0);
+            tma_store_commit();
+          }
+          ++store_iter;
+        } else {
+          const int grow = row0 + (int)row_in_cta;
+          if (grow < M) {
+            float* dst = out_f32 + (size_t)grow * ldd + col0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+              if (col0 + i < N) {   // N % 4 == 0 required
+                float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                if constexpr (kOutMode == 2) {
+                  const float4 old = *reinterpret_cast<const float4*>(dst + i);
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(dst + i) = o;
+              }
+            }
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (kOutMode == 0 && is_store_thread) tma_store_wait<0>();
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tcgen05_fence_before();
+  if (kCG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCG>(tmem_base, kTmemCols);
+}
+
+// ============================================================================ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* p = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [outer, inner] (inner contiguous), 128-byte swizzle, box = [box_outer, box_inner].
+bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_code, uint64_t inner, uint64_t outer,
+                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  CUtensorMapDataType dt;
+  switch (dtype_code) {
+    case 0: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16; break;
+    case 1: dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; break;
+    case 2: dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; break;
+    default: dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32; break;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  (void)elem_bytes;
+  return r == CUDA_SUCCESS;
+}
+
+template <int kCG, int kBlockN, bool kAK, bool kBK, int kOutMode>
+static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
+  using S = GemmSmem<kCG, kBlockN>;
+  constexpr int kLoadN = S::kLoadN;
+  CUtensorMap ta, tb, td;
+  const int dt = g.ab_format;  // 0 = fp16, 1 = bf16
+  bool ok = true;
+  if (kAK) ok &= make_tmap_2d(&ta, g.a, 2, dt, g.K, g.M, (uint64_t)g.lda * 2, kBlockK, kBlockM);
+  else     ok &= make_tmap_2d(&ta, g.a, 2, dt, g.M, g.K, (uint64_t)g.lda * 2, 64, kBlockK);
+  if (kBK) ok &= make_tmap_2d(&tb, g.b, 2, dt, g.K, g.N, (uint64_t)g.ldb * 2, kBlockK, kLoadN);
+  else     ok &= make_tmap_2d(&tb, g.b, 2, dt, g.N, g.K, (uint64_t)g.ldb * 2, 64, kBlockK);
+  if (kOutMode == 0) ok &= make_tmap_2d(&td, g.d, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
+  else td = ta;
+  if (!ok) return cudaErrorInvalidValue;
+
+  auto kern = gemm_tcgen05_kernel<kCG, kBlockN, kAK, kBK, kOutMode>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int num_m_blocks = (g.M + kBlockM * kCG - 1) / (kBlockM * kCG);
+  const int num_n_blocks = (g.N + kBlockN - 1) / kBlockN;
+  const int tiles = num_m_blocks * num_n_blocks;
+  int clusters = g.num_sms / kCG;
+  if (clusters > tiles) clusters = tiles;
+  if (clusters < 1) clusters = 1;
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kCG);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kCG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
+                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format);
+}
+
+template <int kCG, int kBlockN, int kOutMode>
+static cudaError_t launch_major(const GemmArgs& g, cudaStream_t s) {
+  if (g.a_kmajor && g.b_kmajor) return launch_cfg<kCG, kBlockN, true, true, kOutMode>(g, s);
+  if (g.a_kmajor && !g.b_kmajor) return launch_cfg<kCG, kBlockN, true, false, kOutMode>(g, s);
+  if (!g.a_kmajor && g.b_kmajor) return launch_cfg<kCG, kBlockN, false, true, kOutMode>(g, s);
+  return launch_cfg<kCG, kBlockN, false, false, kOutMode>(g, s);
+}
+
+template <int kCG, int kBlockN>
+static cudaError_t launch_out(const GemmArgs& g, cudaStream_t s) {
+  switch (g.out_mode) {
+    case 0: return launch_major<kCG, kBlockN, 0>(g, s);
+    case 1: return launch_major<kCG, kBlockN, 1>(g, s);
+    default: return launch_major<kCG, kBlockN, 2>(g, s);
+  }
+}
+
+cudaError_t gemm_tcgen05(const GemmArgs& g, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
+  // config: 0 = auto, 1 = 1-CTA 128x256, 2 = 2-CTA 256x256, 3 = 1-CTA 128x128, 4 = 2-CTA 256x128
+  int cfg = g.config;
+  if (cfg == 0) {
+    const long tiles_big = (long)((g.M + 255) / 256) * ((g.N + 255) / 256);
+    cfg = (tiles_big >= g.num_sms / 2) ? 2 : ((g.N > 128) ? 1 : 3);
+  }
+  switch (cfg) {
+    case 1: return launch_out<1, 256>(g, stream);
+    case 2: return launch_out<2, 256>(g, stream);
+    case 3: return launch_out<1, 128>(g, stream);
+    default: return launch_out<2, 128>(g, stream);
+  }
+}
+
+}  // namespace pfx

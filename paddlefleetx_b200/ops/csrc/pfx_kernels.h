@@ -1,0 +1,51 @@
+// C++ launch interface of the non-GEMM kernels.  dtype codes: 0 = fp16, 1 = bf16, 3 = fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace pfx {
+
+cudaError_t norm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int rows, int cols, float eps,
+                     int dtype, bool rms, cudaStream_t st);
+int norm_bwd_num_parts(int rows, int num_sms);
+cudaError_t norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, void* dw, void* db,
+                     float* workspace, int rows, int cols, int dtype, bool rms, int num_sms, cudaStream_t st);
+
+cudaError_t bias_gelu(const void* x, const void* bias, const void* dy, void* out, size_t rows, int cols, int dtype, bool bwd, int num_sms,
+                      cudaStream_t st);
+cudaError_t bias_dropout_add(const void* x, const void* bias, const void* residual, void* out, size_t rows, int cols, float p,
+                             uint64_t seed, uint64_t offset, int dtype, bool bwd, int num_sms, cudaStream_t st);
+int colsum_num_parts(int rows);
+cudaError_t colsum(const void* x, void* out, float* workspace, int rows, int cols, int dtype, bool out_fp32, cudaStream_t st);
+
+cudaError_t ce_stats(const void* logits, const int64_t* labels, float* row_max, float* row_sum, float* tgt, int rows, int cols,
+                     int64_t vocab_start, int dtype, cudaStream_t st);
+cudaError_t ce_bwd(void* logits, const int64_t* labels, const float* lse, const float* gscale, int rows, int cols, int64_t vocab_start,
+                   int dtype, cudaStream_t st);
+
+cudaError_t sumsq(const void* x, size_t n, float* out, float* workspace, int dtype, bool accumulate, int num_sms, cudaStream_t st);
+cudaError_t clip_coef(const float* sq, float inv_loss_scale, float clip_norm, float* gscale, float* found_inf, float* gnorm, cudaStream_t st);
+cudaError_t adamw_flat(void* p_lp, float* master, const void* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                       float eps, float wd, float bc1, float bc2, const float* gscale, const float* found_inf, int grad_dtype,
+                       int lp_dtype, int num_sms, cudaStream_t st);
+cudaError_t accumulate_f32(float* dst, const void* src, size_t n, float scale, int dtype, int num_sms, cudaStream_t st);
+
+cudaError_t topp_sampling(const void* probs, const float* top_ps, float* out_prob, int64_t* out_id, int rows, int V, uint64_t seed,
+                          uint64_t offset, int dtype, cudaStream_t st);
+cudaError_t rope(const void* x, void* y, const int64_t* positions, size_t tokens, int heads, int d, int seq_len, float base, bool bwd,
+                 int dtype, int num_sms, cudaStream_t st);
+cudaError_t causal_softmax(const void* a, const void* b, void* out, size_t batch, int sq, int sk, float scale, bool bwd, int dtype,
+                           cudaStream_t st);
+
+// ---- peer-memory collectives (comm_p2p.cu): every pointer table lives in device memory
+cudaError_t p2p_barrier(uint32_t** signal_pads, int rank, int world, uint32_t epoch_slot, cudaStream_t st);
+cudaError_t p2p_reduce_scatter(void** peer_bufs, void* out, size_t shard_elems, int rank, int world, int in_dtype, int out_dtype,
+                               bool accumulate, float scale, int num_sms, cudaStream_t st);
+cudaError_t p2p_all_gather(void** peer_bufs, const void* src, size_t shard_elems, int rank, int world, int dtype, int num_sms,
+                           cudaStream_t st);
+cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, float* master, const void* grad, float* m, float* v, size_t n,
+                                float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, const float* gscale,
+                                const float* found_inf, int grad_dtype, int lp_dtype, int world, int num_sms, cudaStream_t st);
+
+}  // namespace pfx

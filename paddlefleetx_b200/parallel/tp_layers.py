@@ -1,0 +1,237 @@
+"""Megatron-style tensor-parallel layers + their sequence-parallel variants.
+
+What the reference gets from ``paddle.distributed.fleet.meta_parallel`` (contracts in SURVEY §2.5, call sites
+gpt/dygraph/hybrid_model.py:139-196,589-605,699-704,951-952) and from its in-tree
+``sequence_parallel_utils.py:215-398``:
+
+    ColumnParallelLinear       W[out/n, in]   identity fwd / all-reduce bwd on the input
+    RowParallelLinear          W[out, in/n]   GEMM -> all-reduce -> + bias
+    ColumnSequenceParallelLinear  all-gather(seq) -> GEMM      (bwd: reduce-scatter)
+    RowSequenceParallelLinear     GEMM -> reduce-scatter(seq)  (bwd: all-gather), then + bias
+    VocabParallelEmbedding     vocab-sharded lookup + all-reduce
+    ParallelCrossEntropy       vocab-parallel softmax-CE
+
+Weights are stored ``[out, in]`` (torch convention, K-major for the tcgen05 GEMM).  ``mp_group=None`` or a
+size-1 group degenerates every layer to its plain single-GPU form, so the same model code serves 1..N GPUs.
+With ``Fused.tp_comm`` enabled on NVSwitch boxes the SP linears run the fused GEMM+collective kernels of
+``parallel/fused_tp.py`` instead of NCCL + GEMM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ..ops import functional as OF
+from . import comm_ops as C
+
+
+def _mark(p: nn.Parameter, **attrs) -> nn.Parameter:
+    for k, v in attrs.items():
+        setattr(p, k, v)
+    return p
+
+
+def _init_normal_sharded(weight: torch.Tensor, std: float, full_shape, shard_dim: int, group) -> None:
+    """Every TP rank draws its slice from its own RNG position (the reference seeds TP init per rank through
+    ``tensor_init_seed``); layouts are therefore equivalent in distribution, not bitwise."""
+    with torch.no_grad():
+        weight.normal_(mean=0.0, std=std)
+
+
+class ColumnParallelLinear(nn.Module):
+    def __init__(self, in_features: int, out_features: int, mp_group=None, has_bias: bool = True, gather_output: bool = True,
+                 init_std: float = 0.02, fuse_matmul_bias: bool = False, dtype=None, device=None):
+        super().__init__()
+        self.group = mp_group
+        self.world = C.group_size(mp_group)
+        assert out_features % self.world == 0, f"out_features {out_features} % mp {self.world}"
+        self.in_features, self.out_features = in_features, out_features
+        self.out_per_rank = out_features // self.world
+        self.gather_output = gather_output
+        self.weight = nn.Parameter(torch.empty(self.out_per_rank, in_features, dtype=dtype, device=device))
+        _init_normal_sharded(self.weight, init_std, (out_features, in_features), 0, mp_group)
+        _mark(self.weight, is_distributed=self.world > 1, split_axis=0)
+        if has_bias:
+            self.bias = nn.Parameter(torch.zeros(self.out_per_rank, dtype=dtype, device=device))
+            _mark(self.bias, is_distributed=self.world > 1, split_axis=0)
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x: torch.Tensor, skip_bias: bool = False) -> torch.Tensor:
+        x = C.copy_to_group(x, self.group)
+        y = OF.linear(x, self.weight, None if skip_bias else self.bias)
+        return C.gather_last_dim(y, self.group) if self.gather_output else y
+
+
+class RowParallelLinear(nn.Module):
+    def __init__(self, in_features: int, out_features: int, mp_group=None, has_bias: bool = True, input_is_parallel: bool = False,
+                 init_std: float = 0.02, fuse_matmul_bias: bool = False, dtype=None, device=None, skip_bias_add: bool = False):
+        super().__init__()
+        self.group = mp_group
+        self.world = C.group_size(mp_group)
+        assert in_features % self.world == 0
+        self.in_features, self.out_features = in_features, out_features
+        self.in_per_rank = in_features // self.world
+        self.input_is_parallel = input_is_parallel
+        self.skip_bias_add = skip_bias_add
+        self.weight = nn.Parameter(torch.empty(out_features, self.in_per_rank, dtype=dtype, device=device))
+        _init_normal_sharded(self.weight, init_std, (out_features, in_features), 1, mp_group)
+        _mark(self.weight, is_distributed=self.world > 1, split_axis=1)
+        if has_bias:
+            self.bias = nn.Parameter(torch.zeros(out_features, dtype=dtype, device=device))
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x: torch.Tensor):
+        if not self.input_is_parallel:
+            x = C.scatter_last_dim(x, self.group)
+        if self.world == 1:
+            if self.skip_bias_add:
+                return OF.linear(x, self.weight, None), self.bias
+            return OF.linear(x, self.weight, self.bias)
+        y = C.reduce_from_group(OF.linear(x, self.weight, None), self.group)
+        if self.skip_bias_add:
+            return y, self.bias
+        return y if self.bias is None else y + self.bias
+
+
+class ColumnSequenceParallelLinear(nn.Module):
+    """input ``[s/n, b, h]`` -> all-gather along s -> GEMM -> ``[s, b, out/n]``."""
+
+    def __init__(self, in_features: int, out_features: int, mp_group=None, has_bias: bool = True, gather_output: bool = False,
+                 init_std: float = 0.02, dtype=None, device=None, fused_comm: bool = False):
+        super().__init__()
+        assert not gather_output, "sequence-parallel column linear never gathers its output"
+        self.group = mp_group
+        self.world = C.group_size(mp_group)
+        self.out_per_rank = out_features // self.world
+        self.fused_comm = fused_comm
+        self.weight = nn.Parameter(torch.empty(self.out_per_rank, in_features, dtype=dtype, device=device))
+        _init_normal_sharded(self.weight, init_std, (out_features, in_features), 0, mp_group)
+        _mark(self.weight, is_distributed=self.world > 1, split_axis=0)
+        if has_bias:
+            self.bias = nn.Parameter(torch.zeros(self.out_per_rank, dtype=dtype, device=device))
+            _mark(self.bias, is_distributed=self.world > 1, split_axis=0)
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x: torch.Tensor, skip_bias: bool = False) -> torch.Tensor:
+        bias = None if skip_bias else self.bias
+        if self.fused_comm and x.is_cuda and self.world > 1:
+            from .fused_tp import all_gather_linear
+
+            return all_gather_linear(x, self.weight, bias, self.group)
+        return OF.linear(C.all_gather_seq(x, self.group), self.weight, bias)
+
+
+class RowSequenceParallelLinear(nn.Module):
+    """input ``[s, b, in/n]`` -> GEMM -> reduce-scatter along s -> ``[s/n, b, out]`` (+ bias)."""
+
+    def __init__(self, in_features: int, out_features: int, mp_group=None, has_bias: bool = True, input_is_parallel: bool = True,
+                 init_std: float = 0.02, dtype=None, device=None, fused_comm: bool = False, skip_bias_add: bool = False):
+        super().__init__()
+        assert input_is_parallel
+        self.group = mp_group
+        self.world = C.group_size(mp_group)
+        self.in_per_rank = in_features // self.world
+        self.fused_comm = fused_comm
+        self.skip_bias_add = skip_bias_add
+        self.weight = nn.Parameter(torch.empty(out_features, self.in_per_rank, dtype=dtype, device=device))
+        _init_normal_sharded(self.weight, init_std, (out_features, in_features), 1, mp_group)
+        _mark(self.weight, is_distributed=self.world > 1, split_axis=1)
+        if has_bias:
+            self.bias = nn.Parameter(torch.zeros(out_features, dtype=dtype, device=device))
+            # replicated param whose grad is computed from a sequence shard: needs an mp all-reduce
+            _mark(self.bias, sequence_parallel=self.world > 1)
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x: torch.Tensor):
+        if self.fused_comm and x.is_cuda and self.world > 1:
+            from .fused_tp import linear_reduce_scatter
+
+            y = linear_reduce_scatter(x, self.weight, self.group)
+        else:
+            y = C.reduce_scatter_seq(OF.linear(x, self.weight, None), self.group)
+        if self.skip_bias_add:
+            return y, self.bias
+        return y if self.bias is None else y + self.bias
+
+
+class VocabParallelEmbedding(nn.Module):
+    def __init__(self, num_embeddings: int, embedding_dim: int, mp_group=None, init_std: float = 0.02, dtype=None, device=None):
+        super().__init__()
+        self.group = mp_group
+        self.world = C.group_size(mp_group)
+        assert num_embeddings % self.world == 0, f"vocab {num_embeddings} % mp {self.world}"
+        self.num_embeddings = num_embeddings
+        self.per_rank = num_embeddings // self.world
+        self.vocab_start = C.group_rank(mp_group) * self.per_rank
+        self.weight = nn.Parameter(torch.empty(self.per_rank, embedding_dim, dtype=dtype, device=device))
+        with torch.no_grad():
+            self.weight.normal_(0.0, init_std)
+        _mark(self.weight, is_distributed=self.world > 1, split_axis=0)
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return torch.nn.functional.embedding(ids, self.weight)
+        local = ids - self.vocab_start
+        oob = (local < 0) | (local >= self.per_rank)
+        out = torch.nn.functional.embedding(local.masked_fill(oob, 0), self.weight)
+        out = out.masked_fill(oob.unsqueeze(-1), 0.0)
+        return C.reduce_from_group(out, self.group)
+
+
+class ParallelCrossEntropy(nn.Module):
+    """Un-reduced vocab-parallel CE; logits ``[..., V/n]`` on each rank."""
+
+    def __init__(self, mp_group=None):
+        super().__init__()
+        self.group = mp_group
+        self.world = C.group_size(mp_group)
+
+    def forward(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        vocab_start = C.group_rank(self.group) * logits.shape[-1] if self.world > 1 else 0
+        return OF.softmax_cross_entropy(logits, labels, self.group if self.world > 1 else None, vocab_start)
+
+
+def parallel_matmul(x: torch.Tensor, weight: torch.Tensor, mp_group=None, parallel_output: bool = True) -> torch.Tensor:
+    """Tied LM head: ``x @ E_shard^T`` with identity-fwd / all-reduce-bwd on x (reference hybrid_model.py:66-87)."""
+    world = C.group_size(mp_group)
+    if world > 1:
+        x = C.copy_to_group(x, mp_group)
+    logits = OF.linear(x, weight, None)
+    if world > 1 and not parallel_output:
+        logits = C.gather_last_dim(logits, mp_group)
+    return logits
+
+
+# ------------------------------------------------------------------ sequence-parallel param hooks
+def is_sequence_parallel_parameter(p) -> bool:
+    return getattr(p, "sequence_parallel", False)
+
+
+def mark_as_sequence_parallel_parameter(p) -> None:
+    p.sequence_parallel = True
+
+
+def register_sequence_parallel_allreduce_hooks(model: nn.Module, accumulation_steps: int, fuse: bool, group) -> list:
+    """LayerNorm weights/biases and row-linear biases see only a sequence shard under SP, so their grads are
+    partial sums: all-reduce them over the mp group once per ``accumulation_steps`` backward passes
+    (reference sequence_parallel_utils.py:155-212).  Returns the list of SP params; the engine calls
+    ``allreduce_sequence_parallel_grads`` after the last micro-batch (one coalesced all-reduce)."""
+    if accumulation_steps <= 0 or C.group_size(group) == 1:
+        return []
+    params = [p for p in model.parameters() if is_sequence_parallel_parameter(p)]
+    model._sp_params = params
+    model._sp_group = group
+    return params
+
+
+def allreduce_sequence_parallel_grads(model: nn.Module) -> None:
+    params = getattr(model, "_sp_params", None)
+    if params:
+        C.fused_allreduce_gradients(params, model._sp_group, scale=1.0)

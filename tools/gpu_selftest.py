@@ -1,0 +1,312 @@
+"""Stand-alone numerics + timing sweep of the native kernels on one B200.
+
+Each check runs in its own subprocess under a timeout so that a hung or trapping kernel cannot take the whole
+sweep (or the GPU box) down.  Results are appended to ``gpurun_out/selftest.log`` as JSON lines.
+
+    python tools/gpu_selftest.py            # all checks
+    python tools/gpu_selftest.py gemm_nt    # one check (runs in-process)
+"""
+from __future__ import annotations
+
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _lib():
+    from paddlefleetx_b200.ops import _native
+    return _native.require()
+
+
+def _time(fn, iters=20, warmup=5, flush_mb=256):
+    import torch
+    flush = torch.empty(flush_mb * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()  # > L2 (126 MB): cold-L2 timing
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def _relerr(a, b):
+    import torch
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+# ------------------------------------------------------------------------------------ checks
+def check_gemm(a_k=True, b_k=True, cfg=1, M=512, N=512, K=256, out_mode=0, epilogue=0, time_it=False):
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16) if epilogue in (1, 2) else None
+    a = A if a_k else A.t().contiguous()
+    b = B if b_k else B.t().contiguous()
+    ref = A.float() @ B.float().t()
+    if bias is not None:
+        ref = ref + bias.float()
+    if epilogue in (2, 3):
+        ref = torch.nn.functional.gelu(ref, approximate="tanh")
+    out = None
+    if out_mode == 2:
+        out = torch.randn(M, N, device="cuda", dtype=torch.float32)
+        ref = ref + out
+    d = lib.gemm(a, b, bias, out, a_k, b_k, epilogue, out_mode, cfg)
+    torch.cuda.synchronize()
+    err = _relerr(d, ref)
+    res = dict(err=err, ok=bool(err < 2e-2 if out_mode == 0 else err < 1e-2))
+    if time_it:
+        med, best = _time(lambda: lib.gemm(a, b, bias, None if out_mode != 2 else out, a_k, b_k, epilogue, out_mode, cfg))
+        res.update(ms=med, ms_best=best, tflops=2.0 * M * N * K / med / 1e9, tflops_best=2.0 * M * N * K / best / 1e9)
+        med2, best2 = _time(lambda: torch.matmul(A, B.t()))
+        res.update(cublas_ms=med2, cublas_tflops=2.0 * M * N * K / med2 / 1e9)
+    return res
+
+
+def check_norm(rms=False, rows=4096, cols=4096):
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16)
+    w = (torch.randn(cols, device="cuda") * 0.1 + 1).bfloat16()
+    b = (torch.randn(cols, device="cuda") * 0.1).bfloat16()
+    dy = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16)
+    xf = x.float().requires_grad_(True); wf = w.float().requires_grad_(True); bf = b.float().requires_grad_(True)
+    if rms:
+        ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    else:
+        ref = torch.nn.functional.layer_norm(xf, (cols,), wf, bf, 1e-5)
+    ref.backward(dy.float())
+    y, mean, rstd = lib.norm_fwd(x, w, None if rms else b, 1e-5, rms)
+    dx, dw, db = lib.norm_bwd(dy, x, w, mean, rstd, rms, not rms)
+    torch.cuda.synchronize()
+    errs = dict(y=_relerr(y, ref), dx=_relerr(dx, xf.grad), dw=_relerr(dw, wf.grad))
+    if not rms:
+        errs["db"] = _relerr(db, bf.grad)
+    med, _ = _time(lambda: lib.norm_fwd(x, w, None if rms else b, 1e-5, rms))
+    medb, _ = _time(lambda: lib.norm_bwd(dy, x, w, mean, rstd, rms, not rms))
+    nbytes = rows * cols * 2
+    return dict(errs=errs, ok=all(v < 1.5e-2 for v in errs.values()), fwd_ms=med, fwd_gbs=2 * nbytes / med / 1e6,
+                bwd_ms=medb, bwd_gbs=3 * nbytes / medb / 1e6)
+
+
+def check_gelu_dropout():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    rows, cols = 4096, 4096
+    x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16)
+    bias = torch.randn(cols, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16)
+    dy = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16)
+    xf = (x.float() + bias.float()).requires_grad_(True)
+    ref = torch.nn.functional.gelu(xf, approximate="tanh")
+    ref.backward(dy.float())
+    y = lib.bias_gelu_fwd(x, bias)
+    dx = lib.bias_gelu_bwd(dy, x, bias)
+    errs = dict(gelu=_relerr(y, ref), dgelu=_relerr(dx, xf.grad))
+    p = 0.1
+    yd = lib.bias_dropout_add_fwd(x, bias, res, p, 1234, 77)
+    dxd = lib.dropout_bwd(dy, p, 1234, 77)
+    pre = (x.float() + bias.float())
+    kept = (yd.float() - res.float()).abs() > 1e-6 * 0  # placeholder
+    diff = yd.float() - res.float()
+    keep_mask = dxd.float() != 0
+    frac = float(keep_mask.float().mean())
+    # where kept, diff ~= pre / (1-p); where dropped, diff ~= 0 (bf16 rounding of res + val)
+    exp = torch.where(keep_mask, pre / (1 - p), torch.zeros_like(pre)) + res.float()
+    errs["dropout_fwd"] = _relerr(yd, exp)
+    errs["dropout_bwd"] = _relerr(dxd, torch.where(keep_mask, dy.float() / (1 - p), torch.zeros_like(pre)))
+    y0 = lib.bias_dropout_add_fwd(x, bias, res, 0.0, 1, 0)
+    errs["p0"] = _relerr(y0, pre + res.float())
+    cs = lib.colsum(dy, True)
+    errs["colsum"] = _relerr(cs, dy.float().sum(0))
+    med, _ = _time(lambda: lib.bias_dropout_add_fwd(x, bias, res, p, 1234, 77))
+    return dict(errs=errs, keep_frac=frac, ok=all(v < 1.5e-2 for v in errs.values()) and abs(frac - 0.9) < 5e-3,
+                bda_ms=med, bda_gbs=3 * rows * cols * 2 / med / 1e6)
+
+
+def check_ce():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    rows, V = 2048, 50304
+    logits = (torch.randn(rows, V, device="cuda") * 2).bfloat16()
+    labels = torch.randint(0, V, (rows,), device="cuda")
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf, labels, reduction="none")
+    g = torch.rand(rows, device="cuda")
+    (ref * g).sum().backward()
+    mx, sm, tg = lib.ce_stats(logits, labels, 0)
+    lse = mx + sm.log()
+    loss = lse - tg
+    work = logits.clone()
+    lib.ce_bwd_(work, labels, lse, g, 0)
+    errs = dict(loss=_relerr(loss, ref), dlogits=_relerr(work, lf.grad))
+    med, _ = _time(lambda: lib.ce_stats(logits, labels, 0))
+    return dict(errs=errs, ok=all(v < 1.5e-2 for v in errs.values()), stats_ms=med, stats_gbs=rows * V * 2 / med / 1e6)
+
+
+def check_adam():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    n = 1 << 24
+    master = torch.randn(n, device="cuda")
+    grad = (torch.randn(n, device="cuda") * 0.01).bfloat16()
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    p_lp = master.bfloat16()
+    ref_p = torch.nn.Parameter(master.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.01)
+    sq = torch.zeros(1, device="cuda"); gscale = torch.zeros(1, device="cuda"); finf = torch.zeros(1, device="cuda"); gn = torch.zeros(1, device="cuda")
+    lib.sumsq_(grad, sq, False)
+    norm_ref = grad.float().norm()
+    lib.clip_coef_(sq, 1.0, 1.0, gscale, finf, gn)
+    coef = min(1.0, 1.0 / (float(norm_ref) + 1e-6))
+    for step in (1, 2, 3):
+        ref_p.grad = grad.float() * coef
+        opt.step()
+        lib.adamw_flat_(p_lp, master, grad, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.01, step, gscale, finf)
+    errs = dict(norm=abs(float(gn) - float(norm_ref)) / float(norm_ref), master=_relerr(master, ref_p.data), lp=_relerr(p_lp, ref_p.data))
+    med, _ = _time(lambda: lib.adamw_flat_(p_lp, master, grad, m, v, 1e-3, 0.9, 0.95, 1e-8, 0.01, 4, gscale, finf))
+    return dict(errs=errs, ok=errs["norm"] < 1e-3 and errs["master"] < 1e-5 and errs["lp"] < 1e-2, adam_ms=med,
+                adam_gbs=n * (4 * 3 * 2 + 2 + 2) / med / 1e6)
+
+
+def check_topp():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    bs, V = 8, 50304
+    probs = torch.softmax(torch.randn(bs, V, device="cuda") * 3, -1)
+    top_ps = torch.full((bs,), 0.8, device="cuda")
+    # empirical distribution vs renormalised nucleus
+    counts = torch.zeros(bs, V, device="cuda")
+    trials = 2000
+    for t in range(trials):
+        _, ids = lib.topp_sampling(probs, top_ps, 42, t * bs)
+        counts.scatter_add_(1, ids, torch.ones_like(ids, dtype=torch.float))
+    sp, si = probs.sort(-1, descending=True)
+    cum = sp.cumsum(-1)
+    in_nucleus_sorted = (cum - sp) < 0.8
+    nucleus = torch.zeros_like(probs).scatter(1, si, in_nucleus_sorted.float())
+    outside = float((counts * (1 - nucleus)).sum() / counts.sum())
+    emp = counts / trials
+    target = probs * nucleus
+    # mass is u*top_p truncated inverse-CDF: P(token) = p / top_p for tokens fully inside
+    tv = float((emp - target / 0.8).abs().sum(-1).mean()) / 2
+    # half / bf16 inputs run
+    _, ids16 = lib.topp_sampling(probs.half(), top_ps, 1, 0)
+    med, _ = _time(lambda: lib.topp_sampling(probs, top_ps, 42, 0), flush_mb=1)
+    return dict(outside_frac=outside, tv=tv, ok=outside < 2e-3 and tv < 0.12, ms=med, ids16=ids16.flatten().tolist()[:4])
+
+
+def check_rope_softmax():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    b, s, h, d = 2, 128, 4, 64
+    x = torch.randn(b, s, h, d, device="cuda", dtype=torch.bfloat16)
+    y = lib.rope(x.view(b * s, h, d), None, s, 10000.0, False).view(b, s, h, d)
+    pos = torch.arange(s, device="cuda").float()
+    inv = 10000.0 ** (-torch.arange(0, d, 2, device="cuda").float() / d)
+    ang = pos[:, None] * inv[None]
+    cs, sn = ang.cos()[None, :, None, :], ang.sin()[None, :, None, :]
+    xf = x.float(); x1, x2 = xf[..., : d // 2], xf[..., d // 2:]
+    ref = torch.cat([x1 * cs - x2 * sn, x2 * cs + x1 * sn], -1)
+    back = lib.rope(y.view(b * s, h, d), None, s, 10000.0, True).view(b, s, h, d)
+    errs = dict(rope=_relerr(y, ref), rope_inv=_relerr(back, x))
+    sc = torch.randn(b * h, s, s, device="cuda", dtype=torch.bfloat16)
+    p = lib.causal_softmax_fwd(sc, 0.125)
+    scf = sc.float().requires_grad_(True)
+    mask = torch.triu(torch.ones(s, s, device="cuda", dtype=torch.bool), 1)
+    pref = torch.softmax((scf * 0.125).masked_fill(mask, float("-inf")), -1)
+    dyy = torch.randn_like(pref)
+    pref.backward(dyy)
+    dx = lib.causal_softmax_bwd(dyy.bfloat16(), p, 0.125)
+    errs.update(csm=_relerr(p, pref), dcsm=_relerr(dx, scf.grad))
+    return dict(errs=errs, ok=all(v < 2e-2 for v in errs.values()))
+
+
+CHECKS = {
+    "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
+    "gemm_nt_1cta_n128": lambda: check_gemm(True, True, 3),
+    "gemm_nt_2cta": lambda: check_gemm(True, True, 2),
+    "gemm_nt_2cta_n128": lambda: check_gemm(True, True, 4),
+    "gemm_nn_1cta": lambda: check_gemm(True, False, 1),
+    "gemm_tn_1cta": lambda: check_gemm(False, False, 1),
+    "gemm_tk_1cta": lambda: check_gemm(False, True, 1),
+    "gemm_nn_2cta": lambda: check_gemm(True, False, 2),
+    "gemm_tn_2cta": lambda: check_gemm(False, False, 2),
+    "gemm_tail": lambda: check_gemm(True, True, 1, M=300, N=264, K=136),
+    "gemm_tail_2cta": lambda: check_gemm(True, True, 2, M=300, N=264, K=136),
+    "gemm_bias_gelu": lambda: check_gemm(True, True, 1, epilogue=2),
+    "gemm_f32_acc": lambda: check_gemm(False, False, 2, out_mode=2),
+    "gemm_f32": lambda: check_gemm(True, True, 1, out_mode=1),
+    "gemm_perf_1cta": lambda: check_gemm(True, True, 1, 8192, 8192, 8192, time_it=True),
+    "gemm_perf_2cta": lambda: check_gemm(True, True, 2, 8192, 8192, 8192, time_it=True),
+    "gemm_perf_ffn1": lambda: check_gemm(True, True, 2, 8192, 16384, 4096, epilogue=1, time_it=True),
+    "gemm_perf_dgrad": lambda: check_gemm(True, False, 2, 8192, 4096, 16384, time_it=True),
+    "gemm_perf_wgrad": lambda: check_gemm(False, False, 2, 16384, 4096, 8192, out_mode=1, time_it=True),
+    "layernorm": lambda: check_norm(False),
+    "rmsnorm": lambda: check_norm(True),
+    "gelu_dropout": check_gelu_dropout,
+    "cross_entropy": check_ce,
+    "adamw": check_adam,
+    "topp": check_topp,
+    "rope_softmax": check_rope_softmax,
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] in CHECKS:
+        name = sys.argv[1]
+        try:
+            res = CHECKS[name]()
+        except Exception as e:  # noqa: BLE001
+            res = dict(ok=False, error=repr(e)[:500])
+        print("RESULT " + json.dumps(dict(check=name, **res)))
+        return
+    names = sys.argv[1:] or list(CHECKS)
+    log = open(os.path.join(OUT, "selftest.log"), "a")
+    n_ok = 0
+    n_timeouts = 0
+    for name in names:
+        t0 = time.time()
+        if n_timeouts >= 3 and name.startswith("gemm"):
+            print(json.dumps(dict(check=name, ok=False, error="skipped after repeated timeouts")), flush=True)
+            continue
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=90)
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            res = json.loads(line[-1][7:]) if line else dict(check=name, ok=False, rc=p.returncode,
+                                                             tail=(p.stdout[-600:] + p.stderr[-1200:]))
+        except subprocess.TimeoutExpired:
+            res = dict(check=name, ok=False, error="timeout")
+            n_timeouts += 1
+        res["wall_s"] = round(time.time() - t0, 1)
+        n_ok += bool(res.get("ok"))
+        msg = json.dumps(res)
+        print(msg, flush=True)
+        log.write(msg + "\n"); log.flush()
+    print(f"SELFTEST {n_ok}/{len(names)} ok")
+
+
+if __name__ == "__main__":
+    main()
