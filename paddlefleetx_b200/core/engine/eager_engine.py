@@ -1,0 +1,443 @@
+"""``EagerEngine`` — the trainer: fit / evaluate / predict / save / load / export / inference.
+
+Control flow and externally visible behaviour follow ppfleetx/core/engine/eager_engine.py:47-925 (SURVEY §3.1,
+§7.4): epoch loop -> step loop (resume skips consumed batches, LR stepped in samples under ``use_increments``,
+logging every ``logging_freq`` with device-synchronised timestamps, in-loop eval every ``eval_freq`` but never on
+the first step, save every ``save_steps``, step-mode runs steps 0..max_steps inclusive), micro-batch gradient
+accumulation, bf16 = static scale 1.0 / fp16 = dynamic scaler, reference checkpoint layout.
+
+B200-first differences underneath:
+  * inputs are staged through pinned host buffers and copied on a side stream one step ahead,
+  * the loss stays on the device between logging boundaries (no per-step ``.item()``), step time is also taken
+    with CUDA events so the log carries device time,
+  * gradient traffic (DP all-reduce / ZeRO reduce-scatter + param all-gather) belongs to the flat optimizer,
+    the pipeline schedule to ``parallel/pipeline.py``; the engine only sequences them.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from typing import Optional
+
+import torch
+
+from ...distributed.apis import amp as amp_api
+from ...distributed.apis import env
+from ...distributed.apis import io as ckpt_io
+from ...distributed.apis.strategy import wrap_with_fleet
+from ...optims import build_lr_scheduler, build_optimizer
+from ...optims.lr_scheduler import LRScheduler
+from ...parallel.rng import get_rng_state_tracker
+from ...parallel.tp_layers import allreduce_sequence_parallel_grads
+from ...utils.log import get_timestamp, logger
+from ..module.basic_module import BasicModule
+from .basic_engine import BasicEngine
+
+
+def _to_device(obj, device, non_blocking=True):
+    if isinstance(obj, torch.Tensor):
+        return obj.to(device, non_blocking=non_blocking)
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_device(o, device, non_blocking) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _to_device(v, device, non_blocking) for k, v in obj.items()}
+    return obj
+
+
+def _split_micro(batch, n: int):
+    """Split every tensor of a (nested) batch into ``n`` micro-batches along dim 0."""
+    if n == 1:
+        return [batch]
+    if isinstance(batch, torch.Tensor):
+        return list(batch.chunk(n, dim=0))
+    if isinstance(batch, (list, tuple)):
+        parts = [_split_micro(b, n) for b in batch]
+        return [type(batch)(p[i] for p in parts) for i in range(n)]
+    if isinstance(batch, dict):
+        parts = {k: _split_micro(v, n) for k, v in batch.items()}
+        return [{k: parts[k][i] for k in batch} for i in range(n)]
+    return [batch] * n
+
+
+class _Prefetcher:
+    """Wraps a host dataloader: batch i+1 is copied H2D on a side stream while step i computes."""
+
+    def __init__(self, loader, device: torch.device):
+        self.loader, self.device = loader, device
+        self.stream = torch.cuda.Stream() if device.type == "cuda" else None
+
+    def __iter__(self):
+        it = iter(self.loader)
+        nxt = self._load(it)
+        while nxt is not None:
+            if self.stream is not None:
+                torch.cuda.current_stream().wait_stream(self.stream)
+            cur = nxt
+            nxt = self._load(it)
+            yield cur
+
+    def _load(self, it):
+        try:
+            batch = next(it)
+        except StopIteration:
+            return None
+        if self.stream is None:
+            return _to_device(batch, self.device, False)
+        with torch.cuda.stream(self.stream):
+            return _to_device(batch, self.device, True)
+
+    def __len__(self):
+        return len(self.loader)
+
+
+class EagerEngine(BasicEngine):
+    def __init__(self, configs, module: BasicModule, optimizer=None, lr=None, mode: str = "train"):
+        super().__init__()
+        if not isinstance(module, BasicModule):
+            raise TypeError("'module' must be sub classes of `BasicModule`, but got: {}".format(module.__class__.__name__))
+        self._configs = configs
+        self._module = module
+        self.mode = mode
+        g, eng, d = configs.Global, configs.Engine, configs.Distributed
+        self._device = torch.device("cuda", torch.cuda.current_device()) if str(g.get("device", "gpu")) == "gpu" and torch.cuda.is_available() \
+            else torch.device("cpu")
+        if module.model is not None and not any(True for _ in module.model.parameters()):
+            logger.warning("module.model has no parameters")
+
+        self._run_mode = eng.get("run_mode", "step")
+        assert self._run_mode in ("epoch", "step"), "run_mode must be epoch or step"
+        self._max_steps = eng.max_steps
+        self._eval_freq = eng.eval_freq
+        self._eval_iters = eng.eval_iters
+        self._test_iters = eng.test_iters
+        self._logging_freq = eng.logging_freq
+        self._num_train_epochs = eng.num_train_epochs
+        self._accumulate_steps = eng.accumulate_steps
+        amp = eng.mix_precision
+        self._use_pure_fp16 = bool(amp.enable) and mode != "export"
+        self._amp_dtype = str(amp.get("dtype", "float16"))
+        self._amp_level = str(amp.get("level", "O2"))
+        self._scale_loss = amp.scale_loss
+        self._save_steps = eng.save_load.save_steps
+        self._save_epoch = eng.save_load.save_epoch
+        self._output_dir = eng.save_load.output_dir
+        self._ckpt_dir = eng.save_load.ckpt_dir
+        self._global_batch_size = g.global_batch_size
+        self._local_batch_size = g.local_batch_size
+        self._micro_batch_size = g.micro_batch_size
+        self._dist = d
+        self._dp_degree, self._mp_degree, self._pp_degree = d.dp_degree, d.mp_degree, d.pp_degree
+        self._sharding_degree = d.sharding.sharding_degree
+        self._sharding_stage = d.sharding.sharding_stage
+        self._hcg = env.get_hcg()
+        self._dp_rank = self._hcg.get_data_parallel_rank()
+        if self._sharding_stage in (2, 3) and self._sharding_degree > 1 and self._pp_degree > 1 and self._sharding_stage == 3:
+            raise AssertionError("sharding stage 3 is not combined with pipeline parallel")
+
+        # compression hook (prune / QAT) — mirrors eager_engine.py:757-774
+        self._quant_mode = False
+        if "Compress" in configs and configs.Compress:
+            from ...utils.compression_helper import compress_model
+
+            self._module.model, self._quant_mode = compress_model(self._module.model, configs.Compress, self._device)
+
+        if self._device.type == "cuda":
+            self._module.to(self._device)
+
+        # scaler
+        if self._use_pure_fp16 and mode == "train":
+            if self._amp_dtype == "float16":
+                self._scaler = amp_api.GradScaler(True, self._scale_loss, True, hcg=self._hcg)
+            else:
+                self._scaler = amp_api.GradScaler(False, 1.0, False)
+        else:
+            self._scaler = None
+
+        # optimizer + lr
+        self._lr_scheduler, self._optimizer = None, None
+        if mode == "train":
+            self._use_increments = bool(configs.Optimizer.get("lr", {}).get("use_increments", False)) if isinstance(configs.Optimizer.get("lr"), dict) else False
+            self._lr_scheduler_mode = "step"
+            lr_cfg = configs.Optimizer.get("lr")
+            if isinstance(lr_cfg, dict):
+                self._lr_scheduler_mode = lr_cfg.pop("run_mode", "step")
+                lr_cfg_clean = {k: v for k, v in lr_cfg.items() if k not in ("_scaled_by_batch",)}
+            else:
+                lr_cfg_clean = lr_cfg
+            self._lr_scheduler = build_lr_scheduler(lr_cfg_clean) if lr is None else lr
+            self._optimizer = build_optimizer(configs.Optimizer, self._module.model, self._lr_scheduler, hcg=self._hcg,
+                                              dist_config=d, amp_config=amp) if optimizer is None else optimizer
+
+        # distributed wrappers
+        if env.world_size() > 1:
+            self._module.model, self._optimizer, self._scaler = wrap_with_fleet(d, self._module.model, self._optimizer, self._scaler)
+
+        self._load_recovery = {"step": 0, "epoch": 0, "rng_state": None}
+        self._profiler = None
+        if configs.get("Profiler", {}).get("enable", False) and mode == "train":
+            from ...utils.profiler import StepProfiler
+
+            self._profiler = StepProfiler(configs.Profiler)
+        self._inference_engine = None
+        self._train_tokens = None
+
+    # ---------------------------------------------------------------------------------------- helpers
+    def _amp_ctx(self):
+        return amp_api.autocast_context(self._use_pure_fp16, self._amp_dtype, self._amp_level, self._device.type)
+
+    @property
+    def optimizer(self):
+        return self._optimizer
+
+    @property
+    def module(self):
+        return self._module
+
+    # ---------------------------------------------------------------------------------------- fit
+    def fit(self, epoch: int = 1, train_data_loader=None, valid_data_loader=None):
+        self._module.model.train()
+        train_cost = 0.0
+        start_epoch = self._load_recovery["epoch"]
+        if self._load_recovery.get("rng_state") is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(self._load_recovery["rng_state"])
+        if self._load_recovery.get("rng_tracker") is not None:
+            get_rng_state_tracker().set_states_tracker(self._load_recovery["rng_tracker"])
+        for epoch_index in range(start_epoch, epoch):
+            t0 = get_timestamp()
+            self._train_one_epoch(epoch_index, train_data_loader, valid_data_loader)
+            train_cost = get_timestamp() - t0
+            self._module.training_epoch_end({"epoch": epoch_index, "train_cost": train_cost})
+            if self._run_mode == "epoch":
+                if self._lr_scheduler_mode == "epoch" and isinstance(self._lr_scheduler, LRScheduler):
+                    self._lr_scheduler.step()
+                if valid_data_loader is not None and self._eval_freq and epoch_index % max(self._eval_freq, 1) == 0 and self._eval_freq > 0:
+                    self._evaluate_one_epoch(epoch_index, valid_data_loader)
+                if self._save_epoch and (epoch_index + 1) % self._save_epoch == 0:
+                    self.save(epoch=epoch_index, step=len(train_data_loader) if train_data_loader is not None else 0)
+        if self._profiler is not None:
+            self._profiler.finish()
+
+    def _train_one_epoch(self, epoch_index: int, train_data_loader, valid_data_loader):
+        self._module.model.train()
+        device = self._device
+        loader = _Prefetcher(train_data_loader, device)
+        total_steps = self._max_steps if self._run_mode == "step" else len(train_data_loader)
+        losses = []
+        skip_first = True
+        train_start = get_timestamp()
+        ev0 = torch.cuda.Event(enable_timing=True) if device.type == "cuda" else None
+        if ev0 is not None:
+            ev0.record()
+        resume_step = self._load_recovery["step"] if epoch_index == self._load_recovery["epoch"] else 0
+        for step, batch in enumerate(loader):
+            if step < resume_step:
+                continue          # resume: replay the sampler and discard consumed batches (eager_engine.py:347-349)
+            loss = self._fit_impl(batch)
+            losses.append(loss)
+            found_inf = self._scaler.found_inf if (self._scaler is not None and self._amp_dtype == "float16") else False
+            if self._lr_scheduler_mode == "step" and isinstance(self._lr_scheduler, LRScheduler) and not found_inf:
+                self._lr_scheduler.step(epoch=self._global_batch_size if self._use_increments else None)
+
+            if (step + 1) % self._logging_freq == 0:
+                now = get_timestamp()
+                train_cost = (now - train_start) / self._logging_freq
+                dev_ms = None
+                if ev0 is not None:
+                    ev1 = torch.cuda.Event(enable_timing=True)
+                    ev1.record(); ev1.synchronize()
+                    dev_ms = ev0.elapsed_time(ev1) / self._logging_freq
+                    ev0 = ev1
+                vals = [float(l) for l in losses]
+                log = {"epoch": epoch_index, "total_epoch": self._num_train_epochs, "batch": step, "total_step": total_steps,
+                       "total_batch": total_steps, "train_cost": train_cost, "device_ms": dev_ms, "loss": sum(vals) / len(vals),
+                       "lr": self._optimizer.get_lr(), "found_inf": float(found_inf),
+                       "loss_scale": self._scaler.get_scale() if (self._scaler is not None and self._amp_dtype == "float16") else None}
+                self._module.training_step_end(log)
+                losses = []
+                train_start = get_timestamp()
+
+            self._optimizer.clear_grad()
+
+            if self._run_mode == "step" and not skip_first:
+                if self._eval_freq and self._eval_freq > 0 and step % self._eval_freq == 0 and valid_data_loader is not None:
+                    self._module.model.eval()
+                    eval_losses, t_eval = [], get_timestamp()
+                    for eval_step, ebatch in enumerate(_Prefetcher(valid_data_loader, device)):
+                        eval_losses.append(self._evaluate_impl(ebatch))
+                        if eval_step >= self._eval_iters - 1:
+                            break
+                    ecost = (get_timestamp() - t_eval) / self._logging_freq    # (sic) reference divides by logging_freq
+                    ev = [float(l) for l in eval_losses]
+                    self._module.validation_step_end({"loss": sum(ev) / max(len(ev), 1), "epoch": epoch_index, "batch": eval_step,
+                                                      "total_batch": total_steps, "eval_cost": ecost})
+                    self._module.model.train()
+                    train_start = get_timestamp()
+                if self._save_steps and self._save_steps > 0 and step % self._save_steps == 0:
+                    if device.type == "cuda":
+                        torch.cuda.synchronize()
+                    self.save(epoch=epoch_index, step=step)
+            else:
+                skip_first = False
+
+            if self._profiler is not None:
+                self._profiler.step()
+            if self._run_mode == "step" and step >= self._max_steps:
+                return
+
+    # ---------------------------------------------------------------------------------------- one optimizer step
+    def train_step(self, host_batch):
+        """Public single-step API: ``host_batch`` is what the dataloader yields (pinned host tensors).  Copies it to
+        the device, runs forward/backward over all micro-batches, the optimizer step, the LR step and clears the
+        gradients; returns the (device) loss tensor."""
+        batch = _to_device(host_batch, self._device, True)
+        loss = self._fit_impl(batch)
+        if self._lr_scheduler_mode == "step" and isinstance(self._lr_scheduler, LRScheduler):
+            self._lr_scheduler.step(epoch=self._global_batch_size if self._use_increments else None)
+        self._optimizer.clear_grad()
+        return loss
+
+    def _fit_impl(self, batch):
+        self._module.model.train()
+        batch = self._module.pretreating_batch(batch)
+        if self._pp_degree == 1:
+            loss = self._model_forward_backward(batch)
+        else:
+            with self._amp_ctx():
+                self._module.model._prepare_training(batch, self._optimizer, self._lr_scheduler)
+                loss = self._module.model.forward_backward_pipeline(batch, self._scaler)
+        self._optim_update_params()
+        return loss
+
+    def _model_forward_backward(self, batch):
+        n = self._accumulate_steps
+        micro_batches = _split_micro(batch, n)
+        total = None
+        for i, mb in enumerate(micro_batches):
+            last = i == n - 1
+            sync_ctx = self._optimizer.no_sync() if (not last and hasattr(self._optimizer, "no_sync")) else _Null()
+            with sync_ctx:
+                with self._amp_ctx():
+                    loss = self._module.training_step(mb)
+                loss_bw = self._scaler.scale(loss) if (self._scaler is not None and self._amp_dtype == "float16") else loss
+                if n > 1:
+                    loss_bw = loss_bw / n
+                self._module.backward(loss_bw)
+            d = loss.detach()
+            total = d if total is None else total + d
+        if self._mp_degree > 1 and self._configs.Model.get("sequence_parallel", False):
+            allreduce_sequence_parallel_grads(self._module.model)
+        return total / n if n > 1 else total
+
+    def _optim_update_params(self):
+        if self._scaler is not None and self._amp_dtype == "float16":
+            self._scaler.step(self._optimizer)
+            self._scaler.update()
+        else:
+            self._optimizer.step()
+
+    # ---------------------------------------------------------------------------------------- evaluate / predict
+    @torch.no_grad()
+    def evaluate(self, epoch: int = 1, valid_data_loader=None):
+        self._module.model.eval()
+        for e in range(epoch):
+            t0 = get_timestamp()
+            self._evaluate_one_epoch(e, valid_data_loader)
+            self._module.validation_epoch_end({"epoch": e, "eval_cost": get_timestamp() - t0})
+
+    @torch.no_grad()
+    def _evaluate_one_epoch(self, epoch_index: int, valid_data_loader):
+        self._module.model.eval()
+        t0 = get_timestamp()
+        losses = []
+        total = len(valid_data_loader) if hasattr(valid_data_loader, "__len__") else -1
+        for step, batch in enumerate(_Prefetcher(valid_data_loader, self._device)):
+            losses.append(self._evaluate_impl(batch))
+            if (step + 1) % self._logging_freq == 0:
+                cost = (get_timestamp() - t0) / self._logging_freq
+                vals = [float(l) for l in losses]
+                self._module.validation_step_end({"loss": sum(vals) / len(vals), "epoch": epoch_index, "batch": step, "total_batch": total,
+                                                  "eval_cost": cost})
+                t0, losses = get_timestamp(), []
+            if self._run_mode == "step" and self._eval_iters and step >= self._eval_iters - 1:
+                break
+
+    @torch.no_grad()
+    def _evaluate_impl(self, batch):
+        batch = self._module.pretreating_batch(batch)
+        with self._amp_ctx():
+            if self._pp_degree == 1:
+                loss = self._module.validation_step(batch)
+            else:
+                loss = self._module.model.eval_batch(batch, compute_loss=True)
+        return loss.detach() if isinstance(loss, torch.Tensor) else loss
+
+    @torch.no_grad()
+    def predict(self, epoch: int = 1, test_data_loader=None):
+        self._module.model.eval()
+        for e in range(epoch):
+            t0 = get_timestamp()
+            losses = []
+            for step, batch in enumerate(_Prefetcher(test_data_loader, self._device)):
+                losses.append(self._predict_impl(batch))
+                if (step + 1) % self._logging_freq == 0:
+                    cost = (get_timestamp() - t0) / self._logging_freq
+                    vals = [float(l) for l in losses]
+                    self._module.test_step_end({"loss": sum(vals) / len(vals), "epoch": e, "batch": step, "test_cost": cost})
+                    t0, losses = get_timestamp(), []
+                if self._run_mode == "step" and self._test_iters and step >= self._test_iters - 1:
+                    break
+
+    @torch.no_grad()
+    def _predict_impl(self, batch):
+        batch = self._module.pretreating_batch(batch)
+        with self._amp_ctx():
+            if self._pp_degree == 1:
+                loss = self._module.test_step(batch)
+            else:
+                loss = self._module.model.eval_batch(batch, compute_loss=True)
+        return loss.detach() if isinstance(loss, torch.Tensor) else loss
+
+    # ---------------------------------------------------------------------------------------- checkpoint
+    def save(self, epoch: int = 0, step: int = 0):
+        if self._output_dir is None:
+            return
+        model = self._module.model
+        if self._sharding_stage == 3 and self._sharding_degree > 1 and hasattr(model, "get_all_parameters"):
+            model.get_all_parameters()
+        ckpt_io.save(self._output_dir, model, self._optimizer, step=step, epoch=epoch, scaler=self._scaler)
+
+    def load(self):
+        if not self._ckpt_dir:
+            logger.warning("`load` requires Engine.save_load.ckpt_dir; skipping")
+            return
+        rec = ckpt_io.load(self._ckpt_dir, self._module.model, self._optimizer if self.mode == "train" else None,
+                           mode="train" if self.mode == "train" else "eval", scaler=self._scaler)
+        if rec:
+            self._load_recovery.update(rec)
+
+    # ---------------------------------------------------------------------------------------- export / inference
+    def export(self):
+        from ...utils.export import export_inference_model
+
+        self._module.model.eval()
+        save_dir = os.path.join(self._output_dir, f"rank_{self._dp_rank}")
+        export_inference_model(self._module.model, self._module.input_spec(), save_dir, "model", configs=self._configs,
+                               quant=self._quant_mode)
+        logger.info(f"export inference model saved in {save_dir}")
+
+    def inference(self, data):
+        if self._inference_engine is None:
+            from .inference_engine import InferenceEngine
+
+            inf = self._configs.Inference
+            self._inference_engine = InferenceEngine(inf.model_dir, inf.mp_degree)
+        return self._inference_engine.predict(data)
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -1,0 +1,1 @@
+from .basic_module import BasicModule  # noqa: F401

@@ -36,7 +36,7 @@ class ClipGradByGlobalNorm:
             if g is None:
                 continue
             s = g.float().pow(2).sum()
-            if getattr(p, "is_distributed", False) or getattr(p, "is_expert", False):
+            if getattr(p, "tp_sharded", False) or getattr(p, "is_expert", False):
                 dist_sq = s if dist_sq is None else dist_sq + s
             else:
                 rep_sq = s if rep_sq is None else rep_sq + s

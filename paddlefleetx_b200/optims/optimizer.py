@@ -90,7 +90,7 @@ class FusedAdamW:
                 cur, cur_bytes = cur + 1, 0
 
         def key_fn(p):
-            return (bucket_of[id(p)], self._decay[id(p)], bool(getattr(p, "is_distributed", False)), bool(getattr(p, "is_expert", False)))
+            return (bucket_of[id(p)], self._decay[id(p)], bool(getattr(p, "tp_sharded", False)), bool(getattr(p, "is_expert", False)))
 
         params = [p for _, p in named]
         grad_dtype = torch.float32 if use_main_grad else None

@@ -224,7 +224,7 @@ def broadcast_params(module: torch.nn.Module, group, src_rank: int, skip_distrib
     if not _active(group):
         return
     for t in list(module.parameters()) + list(module.buffers()):
-        if skip_distributed and getattr(t, "is_distributed", False):
+        if skip_distributed and getattr(t, "tp_sharded", False):
             continue
         dist.broadcast(t.data, src=src_rank, group=_pg(group))
 

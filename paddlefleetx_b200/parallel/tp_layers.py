@@ -53,10 +53,10 @@ class ColumnParallelLinear(nn.Module):
         self.gather_output = gather_output
         self.weight = nn.Parameter(torch.empty(self.out_per_rank, in_features, dtype=dtype, device=device))
         _init_normal_sharded(self.weight, init_std, (out_features, in_features), 0, mp_group)
-        _mark(self.weight, is_distributed=self.world > 1, split_axis=0)
+        _mark(self.weight, tp_sharded=self.world > 1, split_axis=0)
         if has_bias:
             self.bias = nn.Parameter(torch.zeros(self.out_per_rank, dtype=dtype, device=device))
-            _mark(self.bias, is_distributed=self.world > 1, split_axis=0)
+            _mark(self.bias, tp_sharded=self.world > 1, split_axis=0)
         else:
             self.register_parameter("bias", None)
 
@@ -79,7 +79,7 @@ class RowParallelLinear(nn.Module):
         self.skip_bias_add = skip_bias_add
         self.weight = nn.Parameter(torch.empty(out_features, self.in_per_rank, dtype=dtype, device=device))
         _init_normal_sharded(self.weight, init_std, (out_features, in_features), 1, mp_group)
-        _mark(self.weight, is_distributed=self.world > 1, split_axis=1)
+        _mark(self.weight, tp_sharded=self.world > 1, split_axis=1)
         if has_bias:
             self.bias = nn.Parameter(torch.zeros(out_features, dtype=dtype, device=device))
         else:
@@ -111,10 +111,10 @@ class ColumnSequenceParallelLinear(nn.Module):
         self.fused_comm = fused_comm
         self.weight = nn.Parameter(torch.empty(self.out_per_rank, in_features, dtype=dtype, device=device))
         _init_normal_sharded(self.weight, init_std, (out_features, in_features), 0, mp_group)
-        _mark(self.weight, is_distributed=self.world > 1, split_axis=0)
+        _mark(self.weight, tp_sharded=self.world > 1, split_axis=0)
         if has_bias:
             self.bias = nn.Parameter(torch.zeros(self.out_per_rank, dtype=dtype, device=device))
-            _mark(self.bias, is_distributed=self.world > 1, split_axis=0)
+            _mark(self.bias, tp_sharded=self.world > 1, split_axis=0)
         else:
             self.register_parameter("bias", None)
 
@@ -141,7 +141,7 @@ class RowSequenceParallelLinear(nn.Module):
         self.skip_bias_add = skip_bias_add
         self.weight = nn.Parameter(torch.empty(out_features, self.in_per_rank, dtype=dtype, device=device))
         _init_normal_sharded(self.weight, init_std, (out_features, in_features), 1, mp_group)
-        _mark(self.weight, is_distributed=self.world > 1, split_axis=1)
+        _mark(self.weight, tp_sharded=self.world > 1, split_axis=1)
         if has_bias:
             self.bias = nn.Parameter(torch.zeros(out_features, dtype=dtype, device=device))
             # replicated param whose grad is computed from a sequence shard: needs an mp all-reduce
@@ -173,7 +173,7 @@ class VocabParallelEmbedding(nn.Module):
         self.weight = nn.Parameter(torch.empty(self.per_rank, embedding_dim, dtype=dtype, device=device))
         with torch.no_grad():
             self.weight.normal_(0.0, init_std)
-        _mark(self.weight, is_distributed=self.world > 1, split_axis=0)
+        _mark(self.weight, tp_sharded=self.world > 1, split_axis=0)
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
         if self.world == 1:

@@ -1,0 +1,118 @@
+"""Rank functions for the multi-process gloo tests (imported by name inside the spawned children)."""
+import copy
+
+import torch
+import torch.distributed as dist
+
+from helpers import build_engine, synthetic_batches, tiny_gpt_config
+
+
+def _slice(batch, rank, world):
+    n = batch[0].shape[0] // world
+    return [t[rank * n:(rank + 1) * n].contiguous() for t in batch]
+
+
+def _reference_losses_and_state(overrides, n_steps, seed=11):
+    """Single-process run of the same global batch, executed redundantly on every rank (world-1 topology)."""
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.parallel.topology import HybridCommunicateGroup
+
+    cfg = tiny_gpt_config(overrides, nranks=1)
+    env.set_hcg(HybridCommunicateGroup(world_size=1, rank=0, build_groups=False))
+    real_ws = env.world_size
+    env.world_size = lambda: 1                    # build as if single process
+    try:
+        from paddlefleetx_b200.core import EagerEngine
+        from paddlefleetx_b200.models import build_module
+
+        env.set_seed(cfg.Global.seed)
+        module = build_module(cfg)
+        init = {k: v.detach().clone() for k, v in module.model.state_dict().items()}
+        eng = EagerEngine(configs=cfg, module=module)
+        batches = synthetic_batches(cfg, n_steps, seed=seed)
+        losses = [float(eng.train_step(b)) for b in batches]
+        state = {k: v.detach().clone() for k, v in module.model.state_dict().items()}
+    finally:
+        env.world_size = real_ws
+        env.set_hcg(None)
+    return cfg, batches, losses, state, init
+
+
+def dp_sharding_matches_single(rank, world, dp, sharding, stage):
+    gb = 4
+    base = [f"Global.global_batch_size={gb}", "Global.local_batch_size=None", "Global.micro_batch_size=1"]
+    _, batches, ref_losses, ref_state, init = _reference_losses_and_state(
+        ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}"], 4)
+    cfg = tiny_gpt_config(base + [f"Distributed.dp_degree={dp}", f"Distributed.sharding.sharding_degree={sharding}",
+                                  f"Distributed.sharding.sharding_stage={stage}"], nranks=world)
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models import build_module
+
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    module = build_module(cfg)
+    module.model.load_state_dict(init)
+    eng = EagerEngine(configs=cfg, module=module)
+    dr, dw = env.get_data_world_rank(), env.get_data_world_size()
+    assert dw == dp * sharding
+    losses = []
+    for b in batches:
+        l = eng.train_step(_slice(b, dr, dw)).detach().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
+    for k, v in eng.module.model.state_dict().items():
+        assert torch.allclose(v, ref_state[k], atol=5e-5, rtol=1e-4), k
+    if sharding > 1:        # optimizer state really is sharded
+        g = eng.optimizer.groups[0]
+        assert g.meta["m"].numel() == g.numel // sharding
+
+
+def _shard_like(full: torch.Tensor, p: torch.nn.Parameter, mp_rank: int, mp: int) -> torch.Tensor:
+    if getattr(p, "tp_sharded", False):
+        return full.chunk(mp, dim=p.split_axis)[mp_rank].clone()
+    return full.clone()
+
+
+def tp_matches_single(rank, world, sequence_parallel):
+    mp = world
+    gb = 2
+    single_ov = ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}"]
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.parallel.topology import HybridCommunicateGroup
+
+    # reference model: remember its *initial* weights
+    cfg1 = tiny_gpt_config(single_ov, nranks=1)
+    env.set_hcg(HybridCommunicateGroup(world_size=1, rank=0, build_groups=False))
+    real_ws = env.world_size
+    env.world_size = lambda: 1
+    try:
+        from paddlefleetx_b200.core import EagerEngine
+        from paddlefleetx_b200.models import build_module
+
+        env.set_seed(cfg1.Global.seed)
+        module1 = build_module(cfg1)
+        init = {k: v.detach().clone() for k, v in module1.model.state_dict().items()}
+        eng1 = EagerEngine(configs=cfg1, module=module1)
+        batches = synthetic_batches(cfg1, 3, seed=21)
+        ref_losses = [float(eng1.train_step(b)) for b in batches]
+        ref_state = {k: v.detach().clone() for k, v in module1.model.state_dict().items()}
+    finally:
+        env.world_size = real_ws
+        env.set_hcg(None)
+
+    cfg = tiny_gpt_config(single_ov + [f"Distributed.mp_degree={mp}", f"Model.sequence_parallel={sequence_parallel}"], nranks=world)
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    module = build_module(cfg)
+    hcg = env.get_hcg()
+    with torch.no_grad():
+        for k, p in module.model.named_parameters():
+            p.copy_(_shard_like(init[k], p, hcg.get_model_parallel_rank(), mp))
+    eng = EagerEngine(configs=cfg, module=module)
+    losses = [float(eng.train_step(b)) for b in batches]
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 3e-4, (losses, ref_losses)
+    for k, p in module.model.named_parameters():
+        want = _shard_like(ref_state[k], p, hcg.get_model_parallel_rank(), mp)
+        assert torch.allclose(p.detach(), want, atol=1e-4, rtol=1e-3), (k, (p.detach() - want).abs().max())

@@ -1,0 +1,28 @@
+"""Multi-process correctness on CPU/gloo: layouts must reproduce the single-process loss curve and weights."""
+import pytest
+
+from dist_utils import run_distributed
+
+
+def test_dp2_sharding_stage1_matches_single():           # BASELINE.json config #1 layout (plumbing on gloo)
+    run_distributed("dist_fns:dp_sharding_matches_single", 2, 2, 1, 1)
+
+
+def test_sharding2_stage1_matches_single():
+    run_distributed("dist_fns:dp_sharding_matches_single", 2, 1, 2, 1)
+
+
+def test_sharding2_stage2_matches_single():
+    run_distributed("dist_fns:dp_sharding_matches_single", 2, 1, 2, 2)
+
+
+def test_dp2_x_sharding2_matches_single():
+    run_distributed("dist_fns:dp_sharding_matches_single", 4, 2, 2, 1)
+
+
+def test_tensor_parallel_matches_single():
+    run_distributed("dist_fns:tp_matches_single", 2, False)
+
+
+def test_sequence_parallel_matches_single():
+    run_distributed("dist_fns:tp_matches_single", 2, True)

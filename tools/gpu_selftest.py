@@ -207,13 +207,19 @@ def check_topp():
     nucleus = torch.zeros_like(probs).scatter(1, si, in_nucleus_sorted.float())
     outside = float((counts * (1 - nucleus)).sum() / counts.sum())
     emp = counts / trials
-    target = probs * nucleus
-    # mass is u*top_p truncated inverse-CDF: P(token) = p / top_p for tokens fully inside
-    tv = float((emp - target / 0.8).abs().sum(-1).mean()) / 2
+    # exact law of the sorted-prefix search: u ~ U(0, top_p); token j (sorted) wins on (cum_{j-1}, cum_j] clipped to top_p
+    lo = (cum - sp).clamp(max=0.8)
+    hi = cum.clamp(max=0.8)
+    target = torch.zeros_like(probs).scatter(1, si, (hi - lo) / 0.8)
+    tv = float((emp - target).abs().sum(-1).mean()) / 2
+    ref_counts = torch.zeros_like(counts)
+    ref_ids = torch.multinomial(target, trials, replacement=True)
+    ref_counts.scatter_add_(1, ref_ids, torch.ones_like(ref_ids, dtype=torch.float))
+    tv_ref = float((ref_counts / trials - target).abs().sum(-1).mean()) / 2
     # half / bf16 inputs run
     _, ids16 = lib.topp_sampling(probs.half(), top_ps, 1, 0)
     med, _ = _time(lambda: lib.topp_sampling(probs, top_ps, 42, 0), flush_mb=1)
-    return dict(outside_frac=outside, tv=tv, ok=outside < 2e-3 and tv < 0.12, ms=med, ids16=ids16.flatten().tolist()[:4])
+    return dict(outside_frac=outside, tv=tv, tv_ref=tv_ref, ok=outside < 2e-3 and tv < 1.3 * tv_ref + 0.01, ms=med, ids16=ids16.flatten().tolist()[:4])
 
 
 def check_rope_softmax():
