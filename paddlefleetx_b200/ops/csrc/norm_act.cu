@@ -66,8 +66,8 @@ __global__ void norm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w
 
 // --------------------------------------------------------------------------- LayerNorm / RMSNorm bwd
 // grid-stride over rows; per-thread dw/db partials live in registers and are flushed once per CTA.
-template <typename T, bool kRms>
-__global__ void norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
+template <typename T, bool kRms, int kVPT>
+__global__ void __launch_bounds__(1024) norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dx,
                                 float* __restrict__ dw_part, float* __restrict__ db_part, int rows, int cols) {
   __shared__ float scratch[33];
@@ -135,14 +135,30 @@ __global__ void norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
   }
 }
 
-// out[c] = sum_r part[r, c]   (fp32 partials -> T or fp32)
+// out[c] = sum_r part[r, c]   (fp32 partials -> T or fp32); block = 32 column lanes x 8 part lanes
 template <typename TOut>
 __global__ void reduce_partials_kernel(const float* __restrict__ part, TOut* __restrict__ out, int nparts, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float red[8][33];
+  const int lc = threadIdx.x & 31, lr = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lc;
   float s = 0.f;
-  for (int r = 0; r < nparts; ++r) s += part[(size_t)r * cols + c];
-  out[c] = from_f32<TOut>(s);
+  if (c < cols)
+    for (int r = lr; r < nparts; r += 8) s += part[(size_t)r * cols + c];
+  red[lr][lc] = s;
+  __syncthreads();
+  if (lr == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][lc];
+    out[c] = from_f32<TOut>(t);
+  }
+}
+
+static int norm_threads_vpt(int cols, int vpt) {
+  const int nvec = cols / 8;
+  int t = (nvec + vpt - 1) / vpt;
+  t = ((t + 31) / 32) * 32;
+  return t < 32 ? 32 : t;
 }
 
 static int norm_threads(int cols) {
@@ -170,21 +186,27 @@ cudaError_t norm_fwd(const void* x, const void* w, const void* b, void* y, float
                     : norm_fwd_t<__half>(x, w, b, y, mean, rstd, rows, cols, eps, rms, st);
 }
 
-int norm_bwd_num_parts(int rows, int num_sms) { int g = num_sms * 4; return rows < g ? rows : g; }
+int norm_bwd_num_parts(int rows, int num_sms) { int g = num_sms * 2; return rows < g ? rows : g; }
 
 template <typename T>
 static cudaError_t norm_bwd_t(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, void* dw,
                               void* db, float* workspace, int rows, int cols, bool rms, int num_sms, cudaStream_t st) {
-  const int threads = norm_threads(cols);
-  if (threads > 1024 || cols % 8) return cudaErrorInvalidValue;
+  if (cols % 8) return cudaErrorInvalidValue;
+  const int vpt = cols <= 16384 ? 2 : 4;       // fewer vectors per thread: the backward keeps 5 fp32 copies in registers
+  const int threads = norm_threads_vpt(cols, vpt);
+  if (threads > 1024) return cudaErrorInvalidValue;
   const int parts = norm_bwd_num_parts(rows, num_sms);
   float* dwp = workspace;
   float* dbp = workspace + (size_t)parts * cols;
-  if (rms) norm_bwd_kernel<T, true><<<parts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, nullptr, rstd, (T*)dx, dwp, dbp, rows, cols);
-  else norm_bwd_kernel<T, false><<<parts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx, dwp, dbp, rows, cols);
-  const int rt = 128, rg = (cols + rt - 1) / rt;
-  reduce_partials_kernel<T><<<rg, rt, 0, st>>>(dwp, (T*)dw, parts, cols);
-  if (!rms && db) reduce_partials_kernel<T><<<rg, rt, 0, st>>>(dbp, (T*)db, parts, cols);
+#define PFX_NB(RMS, VPT)                                                                                                        \
+  norm_bwd_kernel<T, RMS, VPT><<<parts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, RMS ? nullptr : mean, rstd, (T*)dx, dwp, \
+                                                          dbp, rows, cols)
+  if (rms) { if (vpt == 2) PFX_NB(true, 2); else PFX_NB(true, 4); }
+  else { if (vpt == 2) PFX_NB(false, 2); else PFX_NB(false, 4); }
+#undef PFX_NB
+  const int rg = (cols + 31) / 32;
+  reduce_partials_kernel<T><<<rg, 256, 0, st>>>(dwp, (T*)dw, parts, cols);
+  if (!rms && db) reduce_partials_kernel<T><<<rg, 256, 0, st>>>(dbp, (T*)db, parts, cols);
   return cudaGetLastError();
 }
 
@@ -321,15 +343,22 @@ __global__ void colsum_partial_kernel(const T* __restrict__ x, float* __restrict
   }
 }
 
-int colsum_num_parts(int rows) { int p = (rows + 255) / 256; return p < 1 ? 1 : (p > 64 ? 64 : p); }
+int colsum_num_parts(int rows) { int p = (rows + 31) / 32; return p < 1 ? 1 : (p > 256 ? 256 : p); }
+static int colsum_parts_for(int rows, int cols) {
+  const int gx = (cols / 8 + 31) / 32;
+  int p = (592 + gx - 1) / gx;                 // aim at >= 4 CTAs per SM
+  const int cap = colsum_num_parts(rows);
+  if (p > cap) p = cap;
+  return p < 1 ? 1 : p;
+}
 
 cudaError_t colsum(const void* x, void* out, float* workspace, int rows, int cols, int dtype, bool out_fp32, cudaStream_t st) {
   if (cols % 8) return cudaErrorInvalidValue;
-  const int parts = colsum_num_parts(rows);
+  const int parts = colsum_parts_for(rows, cols);
   dim3 grid((cols / 8 + 31) / 32, parts);
   if (dtype == 1) colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, workspace, rows, cols);
   else colsum_partial_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, workspace, rows, cols);
-  const int rt = 128, rg = (cols + rt - 1) / rt;
+  const int rt = 256, rg = (cols + 31) / 32;
   if (out_fp32) reduce_partials_kernel<float><<<rg, rt, 0, st>>>(workspace, (float*)out, parts, cols);
   else if (dtype == 1) reduce_partials_kernel<__nv_bfloat16><<<rg, rt, 0, st>>>(workspace, (__nv_bfloat16*)out, parts, cols);
   else reduce_partials_kernel<__half><<<rg, rt, 0, st>>>(workspace, (__half*)out, parts, cols);

@@ -90,7 +90,8 @@ class FusedAdamW:
                 cur, cur_bytes = cur + 1, 0
 
         def key_fn(p):
-            return (bucket_of[id(p)], self._decay[id(p)], bool(getattr(p, "tp_sharded", False)), bool(getattr(p, "is_expert", False)))
+            return (bucket_of[id(p)], self._decay[id(p)], bool(getattr(p, "tp_sharded", False)), bool(getattr(p, "is_expert", False)),
+                    bool(getattr(p, "pp_shared_duplicate", False)))   # [4]: tied copy on another stage, skipped in the norm
 
         params = [p for _, p in named]
         grad_dtype = torch.float32 if use_main_grad else None
@@ -267,7 +268,7 @@ class FusedAdamW:
             lib = _native.require()
             self._sq.zero_()
             for g in self.groups:
-                counted = g.key[2] or g.key[3] or mp_rank == 0
+                counted = (g.key[2] or g.key[3] or mp_rank == 0) and not g.key[4]
                 if counted and not g.key[3]:
                     lib.sumsq_(g.grad_buf[g.meta["lo"]:g.meta["hi"]], self._sq, True)
                     OF._count(2)
@@ -280,6 +281,8 @@ class FusedAdamW:
         else:
             sq = torch.zeros(1, dtype=torch.float32, device=self._dev)
             for g in self.groups:
+                if g.key[4]:
+                    continue
                 s = g.grad_buf[g.meta["lo"]:g.meta["hi"]].float().pow(2).sum()
                 if g.key[3]:
                     moe_sq = s.reshape(1) if moe_sq is None else moe_sq + s

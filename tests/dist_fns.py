@@ -116,3 +116,63 @@ def tp_matches_single(rank, world, sequence_parallel):
     for k, p in module.model.named_parameters():
         want = _shard_like(ref_state[k], p, hcg.get_model_parallel_rank(), mp)
         assert torch.allclose(p.detach(), want, atol=1e-4, rtol=1e-3), (k, (p.detach() - want).abs().max())
+
+
+def pipeline_matches_single(rank, world, pp, mp, vpp, acc):
+    """pp (x mp) pipeline with tied embeddings reproduces the single-process loss curve."""
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models import build_module
+
+    gb = acc
+    L = 4
+    common = [f"Model.num_layers={L}", "Model.use_flash_attn=False"]
+    _, batches, ref_losses, ref_state, init = _reference_losses_and_state(
+        common + ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}"], 3, seed=31)
+    ov = common + ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", "Global.micro_batch_size=1",
+                   f"Distributed.pp_degree={pp}", f"Distributed.mp_degree={mp}"]
+    if vpp > 1:
+        ov.append(f"Model.virtual_pp_degree={vpp}")
+    cfg = tiny_gpt_config(ov, nranks=world)
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    module = build_module(cfg)
+    hcg = env.get_hcg()
+    pipe = module.model
+    # map the single-model initial weights onto this stage's layers
+    stage, P, V = hcg.get_stage_id(), pp, max(vpp, 1)
+    parts = pipe.segment_parts
+
+    def src_key(global_layer_idx, sub):          # decoder layer index in the flat desc list = idx - 1
+        return f"gpt.decoder.layers.{global_layer_idx - 1}.{sub}"
+
+    with torch.no_grad():
+        for v in range(V):
+            part = v * P + stage
+            start, end = parts[part], parts[part + 1]
+            local = 0
+            for idx in range(start, end):
+                if idx == 0 or idx == L + 2:
+                    continue
+                holder = pipe._model_chunks[v][local]
+                local += 1
+                for n, p in holder.named_parameters():
+                    if idx == L + 1:
+                        full = init[f"gpt.decoder.norm.{n.split('.', 1)[1]}"]
+                    else:
+                        full = init[src_key(idx, n)]
+                    p.copy_(_shard_like(full, p, hcg.get_model_parallel_rank(), mp))
+        if "embed" in pipe.shared_layers:
+            emb = pipe.shared_layers["embed"]
+            emb.word_embeddings.weight.copy_(_shard_like(init["gpt.embeddings.word_embeddings.weight"], emb.word_embeddings.weight,
+                                                         hcg.get_model_parallel_rank(), mp))
+            emb.position_embeddings.weight.copy_(init["gpt.embeddings.position_embeddings.weight"])
+    eng = EagerEngine(configs=cfg, module=module)
+    losses = [float(eng.train_step(b)) for b in batches]
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 3e-4, (rank, losses, ref_losses)
+    # tied embedding stays identical on first and last stage
+    if "embed" in pipe.shared_layers:
+        w = pipe.shared_layers["embed"].word_embeddings.weight.detach()
+        want = _shard_like(ref_state["gpt.embeddings.word_embeddings.weight"], pipe.shared_layers["embed"].word_embeddings.weight,
+                           hcg.get_model_parallel_rank(), mp)
+        assert torch.allclose(w, want, atol=1e-4, rtol=1e-3), (w - want).abs().max()

@@ -26,3 +26,15 @@ def test_tensor_parallel_matches_single():
 
 def test_sequence_parallel_matches_single():
     run_distributed("dist_fns:tp_matches_single", 2, True)
+
+
+def test_pipeline_1f1b_pp2_matches_single():
+    run_distributed("dist_fns:pipeline_matches_single", 2, 2, 1, 1, 4)
+
+
+def test_pipeline_pp2_mp2_matches_single():
+    run_distributed("dist_fns:pipeline_matches_single", 4, 2, 2, 1, 4)
+
+
+def test_pipeline_interleaved_pp2_vpp2_matches_single():
+    run_distributed("dist_fns:pipeline_matches_single", 2, 2, 1, 2, 4)
