@@ -82,6 +82,65 @@ at::Tensor gemm(const at::Tensor& a, const at::Tensor& b, c10::optional<at::Tens
   return d;
 }
 
+// ------------------------------------------------------------------------------- fused GEMM + collectives
+// GEMM -> reduce-scatter, phase 1: every tile of a*op(b)^T goes straight to the owner rank's staging slot over NVLink.
+void gemm_rs_scatter(const at::Tensor& a, const at::Tensor& b, const std::vector<int64_t>& peer_staging, int64_t my_rank, int64_t rows_per_rank,
+                     bool a_kmajor, bool b_kmajor, int64_t config) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm_rs: bf16 CUDA operands");
+  const c10::cuda::CUDAGuard guard(a.device());
+  const int64_t M = a_kmajor ? a.size(0) : a.size(1), K = a_kmajor ? a.size(1) : a.size(0), N = b_kmajor ? b.size(0) : b.size(1);
+  const int world = (int)peer_staging.size();
+  TORCH_CHECK(world >= 2 && world <= 8 && M == rows_per_rank * world && N % 8 == 0, "gemm_rs: bad partition");
+  pfx::GemmArgs g{};
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = nullptr; g.bias = nullptr;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.lda = (int)a.stride(0); g.ldb = (int)b.stride(0); g.ldd = (int)N;
+  g.a_kmajor = a_kmajor; g.b_kmajor = b_kmajor; g.out_mode = 3; g.epilogue = pfx::EPI_NONE; g.ab_format = 1;
+  g.num_sms = num_sms(); g.config = config ? (int)config : 2;
+  for (int i = 0; i < world; ++i) g.comm.peer_out[i] = reinterpret_cast<void*>((uintptr_t)peer_staging[i]);
+  g.comm.rows_per_rank = (int)rows_per_rank; g.comm.my_rank = (int)my_rank; g.comm.world = world; g.comm.ag_world = 0;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+}
+at::Tensor slot_reduce(const at::Tensor& staging, c10::optional<at::Tensor> bias, int64_t world) {
+  PFX_CHECK_CUDA_CONTIG(staging);
+  const c10::cuda::CUDAGuard guard(staging.device());
+  const int64_t cols = staging.size(-1), rows = staging.numel() / cols / world;
+  auto out = at::empty({rows, cols}, staging.options());
+  PFX_CUDA_CHECK(pfx::slot_reduce(staging.data_ptr(), out.data_ptr(), (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr,
+                                  (size_t)rows * cols, (int)world, (int)cols, dtype_code(staging), num_sms(), cur_stream()));
+  return out;
+}
+// all-gather -> GEMM in one kernel: d[M,N] = gathered(a_local)[M,K] * b[N,K]^T (+bias).  `gathered` is this rank's symmetric
+// gather buffer (peers push their shards into it), flags / peer pointers come from the symmetric allocator.
+at::Tensor gemm_ag(const at::Tensor& a_local, const at::Tensor& b, const at::Tensor& gathered, const std::vector<int64_t>& peer_gather,
+                   const std::vector<int64_t>& peer_flags, const at::Tensor& my_flags, c10::optional<at::Tensor> bias, int64_t my_rank,
+                   int64_t chunk_rows, int64_t num_comm_ctas, int64_t epoch, bool b_kmajor, int64_t config) {
+  TORCH_CHECK(a_local.is_cuda() && a_local.is_contiguous() && a_local.scalar_type() == at::kBFloat16, "gemm_ag: a_local bf16 contiguous");
+  const c10::cuda::CUDAGuard guard(a_local.device());
+  const int world = (int)peer_gather.size();
+  const int64_t rows = a_local.size(0), K = a_local.size(1), M = rows * world, N = b_kmajor ? b.size(0) : b.size(1);
+  TORCH_CHECK(gathered.size(0) == M && gathered.size(1) == K && gathered.is_contiguous(), "gemm_ag: gathered buffer shape");
+  TORCH_CHECK(rows % chunk_rows == 0 && N % 8 == 0 && K % 8 == 0, "gemm_ag: bad shapes");
+  auto d = at::empty({M, N}, a_local.options());
+  pfx::GemmArgs g{};
+  g.a = gathered.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr();
+  g.bias = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.lda = (int)K; g.ldb = (int)b.stride(0); g.ldd = (int)N;
+  g.a_kmajor = true; g.b_kmajor = b_kmajor; g.out_mode = 0; g.epilogue = g.bias ? pfx::EPI_BIAS : pfx::EPI_NONE; g.ab_format = 1;
+  g.num_sms = num_sms(); g.config = config ? (int)config : 2;
+  for (int i = 0; i < world; ++i) {
+    g.comm.peer_gather[i] = reinterpret_cast<void*>((uintptr_t)peer_gather[i]);
+    g.comm.peer_flags[i] = reinterpret_cast<uint32_t*>((uintptr_t)peer_flags[i]);
+  }
+  g.comm.my_flags = reinterpret_cast<const uint32_t*>(my_flags.data_ptr());
+  g.comm.a_local = a_local.data_ptr();
+  g.comm.rows_per_rank = (int)rows; g.comm.chunk_rows = (int)chunk_rows; g.comm.my_rank = (int)my_rank; g.comm.world = world;
+  g.comm.ag_world = world; g.comm.num_comm_ctas = (int)num_comm_ctas; g.comm.epoch = (uint32_t)epoch;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+  return d;
+}
+
 // ------------------------------------------------------------------------------- norms
 std::vector<at::Tensor> norm_fwd(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> b, double eps, bool rms) {
   PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(w);
@@ -329,6 +388,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "paddlefleetx_b200 sm_100a kernel library";
   m.def("gemm", &gemm, py::arg("a"), py::arg("b"), py::arg("bias") = py::none(), py::arg("out") = py::none(), py::arg("a_kmajor") = true,
         py::arg("b_kmajor") = true, py::arg("epilogue") = 0, py::arg("out_mode") = 0, py::arg("config") = 0);
+  m.def("gemm_rs_scatter", &gemm_rs_scatter);
+  m.def("slot_reduce", &slot_reduce);
+  m.def("gemm_ag", &gemm_ag);
   m.def("norm_fwd", &norm_fwd);
   m.def("norm_bwd", &norm_bwd);
   m.def("bias_gelu_fwd", &bias_gelu_fwd);

@@ -103,6 +103,43 @@ cudaError_t p2p_reduce_scatter(void** peer_bufs, void* out, size_t shard_elems, 
   return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------ local slot reduce (second half of GEMM -> reduce-scatter)
+// out[i] = sum_s staging[s][i] (+ bias[col]); every slot was written by a different rank's GEMM epilogue.
+template <typename T>
+__global__ void slot_reduce_kernel(const T* __restrict__ staging, T* __restrict__ out, const T* __restrict__ bias, size_t slot_elems, int world,
+                                   int cols) {
+  const size_t nvec = slot_elems >> 3;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < world; ++s) {
+      float v[8];
+      unpack8<T>(ld_stream(reinterpret_cast<const uint4*>(staging + (size_t)s * slot_elems) + i), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+    if (bias) {
+      float b[8];
+      unpack8<T>(__ldg(reinterpret_cast<const uint4*>(bias) + (i % (size_t)(cols >> 3))), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += b[j];
+    }
+    st_stream(reinterpret_cast<uint4*>(out) + i, pack8<T>(acc));
+  }
+}
+
+cudaError_t slot_reduce(const void* staging, void* out, const void* bias, size_t slot_elems, int world, int cols, int dtype, int num_sms,
+                        cudaStream_t st) {
+  if (slot_elems % 8 || cols % 8) return cudaErrorInvalidValue;
+  const int threads = 256;
+  size_t g = (slot_elems / 8 + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms * 8;
+  const int grid = (int)(g < cap ? (g ? g : 1) : cap);
+  if (dtype == 1) slot_reduce_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>((const __nv_bfloat16*)staging, (__nv_bfloat16*)out, (const __nv_bfloat16*)bias, slot_elems, world, cols);
+  else slot_reduce_kernel<__half><<<grid, threads, 0, st>>>((const __half*)staging, (__half*)out, (const __half*)bias, slot_elems, world, cols);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ push all-gather
 __global__ void p2p_all_gather_kernel(PeerPtrs bufs, const uint4* __restrict__ src, size_t nvec, size_t dst_vec_offset, int rank, int world) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -12,6 +12,16 @@
 //   * kCG = 2 pairs two CTAs (cta_group::2): UMMA 256 x BLOCK_N x 16, each CTA stages half of B.
 //   * TMEM holds two accumulator buffers so the epilogue of tile i overlaps the mainloop of i+1.
 //
+// Fused compute+collective modes (tensor/sequence parallel linears, see parallel/fused_tp.py):
+//   * kOutMode = 3  "GEMM -> reduce-scatter": the epilogue stores each finished tile straight into the DESTINATION
+//     rank's staging buffer through its NVLink-mapped (CUDA IPC) address — slot [src_rank][row_in_shard][N] — tile
+//     by tile while the mainloop keeps the tensor cores busy; tiles for remote ranks are scheduled first.  A small
+//     reduce kernel (comm_p2p.cu) then sums the world slots.
+//   * comm.ag_world > 1  "all-gather -> GEMM": extra CTAs of the SAME kernel push this rank's A shard into every
+//     peer's gathered buffer (posted P2P stores) and raise per-chunk flags; the TMA producer of each GEMM CTA
+//     waits on the flag of the chunk it is about to load.  Local-shard tiles are issued first so the mainloop
+//     starts immediately and the transfer hides behind it.
+//
 // This is the kernel every Linear layer of the framework runs on (reference call sites L1-L5 in
 // QKV / out-proj / FFN1 / FFN2 / LM head use cuBLAS(Lt) in the reference).
 #include "pfx_ptx.cuh"
@@ -44,21 +54,62 @@ struct GemmSmem {
 
 struct TileCoord { int m_blk, n_blk; };
 
-__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks) {
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks, int m_rotate = 0) {
   const int tiles_per_group = kGroupM * num_n_blocks;
   const int group = tile / tiles_per_group;
   const int first_m = group * kGroupM;
   const int group_m = min(kGroupM, num_m_blocks - first_m);
   const int in_group = tile - group * tiles_per_group;
-  return {first_m + in_group % group_m, in_group / group_m};
+  int m = first_m + in_group % group_m;
+  if (m_rotate) { m += m_rotate; if (m >= num_m_blocks) m -= num_m_blocks; }
+  return {m, in_group / group_m};
 }
 
-// kOutMode: 0 = bf16/fp16 via TMA store, 1 = fp32 direct store, 2 = fp32 direct accumulate (D += acc)
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Communication role of the all-gather->GEMM mode: push rows [my_rank*rows_per_rank, +rows_per_rank) of A (local
+// shard, row stride K elements) into every peer's gathered buffer, chunk by chunk, then publish the chunk flag.
+__device__ void ag_push_role(const GemmComm& c, int comm_cta, int num_comm_ctas, int K) {
+  const int chunk_rows = c.chunk_rows;
+  const int chunks = c.rows_per_rank / chunk_rows;
+  const size_t vec_per_row = (size_t)K * 2 / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(c.a_local);
+  for (int ch = comm_cta; ch < chunks; ch += num_comm_ctas) {
+    const size_t v0 = (size_t)ch * chunk_rows * vec_per_row, nv = (size_t)chunk_rows * vec_per_row;
+    for (int p = 1; p < c.ag_world; ++p) {
+      const int dst = (c.my_rank + p) % c.ag_world;
+      uint4* out = reinterpret_cast<uint4*>(c.peer_gather[dst]) + (size_t)c.my_rank * c.rows_per_rank * vec_per_row + v0;
+      for (size_t i = threadIdx.x; i < nv; i += 4 * blockDim.x) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (i + u * blockDim.x < nv) r[u] = __ldg(src + v0 + i + u * blockDim.x);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (i + u * blockDim.x < nv) out[i + u * blockDim.x] = r[u];
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < c.ag_world && (int)threadIdx.x != c.my_rank)
+      st_release_sys(c.peer_flags[threadIdx.x] + c.my_rank * chunks + ch, c.epoch);
+    __syncthreads();
+  }
+}
+
+// kOutMode: 0 = bf16/fp16 via TMA store, 1 = fp32 direct store, 2 = fp32 direct accumulate (D += acc),
+//           3 = bf16 scatter into the destination rank's staging buffer over NVLink (GEMM -> reduce-scatter)
 template <int kCG, int kBlockN, bool kAK, bool kBK, int kOutMode>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_d, float* __restrict__ out_f32, const __nv_bfloat16* __restrict__ bias,
-                    int M, int N, int K, int ldd, int epilogue, uint32_t ab_format) {
+                    const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_a_local,
+                    float* __restrict__ out_f32, const __nv_bfloat16* __restrict__ bias,
+                    int M, int N, int K, int ldd, int epilogue, uint32_t ab_format, const __grid_constant__ GemmComm comm) {
   using S = GemmSmem<kCG, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kLoadN = S::kLoadN;
@@ -87,8 +138,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int num_n_blocks = (N + kBlockN - 1) / kBlockN;
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k_blocks = (K + kBlockK - 1) / kBlockK;
-  const int num_clusters = gridDim.x / kCG;
+  const int num_comm_clusters = comm.ag_world > 1 ? comm.num_comm_ctas / kCG : 0;
+  const int num_clusters = gridDim.x / kCG - num_comm_clusters;
   const int cluster_id = blockIdx.x / kCG;
+  if (cluster_id >= num_clusters) {   // ---- communication CTAs (all-gather -> GEMM mode): no TMEM, no barriers
+    ag_push_role(comm, blockIdx.x - num_clusters * kCG, num_comm_clusters * kCG, K);
+    return;
+  }
+  int m_rotate = 0;
+  if (comm.rows_per_rank > 0 && comm.world > 1) {   // start one rank "after" ourselves: remote tiles first (RS) /
+    const int blocks_per_rank = comm.rows_per_rank / kUmmaM;                 // local tiles first (AG)
+    m_rotate = ((comm.my_rank + (kOutMode == 3 ? 1 : 0)) % comm.world) * blocks_per_rank;
+  }
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmap_a);
@@ -114,7 +175,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks);
+        const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks, m_rotate);
         const int m_idx = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
         const int n_idx = tc.n_blk * kBlockN + (int)cta_rank * kLoadN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -125,7 +186,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const int k_idx = kb * kBlockK;
           if (kCG == 1 || is_leader) mbar_arrive_expect_tx(fb, S::kStageBytes * kCG);
           if constexpr (kAK) {
-            if (kCG == 2) tma_load_2d_2sm(&tmap_a, fb, sa, k_idx, m_idx); else tma_load_2d(&tmap_a, fb, sa, k_idx, m_idx);
+            if (comm.ag_world > 1) {
+              const int src_rank = m_idx / comm.rows_per_rank;
+              if (src_rank == comm.my_rank) {
+                const int lm = m_idx - src_rank * comm.rows_per_rank;
+                if (kCG == 2) tma_load_2d_2sm(&tmap_a_local, fb, sa, k_idx, lm); else tma_load_2d(&tmap_a_local, fb, sa, k_idx, lm);
+              } else {
+                if (kb == 0) {   // first touch of this m-block: wait until the owner has pushed the chunk
+                  const int chunks = comm.rows_per_rank / comm.chunk_rows;
+                  const uint32_t* fl = comm.my_flags + src_rank * chunks + (m_idx - src_rank * comm.rows_per_rank) / comm.chunk_rows;
+                  const long long t0 = clock64();
+                  while (ld_acquire_sys(fl) != comm.epoch) {
+                    if (clock64() - t0 > 20000000000ll) { printf("pfx: all-gather flag timeout\n"); __trap(); }
+                  }
+                }
+                if (kCG == 2) tma_load_2d_2sm(&tmap_a, fb, sa, k_idx, m_idx); else tma_load_2d(&tmap_a, fb, sa, k_idx, m_idx);
+              }
+            } else {
+              if (kCG == 2) tma_load_2d_2sm(&tmap_a, fb, sa, k_idx, m_idx); else tma_load_2d(&tmap_a, fb, sa, k_idx, m_idx);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < kBlockM / 64; ++j) {
@@ -189,7 +268,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t store_iter = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks);
+      const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks, m_rotate);
       const int row0 = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
       const int col_tile = tc.n_blk * kBlockN;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -258,6 +337,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tma_store_commit();
           }
           ++store_iter;
+        } else if constexpr (kOutMode == 3) {
+          const int grow = row0 + (int)row_in_cta;
+          if (grow < M) {
+            const int dst_rank = grow / comm.rows_per_rank;
+            const int lrow = grow - dst_rank * comm.rows_per_rank;
+            __nv_bfloat16* dstp = reinterpret_cast<__nv_bfloat16*>(comm.peer_out[dst_rank]) +
+                                  ((size_t)comm.my_rank * comm.rows_per_rank + lrow) * ldd + col0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+              if (col0 + i < N) {
+                uint4 o;
+                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                *reinterpret_cast<uint4*>(dstp + i) = o;      // 16 B posted store, peer memory when dst_rank != my_rank
+              }
+            }
+          }
         } else {
           const int grow = row0 + (int)row_in_cta;
           if (grow < M) {
@@ -335,7 +431,13 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   else     ok &= make_tmap_2d(&tb, g.b, 2, dt, g.N, g.K, (uint64_t)g.ldb * 2, 64, kBlockK);
   if (kOutMode == 0) ok &= make_tmap_2d(&td, g.d, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
   else td = ta;
+  CUtensorMap tal = ta;
+  if (g.comm.ag_world > 1) {
+    if (!kAK) return cudaErrorInvalidValue;
+    ok &= make_tmap_2d(&tal, g.comm.a_local, 2, dt, g.K, g.comm.rows_per_rank, (uint64_t)g.K * 2, kBlockK, kBlockM);
+  }
   if (!ok) return cudaErrorInvalidValue;
+  if (g.comm.rows_per_rank > 0 && (g.comm.rows_per_rank % (kBlockM * kCG)) != 0) return cudaErrorInvalidValue;
 
   auto kern = gemm_tcgen05_kernel<kCG, kBlockN, kAK, kBK, kOutMode>;
   static bool attr_set = false;
@@ -347,9 +449,11 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   const int num_m_blocks = (g.M + kBlockM * kCG - 1) / (kBlockM * kCG);
   const int num_n_blocks = (g.N + kBlockN - 1) / kBlockN;
   const int tiles = num_m_blocks * num_n_blocks;
-  int clusters = g.num_sms / kCG;
+  const int comm_clusters = g.comm.ag_world > 1 ? g.comm.num_comm_ctas / kCG : 0;
+  int clusters = g.num_sms / kCG - comm_clusters;
   if (clusters > tiles) clusters = tiles;
   if (clusters < 1) clusters = 1;
+  clusters += comm_clusters;
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * kCG);
@@ -360,8 +464,8 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kCG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
-                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tal, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
+                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm);
 }
 
 template <int kCG, int kBlockN, int kOutMode>
@@ -377,7 +481,8 @@ static cudaError_t launch_out(const GemmArgs& g, cudaStream_t s) {
   switch (g.out_mode) {
     case 0: return launch_major<kCG, kBlockN, 0>(g, s);
     case 1: return launch_major<kCG, kBlockN, 1>(g, s);
-    default: return launch_major<kCG, kBlockN, 2>(g, s);
+    case 2: return launch_major<kCG, kBlockN, 2>(g, s);
+    default: return launch_major<kCG, kBlockN, 3>(g, s);
   }
 }
 

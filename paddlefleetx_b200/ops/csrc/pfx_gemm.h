@@ -8,6 +8,21 @@ namespace pfx {
 
 enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_GELU = 3 };
 
+// Peer-memory communication descriptor of the fused GEMM+collective modes (passed to the kernel by value).
+struct GemmComm {
+  void* peer_out[8];          // mode 3: per destination rank, staging base [world][rows_per_rank][ldd] (bf16)
+  void* peer_gather[8];       // AG mode: per rank, gathered A buffer [world * rows_per_rank][K]
+  uint32_t* peer_flags[8];    // AG mode: per rank, chunk flags [world][chunks]
+  const uint32_t* my_flags;   // AG mode: this rank's flags (local)
+  const void* a_local;        // AG mode: this rank's A shard [rows_per_rank][K]
+  int rows_per_rank;          // rows of the M dimension owned by one rank (0 = no comm)
+  int chunk_rows;             // AG mode: rows per flag
+  int my_rank, world;
+  int ag_world;               // > 1 enables the all-gather -> GEMM mode
+  int num_comm_ctas;          // AG mode: CTAs reserved for the push role
+  uint32_t epoch;             // AG mode: value that marks "chunk present" for this call
+};
+
 struct GemmArgs {
   const void* a;     // K-major: [M, K] row-major (lda = row stride, elements); MN-major: [K, M]
   const void* b;     // K-major: [N, K] row-major;                              MN-major: [K, N]
@@ -16,11 +31,12 @@ struct GemmArgs {
   int M, N, K;
   int lda, ldb, ldd;
   bool a_kmajor, b_kmajor;
-  int out_mode;      // 0 = same dtype as inputs (TMA store), 1 = fp32 store, 2 = fp32 accumulate
+  int out_mode;      // 0 = same dtype as inputs (TMA store), 1 = fp32 store, 2 = fp32 accumulate, 3 = peer scatter (GEMM->RS)
   int epilogue;      // Epilogue
   int ab_format;     // 0 = fp16, 1 = bf16
   int num_sms;
   int config;        // 0 = auto
+  GemmComm comm;     // zero-initialised = plain GEMM
 };
 
 cudaError_t gemm_tcgen05(const GemmArgs& args, cudaStream_t stream);

@@ -42,6 +42,8 @@ cudaError_t causal_softmax(const void* a, const void* b, void* out, size_t batch
 cudaError_t p2p_barrier(uint32_t** signal_pads, int rank, int world, uint32_t epoch_slot, cudaStream_t st);
 cudaError_t p2p_reduce_scatter(void** peer_bufs, void* out, size_t shard_elems, int rank, int world, int in_dtype, int out_dtype,
                                bool accumulate, float scale, int num_sms, cudaStream_t st);
+cudaError_t slot_reduce(const void* staging, void* out, const void* bias, size_t slot_elems, int world, int cols, int dtype, int num_sms,
+                        cudaStream_t st);
 cudaError_t p2p_all_gather(void** peer_bufs, const void* src, size_t shard_elems, int rank, int world, int dtype, int num_sms,
                            cudaStream_t st);
 cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, float* master, const void* grad, float* m, float* v, size_t n,

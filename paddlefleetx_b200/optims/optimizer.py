@@ -200,8 +200,8 @@ class FusedAdamW:
 
     # ------------------------------------------------------------------ gradient sync (DP all-reduce / ZeRO reduce-scatter)
     def _sync_group_grads(self, g: FlatGroup, async_op: bool = False) -> None:
-        if g.meta["synced"] or self.replicas == 1:
-            g.meta["synced"] = True
+        if g.meta["synced"] or self.replicas == 1 or g.key[3]:
+            g.meta["synced"] = True      # expert parameters are private to their rank: no replica reduction
             return
         lo, hi = g.meta["lo"], g.meta["hi"]
         stream_ctx = None

@@ -226,6 +226,8 @@ def broadcast_params(module: torch.nn.Module, group, src_rank: int, skip_distrib
     for t in list(module.parameters()) + list(module.buffers()):
         if skip_distributed and getattr(t, "tp_sharded", False):
             continue
+        if getattr(t, "no_sync", False):          # expert parameters differ per rank by design
+            continue
         dist.broadcast(t.data, src=src_rank, group=_pg(group))
 
 

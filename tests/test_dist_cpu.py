@@ -38,3 +38,12 @@ def test_pipeline_pp2_mp2_matches_single():
 
 def test_pipeline_interleaved_pp2_vpp2_matches_single():
     run_distributed("dist_fns:pipeline_matches_single", 2, 2, 1, 2, 4)
+
+
+@pytest.mark.parametrize("gate", ["naive", "gshard"])
+def test_moe_expert_parallel_matches_single(gate):
+    run_distributed("dist_fns:moe_ep_matches_single", 2, gate)
+
+
+def test_moe_module_trains_with_expert_parallel():
+    run_distributed("dist_fns:moe_module_trains", 2)
