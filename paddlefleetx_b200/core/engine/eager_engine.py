@@ -166,11 +166,17 @@ class EagerEngine(BasicEngine):
             else:
                 lr_cfg_clean = lr_cfg
             self._lr_scheduler = build_lr_scheduler(lr_cfg_clean) if lr is None else lr
+            if self._sharding_stage == 3 and self._sharding_degree > 1 and self._pp_degree == 1 and env.world_size() > 1:
+                from ...distributed.apis.strategy import broadcast_initial_parameters
+                from ...parallel.sharding import GroupShardedStage3
+
+                broadcast_initial_parameters(self._module.model, self._hcg)
+                self._module.model = GroupShardedStage3(self._module.model, self._hcg)
             self._optimizer = build_optimizer(configs.Optimizer, self._module.model, self._lr_scheduler, hcg=self._hcg,
                                               dist_config=d, amp_config=amp) if optimizer is None else optimizer
 
         # distributed wrappers
-        if env.world_size() > 1:
+        if env.world_size() > 1 and not hasattr(self._module.model, "optimizer_named_parameters"):
             self._module.model, self._optimizer, self._scaler = wrap_with_fleet(d, self._module.model, self._optimizer, self._scaler)
 
         self._load_recovery = {"step": 0, "epoch": 0, "rng_state": None}
@@ -322,7 +328,9 @@ class EagerEngine(BasicEngine):
                 loss_bw = self._scaler.scale(loss) if (self._scaler is not None and self._amp_dtype == "float16") else loss
                 if n > 1:
                     loss_bw = loss_bw / n
-                self._module.backward(loss_bw)
+                bw_ctx = self._module.model.backward_phase() if hasattr(self._module.model, "backward_phase") else _Null()
+                with bw_ctx:
+                    self._module.backward(loss_bw)
             d = loss.detach()
             total = d if total is None else total + d
         if self._mp_degree > 1 and self._configs.Model.get("sequence_parallel", False):
@@ -335,6 +343,8 @@ class EagerEngine(BasicEngine):
             self._scaler.update()
         else:
             self._optimizer.step()
+        if hasattr(self._module.model, "after_optimizer_step"):
+            self._module.model.after_optimizer_step()
 
     # ---------------------------------------------------------------------------------------- evaluate / predict
     @torch.no_grad()

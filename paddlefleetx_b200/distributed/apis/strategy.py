@@ -38,8 +38,4 @@ def wrap_with_fleet(dist_config, model, optimizer=None, scaler=None):
         from ...parallel.pipeline import PipelineParallel
 
         model = PipelineParallel(model, hcg, env.get_strategy())
-    elif stage == 3 and dist_config.sharding.sharding_degree > 1:
-        from ...parallel.sharding import GroupShardedStage3
-
-        model = GroupShardedStage3(model, hcg)
     return model, optimizer, scaler

@@ -52,30 +52,45 @@ cudaError_t p2p_barrier(uint32_t** signal_pads, int rank, int world, uint32_t sl
 
 // ------------------------------------------------------------------ pull reduce-scatter
 template <typename TIn, typename TOut, int kWorld>
-__global__ void p2p_reduce_scatter_kernel(PeerPtrs bufs, TOut* __restrict__ out, size_t shard_elems, int rank, bool accumulate, float scale) {
+__global__ void __launch_bounds__(512) p2p_reduce_scatter_kernel(PeerPtrs bufs, TOut* __restrict__ out, size_t shard_elems, int rank, bool accumulate,
+                                                                 float scale) {
+  constexpr int kUnroll = (kWorld <= 2) ? 4 : 2;     // independent 16 B loads per peer in flight per thread
   const size_t nvec = shard_elems >> 3;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    uint4 raw[kWorld];
+  const uint4* src[kWorld];
 #pragma unroll
-    for (int p = 0; p < kWorld; ++p) {   // issue all peer loads before consuming: kWorld NVLink requests in flight per thread
-      const int src = (rank + p) % kWorld;
-      raw[p] = ld_stream(reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(bufs.p[src]) + (size_t)rank * shard_elems) + i);
+  for (int p = 0; p < kWorld; ++p)
+    src[p] = reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(bufs.p[(rank + p) % kWorld]) + (size_t)rank * shard_elems);
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < nvec; i0 += stride * kUnroll) {
+    uint4 raw[kUnroll][kWorld];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i < nvec) {
+#pragma unroll
+        for (int p = 0; p < kWorld; ++p) raw[u][p] = ld_stream(src[p] + i);
+      }
     }
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int p = 0; p < kWorld; ++p) {   // fixed (rank-relative) order -> bitwise identical sums on every run
-      float v[8];
-      unpack8<TIn>(raw[p], v);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t i = i0 + u * stride;
+      if (i >= nvec) continue;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += v[j];
-    }
-    TOut* o = out + i * 8;
+      for (int p = 0; p < kWorld; ++p) {   // fixed (rank-relative) order -> bitwise identical sums on every run
+        float v[8];
+        unpack8<TIn>(raw[u][p], v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float r = acc[j] * scale;
-      if (accumulate) r += to_f32<TOut>(o[j]);
-      o[j] = from_f32<TOut>(r);
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+      TOut* o = out + i * 8;
+      if (accumulate) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = from_f32<TOut>(acc[j] * scale + to_f32<TOut>(o[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = from_f32<TOut>(acc[j] * scale);
+      }
     }
   }
 }

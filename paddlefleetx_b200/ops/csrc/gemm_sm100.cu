@@ -53,6 +53,7 @@ struct GemmSmem {
 };
 
 struct TileCoord { int m_blk, n_blk; };
+struct alignas(64) PeerMaps { CUtensorMap m[8]; };   // per-destination-rank staging tensor maps (GEMM -> reduce-scatter)
 
 __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m_blocks, int num_n_blocks, int m_rotate = 0) {
   const int tiles_per_group = kGroupM * num_n_blocks;
@@ -109,7 +110,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_a_local,
                     float* __restrict__ out_f32, const __nv_bfloat16* __restrict__ bias,
-                    int M, int N, int K, int ldd, int epilogue, uint32_t ab_format, const __grid_constant__ GemmComm comm) {
+                    int M, int N, int K, int ldd, int epilogue, uint32_t ab_format, const __grid_constant__ GemmComm comm,
+                    const __grid_constant__ PeerMaps peer_maps) {
   using S = GemmSmem<kCG, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kLoadN = S::kLoadN;
@@ -155,6 +157,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     if (kOutMode == 0) tma_prefetch_desc(&tmap_d);
+    if (kOutMode == 3) { for (int i = 0; i < comm.world; ++i) tma_prefetch_desc(&peer_maps.m[i]); }
   }
   if (warp == 1 && elect_one()) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -196,7 +199,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                   const int chunks = comm.rows_per_rank / comm.chunk_rows;
                   const uint32_t* fl = comm.my_flags + src_rank * chunks + (m_idx - src_rank * comm.rows_per_rank) / comm.chunk_rows;
                   const long long t0 = clock64();
-                  while (ld_acquire_sys(fl) != comm.epoch) {
+                  while ((int32_t)(ld_acquire_sys(fl) - comm.epoch) < 0) {   // epochs only grow
                     if (clock64() - t0 > 20000000000ll) { printf("pfx: all-gather flag timeout\n"); __trap(); }
                   }
                 }
@@ -308,7 +311,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
         }
-        if constexpr (kOutMode == 0) {
+        if constexpr (kOutMode == 0 || kOutMode == 3) {
           const uint32_t buf = store_iter & 1u;
           if (store_iter >= 2) {
             if (is_store_thread) tma_store_wait_read<1>();
@@ -333,27 +336,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (is_store_thread) {
-            if (col0 < N && row0 < M) tma_store_2d(&tmap_d, smem_epi + buf * S::kEpiBytes, col0, row0);
+            if (col0 < N && row0 < M) {
+              if constexpr (kOutMode == 3) {
+                // tile -> owner rank's staging slot [my_rank] through its NVLink-mapped address (TMA store to peer memory)
+                const int dst_rank = row0 / comm.rows_per_rank;
+                tma_store_2d(&peer_maps.m[dst_rank], smem_epi + buf * S::kEpiBytes, col0,
+                             comm.my_rank * comm.rows_per_rank + (row0 - dst_rank * comm.rows_per_rank));
+              } else {
+                tma_store_2d(&tmap_d, smem_epi + buf * S::kEpiBytes, col0, row0);
+              }
+            }
             tma_store_commit();
           }
           ++store_iter;
-        } else if constexpr (kOutMode == 3) {
-          const int grow = row0 + (int)row_in_cta;
-          if (grow < M) {
-            const int dst_rank = grow / comm.rows_per_rank;
-            const int lrow = grow - dst_rank * comm.rows_per_rank;
-            __nv_bfloat16* dstp = reinterpret_cast<__nv_bfloat16*>(comm.peer_out[dst_rank]) +
-                                  ((size_t)comm.my_rank * comm.rows_per_rank + lrow) * ldd + col0;
-#pragma unroll
-            for (int i = 0; i < 64; i += 8) {
-              if (col0 + i < N) {
-                uint4 o;
-                o.x = pack_bf16x2(v[i], v[i + 1]); o.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                o.z = pack_bf16x2(v[i + 4], v[i + 5]); o.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(dstp + i) = o;      // 16 B posted store, peer memory when dst_rank != my_rank
-              }
-            }
-          }
         } else {
           const int grow = row0 + (int)row_in_cta;
           if (grow < M) {
@@ -374,7 +369,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
-    if (kOutMode == 0 && is_store_thread) tma_store_wait<0>();
+    if ((kOutMode == 0 || kOutMode == 3) && is_store_thread) tma_store_wait<0>();
   }
 
   // ------------------------------------------------------------------ teardown
@@ -431,6 +426,13 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   else     ok &= make_tmap_2d(&tb, g.b, 2, dt, g.N, g.K, (uint64_t)g.ldb * 2, 64, kBlockK);
   if (kOutMode == 0) ok &= make_tmap_2d(&td, g.d, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
   else td = ta;
+  PeerMaps pm;
+  for (int i = 0; i < 8; ++i) pm.m[i] = ta;
+  if (kOutMode == 3) {
+    for (int i = 0; i < g.comm.world; ++i)
+      ok &= make_tmap_2d(&pm.m[i], g.comm.peer_out[i], 2, dt, g.N, (uint64_t)g.comm.world * g.comm.rows_per_rank, (uint64_t)g.ldd * 2,
+                         kStoreCols, kBlockM);
+  }
   CUtensorMap tal = ta;
   if (g.comm.ag_world > 1) {
     if (!kAK) return cudaErrorInvalidValue;
@@ -465,7 +467,7 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   attrs[0].val.clusterDim.x = kCG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tal, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
-                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm);
+                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm, pm);
 }
 
 template <int kCG, int kBlockN, int kOutMode>

@@ -65,7 +65,11 @@ def build_optimizer(config, model: torch.nn.Module, lr_scheduler=None, hcg=None,
                      bucket_mb=sh.get("bucket_mb", 512))
     if amp_config is not None:
         extra["use_main_grad"] = bool(amp_config.get("use_main_grad", False))
-    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    if hasattr(model, "optimizer_named_parameters"):            # ZeRO-3 wrapper: optimise the shards
+        named = model.optimizer_named_parameters()
+        extra.update(params_are_shards=True, apply_decay_param_fun=model.shard_decay_fn())
+    else:
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
     cls = _lookup(_opt, name)
     opt = cls(learning_rate=lr_scheduler if lr_scheduler is not None else cfg.pop("learning_rate", 1e-3),
               named_parameters=named, grad_clip=grad_clip, hcg=hcg, **{**cfg, **extra})

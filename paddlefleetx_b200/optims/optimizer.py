@@ -48,7 +48,7 @@ class FusedAdamW:
                  weight_decay: float = 0.01, grad_clip=None, multi_precision: bool = False, tensor_fusion: bool = True,
                  named_parameters=None, apply_decay_param_fun: Optional[Callable] = None, hcg=None, sharding_stage: int = 1,
                  use_main_grad: bool = False, bucket_mb: int = 512, reduce_overlap: bool = False, broadcast_overlap: bool = False,
-                 use_p2p: bool = False, lazy_init: bool = False, **unused):
+                 use_p2p: bool = False, lazy_init: bool = False, params_are_shards: bool = False, **unused):
         self._learning_rate = learning_rate
         self.beta1, self.beta2, self.eps, self.weight_decay = float(beta1), float(beta2), float(epsilon), float(weight_decay)
         self.grad_clip = grad_clip
@@ -73,7 +73,11 @@ class FusedAdamW:
         self.sh_world = C.group_size(self.sh_group)
         self.sh_rank = C.group_rank(self.sh_group)
         self.dp_world = C.group_size(self.dp_group)
-        self.replicas = self.sh_world * self.dp_world
+        self.replicas = self.sh_world * self.dp_world          # data replicas the gradient is averaged over
+        if params_are_shards:
+            # ZeRO-3: the "parameters" handed in are already per-rank shards (parallel/sharding.py): no further
+            # partitioning or reduce-scatter here, only the dp all-reduce, the cross-group norm and the update
+            self.sh_world, self.sh_rank = 1, 0
         self.use_p2p = bool(use_p2p) and self.sh_world > 1 and named[0][1].is_cuda
 
         # ---- bucket assignment (reverse registration order: last layers finish backward first)
@@ -216,7 +220,7 @@ class FusedAdamW:
                     # fp32-accumulated sum back into slice r of its own bucket (nobody else reads that slice)
                     self._symm.barrier()
                     _native.require().p2p_reduce_scatter(g.meta["peer_grads"], g.grad_buf[lo:hi], self.sh_rank,
-                                                         1 if g.grad_buf.dtype == torch.bfloat16 else 0, False, 1.0, 32)
+                                                         1 if g.grad_buf.dtype == torch.bfloat16 else 0, False, 1.0, 128)
                     self._symm.barrier()
                     OF._count(3)
                 else:
@@ -301,7 +305,7 @@ class FusedAdamW:
                 if self.use_p2p and g.meta["has_master"]:
                     lp_code = 1 if g.param_buf.dtype == torch.bfloat16 else 0
                     lib.adamw_p2p_broadcast_(g.meta["peer_params"], lo, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr,
-                                             self.beta1, self.beta2, self.eps, wd, self._step_count, self._gscale, self._found_inf, lp_code, 32)
+                                             self.beta1, self.beta2, self.eps, wd, self._step_count, self._gscale, self._found_inf, lp_code, 296)
                 else:
                     lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
                                     wd, self._step_count, self._gscale, self._found_inf)

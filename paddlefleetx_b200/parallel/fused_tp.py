@@ -27,26 +27,37 @@ _bufs: Dict[Tuple, dict] = {}
 
 
 def _ag_buffers(group, rows: int, K: int, dtype):
+    """Two alternating gather buffers (+ flag arrays) per shape: a peer may already push call k+1 while this rank still
+    reads call k; it can never be two calls ahead because its kernel k needs this rank's pushes of call k to finish."""
     key = ("ag", id(group), rows, K, dtype)
     if key not in _bufs:
         sm = get_allocator(group)
         chunk = 256
-        gathered = sm.empty((rows * group.nranks, K), dtype)
-        flags = sm.alloc_tensor(group.nranks * max(rows // chunk, 1) + 64, torch.int32)
-        flags.zero_()
+        sets = []
+        for _ in range(2):
+            gathered = sm.empty((rows * group.nranks, K), dtype)
+            flags = sm.alloc_tensor(group.nranks * max(rows // chunk, 1) + 64, torch.int32)
+            flags.zero_()
+            sets.append(dict(gathered=gathered, flags=flags, peer_gather=sm.peer_ptrs(gathered), peer_flags=sm.peer_ptrs(flags)))
         torch.cuda.synchronize()
         sm.barrier()
-        _bufs[key] = dict(sm=sm, gathered=gathered, flags=flags, peer_gather=sm.peer_ptrs(gathered), peer_flags=sm.peer_ptrs(flags),
-                          chunk=chunk)
+        _bufs[key] = dict(sm=sm, sets=sets, chunk=chunk, calls=0)
     return _bufs[key]
 
 
 def _rs_buffers(group, rows_per_rank: int, N: int, dtype):
+    """Two alternating staging buffers: the single barrier between scatter and reduce of call k also proves that every
+    rank finished reducing call k-1, so slot set (k+1) % 2 is free when call k+1 starts."""
     key = ("rs", id(group), rows_per_rank, N, dtype)
     if key not in _bufs:
         sm = get_allocator(group)
-        staging = sm.empty((group.nranks, rows_per_rank, N), dtype)
-        _bufs[key] = dict(sm=sm, staging=staging, peer_staging=sm.peer_ptrs(staging))
+        sets = []
+        for _ in range(2):
+            staging = sm.empty((group.nranks, rows_per_rank, N), dtype)
+            sets.append(dict(staging=staging, peer_staging=sm.peer_ptrs(staging)))
+        torch.cuda.synchronize()
+        sm.barrier()
+        _bufs[key] = dict(sm=sm, sets=sets, calls=0)
     return _bufs[key]
 
 
@@ -60,14 +71,15 @@ def ag_gemm(x_shard: torch.Tensor, w: torch.Tensor, bias, group, b_kmajor: bool 
     lib = _native.require()
     rows, K = x_shard.shape
     b = _ag_buffers(group, rows, K, x_shard.dtype)
-    b["sm"].barrier()                        # peers finished reading the gather buffer of the previous call
+    cur = b["sets"][b["calls"] % 2]
+    b["calls"] += 1
     _epoch[0] += 1
-    y = lib.gemm_ag(x_shard.contiguous(), w, b["gathered"], b["peer_gather"], b["peer_flags"], b["flags"], bias, group.rank, b["chunk"],
-                    _NUM_COMM_CTAS, _epoch[0], b_kmajor, 0)
+    y = lib.gemm_ag(x_shard.contiguous(), w, cur["gathered"], cur["peer_gather"], cur["peer_flags"], cur["flags"], bias, group.rank,
+                    b["chunk"], _NUM_COMM_CTAS, _epoch[0], b_kmajor, 0)
     OF._count()
     # the local shard is consumed straight from x_shard by the kernel; complete the gathered buffer for later (wgrad) use
-    b["gathered"][group.rank * rows:(group.rank + 1) * rows].copy_(x_shard)
-    return y, b["gathered"]
+    cur["gathered"][group.rank * rows:(group.rank + 1) * rows].copy_(x_shard)
+    return y, cur["gathered"]
 
 
 def gemm_rs(a: torch.Tensor, w: torch.Tensor, group, a_kmajor: bool = True, b_kmajor: bool = True, bias=None) -> torch.Tensor:
@@ -77,11 +89,12 @@ def gemm_rs(a: torch.Tensor, w: torch.Tensor, group, a_kmajor: bool = True, b_km
     N = w.shape[0] if b_kmajor else w.shape[1]
     rpr = M // group.nranks
     b = _rs_buffers(group, rpr, N, a.dtype)
-    b["sm"].barrier()                        # staging slots of the previous call have been reduced everywhere
-    lib.gemm_rs_scatter(a, w, b["peer_staging"], group.rank, rpr, a_kmajor, b_kmajor, 0)
-    b["sm"].barrier()                        # every rank's tiles have landed
-    out = lib.slot_reduce(b["staging"], bias, group.nranks)
-    OF._count(4)
+    cur = b["sets"][b["calls"] % 2]
+    b["calls"] += 1
+    lib.gemm_rs_scatter(a, w, cur["peer_staging"], group.rank, rpr, a_kmajor, b_kmajor, 0)
+    b["sm"].barrier()                        # every rank's tiles have landed (and everyone is done with the other slot set)
+    out = lib.slot_reduce(cur["staging"], bias, group.nranks)
+    OF._count(3)
     return out
 
 

@@ -64,7 +64,7 @@ def dp_sharding_matches_single(rank, world, dp, sharding, stage):
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
     for k, v in eng.module.model.state_dict().items():
         assert torch.allclose(v, ref_state[k], atol=5e-5, rtol=1e-4), k
-    if sharding > 1:        # optimizer state really is sharded
+    if sharding > 1 and stage < 3:        # optimizer state really is sharded
         g = eng.optimizer.groups[0]
         assert g.meta["m"].numel() == g.numel // sharding
 

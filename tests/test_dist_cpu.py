@@ -47,3 +47,11 @@ def test_moe_expert_parallel_matches_single(gate):
 
 def test_moe_module_trains_with_expert_parallel():
     run_distributed("dist_fns:moe_module_trains", 2)
+
+
+def test_sharding2_stage3_matches_single():
+    run_distributed("dist_fns:dp_sharding_matches_single", 2, 1, 2, 3)
+
+
+def test_stage3_with_recompute_and_dp():
+    run_distributed("dist_fns:dp_sharding_matches_single", 4, 2, 2, 3)

@@ -66,12 +66,12 @@ def main():
     ref = torch.empty(n, dtype=torch.bfloat16, device="cuda")
     dist.reduce_scatter_tensor(ref, local.clone())
     out = torch.empty(n, dtype=torch.float32, device="cuda")
-    lib.p2p_reduce_scatter(ptrs, out, rank, 1, False, 1.0, 32)
+    lib.p2p_reduce_scatter(ptrs, out, rank, 1, False, 1.0, 128)
     torch.cuda.synchronize(); sm.barrier()
     report("p2p_reduce_scatter", err=relerr(out, ref), ok=relerr(out, ref) < 1e-2)
 
     def rs_p2p():
-        sm.barrier(); lib.p2p_reduce_scatter(ptrs, out, rank, 1, False, 1.0, 32); sm.barrier()
+        sm.barrier(); lib.p2p_reduce_scatter(ptrs, out, rank, 1, False, 1.0, 128); sm.barrier()
     t_p2p = timed(rs_p2p)
     scratch = local.clone()
     t_nccl = timed(lambda: dist.reduce_scatter_tensor(ref, scratch))
