@@ -317,7 +317,10 @@ class EagerEngine(BasicEngine):
 
     def _model_forward_backward(self, batch):
         n = self._accumulate_steps
-        micro_batches = _split_micro(batch, n)
+        if n > 1 and isinstance(batch, (list, tuple)) and len(batch) == n and all(isinstance(b, (list, tuple)) for b in batch):
+            micro_batches = list(batch)          # collate already produced per-micro-batch lists (ErnieCollateData)
+        else:
+            micro_batches = _split_micro(batch, n)
         total = None
         for i, mb in enumerate(micro_batches):
             last = i == n - 1

@@ -1,0 +1,158 @@
+"""Byte-level BPE tokenizer for GPT (GPT-2 vocabulary format: ``vocab.json`` + ``merges.txt``).
+
+The reference tokenizer (ppfleetx/data/tokenizers/gpt_tokenizer.py:97-819) downloads ``gpt2-vocab.json`` /
+``gpt2-merges.txt`` on first use; this box is offline, so ``from_pretrained`` takes a *local directory* (or the
+``PFX_GPT_VOCAB_DIR`` environment variable, or ``~/.cache/ppfleetx/<name>``) and raises a clear error otherwise.
+``GPTTokenizer.byte_fallback()`` builds a 256-symbol byte vocabulary (+ ``<|endoftext|>``) that needs no files — handy
+for tests and smoke runs.  Pre-training itself never needs a tokenizer (``eos_id`` is a dataset option).
+"""
+from __future__ import annotations
+
+import json
+import os
+from functools import lru_cache
+from typing import Dict, List, Optional, Tuple
+
+import regex as re
+
+
+@lru_cache()
+def bytes_to_unicode() -> Dict[int, str]:
+    keep = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAC + 1)) + list(range(0xAE, 0xFF + 1))
+    chars, extra = keep[:], 0
+    for b in range(256):
+        if b not in keep:
+            keep.append(b)
+            chars.append(256 + extra)
+            extra += 1
+    return dict(zip(keep, (chr(c) for c in chars)))
+
+
+_SPLIT = re.compile(r"""'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+""")
+
+
+class GPTTokenizer:
+    eos_token = "<|endoftext|>"
+
+    def __init__(self, vocab: Dict[str, int], merges: List[Tuple[str, str]], errors: str = "replace", max_len: Optional[int] = None,
+                 pad_token: Optional[str] = None):
+        self.encoder = dict(vocab)
+        self.decoder = {v: k for k, v in self.encoder.items()}
+        self.bpe_ranks = {tuple(m): i for i, m in enumerate(merges)}
+        self.byte_encoder = bytes_to_unicode()
+        self.byte_decoder = {v: k for k, v in self.byte_encoder.items()}
+        self.errors = errors
+        self.max_len = max_len or int(1e12)
+        self._cache: Dict[str, List[str]] = {}
+        self.eos_token_id = self.encoder.get(self.eos_token, len(self.encoder) - 1)
+        self.bos_token_id = self.eos_token_id
+        self.pad_token_id = self.encoder.get(pad_token, self.eos_token_id) if pad_token else self.eos_token_id
+        self.padding_side = "left"
+
+    # ---------------------------------------------------------------- construction
+    @classmethod
+    def from_pretrained(cls, name_or_dir: str = "gpt2", **kw) -> "GPTTokenizer":
+        cands = [name_or_dir, os.environ.get("PFX_GPT_VOCAB_DIR", ""), os.path.expanduser(os.path.join("~/.cache/ppfleetx", name_or_dir))]
+        for d in cands:
+            if d and os.path.isdir(d):
+                for vname, mname in (("vocab.json", "merges.txt"), ("gpt2-vocab.json", "gpt2-merges.txt")):
+                    vp, mp = os.path.join(d, vname), os.path.join(d, mname)
+                    if os.path.isfile(vp) and os.path.isfile(mp):
+                        return cls.from_files(vp, mp, **kw)
+        raise FileNotFoundError(
+            f"GPT vocabulary for {name_or_dir!r} not found locally (looked in {[c for c in cands if c]}). This machine is offline: "
+            "place vocab.json + merges.txt in a directory and pass it (or set PFX_GPT_VOCAB_DIR), or use GPTTokenizer.byte_fallback().")
+
+    @classmethod
+    def from_files(cls, vocab_file: str, merges_file: str, **kw) -> "GPTTokenizer":
+        with open(vocab_file, encoding="utf-8") as f:
+            vocab = json.load(f)
+        with open(merges_file, encoding="utf-8") as f:
+            lines = f.read().split("\n")
+        merges = [tuple(l.split()) for l in lines[1:] if l and not l.startswith("#") and len(l.split()) == 2]
+        return cls(vocab, merges, **kw)
+
+    @classmethod
+    def byte_fallback(cls, **kw) -> "GPTTokenizer":
+        b2u = bytes_to_unicode()
+        vocab = {b2u[i]: i for i in range(256)}
+        vocab[cls.eos_token] = 256
+        return cls(vocab, [], **kw)
+
+    # ---------------------------------------------------------------- BPE
+    def _bpe(self, token: str) -> List[str]:
+        if token in self._cache:
+            return self._cache[token]
+        word = list(token)
+        while len(word) > 1:
+            pairs = [(self.bpe_ranks.get((a, b), 1 << 60), i) for i, (a, b) in enumerate(zip(word, word[1:]))]
+            rank, _ = min(pairs)
+            if rank == 1 << 60:
+                break
+            first, second = self._pair_of_rank(word, rank)
+            merged, i = [], 0
+            while i < len(word):
+                if i < len(word) - 1 and word[i] == first and word[i + 1] == second:
+                    merged.append(first + second)
+                    i += 2
+                else:
+                    merged.append(word[i])
+                    i += 1
+            word = merged
+        self._cache[token] = word
+        return word
+
+    def _pair_of_rank(self, word: List[str], rank: int) -> Tuple[str, str]:
+        for a, b in zip(word, word[1:]):
+            if self.bpe_ranks.get((a, b)) == rank:
+                return a, b
+        raise KeyError(rank)
+
+    def tokenize(self, text: str) -> List[str]:
+        out: List[str] = []
+        for piece in _SPLIT.findall(text):
+            mapped = "".join(self.byte_encoder[b] for b in piece.encode("utf-8"))
+            out.extend(self._bpe(mapped))
+        return out
+
+    def convert_tokens_to_ids(self, tokens) -> List[int]:
+        if isinstance(tokens, str):
+            return self.encoder[tokens]
+        return [self.encoder[t] for t in tokens]
+
+    def convert_ids_to_tokens(self, ids, skip_special_tokens: bool = False) -> List[str]:
+        return [self.decoder[int(i)] for i in ids if not (skip_special_tokens and int(i) == self.eos_token_id)]
+
+    def encode(self, text: str) -> List[int]:
+        return self.convert_tokens_to_ids(self.tokenize(text))
+
+    def decode(self, ids, skip_special_tokens: bool = False) -> str:
+        text = "".join(self.convert_ids_to_tokens(ids, skip_special_tokens))
+        return bytearray(self.byte_decoder[c] for c in text if c in self.byte_decoder).decode("utf-8", errors=self.errors)
+
+    convert_ids_to_string = decode
+
+    def __len__(self) -> int:
+        return len(self.encoder)
+
+    @property
+    def vocab_size(self) -> int:
+        return len(self.encoder)
+
+    def __call__(self, text, padding: bool = False, max_length: Optional[int] = None, return_attention_mask: bool = True, **unused):
+        texts = [text] if isinstance(text, str) else list(text)
+        ids = [self.encode(t)[: max_length or self.max_len] for t in texts]
+        if padding:
+            mx = max(len(i) for i in ids)
+            if self.padding_side == "left":
+                masks = [[0] * (mx - len(i)) + [1] * len(i) for i in ids]
+                ids = [[self.pad_token_id] * (mx - len(i)) + i for i in ids]
+            else:
+                masks = [[1] * len(i) + [0] * (mx - len(i)) for i in ids]
+                ids = [i + [self.pad_token_id] * (mx - len(i)) for i in ids]
+        else:
+            masks = [[1] * len(i) for i in ids]
+        out = {"input_ids": ids if not isinstance(text, str) else ids[0]}
+        if return_attention_mask:
+            out["attention_mask"] = masks if not isinstance(text, str) else masks[0]
+        return out

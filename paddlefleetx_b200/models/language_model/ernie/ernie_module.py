@@ -1,0 +1,160 @@
+"""ERNIE task modules (reference ernie/ernie_module.py:44-382): ``ErnieModule`` (MLM + SOP pre-training on the
+6-field batch ``input_ids, segment_ids, input_mask, masked_lm_positions, masked_lm_labels, next_sentence_labels``) and
+``ErnieSeqClsModule`` (sequence classification fine-tune).  ``*Auto`` names map to the same eager classes."""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+from ....core.module.basic_module import BasicModule
+from ....distributed.apis import env
+from ....utils.log import logger
+from ..language_module import _device, _param_dtype, process_optim_configs
+from . import model as E
+
+_KEYS = ("vocab_size", "hidden_size", "num_hidden_layers", "num_layers", "num_attention_heads", "ffn_hidden_size", "intermediate_size",
+         "hidden_act", "hidden_dropout_prob", "attention_probs_dropout_prob", "max_position_embeddings", "type_vocab_size",
+         "task_type_vocab_size", "task_id", "use_task_id", "initializer_range", "pad_token_id", "use_recompute", "use_flash_attn")
+
+
+def get_model_size(l, h, v, s) -> float:
+    p = 12 * l * h * h * (1 + 13 / (12 * h) + (v + s) / (12 * l * h))
+    logger.info("Model Size: {:.2f} B".format(p / 1e9))
+    return p
+
+
+def process_data_configs(config) -> None:
+    g, eng = config.Global, config.Engine
+    eval_freq = eng.eval_freq if eng.eval_freq and eng.eval_freq > 0 else max(eng.max_steps, 1)
+    n = {"Train": g.global_batch_size * eng.max_steps, "Eval": g.global_batch_size * (eng.max_steps // eval_freq + 1) * eng.eval_iters,
+         "Test": g.global_batch_size * eng.test_iters}
+    for mode in ("Train", "Eval", "Test"):
+        if mode in config.get("Data", {}):
+            ds = config.Data[mode].dataset
+            ds.setdefault("num_samples", n[mode])
+            ds["mode"] = mode
+            ds.setdefault("seed", g.seed)
+            ds.setdefault("binary_head", g.get("binary_head", True))
+            if "sampler" in config.Data[mode]:
+                config.Data[mode].sampler["batch_size"] = g.local_batch_size
+            col = config.Data[mode].get("loader", {}).get("collate_fn")
+            if isinstance(col, dict) and col.get("name") == "ErnieCollateData":
+                col["micro_batch_size"] = g.micro_batch_size
+
+
+class ErnieModule(BasicModule):
+    def __init__(self, configs):
+        self.nranks = env.world_size()
+        self.binary_head = bool(configs.Global.get("binary_head", True))
+        super().__init__(configs)
+        self.loss_fn = self.get_loss_fn()
+
+    def process_configs(self, configs):
+        process_data_configs(configs)
+        m = configs.Model
+        if m.get("ffn_hidden_size") is None and m.get("intermediate_size") is None:
+            m["ffn_hidden_size"] = 4 * m["hidden_size"]
+        process_optim_configs(configs)
+        return configs
+
+    def _kwargs(self):
+        return {k: self.configs.Model[k] for k in _KEYS if k in self.configs.Model and self.configs.Model[k] is not None}
+
+    def get_model(self):
+        cfg, d = self.configs, self.configs.Distributed
+        hcg = env.get_hcg()
+        mp_group = hcg.get_model_parallel_group() if d.mp_degree > 1 else None
+        kw = self._kwargs()
+        unit = 128 * d.mp_degree
+        kw["vocab_size"] = (kw.get("vocab_size", 40000) + unit - 1) // unit * unit
+        cfg.Model["vocab_size"] = kw["vocab_size"]
+        l = kw.get("num_layers") or kw.get("num_hidden_layers", 12)
+        get_model_size(l, kw["hidden_size"], kw["vocab_size"], kw.get("max_position_embeddings", 512))
+        dtype, device = _param_dtype(cfg), _device(cfg)
+        if d.pp_degree > 1:
+            from .pipe import ErnieForPretrainingPipe
+
+            return ErnieForPretrainingPipe(hcg=hcg, mp_group=mp_group, binary_head=self.binary_head, dtype=dtype, device=device, **kw)
+        ernie = E.ErnieModel(mp_group=mp_group, dtype=dtype, device=device, **kw)
+        return E.ErnieForPretraining(ernie, kw["vocab_size"], kw.get("hidden_act", "gelu"), self.binary_head)
+
+    def get_loss_fn(self):
+        d = self.configs.Distributed
+        if d.pp_degree > 1:
+            return None
+        hcg = env.get_hcg()
+        return E.ErniePretrainingCriterion(self.binary_head, hcg.get_model_parallel_group() if d.mp_degree > 1 else None)
+
+    def pretreating_batch(self, batch):
+        if self.configs.Distributed.pp_degree > 1:
+            ids, seg, mask, pos, labels, nsp = batch
+            return [(ids, seg, mask), (pos, labels, nsp)]
+        return batch
+
+    def forward(self, tokens):
+        return self.model(tokens)
+
+    def training_step(self, batch):
+        input_ids, segment_ids, input_mask, masked_lm_positions, masked_lm_labels, next_sentence_labels = batch
+        scores, rel = self.model(input_ids, segment_ids, None, input_mask, masked_lm_positions)
+        out = self.loss_fn(scores, rel, masked_lm_labels, next_sentence_labels if self.binary_head else None)
+        if isinstance(out, tuple):
+            self._last_parts = (out[1].detach(), out[2].detach())
+            return out[0]
+        return out
+
+    def training_step_end(self, log_dict):
+        speed = 1.0 / log_dict["train_cost"]
+        gbs = self.configs.Global.global_batch_size
+        seq = self.configs.Data.Train.dataset.get("max_seq_len", self.configs.Data.Train.dataset.get("max_seq_length", 512))
+        logger.train("[train] epoch: %d, batch: %d, loss: %.9f, avg_batch_cost: %.5f sec, speed: %.2f step/s, ips_total: %.0f tokens/s, "
+                     "ips: %.0f tokens/s, learning rate: %.5e"
+                     % (log_dict["epoch"], log_dict["batch"], log_dict["loss"], log_dict["train_cost"], speed, speed * gbs * seq,
+                        speed * gbs * seq / max(env.get_data_world_size(), 1), log_dict["lr"]))
+
+    def validation_step(self, batch):
+        return self.training_step(batch)
+
+    def validation_step_end(self, log_dict):
+        logger.eval("[eval] epoch: %d, batch: %d, loss: %.9f, avg_eval_cost: %.5f sec, speed: %.2f step/s"
+                    % (log_dict["epoch"], log_dict["batch"], log_dict["loss"], log_dict["eval_cost"], 1.0 / log_dict["eval_cost"]))
+
+    def test_step(self, batch):
+        return self.training_step(batch)
+
+    def test_step_end(self, log_dict):
+        logger.eval("[test] epoch: %d, batch: %d, loss: %.9f, avg_test_cost: %.5f sec, speed: %.2f step/s"
+                    % (log_dict["epoch"], log_dict["batch"], log_dict["loss"], log_dict["test_cost"], 1.0 / log_dict["test_cost"]))
+
+    def training_epoch_end(self, log_dict):
+        logger.info("[Training] epoch: %d, total time: %.5f sec" % (log_dict["epoch"], log_dict["train_cost"]))
+
+    def input_spec(self):
+        return [dict(shape=[None, None], name="input_ids", dtype="int64"), dict(shape=[None, None], name="token_type_ids", dtype="int64")]
+
+
+class ErnieSeqClsModule(ErnieModule):
+    def process_configs(self, configs):
+        process_optim_configs(configs)
+        return configs
+
+    def get_model(self):
+        cfg = self.configs
+        kw = self._kwargs()
+        ernie = E.ErnieModel(dtype=_param_dtype(cfg), device=_device(cfg), **kw)
+        return E.ErnieForSequenceClassification(ernie, int(cfg.Model.get("num_classes", 2)), cfg.Model.get("classifier_dropout"))
+
+    def get_loss_fn(self):
+        return lambda logits, y: torch.nn.functional.cross_entropy(logits.float(), y.long().reshape(-1))
+
+    def training_step(self, batch):
+        if isinstance(batch, dict):
+            ids, seg, labels = batch["input_ids"], batch.get("token_type_ids"), batch["labels"]
+        else:
+            ids, seg, labels = batch[0], batch[1] if len(batch) > 2 else None, batch[-1]
+        return self.loss_fn(self.model(ids, seg), labels)
+
+
+ErnieModuleAuto = ErnieModule
+ErnieSeqClsModuleAuto = ErnieSeqClsModule

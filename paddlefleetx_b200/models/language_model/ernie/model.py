@@ -1,0 +1,270 @@
+"""ERNIE: bidirectional encoder with MLM + sentence-order heads (single card, tensor parallel, pipeline).
+
+Reference: ppfleetx/models/language_model/ernie/dygraph/{single_model.py:34-765, hybrid_model.py:40-992} and
+ernie/layers/*.  Kept: word / position / token-type / task embeddings, post-LN encoder (``normalize_before`` switch),
+tanh pooler, MLM transform (dense + act + LN) with a decoder tied to the word embedding, SOP head, masked-position
+gather before the MLM head, ``ignore_index = -1`` criterion, sequence-classification head.
+
+Beyond the reference (needed for BASELINE config #3, ERNIE-10B mp4 + ZeRO-3): the MLM decoder is vocabulary-parallel
+and the loss uses the vocab-parallel CE kernel (the reference leaves both replicated — SURVEY §2.7); attention runs the
+fused flash path with a padding mask.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ....ops import attention as ATT
+from ....ops import functional as OF
+from ....parallel import comm_ops as C
+from ....parallel.recompute import recompute
+from ....parallel.rng import get_rng_state_tracker
+from ....parallel.tp_layers import (ColumnParallelLinear, ParallelCrossEntropy, RowParallelLinear, VocabParallelEmbedding, parallel_matmul)
+from ..gpt.model import LayerNorm
+
+_ACT = {"gelu": lambda x: F.gelu(x, approximate="none"), "relu": F.relu, "tanh": torch.tanh}
+
+
+class ErnieEmbeddings(nn.Module):
+    def __init__(self, vocab_size, hidden, hidden_dropout=0.1, max_position=512, type_vocab_size=2, task_type_vocab_size=3, task_id=0,
+                 use_task_id=False, init_std=0.02, mp_group=None, dtype=None, device=None):
+        super().__init__()
+        kw = dict(dtype=dtype, device=device)
+        self.word_embeddings = VocabParallelEmbedding(vocab_size, hidden, mp_group, init_std, dtype, device)
+        self.position_embeddings = nn.Embedding(max_position, hidden, **kw)
+        self.token_type_embeddings = nn.Embedding(type_vocab_size, hidden, **kw)
+        self.use_task_id, self.task_id = use_task_id, task_id
+        if use_task_id:
+            self.task_type_embeddings = nn.Embedding(task_type_vocab_size, hidden, **kw)
+        for e in (self.position_embeddings, self.token_type_embeddings, getattr(self, "task_type_embeddings", None)):
+            if e is not None:
+                with torch.no_grad():
+                    e.weight.normal_(0.0, init_std)
+        self.layer_norm = LayerNorm(hidden, 1e-12, False, dtype, device)
+        self.dropout_p = hidden_dropout
+
+    def forward(self, input_ids, token_type_ids=None, position_ids=None, task_type_ids=None):
+        if position_ids is None:
+            position_ids = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0).expand_as(input_ids)
+        if token_type_ids is None:
+            token_type_ids = torch.zeros_like(input_ids)
+        x = self.word_embeddings(input_ids) + self.position_embeddings(position_ids) + self.token_type_embeddings(token_type_ids)
+        if self.use_task_id:
+            if task_type_ids is None:
+                task_type_ids = torch.full_like(input_ids, self.task_id)
+            x = x + self.task_type_embeddings(task_type_ids)
+        return OF.dropout(self.layer_norm(x), self.dropout_p, self.training, "global_seed")
+
+
+class ErnieSelfAttention(nn.Module):
+    """Separate q/k/v column-parallel projections like the reference hybrid model (no fused QKV), row-parallel output."""
+
+    def __init__(self, hidden, heads, attn_dropout, mp_group=None, init_std=0.02, dtype=None, device=None, use_flash_attn=True):
+        super().__init__()
+        self.heads, self.head_dim = heads, hidden // heads
+        self.local_heads = heads // C.group_size(mp_group)
+        kw = dict(mp_group=mp_group, init_std=init_std, dtype=dtype, device=device)
+        self.q_proj = ColumnParallelLinear(hidden, hidden, gather_output=False, **kw)
+        self.k_proj = ColumnParallelLinear(hidden, hidden, gather_output=False, **kw)
+        self.v_proj = ColumnParallelLinear(hidden, hidden, gather_output=False, **kw)
+        self.out_proj = RowParallelLinear(hidden, hidden, input_is_parallel=True, **kw)
+        self.attn_dropout = attn_dropout
+        self.use_flash_attn = use_flash_attn
+
+    def forward(self, x, attn_mask=None):
+        b, s, _ = x.shape
+        q, k, v = (p(x).view(b, s, self.local_heads, self.head_dim) for p in (self.q_proj, self.k_proj, self.v_proj))
+        p = self.attn_dropout if self.training else 0.0
+        scale = self.head_dim ** -0.5
+        if self.use_flash_attn:
+            m = None if attn_mask is None else attn_mask.to(q.dtype)
+            if p > 0:
+                with get_rng_state_tracker().rng_state("local_seed"):
+                    o = ATT.attention(q, k, v, causal=False, dropout_p=p, scale=scale, attn_mask=m)
+            else:
+                o = ATT.attention(q, k, v, causal=False, dropout_p=0.0, scale=scale, attn_mask=m)
+        else:
+            o = ATT.core_attention(q, k, v, scale, p, self.training, attn_mask=attn_mask, causal=False)
+        return self.out_proj(o.reshape(b, s, self.local_heads * self.head_dim))
+
+
+class TransformerEncoderLayer(nn.Module):
+    def __init__(self, hidden, heads, ffn, dropout=0.1, activation="gelu", attn_dropout=None, act_dropout=None, normalize_before=False,
+                 mp_group=None, init_std=0.02, dtype=None, device=None, use_flash_attn=True):
+        super().__init__()
+        self.normalize_before = normalize_before
+        self.self_attn = ErnieSelfAttention(hidden, heads, dropout if attn_dropout is None else attn_dropout, mp_group, init_std, dtype, device,
+                                            use_flash_attn)
+        kw = dict(mp_group=mp_group, init_std=init_std, dtype=dtype, device=device)
+        self.linear1 = ColumnParallelLinear(hidden, ffn, gather_output=False, **kw)
+        self.linear2 = RowParallelLinear(ffn, hidden, input_is_parallel=True, **kw)
+        self.norm1 = LayerNorm(hidden, 1e-12, False, dtype, device)
+        self.norm2 = LayerNorm(hidden, 1e-12, False, dtype, device)
+        self.dropout_p = dropout
+        self.act_dropout_p = dropout if act_dropout is None else act_dropout
+        self.activation = activation
+
+    def forward(self, x, attn_mask=None):
+        res = x
+        if self.normalize_before:
+            x = self.norm1(x)
+        x = res + OF.dropout(self.self_attn(x, attn_mask), self.dropout_p, self.training, "global_seed")
+        if not self.normalize_before:
+            x = self.norm1(x)
+        res = x
+        if self.normalize_before:
+            x = self.norm2(x)
+        h = _ACT[self.activation](self.linear1(x))
+        h = OF.dropout(h, self.act_dropout_p, self.training, "global_seed")
+        x = res + OF.dropout(self.linear2(h), self.dropout_p, self.training, "global_seed")
+        if not self.normalize_before:
+            x = self.norm2(x)
+        return x
+
+
+class TransformerEncoder(nn.Module):
+    def __init__(self, layers: List[nn.Module], norm: Optional[nn.Module] = None, use_recompute: bool = False):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.norm = norm
+        self.use_recompute = use_recompute
+
+    def forward(self, x, attn_mask=None):
+        for layer in self.layers:
+            if self.use_recompute and self.training:
+                x = recompute(layer, x, attn_mask)
+            else:
+                x = layer(x, attn_mask)
+        return x if self.norm is None else self.norm(x)
+
+
+class ErniePooler(nn.Module):
+    def __init__(self, hidden, init_std=0.02, dtype=None, device=None):
+        super().__init__()
+        self.dense = nn.Linear(hidden, hidden, dtype=dtype, device=device)
+        with torch.no_grad():
+            self.dense.weight.normal_(0.0, init_std); self.dense.bias.zero_()
+
+    def forward(self, hidden_states):
+        return torch.tanh(self.dense(hidden_states[:, 0]))
+
+
+class ErnieModel(nn.Module):
+    def __init__(self, vocab_size=40000, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, ffn_hidden_size=None,
+                 intermediate_size=None, hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
+                 max_position_embeddings=512, type_vocab_size=2, task_type_vocab_size=3, task_id=0, use_task_id=False,
+                 initializer_range=0.02, pad_token_id=0, use_recompute=False, mp_group=None, use_flash_attn=True, dtype=None, device=None,
+                 num_layers=None, **unused):
+        super().__init__()
+        num_hidden_layers = num_layers or num_hidden_layers
+        ffn = ffn_hidden_size or intermediate_size or 4 * hidden_size
+        self.pad_token_id, self.initializer_range, self.hidden_size, self.mp_group = pad_token_id, initializer_range, hidden_size, mp_group
+        self.embeddings = ErnieEmbeddings(vocab_size, hidden_size, hidden_dropout_prob, max_position_embeddings, type_vocab_size,
+                                          task_type_vocab_size, task_id, use_task_id, initializer_range, mp_group, dtype, device)
+        layers = [TransformerEncoderLayer(hidden_size, num_attention_heads, ffn, hidden_dropout_prob, hidden_act, attention_probs_dropout_prob,
+                                          0, False, mp_group, initializer_range, dtype, device, use_flash_attn)
+                  for _ in range(num_hidden_layers)]
+        self.encoder = TransformerEncoder(layers, None, use_recompute)
+        self.pooler = ErniePooler(hidden_size, initializer_range, dtype, device)
+
+    def forward(self, input_ids, token_type_ids=None, position_ids=None, attention_mask=None, task_type_ids=None):
+        if attention_mask is None:
+            pad = (input_ids == self.pad_token_id)
+            attention_mask = pad[:, None, None, :].to(self.pooler.dense.weight.dtype) * -1e4
+        elif attention_mask.dim() == 2:
+            attention_mask = (1.0 - attention_mask[:, None, None, :].to(self.pooler.dense.weight.dtype)) * -1e4
+        x = self.embeddings(input_ids, token_type_ids, position_ids, task_type_ids)
+        seq = self.encoder(x, attention_mask)
+        return seq, self.pooler(seq)
+
+
+class ErnieLMPredictionHead(nn.Module):
+    def __init__(self, hidden, vocab_size, activation="gelu", embedding_weights: Optional[nn.Parameter] = None, mp_group=None, init_std=0.02,
+                 dtype=None, device=None):
+        super().__init__()
+        self.transform = nn.Linear(hidden, hidden, dtype=dtype, device=device)
+        with torch.no_grad():
+            self.transform.weight.normal_(0.0, init_std); self.transform.bias.zero_()
+        self.activation = activation
+        self.layer_norm = LayerNorm(hidden, 1e-12, False, dtype, device)
+        self.mp_group = mp_group
+        world = C.group_size(mp_group)
+        self.decoder_weight = embedding_weights if embedding_weights is not None else nn.Parameter(
+            torch.empty(vocab_size // world, hidden, dtype=dtype, device=device).normal_(0.0, init_std))
+        self.decoder_bias = nn.Parameter(torch.zeros(vocab_size // world, dtype=dtype, device=device))
+        self.decoder_bias.tp_sharded = world > 1
+        self.decoder_bias.split_axis = 0
+
+    def forward(self, hidden_states, masked_positions=None):
+        if masked_positions is not None:
+            hidden_states = hidden_states.reshape(-1, hidden_states.shape[-1]).index_select(0, masked_positions.reshape(-1).long())
+        h = self.layer_norm(_ACT[self.activation](self.transform(hidden_states)))
+        return parallel_matmul(h, self.decoder_weight, self.mp_group, parallel_output=True) + self.decoder_bias
+
+
+class ErniePretrainingHeads(nn.Module):
+    def __init__(self, hidden, vocab_size, activation, embedding_weights=None, mp_group=None, init_std=0.02, binary_head=True, dtype=None,
+                 device=None):
+        super().__init__()
+        self.predictions = ErnieLMPredictionHead(hidden, vocab_size, activation, embedding_weights, mp_group, init_std, dtype, device)
+        self.seq_relationship = nn.Linear(hidden, 2, dtype=dtype, device=device) if binary_head else None
+
+    def forward(self, sequence_output, pooled_output, masked_positions=None):
+        scores = self.predictions(sequence_output, masked_positions)
+        rel = self.seq_relationship(pooled_output) if self.seq_relationship is not None else None
+        return scores, rel
+
+
+class ErnieForPretraining(nn.Module):
+    def __init__(self, ernie: ErnieModel, vocab_size: int, hidden_act: str = "gelu", binary_head: bool = True):
+        super().__init__()
+        self.ernie = ernie
+        p = ernie.pooler.dense.weight
+        self.cls = ErniePretrainingHeads(ernie.hidden_size, vocab_size, hidden_act, ernie.embeddings.word_embeddings.weight, ernie.mp_group,
+                                         ernie.initializer_range, binary_head, p.dtype, p.device)
+
+    def forward(self, input_ids, token_type_ids=None, position_ids=None, attention_mask=None, masked_positions=None):
+        seq, pooled = self.ernie(input_ids, token_type_ids, position_ids, attention_mask)
+        return self.cls(seq, pooled, masked_positions)
+
+
+ErnieForPretrainingHybrid = ErnieForPretraining
+ErnieModelHybrid = ErnieModel
+
+
+class ErniePretrainingCriterion(nn.Module):
+    """MLM loss (mean over labels != -1, vocab-parallel CE) + optional SOP loss."""
+
+    def __init__(self, with_nsp_loss: bool = True, mp_group=None):
+        super().__init__()
+        self.with_nsp_loss = with_nsp_loss
+        self.ce = ParallelCrossEntropy(mp_group)
+
+    def forward(self, prediction_scores, seq_relationship_score, masked_lm_labels, next_sentence_labels=None):
+        labels = masked_lm_labels.reshape(-1).long()
+        valid = labels >= 0
+        per_tok = self.ce(prediction_scores.reshape(-1, prediction_scores.shape[-1]).contiguous(), labels.clamp(min=0))
+        mlm = (per_tok * valid.float()).sum() / valid.float().sum().clamp(min=1.0)
+        if not self.with_nsp_loss or seq_relationship_score is None or next_sentence_labels is None:
+            return mlm
+        sop = F.cross_entropy(seq_relationship_score.float(), next_sentence_labels.reshape(-1).long())
+        return mlm + sop, mlm, sop
+
+
+class ErnieForSequenceClassification(nn.Module):
+    def __init__(self, ernie: ErnieModel, num_classes: int = 2, dropout: Optional[float] = None):
+        super().__init__()
+        self.ernie = ernie
+        p = ernie.pooler.dense.weight
+        self.dropout_p = 0.1 if dropout is None else dropout
+        self.classifier = nn.Linear(ernie.hidden_size, num_classes, dtype=p.dtype, device=p.device)
+        with torch.no_grad():
+            self.classifier.weight.normal_(0.0, ernie.initializer_range); self.classifier.bias.zero_()
+
+    def forward(self, input_ids, token_type_ids=None, position_ids=None, attention_mask=None):
+        _, pooled = self.ernie(input_ids, token_type_ids, position_ids, attention_mask)
+        return self.classifier(OF.dropout(pooled, self.dropout_p, self.training, "global_seed"))

@@ -117,7 +117,10 @@ class MultiHeadAttention(nn.Module):
     def _core(self, q, k, v, attn_mask):
         scale = 1.0 / math.sqrt(self.head_dim)
         p = self.attn_dropout if self.training else 0.0
-        if self.use_flash_attn and attn_mask is None:
+        if self.use_flash_attn:
+            if attn_mask is not None:
+                m = attn_mask if attn_mask.dtype == torch.bool else attn_mask.to(q.dtype)
+                return ATT.attention(q, k, v, causal=False, dropout_p=p, scale=scale, attn_mask=m)
             if p > 0:
                 with get_rng_state_tracker().rng_state("local_seed"):
                     return ATT.attention(q, k, v, causal=True, dropout_p=p, scale=scale)
