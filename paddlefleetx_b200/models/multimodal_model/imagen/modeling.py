@@ -1,0 +1,198 @@
+"""``ImagenModel`` — cascaded continuous-time Gaussian diffusion (reference multimodal_model/imagen/modeling.py:36-1026,
+utils.py:26-489): cosine / linear log-SNR schedules, ``q_sample``, noise / x0 / v objectives, conditioning dropout for
+classifier-free guidance, low-resolution noise augmentation for the SR stages, dynamic thresholding and ancestral sampling;
+``ImagenCriterion`` = per-sample mean loss weighted by ``(k + exp(log_snr))^-gamma`` (p2 weighting)."""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import unet as U
+
+
+def log_snr_cosine(t, s: float = 0.008):
+    return -torch.log(torch.clamp(torch.cos((t + s) / (1 + s) * math.pi * 0.5) ** -2 - 1, min=1e-5))
+
+
+def log_snr_linear(t):
+    return -torch.log(torch.expm1(1e-4 + 10 * t ** 2))
+
+
+class GaussianDiffusionContinuousTimes(nn.Module):
+    def __init__(self, noise_schedule: str = "cosine", timesteps: int = 1000):
+        super().__init__()
+        self.log_snr = log_snr_cosine if noise_schedule == "cosine" else log_snr_linear
+        self.num_timesteps = timesteps
+
+    def get_times(self, batch, noise_level, device):
+        return torch.full((batch,), noise_level, device=device, dtype=torch.float32)
+
+    def sample_random_times(self, batch, device):
+        return torch.rand(batch, device=device)
+
+    def get_sampling_timesteps(self, batch, device):
+        times = torch.linspace(1.0, 0.0, self.num_timesteps + 1, device=device)
+        times = times[None].expand(batch, -1)
+        return list(zip(times[:, :-1].unbind(1), times[:, 1:].unbind(1)))
+
+    @staticmethod
+    def alpha_sigma(log_snr):
+        return torch.sqrt(torch.sigmoid(log_snr)), torch.sqrt(torch.sigmoid(-log_snr))
+
+    def q_sample(self, x0, t, noise=None):
+        noise = torch.randn_like(x0) if noise is None else noise
+        ls = self.log_snr(t).view(-1, 1, 1, 1)
+        a, s = self.alpha_sigma(ls)
+        return a * x0 + s * noise, ls.view(-1), a, s
+
+    def q_posterior(self, x0, xt, t, t_next):
+        ls, ln = self.log_snr(t).view(-1, 1, 1, 1), self.log_snr(t_next).view(-1, 1, 1, 1)
+        c = -torch.expm1(ls - ln)
+        a, s = self.alpha_sigma(ls)
+        an, sn = self.alpha_sigma(ln)
+        mean = an * (xt * (1 - c) / a + c * x0)
+        var = sn ** 2 * c
+        return mean, var, torch.log(var.clamp(min=1e-20))
+
+    def predict_start_from_noise(self, xt, t, noise):
+        a, s = self.alpha_sigma(self.log_snr(t).view(-1, 1, 1, 1))
+        return (xt - s * noise) / a.clamp(min=1e-8)
+
+    def predict_start_from_v(self, xt, t, v):
+        a, s = self.alpha_sigma(self.log_snr(t).view(-1, 1, 1, 1))
+        return a * xt - s * v
+
+    def calculate_v(self, x0, t, noise):
+        a, s = self.alpha_sigma(self.log_snr(t).view(-1, 1, 1, 1))
+        return a * noise - s * x0
+
+
+def resize_image_to(img, size):
+    return img if img.shape[-1] == size else F.interpolate(img, size=(size, size), mode="nearest" if size < img.shape[-1] else "bilinear",
+                                                           **({} if size < img.shape[-1] else {"align_corners": False}))
+
+
+class ImagenModel(nn.Module):
+    def __init__(self, unets: Sequence, image_sizes: Sequence[int] = (64,), text_encoder_name: Optional[str] = None, text_embed_dim: int = 1024,
+                 in_chans: int = 3, timesteps: int = 1000, cond_drop_prob: float = 0.1, noise_schedules="cosine", pred_objectives="noise",
+                 lowres_noise_schedule: str = "linear", lowres_sample_noise_level: float = 0.2, dynamic_thresholding: bool = True,
+                 dynamic_thresholding_percentile: float = 0.95, p2_loss_weight_gamma: float = 0.5, p2_loss_weight_k: float = 1.0,
+                 unet_number: int = 1, text_encoder=None, **unused):
+        super().__init__()
+        self.unets = nn.ModuleList([u if isinstance(u, nn.Module) else getattr(U, u["name"])(**{k: v for k, v in u.items() if k != "name"},
+                                                                                             text_embed_dim=text_embed_dim) for u in unets])
+        n = len(self.unets)
+        self.image_sizes = list(image_sizes)
+        ns = [noise_schedules] * n if isinstance(noise_schedules, str) else list(noise_schedules)
+        self.noise_schedulers = nn.ModuleList([GaussianDiffusionContinuousTimes(s, timesteps) for s in ns])
+        self.lowres_noise_schedule = GaussianDiffusionContinuousTimes(lowres_noise_schedule)
+        self.pred_objectives = [pred_objectives] * n if isinstance(pred_objectives, str) else list(pred_objectives)
+        self.cond_drop_prob, self.lowres_sample_noise_level = cond_drop_prob, lowres_sample_noise_level
+        self.dynamic_thresholding, self.dt_pct = dynamic_thresholding, dynamic_thresholding_percentile
+        self.p2_gamma, self.p2_k = p2_loss_weight_gamma, p2_loss_weight_k
+        self.unet_number, self.in_chans = unet_number, in_chans
+        self.text_encoder = text_encoder           # frozen T5 / DeBERTa, optional (pre-computed embeddings are accepted too)
+        if self.text_encoder is not None:
+            for p in self.text_encoder.parameters():
+                p.requires_grad = False
+
+    def encode_text(self, input_ids, attention_mask):
+        with torch.no_grad():
+            self.text_encoder.eval()
+            return self.text_encoder(input_ids, attention_mask).detach()
+
+    def p_losses(self, unet, x0, times, scheduler, objective, text_embeds=None, text_mask=None, lowres_cond_img=None, lowres_aug_times=None, noise=None):
+        x0 = x0 * 2 - 1
+        noise = torch.randn_like(x0) if noise is None else noise
+        xt, log_snr, _, _ = scheduler.q_sample(x0, times, noise)
+        lowres_noisy = None
+        if lowres_cond_img is not None:
+            lowres_cond_img = lowres_cond_img * 2 - 1
+            lowres_noisy, _, _, _ = self.lowres_noise_schedule.q_sample(lowres_cond_img, lowres_aug_times)
+        pred = unet(xt, scheduler.log_snr(times), lowres_cond_img=lowres_noisy,
+                    lowres_noise_times=None if lowres_aug_times is None else self.lowres_noise_schedule.log_snr(lowres_aug_times),
+                    text_embeds=text_embeds, text_mask=text_mask, cond_drop_prob=self.cond_drop_prob)
+        target = {"noise": noise, "x_start": x0, "v": scheduler.calculate_v(x0, times, noise)}[objective]
+        return pred, target, log_snr, self.p2_gamma
+
+    def forward(self, images, text_embeds=None, text_masks=None, input_ids=None, attention_mask=None, unet_number: Optional[int] = None):
+        k = (unet_number or self.unet_number) - 1
+        unet, sched, obj, size = self.unets[k], self.noise_schedulers[k], self.pred_objectives[k], self.image_sizes[k]
+        if text_embeds is None and input_ids is not None and self.text_encoder is not None:
+            text_embeds, text_masks = self.encode_text(input_ids, attention_mask), attention_mask
+        b = images.shape[0]
+        times = sched.sample_random_times(b, images.device)
+        lowres, aug_t = None, None
+        if k > 0:
+            prev = self.image_sizes[k - 1]
+            lowres = resize_image_to(resize_image_to(images, prev), size)
+            aug_t = self.lowres_noise_schedule.sample_random_times(1, images.device).expand(b)
+        x0 = resize_image_to(images, size)
+        return self.p_losses(unet, x0, times, sched, obj, text_embeds, text_masks, lowres, aug_t)
+
+    # ------------------------------------------------------------------ sampling
+    def _threshold(self, x0):
+        if not self.dynamic_thresholding:
+            return x0.clamp(-1, 1)
+        s = torch.quantile(x0.flatten(1).abs().float(), self.dt_pct, dim=-1).clamp(min=1.0).view(-1, 1, 1, 1)
+        return x0.clamp(-s, s) / s
+
+    @torch.no_grad()
+    def sample(self, text_embeds=None, text_masks=None, batch_size: int = 1, cond_scale: float = 1.0, stop_at_unet_number: Optional[int] = None):
+        dev = next(self.parameters()).device
+        img = None
+        outputs = []
+        for k, (unet, sched, obj, size) in enumerate(zip(self.unets, self.noise_schedulers, self.pred_objectives, self.image_sizes)):
+            lowres, lowres_t = None, None
+            if k > 0:
+                lowres = resize_image_to(img, size) * 2 - 1
+                lt = self.lowres_noise_schedule.get_times(batch_size, self.lowres_sample_noise_level, dev)
+                lowres, _, _, _ = self.lowres_noise_schedule.q_sample(lowres, lt)
+                lowres_t = self.lowres_noise_schedule.log_snr(lt)
+            x = torch.randn(batch_size, self.in_chans, size, size, device=dev)
+            for t, t_next in sched.get_sampling_timesteps(batch_size, dev):
+                pred = unet.forward_with_cond_scale(x, sched.log_snr(t), lowres_cond_img=lowres, lowres_noise_times=lowres_t, text_embeds=text_embeds,
+                                                    text_mask=text_masks, cond_scale=cond_scale)
+                x0 = {"noise": sched.predict_start_from_noise, "v": sched.predict_start_from_v}.get(obj, lambda a, b_, c: c)(x, t, pred)
+                x0 = self._threshold(x0)
+                mean, var, _ = sched.q_posterior(x0, x, t, t_next)
+                noise = torch.randn_like(x) * (t_next > 0).float().view(-1, 1, 1, 1)
+                x = mean + var.sqrt() * noise
+            img = (x.clamp(-1, 1) + 1) * 0.5
+            outputs.append(img)
+            if stop_at_unet_number is not None and stop_at_unet_number == k + 1:
+                break
+        return outputs[-1]
+
+
+class ImagenCriterion(nn.Module):
+    def __init__(self, name: str = "mse_loss", p2_loss_weight_k: float = 1.0):
+        super().__init__()
+        self.fn = {"mse_loss": F.mse_loss, "l1_loss": F.l1_loss, "smooth_l1_loss": F.smooth_l1_loss}[name]
+        self.k = p2_loss_weight_k
+
+    def forward(self, pred, target, log_snr, p2_loss_weight_gamma):
+        losses = self.fn(pred.float(), target.float(), reduction="none").flatten(1).mean(1)
+        if p2_loss_weight_gamma > 0:
+            losses = losses * (self.k + log_snr.exp()) ** -p2_loss_weight_gamma
+        return losses.mean()
+
+
+def _preset(unet_names, sizes, **fixed):
+    def build(**kw):
+        cfg = {**fixed, **kw}
+        ted = cfg.get("text_embed_dim", 1024)
+        unets = [getattr(U, n)(text_embed_dim=ted) for n in unet_names]
+        return ImagenModel(unets, image_sizes=sizes, **cfg)
+    return build
+
+
+imagen_397M_text2im_64 = _preset(["Unet64_397M"], [64])
+imagen_2B_text2im_64 = _preset(["BaseUnet64"], [64])
+imagen_text2im_64_debertav2 = _preset(["Unet64_397M"], [64], text_embed_dim=1536)
+imagen_SR256 = _preset(["Unet64_397M", "SRUnet256"], [64, 256], unet_number=2)
+imagen_SR1024 = _preset(["Unet64_397M", "SRUnet256", "SRUnet1024"], [64, 256, 1024], unet_number=3)
