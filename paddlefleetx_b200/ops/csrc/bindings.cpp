@@ -141,6 +141,40 @@ at::Tensor gemm_ag(const at::Tensor& a_local, const at::Tensor& b, const at::Ten
   return d;
 }
 
+// ------------------------------------------------------------------------------- 8-bit GEMMs
+std::vector<at::Tensor> quantize_rows(const at::Tensor& x, c10::optional<at::Tensor> smooth, bool fp8) {
+  PFX_CHECK_CUDA_CONTIG(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t cols = x.size(-1), rows = x.numel() / cols;
+  auto q = at::empty(x.sizes(), x.options().dtype(fp8 ? at::kFloat8_e4m3fn : at::kChar));
+  auto scale = at::empty({rows}, x.options().dtype(at::kFloat));
+  const float* sm = nullptr;
+  at::Tensor smc;
+  if (smooth.has_value() && smooth->defined()) { smc = smooth->to(at::kFloat).contiguous(); sm = smc.data_ptr<float>(); }
+  PFX_CUDA_CHECK(pfx::quantize_rows(x.data_ptr(), sm, q.data_ptr(), scale.data_ptr<float>(), (int)rows, (int)cols, dtype_code(x), fp8, cur_stream()));
+  return {q, scale};
+}
+at::Tensor gemm_lowp(const at::Tensor& a, const at::Tensor& b, c10::optional<at::Tensor> row_scale, c10::optional<at::Tensor> col_scale,
+                     c10::optional<at::Tensor> bias, int64_t config) {
+  TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous(), "gemm_lowp: contiguous 2-D CUDA operands");
+  TORCH_CHECK(a.scalar_type() == b.scalar_type() && (a.scalar_type() == at::kChar || a.scalar_type() == at::kFloat8_e4m3fn), "gemm_lowp: int8 or fp8-e4m3 operands");
+  const c10::cuda::CUDAGuard guard(a.device());
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && K % 16 == 0 && N % 8 == 0, "gemm_lowp: K % 16 == 0 and N % 8 == 0 required");
+  auto d = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  pfx::LowpGemmArgs g{};
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr();
+  at::Tensor rs, cs;
+  if (row_scale.has_value() && row_scale->defined()) { rs = row_scale->to(at::kFloat).contiguous(); TORCH_CHECK(rs.numel() == M); g.row_scale = rs.data_ptr<float>(); }
+  if (col_scale.has_value() && col_scale->defined()) { cs = col_scale->to(at::kFloat).contiguous(); TORCH_CHECK(cs.numel() == N); g.col_scale = cs.data_ptr<float>(); }
+  if (bias.has_value() && bias->defined()) { TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N); g.bias = bias->data_ptr(); }
+  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = (int)K; g.ldb = (int)K; g.ldd = (int)N;
+  g.kind = a.scalar_type() == at::kChar ? 1 : 2;
+  g.num_sms = num_sms(); g.config = (int)config;
+  PFX_CUDA_CHECK(pfx::gemm_lowp_tcgen05(g, cur_stream()));
+  return d;
+}
+
 // ------------------------------------------------------------------------------- norms
 std::vector<at::Tensor> norm_fwd(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> b, double eps, bool rms) {
   PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(w);
@@ -391,6 +425,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_rs_scatter", &gemm_rs_scatter);
   m.def("slot_reduce", &slot_reduce);
   m.def("gemm_ag", &gemm_ag);
+  m.def("quantize_rows", &quantize_rows);
+  m.def("gemm_lowp", &gemm_lowp, py::arg("a"), py::arg("b"), py::arg("row_scale") = py::none(), py::arg("col_scale") = py::none(),
+        py::arg("bias") = py::none(), py::arg("config") = 0);
   m.def("norm_fwd", &norm_fwd);
   m.def("norm_bwd", &norm_bwd);
   m.def("bias_gelu_fwd", &bias_gelu_fwd);

@@ -41,6 +41,18 @@ struct GemmArgs {
 
 cudaError_t gemm_tcgen05(const GemmArgs& args, cudaStream_t stream);
 
+// 8-bit GEMM: D(bf16)[M,N] = (A_q[M,K] * B_q[N,K]^T) * row_scale[M] * col_scale[N] (+ bias[N]); both operands K-major.
+struct LowpGemmArgs {
+  const void* a; const void* b; void* d;
+  const float* row_scale;   // [M] or nullptr
+  const float* col_scale;   // [N] or nullptr
+  const void* bias;         // [N] bf16 or nullptr
+  int M, N, K, lda, ldb, ldd;
+  int kind;                 // 1 = int8 (kind::i8), 2 = fp8 e4m3 (kind::f8f6f4)
+  int num_sms, config;
+};
+cudaError_t gemm_lowp_tcgen05(const LowpGemmArgs& args, cudaStream_t stream);
+
 bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_code, uint64_t inner, uint64_t outer,
                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 

@@ -38,6 +38,8 @@ cudaError_t rope(const void* x, void* y, const int64_t* positions, size_t tokens
 cudaError_t causal_softmax(const void* a, const void* b, void* out, size_t batch, int sq, int sk, float scale, bool bwd, int dtype,
                            cudaStream_t st);
 
+cudaError_t quantize_rows(const void* x, const float* smooth, void* q, float* scale, int rows, int cols, int dtype, bool fp8, cudaStream_t st);
+
 // ---- peer-memory collectives (comm_p2p.cu): every pointer table lives in device memory
 cudaError_t p2p_barrier(uint32_t** signal_pads, int rank, int world, uint32_t epoch_slot, cudaStream_t st);
 cudaError_t p2p_reduce_scatter(void** peer_bufs, void* out, size_t shard_elems, int rank, int world, int in_dtype, int out_dtype,

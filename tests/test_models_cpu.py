@@ -1,0 +1,229 @@
+"""Model-zoo and task-module coverage on CPU: every family builds from YAML configs, trains a step, and the
+export -> InferenceEngine round trip reproduces eager outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT
+from paddlefleetx_b200.utils import config as C
+
+CFG = os.path.join(ROOT, "paddlefleetx_b200", "configs")
+TINY_MODEL = ["Global.device=cpu", "Model.num_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.ffn_hidden_size=128",
+              "Model.vocab_size=512", "Model.vocab_size_divisible_unit=8", "Model.max_position_embeddings=64", "Model.hidden_dropout_prob=0.0",
+              "Model.attention_probs_dropout_prob=0.0", "Engine.mix_precision.enable=False"]
+
+
+def _module(cfg):
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models import build_module
+
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    return build_module(cfg)
+
+
+def test_generation_module_export_and_inference_roundtrip(tmp_path):
+    out = str(tmp_path / "exp")
+    cfg = C.get_config(os.path.join(CFG, "nlp/gpt/generation_gpt_345M_single_card.yaml"),
+                       TINY_MODEL + ["Generation.max_dec_len=6", "Generation.decode_strategy=greedy_search", f"Engine.save_load.output_dir={out}",
+                                     "Generation.top_k=0", "Generation.top_p=1.0"], nranks=1)
+    module = _module(cfg)
+    texts = module.generate(["hello world", "b200"])
+    assert len(texts) == 2 and all(isinstance(t, str) for t in texts)
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.core.engine.inference_engine import InferenceEngine
+
+    eng = EagerEngine(configs=cfg, module=module, mode="export")
+    eng.export()
+    assert sorted(os.listdir(os.path.join(out, "rank_0"))) == ["model.pdiparams", "model.pdmodel"]
+    ids = torch.tensor([module.tokenizer.encode("hello world")])
+    want, _ = module.model.generate(ids)
+    got = InferenceEngine(out, 1, device="cpu").predict([ids.numpy()])["output_0"]
+    assert np.array_equal(got, want.numpy())
+
+
+def test_sampling_is_seed_reproducible_and_respects_eos():
+    cfg = C.get_config(os.path.join(CFG, "nlp/gpt/generation_gpt_345M_single_card.yaml"), TINY_MODEL + ["Generation.max_dec_len=12"], nranks=1)
+    module = _module(cfg)
+    ids = torch.randint(0, 200, (3, 5))
+    a, sa = module.model.generate(ids, seed=7)
+    b, _ = module.model.generate(ids, seed=7)
+    assert torch.equal(a, b) and sa.shape == (3, 1) and a.shape[1] <= 12
+    eos = module.model.eos_token_id
+    for row in a.tolist():
+        if eos in row:
+            assert all(t == eos for t in row[row.index(eos):])
+
+
+def test_logits_processors():
+    from paddlefleetx_b200.models.language_model.gpt import processor as P
+
+    logits = torch.zeros(2, 10)
+    ids = torch.tensor([[1, 2], [3, 3]])
+    assert torch.isinf(P.MinLengthLogitsProcessor(5, 9)(ids, logits)[:, 9]).all()
+    rp = P.RepetitionPenaltyLogitsProcessor(2.0)(ids, torch.ones(2, 10))
+    assert rp[0, 1] == 0.5 and rp[0, 0] == 1.0
+    assert P.ForcedEOSTokenLogitsProcessor(3, 4)(ids, logits).argmax(-1).tolist() == [4, 4]
+    assert P.ForcedBOSTokenLogitsProcessor(6)(ids[:, :1], logits).argmax(-1).tolist() == [6, 6]
+
+
+def _write_glue(root):
+    d = os.path.join(root, "CoLA")
+    os.makedirs(d)
+    rows = [f"s\t{i % 2}\t*\tsentence number {i} {'good' if i % 2 else 'bad'}" for i in range(24)]
+    for fn in ("train.tsv", "dev.tsv"):
+        with open(os.path.join(d, fn), "w") as f:
+            f.write("\n".join(rows) + "\n")
+
+
+def test_glue_finetune_module_trains_and_scores(tmp_path):
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.data import build_dataloader
+
+    _write_glue(str(tmp_path))
+    cfg = C.get_config(os.path.join(CFG, "nlp/gpt/finetune_gpt_345M_single_card_glue.yaml"),
+                       TINY_MODEL + [f"Data.Train.dataset.root={tmp_path}", f"Data.Eval.dataset.root={tmp_path}", "Data.Train.sampler.batch_size=8",
+                                     "Data.Eval.sampler.batch_size=8", "Data.Train.loader.num_workers=0", "Data.Eval.loader.num_workers=0",
+                                     "Global.local_batch_size=8", "Global.micro_batch_size=8", "Engine.num_train_epochs=2", "Model.vocab_size=512",
+                                     "Optimizer.lr.learning_rate=1e-3", "Model.pad_token_id=256"], nranks=1)
+    module = _module(cfg)
+    tl, el = build_dataloader(cfg.Data, "Train"), build_dataloader(cfg.Data, "Eval")
+    cfg.Optimizer.lr.update(epochs=2, step_each_epoch=len(tl))
+    eng = EagerEngine(configs=cfg, module=module)
+    eng.fit(epoch=2, train_data_loader=tl, valid_data_loader=el)
+    eng.evaluate(valid_data_loader=el)
+    assert 0.0 <= module.best_metric <= 1.0
+
+
+def test_qkv_fuse_split_conversion_roundtrip():
+    from paddlefleetx_b200.models.language_model.finetune_module import convert_qkv_layout
+
+    h, heads = 16, 4
+    st = {"l.self_attn.q_proj.weight": torch.randn(h, h), "l.self_attn.k_proj.weight": torch.randn(h, h), "l.self_attn.v_proj.weight": torch.randn(h, h),
+          "l.self_attn.q_proj.bias": torch.randn(h), "l.self_attn.k_proj.bias": torch.randn(h), "l.self_attn.v_proj.bias": torch.randn(h)}
+    fused = convert_qkv_layout(st, True, heads)
+    assert fused["l.self_attn.qkv_proj.weight"].shape == (3 * h, h)
+    back = convert_qkv_layout(fused, False, heads)
+    for k, v in st.items():
+        assert torch.equal(back[k], v)
+    hd = h // heads           # fused layout is [heads, 3, head_dim]: q of head 1 sits at rows [3*hd, 4*hd)
+    assert torch.equal(fused["l.self_attn.qkv_proj.weight"][3 * hd:4 * hd], st["l.self_attn.q_proj.weight"][hd:2 * hd])
+
+
+def test_eval_datasets_follow_the_reference_formulas():
+    from paddlefleetx_b200.data.dataset.gpt_dataset import Lambada_Eval_Dataset, LM_Eval_Dataset
+
+    toks = list(np.random.RandomState(0).randint(0, 500, size=200))
+    ds = LM_Eval_Dataset(None, 32, overlapping_eval=8, tokens=toks)
+    counted = sum(float(ds[i][1].sum()) for i in range(len(ds)))
+    assert counted == len(toks) - 1                      # every target token is scored exactly once
+    lam = Lambada_Eval_Dataset(None, 16, samples=[([1, 2, 3, 4], [5, 6]), ([7, 8], [9])])
+    t, m, _, _, l, _ = lam[0]
+    assert m.sum() == 2 and l[np.nonzero(m)[0]].tolist() == [5, 6]
+
+
+def test_ernie_module_step_and_dataset(tmp_path):
+    rng = np.random.RandomState(0)
+    sents = rng.randint(2, 6, size=20)
+    lens = rng.randint(4, 16, size=int(sents.sum())).astype(np.int32)
+    np.save(tmp_path / "c_ids.npy", rng.randint(4, 500, size=int(lens.sum())).astype(np.int32))
+    np.savez(tmp_path / "c_idx.npz", lens=lens, docs=np.concatenate([[0], np.cumsum(sents)]))
+    cfg = C.get_config(os.path.join(CFG, "nlp/ernie/pretrain_ernie_base.yaml"),
+                       ["Global.device=cpu", "Engine.mix_precision.enable=False", "Model.hidden_size=32", "Model.num_hidden_layers=2", "Model.num_attention_heads=4",
+                        "Model.vocab_size=512", "Model.max_position_embeddings=64", f"Data.Train.dataset.input_dir={tmp_path}",
+                        f"Data.Eval.dataset.input_dir={tmp_path}", "Data.Train.dataset.max_seq_length=48", "Data.Train.dataset.vocab_size=500",
+                        "Global.local_batch_size=4", "Global.micro_batch_size=4", "Engine.max_steps=3", "Data.Train.loader.num_workers=0",
+                        "Optimizer.lr.max_lr=1e-3"], nranks=1)
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.data import build_dataloader
+
+    module = _module(cfg)
+    loader = build_dataloader(cfg.Data, "Train")
+    eng = EagerEngine(configs=cfg, module=module)
+    losses = [float(eng.train_step(b)) for b in loader]
+    assert len(losses) >= 2 and all(np.isfinite(losses))
+
+
+def test_vit_moco_imagen_modules_train_one_step():
+    from paddlefleetx_b200.models.multimodal_model.imagen import modeling as I
+    from paddlefleetx_b200.models.multimodal_model.imagen import unet as U
+    from paddlefleetx_b200.models.vision_model.factory import build
+    from paddlefleetx_b200.models.vision_model.moco import MoCo
+
+    vit = build(dict(name="ViT_tiny_patch16_224", img_size=32, patch_size=8, depth=2, class_num=10))
+    loss = build(dict(name="CELoss", epsilon=0.1))(vit(torch.randn(2, 3, 32, 32)), torch.tensor([1, 3]))
+    loss.backward()
+    assert vit.blocks[0].attn.qkv.weight.grad is not None and "blocks.0.attn.qkv.weight" in vit.state_dict()
+    moco = MoCo(dim=8, K=16, backbone="resnet18")
+    lg, lb = moco(torch.randn(4, 3, 32, 32), torch.randn(4, 3, 32, 32))
+    assert lg.shape == (4, 17) and int(moco.queue_ptr) == 4
+    u = U.Unet(dim=8, text_embed_dim=12, dim_mults=(1, 2), layer_attns=(False, True), layer_cross_attns=(False, True), attn_heads=2, attn_dim_head=4,
+               max_text_len=6, num_latents=2)
+    m = I.ImagenModel([u], image_sizes=[8], text_embed_dim=12, timesteps=2)
+    out = m(torch.rand(2, 3, 8, 8), text_embeds=torch.randn(2, 4, 12), text_masks=torch.ones(2, 4))
+    assert torch.isfinite(I.ImagenCriterion()(*out))
+    assert m.sample(text_embeds=torch.randn(1, 4, 12), text_masks=torch.ones(1, 4)).shape == (1, 3, 8, 8)
+
+
+def test_text_towers_and_evoformer_forward_backward():
+    from paddlefleetx_b200.models.multimodal_model.debertav2.modeling import DebertaV2Model
+    from paddlefleetx_b200.models.multimodal_model.t5.modeling import T5EncoderModel
+    from paddlefleetx_b200.models.protein_folding import EmbeddingsAndEvoformer
+
+    ids = torch.randint(0, 100, (2, 10))
+    mask = torch.ones(2, 10, dtype=torch.long)
+    mask[0, 7:] = 0
+    t5 = T5EncoderModel(vocab_size=100, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu")
+    assert t5(ids, mask).shape == (2, 10, 32)
+    deb = DebertaV2Model(vocab_size=100, hidden_size=32, num_hidden_layers=2, num_attention_heads=4, intermediate_size=64, position_buckets=8,
+                         conv_kernel_size=3)
+    deb(ids, mask).sum().backward()
+    evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2, pair_heads=2)
+    out = evo(dict(target_feat=torch.randn(1, 10, 6), msa_feat=torch.randn(1, 4, 10, 9), residue_index=torch.arange(10)[None]))
+    assert out["single"].shape == (1, 10, 12) and out["pair"].shape == (1, 10, 10, 8)
+    out["single"].sum().backward()
+
+
+def test_lora_prefix_qat_prune_smoothquant():
+    from paddlefleetx_b200.models.language_model.gpt import model as gpt
+    from paddlefleetx_b200.utils import compression_helper as CH
+    from paddlefleetx_b200.utils import peft
+    from paddlefleetx_b200.utils import smoothquant as SQ
+
+    torch.manual_seed(0)
+    kw = dict(vocab_size=64, hidden_size=32, num_layers=2, num_attention_heads=4, max_position_embeddings=16, hidden_dropout_prob=0, attention_probs_dropout_prob=0)
+    core = gpt.GPTModel(**kw)
+    ids = torch.randint(0, 64, (2, 8))
+    base = core(ids).detach()
+    ad = peft.apply_lora(core, r=4, alpha=8)
+    assert len(ad) == 4 and torch.allclose(core(ids), base, atol=1e-6)        # B = 0 at init
+    trainable = [n for n, p in core.named_parameters() if p.requires_grad]
+    assert trainable and all("lora_" in n for n in trainable)
+    core(ids).sum().backward()
+    with torch.no_grad():
+        for a in ad:
+            a.lora_B.add_(0.01)
+    changed = core(ids).detach()
+    peft.merge_lora(core)
+    assert torch.allclose(core(ids), changed, atol=1e-5) and not any("lora" in k for k in core.state_dict())
+
+    core2 = gpt.GPTModel(**kw)
+    enc = peft.apply_prefix_tuning(core2, num_virtual_tokens=3, hidden=16)
+    core2(ids).sum().backward()
+    assert enc.embed.weight.grad is not None and core2.decoder.layers[0].linear1.weight.grad is None
+
+    core3 = gpt.GPTModel(**dict(kw, num_layers=1, ffn_hidden_size=64))
+    CH.prune_model(core3, dict(ratio=0.25, criterion="l2_norm"))
+    assert core3.decoder.layers[0].linear1.weight.shape[0] == 48 and core3.decoder.layers[0].self_attn.local_heads == 3
+    assert core3(ids).shape == (2, 8, 32)
+    CH.quant_model(core3, dict(activation_preprocess_type="PACT"))
+    core3.train()
+    core3(ids).sum().backward()
+
+    lin = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8))
+    xs = [torch.randn(6, 16) * torch.linspace(0.2, 4, 16) + 0.5 for _ in range(3)]
+    ref = lin(xs[0])
+    q = SQ.smooth_and_quantize(lin, SQ.calibrate(lin, xs))
+    assert float((q(xs[0]) - ref).norm() / ref.norm()) < 0.05

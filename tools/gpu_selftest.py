@@ -249,6 +249,30 @@ def check_rope_softmax():
     return dict(errs=errs, ok=all(v < 2e-2 for v in errs.values()))
 
 
+def check_lowp(kind="int8", M=512, N=512, K=512, cfg=0, time_it=False):
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    x = (torch.randn(M, K, device="cuda")).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda").bfloat16()
+    fp8 = kind == "fp8"
+    xq, xs = lib.quantize_rows(x, None, fp8)
+    wq, ws = lib.quantize_rows(w, None, fp8)
+    y = lib.gemm_lowp(xq, wq, xs, ws, bias, cfg)
+    torch.cuda.synchronize()
+    deq = (xq.float() * xs[:, None]) @ (wq.float() * ws[:, None]).t() + bias.float()
+    ref_full = x.float() @ w.float().t() + bias.float()
+    res = dict(err_vs_dequant=_relerr(y, deq), err_vs_bf16=_relerr(y, ref_full), quant_err=_relerr(xq.float() * xs[:, None], x))
+    res["ok"] = res["err_vs_dequant"] < 1e-2 and res["err_vs_bf16"] < (8e-2 if fp8 else 3e-2)
+    if time_it:
+        med, best = _time(lambda: lib.gemm_lowp(xq, wq, xs, ws, bias, cfg))
+        res.update(ms=med, tops=2.0 * M * N * K / med / 1e9, tops_best=2.0 * M * N * K / best / 1e9)
+        med2, _ = _time(lambda: torch.matmul(x, w.t()))
+        res.update(bf16_cublas_ms=med2)
+    return res
+
+
 CHECKS = {
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
     "gemm_nt_1cta_n128": lambda: check_gemm(True, True, 3),
@@ -269,6 +293,12 @@ CHECKS = {
     "gemm_perf_ffn1": lambda: check_gemm(True, True, 2, 8192, 16384, 4096, epilogue=1, time_it=True),
     "gemm_perf_dgrad": lambda: check_gemm(True, False, 2, 8192, 4096, 16384, time_it=True),
     "gemm_perf_wgrad": lambda: check_gemm(False, False, 2, 16384, 4096, 8192, out_mode=1, time_it=True),
+    "gemm_int8": lambda: check_lowp("int8"),
+    "gemm_int8_pair": lambda: check_lowp("int8", 1024, 1024, 1024, 2),
+    "gemm_fp8": lambda: check_lowp("fp8"),
+    "gemm_fp8_pair": lambda: check_lowp("fp8", 1024, 1024, 1024, 2),
+    "gemm_int8_perf": lambda: check_lowp("int8", 8192, 8192, 8192, 2, True),
+    "gemm_fp8_perf": lambda: check_lowp("fp8", 8192, 8192, 8192, 2, True),
     "layernorm": lambda: check_norm(False),
     "rmsnorm": lambda: check_norm(True),
     "gelu_dropout": check_gelu_dropout,
