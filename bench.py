@@ -92,11 +92,12 @@ def reference_arm(args):
     try:
         import paddle  # noqa: F401
     except Exception as e:  # noqa: BLE001
-        why = f"reference requires paddlepaddle-gpu which is not installed/installable offline ({type(e).__name__}: {e})"
-    if why is None and not os.path.isdir(os.path.join(ROOT, "baseline", "_ref")):
-        why = "baseline/_ref not installed"
+        why = ("pip install of /root/reference into baseline/_ref fails at metadata time: its setup.py imports ppfleetx -> `import paddle` "
+               f"({type(e).__name__}); no paddlepaddle wheel exists in /opt/wheelhouse and there is no network (details: DESIGN.md)")
+    if why is None and not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "ppfleetx")):
+        why = "baseline/_ref/ppfleetx not installed"
     if why is None:
-        why = "reference launcher not wired: paddle import unexpectedly succeeded; see DESIGN.md"
+        why = "paddle import unexpectedly succeeded but the reference launcher is not wired in this build; see DESIGN.md"
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
