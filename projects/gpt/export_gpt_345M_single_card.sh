@@ -1,0 +1,5 @@
+#!/bin/bash
+# GPT: export_gpt_345M_single_card
+set -e
+cd "$(dirname "$0")/../.."
+python tools/export.py -c paddlefleetx_b200/configs/nlp/gpt/generation_gpt_345M_single_card.yaml "$@"

@@ -1,0 +1,6 @@
+#!/bin/bash
+# Imagen: imagen_text2im_64x64_T5-11B
+set -e
+cd "$(dirname "$0")/../.."
+python -m torch.distributed.run --nnodes=${NNODES:-1} --node-rank=${NODE_RANK:-0} --nproc-per-node=8 --master-addr=${MASTER_ADDR:-127.0.0.1} --master-port=${MASTER_PORT:-29500} \
+    tools/train.py -c paddlefleetx_b200/configs/multimodal/imagen/imagen_text2im_64x64_T5-11B.yaml "$@"
