@@ -185,6 +185,21 @@ class EagerEngine(BasicEngine):
             from ...utils.profiler import StepProfiler
 
             self._profiler = StepProfiler(configs.Profiler)
+        # failure detection (utils/watchdog.py): per-rank heartbeat files + stall monitor, SIGTERM/SIGUSR1 emergency checkpoint,
+        # PFX_FAULT test hook.  Engine.watchdog: {enable, timeout, dir}
+        from ...utils import watchdog as _wd
+
+        self._wd = _wd
+        self._fault = _wd.FaultInjector(rank=env.global_rank())
+        self._stop_requested = False
+        self._heartbeat = None
+        wcfg = (configs.Engine.get("watchdog") or {}) if mode == "train" else {}
+        if wcfg.get("enable", False):
+            self._heartbeat = _wd.Heartbeat(wcfg.get("dir") or os.path.join(self._output_dir or ".", "heartbeat"),
+                                            int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)),
+                                            timeout_s=float(wcfg.get("timeout", 600))).start()
+        if mode == "train":
+            _wd.install_signal_checkpoint()
         self._inference_engine = None
         self._train_tokens = None
 
@@ -212,6 +227,8 @@ class EagerEngine(BasicEngine):
         for epoch_index in range(start_epoch, epoch):
             t0 = get_timestamp()
             self._train_one_epoch(epoch_index, train_data_loader, valid_data_loader)
+            if self._stop_requested:
+                break
             train_cost = get_timestamp() - t0
             self._module.training_epoch_end({"epoch": epoch_index, "train_cost": train_cost})
             if self._run_mode == "epoch":
@@ -223,6 +240,8 @@ class EagerEngine(BasicEngine):
                     self.save(epoch=epoch_index, step=len(train_data_loader) if train_data_loader is not None else 0)
         if self._profiler is not None:
             self._profiler.finish()
+        if self._heartbeat is not None:
+            self._heartbeat.stop()
 
     def _train_one_epoch(self, epoch_index: int, train_data_loader, valid_data_loader):
         self._module.model.train()
@@ -240,7 +259,17 @@ class EagerEngine(BasicEngine):
             if step < resume_step:
                 continue          # resume: replay the sampler and discard consumed batches (eager_engine.py:347-349)
             loss = self._fit_impl(batch)
+            loss = self._fault.maybe_fire(step, loss)
             losses.append(loss)
+            if self._heartbeat is not None:
+                self._heartbeat.beat(step)
+            if self._wd.emergency_requested():
+                if device.type == "cuda":
+                    torch.cuda.synchronize()
+                logger.warning(f"emergency checkpoint at epoch {epoch_index} step {step + 1}, then stopping")
+                self.save(epoch=epoch_index, step=step + 1)
+                self._stop_requested = True
+                return
             found_inf = self._scaler.found_inf if (self._scaler is not None and self._amp_dtype == "float16") else False
             if self._lr_scheduler_mode == "step" and isinstance(self._lr_scheduler, LRScheduler) and not found_inf:
                 self._lr_scheduler.step(epoch=self._global_batch_size if self._use_increments else None)

@@ -28,6 +28,14 @@ def ckpt_dir(output_dir: str, epoch: int, step: int) -> str:
     return os.path.join(output_dir, f"epoch_{epoch}_step_{step}", rank_subdir())
 
 
+def _layout() -> dict:
+    if env.world_size() == 1:
+        return {"mp": 1, "pp": 1, "sharding": 1, "dp": 1}
+    h = env.get_hcg()
+    return {"mp": h.get_model_parallel_world_size(), "pp": h.get_pipe_parallel_world_size(),
+            "sharding": h.get_sharding_parallel_world_size(), "dp": h.get_data_parallel_world_size()}
+
+
 def _cpu(obj):
     if isinstance(obj, torch.Tensor):
         return obj.detach().cpu()
@@ -49,7 +57,10 @@ def save(output_dir: str, model: torch.nn.Module, optimizer=None, step: int = 0,
     meta = {"epoch": epoch, "step": step, "cpu_rng_state": torch.get_rng_state(),
             "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
             "rng_tracker": get_rng_state_tracker().get_states_tracker(),
-            "scaler": scaler.state_dict() if scaler is not None else None}
+            "scaler": scaler.state_dict() if scaler is not None else None,
+            # tensor-parallel split axis of every sharded entry; lets utils/ckpt_convert.py merge / re-split offline
+            "tp_axes": {n: int(getattr(p, "split_axis", 0)) for n, p in model.named_parameters() if getattr(p, "tp_sharded", False)},
+            "layout": _layout()}
     torch.save(meta, os.path.join(d, "meta_state.pdopt"))
     logger.info(f"save model to {d}")
     return d

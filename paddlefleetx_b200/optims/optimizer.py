@@ -370,14 +370,37 @@ class FusedAdamW:
         sd = {"step": self._step_count, "groups": []}
         for g in self.groups:
             sd["groups"].append({"key": g.key, "numel": g.numel, "lo": g.meta["lo"], "hi": g.meta["hi"],
-                                 "names": [self._names[id(p)] for p in g.params],
+                                 "names": [self._names[id(p)] for p in g.params], "offsets": list(g.offsets),
+                                 "shapes": [tuple(p.shape) for p in g.params],
                                  "master": g.meta["master"].detach().float().cpu() if g.meta["has_master"] else None,
                                  "moment1": g.meta["m"].cpu(), "moment2": g.meta["v"].cpu()})
         if isinstance(self._learning_rate, LRScheduler):
             sd["LR_Scheduler"] = self._learning_rate.state_dict()
         return sd
 
+    def load_named_state(self, named: dict, step: int = 0) -> None:
+        """Fill this rank's shard from a layout-independent ``{param_name: {moment1, moment2, master}}`` dict of full
+        (TP-local) tensors — the "universal" optimizer checkpoint written by ``utils/ckpt_convert.py``."""
+        self._step_count = step
+        for g in self.groups:
+            lo, hi = g.meta["lo"], g.meta["hi"]
+            for p, off in zip(g.params, g.offsets):
+                n = p.numel()
+                a, b = max(off, lo), min(off + n, hi)
+                if a >= b:
+                    continue
+                st = named[self._names[id(p)]]
+                for key, dst in (("moment1", g.meta["m"]), ("moment2", g.meta["v"]), ("master", g.meta["master"] if g.meta["has_master"] else None)):
+                    if dst is None or st.get(key) is None:
+                        continue
+                    dst[a - lo:b - lo].copy_(st[key].reshape(-1)[a - off:b - off])
+
     def set_state_dict(self, sd: dict) -> None:
+        if sd.get("format") == "named":
+            self.load_named_state(sd["state"], sd.get("step", 0))
+            if "LR_Scheduler" in sd and isinstance(self._learning_rate, LRScheduler):
+                self._learning_rate.set_state_dict(sd["LR_Scheduler"])
+            return
         self._step_count = sd.get("step", 0)
         assert len(sd["groups"]) == len(self.groups), "optimizer layout mismatch (different bucket/sharding layout?)"
         for g, s in zip(self.groups, sd["groups"]):

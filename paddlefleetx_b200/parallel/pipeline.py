@@ -131,7 +131,8 @@ class PipelineLayer(nn.Module):
 
     # -- construction -------------------------------------------------------------------------
     def _build_range(self, start: int, end: int):
-        funcs, holder = [], nn.ModuleList()
+        # keyed by the GLOBAL layer index so checkpoint keys do not depend on the pp layout (utils/ckpt_convert.py)
+        funcs, holder = [], nn.ModuleDict()
         for idx in range(start, end):
             d = self._layers_desc[idx]
             if isinstance(d, SharedLayerDesc):
@@ -145,10 +146,10 @@ class PipelineLayer(nn.Module):
                     funcs.append(_Bound(d.forward_func, layer))
             elif isinstance(d, LayerDesc):
                 layer = d.build_layer()
-                holder.append(layer)
+                holder[str(idx)] = layer
                 funcs.append(layer)
             elif isinstance(d, nn.Module):
-                holder.append(d)
+                holder[str(idx)] = d
                 funcs.append(d)
             elif callable(d):
                 funcs.append(d)

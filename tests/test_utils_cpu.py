@@ -1,0 +1,161 @@
+"""Utility subsystems: checkpoint conversion, watchdog / fault injection, profiler, download/file helpers, config checks."""
+import json
+import os
+import time
+
+import pytest
+import torch
+
+from dist_utils import run_distributed
+from helpers import build_engine, synthetic_batches, tiny_gpt_config
+
+
+def test_reshard_single_process_roundtrip_and_named_optimizer(tmp_path):
+    from paddlefleetx_b200.utils import ckpt_convert as cc
+
+    out = str(tmp_path / "out")
+    ov = ["Global.local_batch_size=2", "Global.micro_batch_size=2"]
+    cfg = tiny_gpt_config(ov + [f"Engine.save_load.output_dir={out}"])
+    eng = build_engine(cfg)
+    batches = synthetic_batches(cfg, 5, seed=3)
+    for b in batches[:3]:
+        eng.train_step(b)
+    eng.save(epoch=0, step=3)
+    cont = [float(eng.train_step(b)) for b in batches[3:]]
+
+    dst = str(tmp_path / "conv")
+    cc.convert(os.path.join(out, "epoch_0_step_3"), dst, mp=1)
+    sd = torch.load(os.path.join(dst, "model_state.pdopt"), weights_only=False)
+    assert sd["format"] == "named" and sd["step"] == 3
+    eng2 = build_engine(tiny_gpt_config(ov + [f"Engine.save_load.ckpt_dir={dst}"]))
+    eng2.load()
+    resumed = [float(eng2.train_step(b)) for b in batches[3:]]
+    assert max(abs(a - b) for a, b in zip(cont, resumed)) < 1e-5
+
+
+def test_gpt_pipe_plain_key_mapping_is_inverse():
+    from paddlefleetx_b200.utils.ckpt_convert import gpt_pipe_to_plain, gpt_plain_to_pipe
+
+    plain = {"gpt.embeddings.word_embeddings.weight": 1, "gpt.decoder.layers.0.norm1.weight": 2, "gpt.decoder.layers.3.linear2.bias": 3,
+             "gpt.decoder.norm.weight": 4}
+    pipe = gpt_plain_to_pipe(plain, num_layers=4)
+    assert set(pipe) == {"shared_layers.embed.word_embeddings.weight", "layers.1.norm1.weight", "layers.4.linear2.bias", "layers.5.norm.weight"}
+    assert gpt_pipe_to_plain(pipe, num_layers=4) == plain
+
+
+def test_reshard_tensor_parallel_checkpoint(tmp_path):
+    run_distributed("dist_fns:ckpt_reshard_tp_sharding", 2, str(tmp_path))
+
+
+def test_heartbeat_detects_stalled_rank(tmp_path):
+    from paddlefleetx_b200.utils.watchdog import Heartbeat
+
+    fired = []
+    a = Heartbeat(str(tmp_path), rank=0, world=2, timeout_s=0.3, interval_s=0.05, on_stall=fired.append)
+    b = Heartbeat(str(tmp_path), rank=1, world=2, timeout_s=0.3, interval_s=0.05, on_stall=lambda late: None)
+    b.beat(0)
+    a.start()
+    for s in range(8):               # rank 0 keeps beating, rank 1 went silent after step 0
+        a.beat(s)
+        time.sleep(0.08)
+    a.stop()
+    assert fired and fired[0] == [1]
+
+
+def test_fault_injector_and_signal_flag():
+    from paddlefleetx_b200.utils import watchdog as wd
+
+    inj = wd.FaultInjector("0:3:raise", rank=0)
+    inj.maybe_fire(2)
+    with pytest.raises(RuntimeError):
+        inj.maybe_fire(3)
+    nan = wd.FaultInjector("1:0:nan", rank=1).maybe_fire(0, torch.tensor(1.0))
+    assert torch.isnan(nan)
+    assert not wd.FaultInjector("1:0:nan", rank=0).active
+    wd.install_signal_checkpoint()
+    import signal
+
+    os.kill(os.getpid(), signal.SIGUSR1)
+    time.sleep(0.05)
+    assert wd.emergency_requested()
+    wd.clear_emergency()
+
+
+def test_engine_emergency_checkpoint_on_signal(tmp_path):
+    from paddlefleetx_b200.utils import watchdog as wd
+
+    out = str(tmp_path / "out")
+    cfg = tiny_gpt_config(["Global.local_batch_size=2", "Global.micro_batch_size=2", f"Engine.save_load.output_dir={out}", "Engine.max_steps=50"])
+    eng = build_engine(cfg)
+    data = synthetic_batches(cfg, 10, seed=1)
+
+    class Loader(list):
+        pass
+
+    wd._EMERGENCY.set()
+    try:
+        eng.fit(epoch=1, train_data_loader=Loader(data))
+    finally:
+        wd.clear_emergency()
+    saved = os.listdir(out)
+    assert any(d.startswith("epoch_0_step_1") for d in saved), saved     # stopped and saved after the first step
+
+
+def test_step_profiler_window(tmp_path):
+    from paddlefleetx_b200.utils.config import AttrDict
+    from paddlefleetx_b200.utils.profiler import StepProfiler
+
+    prof = StepProfiler(AttrDict(scheduler=[1, 3], profiler_log=str(tmp_path), detailed=False))
+    x = torch.randn(64, 64)
+    for _ in range(5):
+        (x @ x).sum()
+        prof.step()
+    prof.finish()
+    summ = json.load(open(tmp_path / "summary_rank0.json"))
+    assert summ["window"] == [1, 3] and summ["events"]
+    assert (tmp_path / "trace_rank0.json").exists()
+
+
+def test_download_and_file_helpers(tmp_path):
+    import zipfile
+
+    from paddlefleetx_b200.utils import download, file as pfile
+
+    src = tmp_path / "vocab.json"
+    src.write_text("{}")
+    got = download.get_path_from_url("file://" + str(src), str(tmp_path / "cache"))
+    assert open(got).read() == "{}" and download.cached_path(str(src)) == str(src)
+    with pytest.raises(FileNotFoundError):
+        download.cached_path(str(tmp_path / "missing"))
+    z = tmp_path / "a.zip"
+    with zipfile.ZipFile(z, "w") as f:
+        f.writestr("d/x.txt", "hi")
+    pfile.unzip(str(z), str(tmp_path / "unz"))
+    assert (tmp_path / "unz" / "d" / "x.txt").read_text() == "hi"
+    (tmp_path / "t.csv").write_text("skip\n1 2\n3 4\n")
+    assert pfile.parse_csv(str(tmp_path / "t.csv"), skip_lines=1) == [["1", "2"], ["3", "4"]]
+
+
+def test_config_checks():
+    from paddlefleetx_b200.utils import check
+
+    cfg = tiny_gpt_config()
+    assert check.check_config(cfg) and check.check_version()
+    cfg.Model.num_attention_heads = 7
+    with pytest.raises(ValueError):
+        check.check_config(cfg)
+    with pytest.raises(ValueError):
+        check.check_device("xpu")
+
+
+def test_tensor_fusion_helper_groups_and_keeps_values():
+    from paddlefleetx_b200.utils.tensor_fusion_helper import all_reduce_parameters, fused_parameters
+
+    m = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.LayerNorm(8))
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    decay, allg = fused_parameters(m.parameters())
+    assert len(allg) == 2 and len(decay) == 1 and decay[0].params[0].dim() == 2
+    for n, p in m.named_parameters():
+        assert torch.equal(p, before[n])
+        assert p.data_ptr() >= min(g.param_buf.data_ptr() for g in allg)
+    all_reduce_parameters(allg)      # no process group: no-op
