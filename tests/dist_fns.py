@@ -139,34 +139,20 @@ def pipeline_matches_single(rank, world, pp, mp, vpp, acc):
     module = build_module(cfg)
     hcg = env.get_hcg()
     pipe = module.model
-    # map the single-model initial weights onto this stage's layers
-    stage, P, V = hcg.get_stage_id(), pp, max(vpp, 1)
-    parts = pipe.segment_parts
+    # map the single-model initial weights onto this stage's layers through the converter's plain -> pipe key map
+    # (pipeline keys carry the global layer index, so the same map works for every pp / virtual-pp layout)
+    import re
 
-    def src_key(global_layer_idx, sub):          # decoder layer index in the flat desc list = idx - 1
-        return f"gpt.decoder.layers.{global_layer_idx - 1}.{sub}"
+    from paddlefleetx_b200.utils.ckpt_convert import gpt_plain_to_pipe
 
+    pipe_init = gpt_plain_to_pipe(init, L)
     with torch.no_grad():
-        for v in range(V):
-            part = v * P + stage
-            start, end = parts[part], parts[part + 1]
-            local = 0
-            for idx in range(start, end):
-                if idx == 0 or idx == L + 2:
-                    continue
-                holder = pipe._model_chunks[v][local]
-                local += 1
-                for n, p in holder.named_parameters():
-                    if idx == L + 1:
-                        full = init[f"gpt.decoder.norm.{n.split('.', 1)[1]}"]
-                    else:
-                        full = init[src_key(idx, n)]
-                    p.copy_(_shard_like(full, p, hcg.get_model_parallel_rank(), mp))
-        if "embed" in pipe.shared_layers:
-            emb = pipe.shared_layers["embed"]
-            emb.word_embeddings.weight.copy_(_shard_like(init["gpt.embeddings.word_embeddings.weight"], emb.word_embeddings.weight,
-                                                         hcg.get_model_parallel_rank(), mp))
-            emb.position_embeddings.weight.copy_(init["gpt.embeddings.position_embeddings.weight"])
+        seen = 0
+        for n, p in pipe.named_parameters():
+            key = re.sub(r"^_model_chunks\.\d+\.", "layers.", n)
+            p.copy_(_shard_like(pipe_init[key], p, hcg.get_model_parallel_rank(), mp))
+            seen += 1
+        assert seen > 0
     eng = EagerEngine(configs=cfg, module=module)
     losses = [float(eng.train_step(b)) for b in batches]
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 3e-4, (rank, losses, ref_losses)
