@@ -44,9 +44,15 @@ class ExpertLayer(nn.Module):
 
 
 class MoELayer(nn.Module):
+    _instances = 0
+
     def __init__(self, d_model: int, experts: List[nn.Module], gate=None, moe_group=None, mp_group=None, recompute_interval: int = 0,
-                 recompute_ctx=None, top_k: int = 2, dtype=None, device=None):
+                 recompute_ctx=None, top_k: int = 2, dtype=None, device=None, fused_p2p: bool = False, capacity_factor: float = 2.0):
         super().__init__()
+        self.fused_p2p = fused_p2p              # peer-memory dispatch/combine kernels (fused_dispatch.py) instead of NCCL all-to-all
+        self.capacity_factor = capacity_factor
+        MoELayer._instances += 1
+        self._layer_key = MoELayer._instances
         self.d_model = d_model
         self.experts = nn.ModuleList(experts)
         self.num_expert = len(experts)
@@ -83,6 +89,32 @@ class MoELayer(nn.Module):
             return x.new_zeros(0, self.d_model) + sum(p.sum() * 0 for p in self.experts.parameters())
         return torch.cat(outs, 0)
 
+    def _experts_forward_segments(self, xs: torch.Tensor, starts: List[int], counts: List[int], total: int) -> torch.Tensor:
+        """Expert-major rows with every expert's block padded to the dispatch alignment (pad rows are zero)."""
+        outs = []
+        for e in range(self.num_expert):
+            end = starts[e + 1] if e + 1 < self.num_expert else total
+            if end > starts[e]:
+                outs.append(self.experts[e](xs[starts[e]:end]))
+        if not outs:
+            return xs.new_zeros(0, self.d_model) + sum(p.sum() * 0 for p in self.experts.parameters())
+        return torch.cat(outs, 0)
+
+    def _forward_p2p(self, x: torch.Tensor, value: torch.Tensor, gate_idx: torch.Tensor) -> torch.Tensor:
+        from .fused_dispatch import FusedCombine, FusedDispatch, get_dispatcher, make_plan
+
+        disp = get_dispatcher(self.group, self.d_model, self.num_expert, x.dtype, self.capacity_factor)
+        if gate_idx.dim() == 1:
+            gate_idx = gate_idx.unsqueeze(1)
+        plan = make_plan(disp, gate_idx, x.shape[0])
+        xs, seg = FusedDispatch.apply(x, plan, self._layer_key if (self.training and torch.is_grad_enabled()) else None)
+        starts, counts, total = seg[:self.num_expert], seg[self.num_expert:2 * self.num_expert], seg[2 * self.num_expert]
+        if self.recompute_interval > 0 and self.training and xs.requires_grad:
+            ys = recompute(self._experts_forward_segments, xs, starts, counts, total)
+        else:
+            ys = self._experts_forward_segments(xs, starts, counts, total)
+        return FusedCombine.apply(ys, value.reshape(x.shape[0], -1), plan)
+
     def forward(self, inp: torch.Tensor) -> torch.Tensor:
         origin_shape = inp.shape
         x = inp.reshape(-1, origin_shape[-1])
@@ -90,6 +122,11 @@ class MoELayer(nn.Module):
         if mp_world > 1:
             x = Slice.apply(x, self.mp_group.rank, mp_world, self.mp_group)
         value, gate_idx = self.gate(x)
+        if self.fused_p2p and x.is_cuda and self.world_size > 1:
+            out = self._forward_p2p(x, value, gate_idx)
+            if mp_world > 1:
+                out = AllGather.apply(out, self.mp_group.rank, mp_world, self.mp_group)
+            return out.reshape(origin_shape)
         pos, lec, gec = count_by_gate(gate_idx, self.num_expert, self.world_size, group=self.group)
         fwd_counts = gec.view(self.world_size, self.num_expert).sum(0)
         counts = fwd_counts.tolist()                       # host sync #1 (sizes the expert loop); the P2P path avoids it
@@ -121,4 +158,5 @@ def build_moe_layer(hidden: int, ffn_hidden: int, moe_configs: dict, num_layers:
     experts = [ExpertLayer(hidden, ffn_hidden, init_std, out_std, dtype, device) for _ in range(n)]
     gate_cfg = {"type": moe_configs.get("gate", "gshard"), "top_k": int(moe_configs.get("top_k", 2))}
     return MoELayer(hidden, experts, gate=gate_cfg, moe_group=moe_group, mp_group=mp_group if C.group_size(mp_group) > 1 else None,
-                    recompute_interval=int(moe_configs.get("recompute_interval", 0)), dtype=dtype, device=device)
+                    recompute_interval=int(moe_configs.get("recompute_interval", 0)), dtype=dtype, device=device,
+                    fused_p2p=bool(moe_configs.get("fused_p2p", False)), capacity_factor=float(moe_configs.get("p2p_capacity_factor", 2.0)))

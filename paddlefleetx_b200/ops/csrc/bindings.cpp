@@ -416,6 +416,44 @@ void adamw_p2p_broadcast_(const std::vector<int64_t>& peer_param_bufs, int64_t s
                                           dtype_code(grad), (int)lp_dtype, (int)peer_param_bufs.size(), (int)num_ctas, cur_stream()));
 }
 
+// ---- MoE dispatch / combine over peer memory
+std::vector<at::Tensor> moe_route(const at::Tensor& gate_idx, int64_t total_experts) {
+  TORCH_CHECK(gate_idx.is_cuda() && gate_idx.scalar_type() == at::kLong && gate_idx.is_contiguous(), "gate_idx: contiguous int64 CUDA tensor");
+  auto iopt = gate_idx.options().dtype(at::kInt);
+  at::Tensor slot_rank = at::empty({gate_idx.numel()}, iopt), counts = at::empty({total_experts}, iopt);
+  PFX_CUDA_CHECK(pfx::moe_route(gate_idx.data_ptr<int64_t>(), (int)gate_idx.numel(), (int)total_experts, slot_rank.data_ptr<int>(),
+                                counts.data_ptr<int>(), cur_stream()));
+  return {slot_rank, counts};
+}
+std::vector<at::Tensor> moe_dispatch(const at::Tensor& src, c10::optional<at::Tensor> scale, const at::Tensor& gate_idx,
+                                     const at::Tensor& slot_rank, const at::Tensor& counts, const std::vector<int64_t>& peer_recv,
+                                     const std::vector<int64_t>& peer_cnt, const std::vector<int64_t>& peer_flags, at::Tensor& block_counter,
+                                     int64_t src_div, int64_t e_local, int64_t rank, int64_t align, int64_t cap_rows, int64_t epoch,
+                                     int64_t num_ctas) {
+  TORCH_CHECK(src.is_cuda() && src.is_contiguous() && src.dim() == 2, "src: contiguous [rows, H]");
+  const int world = (int)peer_recv.size();
+  auto iopt = gate_idx.options().dtype(at::kInt);
+  at::Tensor slot_loc = at::empty({gate_idx.numel()}, iopt), seg = at::empty({2 * e_local + 2}, iopt);
+  auto pr = to_ptrs(peer_recv), pc = to_ptrs(peer_cnt), pf = to_ptrs(peer_flags);
+  const float* sc = (scale.has_value() && scale->defined()) ? scale->data_ptr<float>() : nullptr;
+  PFX_CUDA_CHECK(pfx::moe_dispatch(src.data_ptr(), sc, gate_idx.data_ptr<int64_t>(), slot_rank.data_ptr<int>(), counts.data_ptr<int>(),
+                                   slot_loc.data_ptr<int>(), seg.data_ptr<int>(), pr.data(), pc.data(), pf.data(),
+                                   reinterpret_cast<unsigned*>(block_counter.data_ptr<int>()), (int)gate_idx.numel(), (int)src_div,
+                                   (int)src.size(1), (int)e_local, world, (int)rank, (int)align, (int)cap_rows, (uint32_t)epoch,
+                                   dtype_code(src), (int)num_ctas, cur_stream()));
+  return {slot_loc, seg};
+}
+void moe_combine(const std::vector<int64_t>& peer_src, const at::Tensor& slot_loc, c10::optional<at::Tensor> weights, at::Tensor& out,
+                 c10::optional<at::Tensor> rows, const std::vector<int64_t>& peer_flags, int64_t topk, int64_t rank, int64_t epoch,
+                 int64_t num_ctas) {
+  auto ps = to_ptrs(peer_src), pf = to_ptrs(peer_flags);
+  const float* w = (weights.has_value() && weights->defined()) ? weights->data_ptr<float>() : nullptr;
+  void* r = (rows.has_value() && rows->defined()) ? rows->data_ptr() : nullptr;
+  PFX_CUDA_CHECK(pfx::moe_combine(ps.data(), slot_loc.data_ptr<int>(), w, out.data_ptr(), r, pf.data(), (int)out.size(0), (int)topk,
+                                  (int)out.size(1), (int)peer_src.size(), (int)rank, (uint32_t)epoch, dtype_code(out), (int)num_ctas,
+                                  cur_stream()));
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -453,5 +491,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
+  m.def("moe_route", &moe_route);
+  m.def("moe_dispatch", &moe_dispatch);
+  m.def("moe_combine", &moe_combine);
   m.def("adamw_p2p_broadcast_", &adamw_p2p_broadcast_);
 }

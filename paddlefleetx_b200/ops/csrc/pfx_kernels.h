@@ -52,4 +52,13 @@ cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, flo
                                 float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2, const float* gscale,
                                 const float* found_inf, int grad_dtype, int lp_dtype, int world, int num_sms, cudaStream_t st);
 
+// moe_kernels.cu — expert-parallel dispatch / combine over peer memory
+cudaError_t moe_route(const int64_t* gate_idx, int num_slots, int total_experts, int* slot_rank, int* counts, cudaStream_t st);
+cudaError_t moe_dispatch(const void* src, const float* scale, const int64_t* gate_idx, const int* slot_rank, const int* counts, int* slot_loc,
+                         int* seg, void** peer_recv, void** peer_cnt, void** peer_flags, unsigned* block_counter, int num_slots, int src_div,
+                         int H, int e_local, int world, int rank, int align, int cap_rows, uint32_t epoch, int dtype, int num_ctas,
+                         cudaStream_t st);
+cudaError_t moe_combine(void** peer_src, const int* slot_loc, const float* weights, void* out, void* rows, void** peer_flags, int T, int topk,
+                        int H, int world, int rank, uint32_t epoch, int dtype, int num_ctas, cudaStream_t st);
+
 }  // namespace pfx

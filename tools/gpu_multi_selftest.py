@@ -189,6 +189,38 @@ def main():
     errs = [relerr(a, b_) for a, b_ in zip(m2.parameters(), m1.parameters())]
     report("zero_p2p_vs_nccl", errs=errs, ok=max(errs) < 5e-3)
 
+    # ---------------------------------------------------------------- MoE: peer-memory dispatch/combine == NCCL all-to-all path
+    from paddlefleetx_b200.models.language_model.moe.moe_layer import ExpertLayer, MoELayer
+
+    hc3 = HybridCommunicateGroup(dp=world)
+    mg = hc3.get_moe_group()
+    hm, e_local, tok = 1024, 2, 8192
+    torch.manual_seed(7 + rank)
+    def make_moe(fused):
+        torch.manual_seed(7 + rank)
+        ex = [ExpertLayer(hm, 4 * hm, dtype=torch.bfloat16, device="cuda") for _ in range(e_local)]
+        return MoELayer(hm, ex, gate={"type": "naive", "top_k": 2}, moe_group=mg, dtype=torch.bfloat16, device="cuda", fused_p2p=fused)
+    l_ref, l_p2p = make_moe(False), make_moe(True)
+    l_p2p.load_state_dict(l_ref.state_dict())
+    torch.manual_seed(99 + rank)
+    xin = (torch.randn(tok, hm, device="cuda") * 0.5).bfloat16()
+    gout = (torch.randn(tok, hm, device="cuda") * 0.1).bfloat16()
+    outs = []
+    for layer in (l_ref, l_p2p):
+        xi = xin.clone().requires_grad_(True)
+        y = layer(xi)
+        y.backward(gout)
+        outs.append([y.detach(), xi.grad.detach()] + [p.grad.detach().float() for p in layer.parameters()])
+    errs = [relerr(a, b_) for a, b_ in zip(outs[1], outs[0])]
+    def moe_step(layer):
+        def f():
+            xi = xin.clone().requires_grad_(True)
+            layer(xi).backward(gout)
+        return f
+    t_ref, t_p2p = timed(moe_step(l_ref), iters=5), timed(moe_step(l_p2p), iters=5)
+    report("moe_p2p_dispatch_combine", errs=[round(e, 5) for e in errs], ok=max(errs) < 3e-2, ms_nccl=t_ref, ms_p2p=t_p2p,
+           shape=dict(tokens=tok, hidden=hm, experts_per_rank=e_local, topk=2))
+
     dist.barrier()
     if rank == 0:
         n_ok = sum(1 for v in res.values() if v.get("ok"))
