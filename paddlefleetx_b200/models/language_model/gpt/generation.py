@@ -67,6 +67,10 @@ class GPTForGeneration(nn.Module):
         self.use_topp_sampling = bool(cfg.get("use_topp_sampling", True))
         self.sync_every = int(cfg.get("sync_every", 8))
         self.max_dec_len_limit = int(cfg.get("max_dec_len_limit", 512))
+        # decode steps replayed from a CUDA graph (static KV cache + masked full-length attention); reference decodes eagerly
+        self.use_cuda_graph = bool(cfg.get("use_cuda_graph", True))
+        self._graphs = {}
+        self._force_static = bool(cfg.get("force_static_decode", False))   # exercise the static-cache step without a GPU (tests)
         if self.decode_strategy not in ("sampling", "greedy_search"):
             raise ValueError(f"decode_strategy {self.decode_strategy!r} is not implemented (sampling | greedy_search); "
                              "the reference accepts beam_search in its validator and then rejects it as well")
@@ -123,7 +127,13 @@ class GPTForGeneration(nn.Module):
         valid, pos = self._prompt_masks(input_ids, self.pad_token_id, attention_mask)
         if position_ids is not None:
             pos = position_ids
-        caches = self.gpt.new_caches(b, total_len)
+        graph_state = self._graph_state(b, total_len, dev) if (self.use_cuda_graph and (dev.type == "cuda" or self._force_static) and self.gpt.mp_group is None) else None
+        if graph_state is not None:
+            caches = graph_state["caches"]
+            for c in caches:
+                c.reset()
+        else:
+            caches = self.gpt.new_caches(b, total_len)
         key_valid = torch.zeros(b, total_len, dtype=torch.bool, device=dev)
         key_valid[:, :prompt_len] = valid
         # prefill: causal + padding mask
@@ -176,11 +186,64 @@ class GPTForGeneration(nn.Module):
                 break
             key_valid[:, prompt_len + step] = True
             cur = prompt_len + step + 1
-            dmask = _to_additive(key_valid[:, :cur].view(b, 1, 1, cur), hidden_dtype(self.gpt))
-            hidden = self.gpt(next_tok, next_pos, dmask, caches)
+            if graph_state is not None:
+                logits = self._graph_decode(graph_state, next_tok, next_pos, key_valid, prompt_len + step)
+            else:
+                dmask = _to_additive(key_valid[:, :cur].view(b, 1, 1, cur), hidden_dtype(self.gpt))
+                hidden = self.gpt(next_tok, next_pos, dmask, caches)
+                logits = self._lm_logits(hidden)[:, 0, :].float()
             next_pos = next_pos + 1
-            logits = self._lm_logits(hidden)[:, 0, :].float()
         return out_ids[:, :steps_done], scores
+
+
+def _graph_methods():
+    """CUDA-graph decode: one captured step = embeddings + all layers (KV written at a device-side index, attention over the whole
+    static cache with an additive validity mask) + LM head.  Captured lazily per (batch, total_len); replays cost one launch."""
+
+    def _graph_state(self, b: int, total_len: int, dev):
+        key = (b, total_len)
+        st = self._graphs.get(key)
+        if st is None:
+            dt = hidden_dtype(self.gpt)
+            st = {"caches": self.gpt.new_caches(b, total_len), "graph": None,
+                  "tok": torch.zeros(b, 1, dtype=torch.long, device=dev), "pos": torch.zeros(b, 1, dtype=torch.long, device=dev),
+                  "idx": torch.zeros(1, dtype=torch.long, device=dev), "mask": torch.zeros(b, 1, 1, total_len, dtype=dt, device=dev),
+                  "logits": None}
+            if len(self._graphs) >= 4:                      # bound the memory held by stale shapes
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = st
+        return st
+
+    def _decode_static(self, st):
+        hidden = self.gpt(st["tok"], st["pos"], st["mask"], st["caches"])
+        return self._lm_logits(hidden)[:, 0, :].float()
+
+    def _graph_decode(self, st, next_tok, next_pos, key_valid, write_index: int):
+        st["tok"].copy_(next_tok)
+        st["pos"].copy_(next_pos)
+        st["idx"].fill_(write_index)
+        st["mask"].copy_(_to_additive(key_valid.view(key_valid.shape[0], 1, 1, -1), st["mask"].dtype))
+        for c in st["caches"]:
+            c.static_index = st["idx"]
+        if st["tok"].device.type != "cuda":
+            return self._decode_static(st)
+        if st["graph"] is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                    # warm-up outside capture (lazy inits, autotune-free but allocates)
+                self._decode_static(st)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["logits"] = self._decode_static(st)
+            st["graph"] = g
+        st["graph"].replay()
+        return st["logits"]
+
+    return _graph_state, _decode_static, _graph_decode
+
+
+GPTForGeneration._graph_state, GPTForGeneration._decode_static, GPTForGeneration._graph_decode = _graph_methods()
 
 
 def hidden_dtype(model: gpt.GPTModel):

@@ -55,8 +55,19 @@ class KVCache:
         self.k = torch.zeros(batch, max_len, heads, head_dim, dtype=dtype, device=device)
         self.v = torch.zeros_like(self.k)
         self.length = 0
+        # graph mode: the write position is a device tensor and the whole buffer is attended (invalid keys are masked), so a
+        # decode step has static shapes and can be replayed from a CUDA graph
+        self.static_index: Optional[torch.Tensor] = None
+
+    def reset(self) -> None:
+        self.length = 0
+        self.static_index = None
 
     def append(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.static_index is not None:
+            self.k.index_copy_(1, self.static_index, k)
+            self.v.index_copy_(1, self.static_index, v)
+            return self.k, self.v
         n = k.shape[1]
         self.k[:, self.length:self.length + n] = k
         self.v[:, self.length:self.length + n] = v

@@ -416,6 +416,16 @@ void adamw_p2p_broadcast_(const std::vector<int64_t>& peer_param_bufs, int64_t s
                                           dtype_code(grad), (int)lp_dtype, (int)peer_param_bufs.size(), (int)num_ctas, cur_stream()));
 }
 
+at::Tensor gemv_skinny(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1), "gemv_skinny: x [M,K], w [N,K]");
+  TORCH_CHECK(x.scalar_type() == w.scalar_type(), "gemv_skinny: dtype mismatch");
+  at::Tensor y = at::empty({x.size(0), w.size(0)}, x.options());
+  const void* b = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  PFX_CUDA_CHECK(pfx::gemv_skinny(x.data_ptr(), w.data_ptr(), b, y.data_ptr(), (int)x.size(0), (int)w.size(0), (int)x.size(1), dtype_code(x),
+                                  at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream()));
+  return y;
+}
+
 // ---- MoE dispatch / combine over peer memory
 std::vector<at::Tensor> moe_route(const at::Tensor& gate_idx, int64_t total_experts) {
   TORCH_CHECK(gate_idx.is_cuda() && gate_idx.scalar_type() == at::kLong && gate_idx.is_contiguous(), "gate_idx: contiguous int64 CUDA tensor");
@@ -491,6 +501,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
+  m.def("gemv_skinny", &gemv_skinny);
   m.def("moe_route", &moe_route);
   m.def("moe_dispatch", &moe_dispatch);
   m.def("moe_combine", &moe_combine);

@@ -101,6 +101,13 @@ class _LinearFn(torch.autograd.Function):
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """weight is ``[out, in]``."""
+    if (x.is_cuda and x.dtype == weight.dtype and x.dtype in (torch.bfloat16, torch.float16) and weight.is_contiguous()
+            and x.numel() // x.shape[-1] <= 8 and x.shape[-1] % 8 == 0 and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))
+            and _native.available()):
+        # token-by-token decoding: a weight stream, not a tensor-core problem (csrc/gemv_skinny.cu)
+        _count()
+        y = _native.require().gemv_skinny(x.reshape(-1, x.shape[-1]).contiguous(), weight, bias)
+        return y.view(*x.shape[:-1], weight.shape[0])
     if _gemm_ok(x, weight.shape[0], weight.shape[1]) and weight.dtype == torch.bfloat16 and weight.is_contiguous():
         return _LinearFn.apply(x, weight, bias)
     return F.linear(x, weight, bias)

@@ -227,3 +227,25 @@ def test_lora_prefix_qat_prune_smoothquant():
     ref = lin(xs[0])
     q = SQ.smooth_and_quantize(lin, SQ.calibrate(lin, xs))
     assert float((q(xs[0]) - ref).norm() / ref.norm()) < 0.05
+
+
+def test_generation_static_cache_decode_matches_dynamic_cache():
+    """The graph-mode decode step (KV written at a device-side index, masked attention over the whole static cache) produces the
+    same tokens as the growing-view cache, including left-padded prompts."""
+    import torch
+
+    from paddlefleetx_b200.models.language_model.gpt import model as gpt
+    from paddlefleetx_b200.models.language_model.gpt.generation import GPTForGeneration
+
+    torch.manual_seed(0)
+    core = gpt.GPTModel(vocab_size=128, hidden_size=32, num_layers=2, num_attention_heads=4, ffn_hidden_size=64, max_position_embeddings=64,
+                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg = dict(max_dec_len=6, decode_strategy="greedy_search", eos_token_id=127, pad_token_id=0)
+    dyn = GPTForGeneration(core, dict(cfg, use_cuda_graph=False))
+    sta = GPTForGeneration(core, dict(cfg, use_cuda_graph=True, force_static_decode=True))
+    ids = torch.randint(1, 120, (3, 7))
+    ids[1, :3] = 0                                    # left padding
+    a, _ = dyn.generate(ids)
+    b, _ = sta.generate(ids)
+    c, _ = sta.generate(ids)                          # second call reuses the cached static state
+    assert torch.equal(a, b) and torch.equal(a, c)

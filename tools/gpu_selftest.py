@@ -273,7 +273,29 @@ def check_lowp(kind="int8", M=512, N=512, K=512, cfg=0, time_it=False):
     return res
 
 
+def check_gemv():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    for (M, N, K) in [(1, 4096, 4096), (3, 12288, 4096), (8, 4096, 16384), (5, 50304, 4096), (2, 1000, 1032)]:
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        y = lib.gemv_skinny(x, w, b)
+        ref = x.float() @ w.float().t() + b.float()
+        e = _relerr(y, ref)
+        ok = ok and e < 1e-2
+        med, best = _time(lambda: lib.gemv_skinny(x, w, b))
+        med_c, _ = _time(lambda: torch.nn.functional.linear(x, w, b))
+        med_t, _ = _time(lambda: lib.gemm(x, w, b, None, True, True, 1, 0, 0))
+        res[f"{M}x{N}x{K}"] = dict(err=round(e, 5), ms=round(med, 4), gbs=round(N * K * 2 / med / 1e6, 1), cublas_ms=round(med_c, 4),
+                                   tcgen05_gemm_ms=round(med_t, 4))
+    return dict(ok=ok, shapes=res)
+
+
 CHECKS = {
+    "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
     "gemm_nt_1cta_n128": lambda: check_gemm(True, True, 3),
     "gemm_nt_2cta": lambda: check_gemm(True, True, 2),
@@ -311,7 +333,7 @@ CHECKS = {
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] in CHECKS:
+    if len(sys.argv) == 2 and sys.argv[1] in CHECKS:
         name = sys.argv[1]
         try:
             res = CHECKS[name]()
