@@ -187,22 +187,33 @@ __global__ void adamw_p2p_kernel(PeerPtrs params, size_t shard_offset, float* __
   const float gs = gscale ? gscale[0] : 1.f;
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float decay = 1.f - lr * wd, omb1 = 1.f - beta1, omb2 = 1.f - beta2;
   const size_t nvec = n >> 3;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    float w8[8];
+    float g[8], w8[8], mm[8], vv[8];
+    // all loads first (7 independent 16-byte / 8-byte requests per thread in flight), then math, then stores
+    load4<TG>(grad + i * 8, *reinterpret_cast<float(*)[4]>(&g[0]));
+    load4<TG>(grad + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&g[4]));
+    load4<float>(master + i * 8, *reinterpret_cast<float(*)[4]>(&w8[0]));
+    load4<float>(master + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&w8[4]));
+    load4<float>(m + i * 8, *reinterpret_cast<float(*)[4]>(&mm[0]));
+    load4<float>(m + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&mm[4]));
+    load4<float>(v + i * 8, *reinterpret_cast<float(*)[4]>(&vv[0]));
+    load4<float>(v + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&vv[4]));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const size_t e = i * 8 + j;
-      const float g = to_f32<TG>(grad[e]) * gs;
-      float w = master[e];
-      const float mi = beta1 * m[e] + (1.f - beta1) * g;
-      const float vi = beta2 * v[e] + (1.f - beta2) * g * g;
-      m[e] = mi; v[e] = vi;
-      w = w * (1.f - lr * wd) - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
-      master[e] = w;
-      w8[j] = w;
+      const float gj = g[j] * gs;
+      mm[j] = beta1 * mm[j] + omb1 * gj;
+      vv[j] = beta2 * vv[j] + omb2 * gj * gj;
+      w8[j] = w8[j] * decay - step_size * mm[j] / (sqrtf(vv[j]) * inv_sqrt_bc2 + eps);
     }
+    store4<float>(m + i * 8, *reinterpret_cast<float(*)[4]>(&mm[0]));
+    store4<float>(m + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&mm[4]));
+    store4<float>(v + i * 8, *reinterpret_cast<float(*)[4]>(&vv[0]));
+    store4<float>(v + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&vv[4]));
+    store4<float>(master + i * 8, *reinterpret_cast<float(*)[4]>(&w8[0]));
+    store4<float>(master + i * 8 + 4, *reinterpret_cast<float(*)[4]>(&w8[4]));
     const uint4 packed = pack8<TP>(w8);
     for (int p = 0; p < world; ++p)
       st_stream(reinterpret_cast<uint4*>(reinterpret_cast<TP*>(params.p[p]) + shard_offset) + i, packed);

@@ -159,31 +159,63 @@ cudaError_t clip_coef(const float* sq, float inv_loss_scale, float clip_norm, fl
 // ------------------------------------------------------------------ flat multi-precision AdamW
 // One launch updates a whole flat shard: fp32 master + moments, optional low-precision mirror written in
 // the same pass (this mirror is what ZeRO broadcasts / the next forward reads).
+// 28-32 B of traffic per element and nothing to reuse: the kernel is a pure stream.  Every thread moves two independent
+// 4-element packets per iteration (16-byte accesses on the fp32 state, 8-byte on bf16 grads / weights) so that enough
+// bytes are in flight per SM to cover HBM latency; the scalar tail is handled by the last threads.
 template <typename TG, typename TP>
-__global__ void adamw_kernel(TP* __restrict__ p_lp, float* __restrict__ master, const TG* __restrict__ grad, float* __restrict__ m,
-                             float* __restrict__ v, size_t n, float lr, float beta1, float beta2, float eps, float wd, float bc1,
-                             float bc2, const float* __restrict__ gscale, const float* __restrict__ found_inf) {
+__global__ void __launch_bounds__(256) adamw_kernel(TP* __restrict__ p_lp, float* __restrict__ master, const TG* __restrict__ grad,
+                                                    float* __restrict__ m, float* __restrict__ v, size_t n, float lr, float beta1, float beta2,
+                                                    float eps, float wd, float bc1, float bc2, const float* __restrict__ gscale,
+                                                    const float* __restrict__ found_inf) {
   if (found_inf && found_inf[0] != 0.f) return;
   const float gs = gscale ? gscale[0] : 1.f;
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
-  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
-  for (size_t base = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4; base < n; base += stride) {
+  const float decay = 1.f - lr * wd, omb1 = 1.f - beta1, omb2 = 1.f - beta2;
+  constexpr int kUnroll = 2;
+  const size_t nvec = n >> 2;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = tid; i0 < nvec; i0 += nthreads * kUnroll) {
+    float g[kUnroll][4], w[kUnroll][4], mm[kUnroll][4], vv[kUnroll][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t i = base + k;
-      if (i < n) {
-        const float g = to_f32<TG>(grad[i]) * gs;
-        float w = master[i];
-        const float mi = beta1 * m[i] + (1.f - beta1) * g;
-        const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
-        m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-        w = w * (1.f - lr * wd) - step_size * mi / denom;
-        master[i] = w;
-        if (p_lp) p_lp[i] = from_f32<TP>(w);
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t i = i0 + u * nthreads;
+      if (i < nvec) {
+        load4<TG>(grad + i * 4, g[u]);
+        load4<float>(master + i * 4, w[u]);
+        load4<float>(m + i * 4, mm[u]);
+        load4<float>(v + i * 4, vv[u]);
       }
     }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const size_t i = i0 + u * nthreads;
+      if (i >= nvec) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gj = g[u][j] * gs;
+        mm[u][j] = beta1 * mm[u][j] + omb1 * gj;
+        vv[u][j] = beta2 * vv[u][j] + omb2 * gj * gj;
+        const float denom = sqrtf(vv[u][j]) * inv_sqrt_bc2 + eps;
+        w[u][j] = w[u][j] * decay - step_size * mm[u][j] / denom;
+      }
+      store4<float>(m + i * 4, mm[u]);
+      store4<float>(v + i * 4, vv[u]);
+      store4<float>(master + i * 4, w[u]);
+      if (p_lp) store4<TP>(p_lp + i * 4, w[u]);
+    }
+  }
+  // tail (n % 4 elements)
+  const size_t i = (nvec << 2) + tid;
+  if (i < n) {
+    const float gj = to_f32<TG>(grad[i]) * gs;
+    const float mi = beta1 * m[i] + omb1 * gj;
+    const float vi = beta2 * v[i] + omb2 * gj * gj;
+    m[i] = mi; v[i] = vi;
+    const float wi = master[i] * decay - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    master[i] = wi;
+    if (p_lp) p_lp[i] = from_f32<TP>(wi);
   }
 }
 
@@ -192,9 +224,12 @@ cudaError_t adamw_flat(void* p_lp, float* master, const void* grad, float* m, fl
                        int lp_dtype, int num_sms, cudaStream_t st) {
   if (!n) return cudaSuccess;
   const int threads = 256;
-  size_t g = (n / 4 + threads - 1) / threads;
+  size_t g = (n / 8 + threads - 1) / threads;
   const size_t cap = (size_t)num_sms * 8;
   const int grid = (int)(g < cap ? (g ? g : 1) : cap);
+  // vector accesses need 16-byte aligned state and 8-byte aligned low-precision pointers (flat buffers are 256 B aligned)
+  if ((reinterpret_cast<uintptr_t>(master) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) return cudaErrorMisalignedAddress;
+  if ((reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(p_lp)) & 7) return cudaErrorMisalignedAddress;
 #define PFX_ADAM(TG, TP) adamw_kernel<TG, TP><<<grid, threads, 0, st>>>((TP*)p_lp, master, (const TG*)grad, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2, gscale, found_inf)
   if (grad_dtype == 3) { if (lp_dtype == 1) PFX_ADAM(float, __nv_bfloat16); else if (lp_dtype == 0) PFX_ADAM(float, __half); else PFX_ADAM(float, float); }
   else if (grad_dtype == 1) { if (lp_dtype == 1) PFX_ADAM(__nv_bfloat16, __nv_bfloat16); else PFX_ADAM(__nv_bfloat16, float); }

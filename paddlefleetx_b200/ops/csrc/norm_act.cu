@@ -65,71 +65,116 @@ __global__ void norm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w
 }
 
 // --------------------------------------------------------------------------- LayerNorm / RMSNorm bwd
-// grid-stride over rows; per-thread dw/db partials live in registers and are flushed once per CTA.
-template <typename T, bool kRms, int kVPT>
-__global__ void __launch_bounds__(1024) norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
+// Persistent CTAs grid-stride over rows.  Register budget is what makes or breaks this kernel (an earlier version was
+// compiled under __launch_bounds__(1024) and spilled 128-624 B/thread): x, dy and gamma stay PACKED (4 registers per
+// 8 elements) and are unpacked twice instead of keeping fp32 copies of xhat and dy*gamma, the block size is a template
+// parameter so ptxas gets the real bound, the next row's x / dy are prefetched before the current row's reductions so
+// the CTA always has loads in flight, and the two row sums share one barrier pair.  dgamma / dbeta partials live in
+// registers and are flushed once per CTA.
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  a = warp_sum(a); b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) scratch[w] = make_float2(a, b);
+  __syncthreads();
+  float2 t = (lane < nw) ? scratch[lane] : make_float2(0.f, 0.f);
+  t.x = warp_sum(t.x); t.y = warp_sum(t.y);
+  return t;
+}
+
+template <typename T, bool kRms, int kVPT, int kThreads>
+__global__ void __launch_bounds__(kThreads) norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dx,
                                 float* __restrict__ dw_part, float* __restrict__ db_part, int rows, int cols) {
-  __shared__ float scratch[33];
+  __shared__ float2 scratch[33];
   const int nvec = cols >> 3;
-  float dwp[kVPT][8], dbp[kVPT][8], wv[kVPT][8];
+  float dwp[kVPT][8], dbp[kVPT][8];
+  uint4 wraw[kVPT], xn[kVPT], gn[kVPT];
 #pragma unroll
   for (int i = 0; i < kVPT; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
+    const int vi = threadIdx.x + i * kThreads;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dwp[i][j] = 0.f; dbp[i][j] = 0.f; wv[i][j] = 0.f; }
-    if (vi < nvec) unpack8<T>(__ldg(reinterpret_cast<const uint4*>(w) + vi), wv[i]);
+    for (int j = 0; j < 8; ++j) { dwp[i][j] = 0.f; dbp[i][j] = 0.f; }
+    wraw[i] = vi < nvec ? __ldg(reinterpret_cast<const uint4*>(w) + vi) : make_uint4(0, 0, 0, 0);
+    xn[i] = gn[i] = make_uint4(0, 0, 0, 0);
   }
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * cols);
-    const uint4* gr = reinterpret_cast<const uint4*>(dy + (size_t)row * cols);
-    const float mean = kRms ? 0.f : mean_in[row];
-    const float rstd = rstd_in[row];
-    float xh[kVPT][8], g[kVPT][8];
-    float s1 = 0.f, s2 = 0.f;
+  int row = blockIdx.x;
+  if (row < rows) {
 #pragma unroll
     for (int i = 0; i < kVPT; ++i) {
-      const int vi = threadIdx.x + i * blockDim.x;
+      const int vi = threadIdx.x + i * kThreads;
       if (vi < nvec) {
-        float xv[8], gv[8];
-        unpack8<T>(ld_stream(xr + vi), xv);
-        unpack8<T>(ld_stream(gr + vi), gv);
+        xn[i] = ld_stream(reinterpret_cast<const uint4*>(x + (size_t)row * cols) + vi);
+        gn[i] = ld_stream(reinterpret_cast<const uint4*>(dy + (size_t)row * cols) + vi);
+      }
+    }
+  }
+  for (; row < rows; row += gridDim.x) {
+    uint4 xc[kVPT], gc[kVPT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mean) * rstd;
-          g[i][j] = gv[j] * wv[i][j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
-          dwp[i][j] += gv[j] * xh[i][j];
-          dbp[i][j] += gv[j];
+    for (int i = 0; i < kVPT; ++i) { xc[i] = xn[i]; gc[i] = gn[i]; }
+    const int nrow = row + gridDim.x;
+    if (nrow < rows) {                            // prefetch: in flight across this row's reductions and stores
+#pragma unroll
+      for (int i = 0; i < kVPT; ++i) {
+        const int vi = threadIdx.x + i * kThreads;
+        if (vi < nvec) {
+          xn[i] = ld_stream(reinterpret_cast<const uint4*>(x + (size_t)nrow * cols) + vi);
+          gn[i] = ld_stream(reinterpret_cast<const uint4*>(dy + (size_t)nrow * cols) + vi);
         }
       }
     }
-    const float c2 = block_sum(s2, scratch) / cols;
-    const float c1 = kRms ? 0.f : block_sum(s1, scratch) / cols;
+    const float mean = kRms ? 0.f : mean_in[row];
+    const float rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVPT; ++i) {
+      const int vi = threadIdx.x + i * kThreads;
+      if (vi < nvec) {
+        float xv[8], gv[8], wv[8];
+        unpack8<T>(xc[i], xv);
+        unpack8<T>(gc[i], gv);
+        unpack8<T>(wraw[i], wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mean) * rstd;
+          const float gw = gv[j] * wv[j];
+          s1 += gw;
+          s2 += gw * xh;
+          dwp[i][j] += gv[j] * xh;
+          if (!kRms) dbp[i][j] += gv[j];
+        }
+      }
+    }
+    const float2 sums = block_sum2(s1, s2, scratch);
+    const float c1 = kRms ? 0.f : sums.x / cols;
+    const float c2 = sums.y / cols;
     uint4* dxr = reinterpret_cast<uint4*>(dx + (size_t)row * cols);
 #pragma unroll
     for (int i = 0; i < kVPT; ++i) {
-      const int vi = threadIdx.x + i * blockDim.x;
+      const int vi = threadIdx.x + i * kThreads;
       if (vi < nvec) {
-        float o[8];
+        float xv[8], gv[8], wv[8], o[8];
+        unpack8<T>(xc[i], xv);
+        unpack8<T>(gc[i], gv);
+        unpack8<T>(wraw[i], wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - c1 - xh[i][j] * c2);
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[j] * wv[j] - c1 - (xv[j] - mean) * rstd * c2);
         st_stream(dxr + vi, pack8<T>(o));
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < kVPT; ++i) {
-    const int vi = threadIdx.x + i * blockDim.x;
+    const int vi = threadIdx.x + i * kThreads;
     if (vi < nvec) {
-      float* dwo = dw_part + (size_t)blockIdx.x * cols + vi * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dwo[j] = dwp[i][j];
+      float4* dwo = reinterpret_cast<float4*>(dw_part + (size_t)blockIdx.x * cols + vi * 8);
+      dwo[0] = make_float4(dwp[i][0], dwp[i][1], dwp[i][2], dwp[i][3]);
+      dwo[1] = make_float4(dwp[i][4], dwp[i][5], dwp[i][6], dwp[i][7]);
       if (!kRms) {
-        float* dbo = db_part + (size_t)blockIdx.x * cols + vi * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dbo[j] = dbp[i][j];
+        float4* dbo = reinterpret_cast<float4*>(db_part + (size_t)blockIdx.x * cols + vi * 8);
+        dbo[0] = make_float4(dbp[i][0], dbp[i][1], dbp[i][2], dbp[i][3]);
+        dbo[1] = make_float4(dbp[i][4], dbp[i][5], dbp[i][6], dbp[i][7]);
       }
     }
   }
@@ -191,18 +236,24 @@ int norm_bwd_num_parts(int rows, int num_sms) { int g = num_sms * 2; return rows
 template <typename T>
 static cudaError_t norm_bwd_t(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, void* dw,
                               void* db, float* workspace, int rows, int cols, bool rms, int num_sms, cudaStream_t st) {
-  if (cols % 8) return cudaErrorInvalidValue;
-  const int vpt = cols <= 16384 ? 2 : 4;       // fewer vectors per thread: the backward keeps 5 fp32 copies in registers
-  const int threads = norm_threads_vpt(cols, vpt);
-  if (threads > 1024) return cudaErrorInvalidValue;
+  if (cols % 8 || cols > 32768) return cudaErrorInvalidValue;
+  const int nvec = cols / 8;
   const int parts = norm_bwd_num_parts(rows, num_sms);
   float* dwp = workspace;
   float* dbp = workspace + (size_t)parts * cols;
-#define PFX_NB(RMS, VPT)                                                                                                        \
-  norm_bwd_kernel<T, RMS, VPT><<<parts, threads, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, RMS ? nullptr : mean, rstd, (T*)dx, dwp, \
-                                                          dbp, rows, cols)
-  if (rms) { if (vpt == 2) PFX_NB(true, 2); else PFX_NB(true, 4); }
-  else { if (vpt == 2) PFX_NB(false, 2); else PFX_NB(false, 4); }
+#define PFX_NB(VPT, THREADS)                                                                                                              \
+  do {                                                                                                                                    \
+    if (rms) norm_bwd_kernel<T, true, VPT, THREADS><<<parts, THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, nullptr, rstd,      \
+                                                                              (T*)dx, dwp, dbp, rows, cols);                              \
+    else norm_bwd_kernel<T, false, VPT, THREADS><<<parts, THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx,    \
+                                                                           dwp, dbp, rows, cols);                                         \
+  } while (0)
+  if (nvec <= 128) PFX_NB(1, 128);
+  else if (nvec <= 256) PFX_NB(1, 256);
+  else if (nvec <= 512) PFX_NB(2, 256);
+  else if (nvec <= 1024) PFX_NB(4, 256);
+  else if (nvec <= 2048) PFX_NB(4, 512);
+  else PFX_NB(8, 512);
 #undef PFX_NB
   const int rg = (cols + 31) / 32;
   reduce_partials_kernel<T><<<rg, 256, 0, st>>>(dwp, (T*)dw, parts, cols);

@@ -116,4 +116,29 @@ struct Philox {
   }
 };
 
+// 4-element packets: 16-byte accesses for fp32, 8-byte for bf16/fp16
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&f)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w;
+  } else {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    const T* h = reinterpret_cast<const T*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[j] = to_f32<T>(h[j]);
+  }
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&f)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  } else {
+    uint2 r;
+    T* h = reinterpret_cast<T*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = from_f32<T>(f[j]);
+    *reinterpret_cast<uint2*>(p) = r;
+  }
+}
+
+
 }  // namespace pfx

@@ -85,7 +85,14 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             main_grad = getattr(weight, "main_grad", None)
             if main_grad is not None:
-                lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 2, 0)   # main_grad += dY^T X
+                fresh = getattr(weight, "_grad_fresh", False)      # first touch since clear_grad: store, do not accumulate
+                if main_grad.dtype == torch.float32:
+                    lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 1 if fresh else 2, 0)   # main_grad (+)= dY^T X
+                elif fresh:
+                    lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 0, 0)
+                else:
+                    main_grad.add_(lib.gemm(g2, x2, None, None, False, False, EPI_NONE, 0, 0))
+                weight._grad_fresh = False
                 # autograd still needs a tensor so that post-accumulate hooks (DP / ZeRO bucket readiness)
                 # fire; the engines drop ``weight.grad`` inside that hook when this flag is set.
                 weight.grad_added_to_main_grad = True

@@ -28,7 +28,7 @@ import torch.distributed as dist
 from ..ops import _native
 from ..ops import functional as OF
 from ..parallel import comm_ops as C
-from ..parallel.flat_buffer import FlatGroup, build_flat_groups
+from ..parallel.flat_buffer import FlatGroup, attach_grad_views, build_flat_groups
 from ..utils.log import logger
 from .grad_clip import ClipGradByGlobalNorm, ClipGradForMOEByGlobalNorm
 from .lr_scheduler import LRScheduler
@@ -48,7 +48,8 @@ class FusedAdamW:
                  weight_decay: float = 0.01, grad_clip=None, multi_precision: bool = False, tensor_fusion: bool = True,
                  named_parameters=None, apply_decay_param_fun: Optional[Callable] = None, hcg=None, sharding_stage: int = 1,
                  use_main_grad: bool = False, bucket_mb: int = 512, reduce_overlap: bool = False, broadcast_overlap: bool = False,
-                 use_p2p: bool = False, lazy_init: bool = False, params_are_shards: bool = False, **unused):
+                 use_p2p: bool = False, lazy_init: bool = False, params_are_shards: bool = False, direct_grad: Optional[bool] = None,
+                 **unused):
         self._learning_rate = learning_rate
         self.beta1, self.beta2, self.eps, self.weight_decay = float(beta1), float(beta2), float(epsilon), float(weight_decay)
         self.grad_clip = grad_clip
@@ -108,6 +109,16 @@ class FusedAdamW:
             alloc = self._symm.alloc_tensor
         self.groups: List[FlatGroup] = build_flat_groups(params, key_fn, pad_multiple=self.sh_world, grad_dtype=grad_dtype, alloc_fn=alloc)
         self.groups.sort(key=lambda g: (g.key[0] if g.key[0] >= 0 else 1 << 30))
+        # Direct gradient writes: autograd never owns a view of the flat grad buffer.  ``p.main_grad`` (bf16 or fp32 view) is
+        # the only persistent gradient; the wgrad GEMM stores straight into it (first touch after clear_grad = plain store, no
+        # zero-fill pass and no read-modify-write), every other parameter's grad is moved in by the post-accumulate hook.
+        # That removes the per-parameter ``grad += new`` passes and the whole-buffer memset of the classic layout.
+        self.direct_grad = bool(use_main_grad or ((params[0].is_cuda if direct_grad is None else direct_grad) and not params_are_shards))
+        if self.direct_grad:
+            for g in self.groups:
+                attach_grad_views(g, main_grad=True)
+                for p in g.params:
+                    p._grad_fresh = True
         dev = params[0].device
         self._dev = dev
         for g in self.groups:
@@ -132,7 +143,7 @@ class FusedAdamW:
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._comm_stream = torch.cuda.Stream() if dev.type == "cuda" else None
         self._hooks = []
-        if self.replicas > 1 or use_main_grad:
+        if self.replicas > 1 or self.direct_grad:
             self._register_hooks()
         self._ag_events: Dict[int, "torch.cuda.Event"] = {}
 
@@ -153,12 +164,23 @@ class FusedAdamW:
 
     def clear_grad(self, set_to_zero: bool = True) -> None:
         for g in self.groups:
-            g.grad_buf.zero_()
             g.meta["synced"] = False
             g.meta["pending"] = len(g.params)
-            if self.use_main_grad:
-                for p in g.params:
+            if self.direct_grad:
+                for p in g.params:          # lazy zero: the first writer of the step overwrites (see _finalize_fresh)
                     p.grad = None
+                    p._grad_fresh = True
+            else:
+                g.grad_buf.zero_()
+
+    def _finalize_fresh(self, g: FlatGroup) -> None:
+        """Parameters that received no gradient since ``clear_grad`` still hold last step's values: zero them now."""
+        if not self.direct_grad:
+            return
+        for p in g.params:
+            if p._grad_fresh:
+                p.main_grad.zero_()
+                p._grad_fresh = False
 
     zero_grad = clear_grad
 
@@ -171,13 +193,17 @@ class FusedAdamW:
 
     def _make_hook(self, g: FlatGroup, p: torch.nn.Parameter):
         def hook(param):
-            if self.use_main_grad and param.grad is not None:
+            if self.direct_grad and param.grad is not None:
                 if not getattr(param, "grad_added_to_main_grad", False):
-                    if param.grad.is_cuda and _native.available():
-                        _native.require().accumulate_f32_(param.main_grad.view(-1), param.grad.contiguous().view(-1), 1.0)
+                    mg = param.main_grad
+                    if param._grad_fresh:
+                        mg.copy_(param.grad)
+                    elif mg.dtype == torch.float32 and param.grad.is_cuda and param.grad.dtype != torch.float32 and _native.available():
+                        _native.require().accumulate_f32_(mg.view(-1), param.grad.contiguous().view(-1), 1.0)
                         OF._count()
                     else:
-                        param.main_grad.add_(param.grad.float())
+                        mg.add_(param.grad)
+                param._grad_fresh = False
                 param.grad_added_to_main_grad = False
                 param.grad = None
             if self._accumulating or not self.reduce_overlap:
@@ -204,6 +230,7 @@ class FusedAdamW:
 
     # ------------------------------------------------------------------ gradient sync (DP all-reduce / ZeRO reduce-scatter)
     def _sync_group_grads(self, g: FlatGroup, async_op: bool = False) -> None:
+        self._finalize_fresh(g)
         if g.meta["synced"] or self.replicas == 1 or g.key[3]:
             g.meta["synced"] = True      # expert parameters are private to their rank: no replica reduction
             return

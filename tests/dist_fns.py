@@ -38,13 +38,13 @@ def _reference_losses_and_state(overrides, n_steps, seed=11):
     return cfg, batches, losses, state, init
 
 
-def dp_sharding_matches_single(rank, world, dp, sharding, stage):
+def dp_sharding_matches_single(rank, world, dp, sharding, stage, extra=()):
     gb = 4
     base = [f"Global.global_batch_size={gb}", "Global.local_batch_size=None", "Global.micro_batch_size=1"]
     _, batches, ref_losses, ref_state, init = _reference_losses_and_state(
         ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}"], 4)
     cfg = tiny_gpt_config(base + [f"Distributed.dp_degree={dp}", f"Distributed.sharding.sharding_degree={sharding}",
-                                  f"Distributed.sharding.sharding_stage={stage}"], nranks=world)
+                                  f"Distributed.sharding.sharding_stage={stage}"] + list(extra), nranks=world)
     from paddlefleetx_b200.core import EagerEngine
     from paddlefleetx_b200.distributed.apis import env
     from paddlefleetx_b200.models import build_module

@@ -16,6 +16,12 @@ def test_sharding2_stage2_matches_single():
     run_distributed("dist_fns:dp_sharding_matches_single", 2, 1, 2, 2)
 
 
+def test_sharding2_stage2_direct_grad_overlap_matches_single():
+    # direct gradient writes (no autograd-owned flat views, lazy zero) + overlapped bucket reduction
+    run_distributed("dist_fns:dp_sharding_matches_single", 2, 1, 2, 2,
+                    ("Optimizer.direct_grad=True", "Distributed.sharding.reduce_overlap=True"))
+
+
 def test_dp2_x_sharding2_matches_single():
     run_distributed("dist_fns:dp_sharding_matches_single", 4, 2, 2, 1)
 

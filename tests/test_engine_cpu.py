@@ -75,3 +75,29 @@ def test_fit_loop_logs_and_respects_max_steps(caplog):
         eng.fit(train_data_loader=loader, epoch=1)
     out = caplog.text
     assert out.count("[train] epoch: [0/1]") == 4 and "ips_total:" in out and "tokens/s" in out
+
+
+def test_direct_grad_layout_matches_classic_layout_with_accumulation():
+    """``direct_grad`` (autograd never owns flat-grad views; first touch overwrites, no memset) trains identically to the classic
+    p.grad-view layout, including gradient accumulation and parameters that get no gradient in a step."""
+    import torch
+
+    ov = ["Global.local_batch_size=4", "Global.micro_batch_size=2"]
+    cfg_a = tiny_gpt_config(ov)
+    cfg_b = tiny_gpt_config(ov + ["Optimizer.direct_grad=True"])
+    ea, eb = build_engine(cfg_a), build_engine(cfg_b)
+    eb._module.model.load_state_dict(ea._module.model.state_dict())
+    assert eb.optimizer.direct_grad and not ea.optimizer.direct_grad
+    batches = synthetic_batches(cfg_a, 4, seed=9)
+    la = [float(ea.train_step(b)) for b in batches]
+    lb = [float(eb.train_step(b)) for b in batches]
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-6, (la, lb)
+    for (n, p), (_, q) in zip(ea._module.model.named_parameters(), eb._module.model.named_parameters()):
+        assert torch.allclose(p, q, atol=1e-6), n
+    # a parameter without gradient this step must see zeros, not last step's values
+    opt = eb.optimizer
+    opt.clear_grad()
+    g0 = opt.groups[0]
+    g0.params[0].main_grad.fill_(7.0)
+    opt._finalize_fresh(g0)
+    assert float(g0.params[0].main_grad.abs().sum()) == 0.0
