@@ -255,3 +255,35 @@ def ckpt_reshard_tp_sharding(rank, world, tmpdir):
     eng2.load()
     resumed = [float(eng2.train_step(b)) for b in batches[2:]]
     assert max(abs(a - b) for a, b in zip(cont, resumed)) < 2e-4, (cont, resumed)
+
+
+def moe_exp_ep_matches_single(rank, world):
+    """GShard-style MoE: experts sharded over ep=world (live all-to-all) reproduce the ep=1 layer when every rank feeds the same
+    tokens (outputs and expert gradients of the locally-owned experts)."""
+    from paddlefleetx_b200.models.language_model.moe_exp import MoE
+    from paddlefleetx_b200.parallel.topology import HybridCommunicateGroup
+
+    hcg = HybridCommunicateGroup(dp=world)
+    grp = hcg.get_moe_group()
+    torch.manual_seed(3)
+    expert = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 8))
+    E = 2 * world
+    full = MoE(8, expert, num_experts=E, ep_size=1, k=1, capacity_factor=4.0, use_rts=False)
+    for e in full.fleetx_moe.experts.experts:
+        for p in e.parameters():
+            torch.nn.init.normal_(p, std=0.3)
+    sharded = MoE(8, expert, num_experts=E, ep_size=world, k=1, capacity_factor=4.0, use_rts=False, ep_group=grp)
+    sharded.gate.load_state_dict(full.gate.state_dict())
+    for i, e in enumerate(sharded.fleetx_moe.experts.experts):
+        e.load_state_dict(full.fleetx_moe.experts.experts[rank * 2 + i].state_dict())
+    x = torch.randn(24, 8)
+    y_full, _, _ = full(x)
+    y_sh, _, _ = sharded(x)
+    assert torch.allclose(y_full, y_sh, atol=1e-5), (y_full - y_sh).abs().max()
+    y_full.pow(2).sum().backward()
+    y_sh.pow(2).sum().backward()
+    for i, e in enumerate(sharded.fleetx_moe.experts.experts):
+        ref = full.fleetx_moe.experts.experts[rank * 2 + i]
+        for p, q in zip(e.parameters(), ref.parameters()):
+            # every rank contributed the same tokens -> the owner sees `world` copies of each routed token
+            assert torch.allclose(p.grad, q.grad * world, atol=1e-4), (p.grad - q.grad * world).abs().max()

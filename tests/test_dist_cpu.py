@@ -61,3 +61,7 @@ def test_sharding2_stage3_matches_single():
 
 def test_stage3_with_recompute_and_dp():
     run_distributed("dist_fns:dp_sharding_matches_single", 4, 2, 2, 3)
+
+
+def test_moe_exp_expert_parallel_all_to_all_matches_single():
+    run_distributed("dist_fns:moe_exp_ep_matches_single", 2)

@@ -249,3 +249,29 @@ def test_generation_static_cache_decode_matches_dynamic_cache():
     b, _ = sta.generate(ids)
     c, _ = sta.generate(ids)                          # second call reuses the cached static state
     assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_moe_exp_gating_respects_capacity_and_layer_trains():
+    import torch
+
+    from paddlefleetx_b200.models.language_model.moe_exp import MoE, top1gating, top2gating
+
+    torch.manual_seed(0)
+    logits = torch.randn(64, 4)
+    l1, c1, d1, n1 = top1gating(logits, 1.0, 4, use_rts=False)
+    assert c1.shape == (64, 4, 16) and d1.sum((0, 2)).max() <= 16 and d1.sum((1, 2)).max() <= 1
+    assert d1.sum(0).max() <= 1                            # one token per (expert, slot)
+    l2, c2, d2, _ = top2gating(logits, 1.0, 4)
+    assert c2.shape == (64, 4, 32) and d2.sum((1, 2)).max() <= 2
+    kept_two = d2.sum((1, 2)) == 2
+    assert torch.allclose(c2.sum((1, 2))[kept_two], torch.ones(int(kept_two.sum())), atol=1e-5)
+    assert float(l1) > 0 and float(l2) > 0
+
+    expert = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.GELU(), torch.nn.Linear(32, 16))
+    moe = MoE(16, expert, num_experts=4, k=2, capacity_factor=2.0, use_residual=True)
+    x = torch.randn(2, 12, 16, requires_grad=True)
+    y, l_aux, counts = moe(x)
+    (y.pow(2).mean() + 0.01 * l_aux).backward()
+    assert y.shape == x.shape and counts.sum() == 24 and x.grad is not None
+    assert all(p.grad is not None for p in moe.fleetx_moe.experts.parameters()) and moe.gate.wg.weight.grad is not None
+    assert all(getattr(p, "is_expert", False) for p in moe.fleetx_moe.experts.parameters())

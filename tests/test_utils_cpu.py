@@ -159,3 +159,24 @@ def test_tensor_fusion_helper_groups_and_keeps_values():
         assert torch.equal(p, before[n])
         assert p.data_ptr() >= min(g.param_buf.data_ptr() for g in allg)
     all_reduce_parameters(allg)      # no process group: no-op
+
+
+def test_data_tools_produce_a_corpus_gpt_dataset_can_read(tmp_path):
+    import numpy as np
+
+    from paddlefleetx_b200.data.data_tools.ernie import create_pretraining_data
+    from paddlefleetx_b200.data.data_tools.gpt import preprocess_data, raw_trans_to_json
+
+    raw = tmp_path / "a.txt"
+    raw.write_text("First document. It has two sentences!\nAnd a second line.\n\nSecond document, also long enough.\n\nshort\n")
+    raw_trans_to_json.main(["--input_path", str(raw), "--output_path", str(tmp_path / "corpus")])
+    lines = (tmp_path / "corpus.jsonl").read_text().strip().splitlines()
+    assert len(lines) == 2 and json.loads(lines[0])["text"].startswith("First")
+    preprocess_data.main(["--input_path", str(tmp_path / "corpus.jsonl"), "--output_prefix", str(tmp_path / "c"), "--append_eos",
+                          "--tokenizer_name", "ByteTokenizer"])
+    ids, idx = np.load(tmp_path / "c_ids.npy"), np.load(tmp_path / "c_idx.npz")
+    assert idx["lens"].sum() == ids.size and len(idx["lens"]) == 2
+    create_pretraining_data.main(["--input_path", str(tmp_path / "corpus.jsonl"), "--output_prefix", str(tmp_path / "e"),
+                                  "--tokenizer_name", "ByteTokenizer"])
+    e = np.load(tmp_path / "e_idx.npz")
+    assert e["docs"].tolist() == [0, 3, 4] and e["sents"].sum() == np.load(tmp_path / "e_ids.npy").size
