@@ -13,47 +13,53 @@ namespace pfx {
 
 namespace {
 
-template <typename T, int kRows, int kCols>
+// block = 8 warps arranged as (8 / kSplit) column groups x kSplit K-slices; a column group owns kCols weight rows.
+template <typename T, int kRows, int kCols, int kSplit>
 __global__ void __launch_bounds__(256) gemv_skinny_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ bias,
                                                           T* __restrict__ y, int N, int K) {
-  const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int n0 = warp * kCols;
-  if (n0 >= N) return;
+  constexpr int kGroups = 8 / kSplit;
+  __shared__ float red[8][kCols * kRows];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int group = wid / kSplit, slice = wid % kSplit;
+  const int n0 = (blockIdx.x * kGroups + group) * kCols;
   float acc[kCols][kRows];
 #pragma unroll
   for (int c = 0; c < kCols; ++c)
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[c][r] = 0.f;
-  const uint4* wp[kCols];
+  if (n0 < N) {
+    const uint4* wp[kCols];
 #pragma unroll
-  for (int c = 0; c < kCols; ++c) wp[c] = reinterpret_cast<const uint4*>(w + (size_t)min(n0 + c, N - 1) * K);
-  const uint4* xp = reinterpret_cast<const uint4*>(x);
-  const int kvec = K >> 3;                       // 8 elements per 16-byte vector
-  for (int v0 = lane; v0 < kvec; v0 += 64) {
-    const int v1 = v0 + 32;
-    const bool has1 = v1 < kvec;
-    uint4 wa[kCols], wb[kCols];
+    for (int c = 0; c < kCols; ++c) wp[c] = reinterpret_cast<const uint4*>(w + (size_t)min(n0 + c, N - 1) * K);
+    const uint4* xp = reinterpret_cast<const uint4*>(x);
+    const int kvec = K >> 3;                              // 8 elements per 16-byte vector
+    const int per = ((kvec + kSplit - 1) / kSplit + 31) / 32 * 32;
+    const int v_lo = slice * per, v_hi = min(kvec, v_lo + per);
+    constexpr int kU = 4;                                 // k-steps in flight per lane: kU * kCols 16-byte loads
+    for (int v0 = v_lo + lane; v0 < v_hi; v0 += 32 * kU) {
+      uint4 wr[kU][kCols];
 #pragma unroll
-    for (int c = 0; c < kCols; ++c) {
-      wa[c] = ld_stream(wp[c] + v0);
-      wb[c] = has1 ? ld_stream(wp[c] + v1) : make_uint4(0, 0, 0, 0);
-    }
+      for (int u = 0; u < kU; ++u) {
+        const int v = v0 + u * 32;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      if (half == 1 && !has1) break;
-      const int v = half ? v1 : v0;
-      float xf[kRows][8];
+        for (int c = 0; c < kCols; ++c) wr[u][c] = v < v_hi ? ld_stream(wp[c] + v) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) unpack8<T>(__ldg(xp + (size_t)r * kvec + v), xf[r]);
+      for (int u = 0; u < kU; ++u) {
+        const int v = v0 + u * 32;
+        if (v >= v_hi) break;
+        float xf[kRows][8];
 #pragma unroll
-      for (int c = 0; c < kCols; ++c) {
-        float wf[8];
-        unpack8<T>(half ? wb[c] : wa[c], wf);
+        for (int r = 0; r < kRows; ++r) unpack8<T>(__ldg(xp + (size_t)r * kvec + v), xf[r]);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r)
+        for (int c = 0; c < kCols; ++c) {
+          float wf[8];
+          unpack8<T>(wr[u][c], wf);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[c][r] = fmaf(wf[j], xf[r][j], acc[c][r]);
+          for (int r = 0; r < kRows; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[c][r] = fmaf(wf[j], xf[r][j], acc[c][r]);
+        }
       }
     }
   }
@@ -64,32 +70,41 @@ __global__ void __launch_bounds__(256) gemv_skinny_kernel(const T* __restrict__ 
       float v = acc[c][r];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[c][r] = v;
+      if (lane == 0) red[wid][c * kRows + r] = v;
     }
-  if (lane == 0) {
+  __syncthreads();
+  // one thread per (group, column, row) finishes the K-slice sum and writes the output
+  for (int t = threadIdx.x; t < kGroups * kCols * kRows; t += blockDim.x) {
+    const int g = t / (kCols * kRows), cr = t % (kCols * kRows), c = cr / kRows, r = cr % kRows;
+    const int n = (blockIdx.x * kGroups + g) * kCols + c;
+    if (n >= N) continue;
+    float v = bias ? to_f32<T>(bias[n]) : 0.f;
 #pragma unroll
-    for (int c = 0; c < kCols; ++c) {
-      const int n = n0 + c;
-      if (n >= N) break;
-      const float b = bias ? to_f32<T>(bias[n]) : 0.f;
-#pragma unroll
-      for (int r = 0; r < kRows; ++r) y[(size_t)r * N + n] = from_f32<T>(acc[c][r] + b);
-    }
+    for (int s2 = 0; s2 < kSplit; ++s2) v += red[g * kSplit + s2][cr];
+    y[(size_t)r * N + n] = from_f32<T>(v);
   }
+}
+
+template <typename T, int kRows, int kCols, int kSplit>
+cudaError_t launch_cfg(const T* x, const T* w, const T* bias, T* y, int N, int K, cudaStream_t st) {
+  constexpr int kGroups = 8 / kSplit;
+  const int groups = (N + kCols - 1) / kCols;
+  gemv_skinny_kernel<T, kRows, kCols, kSplit><<<(groups + kGroups - 1) / kGroups, 256, 0, st>>>(x, w, bias, y, N, K);
+  return cudaGetLastError();
 }
 
 template <typename T, int kRows>
 cudaError_t launch_rows(const T* x, const T* w, const T* bias, T* y, int N, int K, int num_sms, cudaStream_t st) {
-  // enough warps to cover the machine twice over; fewer columns per warp when N is small
-  const bool narrow = (N / 4 + 7) / 8 < 2 * num_sms;
-  if (narrow) {
-    const int warps = (N + 1) / 2;
-    gemv_skinny_kernel<T, kRows, 2><<<(warps + 7) / 8, 256, 0, st>>>(x, w, bias, y, N, K);
-  } else {
-    const int warps = (N + 3) / 4;
-    gemv_skinny_kernel<T, kRows, 4><<<(warps + 7) / 8, 256, 0, st>>>(x, w, bias, y, N, K);
-  }
-  return cudaGetLastError();
+  // aim for >= ~24 warps per SM of work; split K across the warps of a block when N alone does not provide that
+  const long target = (long)num_sms * 24;
+  const int cols = (kRows <= 2 || N / 4 < target) ? 2 : 4;
+  const long groups = (N + cols - 1) / cols;
+  int split = 1;
+  while (split < 8 && groups * split < target && K / (split * 2) >= 1024) split *= 2;
+#define PFX_GV(C, S) return launch_cfg<T, kRows, C, S>(x, w, bias, y, N, K, st)
+  if (cols == 2) { if (split == 1) PFX_GV(2, 1); if (split == 2) PFX_GV(2, 2); if (split == 4) PFX_GV(2, 4); PFX_GV(2, 8); }
+  if (split == 1) PFX_GV(4, 1); if (split == 2) PFX_GV(4, 2); if (split == 4) PFX_GV(4, 4); PFX_GV(4, 8);
+#undef PFX_GV
 }
 
 template <typename T>
