@@ -180,3 +180,22 @@ def test_data_tools_produce_a_corpus_gpt_dataset_can_read(tmp_path):
                                   "--tokenizer_name", "ByteTokenizer"])
     e = np.load(tmp_path / "e_idx.npz")
     assert e["docs"].tolist() == [0, 3, 4] and e["sents"].sum() == np.load(tmp_path / "e_ids.npy").size
+
+
+def test_launcher_spawns_ranks_logs_and_restarts(tmp_path):
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worker = tmp_path / "w.py"
+    worker.write_text(
+        "import os, sys\n"
+        "r, w, n = os.environ['RANK'], os.environ['WORLD_SIZE'], int(os.environ['PFX_RESTART_COUNT'])\n"
+        "print(f'hello from {r}/{w} attempt {n}', flush=True)\n"
+        "sys.exit(3 if (r == '1' and n == 0) else 0)\n")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "launch.py"), "--devices", "cpu:2", "--log_dir", str(tmp_path / "log"),
+                        "--max_restart", "1", "--master", "127.0.0.1:29731", str(worker)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    log1 = (tmp_path / "log" / "workerlog.1").read_text()
+    assert "hello from 1/2 attempt 0" in log1 and "hello from 1/2 attempt 1" in log1
+    assert "hello from 0/2" in p.stdout
