@@ -426,6 +426,16 @@ at::Tensor gemv_skinny(const at::Tensor& x, const at::Tensor& w, c10::optional<a
   return y;
 }
 
+at::Tensor gemm_smallm(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, int64_t split) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1), "gemm_smallm: x [M,K], w [N,K]");
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "gemm_smallm: bf16 only");
+  at::Tensor y = at::empty({x.size(0), w.size(0)}, x.options());
+  const void* b = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  PFX_CUDA_CHECK(pfx::gemm_smallm(x.data_ptr(), w.data_ptr(), b, y.data_ptr(), (int)x.size(0), (int)w.size(0), (int)x.size(1), 1, (int)split,
+                                  at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream()));
+  return y;
+}
+
 // ---- MoE dispatch / combine over peer memory
 std::vector<at::Tensor> moe_route(const at::Tensor& gate_idx, int64_t total_experts) {
   TORCH_CHECK(gate_idx.is_cuda() && gate_idx.scalar_type() == at::kLong && gate_idx.is_contiguous(), "gate_idx: contiguous int64 CUDA tensor");
@@ -502,6 +512,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("gemv_skinny", &gemv_skinny);
+  m.def("gemm_smallm", &gemm_smallm);
   m.def("moe_route", &moe_route);
   m.def("moe_dispatch", &moe_dispatch);
   m.def("moe_combine", &moe_combine);

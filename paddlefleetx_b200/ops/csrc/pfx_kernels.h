@@ -55,6 +55,10 @@ cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, flo
 // gemv_skinny.cu — decode-time y = x W^T (+b) for <= 8 activation rows
 cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st);
 
+// gemm_smallm_sm100.cu — swap-AB tcgen05 GEMM, split-K over a cluster with DSMEM reduction (1 <= M <= 128, bf16)
+cudaError_t gemm_smallm(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int split, int num_sms,
+                        cudaStream_t st);
+
 // moe_kernels.cu — expert-parallel dispatch / combine over peer memory
 cudaError_t moe_route(const int64_t* gate_idx, int num_slots, int total_experts, int* slot_rank, int* counts, cudaStream_t st);
 cudaError_t moe_dispatch(const void* src, const float* scale, const int64_t* gate_idx, const int* slot_rank, const int* counts, int* slot_loc,

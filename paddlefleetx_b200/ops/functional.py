@@ -12,6 +12,7 @@ LayerNorm, ``softmax_mask_fuse_upper_triangle``, ``c_softmax_with_cross_entropy`
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -21,6 +22,7 @@ from . import _native
 from ..parallel.rng import get_rng_state_tracker
 
 _LOWP = (torch.bfloat16, torch.float16)
+_SMALLM = os.environ.get("PFX_SMALLM_GEMM", "1") == "1"
 
 # launch accounting for bench.py ("gpu_launches": kernels of OURS inside the timed region)
 _launch_count = 0
@@ -114,6 +116,13 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
         # token-by-token decoding: a weight stream, not a tensor-core problem (csrc/gemv_skinny.cu)
         _count()
         y = _native.require().gemv_skinny(x.reshape(-1, x.shape[-1]).contiguous(), weight, bias)
+        return y.view(*x.shape[:-1], weight.shape[0])
+    if (_SMALLM and x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
+            and x.numel() // x.shape[-1] <= 128 and x.shape[-1] % 8 == 0 and weight.shape[0] % 8 == 0
+            and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)) and _native.available()):
+        # prefill / batched decode: swap-AB tcgen05 GEMM, split-K over a cluster (csrc/gemm_smallm_sm100.cu)
+        _count()
+        y = _native.require().gemm_smallm(x.reshape(-1, x.shape[-1]).contiguous(), weight, bias, 0)
         return y.view(*x.shape[:-1], weight.shape[0])
     if _gemm_ok(x, weight.shape[0], weight.shape[1]) and weight.dtype == torch.bfloat16 and weight.is_contiguous():
         return _LinearFn.apply(x, weight, bias)

@@ -294,7 +294,34 @@ def check_gemv():
     return dict(ok=ok, shapes=res)
 
 
+def check_smallm():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    for (M, N, K, split) in [(4, 512, 512, 1), (16, 512, 1024, 2), (7, 4096, 4096, 0), (16, 12288, 4096, 0), (33, 4096, 16384, 0),
+                             (128, 16384, 4096, 0), (100, 50304, 4096, 0), (8, 4096, 16384, 8), (1, 4096, 4096, 0), (2, 16384, 4096, 0),
+                             (128, 4096, 4096, 4)]:
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        y = lib.gemm_smallm(x, w, b, split)
+        torch.cuda.synchronize()
+        ref = x.float() @ w.float().t() + b.float()
+        e = _relerr(y, ref)
+        ok = ok and e < 1e-2
+        med, best = _time(lambda: lib.gemm_smallm(x, w, b, split))
+        med_c, _ = _time(lambda: torch.nn.functional.linear(x, w, b))
+        row = dict(err=round(e, 5), ms=round(med, 4), gbs=round(N * K * 2 / med / 1e6, 1), cublas_ms=round(med_c, 4))
+        if M <= 8:
+            med_g, _ = _time(lambda: lib.gemv_skinny(x, w, b))
+            row["gemv_ms"] = round(med_g, 4)
+        res[f"{M}x{N}x{K}/s{split}"] = row
+    return dict(ok=ok, shapes=res)
+
+
 CHECKS = {
+    "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
     "gemm_nt_1cta_n128": lambda: check_gemm(True, True, 3),
