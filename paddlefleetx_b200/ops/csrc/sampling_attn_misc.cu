@@ -71,11 +71,26 @@ topp_sampling_kernel(const T* __restrict__ probs, const float* __restrict__ top_
     for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) (&hist[0][0])[i] = 0.f;
     __syncthreads();
     const uint32_t prefix = s_prefix;
+    // run-length privatisation: probabilities cluster in a handful of exponent bins (all of them in ONE bin for a flat
+    // distribution), so each thread keeps the current bin's partial sum in a register and touches shared memory only when
+    // the bin changes — the per-element shared atomics were 32-way serialised on exactly those hot bins
+    int cur_bin = -1;
+    float cur_sum = 0.f;
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
       const float p = to_f32<T>(pr[i]);
       const uint32_t key = __float_as_uint(p);
-      if ((key & prefix_mask) == prefix && p > 0.f) atomicAdd(&hist[w][(key >> shift) & 0xFFu], p);
+      if ((key & prefix_mask) == prefix && p > 0.f) {
+        const int bin = (int)((key >> shift) & 0xFFu);
+        if (bin == cur_bin) {
+          cur_sum += p;
+        } else {
+          if (cur_bin >= 0) atomicAdd(&hist[w][cur_bin], cur_sum);
+          cur_bin = bin;
+          cur_sum = p;
+        }
+      }
     }
+    if (cur_bin >= 0) atomicAdd(&hist[w][cur_bin], cur_sum);
     __syncthreads();
     if (threadIdx.x < 256) {
       float s = 0.f;
