@@ -127,7 +127,7 @@ def build_config(args, world: int):
         f"Global.local_batch_size={local}", f"Global.micro_batch_size={micro}", "Global.global_batch_size=None",
         f"Distributed.dp_degree={dp}", f"Distributed.mp_degree={mp}", f"Distributed.pp_degree={pp}",
         f"Distributed.sharding.sharding_degree={sharding}", f"Distributed.sharding.sharding_stage={stage}",
-        f"Distributed.sharding.reduce_overlap={world > 1}", f"Distributed.sharding.use_p2p={bool(args.p2p) if args.p2p >= 0 else False}",
+        f"Distributed.sharding.reduce_overlap={world > 1}", f"Distributed.sharding.broadcast_overlap={world > 1}", f"Distributed.sharding.use_p2p={bool(args.p2p) if args.p2p >= 0 else False}",
         f"Model.use_recompute={recompute != 'none'}", f"Model.recompute_granularity={'full' if recompute == 'none' else recompute}",
         f"Model.sequence_parallel={mp > 1}",
         "Engine.max_steps=1000000", "Engine.eval_freq=-1", "Engine.eval_iters=0", "Engine.logging_freq=1000000",

@@ -179,6 +179,9 @@ class EagerEngine(BasicEngine):
         if env.world_size() > 1 and not hasattr(self._module.model, "optimizer_named_parameters"):
             self._module.model, self._optimizer, self._scaler = wrap_with_fleet(d, self._module.model, self._optimizer, self._scaler)
 
+        if mode == "train" and hasattr(self._optimizer, "install_forward_hooks"):
+            self._optimizer.install_forward_hooks(self._module.model)      # overlapped ZeRO parameter all-gather (no-op otherwise)
+
         self._load_recovery = {"step": 0, "epoch": 0, "rng_state": None}
         self._profiler = None
         if configs.get("Profiler", {}).get("enable", False) and mode == "train":
@@ -444,6 +447,8 @@ class EagerEngine(BasicEngine):
     def save(self, epoch: int = 0, step: int = 0):
         if self._output_dir is None:
             return
+        if hasattr(self._optimizer, "finish_param_sync"):
+            self._optimizer.finish_param_sync()
         model = self._module.model
         if self._sharding_stage == 3 and self._sharding_degree > 1 and hasattr(model, "get_all_parameters"):
             model.get_all_parameters()

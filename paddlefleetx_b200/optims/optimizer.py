@@ -146,6 +146,7 @@ class FusedAdamW:
         if self.replicas > 1 or self.direct_grad:
             self._register_hooks()
         self._ag_events: Dict[int, "torch.cuda.Event"] = {}
+        self._fwd_hooks_installed = False
 
     # ------------------------------------------------------------------ basic API
     @property
@@ -367,9 +368,54 @@ class FusedAdamW:
         if self.sh_world > 1:
             if self.use_p2p and native:
                 self._symm.barrier()          # peers' stores have landed before anyone reads its params
+            elif self.broadcast_overlap and self._comm_stream is not None and self._fwd_hooks_installed:
+                # all-gathers run on the communication stream in FORWARD order (small no-decay bucket, then the buckets of
+                # the first layers ...); each module's forward pre-hook waits only for the buckets it reads, so layer 0 starts
+                # while the gathers of the later layers are still in flight
+                self._comm_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._comm_stream):
+                    for g in sorted(self.groups, key=lambda g: (0 if g.key[0] < 0 else 1, -g.key[0])):
+                        self._all_gather_params(g)
+                        ev = torch.cuda.Event()
+                        ev.record(self._comm_stream)
+                        self._ag_events[id(g)] = ev
             else:
                 for g in self.groups:
                     self._all_gather_params(g)
+
+    # ------------------------------------------------------------------ overlapped parameter all-gather: consumer side
+    def install_forward_hooks(self, model: torch.nn.Module) -> None:
+        """Make every module wait (on the compute stream) for the all-gather of the buckets holding its own parameters."""
+        if not (self.broadcast_overlap and self.sh_world > 1 and self._comm_stream is not None) or self._fwd_hooks_installed:
+            return
+        group_of = {id(p): g for g in self.groups for p in g.params}
+
+        def make(gids):
+            def pre_hook(module, inputs):
+                if self._ag_events:
+                    for gid in gids:
+                        ev = self._ag_events.pop(gid, None)
+                        if ev is not None:
+                            torch.cuda.current_stream().wait_event(ev)
+            return pre_hook
+
+        for mod in model.modules():
+            gids = []
+            for p in mod.parameters(recurse=False):
+                g = group_of.get(id(p))
+                if g is not None and id(g) not in gids:
+                    gids.append(id(g))
+            if gids:
+                mod.register_forward_pre_hook(make(tuple(gids)))
+        self._fwd_hooks_installed = True
+
+    def finish_param_sync(self) -> None:
+        """Block the compute stream until every in-flight parameter all-gather has landed (checkpointing, evaluation of
+        tied / externally-read weights)."""
+        if self._ag_events:
+            for ev in self._ag_events.values():
+                torch.cuda.current_stream().wait_event(ev)
+            self._ag_events.clear()
 
     def _reduce_norm(self, sq: torch.Tensor, moe_sq: Optional[torch.Tensor]) -> torch.Tensor:
         h = self.hcg
@@ -394,6 +440,7 @@ class FusedAdamW:
 
     # ------------------------------------------------------------------ checkpointing
     def state_dict(self) -> dict:
+        self.finish_param_sync()
         sd = {"step": self._step_count, "groups": []}
         for g in self.groups:
             sd["groups"].append({"key": g.key, "numel": g.numel, "lo": g.meta["lo"], "hi": g.meta["hi"],
