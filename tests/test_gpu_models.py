@@ -1,0 +1,147 @@
+"""Model families on a real B200: every zoo member runs forward + backward + optimizer step in bf16 on CUDA through the native
+op layer (the CPU suite only exercises the PyTorch expressions), and the serving / parallel-free engine paths work end to end."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT
+from paddlefleetx_b200.utils import config as C
+
+pytestmark = pytest.mark.gpu
+CFG = os.path.join(ROOT, "paddlefleetx_b200", "configs")
+SMALL_GPT = ["Model.num_layers=2", "Model.hidden_size=256", "Model.num_attention_heads=4", "Model.ffn_hidden_size=1024", "Model.vocab_size=1024",
+             "Model.max_position_embeddings=128", "Data.Train.dataset.max_seq_len=128", "Data.Eval.dataset.max_seq_len=128",
+             "Global.local_batch_size=4", "Global.micro_batch_size=2", "Engine.logging_freq=1", "Data.Train.dataset.name=SyntheticGPTDataset",
+             "Data.Eval.dataset.name=SyntheticGPTDataset", "Data.Train.loader.num_workers=0", "Data.Eval.loader.num_workers=0"]
+
+
+def _engine(cfg):
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models import build_module
+
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    return EagerEngine(configs=cfg, module=build_module(cfg))
+
+
+def _gpt_batches(cfg, n):
+    g = torch.Generator().manual_seed(0)
+    b, s, v = cfg.Global.global_batch_size, cfg.Data.Train.dataset.max_seq_len, cfg.Model.vocab_size
+    out = []
+    for _ in range(n):
+        t = torch.randint(0, v, (b, s + 1), generator=g)
+        out.append([t[:, :-1].contiguous(), torch.arange(s).unsqueeze(0).expand(b, s).contiguous(), t[:, 1:].contiguous(), torch.ones(b, s)])
+    return out
+
+
+@pytest.mark.parametrize("extra", [[], ["Model.use_recompute=True", "Model.recompute_granularity=full"],
+                                   ["Model.use_recompute=True", "Model.recompute_granularity=core_attn"], ["Model.use_rope=True"],
+                                   ["Engine.mix_precision.use_main_grad=True"]])
+def test_gpt_trains_on_gpu_with_native_kernels(extra):
+    from paddlefleetx_b200.ops import functional as OF
+
+    cfg = C.get_config(os.path.join(CFG, "nlp/gpt/pretrain_gpt_345M_single_card.yaml"), SMALL_GPT + extra, nranks=1)
+    eng = _engine(cfg)
+    assert next(eng._module.model.parameters()).dtype == torch.bfloat16 and eng.optimizer.direct_grad
+    OF.reset_launch_count()
+    batch = _gpt_batches(cfg, 1)[0]
+    losses = [float(eng.train_step(batch)) for _ in range(8)]           # same batch: the loss must go down
+    assert OF.native_launch_count() > 100, "native kernels were not used"
+    assert np.isfinite(losses).all() and losses[-1] < losses[0] - 0.5, losses
+
+
+def test_moe_gpt_trains_on_gpu():
+    cfg = C.get_config(os.path.join(CFG, "nlp/moe/pretrain_moe_345M_single_card.yaml"), SMALL_GPT, nranks=1)
+    eng = _engine(cfg)
+    batch = _gpt_batches(cfg, 1)[0]
+    losses = [float(eng.train_step(batch)) for _ in range(6)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+def test_generation_cuda_graph_matches_eager_on_gpu():
+    from paddlefleetx_b200.models.language_model.gpt import model as gpt
+    from paddlefleetx_b200.models.language_model.gpt.generation import GPTForGeneration
+
+    torch.manual_seed(0)
+    core = gpt.GPTModel(vocab_size=1024, hidden_size=256, num_layers=2, num_attention_heads=4, ffn_hidden_size=1024, max_position_embeddings=128,
+                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, dtype=torch.bfloat16, device="cuda")
+    cfg = dict(max_dec_len=10, decode_strategy="greedy_search", eos_token_id=1023, pad_token_id=0)
+    eager = GPTForGeneration(core, dict(cfg, use_cuda_graph=False))
+    graph = GPTForGeneration(core, dict(cfg, use_cuda_graph=True))
+    for bs in (1, 3, 12):
+        ids = torch.randint(1, 1000, (bs, 9), device="cuda")
+        a, _ = eager.generate(ids)
+        b, _ = graph.generate(ids)
+        c, _ = graph.generate(ids)              # replay of the captured graph
+        assert torch.equal(b, c)
+        assert (a == b).float().mean() > 0.9, (a, b)       # bf16 ties may flip an argmax; sequences must essentially agree
+    sam = GPTForGeneration(core, dict(cfg, decode_strategy="sampling", top_p=0.8, use_cuda_graph=True))
+    x, _ = sam.generate(ids, seed=3)
+    y, _ = sam.generate(ids, seed=3)
+    assert torch.equal(x, y)
+
+
+def test_vision_multimodal_and_text_towers_on_gpu():
+    from paddlefleetx_b200.models.multimodal_model.debertav2.modeling import DebertaV2Model
+    from paddlefleetx_b200.models.multimodal_model.imagen import modeling as I
+    from paddlefleetx_b200.models.multimodal_model.imagen import unet as U
+    from paddlefleetx_b200.models.multimodal_model.t5.modeling import T5EncoderModel
+    from paddlefleetx_b200.models.protein_folding import EmbeddingsAndEvoformer
+    from paddlefleetx_b200.models.vision_model.factory import build
+    from paddlefleetx_b200.models.vision_model.moco import MoCo
+    from paddlefleetx_b200.optims import FusedAdamW
+
+    dev = "cuda"
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        vit = build(dict(name="ViT_tiny_patch16_224", img_size=64, patch_size=8, depth=2, class_num=10)).to(dev)
+        opt = FusedAdamW(1e-3, named_parameters=list(vit.named_parameters()))
+        x, y = torch.randn(8, 3, 64, 64, device=dev), torch.randint(0, 10, (8,), device=dev)
+        losses = []
+        for _ in range(5):
+            loss = build(dict(name="CELoss", epsilon=0.1))(vit(x), y)
+            loss.backward()
+            opt.step(); opt.clear_grad()
+            losses.append(float(loss))
+        assert losses[-1] < losses[0]
+        moco = MoCo(dim=8, K=16, backbone="resnet18").to(dev)
+        lg, _ = moco(torch.randn(4, 3, 32, 32, device=dev), torch.randn(4, 3, 32, 32, device=dev))
+        lg.float().logsumexp(1).mean().backward()
+        u = U.Unet(dim=16, text_embed_dim=12, dim_mults=(1, 2), layer_attns=(False, True), layer_cross_attns=(False, True), attn_heads=2,
+                   attn_dim_head=8, max_text_len=6, num_latents=2).to(dev)
+        m = I.ImagenModel([u], image_sizes=[16], text_embed_dim=12, timesteps=2).to(dev)
+        out = m(torch.rand(2, 3, 16, 16, device=dev), text_embeds=torch.randn(2, 4, 12, device=dev), text_masks=torch.ones(2, 4, device=dev))
+        I.ImagenCriterion()(*out).backward()
+        ids = torch.randint(0, 100, (2, 16), device=dev)
+        mask = torch.ones(2, 16, dtype=torch.long, device=dev)
+        t5 = T5EncoderModel(vocab_size=100, d_model=64, d_kv=16, d_ff=128, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu").to(dev)
+        t5(ids, mask).float().sum().backward()
+        deb = DebertaV2Model(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, position_buckets=8,
+                             conv_kernel_size=3).to(dev)
+        deb(ids, mask).float().sum().backward()
+        evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2,
+                                     pair_heads=2).to(dev)
+        o = evo(dict(target_feat=torch.randn(1, 10, 6, device=dev), msa_feat=torch.randn(1, 4, 10, 9, device=dev),
+                     residue_index=torch.arange(10, device=dev)[None]))
+        o["single"].float().sum().backward()
+    torch.cuda.synchronize()
+
+
+def test_ernie_trains_on_gpu(tmp_path):
+    rng = np.random.RandomState(0)
+    sents = rng.randint(2, 6, size=40)
+    lens = rng.randint(8, 24, size=int(sents.sum())).astype(np.int32)
+    np.save(tmp_path / "c_ids.npy", rng.randint(4, 500, size=int(lens.sum())).astype(np.int32))
+    np.savez(tmp_path / "c_idx.npz", lens=lens, docs=np.concatenate([[0], np.cumsum(sents)]))
+    cfg = C.get_config(os.path.join(CFG, "nlp/ernie/pretrain_ernie_base.yaml"),
+                       ["Model.hidden_size=128", "Model.num_hidden_layers=2", "Model.num_attention_heads=4", "Model.vocab_size=512",
+                        "Model.max_position_embeddings=128", f"Data.Train.dataset.input_dir={tmp_path}", f"Data.Eval.dataset.input_dir={tmp_path}",
+                        "Data.Train.dataset.max_seq_length=64", "Data.Train.dataset.vocab_size=500", "Global.local_batch_size=4",
+                        "Global.micro_batch_size=4", "Engine.max_steps=4", "Data.Train.loader.num_workers=0", "Optimizer.lr.max_lr=1e-3"], nranks=1)
+    from paddlefleetx_b200.data import build_dataloader
+
+    eng = _engine(cfg)
+    losses = [float(eng.train_step(b)) for _, b in zip(range(4), build_dataloader(cfg.Data, "Train"))]
+    assert len(losses) >= 2 and np.isfinite(losses).all()
