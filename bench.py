@@ -37,13 +37,14 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--model", default="gpt-6.7b", choices=sorted(MODELS))
-    p.add_argument("--layout", default="auto", help="auto | sharding | mp2_pp2_sharding2 | dp")
+    p.add_argument("--layout", default="auto", help="auto | sharding | mp2_pp2_sharding2 | dp | mpN")
     p.add_argument("--local-batch", type=int, default=8)
     p.add_argument("--micro-batch", type=int, default=0, help="0 = auto")
     p.add_argument("--recompute", default="auto", help="auto | none | full | full_attn | core_attn")
     p.add_argument("--seq-len", type=int, default=1024)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--p2p", type=int, default=-1, help="peer-memory ZeRO kernels: -1 auto, 0 off, 1 on")
+    p.add_argument("--fused-tp", type=int, default=0, help="1: all-gather->GEMM and GEMM->reduce-scatter as single kernels (TP+SP layouts)")
     p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the result invalid)")
     return p.parse_args()
 
@@ -118,8 +119,12 @@ def build_config(args, world: int):
         mp, pp, sharding = 2, 2, 2
     elif layout == "dp":
         sharding, dp = 1, world
-    local = args.local_batch if pp == 1 else args.local_batch * mp * pp
-    micro = args.micro_batch or (args.local_batch if pp == 1 else max(args.local_batch // 2, 1))
+    elif layout.startswith("mp"):            # "mp2", "mp4", ...: tensor + sequence parallel, rest of the world is ZeRO-1 sharding
+        mp = int(layout[2:])
+        assert world % mp == 0
+        sharding = world // mp
+    local = args.local_batch * mp * pp          # per data-rank batch: per-GPU work stays fixed (weak scaling)
+    micro = args.micro_batch or (local if pp == 1 else max(args.local_batch // 2, 1))
     recompute = args.recompute
     if recompute == "auto":
         recompute = "none"
@@ -136,6 +141,8 @@ def build_config(args, world: int):
     ]
     if args.layers:
         ov.append(f"Model.num_layers={args.layers}")
+    if args.fused_tp:
+        ov.append("Fused.tp_comm=True")
     cfg_path = os.path.join(ROOT, "paddlefleetx_b200", "configs", "nlp", "gpt", spec["cfg"])
     cfg = C.get_config(cfg_path, overrides=ov, show=False, nranks=world)
     # synthetic data of the named shape
@@ -243,7 +250,9 @@ def main():
     if rank == 0:
         tokens = global_batch * seq * args.steps
         par = {"single": "single", "sharding": f"sharding{world}_stage1", "dp": f"dp{world}",
-               "mp2_pp2_sharding2": "mp2_pp2_sharding2"}[lay["layout"]]
+               "mp2_pp2_sharding2": "mp2_pp2_sharding2"}.get(lay["layout"])
+        if par is None:
+            par = f"mp{lay['mp']}_sp_sharding{lay['sharding']}_stage1" + ("_fusedtp" if args.fused_tp else "")
         out = {
             "metric": f"GPT-3 {args.model.split('-')[1].upper()} pre-training tokens/sec (whole job, device-timed, max over ranks)",
             "value": tokens / (ms_total / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
