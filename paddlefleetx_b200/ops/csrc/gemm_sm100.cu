@@ -82,23 +82,25 @@ __device__ void ag_push_role(const GemmComm& c, int comm_cta, int num_comm_ctas,
   const int chunks = c.rows_per_rank / chunk_rows;
   const size_t vec_per_row = (size_t)K * 2 / 16;
   const uint4* src = reinterpret_cast<const uint4*>(c.a_local);
-  for (int ch = comm_cta; ch < chunks; ch += num_comm_ctas) {
+  // work item = (chunk, peer): with W ranks a shard has only rows/chunk chunks but (W - 1) destinations each, so the items —
+  // not the chunks — are spread over the communication CTAs (at W = 8 a chunk-per-CTA split left 12 of 16 CTAs idle and
+  // serialised seven 2 MB pushes on each of the others)
+  const int peers = c.ag_world - 1;
+  for (int item = comm_cta; item < chunks * peers; item += num_comm_ctas) {
+    const int ch = item / peers;
+    const int dst = (c.my_rank + 1 + item % peers) % c.ag_world;
     const size_t v0 = (size_t)ch * chunk_rows * vec_per_row, nv = (size_t)chunk_rows * vec_per_row;
-    for (int p = 1; p < c.ag_world; ++p) {
-      const int dst = (c.my_rank + p) % c.ag_world;
-      uint4* out = reinterpret_cast<uint4*>(c.peer_gather[dst]) + (size_t)c.my_rank * c.rows_per_rank * vec_per_row + v0;
-      for (size_t i = threadIdx.x; i < nv; i += 4 * blockDim.x) {
-        uint4 r[4];
+    uint4* out = reinterpret_cast<uint4*>(c.peer_gather[dst]) + (size_t)c.my_rank * c.rows_per_rank * vec_per_row + v0;
+    for (size_t i = threadIdx.x; i < nv; i += 4 * blockDim.x) {
+      uint4 r[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (i + u * blockDim.x < nv) r[u] = __ldg(src + v0 + i + u * blockDim.x);
+      for (int u = 0; u < 4; ++u) if (i + u * blockDim.x < nv) r[u] = __ldg(src + v0 + i + u * blockDim.x);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) if (i + u * blockDim.x < nv) out[i + u * blockDim.x] = r[u];
-      }
+      for (int u = 0; u < 4; ++u) if (i + u * blockDim.x < nv) out[i + u * blockDim.x] = r[u];
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x < c.ag_world && (int)threadIdx.x != c.my_rank)
-      st_release_sys(c.peer_flags[threadIdx.x] + c.my_rank * chunks + ch, c.epoch);
+    if (threadIdx.x == 0) st_release_sys(c.peer_flags[dst] + c.my_rank * chunks + ch, c.epoch);
     __syncthreads();
   }
 }

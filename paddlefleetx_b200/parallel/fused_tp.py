@@ -21,7 +21,7 @@ from ..ops import functional as OF
 from . import comm_ops as C
 from .symmetric_memory import get_allocator
 
-_NUM_COMM_CTAS = 16
+_MAX_COMM_CTAS = 32
 _epoch = [0]
 _bufs: Dict[Tuple, dict] = {}
 
@@ -74,8 +74,10 @@ def ag_gemm(x_shard: torch.Tensor, w: torch.Tensor, bias, group, b_kmajor: bool 
     cur = b["sets"][b["calls"] % 2]
     b["calls"] += 1
     _epoch[0] += 1
+    items = max(rows // b["chunk"], 1) * (group.nranks - 1)          # (chunk, peer) push items, see ag_push_role
+    comm_ctas = max(2, min(_MAX_COMM_CTAS, items) // 2 * 2)          # even: the GEMM runs CTA pairs
     y = lib.gemm_ag(x_shard.contiguous(), w, cur["gathered"], cur["peer_gather"], cur["peer_flags"], cur["flags"], bias, group.rank,
-                    b["chunk"], _NUM_COMM_CTAS, _epoch[0], b_kmajor, 0)
+                    b["chunk"], comm_ctas, _epoch[0], b_kmajor, 0)
     OF._count()
     # the local shard is consumed straight from x_shard by the kernel; complete the gathered buffer for later (wgrad) use
     cur["gathered"][group.rank * rows:(group.rank + 1) * rows].copy_(x_shard)
