@@ -45,6 +45,9 @@ def process_data_configs(config) -> None:
 
 class ErnieModule(BasicModule):
     def __init__(self, configs):
+        from ....parallel import tp_layers as _tp
+
+        _tp.configure(configs.get("Fused", {}))
         self.nranks = env.world_size()
         self.binary_head = bool(configs.Global.get("binary_head", True))
         super().__init__(configs)

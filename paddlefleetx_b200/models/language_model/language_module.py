@@ -128,6 +128,9 @@ def _device(config):
 # ------------------------------------------------------------------------------------ modules
 class LanguageModule(BasicModule):
     def __init__(self, configs):
+        from ...parallel import tp_layers as _tp
+
+        _tp.configure(configs.get("Fused", {}))
         self.nranks = env.world_size()
         self.data_world_size = env.get_data_world_size()
         super().__init__(configs)

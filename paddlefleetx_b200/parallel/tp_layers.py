@@ -28,6 +28,27 @@ from ..ops import functional as OF
 from . import comm_ops as C
 
 
+# process-wide defaults taken from the YAML ``Fused`` section (``configure`` is called by the task modules before the model is
+# built): ``tp_comm`` = fused all-gather->GEMM / GEMM->reduce-scatter kernels in the SP linears, ``fp8_tp_gemm`` = forward GEMMs of
+# the tensor-parallel linears in scaled fp8-e4m3 (tcgen05 kind::f8f6f4, per-token / per-channel scales; backward stays bf16)
+_OPTIONS = {"tp_comm": False, "fp8_tp_gemm": False}
+
+
+def configure(fused_cfg=None) -> dict:
+    fused_cfg = fused_cfg or {}
+    _OPTIONS["tp_comm"] = bool(fused_cfg.get("tp_comm", False))
+    _OPTIONS["fp8_tp_gemm"] = bool(fused_cfg.get("fp8_tp_gemm", False))
+    return dict(_OPTIONS)
+
+
+def _tp_linear(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+    if _OPTIONS["fp8_tp_gemm"] and x.is_cuda:
+        from ..ops.quant import fp8_linear
+
+        return fp8_linear(x, weight, bias)
+    return OF.linear(x, weight, bias)
+
+
 def _mark(p: nn.Parameter, **attrs) -> nn.Parameter:
     for k, v in attrs.items():
         setattr(p, k, v)
@@ -62,7 +83,7 @@ class ColumnParallelLinear(nn.Module):
 
     def forward(self, x: torch.Tensor, skip_bias: bool = False) -> torch.Tensor:
         x = C.copy_to_group(x, self.group)
-        y = OF.linear(x, self.weight, None if skip_bias else self.bias)
+        y = _tp_linear(x, self.weight, None if skip_bias else self.bias)
         return C.gather_last_dim(y, self.group) if self.gather_output else y
 
 
@@ -92,7 +113,7 @@ class RowParallelLinear(nn.Module):
             if self.skip_bias_add:
                 return OF.linear(x, self.weight, None), self.bias
             return OF.linear(x, self.weight, self.bias)
-        y = C.reduce_from_group(OF.linear(x, self.weight, None), self.group)
+        y = C.reduce_from_group(_tp_linear(x, self.weight, None), self.group)
         if self.skip_bias_add:
             return y, self.bias
         return y if self.bias is None else y + self.bias
@@ -120,11 +141,11 @@ class ColumnSequenceParallelLinear(nn.Module):
 
     def forward(self, x: torch.Tensor, skip_bias: bool = False) -> torch.Tensor:
         bias = None if skip_bias else self.bias
-        if self.fused_comm and x.is_cuda and self.world > 1:
+        if (self.fused_comm or _OPTIONS["tp_comm"]) and x.is_cuda and self.world > 1:
             from .fused_tp import all_gather_linear
 
             return all_gather_linear(x, self.weight, bias, self.group)
-        return OF.linear(C.all_gather_seq(x, self.group), self.weight, bias)
+        return _tp_linear(C.all_gather_seq(x, self.group), self.weight, bias)
 
 
 class RowSequenceParallelLinear(nn.Module):
@@ -150,12 +171,12 @@ class RowSequenceParallelLinear(nn.Module):
             self.register_parameter("bias", None)
 
     def forward(self, x: torch.Tensor):
-        if self.fused_comm and x.is_cuda and self.world > 1:
+        if (self.fused_comm or _OPTIONS["tp_comm"]) and x.is_cuda and self.world > 1:
             from .fused_tp import linear_reduce_scatter
 
             y = linear_reduce_scatter(x, self.weight, self.group)
         else:
-            y = C.reduce_scatter_seq(OF.linear(x, self.weight, None), self.group)
+            y = C.reduce_scatter_seq(_tp_linear(x, self.weight, None), self.group)
         if self.skip_bias_add:
             return y, self.bias
         return y if self.bias is None else y + self.bias
