@@ -34,6 +34,8 @@ class _Unit:
         self.gathered = False
         self.pending_grads = 0
         self.grads_attached = False
+        self.gather_event = None       # set while a prefetched all-gather is in flight on the communication stream
+        self.index = 0
 
 
 class GroupShardedStage3(nn.Module):
@@ -53,7 +55,9 @@ class GroupShardedStage3(nn.Module):
         self._comm_stream = torch.cuda.Stream() if next(model.parameters()).is_cuda else None
         self.units: List[_Unit] = []
         self._build_units(unit_classes)
-        for u in self.units:
+        self.prefetch = True
+        for i, u in enumerate(self.units):
+            u.index = i
             self._shard_unit(u)
             self._install_hooks(u)
         self._release_all(force=False)
@@ -101,7 +105,7 @@ class GroupShardedStage3(nn.Module):
     # ------------------------------------------------------------------ hooks
     def _install_hooks(self, u: _Unit) -> None:
         if u.module is not None:
-            u.module.register_forward_pre_hook(lambda m, a, u=u: self._gather(u))
+            u.module.register_forward_pre_hook(lambda m, a, u=u: self._use(u))
             u.module.register_forward_hook(lambda m, a, o, u=u: self._after_forward(u))
             u.module.register_full_backward_pre_hook(lambda m, g, u=u: self._before_backward(u))
         else:
@@ -113,28 +117,56 @@ class GroupShardedStage3(nn.Module):
     def _alloc_full(self, g: dict) -> torch.Tensor:
         return torch.empty(g["total"], dtype=g["shard"].dtype, device=g["shard"].device)
 
-    def _gather(self, u: _Unit) -> None:
+    def _gather(self, u: _Unit, prefetch: bool = False) -> None:
+        """All-gather the unit's parameters.  ``prefetch`` issues the collective on the communication stream and returns at once;
+        the consumer side (`_use`) makes the compute stream wait for it."""
         if u.gathered:
             return
-        for g in u.groups:
-            full = self._alloc_full(g)
-            if self.world > 1 and self.group.process_group is not None:
-                if full.is_cuda:
-                    dist.all_gather_into_tensor(full, g["shard"].data, group=self.group.process_group)
+        side = prefetch and self._comm_stream is not None and self.world > 1
+        if side:
+            self._comm_stream.wait_stream(torch.cuda.current_stream())      # shards are final (optimizer step) before we read them
+        with (torch.cuda.stream(self._comm_stream) if side else contextlib.nullcontext()):
+            for g in u.groups:
+                full = self._alloc_full(g)
+                if self.world > 1 and self.group.process_group is not None:
+                    if full.is_cuda:
+                        dist.all_gather_into_tensor(full, g["shard"].data, group=self.group.process_group)
+                    else:
+                        parts = [torch.empty_like(g["shard"].data) for _ in range(self.world)]
+                        dist.all_gather(parts, g["shard"].data.contiguous(), group=self.group.process_group)
+                        full.copy_(torch.cat(parts))
                 else:
-                    parts = [torch.empty_like(g["shard"].data) for _ in range(self.world)]
-                    dist.all_gather(parts, g["shard"].data.contiguous(), group=self.group.process_group)
-                    full.copy_(torch.cat(parts))
-            else:
-                full.copy_(g["shard"].data)
-            g["full"] = full
-            for p, o, shp in zip(g["params"], g["offsets"], g["shapes"]):
-                p.data = full[o:o + shp.numel()].view(shp)
+                    full.copy_(g["shard"].data)
+                g["full"] = full
+                for p, o, shp in zip(g["params"], g["offsets"], g["shapes"]):
+                    p.data = full[o:o + shp.numel()].view(shp)
+            if side:
+                u.gather_event = torch.cuda.Event()
+                u.gather_event.record(self._comm_stream)
         u.gathered = True
+
+    def _use(self, u: _Unit) -> None:
+        """Gather now if nobody prefetched; otherwise wait for the prefetch.  Then prefetch the neighbour that runs next
+        (the following unit in forward, the preceding one in backward) so its all-gather overlaps this unit's compute."""
+        self._gather(u)
+        if u.gather_event is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_event(u.gather_event)
+            for g in u.groups:
+                if g["full"] is not None:
+                    g["full"].record_stream(cur)         # allocated on the communication stream, consumed here
+            u.gather_event = None
+        if self._comm_stream is not None and self.world > 1 and self.prefetch:
+            j = u.index + (-1 if self._in_backward else 1)
+            if 0 <= j < len(self.units) and not self.units[j].resident and not self.units[j].gathered:
+                self._gather(self.units[j], prefetch=True)
 
     def _release(self, u: _Unit, force: bool = False) -> None:
         if not u.gathered or (u.resident and not force):
             return
+        if u.gather_event is not None:          # prefetched but never consumed: order the free after the collective
+            torch.cuda.current_stream().wait_event(u.gather_event)
+            u.gather_event = None
         for g in u.groups:
             for p in g["params"]:
                 p.data = torch.empty(0, dtype=p.dtype, device=p.device)
@@ -162,7 +194,7 @@ class GroupShardedStage3(nn.Module):
         u.grads_attached = True
 
     def _before_backward(self, u: _Unit) -> None:
-        self._gather(u)
+        self._use(u)
         self._attach_grad_buffers(u)
 
     def _grad_ready(self, u: _Unit) -> None:
