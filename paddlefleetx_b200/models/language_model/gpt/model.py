@@ -128,6 +128,11 @@ class MultiHeadAttention(nn.Module):
     def _core(self, q, k, v, attn_mask):
         scale = 1.0 / math.sqrt(self.head_dim)
         p = self.attn_dropout if self.training else 0.0
+        if (q.shape[1] == 1 and p == 0.0 and q.is_cuda and not torch.is_grad_enabled() and attn_mask is not None and attn_mask.dtype == q.dtype
+                and attn_mask.shape[-1] == k.shape[1] and attn_mask.numel() == q.shape[0] * k.shape[1] and k.is_contiguous() and v.is_contiguous()
+                and self.head_dim in (64, 128) and q.dtype in (torch.bfloat16, torch.float16) and OF.native_available()):
+            # decode step over the static KV cache: one streaming kernel instead of a library attention call
+            return OF.attention_decode(q, k, v, attn_mask, scale)
         if self.use_flash_attn:
             if attn_mask is not None:
                 m = attn_mask if attn_mask.dtype == torch.bool else attn_mask.to(q.dtype)

@@ -436,6 +436,25 @@ at::Tensor gemm_smallm(const at::Tensor& x, const at::Tensor& w, c10::optional<a
   return y;
 }
 
+at::Tensor attention_decode(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, c10::optional<at::Tensor> mask, int64_t L, double scale) {
+  // q [B,1,H,D]; k, v [B,Lmax,H,D] (contiguous cache); mask additive [B,Lmax] in the same dtype, or none
+  PFX_CHECK_CUDA_CONTIG(q); PFX_CHECK_CUDA_CONTIG(k); PFX_CHECK_CUDA_CONTIG(v);
+  TORCH_CHECK(q.dim() == 4 && q.size(1) == 1 && k.dim() == 4 && k.sizes() == v.sizes() && k.size(0) == q.size(0) && k.size(2) == q.size(2) &&
+              k.size(3) == q.size(3) && k.scalar_type() == q.scalar_type(), "attention_decode: shape mismatch");
+  const c10::cuda::CUDAGuard guard(q.device());
+  const void* mp = nullptr;
+  at::Tensor mc;
+  if (mask.has_value() && mask->defined()) {
+    mc = mask->reshape({q.size(0), -1}).to(q.scalar_type()).contiguous();
+    TORCH_CHECK(mc.size(1) == k.size(1), "attention_decode: mask must cover the whole cache");
+    mp = mc.data_ptr();
+  }
+  auto out = at::empty_like(q);
+  PFX_CUDA_CHECK(pfx::attention_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), mp, out.data_ptr(), (int)q.size(0), (int)q.size(2), (int)q.size(3),
+                                       (int)L, (int)k.size(1), (float)scale, dtype_code(q), cur_stream()));
+  return out;
+}
+
 // ---- MoE dispatch / combine over peer memory
 std::vector<at::Tensor> moe_route(const at::Tensor& gate_idx, int64_t total_experts) {
   TORCH_CHECK(gate_idx.is_cuda() && gate_idx.scalar_type() == at::kLong && gate_idx.is_contiguous(), "gate_idx: contiguous int64 CUDA tensor");
@@ -511,6 +530,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
+  m.def("attention_decode", &attention_decode);
   m.def("gemv_skinny", &gemv_skinny);
   m.def("gemm_smallm", &gemm_smallm);
   m.def("moe_route", &moe_route);

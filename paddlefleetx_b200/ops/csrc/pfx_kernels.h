@@ -59,6 +59,10 @@ cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y,
 cudaError_t gemm_smallm(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int split, int num_sms,
                         cudaStream_t st);
 
+// attention_decode.cu — single-query attention over the static KV cache
+cudaError_t attention_decode(const void* q, const void* k, const void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
+                             float scale, int dtype, cudaStream_t st);
+
 // moe_kernels.cu — expert-parallel dispatch / combine over peer memory
 cudaError_t moe_route(const int64_t* gate_idx, int num_slots, int total_experts, int* slot_rank, int* counts, cudaStream_t st);
 cudaError_t moe_dispatch(const void* src, const float* scale, const int64_t* gate_idx, const int* slot_rank, const int* counts, int* slot_loc,

@@ -129,6 +129,20 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
     return F.linear(x, weight, bias)
 
 
+def native_available() -> bool:
+    return _native.available()
+
+
+def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, additive_mask: torch.Tensor, scale: float) -> torch.Tensor:
+    """q [B,1,H,D] against the whole static cache [B,Lmax,H,D]; ``additive_mask`` ([B,1,1,Lmax] or [B,Lmax]) hides padded and
+    not-yet-written positions.  CPU / fallback: the plain softmax expression (also the numerical reference in the tests)."""
+    if q.is_cuda and _native.available():
+        _count()
+        return _native.require().attention_decode(q.contiguous(), k_cache, v_cache, additive_mask, k_cache.shape[1], float(scale))
+    s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k_cache.float()) * scale + additive_mask.reshape(q.shape[0], 1, 1, -1).float()
+    return torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v_cache.float()).to(q.dtype)
+
+
 def matmul_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a[M,K] @ b[N,K]^T without autograd (used by fused comm paths and inference)."""
     if _gemm_ok(a, a.shape[-1], b.shape[0]):

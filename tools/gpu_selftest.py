@@ -320,7 +320,32 @@ def check_smallm():
     return dict(ok=ok, shapes=res)
 
 
+def check_attention_decode():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    for (B, H, D, Lmax, L) in [(1, 32, 128, 136, 136), (4, 32, 128, 1024, 1024), (3, 16, 64, 200, 200), (16, 32, 128, 136, 136)]:
+        q = torch.randn(B, 1, H, D, device="cuda").bfloat16()
+        k = torch.randn(B, Lmax, H, D, device="cuda").bfloat16()
+        v = torch.randn(B, Lmax, H, D, device="cuda").bfloat16()
+        valid = torch.rand(B, Lmax, device="cuda") > 0.3
+        valid[:, 0] = True
+        mask = torch.zeros(B, 1, 1, Lmax, device="cuda").masked_fill(~valid.view(B, 1, 1, Lmax), -1e4).bfloat16()
+        scale = D ** -0.5
+        y = lib.attention_decode(q, k, v, mask, L, scale)
+        s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale + mask.float()
+        ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v.float())
+        e = _relerr(y, ref)
+        ok = ok and e < 1e-2
+        med, _ = _time(lambda: lib.attention_decode(q, k, v, mask, L, scale))
+        med_s, _ = _time(lambda: torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=mask, scale=scale))
+        res[f"B{B}xH{H}xD{D}xL{L}"] = dict(err=round(e, 5), ms=round(med, 4), gbs=round(2 * B * L * H * D * 2 / med / 1e6, 1), sdpa_ms=round(med_s, 4))
+    return dict(ok=ok, shapes=res)
+
+
 CHECKS = {
+    "attention_decode": check_attention_decode,
     "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
