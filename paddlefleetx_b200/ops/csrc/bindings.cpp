@@ -426,6 +426,17 @@ at::Tensor gemv_skinny(const at::Tensor& x, const at::Tensor& w, c10::optional<a
   return y;
 }
 
+at::Tensor gemv_w8a8(const at::Tensor& xq, const at::Tensor& wq, const at::Tensor& xs, const at::Tensor& ws, c10::optional<at::Tensor> bias) {
+  TORCH_CHECK(xq.is_cuda() && xq.scalar_type() == at::kChar && wq.scalar_type() == at::kChar && xq.is_contiguous() && wq.is_contiguous() &&
+              xq.dim() == 2 && wq.dim() == 2 && xq.size(1) == wq.size(1), "gemv_w8a8: int8 x [M,K], w [N,K]");
+  TORCH_CHECK(xs.scalar_type() == at::kFloat && ws.scalar_type() == at::kFloat && xs.numel() == xq.size(0) && ws.numel() == wq.size(0), "gemv_w8a8: scales");
+  at::Tensor y = at::empty({xq.size(0), wq.size(0)}, xq.options().dtype(at::kBFloat16));
+  const void* b = (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr;
+  PFX_CUDA_CHECK(pfx::gemv_w8a8(xq.data_ptr(), wq.data_ptr(), xs.data_ptr<float>(), ws.data_ptr<float>(), b, y.data_ptr(), (int)xq.size(0),
+                                (int)wq.size(0), (int)xq.size(1), at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream()));
+  return y;
+}
+
 at::Tensor gemm_smallm(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, int64_t split) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1), "gemm_smallm: x [M,K], w [N,K]");
   TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16, "gemm_smallm: bf16 only");
@@ -533,6 +544,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_decode", &attention_decode);
   m.def("gemv_skinny", &gemv_skinny);
   m.def("gemm_smallm", &gemm_smallm);
+  m.def("gemv_w8a8", &gemv_w8a8);
   m.def("moe_route", &moe_route);
   m.def("moe_dispatch", &moe_dispatch);
   m.def("moe_combine", &moe_combine);

@@ -107,6 +107,109 @@ cudaError_t launch_rows(const T* x, const T* w, const T* bias, T* y, int N, int 
 #undef PFX_GV
 }
 
+// ---------------------------------------------------------------------------------------------------------------- W8A8 variant
+// int8 weights (per-output-channel scale) x int8 activations (per-row scale): half the weight bytes of the bf16 stream, dot
+// products on dp4a, dequantisation + bias in the finish.  Same warp layout as above (column groups x K-slices).
+template <int kRows, int kCols, int kSplit>
+__global__ void __launch_bounds__(256) gemv_w8a8_kernel(const int8_t* __restrict__ x, const int8_t* __restrict__ w, const float* __restrict__ xs,
+                                                        const float* __restrict__ ws, const __nv_bfloat16* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ y, int N, int K) {
+  constexpr int kGroups = 8 / kSplit;
+  __shared__ int red[8][kCols * kRows];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int group = wid / kSplit, slice = wid % kSplit;
+  const int n0 = (blockIdx.x * kGroups + group) * kCols;
+  int acc[kCols][kRows];
+#pragma unroll
+  for (int c = 0; c < kCols; ++c)
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[c][r] = 0;
+  if (n0 < N) {
+    const int4* wp[kCols];
+#pragma unroll
+    for (int c = 0; c < kCols; ++c) wp[c] = reinterpret_cast<const int4*>(w + (size_t)min(n0 + c, N - 1) * K);
+    const int4* xp = reinterpret_cast<const int4*>(x);
+    const int kvec = K >> 4;                              // 16 int8 per 16-byte vector
+    const int per = ((kvec + kSplit - 1) / kSplit + 31) / 32 * 32;
+    const int v_lo = slice * per, v_hi = min(kvec, v_lo + per);
+    constexpr int kU = 4;
+    for (int v0 = v_lo + lane; v0 < v_hi; v0 += 32 * kU) {
+      int4 wr[kU][kCols];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int v = v0 + u * 32;
+#pragma unroll
+        for (int c = 0; c < kCols; ++c) {
+          if (v < v_hi) {
+            const uint4 t = ld_stream(reinterpret_cast<const uint4*>(wp[c]) + v);
+            wr[u][c] = make_int4((int)t.x, (int)t.y, (int)t.z, (int)t.w);
+          } else {
+            wr[u][c] = make_int4(0, 0, 0, 0);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int v = v0 + u * 32;
+        if (v >= v_hi) break;
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int4 xv = __ldg(xp + (size_t)r * kvec + v);
+#pragma unroll
+          for (int c = 0; c < kCols; ++c) {
+            int a = acc[c][r];
+            a = __dp4a(wr[u][c].x, xv.x, a);
+            a = __dp4a(wr[u][c].y, xv.y, a);
+            a = __dp4a(wr[u][c].z, xv.z, a);
+            a = __dp4a(wr[u][c].w, xv.w, a);
+            acc[c][r] = a;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kCols; ++c)
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      int v = acc[c][r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wid][c * kRows + r] = v;
+    }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kGroups * kCols * kRows; t += blockDim.x) {
+    const int g = t / (kCols * kRows), cr = t % (kCols * kRows), c = cr / kRows, r = cr % kRows;
+    const int n = (blockIdx.x * kGroups + g) * kCols + c;
+    if (n >= N) continue;
+    int v = 0;
+#pragma unroll
+    for (int s2 = 0; s2 < kSplit; ++s2) v += red[g * kSplit + s2][cr];
+    const float f = (float)v * xs[r] * ws[n] + (bias ? __bfloat162float(bias[n]) : 0.f);
+    y[(size_t)r * N + n] = __float2bfloat16(f);
+  }
+}
+
+template <int kRows>
+cudaError_t launch_w8a8_rows(const int8_t* x, const int8_t* w, const float* xs, const float* ws, const __nv_bfloat16* bias, __nv_bfloat16* y, int N,
+                             int K, int num_sms, cudaStream_t st) {
+  const long target = (long)num_sms * 24;
+  const long groups = (N + 1) / 2;
+  int split = 1;
+  while (split < 8 && groups * split < target && K / (split * 2) >= 2048) split *= 2;
+#define PFX_GW(S)                                                                                                             \
+  do {                                                                                                                        \
+    constexpr int kG = 8 / S;                                                                                                 \
+    gemv_w8a8_kernel<kRows, 2, S><<<(int)((groups + kG - 1) / kG), 256, 0, st>>>(x, w, xs, ws, bias, y, N, K);                  \
+    return cudaGetLastError();                                                                                                \
+  } while (0)
+  if (split == 1) PFX_GW(1);
+  if (split == 2) PFX_GW(2);
+  if (split == 4) PFX_GW(4);
+  PFX_GW(8);
+#undef PFX_GW
+}
+
 template <typename T>
 cudaError_t launch(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int num_sms, cudaStream_t st) {
   const T *xx = (const T*)x, *ww = (const T*)w, *bb = (const T*)bias;
@@ -131,6 +234,24 @@ cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y,
   if (dtype == 1) return launch<__nv_bfloat16>(x, w, bias, y, M, N, K, num_sms, st);
   if (dtype == 0) return launch<__half>(x, w, bias, y, M, N, K, num_sms, st);
   return cudaErrorInvalidValue;
+}
+
+cudaError_t gemv_w8a8(const void* x, const void* w, const float* xs, const float* ws, const void* bias, void* y, int M, int N, int K, int num_sms,
+                      cudaStream_t st) {
+  if (M < 1 || M > 8 || K % 16) return cudaErrorInvalidValue;
+  const int8_t *xx = (const int8_t*)x, *ww = (const int8_t*)w;
+  const __nv_bfloat16* bb = (const __nv_bfloat16*)bias;
+  __nv_bfloat16* yy = (__nv_bfloat16*)y;
+  switch (M) {
+    case 1: return launch_w8a8_rows<1>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    case 2: return launch_w8a8_rows<2>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    case 3: return launch_w8a8_rows<3>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    case 4: return launch_w8a8_rows<4>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    case 5: return launch_w8a8_rows<5>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    case 6: return launch_w8a8_rows<6>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    case 7: return launch_w8a8_rows<7>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+    default: return launch_w8a8_rows<8>(xx, ww, xs, ws, bb, yy, N, K, num_sms, st);
+  }
 }
 
 }  // namespace pfx

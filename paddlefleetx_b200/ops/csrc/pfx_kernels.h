@@ -55,6 +55,9 @@ cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, flo
 // gemv_skinny.cu — decode-time y = x W^T (+b) for <= 8 activation rows
 cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st);
 
+cudaError_t gemv_w8a8(const void* x, const void* w, const float* xs, const float* ws, const void* bias, void* y, int M, int N, int K, int num_sms,
+                      cudaStream_t st);
+
 // gemm_smallm_sm100.cu — swap-AB tcgen05 GEMM, split-K over a cluster with DSMEM reduction (1 <= M <= 128, bf16)
 cudaError_t gemm_smallm(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int split, int num_sms,
                         cudaStream_t st);

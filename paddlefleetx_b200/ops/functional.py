@@ -23,6 +23,7 @@ from ..parallel.rng import get_rng_state_tracker
 
 _LOWP = (torch.bfloat16, torch.float16)
 _SMALLM = os.environ.get("PFX_SMALLM_GEMM", "1") == "1"
+_GEMV_MAX_ROWS = 2 if _SMALLM else 8       # measured on B200: the swap-AB tcgen05 kernel wins from 3 rows up (profiles/README.md)
 
 # launch accounting for bench.py ("gpu_launches": kernels of OURS inside the timed region)
 _launch_count = 0
@@ -111,7 +112,7 @@ class _LinearFn(torch.autograd.Function):
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """weight is ``[out, in]``."""
     if (x.is_cuda and x.dtype == weight.dtype and x.dtype in (torch.bfloat16, torch.float16) and weight.is_contiguous()
-            and x.numel() // x.shape[-1] <= 8 and x.shape[-1] % 8 == 0 and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))
+            and x.numel() // x.shape[-1] <= _GEMV_MAX_ROWS and x.shape[-1] % 8 == 0 and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))
             and _native.available()):
         # token-by-token decoding: a weight stream, not a tensor-core problem (csrc/gemv_skinny.cu)
         _count()

@@ -63,7 +63,10 @@ class Int8Linear(nn.Module):
         if x2.is_cuda and _native.use_native(x2) and x2.dtype in (torch.bfloat16, torch.float16) and shp[-1] % 16 == 0 and self.out_features % 8 == 0:
             lib = _native.require()
             xq, xs = lib.quantize_rows(x2.contiguous(), self.smooth, False)
-            y = lib.gemm_lowp(xq, self.weight_q, xs, self.weight_scale, self.bias, 0)
+            if x2.shape[0] <= 8:          # decode: int8 weight stream on dp4a (csrc/gemv_skinny.cu)
+                y = lib.gemv_w8a8(xq, self.weight_q, xs, self.weight_scale, self.bias)
+            else:
+                y = lib.gemm_lowp(xq, self.weight_q, xs, self.weight_scale, self.bias, 0)
             OF._count(2)
             return y.view(*shp[:-1], self.out_features).to(x.dtype)
         xq, xs = quantize_rows_reference(x2, self.smooth)
@@ -71,6 +74,22 @@ class Int8Linear(nn.Module):
         if self.bias is not None:
             y = y + self.bias.float()
         return y.to(x.dtype).view(*shp[:-1], self.out_features)
+
+
+def quantize_tp_linears_int8(model: nn.Module, skip=("word_embeddings",)) -> int:
+    """Serving-time W8A8 conversion of a (single-GPU) model built from the tensor-parallel linear layers: every
+    ``ColumnParallelLinear`` / ``RowParallelLinear`` weight is replaced by an :class:`Int8Linear` (per-output-channel weight scales,
+    dynamic per-token activation scales).  Returns the number of converted layers.  The tied LM head / embedding stays bf16."""
+    from ..parallel.tp_layers import ColumnParallelLinear, RowParallelLinear
+
+    n = 0
+    for name, mod in model.named_modules():
+        if isinstance(mod, (ColumnParallelLinear, RowParallelLinear)) and mod.world == 1 and getattr(mod, "int8", None) is None \
+                and not any(s in name for s in skip) and mod.weight is not None:
+            mod.int8 = Int8Linear.from_float(mod.weight.data, None)
+            mod._parameters["weight"] = None        # free the bf16 copy
+            n += 1
+    return n
 
 
 class _Fp8LinearFn(torch.autograd.Function):

@@ -41,7 +41,11 @@ def configure(fused_cfg=None) -> dict:
     return dict(_OPTIONS)
 
 
-def _tp_linear(x: torch.Tensor, weight: torch.Tensor, bias) -> torch.Tensor:
+def _tp_linear(x: torch.Tensor, weight, bias, owner=None) -> torch.Tensor:
+    int8 = getattr(owner, "int8", None) if owner is not None else None
+    if int8 is not None:                  # serving: W8A8 (weights replaced by ops.quant.quantize_tp_linears_int8)
+        y = int8(x)
+        return y if bias is None else y + bias
     if _OPTIONS["fp8_tp_gemm"] and x.is_cuda:
         from ..ops.quant import fp8_linear
 
@@ -83,7 +87,7 @@ class ColumnParallelLinear(nn.Module):
 
     def forward(self, x: torch.Tensor, skip_bias: bool = False) -> torch.Tensor:
         x = C.copy_to_group(x, self.group)
-        y = _tp_linear(x, self.weight, None if skip_bias else self.bias)
+        y = _tp_linear(x, self.weight, None if skip_bias else self.bias, self)
         return C.gather_last_dim(y, self.group) if self.gather_output else y
 
 
@@ -111,9 +115,9 @@ class RowParallelLinear(nn.Module):
             x = C.scatter_last_dim(x, self.group)
         if self.world == 1:
             if self.skip_bias_add:
-                return OF.linear(x, self.weight, None), self.bias
-            return OF.linear(x, self.weight, self.bias)
-        y = C.reduce_from_group(_tp_linear(x, self.weight, None), self.group)
+                return _tp_linear(x, self.weight, None, self), self.bias
+            return _tp_linear(x, self.weight, self.bias, self)
+        y = C.reduce_from_group(_tp_linear(x, self.weight, None, self), self.group)
         if self.skip_bias_add:
             return y, self.bias
         return y if self.bias is None else y + self.bias

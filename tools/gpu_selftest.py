@@ -320,6 +320,27 @@ def check_smallm():
     return dict(ok=ok, shapes=res)
 
 
+def check_gemv_w8a8():
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    for (M, N, K) in [(1, 4096, 4096), (2, 12288, 4096), (8, 4096, 16384), (4, 16384, 4096), (1, 1000, 1040)]:
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        xq, xs = lib.quantize_rows(x, None, False)
+        wq, ws = lib.quantize_rows(w, None, False)
+        y = lib.gemv_w8a8(xq, wq, xs, ws, b)
+        deq = (xq.float() * xs[:, None]) @ (wq.float() * ws[:, None]).t() + b.float()
+        e = _relerr(y, deq)
+        ok = ok and e < 5e-3
+        med, _ = _time(lambda: lib.gemv_w8a8(xq, wq, xs, ws, b))
+        med_b, _ = _time(lambda: lib.gemv_skinny(x, w, b))
+        res[f"{M}x{N}x{K}"] = dict(err=round(e, 5), ms=round(med, 4), gbs=round(N * K / med / 1e6, 1), bf16_gemv_ms=round(med_b, 4))
+    return dict(ok=ok, shapes=res)
+
+
 def check_attention_decode():
     import torch
     lib = _lib()
@@ -346,6 +367,7 @@ def check_attention_decode():
 
 CHECKS = {
     "attention_decode": check_attention_decode,
+    "gemv_w8a8": check_gemv_w8a8,
     "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
