@@ -90,28 +90,17 @@ def test_int8_serving_conversion_on_gpu():
     from paddlefleetx_b200.models.language_model.gpt import model as gpt
     from paddlefleetx_b200.ops.quant import quantize_tp_linears_int8
 
-    torch.manual_seed(0)
-    core = gpt.GPTModel(vocab_size=1024, hidden_size=256, num_layers=2, num_attention_heads=4, ffn_hidden_size=1024, max_position_embeddings=128,
-                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, dtype=torch.bfloat16, device="cuda")
-    with torch.no_grad():
-        for rows in (1, 3, 40):                 # W8A8 GEMV (<= 8 rows) and the tcgen05 int8 GEMM
-            ids = torch.randint(0, 1000, (1, rows), device="cuda")
-            if rows == 1:
-                ref = {}
-            ref[rows] = core(ids).float()
-        assert quantize_tp_linears_int8(core) == 8
-        for rows in (1, 3, 40):
-            ids = torch.randint(0, 1000, (1, rows), device="cuda")
+    def build():
         torch.manual_seed(0)
-    # same inputs again (deterministic generator state is not needed: compare on fresh fixed ids)
+        return gpt.GPTModel(vocab_size=1024, hidden_size=256, num_layers=2, num_attention_heads=4, ffn_hidden_size=1024, max_position_embeddings=128,
+                            hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, dtype=torch.bfloat16, device="cuda")
+
+    ref, q = build(), build()
+    assert quantize_tp_linears_int8(q) == 8
     ids = torch.arange(1, 41, device="cuda").view(1, 40)
-    torch.manual_seed(0)
-    fresh = gpt.GPTModel(vocab_size=1024, hidden_size=256, num_layers=2, num_attention_heads=4, ffn_hidden_size=1024, max_position_embeddings=128,
-                         hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, dtype=torch.bfloat16, device="cuda")
     with torch.no_grad():
-        for n in (1, 3, 40):
-            a = fresh(ids[:, :n]).float()
-            b = core(ids[:, :n]).float()
+        for n in (1, 3, 40):                    # W8A8 GEMV (<= 8 rows) and the tcgen05 int8 GEMM
+            a, b = ref(ids[:, :n]).float(), q(ids[:, :n]).float()
             assert float((a - b).norm() / a.norm()) < 0.05, n
 
 
