@@ -205,8 +205,35 @@ class TransformerDecoderLayer(nn.Module):
         z = self.linear1(h, skip_bias=True)      # GEMM only; bias rides in the fused bias+GELU kernel
         return self.linear2(OF.bias_gelu(z, self.linear1.bias))
 
+    def _decode_fast_ok(self, x, attn_mask, cache) -> bool:
+        a = self.self_attn
+        forced = getattr(self, "_force_decode_fast", False)          # tests: run the fused-step composition through the CPU expressions
+        hw = forced or (x.is_cuda and x.shape[0] <= OF.gemv_max_rows() and a.head_dim in (64, 128) and x.dtype in (torch.bfloat16, torch.float16)
+                        and OF.native_available())
+        return (hw and cache is not None and cache.static_index is not None and x.shape[1] == 1
+                and not self.training and not torch.is_grad_enabled() and self.moe_mlp is None and a.world == 1 and not a.sequence_parallel
+                and a.fuse_attn_qkv and not a.use_rope and a.use_flash_attn
+                and attn_mask is not None and attn_mask.dtype == x.dtype and attn_mask.numel() == x.shape[0] * cache.k.shape[1]
+                and getattr(a.qkv_proj, "int8", None) is None and a.qkv_proj.weight is not None)
+
+    def _decode_fast(self, x, attn_mask, cache):
+        """One decode token through the layer in five launches: LN1+QKV GEMV, cache-append + attention, out-proj GEMV + bias + residual,
+        LN2+FFN1 GEMV + bias + GELU, FFN2 GEMV + bias + residual (the generic path takes thirteen)."""
+        a = self.self_attn
+        b = x.shape[0]
+        x2 = x.reshape(b, -1)
+        qkv = OF.gemv_fused(x2, a.qkv_proj.weight, a.qkv_proj.bias, ln=(self.norm1.weight, self.norm1.bias, self.norm1.eps))
+        o = OF.attention_decode_packed(qkv.view(b, 1, a.local_heads, 3, a.head_dim), cache.k, cache.v, attn_mask, cache.static_index,
+                                       1.0 / math.sqrt(a.head_dim))
+        x2 = OF.gemv_fused(o.view(b, -1), a.out_proj.weight, a.out_proj.bias, residual=x2)
+        h = OF.gemv_fused(x2, self.linear1.weight, self.linear1.bias, ln=(self.norm2.weight, self.norm2.bias, self.norm2.eps), act="gelu")
+        x2 = OF.gemv_fused(h, self.linear2.weight, self.linear2.bias, residual=x2)
+        return x2.view_as(x)
+
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, cache: Optional[KVCache] = None,
                 positions: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._decode_fast_ok(x, attn_mask, cache):
+            return self._decode_fast(x, attn_mask, cache)
         if self.recompute_attn and self.training and cache is None:
             x = recompute(self._attn_block, x, attn_mask, None, positions)
         else:

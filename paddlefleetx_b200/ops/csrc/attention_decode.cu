@@ -18,17 +18,29 @@ namespace {
 constexpr int kDecWarps = 8;
 
 template <typename T, int kPerLane>      // kPerLane = D / 32 channels per lane (2 or 4)
-__global__ void __launch_bounds__(kDecWarps * 32) attention_decode_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+__global__ void __launch_bounds__(kDecWarps * 32) attention_decode_kernel(const T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
                                                                            const T* __restrict__ mask, T* __restrict__ out, int L, int Lmax,
-                                                                           int H, float scale) {
+                                                                           int H, float scale, const int64_t* __restrict__ write_idx) {
   constexpr int D = kPerLane * 32;
   __shared__ float s_m[kDecWarps], s_l[kDecWarps];
   __shared__ float s_acc[kDecWarps][D];
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // packed mode (write_idx != null): q points at the fused QKV projection [B, 1, H, 3, D]; this CTA first appends its head's new
+  // key / value at cache position *write_idx (the cache write used to be two separate index_copy launches), then attends
+  const int q_head_stride = write_idx ? 3 * D : D;
+  if (write_idx != nullptr) {
+    const int64_t pos = write_idx[0];
+    if (w < 2 && pos >= 0 && pos < Lmax) {
+      const T* src = q + ((size_t)b * H + h) * 3 * D + (1 + w) * D;
+      T* dst = (w == 0 ? k : v) + ((size_t)b * Lmax + pos) * H * D + (size_t)h * D;
+      for (int i = lane; i < D; i += 32) dst[i] = src[i];
+    }
+    __syncthreads();
+  }
   float qv[kPerLane];
   {
-    const T* qp = q + ((size_t)b * H + h) * D + lane * kPerLane;
+    const T* qp = q + ((size_t)b * H + h) * q_head_stride + lane * kPerLane;
 #pragma unroll
     for (int i = 0; i < kPerLane; ++i) qv[i] = to_f32<T>(qp[i]) * scale;
   }
@@ -103,12 +115,12 @@ __global__ void __launch_bounds__(kDecWarps * 32) attention_decode_kernel(const 
 
 }  // namespace
 
-cudaError_t attention_decode(const void* q, const void* k, const void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
-                             float scale, int dtype, cudaStream_t st) {
+cudaError_t attention_decode(const void* q, void* k, void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
+                             float scale, int dtype, cudaStream_t st, const int64_t* write_idx) {
   if (!B || !H) return cudaSuccess;
   if ((D != 64 && D != 128) || L < 1 || L > Lmax) return cudaErrorInvalidValue;
   const dim3 grid(H, B), block(kDecWarps * 32);
-#define PFX_AD(T, P) attention_decode_kernel<T, P><<<grid, block, 0, st>>>((const T*)q, (const T*)k, (const T*)v, (const T*)mask, (T*)out, L, Lmax, H, scale)
+#define PFX_AD(T, P) attention_decode_kernel<T, P><<<grid, block, 0, st>>>((const T*)q, (T*)k, (T*)v, (const T*)mask, (T*)out, L, Lmax, H, scale, write_idx)
   if (dtype == 1) { if (D == 128) PFX_AD(__nv_bfloat16, 4); else PFX_AD(__nv_bfloat16, 2); }
   else if (dtype == 0) { if (D == 128) PFX_AD(__half, 4); else PFX_AD(__half, 2); }
   else return cudaErrorInvalidValue;

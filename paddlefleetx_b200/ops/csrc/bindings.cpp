@@ -426,6 +426,22 @@ at::Tensor gemv_skinny(const at::Tensor& x, const at::Tensor& w, c10::optional<a
   return y;
 }
 
+at::Tensor gemv_fused(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> ln_w,
+                      c10::optional<at::Tensor> ln_b, double ln_eps, c10::optional<at::Tensor> residual, int64_t act) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1), "gemv_fused: x [M,K], w [N,K]");
+  TORCH_CHECK(x.scalar_type() == w.scalar_type(), "gemv_fused: dtype mismatch");
+  at::Tensor y = at::empty({x.size(0), w.size(0)}, x.options());
+  auto ptr = [](const c10::optional<at::Tensor>& t) -> const void* { return (t.has_value() && t->defined()) ? t->data_ptr() : nullptr; };
+  if (residual.has_value() && residual->defined())
+    TORCH_CHECK(residual->is_contiguous() && residual->numel() == y.numel() && residual->scalar_type() == x.scalar_type(), "gemv_fused: residual [M,N]");
+  if (ln_w.has_value() && ln_w->defined())
+    TORCH_CHECK(ln_w->numel() == x.size(1) && ln_b.has_value() && ln_b->numel() == x.size(1) && ln_w->scalar_type() == x.scalar_type(), "gemv_fused: ln params [K]");
+  PFX_CUDA_CHECK(pfx::gemv_skinny(x.data_ptr(), w.data_ptr(), ptr(bias), y.data_ptr(), (int)x.size(0), (int)w.size(0), (int)x.size(1), dtype_code(x),
+                                  at::cuda::getCurrentDeviceProperties()->multiProcessorCount, cur_stream(), ptr(ln_w), ptr(ln_b), (float)ln_eps,
+                                  ptr(residual), (int)act));
+  return y;
+}
+
 at::Tensor gemv_w8a8(const at::Tensor& xq, const at::Tensor& wq, const at::Tensor& xs, const at::Tensor& ws, c10::optional<at::Tensor> bias) {
   TORCH_CHECK(xq.is_cuda() && xq.scalar_type() == at::kChar && wq.scalar_type() == at::kChar && xq.is_contiguous() && wq.is_contiguous() &&
               xq.dim() == 2 && wq.dim() == 2 && xq.size(1) == wq.size(1), "gemv_w8a8: int8 x [M,K], w [N,K]");
@@ -463,6 +479,28 @@ at::Tensor attention_decode(const at::Tensor& q, const at::Tensor& k, const at::
   auto out = at::empty_like(q);
   PFX_CUDA_CHECK(pfx::attention_decode(q.data_ptr(), k.data_ptr(), v.data_ptr(), mp, out.data_ptr(), (int)q.size(0), (int)q.size(2), (int)q.size(3),
                                        (int)L, (int)k.size(1), (float)scale, dtype_code(q), cur_stream()));
+  return out;
+}
+
+at::Tensor attention_decode_packed(const at::Tensor& qkv, at::Tensor& k, at::Tensor& v, c10::optional<at::Tensor> mask, const at::Tensor& write_idx,
+                                   double scale) {
+  // qkv [B,1,H,3,D] (fused projection output); appends this step's K/V at cache position write_idx[0] and attends over the whole cache
+  PFX_CHECK_CUDA_CONTIG(qkv); PFX_CHECK_CUDA_CONTIG(k); PFX_CHECK_CUDA_CONTIG(v);
+  TORCH_CHECK(qkv.dim() == 5 && qkv.size(1) == 1 && qkv.size(3) == 3 && k.dim() == 4 && k.sizes() == v.sizes() && k.size(0) == qkv.size(0) &&
+              k.size(2) == qkv.size(2) && k.size(3) == qkv.size(4) && k.scalar_type() == qkv.scalar_type(), "attention_decode_packed: shape mismatch");
+  TORCH_CHECK(write_idx.is_cuda() && write_idx.scalar_type() == at::kLong && write_idx.numel() == 1, "attention_decode_packed: write_idx");
+  const c10::cuda::CUDAGuard guard(qkv.device());
+  const void* mp = nullptr;
+  at::Tensor mc;
+  if (mask.has_value() && mask->defined()) {
+    mc = mask->reshape({qkv.size(0), -1}).to(qkv.scalar_type()).contiguous();
+    TORCH_CHECK(mc.size(1) == k.size(1), "attention_decode_packed: mask must cover the whole cache");
+    mp = mc.data_ptr();
+  }
+  auto out = at::empty({qkv.size(0), 1, qkv.size(2), qkv.size(4)}, qkv.options());
+  PFX_CUDA_CHECK(pfx::attention_decode(qkv.data_ptr(), k.data_ptr(), v.data_ptr(), mp, out.data_ptr(), (int)qkv.size(0), (int)qkv.size(2),
+                                       (int)qkv.size(4), (int)k.size(1), (int)k.size(1), (float)scale, dtype_code(qkv), cur_stream(),
+                                       write_idx.data_ptr<int64_t>()));
   return out;
 }
 
@@ -542,9 +580,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("attention_decode", &attention_decode);
+  m.def("attention_decode_packed", &attention_decode_packed);
   m.def("gemv_skinny", &gemv_skinny);
   m.def("gemm_smallm", &gemm_smallm);
   m.def("gemv_w8a8", &gemv_w8a8);
+  m.def("gemv_fused", &gemv_fused);
   m.def("moe_route", &moe_route);
   m.def("moe_dispatch", &moe_dispatch);
   m.def("moe_combine", &moe_combine);

@@ -13,13 +13,56 @@ namespace pfx {
 
 namespace {
 
+// Optional fusions for the decode step (every removed launch is ~5 us of a ~100 us layer): LayerNorm of the activation rows as
+// a prologue (each CTA recomputes the two row statistics from the L1/L2-resident x — K reads against N*K/CTAs weight reads),
+// GELU, and "+ residual" in the finish.
+template <typename T>
+struct GemvExtra {
+  const T* ln_w = nullptr;       // LayerNorm gamma (null = no norm)
+  const T* ln_b = nullptr;
+  float ln_eps = 1e-5f;
+  const T* residual = nullptr;   // [M, N] added after bias / activation
+  int act = 0;                   // 0 none, 1 GELU(tanh)
+};
+
+__device__ __forceinline__ float gemv_gelu_tanh(float x) {
+  return 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+}
+
 // block = 8 warps arranged as (8 / kSplit) column groups x kSplit K-slices; a column group owns kCols weight rows.
 template <typename T, int kRows, int kCols, int kSplit>
 __global__ void __launch_bounds__(256) gemv_skinny_kernel(const T* __restrict__ x, const T* __restrict__ w, const T* __restrict__ bias,
-                                                          T* __restrict__ y, int N, int K) {
+                                                          T* __restrict__ y, int N, int K, const GemvExtra<T> ex) {
   constexpr int kGroups = 8 / kSplit;
   __shared__ float red[8][kCols * kRows];
+  __shared__ float s_stat[2][kRows];
+  __shared__ float s_part[8];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (ex.ln_w != nullptr) {      // row mean / rstd (two passes, fp32) — uniform branch
+#pragma unroll 1
+    for (int r = 0; r < kRows; ++r) {
+      float mean = 0.f;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < K; i += 256) {
+          const float v = to_f32<T>(x[(size_t)r * K + i]) - mean;
+          s += pass ? v * v : v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) s_part[wid] = s;
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        __syncthreads();
+        if (pass == 0) mean = t / K;
+        else if (threadIdx.x == 0) { s_stat[0][r] = mean; s_stat[1][r] = rsqrtf(t / K + ex.ln_eps); }
+      }
+    }
+    __syncthreads();
+  }
   const int group = wid / kSplit, slice = wid % kSplit;
   const int n0 = (blockIdx.x * kGroups + group) * kCols;
   float acc[kCols][kRows];
@@ -51,6 +94,17 @@ __global__ void __launch_bounds__(256) gemv_skinny_kernel(const T* __restrict__ 
         float xf[kRows][8];
 #pragma unroll
         for (int r = 0; r < kRows; ++r) unpack8<T>(__ldg(xp + (size_t)r * kvec + v), xf[r]);
+        if (ex.ln_w != nullptr) {
+          float gw[8], gb[8];
+          unpack8<T>(__ldg(reinterpret_cast<const uint4*>(ex.ln_w) + v), gw);
+          unpack8<T>(__ldg(reinterpret_cast<const uint4*>(ex.ln_b) + v), gb);
+#pragma unroll
+          for (int r = 0; r < kRows; ++r) {
+            const float mu = s_stat[0][r], rs = s_stat[1][r];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xf[r][j] = (xf[r][j] - mu) * rs * gw[j] + gb[j];
+          }
+        }
 #pragma unroll
         for (int c = 0; c < kCols; ++c) {
           float wf[8];
@@ -81,27 +135,29 @@ __global__ void __launch_bounds__(256) gemv_skinny_kernel(const T* __restrict__ 
     float v = bias ? to_f32<T>(bias[n]) : 0.f;
 #pragma unroll
     for (int s2 = 0; s2 < kSplit; ++s2) v += red[g * kSplit + s2][cr];
+    if (ex.act == 1) v = gemv_gelu_tanh(v);
+    if (ex.residual != nullptr) v += to_f32<T>(ex.residual[(size_t)r * N + n]);
     y[(size_t)r * N + n] = from_f32<T>(v);
   }
 }
 
 template <typename T, int kRows, int kCols, int kSplit>
-cudaError_t launch_cfg(const T* x, const T* w, const T* bias, T* y, int N, int K, cudaStream_t st) {
+cudaError_t launch_cfg(const T* x, const T* w, const T* bias, T* y, int N, int K, const GemvExtra<T>& ex, cudaStream_t st) {
   constexpr int kGroups = 8 / kSplit;
   const int groups = (N + kCols - 1) / kCols;
-  gemv_skinny_kernel<T, kRows, kCols, kSplit><<<(groups + kGroups - 1) / kGroups, 256, 0, st>>>(x, w, bias, y, N, K);
+  gemv_skinny_kernel<T, kRows, kCols, kSplit><<<(groups + kGroups - 1) / kGroups, 256, 0, st>>>(x, w, bias, y, N, K, ex);
   return cudaGetLastError();
 }
 
 template <typename T, int kRows>
-cudaError_t launch_rows(const T* x, const T* w, const T* bias, T* y, int N, int K, int num_sms, cudaStream_t st) {
+cudaError_t launch_rows(const T* x, const T* w, const T* bias, T* y, int N, int K, int num_sms, const GemvExtra<T>& ex, cudaStream_t st) {
   // aim for >= ~24 warps per SM of work; split K across the warps of a block when N alone does not provide that
   const long target = (long)num_sms * 24;
   const int cols = (kRows <= 2 || N / 4 < target) ? 2 : 4;
   const long groups = (N + cols - 1) / cols;
   int split = 1;
   while (split < 8 && groups * split < target && K / (split * 2) >= 1024) split *= 2;
-#define PFX_GV(C, S) return launch_cfg<T, kRows, C, S>(x, w, bias, y, N, K, st)
+#define PFX_GV(C, S) return launch_cfg<T, kRows, C, S>(x, w, bias, y, N, K, ex, st)
   if (cols == 2) { if (split == 1) PFX_GV(2, 1); if (split == 2) PFX_GV(2, 2); if (split == 4) PFX_GV(2, 4); PFX_GV(2, 8); }
   if (split == 1) PFX_GV(4, 1); if (split == 2) PFX_GV(4, 2); if (split == 4) PFX_GV(4, 4); PFX_GV(4, 8);
 #undef PFX_GV
@@ -211,28 +267,32 @@ cudaError_t launch_w8a8_rows(const int8_t* x, const int8_t* w, const float* xs, 
 }
 
 template <typename T>
-cudaError_t launch(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int num_sms, cudaStream_t st) {
+cudaError_t launch(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int num_sms, const void* ln_w, const void* ln_b,
+                   float ln_eps, const void* residual, int act, cudaStream_t st) {
   const T *xx = (const T*)x, *ww = (const T*)w, *bb = (const T*)bias;
   T* yy = (T*)y;
+  GemvExtra<T> ex;
+  ex.ln_w = (const T*)ln_w; ex.ln_b = (const T*)ln_b; ex.ln_eps = ln_eps; ex.residual = (const T*)residual; ex.act = act;
   switch (M) {
-    case 1: return launch_rows<T, 1>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 2: return launch_rows<T, 2>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 3: return launch_rows<T, 3>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 4: return launch_rows<T, 4>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 5: return launch_rows<T, 5>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 6: return launch_rows<T, 6>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 7: return launch_rows<T, 7>(xx, ww, bb, yy, N, K, num_sms, st);
-    case 8: return launch_rows<T, 8>(xx, ww, bb, yy, N, K, num_sms, st);
+    case 1: return launch_rows<T, 1>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 2: return launch_rows<T, 2>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 3: return launch_rows<T, 3>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 4: return launch_rows<T, 4>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 5: return launch_rows<T, 5>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 6: return launch_rows<T, 6>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 7: return launch_rows<T, 7>(xx, ww, bb, yy, N, K, num_sms, ex, st);
+    case 8: return launch_rows<T, 8>(xx, ww, bb, yy, N, K, num_sms, ex, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
 }  // namespace
 
-cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st) {
-  if (M < 1 || M > 8 || K % 8) return cudaErrorInvalidValue;
-  if (dtype == 1) return launch<__nv_bfloat16>(x, w, bias, y, M, N, K, num_sms, st);
-  if (dtype == 0) return launch<__half>(x, w, bias, y, M, N, K, num_sms, st);
+cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st,
+                        const void* ln_w, const void* ln_b, float ln_eps, const void* residual, int act) {
+  if (M < 1 || M > 8 || K % 8 || ((ln_w == nullptr) != (ln_b == nullptr))) return cudaErrorInvalidValue;
+  if (dtype == 1) return launch<__nv_bfloat16>(x, w, bias, y, M, N, K, num_sms, ln_w, ln_b, ln_eps, residual, act, st);
+  if (dtype == 0) return launch<__half>(x, w, bias, y, M, N, K, num_sms, ln_w, ln_b, ln_eps, residual, act, st);
   return cudaErrorInvalidValue;
 }
 

@@ -53,7 +53,8 @@ cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, flo
                                 const float* found_inf, int grad_dtype, int lp_dtype, int world, int num_sms, cudaStream_t st);
 
 // gemv_skinny.cu — decode-time y = x W^T (+b) for <= 8 activation rows
-cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st);
+cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st,
+                        const void* ln_w = nullptr, const void* ln_b = nullptr, float ln_eps = 1e-5f, const void* residual = nullptr, int act = 0);
 
 cudaError_t gemv_w8a8(const void* x, const void* w, const float* xs, const float* ws, const void* bias, void* y, int M, int N, int K, int num_sms,
                       cudaStream_t st);
@@ -63,8 +64,8 @@ cudaError_t gemm_smallm(const void* x, const void* w, const void* bias, void* y,
                         cudaStream_t st);
 
 // attention_decode.cu — single-query attention over the static KV cache
-cudaError_t attention_decode(const void* q, const void* k, const void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
-                             float scale, int dtype, cudaStream_t st);
+cudaError_t attention_decode(const void* q, void* k, void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
+                             float scale, int dtype, cudaStream_t st, const int64_t* write_idx = nullptr);
 
 // moe_kernels.cu — expert-parallel dispatch / combine over peer memory
 cudaError_t moe_route(const int64_t* gate_idx, int num_slots, int total_experts, int* slot_rank, int* counts, cudaStream_t st);

@@ -134,6 +134,37 @@ def native_available() -> bool:
     return _native.available()
 
 
+def gemv_max_rows() -> int:
+    return _GEMV_MAX_ROWS
+
+
+def gemv_fused(x: torch.Tensor, weight: torch.Tensor, bias=None, ln=None, residual=None, act: Optional[str] = None) -> torch.Tensor:
+    """Decode-step linear with optional LayerNorm prologue (``ln = (gamma, beta, eps)``), GELU(tanh) and ``+ residual``:
+    ``act((LN(x)) W^T + b) + residual`` for <= 8 rows in one weight-streaming kernel (csrc/gemv_skinny.cu)."""
+    if x.is_cuda and _native.available():
+        _count()
+        lw, lb, eps = (ln[0], ln[1], float(ln[2])) if ln is not None else (None, None, 1e-5)
+        return _native.require().gemv_fused(x.contiguous(), weight, bias, lw, lb, eps, None if residual is None else residual.contiguous(),
+                                            1 if act == "gelu" else 0)
+    h = x if ln is None else F.layer_norm(x.float(), (x.shape[-1],), ln[0].float(), ln[1].float(), ln[2]).to(x.dtype)
+    y = F.linear(h, weight, bias)
+    if act == "gelu":
+        y = F.gelu(y, approximate="tanh")
+    return y if residual is None else y + residual
+
+
+def attention_decode_packed(qkv: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, additive_mask: torch.Tensor, write_idx: torch.Tensor,
+                            scale: float) -> torch.Tensor:
+    """``qkv`` [B,1,H,3,D]: append this token's K/V at ``write_idx`` and attend over the whole static cache (one kernel)."""
+    if qkv.is_cuda and _native.available():
+        _count()
+        return _native.require().attention_decode_packed(qkv.contiguous(), k_cache, v_cache, additive_mask, write_idx, float(scale))
+    q, k, v = qkv.unbind(3)
+    k_cache.index_copy_(1, write_idx, k)
+    v_cache.index_copy_(1, write_idx, v)
+    return attention_decode(q, k_cache, v_cache, additive_mask, scale)
+
+
 def attention_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, additive_mask: torch.Tensor, scale: float) -> torch.Tensor:
     """q [B,1,H,D] against the whole static cache [B,Lmax,H,D]; ``additive_mask`` ([B,1,1,Lmax] or [B,Lmax]) hides padded and
     not-yet-written positions.  CPU / fallback: the plain softmax expression (also the numerical reference in the tests)."""

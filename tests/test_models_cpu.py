@@ -249,6 +249,16 @@ def test_generation_static_cache_decode_matches_dynamic_cache():
     b, _ = sta.generate(ids)
     c, _ = sta.generate(ids)                          # second call reuses the cached static state
     assert torch.equal(a, b) and torch.equal(a, c)
+    # the five-launch fused decode layer (LN+QKV, cache-append+attention, out-proj+residual, LN+FFN1+GELU, FFN2+residual) composes to
+    # the same function as the generic layer (CPU expressions of the fused ops)
+    for layer in core.decoder.layers:
+        layer._force_decode_fast = True
+    try:
+        d, _ = GPTForGeneration(core, dict(cfg, use_cuda_graph=True, force_static_decode=True)).generate(ids)
+    finally:
+        for layer in core.decoder.layers:
+            layer._force_decode_fast = False
+    assert torch.equal(a, d)
 
 
 def test_moe_exp_gating_respects_capacity_and_layer_trains():

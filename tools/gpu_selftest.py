@@ -320,6 +320,45 @@ def check_smallm():
     return dict(ok=ok, shapes=res)
 
 
+def check_decode_fused():
+    import torch
+    import torch.nn.functional as F
+    lib = _lib()
+    torch.manual_seed(0)
+    errs = {}
+    for (M, N, K) in [(1, 12288, 4096), (2, 4096, 16384), (1, 1000, 1032)]:
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.03).bfloat16()
+        b = torch.randn(N, device="cuda").bfloat16()
+        g = (1 + 0.1 * torch.randn(K, device="cuda")).bfloat16()
+        be = (0.1 * torch.randn(K, device="cuda")).bfloat16()
+        res = torch.randn(M, N, device="cuda").bfloat16()
+        y = lib.gemv_fused(x, w, b, g, be, 1e-5, res, 1)
+        ref = F.gelu(F.layer_norm(x.float(), (K,), g.float(), be.float(), 1e-5) @ w.float().t() + b.float(), approximate="tanh") + res.float()
+        errs[f"ln_gelu_res_{M}x{N}x{K}"] = _relerr(y, ref)
+        y2 = lib.gemv_fused(x, w, None, None, None, 1e-5, res, 0)
+        errs[f"res_{M}x{N}x{K}"] = _relerr(y2, x.float() @ w.float().t() + res.float())
+    B, H, D, Lmax = 2, 32, 128, 136
+    qkv = torch.randn(B, 1, H, 3, D, device="cuda").bfloat16()
+    k = torch.randn(B, Lmax, H, D, device="cuda").bfloat16()
+    v = torch.randn(B, Lmax, H, D, device="cuda").bfloat16()
+    pos = 77
+    valid = torch.zeros(B, Lmax, dtype=torch.bool, device="cuda")
+    valid[:, :pos + 1] = True
+    mask = torch.zeros(B, 1, 1, Lmax, device="cuda").masked_fill(~valid.view(B, 1, 1, Lmax), -1e4).bfloat16()
+    k_ref, v_ref = k.clone(), v.clone()
+    k_ref[:, pos], v_ref[:, pos] = qkv[:, 0, :, 1], qkv[:, 0, :, 2]
+    idx = torch.tensor([pos], device="cuda")
+    out = lib.attention_decode_packed(qkv, k, v, mask, idx, D ** -0.5)
+    sc = torch.einsum("bqhd,bkhd->bhqk", qkv[:, :, :, 0].float(), k_ref.float()) * D ** -0.5 + mask.float()
+    ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(sc, -1), v_ref.float())
+    errs["attn_packed"] = _relerr(out, ref)
+    errs["cache_k"] = float((k - k_ref).abs().max())
+    errs["cache_v"] = float((v - v_ref).abs().max())
+    ok = all(e < 1e-2 for kk, e in errs.items() if not kk.startswith("cache")) and errs["cache_k"] == 0 and errs["cache_v"] == 0
+    return dict(ok=ok, errs={kk: round(e, 5) for kk, e in errs.items()})
+
+
 def check_gemv_w8a8():
     import torch
     lib = _lib()
@@ -368,6 +407,7 @@ def check_attention_decode():
 CHECKS = {
     "attention_decode": check_attention_decode,
     "gemv_w8a8": check_gemv_w8a8,
+    "decode_fused": check_decode_fused,
     "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
