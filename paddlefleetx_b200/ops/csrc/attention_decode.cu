@@ -17,15 +17,22 @@ namespace {
 
 constexpr int kDecWarps = 8;
 
-template <typename T, int kPerLane>      // kPerLane = D / 32 channels per lane (2 or 4)
+// D / 8 lanes share one key (16-byte loads of 8 channels each), so a warp works on 32 / (D / 8) keys at a time and keeps
+// kU such groups in flight: 8 (D = 128) or 16 (D = 64) keys = 4-8 KB per warp outstanding.  Every lane group carries its own
+// online-softmax state; all states of the CTA are merged through shared memory at the end.
+template <typename T, int D>
 __global__ void __launch_bounds__(kDecWarps * 32) attention_decode_kernel(const T* __restrict__ q, T* __restrict__ k, T* __restrict__ v,
                                                                            const T* __restrict__ mask, T* __restrict__ out, int L, int Lmax,
                                                                            int H, float scale, const int64_t* __restrict__ write_idx) {
-  constexpr int D = kPerLane * 32;
-  __shared__ float s_m[kDecWarps], s_l[kDecWarps];
-  __shared__ float s_acc[kDecWarps][D];
+  constexpr int kLanes = D / 8;               // lanes per key
+  constexpr int kKW = 32 / kLanes;            // keys per warp step
+  constexpr int kStates = kDecWarps * kKW;
+  constexpr int kU = 4;
+  __shared__ float s_m[kStates], s_l[kStates];
+  __shared__ float s_acc[kStates][D];
   const int h = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int sub = lane / kLanes, ch = (lane % kLanes) * 8;
   // packed mode (write_idx != null): q points at the fused QKV projection [B, 1, H, 3, D]; this CTA first appends its head's new
   // key / value at cache position *write_idx (the cache write used to be two separate index_copy launches), then attends
   const int q_head_stride = write_idx ? 3 * D : D;
@@ -38,73 +45,63 @@ __global__ void __launch_bounds__(kDecWarps * 32) attention_decode_kernel(const 
     }
     __syncthreads();
   }
-  float qv[kPerLane];
-  {
-    const T* qp = q + ((size_t)b * H + h) * q_head_stride + lane * kPerLane;
+  float qv[8];
+  unpack8<T>(*reinterpret_cast<const uint4*>(q + ((size_t)b * H + h) * q_head_stride + ch), qv);
 #pragma unroll
-    for (int i = 0; i < kPerLane; ++i) qv[i] = to_f32<T>(qp[i]) * scale;
-  }
+  for (int i = 0; i < 8; ++i) qv[i] *= scale;
   const size_t row_stride = (size_t)H * D;
-  const T* kb = k + (size_t)b * Lmax * row_stride + (size_t)h * D + lane * kPerLane;
-  const T* vb = v + (size_t)b * Lmax * row_stride + (size_t)h * D + lane * kPerLane;
+  const T* kb = k + (size_t)b * Lmax * row_stride + (size_t)h * D + ch;
+  const T* vb = v + (size_t)b * Lmax * row_stride + (size_t)h * D + ch;
   const T* mb = mask ? mask + (size_t)b * Lmax : nullptr;
-  float m = -INFINITY, l = 0.f, acc[kPerLane];
+  float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) acc[i] = 0.f;
-  constexpr int kU = 4;                                     // keys in flight per warp
-  for (int t0 = w * kU; t0 < L; t0 += kDecWarps * kU) {
-    float kk[kU][kPerLane], vv[kU][kPerLane];
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int t0 = w * kU * kKW; t0 < L; t0 += kDecWarps * kU * kKW) {
+    uint4 rk[kU], rv[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int t = t0 + u;
+      const int t = t0 + u * kKW + sub;
       if (t < L) {
-        if constexpr (kPerLane == 4) {
-          const uint2 rk = *reinterpret_cast<const uint2*>(kb + (size_t)t * row_stride);
-          const uint2 rv = *reinterpret_cast<const uint2*>(vb + (size_t)t * row_stride);
-          const T* pk = reinterpret_cast<const T*>(&rk);
-          const T* pv = reinterpret_cast<const T*>(&rv);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { kk[u][i] = to_f32<T>(pk[i]); vv[u][i] = to_f32<T>(pv[i]); }
-        } else {
-          const uint32_t rk = *reinterpret_cast<const uint32_t*>(kb + (size_t)t * row_stride);
-          const uint32_t rv = *reinterpret_cast<const uint32_t*>(vb + (size_t)t * row_stride);
-          const T* pk = reinterpret_cast<const T*>(&rk);
-          const T* pv = reinterpret_cast<const T*>(&rv);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) { kk[u][i] = to_f32<T>(pk[i]); vv[u][i] = to_f32<T>(pv[i]); }
-        }
+        rk[u] = ld_stream(reinterpret_cast<const uint4*>(kb + (size_t)t * row_stride));
+        rv[u] = ld_stream(reinterpret_cast<const uint4*>(vb + (size_t)t * row_stride));
       }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int t = t0 + u;
-      if (t >= L) break;
-      float s = 0.f;
+      const int t = t0 + u * kKW + sub;
+      const bool live = t < L;                      // uniform inside a lane group; shuffles below stay inside the group
+      float kf[8], vf[8];
+      if (live) { unpack8<T>(rk[u], kf); unpack8<T>(rv[u], vf); }
+      float sc = 0.f;
+      if (live) {
 #pragma unroll
-      for (int i = 0; i < kPerLane; ++i) s = fmaf(qv[i], kk[u][i], s);
+        for (int i = 0; i < 8; ++i) sc = fmaf(qv[i], kf[i], sc);
+      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (mb) s += to_f32<T>(mb[t]);
-      const float m_new = fmaxf(m, s);
-      const float corr = __expf(m - m_new), p = __expf(s - m_new);
-      l = l * corr + p;
+      for (int o = kLanes / 2; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
+      if (live) {
+        if (mb) sc += to_f32<T>(mb[t]);
+        const float m_new = fmaxf(m, sc);
+        const float corr = __expf(m - m_new), p = __expf(sc - m_new);
+        l = l * corr + p;
 #pragma unroll
-      for (int i = 0; i < kPerLane; ++i) acc[i] = acc[i] * corr + p * vv[u][i];
-      m = m_new;
+        for (int i = 0; i < 8; ++i) acc[i] = acc[i] * corr + p * vf[i];
+        m = m_new;
+      }
     }
   }
-  if (lane == 0) { s_m[w] = m; s_l[w] = l; }
+  const int state = w * kKW + sub;
+  if (lane % kLanes == 0) { s_m[state] = m; s_l[state] = l; }
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) s_acc[w][lane * kPerLane + i] = acc[i];
+  for (int i = 0; i < 8; ++i) s_acc[state][ch + i] = acc[i];
   __syncthreads();
-  // merge the warps' online-softmax states; thread c finishes channel c
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float mm = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < kDecWarps; ++i) mm = fmaxf(mm, s_m[i]);
+    for (int i = 0; i < kStates; ++i) mm = fmaxf(mm, s_m[i]);
     float ll = 0.f, a = 0.f;
 #pragma unroll
-    for (int i = 0; i < kDecWarps; ++i) {
+    for (int i = 0; i < kStates; ++i) {
       const float f = (s_m[i] == -INFINITY) ? 0.f : __expf(s_m[i] - mm);
       ll += s_l[i] * f;
       a += s_acc[i][c] * f;
@@ -121,8 +118,8 @@ cudaError_t attention_decode(const void* q, void* k, void* v, const void* mask, 
   if ((D != 64 && D != 128) || L < 1 || L > Lmax) return cudaErrorInvalidValue;
   const dim3 grid(H, B), block(kDecWarps * 32);
 #define PFX_AD(T, P) attention_decode_kernel<T, P><<<grid, block, 0, st>>>((const T*)q, (T*)k, (T*)v, (const T*)mask, (T*)out, L, Lmax, H, scale, write_idx)
-  if (dtype == 1) { if (D == 128) PFX_AD(__nv_bfloat16, 4); else PFX_AD(__nv_bfloat16, 2); }
-  else if (dtype == 0) { if (D == 128) PFX_AD(__half, 4); else PFX_AD(__half, 2); }
+  if (dtype == 1) { if (D == 128) PFX_AD(__nv_bfloat16, 128); else PFX_AD(__nv_bfloat16, 64); }
+  else if (dtype == 0) { if (D == 128) PFX_AD(__half, 128); else PFX_AD(__half, 64); }
   else return cudaErrorInvalidValue;
 #undef PFX_AD
   return cudaGetLastError();

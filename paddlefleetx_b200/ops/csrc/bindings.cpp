@@ -207,8 +207,13 @@ std::vector<at::Tensor> norm_bwd(const at::Tensor& dy, const at::Tensor& x, cons
 }
 
 // ------------------------------------------------------------------------------- activations / dropout
+static void check_same_dtype(const at::Tensor& x, const c10::optional<at::Tensor>& t, const char* what) {
+  if (t.has_value() && t->defined())
+    TORCH_CHECK(t->scalar_type() == x.scalar_type(), what, ": operand dtype ", t->scalar_type(), " differs from activation dtype ", x.scalar_type());
+}
 at::Tensor bias_gelu_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias) {
   PFX_CHECK_CUDA_CONTIG(x);
+  check_same_dtype(x, bias, "bias_gelu");
   const c10::cuda::CUDAGuard guard(x.device());
   auto y = at::empty_like(x);
   const int64_t cols = x.size(-1);
@@ -218,6 +223,8 @@ at::Tensor bias_gelu_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias) {
 }
 at::Tensor bias_gelu_bwd(const at::Tensor& dy, const at::Tensor& x, c10::optional<at::Tensor> bias) {
   PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(dy);
+  check_same_dtype(x, bias, "bias_gelu_bwd");
+  TORCH_CHECK(dy.scalar_type() == x.scalar_type(), "bias_gelu_bwd: dy dtype");
   const c10::cuda::CUDAGuard guard(x.device());
   auto dx = at::empty_like(x);
   const int64_t cols = x.size(-1);
@@ -228,6 +235,8 @@ at::Tensor bias_gelu_bwd(const at::Tensor& dy, const at::Tensor& x, c10::optiona
 at::Tensor bias_dropout_add_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> residual, double p,
                                 int64_t seed, int64_t offset) {
   PFX_CHECK_CUDA_CONTIG(x);
+  check_same_dtype(x, bias, "bias_dropout_add");
+  check_same_dtype(x, residual, "bias_dropout_add");
   const c10::cuda::CUDAGuard guard(x.device());
   auto y = at::empty_like(x);
   const int64_t cols = x.size(-1);

@@ -209,6 +209,8 @@ class _BiasGeluFn(torch.autograd.Function):
 def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """tanh-approximated GELU of (x + bias) — reference hybrid_model.py:667 (approximate=True)."""
     if _native_ok(x) and x.shape[-1] % 8 == 0:
+        if bias is not None and bias.dtype != x.dtype:        # O1 autocast: fp32 parameters next to bf16 activations
+            bias = bias.to(x.dtype)
         return _BiasGeluFn.apply(x, bias)
     return F.gelu(x if bias is None else x + bias, approximate="tanh")
 
@@ -248,6 +250,10 @@ def bias_dropout_add(x: torch.Tensor, bias: Optional[torch.Tensor], residual: Op
         seed, offset = (0, 0)
         if p > 0:
             seed, offset = get_rng_state_tracker().philox(x.numel(), rng_name)
+        if bias is not None and bias.dtype != x.dtype:        # the kernels read every operand in x's dtype
+            bias = bias.to(x.dtype)
+        if residual is not None and residual.dtype != x.dtype:
+            residual = residual.to(x.dtype)
         return _BiasDropoutAddFn.apply(x, bias, residual, p, seed, offset)
     y = x if bias is None else x + bias
     if p > 0:
