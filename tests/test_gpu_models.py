@@ -115,37 +115,47 @@ def test_vision_multimodal_and_text_towers_on_gpu():
     from paddlefleetx_b200.optims import FusedAdamW
 
     dev = "cuda"
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        vit = build(dict(name="ViT_tiny_patch16_224", img_size=64, patch_size=8, depth=2, class_num=10)).to(dev)
-        opt = FusedAdamW(1e-3, named_parameters=list(vit.named_parameters()))
-        x, y = torch.randn(8, 3, 64, 64, device=dev), torch.randint(0, 10, (8,), device=dev)
-        losses = []
-        for _ in range(5):
-            loss = build(dict(name="CELoss", epsilon=0.1))(vit(x), y)
-            loss.backward()
-            opt.step(); opt.clear_grad()
-            losses.append(float(loss))
-        assert losses[-1] < losses[0]
-        moco = MoCo(dim=8, K=16, backbone="resnet18").to(dev)
+    amp = lambda: torch.autocast("cuda", dtype=torch.bfloat16)     # forward only: autocast caches weight casts while a context is open
+    vit = build(dict(name="ViT_tiny_patch16_224", img_size=64, patch_size=8, depth=2, class_num=10)).to(dev)
+    opt = FusedAdamW(1e-3, named_parameters=list(vit.named_parameters()))
+    x, y = torch.randn(8, 3, 64, 64, device=dev), torch.randint(0, 10, (8,), device=dev)
+    crit = build(dict(name="CELoss", epsilon=0.1))
+    losses = []
+    for _ in range(5):
+        with amp():
+            loss = crit(vit(x), y)
+        loss.backward()
+        opt.step(); opt.clear_grad()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses
+    moco = MoCo(dim=8, K=16, backbone="resnet18").to(dev)
+    with amp():
         lg, _ = moco(torch.randn(4, 3, 32, 32, device=dev), torch.randn(4, 3, 32, 32, device=dev))
-        lg.float().logsumexp(1).mean().backward()
-        u = U.Unet(dim=16, text_embed_dim=12, dim_mults=(1, 2), layer_attns=(False, True), layer_cross_attns=(False, True), attn_heads=2,
-                   attn_dim_head=8, max_text_len=6, num_latents=2).to(dev)
-        m = I.ImagenModel([u], image_sizes=[16], text_embed_dim=12, timesteps=2).to(dev)
+    lg.float().logsumexp(1).mean().backward()
+    u = U.Unet(dim=16, text_embed_dim=12, dim_mults=(1, 2), layer_attns=(False, True), layer_cross_attns=(False, True), attn_heads=2,
+               attn_dim_head=8, max_text_len=6, num_latents=2).to(dev)
+    m = I.ImagenModel([u], image_sizes=[16], text_embed_dim=12, timesteps=2).to(dev)
+    with amp():
         out = m(torch.rand(2, 3, 16, 16, device=dev), text_embeds=torch.randn(2, 4, 12, device=dev), text_masks=torch.ones(2, 4, device=dev))
-        I.ImagenCriterion()(*out).backward()
-        ids = torch.randint(0, 100, (2, 16), device=dev)
-        mask = torch.ones(2, 16, dtype=torch.long, device=dev)
-        t5 = T5EncoderModel(vocab_size=100, d_model=64, d_kv=16, d_ff=128, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu").to(dev)
-        t5(ids, mask).float().sum().backward()
-        deb = DebertaV2Model(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, position_buckets=8,
-                             conv_kernel_size=3).to(dev)
-        deb(ids, mask).float().sum().backward()
-        evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2,
-                                     pair_heads=2).to(dev)
+        il = I.ImagenCriterion()(*out)
+    il.backward()
+    ids = torch.randint(0, 100, (2, 16), device=dev)
+    mask = torch.ones(2, 16, dtype=torch.long, device=dev)
+    t5 = T5EncoderModel(vocab_size=100, d_model=64, d_kv=16, d_ff=128, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu").to(dev)
+    with amp():
+        o = t5(ids, mask)
+    o.float().sum().backward()
+    deb = DebertaV2Model(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, position_buckets=8,
+                         conv_kernel_size=3).to(dev)
+    with amp():
+        o = deb(ids, mask)
+    o.float().sum().backward()
+    evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2,
+                                 pair_heads=2).to(dev)
+    with amp():
         o = evo(dict(target_feat=torch.randn(1, 10, 6, device=dev), msa_feat=torch.randn(1, 4, 10, 9, device=dev),
                      residue_index=torch.arange(10, device=dev)[None]))
-        o["single"].float().sum().backward()
+    o["single"].float().sum().backward()
     torch.cuda.synchronize()
 
 
