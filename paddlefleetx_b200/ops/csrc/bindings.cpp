@@ -594,6 +594,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_smallm", &gemm_smallm);
   m.def("gemv_w8a8", &gemv_w8a8);
   m.def("gemv_fused", &gemv_fused);
+  m.def("gemv_set_tuning", [](int64_t cols, int64_t split) { pfx::gemv_set_tuning((int)cols, (int)split); });
   m.def("moe_route", &moe_route);
   m.def("moe_dispatch", &moe_dispatch);
   m.def("moe_combine", &moe_combine);

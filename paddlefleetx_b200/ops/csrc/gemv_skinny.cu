@@ -149,14 +149,18 @@ cudaError_t launch_cfg(const T* x, const T* w, const T* bias, T* y, int N, int K
   return cudaGetLastError();
 }
 
+int g_gemv_cols = 0, g_gemv_split = 0;      // tuning overrides (0 = heuristic), see gemv_set_tuning
+
 template <typename T, int kRows>
 cudaError_t launch_rows(const T* x, const T* w, const T* bias, T* y, int N, int K, int num_sms, const GemvExtra<T>& ex, cudaStream_t st) {
   // aim for >= ~24 warps per SM of work; split K across the warps of a block when N alone does not provide that
   const long target = (long)num_sms * 24;
-  const int cols = (kRows <= 2 || N / 4 < target) ? 2 : 4;
+  int cols = (kRows <= 2 || N / 4 < target) ? 2 : 4;
+  if (g_gemv_cols == 2 || g_gemv_cols == 4) cols = g_gemv_cols;
   const long groups = (N + cols - 1) / cols;
   int split = 1;
   while (split < 8 && groups * split < target && K / (split * 2) >= 1024) split *= 2;
+  if (g_gemv_split == 1 || g_gemv_split == 2 || g_gemv_split == 4 || g_gemv_split == 8) split = g_gemv_split;
 #define PFX_GV(C, S) return launch_cfg<T, kRows, C, S>(x, w, bias, y, N, K, ex, st)
   if (cols == 2) { if (split == 1) PFX_GV(2, 1); if (split == 2) PFX_GV(2, 2); if (split == 4) PFX_GV(2, 4); PFX_GV(2, 8); }
   if (split == 1) PFX_GV(4, 1); if (split == 2) PFX_GV(4, 2); if (split == 4) PFX_GV(4, 4); PFX_GV(4, 8);
@@ -295,6 +299,8 @@ cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y,
   if (dtype == 0) return launch<__half>(x, w, bias, y, M, N, K, num_sms, ln_w, ln_b, ln_eps, residual, act, st);
   return cudaErrorInvalidValue;
 }
+
+void gemv_set_tuning(int cols, int split) { g_gemv_cols = cols; g_gemv_split = split; }
 
 cudaError_t gemv_w8a8(const void* x, const void* w, const float* xs, const float* ws, const void* bias, void* y, int M, int N, int K, int num_sms,
                       cudaStream_t st) {

@@ -56,6 +56,7 @@ cudaError_t adamw_p2p_broadcast(void** peer_param_bufs, size_t shard_offset, flo
 cudaError_t gemv_skinny(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int num_sms, cudaStream_t st,
                         const void* ln_w = nullptr, const void* ln_b = nullptr, float ln_eps = 1e-5f, const void* residual = nullptr, int act = 0);
 
+void gemv_set_tuning(int cols, int split);
 cudaError_t gemv_w8a8(const void* x, const void* w, const float* xs, const float* ws, const void* bias, void* y, int M, int N, int K, int num_sms,
                       cudaStream_t st);
 

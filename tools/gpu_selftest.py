@@ -320,6 +320,41 @@ def check_smallm():
     return dict(ok=ok, shapes=res)
 
 
+def check_gemv_tuning():
+    """Sweep the GEMV launch shape (weight rows per warp x K-slices per block) on the decode shapes of GPT-6.7B, L2 cold and warm."""
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    out = {}
+    for (M, N, K) in [(1, 4096, 4096), (1, 12288, 4096), (1, 16384, 4096), (1, 4096, 16384), (1, 50304, 4096)]:
+        x = torch.randn(M, K, device="cuda").bfloat16()
+        w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        row = {}
+        for cols in (2, 4):
+            for split in (1, 2, 4, 8):
+                lib.gemv_set_tuning(cols, split)
+                med, best = _time(lambda: lib.gemv_skinny(x, w, None), iters=15)
+                row[f"c{cols}s{split}"] = round(N * K * 2 / med / 1e6)
+        lib.gemv_set_tuning(0, 0)
+        med, _ = _time(lambda: lib.gemv_skinny(x, w, None), iters=15)
+        row["auto"] = round(N * K * 2 / med / 1e6)
+        # back-to-back (no L2 flush, as inside the decode graph): 8 different weight matrices round-robin > L2
+        ws = [w] + [(torch.randn(N, K, device="cuda") * 0.05).bfloat16() for _ in range(3)]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            for wi in ws:
+                lib.gemv_skinny(x, wi, None)
+        e0.record()
+        for _ in range(10):
+            for wi in ws:
+                lib.gemv_skinny(x, wi, None)
+        e1.record(); torch.cuda.synchronize()
+        row["auto_back_to_back"] = round(N * K * 2 * 40 / e0.elapsed_time(e1) / 1e6)
+        out[f"{M}x{N}x{K}"] = row
+    return dict(ok=True, gbs=out)
+
+
 def check_decode_fused():
     import torch
     import torch.nn.functional as F
@@ -408,6 +443,7 @@ CHECKS = {
     "attention_decode": check_attention_decode,
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
+    "gemv_tuning": check_gemv_tuning,
     "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
