@@ -1,0 +1,282 @@
+// Flash-style attention forward on tcgen05 / TMEM / TMA (sm_100a), bf16, head_dim 64 or 128, causal or full.
+//
+//   O[b, s, h, :] = softmax(scale * Q[b, s, h, :] . K[b, :, h, :]^T (+ causal mask)) @ V[b, :, h, :]
+//
+// Tensors stay in the framework layout [B, S, H, D] (no transposes): a 2-D tensor map over [B*S, H*D] addresses the
+// (128 rows x D) tile of one head directly.  One CTA owns a 128-query tile of one (batch, head):
+//   warp 0   TMA producer: Q once, then K / V tiles of 128 keys through a 2-stage ring
+//   warp 1   MMA issuer:   S = Q K^T  (UMMA 128x128x16, both operands K-major)   -> TMEM columns [0, 128)
+//                          PV = P V   (UMMA 128xDx16, P K-major from smem, V MN-major) -> TMEM columns [128, 128 + D)
+//   warps 2-5 softmax:     one thread per query row (the TMEM lane it can read): row max over the 128 scores, exp2 with the
+//                          running max, P written to shared memory as bf16 in the 128-byte-swizzled K-major layout the second
+//                          MMA consumes, running sum and the O accumulator (fp32, in registers) rescaled once per KV tile
+// S for tile j+1 is issued as soon as the softmax warps have drained S_j from TMEM, so the tensor core computes the next
+// scores while the softmax of the current tile is in its exp / store phase.  Causal tiles above the diagonal are never loaded.
+// Output O (bf16) and the row-wise log-sum-exp (fp32, [B, H, S]) are written straight from registers.
+//
+// Used on the no-grad paths (prefill of generation, evaluation, vision / text encoders in inference).  Training keeps the
+// library (cuDNN) kernels: a matching backward is future work.
+// Reference call site: flash_attention in hybrid_model.py:284-301 (FlashAttention-2 library on Ampere mma.sync).
+#include "pfx_ptx.cuh"
+#include "pfx_gemm.h"
+#include "pfx_kernels.h"
+#include <cudaTypedefs.h>
+
+namespace pfx {
+
+namespace {
+
+constexpr int kFaThreads = 192;
+constexpr int kFaTile = 128;          // queries per CTA, keys per KV tile
+
+template <int kD>
+struct FaSmem {
+  static constexpr int kQBytes = kFaTile * kD * 2;
+  static constexpr int kKBytes = kFaTile * kD * 2;
+  static constexpr int kVBytes = kFaTile * kD * 2;
+  static constexpr int kStageBytes = kKBytes + kVBytes;
+  static constexpr int kPBytes = kFaTile * kFaTile * 2;
+  static constexpr int kStages = 2;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = 1024 + kQBytes + kStages * kStageBytes + kPBytes + kBarBytes;
+};
+
+template <int kD, bool kCausal>
+__global__ void __launch_bounds__(kFaThreads, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                     __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int Sq, int Sk, int H, float scale_log2) {
+  using S = FaSmem<kD>;
+  constexpr int kPanels = kD / 64;                 // 64-element (128-byte) column panels of a D-wide tile
+  constexpr int kTmemCols = 256;                   // S: [0,128), PV: [128, 128 + kD)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_q = smem_base;
+  const uint32_t smem_kv = smem_q + S::kQBytes;
+  const uint32_t smem_p = smem_kv + S::kStages * S::kStageBytes;
+  const uint32_t smem_bar = smem_p + S::kPBytes;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_full = smem_bar;
+  auto kv_full = [&](int s) { return smem_bar + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return smem_bar + 8u * (3 + s); };
+  const uint32_t s_full = smem_bar + 8u * 5, s_free = smem_bar + 8u * 6, p_full = smem_bar + 8u * 7, pv_full = smem_bar + 8u * 8,
+                 pv_free = smem_bar + 8u * 9;
+  const uint32_t tmem_slot = smem_bar + 8u * 10;
+
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const int n_q_tiles = (Sq + kFaTile - 1) / kFaTile;
+  const int q_tile = n_q_tiles - 1 - (int)blockIdx.x;          // longest (most KV tiles under a causal mask) first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = q_tile * kFaTile;
+  const int n_kv_all = (Sk + kFaTile - 1) / kFaTile;
+  const int n_kv = kCausal ? min(n_kv_all, (q0 + kFaTile - 1 + (Sk - Sq)) / kFaTile + 1) : n_kv_all;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < S::kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+      mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_free, 4);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(tmem_slot, kTmemCols);
+    tmem_relinquish<1>();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+
+  if (warp == 0) {
+    // ======================================================================================= TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, S::kQBytes);
+      for (int p = 0; p < kPanels; ++p) tma_load_2d(&tmap_q, q_full, smem_q + p * (kFaTile * 128), h * kD + p * 64, b * Sq + q0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int stage = j & 1;
+        const uint32_t phase = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(kv_empty(stage), phase ^ 1u);
+        const uint32_t sk = smem_kv + stage * S::kStageBytes, sv = sk + S::kKBytes;
+        mbar_arrive_expect_tx(kv_full(stage), S::kStageBytes);
+        const int key0 = b * Sk + j * kFaTile;
+        for (int p = 0; p < kPanels; ++p) tma_load_2d(&tmap_k, kv_full(stage), sk + p * (kFaTile * 128), h * kD + p * 64, key0);
+        for (int kb = 0; kb < 2; ++kb)            // V as the MN-major B operand: [64 keys x 64 channels] boxes, channel chunks 8 KB apart
+          for (int nc = 0; nc < kPanels; ++nc)
+            tma_load_2d(&tmap_v, kv_full(stage), sv + (kb * kPanels + nc) * 8192, h * kD + nc * 64, key0 + kb * 64);
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================================= MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc(1, 1, 1, false, false, kFaTile, kFaTile);
+      const uint32_t idesc_pv = umma_idesc(1, 1, 1, false, true, kFaTile, kD);
+      constexpr uint64_t kDescK = umma_desc_hi_lo(16, 1024);        // K-major, 128-byte swizzle
+      constexpr uint64_t kDescMN = umma_desc_hi_lo(8192, 1024);     // MN-major: 64-channel chunks 8 KB apart
+      mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int stage = j & 1;
+        mbar_wait(kv_full(stage), (uint32_t)(j >> 1) & 1u);
+        mbar_wait(s_free, ((uint32_t)j & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t sk = smem_kv + stage * S::kStageBytes;
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint32_t off = (k / 4) * (kFaTile * 128) + (k % 4) * 32;
+          umma_f16<1>(tmem_s, umma_desc(smem_q + off, kDescK), umma_desc(sk + off, kDescK), idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit<1>(s_full);
+      };
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_s(j + 1);          // next scores while the softmax of tile j runs
+        const int stage = j & 1;
+        mbar_wait(p_full, (uint32_t)j & 1u);
+        mbar_wait(pv_free, ((uint32_t)j & 1u) ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t sv = smem_kv + stage * S::kStageBytes + S::kKBytes;
+#pragma unroll
+        for (int k = 0; k < kFaTile / 16; ++k) {
+          const uint32_t a_off = (k / 4) * (kFaTile * 128) + (k % 4) * 32;                 // P: two 64-key panels
+          const uint32_t b_off = (k / 4) * (kPanels * 8192) + (k % 4) * 2048;              // V: 64-key blocks, 16 keys = 2 KB
+          umma_f16<1>(tmem_pv, umma_desc(smem_p + a_off, kDescK), umma_desc(sv + b_off, kDescMN), idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit<1>(pv_full);
+        umma_commit<1>(kv_empty(stage));
+      }
+    }
+  } else {
+    // ======================================================================================= softmax / epilogue
+    const uint32_t q = warp & 3u;
+    const int row = (int)(q * 32u + lane);               // query row inside the tile == TMEM lane
+    const int row_g = q0 + row;
+    const uint32_t lane_addr = (q * 32u) << 16;
+    float o[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* p_row = smem_gen + (smem_p - smem_base) + (row / 8) * 1024 + (row % 8) * 128;
+    for (int j = 0; j < n_kv; ++j) {
+      const int col0 = j * kFaTile;
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tcgen05_fence_after();
+      const bool need_mask = (kCausal && col0 + kFaTile - 1 > row_g + (Sk - Sq)) || (col0 + kFaTile > Sk);
+      // pass 1: row maximum
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < kFaTile; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]) * scale_log2;
+          if (need_mask) {
+            const int cg = col0 + c + i;
+            if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) s = -INFINITY;
+          }
+          m_tile = fmaxf(m_tile, s);
+        }
+      }
+      const float m_new = fmaxf(m, m_tile);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;        // fully masked row so far: keep everything at zero
+      const float corr = exp2f(m - m_use);
+      // pass 2: probabilities -> bf16 P tile in shared memory (swizzled K-major), running sum
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kFaTile; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_addr + c, r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]) * scale_log2;
+          if (need_mask) {
+            const int cg = col0 + c + i;
+            if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) s = -INFINITY;
+          }
+          p[i] = exp2f(s - m_use);
+          l_tile += p[i];
+        }
+        uint8_t* panel = p_row + (c / 64) * (kFaTile * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {              // four 16-byte chunks (8 keys each) of this 32-key slice
+          const int chunk = ((c % 64) / 8 + g) ^ (row % 8);
+          uint4 v;
+          v.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]); v.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+          v.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]); v.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(panel + chunk * 16) = v;
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();                    // generic-proxy stores of P -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(s_free); mbar_arrive(p_full); }
+      l = l * corr + l_tile;
+      m = m_new;
+      // accumulate O = O * corr + P V
+      mbar_wait(pv_full, (uint32_t)j & 1u);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < kD; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_pv + lane_addr + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(r[i]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pv_free);
+    }
+    if (row_g < Sq) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)(b * Sq + row_g) * H + h) * kD);
+#pragma unroll
+      for (int c = 0; c < kD; c += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(o[c + 0] * inv, o[c + 1] * inv); v.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
+        v.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv); v.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
+        dst[c / 8] = v;
+      }
+      if (lse != nullptr) lse[((size_t)b * H + h) * Sq + row_g] = (l > 0.f) ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, kTmemCols);
+}
+
+template <int kD, bool kCausal>
+cudaError_t launch_fa(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Sk, int H, float scale, cudaStream_t st) {
+  using S = FaSmem<kD>;
+  CUtensorMap tq, tk, tv;
+  const uint64_t row_bytes = (uint64_t)H * kD * 2;
+  bool ok = make_tmap_2d(&tq, q, 2, 1, (uint64_t)H * kD, (uint64_t)B * Sq, row_bytes, 64, kFaTile);
+  ok &= make_tmap_2d(&tk, k, 2, 1, (uint64_t)H * kD, (uint64_t)B * Sk, row_bytes, 64, kFaTile);
+  ok &= make_tmap_2d(&tv, v, 2, 1, (uint64_t)H * kD, (uint64_t)B * Sk, row_bytes, 64, 64);
+  if (!ok) return cudaErrorInvalidValue;
+  auto kern = attention_fwd_kernel<kD, kCausal>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const dim3 grid((Sq + kFaTile - 1) / kFaTile, H, B);
+  kern<<<grid, kFaThreads, S::kTotal, st>>>(tq, tk, tv, (__nv_bfloat16*)out, lse, Sq, Sk, H, scale * 1.4426950408889634f);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Sk, int H, int D, float scale,
+                          bool causal, cudaStream_t st) {
+  if ((D != 64 && D != 128) || B < 1 || Sq < 1 || Sk < 1 || (causal && Sk < Sq)) return cudaErrorInvalidValue;
+  if (D == 128) return causal ? launch_fa<128, true>(q, k, v, out, lse, B, Sq, Sk, H, scale, st) : launch_fa<128, false>(q, k, v, out, lse, B, Sq, Sk, H, scale, st);
+  return causal ? launch_fa<64, true>(q, k, v, out, lse, B, Sq, Sk, H, scale, st) : launch_fa<64, false>(q, k, v, out, lse, B, Sq, Sk, H, scale, st);
+}
+
+}  // namespace pfx

@@ -491,6 +491,20 @@ at::Tensor attention_decode(const at::Tensor& q, const at::Tensor& k, const at::
   return out;
 }
 
+std::vector<at::Tensor> attention_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal, double scale) {
+  // q [B,Sq,H,D], k/v [B,Sk,H,D], contiguous bf16 -> (out [B,Sq,H,D], lse [B,H,Sq] fp32)
+  PFX_CHECK_CUDA_CONTIG(q); PFX_CHECK_CUDA_CONTIG(k); PFX_CHECK_CUDA_CONTIG(v);
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && k.sizes() == v.sizes() && q.size(0) == k.size(0) && q.size(2) == k.size(2) && q.size(3) == k.size(3),
+              "attention_fwd: shape mismatch");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16, "attention_fwd: bf16 only");
+  const c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty_like(q);
+  auto lse = at::empty({q.size(0), q.size(2), q.size(1)}, q.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), (int)q.size(0), (int)q.size(1),
+                                    (int)k.size(1), (int)q.size(2), (int)q.size(3), (float)scale, causal, cur_stream()));
+  return {out, lse};
+}
+
 at::Tensor attention_decode_packed(const at::Tensor& qkv, at::Tensor& k, at::Tensor& v, c10::optional<at::Tensor> mask, const at::Tensor& write_idx,
                                    double scale) {
   // qkv [B,1,H,3,D] (fused projection output); appends this step's K/V at cache position write_idx[0] and attends over the whole cache
@@ -588,6 +602,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_barrier", &p2p_barrier);
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
+  m.def("attention_fwd", &attention_fwd);
   m.def("attention_decode", &attention_decode);
   m.def("attention_decode_packed", &attention_decode_packed);
   m.def("gemv_skinny", &gemv_skinny);

@@ -64,6 +64,10 @@ cudaError_t gemv_w8a8(const void* x, const void* w, const float* xs, const float
 cudaError_t gemm_smallm(const void* x, const void* w, const void* bias, void* y, int M, int N, int K, int dtype, int split, int num_sms,
                         cudaStream_t st);
 
+// attention_fwd_sm100.cu — flash-style attention forward (tcgen05 / TMEM / TMA), [B,S,H,D] bf16, D in {64,128}
+cudaError_t attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Sk, int H, int D, float scale,
+                          bool causal, cudaStream_t st);
+
 // attention_decode.cu — single-query attention over the static KV cache
 cudaError_t attention_decode(const void* q, void* k, void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
                              float scale, int dtype, cudaStream_t st, const int64_t* write_idx = nullptr);

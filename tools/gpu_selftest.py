@@ -320,6 +320,40 @@ def check_smallm():
     return dict(ok=ok, shapes=res)
 
 
+def check_attention_fwd():
+    import torch
+    import torch.nn.functional as F
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    for (B, Sq, Sk, H, D, causal, timed) in [(1, 128, 128, 2, 128, True, False), (2, 256, 256, 4, 128, False, False), (1, 300, 300, 3, 128, True, False),
+                                             (2, 577, 577, 4, 64, False, False), (1, 128, 384, 2, 64, True, False), (8, 1024, 1024, 32, 128, True, True),
+                                             (32, 577, 577, 16, 64, False, True)]:
+        q = torch.randn(B, Sq, H, D, device="cuda").bfloat16()
+        k = torch.randn(B, Sk, H, D, device="cuda").bfloat16()
+        v = torch.randn(B, Sk, H, D, device="cuda").bfloat16()
+        scale = D ** -0.5
+        out, lse = lib.attention_fwd(q, k, v, causal, scale)
+        torch.cuda.synchronize()
+        s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * scale
+        if causal:
+            mask = torch.ones(Sq, Sk, dtype=torch.bool, device="cuda").tril(Sk - Sq)
+            s = s.masked_fill(~mask, float("-inf"))
+        ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), v.float())
+        e = _relerr(out, ref)
+        e_lse = _relerr(lse, torch.logsumexp(s, -1))
+        ok = ok and e < 1e-2 and e_lse < 1e-3
+        row = dict(err=round(e, 5), err_lse=round(e_lse, 6))
+        if timed:
+            med, _ = _time(lambda: lib.attention_fwd(q, k, v, causal, scale))
+            qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))
+            med_c, _ = _time(lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=causal, scale=scale))
+            flops = 4.0 * B * H * Sq * Sk * D * (0.5 if causal else 1.0)
+            row.update(ms=round(med, 4), tflops=round(flops / med / 1e9, 1), sdpa_ms=round(med_c, 4), sdpa_tflops=round(flops / med_c / 1e9, 1))
+        res[f"B{B}_Sq{Sq}_Sk{Sk}_H{H}_D{D}_{'causal' if causal else 'full'}"] = row
+    return dict(ok=ok, shapes=res)
+
+
 def check_gemv_tuning():
     """Sweep the GEMV launch shape (weight rows per warp x K-slices per block) on the decode shapes of GPT-6.7B, L2 cold and warm."""
     import torch
@@ -444,6 +478,7 @@ CHECKS = {
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
     "gemv_tuning": check_gemv_tuning,
+    "attention_fwd": check_attention_fwd,
     "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
     "gemm_nt_1cta": lambda: check_gemm(True, True, 1),
