@@ -140,7 +140,9 @@ class GPTForGeneration(nn.Module):
         causal = torch.ones(prompt_len, prompt_len, dtype=torch.bool, device=dev).tril()
         mask = (causal.unsqueeze(0) & valid.unsqueeze(1)).unsqueeze(1)                 # [b,1,s,s] bool (True = attend)
         mask = mask | torch.eye(prompt_len, dtype=torch.bool, device=dev)              # padded rows still need one key
-        hidden = self.gpt(input_ids, pos, _to_additive(mask, hidden_dtype(self.gpt)), caches)
+        # unpadded prompts (the common serving case) need no explicit mask: plain causal attention runs on the native flash kernel
+        prefill_mask = None if (attention_mask is None and bool(valid.all())) else _to_additive(mask, hidden_dtype(self.gpt))
+        hidden = self.gpt(input_ids, pos, prefill_mask, caches)
         logits = self._lm_logits(hidden[:, -1:, :])[:, 0, :].float()
 
         out_ids = torch.full((b, max_new), int(self.pad_token_id if self.pad_token_id is not None else 0), dtype=torch.long, device=dev)

@@ -1,7 +1,9 @@
 """Attention front-end.
 
 ``attention(q, k, v)`` takes ``[b, s, heads, d]`` tensors.  Path selection:
-  * our fused sm_100a flash kernel (``csrc/attention_sm100.cu``) when built and the shape qualifies,
+  * our tcgen05 / TMEM flash forward (``csrc/attention_fwd_sm100.cu``) on the no-grad paths (generation prefill, evaluation,
+    inference of the vision / text encoders) when no dropout and no explicit mask are requested and head_dim is 64 or 128;
+    single-query decode steps over the static KV cache use ``csrc/attention_decode.cu`` (see models/.../gpt/model.py),
   * otherwise the library SDPA (cuDNN / FlashAttention-2 inside PyTorch) — a *library* call, reported as such
     by the launch accounting (it does not count towards ``gpu_launches``),
   * the unfused reference path (QK^T -> fused causal softmax -> PV) used when an explicit mask is given or
@@ -12,12 +14,36 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import os
+
 import torch
 import torch.nn.functional as F
+
+_NATIVE_FWD = os.environ.get("PFX_NATIVE_ATTN_FWD", "1") == "1"
+
+
+def _native_fwd_ok(q, k, v, dropout_p, attn_mask, causal) -> bool:
+    if not _NATIVE_FWD or attn_mask is not None or dropout_p != 0.0 or not q.is_cuda or q.dtype != torch.bfloat16:
+        return False
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return False                      # training keeps the library forward/backward pair
+    if q.shape[-1] not in (64, 128) or q.shape[1] < 16 or (causal and k.shape[1] < q.shape[1]):
+        return False
+    from . import _native
+
+    return _native.available()
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = True, dropout_p: float = 0.0,
               scale: Optional[float] = None, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if _native_fwd_ok(q, k, v, dropout_p, attn_mask, causal):
+        from . import _native
+        from . import functional as OF
+
+        OF._count()
+        out, _ = _native.require().attention_fwd(q.contiguous(), k.contiguous(), v.contiguous(), bool(causal),
+                                                 float(scale if scale is not None else q.shape[-1] ** -0.5))
+        return out
     qt, kt, vt = (t.transpose(1, 2) for t in (q, k, v))           # [b, h, s, d]
     if attn_mask is not None:
         causal = False

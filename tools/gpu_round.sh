@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 300 python tools/gpu_selftest.py attention_fwd 2>&1 | tail -2 | cut -c1-2200
 timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/pytest_gpu.log | tail -8 | cut -c1-300
 timeout 600 python tools/gpu_selftest.py gemv_tuning 2>&1 | tail -2 | cut -c1-2500
