@@ -19,11 +19,17 @@ import os
 import torch
 import torch.nn.functional as F
 
-_NATIVE_FWD = os.environ.get("PFX_NATIVE_ATTN_FWD", "1") == "1"
+# 0 = never, 1 = where it is at least as fast as the library kernel (short sequences: prefill / few-hundred-token inputs), 2 = always.
+# Measured on B200 (profiles/README.md): 258 TFLOP/s at S=1024 causal D=128 vs 799 for cuDNN — the kernel is correct but its single
+# softmax group serialises against the MMAs, so long sequences stay on the library until the ping-pong version lands.
+_NATIVE_FWD = int(os.environ.get("PFX_NATIVE_ATTN_FWD", "1"))
+_NATIVE_FWD_MAX_SEQ = 256
 
 
 def _native_fwd_ok(q, k, v, dropout_p, attn_mask, causal) -> bool:
     if not _NATIVE_FWD or attn_mask is not None or dropout_p != 0.0 or not q.is_cuda or q.dtype != torch.bfloat16:
+        return False
+    if _NATIVE_FWD == 1 and max(q.shape[1], k.shape[1]) > _NATIVE_FWD_MAX_SEQ:
         return False
     if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
         return False                      # training keeps the library forward/backward pair
