@@ -1,9 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/gpu_selftest.py attention_fwd 2>&1 | tail -2 | cut -c1-2200
-timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/pytest_gpu.log | tail -8 | cut -c1-300
-timeout 600 python tools/gpu_selftest.py gemv_tuning 2>&1 | tail -2 | cut -c1-2500
-bash tools/gpu_ncu.sh 2>&1 | tail -8
-for chk in gemm_nt_2cta gemm_smallm layernorm adamw; do timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/gpu_selftest.py $chk > gpurun_out/sanitizer_memcheck_$chk.log 2>&1; echo "memcheck $chk rc=$? $(grep -c 'ERROR SUMMARY: 0 errors' gpurun_out/sanitizer_memcheck_$chk.log)"; done
-timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/gpu_selftest.py layernorm > gpurun_out/sanitizer_racecheck_layernorm.log 2>&1; echo "racecheck layernorm rc=$?"; tail -2 gpurun_out/sanitizer_racecheck_layernorm.log | cut -c1-200
+timeout 900 python tools/bench_inference.py --model gpt-6.7b --batches 1,2,4,8,16 --iters 10 > gpurun_out/inference_6.7b.log 2>&1; echo "inference rc=$?"; grep '^{' gpurun_out/inference_6.7b.log | cut -c1-230
+timeout 900 python tools/bench_inference.py --model gpt-6.7b --batches 1,2,4,8,16 --iters 10 --int8 > gpurun_out/inference_6.7b_int8.log 2>&1; echo "inference int8 rc=$?"; grep '^{' gpurun_out/inference_6.7b_int8.log | cut -c1-230
+timeout 900 python tools/bench_inference.py --model gpt-345m --batches 1,2,4,8,16 --iters 10 > gpurun_out/inference_345m.log 2>&1; echo "inference345 rc=$?"; grep '^{' gpurun_out/inference_345m.log | cut -c1-230
+timeout 1200 python bench.py --steps 6 --warmup 3 > gpurun_out/bench_6.7b.log 2>&1; echo "bench6.7 rc=$?"; tail -1 gpurun_out/bench_6.7b.log | cut -c1-700
+timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 1700 -c 3300 --csv --log-file gpurun_out/launches_6.7b_v2.csv python bench.py --steps 1 --warmup 1 --no-e2e > gpurun_out/ncu_launches.log 2>&1; echo "launches rc=$?"; wc -l gpurun_out/launches_6.7b_v2.csv
