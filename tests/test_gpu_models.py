@@ -175,3 +175,23 @@ def test_ernie_trains_on_gpu(tmp_path):
     eng = _engine(cfg)
     losses = [float(eng.train_step(b)) for _, b in zip(range(4), build_dataloader(cfg.Data, "Train"))]
     assert len(losses) >= 2 and np.isfinite(losses).all()
+
+
+def test_native_flash_forward_is_used_for_short_unmasked_inference():
+    """attention() routes no-grad, unmasked, dropout-free calls with seq <= 256 to the tcgen05 flash forward and matches SDPA."""
+    import torch.nn.functional as F
+
+    from paddlefleetx_b200.ops import attention as A
+    from paddlefleetx_b200.ops import functional as OF
+
+    torch.manual_seed(0)
+    q, k, v = (torch.randn(2, 200, 8, 64, device="cuda").bfloat16() for _ in range(3))
+    OF.reset_launch_count()
+    with torch.no_grad():
+        y = A.attention(q, k, v, causal=True)
+    assert OF.native_launch_count() == 1
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(), v.transpose(1, 2).float(), is_causal=True).transpose(1, 2)
+    assert float((y.float() - ref).norm() / ref.norm()) < 1e-2
+    OF.reset_launch_count()
+    y2 = A.attention(q.requires_grad_(True), k, v, causal=True)          # training path: library forward + backward
+    assert OF.native_launch_count() == 0 and y2.requires_grad
