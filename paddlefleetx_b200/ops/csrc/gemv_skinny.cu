@@ -155,11 +155,11 @@ template <typename T, int kRows>
 cudaError_t launch_rows(const T* x, const T* w, const T* bias, T* y, int N, int K, int num_sms, const GemvExtra<T>& ex, cudaStream_t st) {
   // aim for >= ~24 warps per SM of work; split K across the warps of a block when N alone does not provide that
   const long target = (long)num_sms * 24;
-  int cols = (N / 4 < target / 8) ? 2 : 4;
+  int cols = (kRows == 1) ? ((N / 4 < target / 8) ? 2 : 4) : ((kRows <= 2 || N / 4 < target) ? 2 : 4);
   if (g_gemv_cols == 2 || g_gemv_cols == 4) cols = g_gemv_cols;
   const long groups = (N + cols - 1) / cols;
   int split = 1;
-  if (kRows <= 2) {
+  if (kRows == 1) {
     // measured sweep on B200 (profiles/selftest_r1_call18.jsonl): 4 rows per warp with the block's warps split 2-way over K is best
     // or within 2 % of best for every GPT-6.7B decode shape; very long K (FFN2) prefers 8 slices
     split = K >= 16384 ? 8 : (K >= 2048 ? 2 : 1);
