@@ -195,6 +195,7 @@ class EagerEngine(BasicEngine):
         self._wd = _wd
         self._fault = _wd.FaultInjector(rank=env.global_rank())
         self._stop_requested = False
+        self._last_saved_step = -1
         self._heartbeat = None
         wcfg = (configs.Engine.get("watchdog") or {}) if mode == "train" else {}
         if wcfg.get("enable", False):
@@ -258,6 +259,7 @@ class EagerEngine(BasicEngine):
         if ev0 is not None:
             ev0.record()
         resume_step = self._load_recovery["step"] if epoch_index == self._load_recovery["epoch"] else 0
+        last_step = None
         for step, batch in enumerate(loader):
             if step < resume_step:
                 continue          # resume: replay the sampler and discard consumed batches (eager_engine.py:347-349)
@@ -315,13 +317,22 @@ class EagerEngine(BasicEngine):
                     if device.type == "cuda":
                         torch.cuda.synchronize()
                     self.save(epoch=epoch_index, step=step)
+                    self._last_saved_step = step
             else:
                 skip_first = False
 
             if self._profiler is not None:
                 self._profiler.step()
+            last_step = step
             if self._run_mode == "step" and step >= self._max_steps:
-                return
+                break
+        # step mode: the loader is sized to max_steps batches, so the periodic `step % save_steps` rule never fires on the last one;
+        # leave a final checkpoint (named by the number of consumed batches) when periodic saving is on
+        if (self._run_mode == "step" and self._save_steps and 0 < self._save_steps < (1 << 30) and last_step is not None
+                and self._last_saved_step != last_step + 1 and not self._stop_requested):
+            if device.type == "cuda":
+                torch.cuda.synchronize()
+            self.save(epoch=epoch_index, step=last_step + 1)
 
     # ---------------------------------------------------------------------------------------- one optimizer step
     def train_step(self, host_batch):

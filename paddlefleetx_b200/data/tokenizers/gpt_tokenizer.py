@@ -121,7 +121,9 @@ class GPTTokenizer:
         return [self.encoder[t] for t in tokens]
 
     def convert_ids_to_tokens(self, ids, skip_special_tokens: bool = False) -> List[str]:
-        return [self.decoder[int(i)] for i in ids if not (skip_special_tokens and int(i) == self.eos_token_id)]
+        # ids outside the vocabulary (a model whose embedding is padded past the tokenizer, or the byte-level fallback vocabulary
+        # next to a 50304-row model) decode to nothing instead of raising
+        return [self.decoder.get(int(i), "") for i in ids if not (skip_special_tokens and int(i) == self.eos_token_id)]
 
     def encode(self, text: str) -> List[int]:
         return self.convert_tokens_to_ids(self.tokenize(text))
