@@ -197,6 +197,27 @@ class ErnieDataset(torch.utils.data.Dataset):
         return [tok, typ, mask, pos, lab, np.asarray([int(swapped)], dtype=np.int64)]
 
 
+class SyntheticErnieDataset(torch.utils.data.Dataset):
+    """Random MLM + SOP samples in the exact sample format of :class:`ErnieDataset` (no corpus needed): smoke runs, benchmarks."""
+
+    def __init__(self, max_seq_length: int = 512, vocab_size: int = 40000, masked_lm_prob: float = 0.15, num_samples: int = 1 << 16, seed: int = 1234,
+                 **unused):
+        self.seq, self.vocab, self.n, self.seed = int(max_seq_length), int(vocab_size), int(num_samples), int(seed)
+        self.n_mask = max(1, int(round(self.seq * masked_lm_prob)))
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx: int):
+        rng = np.random.default_rng(self.seed * 1000003 + idx)
+        tok = rng.integers(4, self.vocab, size=self.seq, dtype=np.int64)
+        split = int(rng.integers(self.seq // 4, 3 * self.seq // 4))
+        typ = (np.arange(self.seq) >= split).astype(np.int64)
+        pos = np.sort(rng.choice(self.seq, size=self.n_mask, replace=False)).astype(np.int64)
+        lab = rng.integers(4, self.vocab, size=self.n_mask, dtype=np.int64)
+        return [tok, typ, np.ones(self.seq, dtype=np.float32), pos, lab, np.asarray([int(rng.integers(0, 2))], dtype=np.int64)]
+
+
 class ErnieSeqClsDataset(torch.utils.data.Dataset):
     """TSV ``text[\\ttext_b]\\tlabel`` classification data, tokenised with a byte-level fallback when no vocab is configured."""
 

@@ -60,3 +60,51 @@ def test_cli_workflow_cpu(tmp_path):
 @pytest.mark.gpu
 def test_cli_workflow_gpu(tmp_path):
     _workflow(tmp_path, "gpu")
+
+
+FAMILIES = {
+    "vit": ("vis/vit/ViT_tiny_patch16_224_ci_cifar10_1n8c_dp_fp16o2.yaml",
+            ["Data.Train.dataset.name=SyntheticImageDataset", "Data.Train.dataset.image_size=32", "Data.Train.dataset.class_num=10", "Data.Train.loader.num_workers=0",
+             "Data.Train.sampler.batch_size=4", "Model.model.img_size=32", "Model.model.patch_size=8", "Model.model.depth=2", "Global.local_batch_size=4",
+             "Global.micro_batch_size=4", "Distributed.dp_degree=1", "Engine.num_train_epochs=1", "Engine.run_mode=step"]),
+    "moco": ("vis/moco/mocov2_pt_in1k_1n8c.yaml",
+             ["Data.Train.dataset.name=SyntheticImageDataset", "Data.Train.dataset.image_size=32", "Data.Train.dataset.two_views=True", "Data.Train.loader.num_workers=0",
+              "Data.Train.sampler.batch_size=4", "Global.local_batch_size=4", "Global.micro_batch_size=4", "Distributed.dp_degree=1", "Engine.run_mode=step",
+              "Engine.num_train_epochs=1", "Model.model.backbone=resnet18", "Model.model.K=16", "Model.model.dim=8"]),
+    "imagen": ("multimodal/imagen/imagen_397M_text2im_64x64.yaml",
+               ["Data.Train.dataset.name=SyntheticImagenDataset", "Data.Train.loader.num_workers=0", "Global.local_batch_size=2", "Global.micro_batch_size=2",
+                "Distributed.dp_degree=1", "Engine.run_mode=step", "Engine.num_train_epochs=1"]),
+    "moe": ("nlp/moe/pretrain_moe_345M_single_card.yaml",
+            ["Model.num_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.ffn_hidden_size=128", "Model.max_position_embeddings=32",
+             "Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0", "Global.local_batch_size=2",
+             "Global.micro_batch_size=2"]),
+    "ernie": ("nlp/ernie/pretrain_ernie_base_345M_single_card.yaml",
+              ["Model.hidden_size=64", "Model.num_hidden_layers=2", "Model.num_attention_heads=4", "Model.vocab_size=512", "Model.max_position_embeddings=64",
+               "Global.local_batch_size=2", "Global.micro_batch_size=2", "Data.Train.loader.num_workers=0", "Data.Train.dataset.name=SyntheticErnieDataset",
+               "Data.Train.dataset.max_seq_length=32", "Data.Train.dataset.vocab_size=512"]),
+}
+
+
+def _family(name, device):
+    cfg, ov = FAMILIES[name]
+    ov = ov + ["Global.device=" + device, "Engine.max_steps=3", "Engine.logging_freq=1", "Engine.eval_freq=-1", "Engine.save_load.save_steps=-1"]
+    if device == "cpu":
+        ov.append("Engine.mix_precision.enable=False")
+    args = ["tools/train.py", "-c", os.path.join(ROOT, "paddlefleetx_b200", "configs", cfg)]
+    for item in ov:
+        args += ["-o", item]
+    log = _run(args, device)
+    assert log.count("[train]") >= 3, log[-1500:]
+    losses = [float(x) for x in re.findall(r"loss: ([0-9.]+)", log)]
+    assert losses and all(l == l and l < 1e4 for l in losses), losses
+
+
+@pytest.mark.parametrize("name", sorted(FAMILIES))
+def test_train_cli_every_model_family_cpu(name):
+    _family(name, "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FAMILIES))
+def test_train_cli_every_model_family_gpu(name):
+    _family(name, "gpu")
