@@ -267,6 +267,19 @@ def wikitext_detokenize(text: str) -> str:
     return out
 
 
+def _default_eval_tokenizer(vocab_dir=None):
+    """The evaluation sets tokenise raw text themselves (reference gpt_dataset.py:484-655 builds ``GPTTokenizer.from_pretrained("gpt2")``);
+    offline boxes without the GPT-2 vocabulary fall back to the byte-level vocabulary with a warning (scores are then not comparable)."""
+    from ..tokenizers.gpt_tokenizer import GPTTokenizer
+    from ...utils.log import logger
+
+    try:
+        return GPTTokenizer.from_pretrained(vocab_dir or "gpt2")
+    except FileNotFoundError as exc:
+        logger.warning(f"{exc}  Falling back to the byte-level tokenizer for evaluation.")
+        return GPTTokenizer.byte_fallback()
+
+
 class LM_Eval_Dataset(torch.utils.data.Dataset):
     """Sliding-window perplexity set: windows of ``max_seq_len`` advanced by ``overlapping_eval``; only the last
     ``overlapping_eval`` targets of every non-first window are scored (reference gpt_dataset.py:484-560)."""
@@ -277,7 +290,7 @@ class LM_Eval_Dataset(torch.utils.data.Dataset):
             with open(input_dir, "rb") as fh:
                 raw = fh.read().decode("utf-8")
             self.num_original_tokens = len(raw.strip().split(" "))
-            assert tokenizer is not None, "LM_Eval_Dataset needs a tokenizer (or pre-tokenised `tokens`)"
+            tokenizer = tokenizer or _default_eval_tokenizer(unused.get("vocab_dir"))
             tokens = tokenizer.encode(wikitext_detokenize(raw))
         else:
             self.num_original_tokens = len(tokens)
@@ -322,7 +335,7 @@ class Lambada_Eval_Dataset(torch.utils.data.Dataset):
         else:
             import json
 
-            assert tokenizer is not None
+            tokenizer = tokenizer or _default_eval_tokenizer(unused.get("vocab_dir"))
             with open(input_dir, "r", encoding="utf-8") as fh:
                 for line in fh:
                     text = json.loads(line)["text"]

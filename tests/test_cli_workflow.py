@@ -108,3 +108,38 @@ def test_train_cli_every_model_family_cpu(name):
 @pytest.mark.parametrize("name", sorted(FAMILIES))
 def test_train_cli_every_model_family_gpu(name):
     _family(name, "gpu")
+
+
+TINY_GPT = ["Global.device=cpu", "Engine.mix_precision.enable=False", "Model.num_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4",
+            "Model.ffn_hidden_size=128", "Model.max_position_embeddings=64", "Model.hidden_dropout_prob=0.0", "Model.attention_probs_dropout_prob=0.0"]
+
+
+def _cli(tool, cfg, ov, device="cpu"):
+    args = [tool, "-c", os.path.join(CFG, cfg)]
+    for item in ov:
+        args += ["-o", item]
+    return _run(args, device)
+
+
+@pytest.mark.parametrize("cfg", ["qat_gpt_345M_single_card.yaml", "prune_gpt_345M_single_card.yaml"])
+def test_compression_recipes_train_through_the_cli(cfg):
+    log = _cli("tools/train.py", cfg, TINY_GPT + ["Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0",
+                                                  "Global.local_batch_size=2", "Global.micro_batch_size=2", "Engine.max_steps=3", "Engine.logging_freq=1",
+                                                  "Engine.eval_freq=-1", "Engine.save_load.save_steps=-1"])
+    assert log.count("[train]") >= 3
+
+
+def test_offline_eval_cli_perplexity_and_lambada(tmp_path):
+    import json
+
+    wiki = tmp_path / "wiki.txt"
+    wiki.write_text(("the quick brown fox jumps over the lazy dog . " * 40 + "\n") * 4)
+    log = _cli("tools/eval.py", "eval_gpt_345M_single_card.yaml", TINY_GPT + [f"Offline_Eval.eval_path={wiki}", "Offline_Eval.cloze_eval=False",
+                                                                             "Offline_Eval.overlapping_eval=16", "Offline_Eval.batch_size=2", "Offline_Eval.max_seq_len=32"])
+    m = re.search(r"ppl: ([0-9.E+-]+) \| adjusted ppl: ([0-9.E+-]+) \| token ratio: ([0-9.]+)", log)
+    assert m and float(m.group(1)) > 1.0 and float(m.group(3)) > 1.0, log[-800:]
+    lam = tmp_path / "lambada.jsonl"
+    lam.write_text("".join(json.dumps({"text": f"the quick brown fox jumps over the lazy dog number {i}"}) + "\n" for i in range(6)))
+    log = _cli("tools/eval.py", "eval_gpt_345M_single_card.yaml", TINY_GPT + [f"Offline_Eval.eval_path={lam}", "Offline_Eval.cloze_eval=True", "Offline_Eval.batch_size=2",
+                                                                             "Offline_Eval.max_seq_len=32"])
+    assert "total examples: 6.0000E+00" in log, log[-800:]
