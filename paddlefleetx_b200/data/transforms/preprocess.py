@@ -19,7 +19,7 @@ except Exception:  # pragma: no cover
 
 
 def _resize(img: np.ndarray, size, interpolation: str = "bilinear") -> np.ndarray:
-    h, w = (size, size) if isinstance(size, int) else (size[1], size[0]) if False else (size[0], size[1]) if isinstance(size, (tuple, list)) else (size, size)
+    h, w = (int(size[0]), int(size[1])) if isinstance(size, (tuple, list)) else (int(size), int(size))      # size = (height, width)
     if _HAS_PIL:
         mode = {"nearest": Image.NEAREST, "bilinear": Image.BILINEAR, "bicubic": Image.BICUBIC, "lanczos": Image.LANCZOS}.get(interpolation, Image.BILINEAR)
         return np.asarray(Image.fromarray(img.astype(np.uint8) if img.dtype != np.uint8 else img).resize((w, h), mode))

@@ -211,9 +211,12 @@ class Unet(nn.Module):
             blocks = nn.ModuleList([ResnetBlock(do + skip, do, cond_dim, time_cond_dim, resnet_groups, lca[j])] +
                                    [ResnetBlock(do + skip, do, None, time_cond_dim, resnet_groups) for _ in range(nrb[j])])
             attn = SelfAttention2d(do, attn_heads, attn_dim_head, cond_dim) if la[j] else (LinearAttention2d(do) if use_linear_attn else nn.Identity())
-            up = nn.Identity() if (last or j == n - 1) else nn.Sequential(nn.Upsample(scale_factor=2, mode="nearest"), nn.Conv2d(do, di, 3, padding=1))
-            if j == n - 1:
-                up = nn.Sequential(nn.Conv2d(do, di, 3, padding=1)) if True else up
+            if j == n - 1:          # innermost level: the down path did not halve here, so only the channel projection is mirrored
+                up = nn.Sequential(nn.Conv2d(do, di, 3, padding=1))
+            elif last:
+                up = nn.Identity()
+            else:
+                up = nn.Sequential(nn.Upsample(scale_factor=2, mode="nearest"), nn.Conv2d(do, di, 3, padding=1))
             self.ups.append(nn.ModuleList([blocks, attn, up, nn.Identity()]))
         self._io = io
         self.final_res = ResnetBlock(dim * 2, dim, None, time_cond_dim, resnet_groups)

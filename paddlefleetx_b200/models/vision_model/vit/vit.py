@@ -105,7 +105,7 @@ class ViT(nn.Module):
         trunc_normal_(self.pos_embed, std=0.02)
         self.apply(self._init_weights)
         if isinstance(self.head, nn.Linear):
-            nn.init.zeros_(self.head.weight); nn.init.constant_(self.head.bias, -10.0 if False else 0.0)
+            nn.init.zeros_(self.head.weight); nn.init.zeros_(self.head.bias)
 
     @staticmethod
     def _init_weights(m):
