@@ -28,6 +28,7 @@ from ....ops import functional as OF
 from ....parallel import comm_ops as C
 from ....parallel.recompute import recompute
 from ....parallel.rng import get_rng_state_tracker
+from ....parallel.tp_layers import _OPTIONS as _TP_OPTIONS
 from ....parallel.tp_layers import (ColumnParallelLinear, ColumnSequenceParallelLinear, ParallelCrossEntropy,
                                     RowParallelLinear, RowSequenceParallelLinear, VocabParallelEmbedding,
                                     mark_as_sequence_parallel_parameter, parallel_matmul)
@@ -202,8 +203,13 @@ class TransformerDecoderLayer(nn.Module):
         return OF.bias_dropout_add(y, b, x, self.hidden_dropout, self.training, self.rng_name)
 
     def _ffn(self, h):
-        z = self.linear1(h, skip_bias=True)      # GEMM only; bias rides in the fused bias+GELU kernel
-        return self.linear2(OF.bias_gelu(z, self.linear1.bias))
+        l1, l2 = self.linear1, self.linear2
+        if (getattr(l1, "world", 1) == 1 and not self.self_attn.sequence_parallel and getattr(l1, "int8", None) is None and l1.weight is not None
+                and l1.bias is not None and getattr(l2, "skip_bias_add", False) and not _TP_OPTIONS["fp8_tp_gemm"]):
+            # single tensor-parallel rank: both GEMMs in one autograd node with GELU / GELU' inside their epilogues
+            return OF.fused_ffn(h, l1.weight, l1.bias, l2.weight), l2.bias
+        z = l1(h, skip_bias=True)                # GEMM only; bias rides in the fused bias+GELU kernel
+        return l2(OF.bias_gelu(z, l1.bias))
 
     def _decode_fast_ok(self, x, attn_mask, cache) -> bool:
         a = self.self_attn

@@ -82,6 +82,41 @@ at::Tensor gemm(const at::Tensor& a, const at::Tensor& b, c10::optional<at::Tens
   return d;
 }
 
+// FFN1 forward in one kernel: z = x W^T + b (kept for the backward) and g = gelu(z), both written by the GEMM epilogue.
+std::vector<at::Tensor> gemm_bias_gelu_dual(const at::Tensor& x, const at::Tensor& w, const at::Tensor& bias) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1), "gemm_bias_gelu_dual: x [M,K], w [N,K]");
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && bias.scalar_type() == at::kBFloat16 && bias.numel() == w.size(0) &&
+              bias.is_contiguous(), "gemm_bias_gelu_dual: bf16 operands, bias [N]");
+  TORCH_CHECK(w.size(0) % 8 == 0 && x.size(1) % 8 == 0, "gemm_bias_gelu_dual: N, K multiples of 8");
+  const c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor z = at::empty({x.size(0), w.size(0)}, x.options()), gl = at::empty({x.size(0), w.size(0)}, x.options());
+  pfx::GemmArgs g{};
+  g.a = x.data_ptr(); g.b = w.data_ptr(); g.d = z.data_ptr(); g.d2 = gl.data_ptr(); g.bias = bias.data_ptr();
+  g.M = (int)x.size(0); g.N = (int)w.size(0); g.K = (int)x.size(1);
+  g.lda = (int)x.stride(0); g.ldb = (int)w.stride(0); g.ldd = (int)z.stride(0);
+  g.a_kmajor = true; g.b_kmajor = true; g.out_mode = 0; g.epilogue = pfx::EPI_BIAS_GELU_DUAL; g.ab_format = 1; g.num_sms = num_sms(); g.config = 0;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+  return {z, gl};
+}
+
+// FFN2 dgrad with the GELU derivative applied in the epilogue: dz = (dy W) * gelu'(z);  w is [K = out_features, N = in_features].
+at::Tensor gemm_dgelu(const at::Tensor& dy, const at::Tensor& w, const at::Tensor& z) {
+  TORCH_CHECK(dy.is_cuda() && dy.dim() == 2 && w.dim() == 2 && z.dim() == 2 && dy.is_contiguous() && w.is_contiguous() && z.is_contiguous(), "gemm_dgelu: contiguous 2-D");
+  TORCH_CHECK(dy.size(1) == w.size(0) && z.size(0) == dy.size(0) && z.size(1) == w.size(1), "gemm_dgelu: dy [M,K], w [K,N], z [M,N]");
+  TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && z.scalar_type() == at::kBFloat16, "gemm_dgelu: bf16 only");
+  TORCH_CHECK(w.size(1) % 8 == 0 && w.size(0) % 8 == 0, "gemm_dgelu: N, K multiples of 8");
+  const c10::cuda::CUDAGuard guard(dy.device());
+  at::Tensor dz = at::empty_like(z);
+  pfx::GemmArgs g{};
+  g.a = dy.data_ptr(); g.b = w.data_ptr(); g.d = dz.data_ptr(); g.aux = z.data_ptr(); g.ld_aux = (int)z.stride(0);
+  g.M = (int)dy.size(0); g.N = (int)w.size(1); g.K = (int)dy.size(1);
+  g.lda = (int)dy.stride(0); g.ldb = (int)w.stride(0); g.ldd = (int)dz.stride(0);
+  g.a_kmajor = true; g.b_kmajor = false; g.out_mode = 0; g.epilogue = pfx::EPI_DGELU; g.ab_format = 1; g.num_sms = num_sms(); g.config = 0;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+  return dz;
+}
+
+
 // ------------------------------------------------------------------------------- fused GEMM + collectives
 // GEMM -> reduce-scatter, phase 1: every tile of a*op(b)^T goes straight to the owner rank's staging slot over NVLink.
 void gemm_rs_scatter(const at::Tensor& a, const at::Tensor& b, const std::vector<int64_t>& peer_staging, int64_t my_rank, int64_t rows_per_rank,
@@ -605,6 +640,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_decode", &attention_decode);
   m.def("attention_decode_packed", &attention_decode_packed);
+  m.def("gemm_bias_gelu_dual", &gemm_bias_gelu_dual);
+  m.def("gemm_dgelu", &gemm_dgelu);
   m.def("gemv_skinny", &gemv_skinny);
   m.def("gemm_smallm", &gemm_smallm);
   m.def("gemv_w8a8", &gemv_w8a8);

@@ -113,7 +113,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ CUtensorMap tmap_a_local,
                     float* __restrict__ out_f32, const __nv_bfloat16* __restrict__ bias,
                     int M, int N, int K, int ldd, int epilogue, uint32_t ab_format, const __grid_constant__ GemmComm comm,
-                    const __grid_constant__ PeerMaps peer_maps) {
+                    const __grid_constant__ PeerMaps peer_maps, const __grid_constant__ CUtensorMap tmap_d2,
+                    const __nv_bfloat16* __restrict__ aux, int ld_aux) {
   using S = GemmSmem<kCG, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kLoadN = S::kLoadN;
@@ -295,7 +296,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float v[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i >> 5][i & 31]);
-        if (epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU) {
+        if (epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_GELU_DUAL) {
 #pragma unroll
           for (int i = 0; i < 64; i += 8) {
             if (col0 + i < N) {   // N % 8 == 0 is required by the host wrapper
@@ -313,7 +314,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
         }
+        if (epilogue == EPI_DGELU) {      // acc * gelu'(saved pre-activation): each thread reads its row's 128 bytes of aux
+          const int grow_aux = row0 + (int)row_in_cta;
+          if (grow_aux < M) {
+            const __nv_bfloat16* ap = aux + (size_t)grow_aux * ld_aux + col0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+              if (col0 + i < N) {
+                const uint4 zv = *reinterpret_cast<const uint4*>(ap + i);
+                const __nv_bfloat162* z2 = reinterpret_cast<const __nv_bfloat162*>(&zv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(z2[j]);
+                  v[i + 2 * j] *= gelu_tanh_grad(f.x); v[i + 2 * j + 1] *= gelu_tanh_grad(f.y);
+                }
+              }
+            }
+          }
+        }
         if constexpr (kOutMode == 0 || kOutMode == 3) {
+          // pack v[] into the swizzled staging buffer and TMA-store it; called twice per chunk by the dual-output epilogue
+          auto store_chunk = [&](const CUtensorMap* map_d) {
           const uint32_t buf = store_iter & 1u;
           if (store_iter >= 2) {
             if (is_store_thread) tma_store_wait_read<1>();
@@ -345,12 +366,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tma_store_2d(&peer_maps.m[dst_rank], smem_epi + buf * S::kEpiBytes, col0,
                              comm.my_rank * comm.rows_per_rank + (row0 - dst_rank * comm.rows_per_rank));
               } else {
-                tma_store_2d(&tmap_d, smem_epi + buf * S::kEpiBytes, col0, row0);
+                tma_store_2d(map_d, smem_epi + buf * S::kEpiBytes, col0, row0);
               }
             }
             tma_store_commit();
           }
           ++store_iter;
+          };
+          store_chunk(&tmap_d);
+          if (epilogue == EPI_BIAS_GELU_DUAL) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = gelu_tanh(v[i]);
+            store_chunk(&tmap_d2);
+          }
         } else {
           const int grow = row0 + (int)row_in_cta;
           if (grow < M) {
@@ -428,6 +456,12 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   else     ok &= make_tmap_2d(&tb, g.b, 2, dt, g.N, g.K, (uint64_t)g.ldb * 2, 64, kBlockK);
   if (kOutMode == 0) ok &= make_tmap_2d(&td, g.d, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
   else td = ta;
+  CUtensorMap td2 = td;
+  if (g.epilogue == EPI_BIAS_GELU_DUAL) {
+    if (kOutMode != 0 || g.d2 == nullptr || g.bias == nullptr) return cudaErrorInvalidValue;
+    ok &= make_tmap_2d(&td2, g.d2, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
+  }
+  if (g.epilogue == EPI_DGELU && (g.aux == nullptr || g.ld_aux % 8 || (reinterpret_cast<uintptr_t>(g.aux) & 15) || dt != 1)) return cudaErrorInvalidValue;
   PeerMaps pm;
   for (int i = 0; i < 8; ++i) pm.m[i] = ta;
   if (kOutMode == 3) {
@@ -469,7 +503,8 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   attrs[0].val.clusterDim.x = kCG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tal, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
-                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm, pm);
+                            g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm, pm, td2,
+                            reinterpret_cast<const __nv_bfloat16*>(g.aux), g.ld_aux);
 }
 
 template <int kCG, int kBlockN, int kOutMode>

@@ -6,7 +6,9 @@
 
 namespace pfx {
 
-enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_GELU = 3 };
+// EPI_BIAS_GELU_DUAL: D = acc + bias (the pre-activation the backward needs) AND D2 = gelu(D), two TMA stores per tile (FFN1 forward).
+// EPI_DGELU:          D = acc * gelu'(aux) with aux = the saved pre-activation [M, N] (FFN2 dgrad producing dL/d(pre-activation)).
+enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_GELU = 3, EPI_BIAS_GELU_DUAL = 4, EPI_DGELU = 5 };
 
 // Peer-memory communication descriptor of the fused GEMM+collective modes (passed to the kernel by value).
 struct GemmComm {
@@ -28,6 +30,9 @@ struct GemmArgs {
   const void* b;     // K-major: [N, K] row-major;                              MN-major: [K, N]
   void* d;           // [M, N] row-major, ldd = row stride (elements)
   const void* bias;  // [N] bf16 or nullptr
+  void* d2 = nullptr;         // EPI_BIAS_GELU_DUAL: second output [M, N] (same dtype / ldd as d)
+  const void* aux = nullptr;  // EPI_DGELU: pre-activation [M, N] (same dtype as the operands), row stride ld_aux
+  int ld_aux = 0;
   int M, N, K;
   int lda, ldb, ldd;
   bool a_kmajor, b_kmajor;

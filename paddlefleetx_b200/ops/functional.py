@@ -56,6 +56,82 @@ def _gemm_ok(x: torch.Tensor, *dims: int) -> bool:
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_GELU = 0, 1, 2, 3
 
 
+def _wgrad(lib, g2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """dW = g2^T x2.  With a flat gradient buffer behind the weight (``weight.main_grad``, set up by FusedAdamW) the GEMM stores or
+    accumulates straight into it and a placeholder is handed to autograd (see optims/optimizer.py: direct gradient writes)."""
+    main_grad = getattr(weight, "main_grad", None)
+    if main_grad is not None:
+        fresh = getattr(weight, "_grad_fresh", False)      # first touch since clear_grad: store, do not accumulate
+        if main_grad.dtype == torch.float32:
+            lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 1 if fresh else 2, 0)   # main_grad (+)= dY^T X
+        elif fresh:
+            lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 0, 0)
+        else:
+            main_grad.add_(lib.gemm(g2, x2, None, None, False, False, EPI_NONE, 0, 0))
+        weight._grad_fresh = False
+        # autograd still needs a tensor so that post-accumulate hooks (DP / ZeRO bucket readiness) fire; the optimizer's hook
+        # drops ``weight.grad`` when this flag is set.
+        weight.grad_added_to_main_grad = True
+        gw = torch.empty_like(weight)
+    else:
+        gw = lib.gemm(g2, x2, None, None, False, False, EPI_NONE, 0, 0)
+    _count()
+    return gw
+
+
+class _FusedFFNFn(torch.autograd.Function):
+    """y = gelu(x W1^T + b1) W2^T with the elementwise work inside the GEMM epilogues: the FFN1 GEMM writes both the pre-activation
+    (kept for the backward) and its GELU, the FFN2 dgrad GEMM multiplies by gelu'(pre-activation) on the way out.  Compared with
+    linear -> bias_gelu -> linear this removes two full passes over the [tokens, 4h] activation in forward and three in backward
+    (reference: FusedLinear + separate gelu kernel, hybrid_model.py:598-669; SURVEY L3 "GELU fusable in epilogue")."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2):
+        lib = _native.require()
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        z, g = lib.gemm_bias_gelu_dual(x2, w1, b1)
+        y = lib.gemm(g, w2, None, None, True, True, EPI_NONE, 0, 0)
+        _count(2)
+        ctx.save_for_backward(x2, w1, w2, z, g)
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _native.require()
+        x2, w1, w2, z, g = ctx.saved_tensors
+        g2 = gy.reshape(-1, gy.shape[-1])
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        dz = lib.gemm_dgelu(g2, w2, z)                      # (dy W2) * gelu'(z)
+        _count()
+        gw2 = _wgrad(lib, g2, g, w2) if ctx.needs_input_grad[3] else None
+        gb1 = None
+        if ctx.needs_input_grad[2]:
+            gb1 = lib.colsum(dz, False)
+            _count(2)
+        gw1 = _wgrad(lib, dz, x2, w1) if ctx.needs_input_grad[1] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = lib.gemm(dz, w1, None, None, True, False, EPI_NONE, 0, 0).view(ctx.x_shape)
+            _count()
+        return gx, gw1, gb1, gw2
+
+
+_FUSED_FFN = os.environ.get("PFX_FUSED_FFN", "1") == "1"
+
+
+def fused_ffn(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
+    """``gelu(x @ w1.T + b1) @ w2.T`` (tanh GELU); the second bias is left to the caller's bias+dropout+residual kernel."""
+    if (_FUSED_FFN and x.is_cuda and x.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16 and b1 is not None
+            and b1.dtype == torch.bfloat16 and w1.is_contiguous() and w2.is_contiguous() and w1.shape[0] % 8 == 0 and w1.shape[1] % 8 == 0
+            and w2.shape[0] % 8 == 0 and x.numel() // x.shape[-1] > 128 and _native.use_native(x)):
+        return _FusedFFNFn.apply(x, w1, b1, w2)
+    return linear(bias_gelu(linear(x, w1, None), b1), w2, None)
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T (+ b).  fwd: TN tcgen05 GEMM with bias epilogue; dgrad: NN GEMM (B MN-major, no transpose
     copy); wgrad: TN GEMM with both operands MN-major, optionally accumulating straight into an fp32
@@ -86,23 +162,7 @@ class _LinearFn(torch.autograd.Function):
             gx = lib.gemm(g2, weight, None, None, True, False, EPI_NONE, 0, 0).view(ctx.x_shape)
             _count()
         if ctx.needs_input_grad[1]:
-            main_grad = getattr(weight, "main_grad", None)
-            if main_grad is not None:
-                fresh = getattr(weight, "_grad_fresh", False)      # first touch since clear_grad: store, do not accumulate
-                if main_grad.dtype == torch.float32:
-                    lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 1 if fresh else 2, 0)   # main_grad (+)= dY^T X
-                elif fresh:
-                    lib.gemm(g2, x2, None, main_grad, False, False, EPI_NONE, 0, 0)
-                else:
-                    main_grad.add_(lib.gemm(g2, x2, None, None, False, False, EPI_NONE, 0, 0))
-                weight._grad_fresh = False
-                # autograd still needs a tensor so that post-accumulate hooks (DP / ZeRO bucket readiness)
-                # fire; the engines drop ``weight.grad`` inside that hook when this flag is set.
-                weight.grad_added_to_main_grad = True
-                gw = torch.empty_like(weight)
-            else:
-                gw = lib.gemm(g2, x2, None, None, False, False, EPI_NONE, 0, 0)
-            _count()
+            gw = _wgrad(lib, g2, x2, weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = lib.colsum(g2, False)
             _count(2)

@@ -354,6 +354,59 @@ def check_attention_fwd():
     return dict(ok=ok, shapes=res)
 
 
+def check_fused_ffn():
+    """Dual-output bias+GELU epilogue, dGELU epilogue and the FFN autograd node built on them vs fp32 PyTorch; timing vs the unfused chain."""
+    import torch
+    import torch.nn.functional as F
+    lib = _lib()
+    from paddlefleetx_b200.ops import functional as OF
+    torch.manual_seed(0)
+    errs = {}
+    for (M, H, Fh) in [(300, 256, 1032), (1024, 512, 2048)]:
+        x = torch.randn(M, H, device="cuda").bfloat16()
+        w1 = (torch.randn(Fh, H, device="cuda") * 0.05).bfloat16()
+        b1 = (torch.randn(Fh, device="cuda") * 0.1).bfloat16()
+        z, g = lib.gemm_bias_gelu_dual(x, w1, b1)
+        zr = x.float() @ w1.float().t() + b1.float()
+        errs[f"dual_z_{M}"] = _relerr(z, zr)
+        errs[f"dual_g_{M}"] = _relerr(g, F.gelu(zr, approximate="tanh"))
+        dy = torch.randn(M, H, device="cuda").bfloat16()
+        w2 = (torch.randn(H, Fh, device="cuda") * 0.05).bfloat16()
+        dz = lib.gemm_dgelu(dy, w2, z)
+        zf = z.float().requires_grad_(True)
+        (F.gelu(zf, approximate="tanh") * (dy.float() @ w2.float())).sum().backward()
+        errs[f"dgelu_{M}"] = _relerr(dz, zf.grad)
+    # autograd node vs the unfused chain (same kernels otherwise) and vs fp32
+    M, H, Fh = 2048, 1024, 4096
+    xs = [torch.randn(M, H, device="cuda").bfloat16().requires_grad_(True) for _ in range(2)]
+    xs[1].data.copy_(xs[0].data)
+    mk = lambda: [(torch.randn(Fh, H, device="cuda") * 0.03).bfloat16().requires_grad_(True), (torch.randn(Fh, device="cuda") * 0.1).bfloat16().requires_grad_(True),
+                  (torch.randn(H, Fh, device="cuda") * 0.03).bfloat16().requires_grad_(True)]
+    torch.manual_seed(1); pa = mk()
+    torch.manual_seed(1); pb = mk()
+    gy = torch.randn(M, H, device="cuda").bfloat16()
+    ya = OF.fused_ffn(xs[0], pa[0], pa[1], pa[2]); ya.backward(gy)
+    yb = OF.linear(OF.bias_gelu(OF.linear(xs[1], pb[0], None), pb[1]), pb[2], None); yb.backward(gy)
+    errs["ffn_y"] = _relerr(ya, yb)
+    errs["ffn_dx"] = _relerr(xs[0].grad, xs[1].grad)
+    for n, a, b in zip(("dw1", "db1", "dw2"), pa, pb):
+        errs["ffn_" + n] = _relerr(a.grad, b.grad)
+    ok = all(e < 1.5e-2 for e in errs.values())
+    M, H, Fh = 8192, 4096, 16384
+    x = torch.randn(M, H, device="cuda").bfloat16().requires_grad_(True)
+    w1 = (torch.randn(Fh, H, device="cuda") * 0.02).bfloat16().requires_grad_(True)
+    b1 = torch.zeros(Fh, device="cuda").bfloat16().requires_grad_(True)
+    w2 = (torch.randn(H, Fh, device="cuda") * 0.02).bfloat16().requires_grad_(True)
+    gy = torch.randn(M, H, device="cuda").bfloat16()
+    def fused():
+        OF.fused_ffn(x, w1, b1, w2).backward(gy)
+    def chain():
+        OF.linear(OF.bias_gelu(OF.linear(x, w1, None), b1), w2, None).backward(gy)
+    t_f, _ = _time(fused, iters=8, warmup=2)
+    t_c, _ = _time(chain, iters=8, warmup=2)
+    return dict(ok=ok, errs={k: round(v, 5) for k, v in errs.items()}, fwd_bwd_ms_fused=round(t_f, 4), fwd_bwd_ms_unfused=round(t_c, 4))
+
+
 def check_gemv_tuning():
     """Sweep the GEMV launch shape (weight rows per warp x K-slices per block) on the decode shapes of GPT-6.7B, L2 cold and warm."""
     import torch
@@ -478,6 +531,7 @@ CHECKS = {
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
     "gemv_tuning": check_gemv_tuning,
+    "fused_ffn": check_fused_ffn,
     "attention_fwd": check_attention_fwd,
     "gemm_smallm": check_smallm,
     "gemv_skinny": check_gemv,
