@@ -40,7 +40,7 @@ class ExpertLayer(nn.Module):
             p.no_sync = True
 
     def forward(self, x):
-        return OF.linear(OF.bias_gelu(OF.linear(x, self.htoh4.weight, None), self.htoh4.bias), self.h4toh.weight, self.h4toh.bias)
+        return OF.fused_ffn(x, self.htoh4.weight, self.htoh4.bias, self.h4toh.weight, self.h4toh.bias)
 
 
 class MoELayer(nn.Module):

@@ -86,16 +86,17 @@ class _FusedFFNFn(torch.autograd.Function):
     (reference: FusedLinear + separate gelu kernel, hybrid_model.py:598-669; SURVEY L3 "GELU fusable in epilogue")."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2):
+    def forward(ctx, x, w1, b1, w2, b2):
         lib = _native.require()
         x2 = x.reshape(-1, x.shape[-1])
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         z, g = lib.gemm_bias_gelu_dual(x2, w1, b1)
-        y = lib.gemm(g, w2, None, None, True, True, EPI_NONE, 0, 0)
+        y = lib.gemm(g, w2, b2, None, True, True, EPI_BIAS if b2 is not None else EPI_NONE, 0, 0)
         _count(2)
         ctx.save_for_backward(x2, w1, w2, z, g)
         ctx.x_shape = x.shape
+        ctx.has_b2 = b2 is not None
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -117,19 +118,24 @@ class _FusedFFNFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = lib.gemm(dz, w1, None, None, True, False, EPI_NONE, 0, 0).view(ctx.x_shape)
             _count()
-        return gx, gw1, gb1, gw2
+        gb2 = None
+        if ctx.has_b2 and ctx.needs_input_grad[4]:
+            gb2 = lib.colsum(g2, False)
+            _count(2)
+        return gx, gw1, gb1, gw2, gb2
 
 
 _FUSED_FFN = os.environ.get("PFX_FUSED_FFN", "1") == "1"
 
 
-def fused_ffn(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor) -> torch.Tensor:
-    """``gelu(x @ w1.T + b1) @ w2.T`` (tanh GELU); the second bias is left to the caller's bias+dropout+residual kernel."""
+def fused_ffn(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``gelu(x @ w1.T + b1) @ w2.T (+ b2)`` (tanh GELU).  The decoder layer passes ``b2 = None`` and folds that bias into its
+    bias+dropout+residual kernel; expert FFNs pass it."""
     if (_FUSED_FFN and x.is_cuda and x.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16 and b1 is not None
             and b1.dtype == torch.bfloat16 and w1.is_contiguous() and w2.is_contiguous() and w1.shape[0] % 8 == 0 and w1.shape[1] % 8 == 0
-            and w2.shape[0] % 8 == 0 and x.numel() // x.shape[-1] > 128 and _native.use_native(x)):
-        return _FusedFFNFn.apply(x, w1, b1, w2)
-    return linear(bias_gelu(linear(x, w1, None), b1), w2, None)
+            and w2.shape[0] % 8 == 0 and x.numel() // x.shape[-1] > 128 and (b2 is None or b2.dtype == torch.bfloat16) and _native.use_native(x)):
+        return _FusedFFNFn.apply(x, w1, b1, w2, b2)
+    return linear(bias_gelu(linear(x, w1, None), b1), w2, b2)
 
 
 class _LinearFn(torch.autograd.Function):
