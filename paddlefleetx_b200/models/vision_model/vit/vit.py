@@ -47,7 +47,7 @@ class ViTMLP(nn.Module):
     def forward(self, x):
         h = OF.linear(x, self.fc1.weight, None)
         if self.act == "gelu":
-            h = F.gelu(h + self.fc1.bias) if not h.is_cuda else OF.bias_gelu(h, self.fc1.bias)
+            h = OF.bias_gelu(h, self.fc1.bias, exact=True)        # nn.GELU (erf form), as in the reference ViT MLP
         else:
             h = F.relu(h + self.fc1.bias)
         h = OF.dropout(h, self.drop, self.training)

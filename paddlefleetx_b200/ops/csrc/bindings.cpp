@@ -246,17 +246,17 @@ static void check_same_dtype(const at::Tensor& x, const c10::optional<at::Tensor
   if (t.has_value() && t->defined())
     TORCH_CHECK(t->scalar_type() == x.scalar_type(), what, ": operand dtype ", t->scalar_type(), " differs from activation dtype ", x.scalar_type());
 }
-at::Tensor bias_gelu_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias) {
+at::Tensor bias_gelu_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias, bool exact) {
   PFX_CHECK_CUDA_CONTIG(x);
   check_same_dtype(x, bias, "bias_gelu");
   const c10::cuda::CUDAGuard guard(x.device());
   auto y = at::empty_like(x);
   const int64_t cols = x.size(-1);
   PFX_CUDA_CHECK(pfx::bias_gelu(x.data_ptr(), (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr, nullptr, y.data_ptr(),
-                                x.numel() / cols, (int)cols, dtype_code(x), false, num_sms(), cur_stream()));
+                                x.numel() / cols, (int)cols, dtype_code(x), false, num_sms(), cur_stream(), exact));
   return y;
 }
-at::Tensor bias_gelu_bwd(const at::Tensor& dy, const at::Tensor& x, c10::optional<at::Tensor> bias) {
+at::Tensor bias_gelu_bwd(const at::Tensor& dy, const at::Tensor& x, c10::optional<at::Tensor> bias, bool exact) {
   PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(dy);
   check_same_dtype(x, bias, "bias_gelu_bwd");
   TORCH_CHECK(dy.scalar_type() == x.scalar_type(), "bias_gelu_bwd: dy dtype");
@@ -264,7 +264,7 @@ at::Tensor bias_gelu_bwd(const at::Tensor& dy, const at::Tensor& x, c10::optiona
   auto dx = at::empty_like(x);
   const int64_t cols = x.size(-1);
   PFX_CUDA_CHECK(pfx::bias_gelu(x.data_ptr(), (bias.has_value() && bias->defined()) ? bias->data_ptr() : nullptr, dy.data_ptr(),
-                                dx.data_ptr(), x.numel() / cols, (int)cols, dtype_code(x), true, num_sms(), cur_stream()));
+                                dx.data_ptr(), x.numel() / cols, (int)cols, dtype_code(x), true, num_sms(), cur_stream(), exact));
   return dx;
 }
 at::Tensor bias_dropout_add_fwd(const at::Tensor& x, c10::optional<at::Tensor> bias, c10::optional<at::Tensor> residual, double p,

@@ -269,9 +269,15 @@ cudaError_t norm_bwd(const void* dy, const void* x, const void* w, const float* 
 }
 
 // --------------------------------------------------------------------------- bias + GELU
+// exact (erf) GELU — nn.GELU's default, used by the vision models; the language models use the tanh form
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+
 template <typename T, bool kBwd>
 __global__ void bias_gelu_kernel(const T* __restrict__ x, const T* __restrict__ bias, const T* __restrict__ dy, T* __restrict__ out,
-                                 size_t total_vec, int nvec_row) {
+                                 size_t total_vec, int nvec_row, bool exact) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
     float xv[8], bv[8], o[8];
     unpack8<T>(ld_stream(reinterpret_cast<const uint4*>(x) + i), xv);
@@ -284,10 +290,10 @@ __global__ void bias_gelu_kernel(const T* __restrict__ x, const T* __restrict__ 
       float gv[8];
       unpack8<T>(ld_stream(reinterpret_cast<const uint4*>(dy) + i), gv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = gv[j] * gelu_tanh_grad(xv[j]);
+      for (int j = 0; j < 8; ++j) o[j] = gv[j] * (exact ? gelu_erf_grad(xv[j]) : gelu_tanh_grad(xv[j]));
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = gelu_tanh(xv[j]);
+      for (int j = 0; j < 8; ++j) o[j] = exact ? gelu_erf(xv[j]) : gelu_tanh(xv[j]);
     }
     st_stream(reinterpret_cast<uint4*>(out) + i, pack8<T>(o));
   }
@@ -300,14 +306,14 @@ static int ew_grid(size_t total_vec, int threads, int num_sms) {
 }
 
 cudaError_t bias_gelu(const void* x, const void* bias, const void* dy, void* out, size_t rows, int cols, int dtype, bool bwd, int num_sms,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool exact) {
   if (cols % 8) return cudaErrorInvalidValue;
   const size_t total = rows * (size_t)(cols / 8);
   if (!total) return cudaSuccess;
   const int threads = 256, grid = ew_grid(total, threads, num_sms);
 #define PFX_LAUNCH(T)                                                                                                     \
-  if (bwd) bias_gelu_kernel<T, true><<<grid, threads, 0, st>>>((const T*)x, (const T*)bias, (const T*)dy, (T*)out, total, cols / 8); \
-  else bias_gelu_kernel<T, false><<<grid, threads, 0, st>>>((const T*)x, (const T*)bias, nullptr, (T*)out, total, cols / 8);
+  if (bwd) bias_gelu_kernel<T, true><<<grid, threads, 0, st>>>((const T*)x, (const T*)bias, (const T*)dy, (T*)out, total, cols / 8, exact); \
+  else bias_gelu_kernel<T, false><<<grid, threads, 0, st>>>((const T*)x, (const T*)bias, nullptr, (T*)out, total, cols / 8, exact);
   if (dtype == 1) { PFX_LAUNCH(__nv_bfloat16) } else { PFX_LAUNCH(__half) }
 #undef PFX_LAUNCH
   return cudaGetLastError();

@@ -13,7 +13,7 @@ cudaError_t norm_bwd(const void* dy, const void* x, const void* w, const float* 
                      float* workspace, int rows, int cols, int dtype, bool rms, int num_sms, cudaStream_t st);
 
 cudaError_t bias_gelu(const void* x, const void* bias, const void* dy, void* out, size_t rows, int cols, int dtype, bool bwd, int num_sms,
-                      cudaStream_t st);
+                      cudaStream_t st, bool exact = false);
 cudaError_t bias_dropout_add(const void* x, const void* bias, const void* residual, void* out, size_t rows, int cols, float p,
                              uint64_t seed, uint64_t offset, int dtype, bool bwd, int num_sms, cudaStream_t st);
 int colsum_num_parts(int rows);

@@ -252,33 +252,35 @@ def matmul_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 # =============================================================================== bias + gelu
 class _BiasGeluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, bias):
+    def forward(ctx, x, bias, exact=False):
         lib = _native.require()
         x = x.contiguous()
         ctx.save_for_backward(x, bias)
+        ctx.exact = bool(exact)
         _count()
-        return lib.bias_gelu_fwd(x, bias)
+        return lib.bias_gelu_fwd(x, bias, ctx.exact)
 
     @staticmethod
     def backward(ctx, gy):
         lib = _native.require()
         x, bias = ctx.saved_tensors
-        gx = lib.bias_gelu_bwd(gy.contiguous(), x, bias)
+        gx = lib.bias_gelu_bwd(gy.contiguous(), x, bias, ctx.exact)
         _count()
         gb = None
         if bias is not None and ctx.needs_input_grad[1]:
             gb = lib.colsum(gx.view(-1, gx.shape[-1]), False)
             _count(2)
-        return gx, gb
+        return gx, gb, None
 
 
-def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """tanh-approximated GELU of (x + bias) — reference hybrid_model.py:667 (approximate=True)."""
+def bias_gelu(x: torch.Tensor, bias: Optional[torch.Tensor] = None, exact: bool = False) -> torch.Tensor:
+    """GELU of (x + bias): tanh approximation by default (reference GPT, hybrid_model.py:667 ``approximate=True``), exact erf form
+    with ``exact=True`` (``nn.GELU`` default, used by the vision / multimodal models)."""
     if _native_ok(x) and x.shape[-1] % 8 == 0:
         if bias is not None and bias.dtype != x.dtype:        # O1 autocast: fp32 parameters next to bf16 activations
             bias = bias.to(x.dtype)
-        return _BiasGeluFn.apply(x, bias)
-    return F.gelu(x if bias is None else x + bias, approximate="tanh")
+        return _BiasGeluFn.apply(x, bias, exact)
+    return F.gelu(x if bias is None else x + bias, approximate="none" if exact else "tanh")
 
 
 # =============================================================================== bias + dropout + residual

@@ -117,9 +117,13 @@ def check_gelu_dropout():
     xf = (x.float() + bias.float()).requires_grad_(True)
     ref = torch.nn.functional.gelu(xf, approximate="tanh")
     ref.backward(dy.float())
-    y = lib.bias_gelu_fwd(x, bias)
-    dx = lib.bias_gelu_bwd(dy, x, bias)
+    y = lib.bias_gelu_fwd(x, bias, False)
+    dx = lib.bias_gelu_bwd(dy, x, bias, False)
     errs = dict(gelu=_relerr(y, ref), dgelu=_relerr(dx, xf.grad))
+    xe = (x.float() + bias.float()).requires_grad_(True)
+    refe = torch.nn.functional.gelu(xe)                     # exact (erf) form used by the vision models
+    refe.backward(dy.float())
+    errs.update(gelu_erf=_relerr(lib.bias_gelu_fwd(x, bias, True), refe), dgelu_erf=_relerr(lib.bias_gelu_bwd(dy, x, bias, True), xe.grad))
     p = 0.1
     yd = lib.bias_dropout_add_fwd(x, bias, res, p, 1234, 77)
     dxd = lib.dropout_bwd(dy, p, 1234, 77)
