@@ -7,8 +7,9 @@
 //   warp 0   TMA producer: Q once, then K / V tiles of 128 keys through a 2-stage ring
 //   warp 1   MMA issuer:   S = Q K^T  (UMMA 128x128x16, both operands K-major)   -> TMEM columns [0, 128)
 //                          PV = P V   (UMMA 128xDx16, P K-major from smem, V MN-major) -> TMEM columns [128, 128 + D)
-//   warps 2-5 softmax:     one thread per query row (the TMEM lane it can read): row max over the 128 scores, exp2 with the
-//                          running max, P written to shared memory as bf16 in the 128-byte-swizzled K-major layout the second
+//   warps 2-9 softmax:     two threads per query row (each reads its TMEM lane; one takes score columns 0-63 and output channels
+//                          0..D/2, the other the rest): scores drained from TMEM in one pass, row max exchanged through shared
+//                          memory, exp2 with the running max, P written as bf16 in the 128-byte-swizzled K-major layout the second
 //                          MMA consumes, running sum and the O accumulator (fp32, in registers) rescaled once per KV tile
 // S for tile j+1 is issued as soon as the softmax warps have drained S_j from TMEM, so the tensor core computes the next
 // scores while the softmax of the current tile is in its exp / store phase.  Causal tiles above the diagonal are never loaded.
@@ -26,7 +27,7 @@ namespace pfx {
 
 namespace {
 
-constexpr int kFaThreads = 192;
+constexpr int kFaThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two column halves x four TMEM lane quarters)
 constexpr int kFaTile = 128;          // queries per CTA, keys per KV tile
 
 template <int kD>
@@ -77,7 +78,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (elect_one()) {
       mbar_init(q_full, 1);
       for (int s = 0; s < S::kStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-      mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_free, 4);
+      mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(p_full, 8); mbar_init(pv_full, 1); mbar_init(pv_free, 8);
       fence_barrier_init();
     }
     __syncwarp();
@@ -149,81 +150,73 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else {
     // ======================================================================================= softmax / epilogue
+    // Two threads per query row: warps 2-5 own score columns [0, 64) and output channels [0, D/2), warps 6-9 the other halves (both
+    // groups map onto the same four TMEM lane quarters).  The row maximum is exchanged through shared memory once per KV tile.
+    __shared__ float s_xchg[2][2][kFaTile];
     const uint32_t q = warp & 3u;
+    const int half = (int)((warp - 2u) >> 2);
     const int row = (int)(q * 32u + lane);               // query row inside the tile == TMEM lane
     const int row_g = q0 + row;
     const uint32_t lane_addr = (q * 32u) << 16;
-    float o[kD];
+    constexpr int kDH = kD / 2;
+    float o[kDH];
 #pragma unroll
-    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    for (int i = 0; i < kDH; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f;
-    uint8_t* p_row = smem_gen + (smem_p - smem_base) + (row / 8) * 1024 + (row % 8) * 128;
+    uint8_t* p_row = smem_gen + (smem_p - smem_base) + half * (kFaTile * 128) + (row / 8) * 1024 + (row % 8) * 128;
     for (int j = 0; j < n_kv; ++j) {
-      const int col0 = j * kFaTile;
+      const int col0 = j * kFaTile + half * 64;
       mbar_wait(s_full, (uint32_t)j & 1u);
       tcgen05_fence_after();
-      const bool need_mask = (kCausal && col0 + kFaTile - 1 > row_g + (Sk - Sq)) || (col0 + kFaTile > Sk);
-      // pass 1: row maximum
-      float m_tile = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < kFaTile; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + c, r);
-        tmem_ld_wait();
+      const bool need_mask = (kCausal && col0 + 63 > row_g + (Sk - Sq)) || (col0 + 64 > Sk);
+      // one pass over this thread's 64 scores: both 32-column loads are issued before the single wait
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(tmem_s + lane_addr + half * 64, r0);
+      tmem_ld_32x32b_x32(tmem_s + lane_addr + half * 64 + 32, r1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);            // S drained into registers: the next QK^T may overwrite it
+      float sc[64];
+      float m_part = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]) * scale_log2;
-          if (need_mask) {
-            const int cg = col0 + c + i;
-            if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) s = -INFINITY;
-          }
-          m_tile = fmaxf(m_tile, s);
+      for (int i = 0; i < 64; ++i) {
+        float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) * scale_log2;
+        if (need_mask) {
+          const int cg = col0 + i;
+          if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) v = -INFINITY;
         }
+        sc[i] = v;
+        m_part = fmaxf(m_part, v);
       }
-      const float m_new = fmaxf(m, m_tile);
+      s_xchg[j & 1][half][row] = m_part;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float m_new = fmaxf(m, fmaxf(m_part, s_xchg[j & 1][half ^ 1][row]));
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;        // fully masked row so far: keep everything at zero
       const float corr = exp2f(m - m_use);
-      // pass 2: probabilities -> bf16 P tile in shared memory (swizzled K-major), running sum
       float l_tile = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kFaTile; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + c, r);
-        tmem_ld_wait();
-        float p[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]) * scale_log2;
-          if (need_mask) {
-            const int cg = col0 + c + i;
-            if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) s = -INFINITY;
-          }
-          p[i] = exp2f(s - m_use);
-          l_tile += p[i];
-        }
-        uint8_t* panel = p_row + (c / 64) * (kFaTile * 128);
+      for (int g = 0; g < 8; ++g) {                  // eight 16-byte chunks (8 keys each) of this half's 64-key panel
+        float pv[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {              // four 16-byte chunks (8 keys each) of this 32-key slice
-          const int chunk = ((c % 64) / 8 + g) ^ (row % 8);
-          uint4 v;
-          v.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]); v.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-          v.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]); v.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(panel + chunk * 16) = v;
-        }
+        for (int i = 0; i < 8; ++i) { pv[i] = exp2f(sc[g * 8 + i] - m_use); l_tile += pv[i]; }
+        const int chunk = g ^ (row % 8);
+        uint4 v;
+        v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]); v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
+        *reinterpret_cast<uint4*>(p_row + chunk * 16) = v;
       }
-      tcgen05_fence_before();
       fence_proxy_async_smem();                    // generic-proxy stores of P -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_free); mbar_arrive(p_full); }
+      if (lane == 0) mbar_arrive(p_full);
       l = l * corr + l_tile;
       m = m_new;
-      // accumulate O = O * corr + P V
+      // accumulate this thread's half of O = O * corr + P V
       mbar_wait(pv_full, (uint32_t)j & 1u);
       tcgen05_fence_after();
 #pragma unroll
-      for (int c = 0; c < kD; c += 32) {
+      for (int c = 0; c < kDH; c += 32) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_pv + lane_addr + c, r);
+        tmem_ld_32x32b_x32(tmem_pv + lane_addr + half * kDH + c, r);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[c + i] = o[c + i] * corr + __uint_as_float(r[i]);
@@ -232,17 +225,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(pv_free);
     }
+    // row sum = sum of the two column halves
+    s_xchg[n_kv & 1][half][row] = l;
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    const float l_all = l + s_xchg[n_kv & 1][half ^ 1][row];
     if (row_g < Sq) {
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)(b * Sq + row_g) * H + h) * kD);
+      const float inv = l_all > 0.f ? 1.f / l_all : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)(b * Sq + row_g) * H + h) * kD + half * kDH);
 #pragma unroll
-      for (int c = 0; c < kD; c += 8) {
+      for (int c = 0; c < kDH; c += 8) {
         uint4 v;
         v.x = pack_bf16x2(o[c + 0] * inv, o[c + 1] * inv); v.y = pack_bf16x2(o[c + 2] * inv, o[c + 3] * inv);
         v.z = pack_bf16x2(o[c + 4] * inv, o[c + 5] * inv); v.w = pack_bf16x2(o[c + 6] * inv, o[c + 7] * inv);
         dst[c / 8] = v;
       }
-      if (lse != nullptr) lse[((size_t)b * H + h) * Sq + row_g] = (l > 0.f) ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      if (lse != nullptr && half == 0) lse[((size_t)b * H + h) * Sq + row_g] = (l_all > 0.f) ? (m + log2f(l_all)) * 0.6931471805599453f : -INFINITY;
     }
   }
   __syncthreads();
