@@ -20,8 +20,8 @@ import torch
 import torch.nn.functional as F
 
 # 0 = never, 1 = where it is at least as fast as the library kernel (short sequences: prefill / few-hundred-token inputs), 2 = always.
-# Measured on B200 (profiles/README.md): 258 TFLOP/s at S=1024 causal D=128 vs 799 for cuDNN — the kernel is correct but its single
-# softmax group serialises against the MMAs, so long sequences stay on the library until the ping-pong version lands.
+# Measured on B200 (profiles/README.md): 373 TFLOP/s at S=1024 causal D=128 vs 839 for cuDNN — correct, but its per-tile softmax path is
+# still ~3x the MMA time, so long sequences stay on the library until the ping-pong version lands.
 _NATIVE_FWD = int(os.environ.get("PFX_NATIVE_ATTN_FWD", "1"))
 _NATIVE_FWD_MAX_SEQ = 256
 
