@@ -49,7 +49,7 @@ class FusedAdamW:
                  named_parameters=None, apply_decay_param_fun: Optional[Callable] = None, hcg=None, sharding_stage: int = 1,
                  use_main_grad: bool = False, bucket_mb: int = 512, reduce_overlap: bool = False, broadcast_overlap: bool = False,
                  use_p2p: bool = False, lazy_init: bool = False, params_are_shards: bool = False, direct_grad: Optional[bool] = None,
-                 **unused):
+                 offload: bool = False, **unused):
         self._learning_rate = learning_rate
         self.beta1, self.beta2, self.eps, self.weight_decay = float(beta1), float(beta2), float(epsilon), float(weight_decay)
         self.grad_clip = grad_clip
@@ -79,7 +79,8 @@ class FusedAdamW:
             # ZeRO-3: the "parameters" handed in are already per-rank shards (parallel/sharding.py): no further
             # partitioning or reduce-scatter here, only the dp all-reduce, the cross-group norm and the update
             self.sh_world, self.sh_rank = 1, 0
-        self.use_p2p = bool(use_p2p) and self.sh_world > 1 and named[0][1].is_cuda
+        self.offload = bool(offload)
+        self.use_p2p = bool(use_p2p) and self.sh_world > 1 and named[0][1].is_cuda and not self.offload
 
         # ---- bucket assignment (reverse registration order: last layers finish backward first)
         bucket_bytes = bucket_mb * 1024 * 1024 if self.replicas > 1 else (1 << 62)
@@ -132,6 +133,15 @@ class FusedAdamW:
             g.meta["master"] = g.param_buf[lo:hi].float().clone() if g.meta["has_master"] else g.param_buf[lo:hi]
             g.meta["m"] = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
             g.meta["v"] = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
+            if self.offload:
+                # reference ``sharding_offload`` (group_sharded stage 2 + CPU offload, eager_engine.py:295-307): fp32 master weights and both
+                # moments live in (pinned) host memory, the update runs on the host and only the low-precision weights return to the device.
+                # With 180 GB per GPU this is a capacity escape hatch, not a performance path.
+                pin = dev.type == "cuda"
+                g.meta["has_master"] = True
+                for k2 in ("master", "m", "v"):
+                    src = g.meta[k2].detach().float().cpu()
+                    g.meta[k2] = src.pin_memory() if pin else src.clone()
             g.meta["pending"] = 0
             g.meta["synced"] = False
             if self.use_p2p:
@@ -290,6 +300,7 @@ class FusedAdamW:
         for g in self.groups:
             self._sync_group_grads(g)
         native = self._dev.type == "cuda" and _native.use_native(self.groups[0].param_buf)
+        native_update = native and not self.offload
         inv_scale = 1.0 / (self.loss_scale * self.replicas)
         clip_norm = self.grad_clip.clip_norm if self.grad_clip is not None else 0.0
 
@@ -323,7 +334,7 @@ class FusedAdamW:
         sq = self._reduce_norm(sq, moe_sq)
 
         # ---- clip coefficient / found-inf on device, fused update
-        if native:
+        if native_update:
             lib.clip_coef_(sq, inv_scale, clip_norm, self._gscale, self._found_inf, self._gnorm)
             OF._count()
             for g in self.groups:
@@ -353,6 +364,8 @@ class FusedAdamW:
                     lo, hi = g.meta["lo"], g.meta["hi"]
                     grad = g.grad_buf[lo:hi].float() * (inv_scale * coef)
                     m, v, w = g.meta["m"], g.meta["v"], g.meta["master"]
+                    if self.offload:
+                        grad = grad.to(m.device)              # D2H: the update runs where the state lives
                     m.mul_(self.beta1).add_(grad, alpha=1 - self.beta1)
                     v.mul_(self.beta2).addcmul_(grad, grad, value=1 - self.beta2)
                     wd = self.weight_decay if g.key[1] else 0.0

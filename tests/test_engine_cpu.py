@@ -101,3 +101,20 @@ def test_direct_grad_layout_matches_classic_layout_with_accumulation():
     g0.params[0].main_grad.fill_(7.0)
     opt._finalize_fresh(g0)
     assert float(g0.params[0].main_grad.abs().sum()) == 0.0
+
+
+def test_optimizer_state_offload_matches_resident_state():
+    """``sharding_offload``: master weights and moments on the host, update on the host, weights copied back — same trajectory."""
+    import torch
+
+    ov = ["Global.local_batch_size=2", "Global.micro_batch_size=2"]
+    ea = build_engine(tiny_gpt_config(ov))
+    eb = build_engine(tiny_gpt_config(ov + ["Optimizer.offload=True"]))
+    eb._module.model.load_state_dict(ea._module.model.state_dict())
+    assert eb.optimizer.offload and all(g.meta["m"].device.type == "cpu" for g in eb.optimizer.groups)
+    batches = synthetic_batches(tiny_gpt_config(ov), 3, seed=4)
+    la = [float(ea.train_step(b)) for b in batches]
+    lb = [float(eb.train_step(b)) for b in batches]
+    assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-6, (la, lb)
+    sd = eb.optimizer.state_dict()
+    eb.optimizer.set_state_dict(sd)
