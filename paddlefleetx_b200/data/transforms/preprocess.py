@@ -18,6 +18,27 @@ except Exception:  # pragma: no cover
     _HAS_PIL = False
 
 
+def _number(expr) -> float:
+    """YAML recipes write constants like ``1.0/255.0``; evaluate that arithmetic without ``eval``."""
+    import ast
+    import operator as op
+
+    if not isinstance(expr, str):
+        return float(expr)
+    ops = {ast.Add: op.add, ast.Sub: op.sub, ast.Mult: op.mul, ast.Div: op.truediv, ast.USub: op.neg, ast.Pow: op.pow}
+
+    def ev(node):
+        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
+            return node.value
+        if isinstance(node, ast.BinOp) and type(node.op) in ops:
+            return ops[type(node.op)](ev(node.left), ev(node.right))
+        if isinstance(node, ast.UnaryOp) and type(node.op) in ops:
+            return ops[type(node.op)](ev(node.operand))
+        raise ValueError(f"unsupported numeric expression: {expr!r}")
+
+    return float(ev(ast.parse(expr, mode="eval").body))
+
+
 def _resize(img: np.ndarray, size, interpolation: str = "bilinear") -> np.ndarray:
     h, w = (int(size[0]), int(size[1])) if isinstance(size, (tuple, list)) else (int(size), int(size))      # size = (height, width)
     if _HAS_PIL:
@@ -109,7 +130,7 @@ class RandFlipImage:
 
 class NormalizeImage:
     def __init__(self, scale=None, mean=None, std=None, order="chw", output_fp16=False, channel_num=3, **unused):
-        self.scale = float(eval(scale)) if isinstance(scale, str) else float(scale if scale is not None else 1.0 / 255.0)
+        self.scale = _number(scale if scale is not None else 1.0 / 255.0)
         shape = (3, 1, 1) if order == "chw" else (1, 1, 3)
         self.mean = np.asarray(mean if mean is not None else [0.485, 0.456, 0.406], np.float32).reshape(shape)
         self.std = np.asarray(std if std is not None else [0.229, 0.224, 0.225], np.float32).reshape(shape)
@@ -193,7 +214,7 @@ class Pixels:
 
 class RandomErasing:
     def __init__(self, EPSILON=0.5, sl=0.02, sh=0.4, r1=0.3, mean=(0.0, 0.0, 0.0), attempt=100, use_log_aspect=False, mode="const", **unused):
-        self.p, self.sl, self.sh, self.r1, self.attempt, self.log = float(eval(EPSILON)) if isinstance(EPSILON, str) else EPSILON, sl, sh, r1, attempt, use_log_aspect
+        self.p, self.sl, self.sh, self.r1, self.attempt, self.log = _number(EPSILON), sl, sh, r1, attempt, use_log_aspect
         self.get = Pixels(mode, mean)
 
     def __call__(self, img):
