@@ -45,13 +45,21 @@ def get_args(argv=None):
 
 
 def build_tokenizer(args):
-    from paddlefleetx_b200.data.tokenizers.gpt_tokenizer import GPTTokenizer
+    """``--tokenizer_name`` x ``--model_name`` (a local vocabulary directory or a cached name) -> an object with ``encode(text) -> ids``
+    *without* sequence-template tokens, ``eos_token_id`` and ``__len__``."""
+    from paddlefleetx_b200.data.tokenizers import ErnieTokenizer, GPTChineseTokenizer, GPTTokenizer
 
     if args.tokenizer_name == "ByteTokenizer":
         return GPTTokenizer.byte_fallback()
+    if args.tokenizer_name == "ErnieTokenizer":
+        tok = ErnieTokenizer.from_pretrained(args.model_name)
+        tok.encode, tok.eos_token_id = tok.encode_plain, tok.sep_token_id      # corpus ids carry no [CLS]/[SEP] frame; documents end with [SEP]
+        return tok
+    if args.tokenizer_name == "GPTChineseTokenizer":
+        return GPTChineseTokenizer.from_pretrained(args.model_name)
     try:
         return GPTTokenizer.from_pretrained(args.model_name)
-    except Exception as exc:   # offline box without the vocab files
+    except FileNotFoundError as exc:   # offline box without the vocab files
         print(f"[preprocess] {exc}; falling back to the byte-level tokenizer", file=sys.stderr)
         return GPTTokenizer.byte_fallback()
 
@@ -107,7 +115,7 @@ def main(argv=None):
     files = sorted(os.path.join(a.input_path, f) for f in os.listdir(a.input_path)) if os.path.isdir(a.input_path) else [a.input_path]
     files = [f for f in files if f.endswith((".json", ".jsonl"))] or files
     vocab_probe = build_tokenizer(a)
-    dtype = np.uint16 if len(getattr(vocab_probe, "encoder", range(65536))) < 65500 else np.int32
+    dtype = np.uint16 if len(vocab_probe) < 65500 else np.int32
     blocks, lens, sent_lens, doc_sent_counts = [], [], [], []
     t0, nbytes, ndocs = time.time(), 0, 0
     pool = mp.Pool(a.workers, initializer=_init, initargs=(a,)) if a.workers > 1 else None

@@ -32,6 +32,10 @@ class ImagenDataset(torch.utils.data.Dataset):
                     parts = line.rstrip("\n").split("\t")
                     if len(parts) > max(caption_col, image_col):
                         self.rows.append((parts[caption_col], parts[image_col]))
+        if isinstance(tokenizer, str):           # a text-tower name or a vocabulary directory (t5-* / *deberta*)
+            from ..tokenizers import get_text_tokenizer
+
+            tokenizer = get_text_tokenizer(tokenizer, strict=True)
         if tokenizer is None:
             from ..tokenizers import GPTTokenizer
 

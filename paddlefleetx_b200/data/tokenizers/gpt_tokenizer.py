@@ -158,3 +158,96 @@ class GPTTokenizer:
         if return_attention_mask:
             out["attention_mask"] = masks if not isinstance(text, str) else masks[0]
         return out
+
+
+class GPTChineseTokenizer:
+    """Sentencepiece tokenizer of the Chinese GPT (CPM) checkpoints (the reference imports paddlenlp's ``GPTChineseTokenizer``,
+    language_module.py:37-44 / gpt_dataset.py:30-39).  Words are segmented first (jieba when importable, otherwise the text is
+    passed through unsegmented), spaces / newlines are carried through sentencepiece as ``\u2582`` / ``\u2583`` and restored by ``decode``."""
+
+    vocab_file_name = "sentencepiece.model"
+    _FWD = str.maketrans(" \n", "\u2582\u2583")
+
+    def __init__(self, model_file: str, max_len: int = 512, unk_token: str = "<unk>", bos_token: str = "<bod>", eos_token: str = "<eod>",
+                 eol_token: str = "\u2583"):
+        import sentencepiece as spm
+
+        if not os.path.isfile(model_file):
+            raise FileNotFoundError(model_file)
+        self.model_file, self.max_len = model_file, max_len or int(1e12)
+        self.sp = spm.SentencePieceProcessor()
+        self.sp.Load(model_file)
+        self.unk_token, self.bos_token, self.eos_token, self.eol_token = unk_token, bos_token, eos_token, eol_token
+        self.padding_side = "left"
+
+    @classmethod
+    def from_pretrained(cls, name_or_dir: str = "gpt-cpm-large-cn", **kw) -> "GPTChineseTokenizer":
+        cands = [name_or_dir, os.environ.get("PFX_GPT_VOCAB_DIR", ""), os.path.expanduser(os.path.join("~/.cache/ppfleetx", name_or_dir))]
+        for d in cands:
+            if d and os.path.isfile(d):
+                return cls(d, **kw)
+            if d and os.path.isdir(d):
+                for name in (cls.vocab_file_name, "gpt-cpm-cn-sentencepiece.model", "spiece.model"):
+                    if os.path.isfile(os.path.join(d, name)):
+                        return cls(os.path.join(d, name), **kw)
+        raise FileNotFoundError(f"sentencepiece model for {name_or_dir!r} not found locally (looked in {[c for c in cands if c]}); this machine is offline")
+
+    def _id_or_unk(self, piece: str) -> int:
+        i = self.sp.piece_to_id(piece)
+        return i
+
+    @property
+    def eos_token_id(self) -> int:
+        return self._id_or_unk(self.eos_token)
+
+    @property
+    def bos_token_id(self) -> int:
+        return self._id_or_unk(self.bos_token)
+
+    @property
+    def eol_token_id(self) -> int:
+        return self._id_or_unk(self.eol_token)
+
+    pad_token_id = eos_token_id
+
+    @property
+    def vocab_size(self) -> int:
+        return self.sp.get_piece_size()
+
+    def __len__(self) -> int:
+        return self.sp.get_piece_size()
+
+    def _segment(self, text: str) -> List[str]:
+        try:
+            import jieba
+
+            return list(jieba.cut(text, cut_all=False))
+        except ImportError:
+            return [text]
+
+    def tokenize(self, text: str) -> List[str]:
+        joined = " ".join(w.translate(self._FWD) for w in self._segment(text))
+        return self.sp.encode(joined, out_type=str)
+
+    def convert_tokens_to_ids(self, tokens):
+        if isinstance(tokens, str):
+            return self.sp.piece_to_id(tokens)
+        return [self.sp.piece_to_id(t) for t in tokens]
+
+    def convert_ids_to_tokens(self, ids, skip_special_tokens: bool = False) -> List[str]:
+        n = self.sp.get_piece_size()
+        return [self.sp.IdToPiece(int(i)) if 0 <= int(i) < n else "" for i in ids if not (skip_special_tokens and int(i) == self.eos_token_id)]
+
+    def encode(self, text: str) -> List[int]:
+        return self.convert_tokens_to_ids(self.tokenize(text))
+
+    def decode(self, ids, skip_special_tokens: bool = False) -> str:
+        n = self.sp.get_piece_size()
+        keep = [int(i) for i in ids if 0 <= int(i) < n and not (skip_special_tokens and int(i) == self.eos_token_id)]
+        text = self.sp.decode(keep)
+        return text.replace(" ", "").replace("\u2582", " ").replace("\u2583", "\n")
+
+    convert_ids_to_string = decode
+
+    def __call__(self, text, padding: bool = False, max_length: Optional[int] = None, return_attention_mask: bool = True, **unused):
+        return GPTTokenizer.__call__(self, text, padding=padding, max_length=max_length, return_attention_mask=return_attention_mask)

@@ -96,6 +96,10 @@ class ImagenModel(nn.Module):
         self.p2_gamma, self.p2_k = p2_loss_weight_gamma, p2_loss_weight_k
         self.unet_number, self.in_chans = unet_number, in_chans
         self.text_encoder = text_encoder           # frozen T5 / DeBERTa, optional (pre-computed embeddings are accepted too)
+        self.text_encoder_name = text_encoder_name
+        from ....data.tokenizers import get_text_tokenizer
+
+        self.tokenizer = get_text_tokenizer(text_encoder_name)      # None when the vocabulary is not on this (offline) machine
         if self.text_encoder is not None:
             for p in self.text_encoder.parameters():
                 p.requires_grad = False
@@ -104,6 +108,13 @@ class ImagenModel(nn.Module):
         with torch.no_grad():
             self.text_encoder.eval()
             return self.text_encoder(input_ids, attention_mask).detach()
+
+    def tokenize_captions(self, texts, max_length: int = 256):
+        """captions -> (input_ids, attention_mask) on the model's device with the text tower's own tokenizer."""
+        assert self.tokenizer is not None, f"no local vocabulary for text encoder {self.text_encoder_name!r} (set PFX_TOKENIZER_DIR)"
+        enc = self.tokenizer.batch_encode_plus(list(texts), return_tensors="pt", padding="longest", max_length=max_length, truncation=True)
+        dev = next(self.parameters()).device
+        return enc.input_ids.to(dev), enc.attention_mask.to(dev)
 
     def p_losses(self, unet, x0, times, scheduler, objective, text_embeds=None, text_mask=None, lowres_cond_img=None, lowres_aug_times=None, noise=None):
         x0 = x0 * 2 - 1
