@@ -33,6 +33,48 @@ class _BroadcastGrad(torch.autograd.Function):
         return g, None, None
 
 
+class _GradBroadcast(torch.autograd.Function):
+    """fwd: identity; bwd: every rank receives ``src``'s gradient (reference bp.py ``broadcast_grad_for_backward``)."""
+
+    @staticmethod
+    def forward(ctx, x, src, group):
+        ctx.src, ctx.group = src, group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.broadcast(g, src=ctx.group.ranks[ctx.src], group=ctx.group.process_group)
+        return g, None, None
+
+
+def broadcast_grad_for_backward(x, src: int = 0, group=None):
+    g = _grp(group)
+    if C.group_size(g) == 1 or g.process_group is None:
+        return x
+    return _GradBroadcast.apply(x, src, g)
+
+
+class _ReplicatedExit(torch.autograd.Function):
+    """fwd: identity; bwd: grad / group size.  Placed where the branch-parallel trunk hands its outputs to code every rank repeats (heads,
+    loss): each rank then back-propagates the same gradient, and the last ``broadcast`` sums them onto the producer — once is right."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n = n
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g / ctx.n, None
+
+
+def replicated_exit(x, group=None):
+    g = _grp(group)
+    n = C.group_size(g)
+    return x if n == 1 or g.process_group is None else _ReplicatedExit.apply(x, n)
+
+
 def broadcast(x, src: int = 0, group=None):
     g = _grp(group)
     if C.group_size(g) == 1 or g.process_group is None:
@@ -44,9 +86,42 @@ def all_reduce(x, group=None):
     return C.reduce_from_group(x, _grp(group))
 
 
-def sync_evoformer_results(msa_act, pair_act, group=None):
-    """``SyncEvoformerResults``: rank 0 owns the fresh MSA activation, rank 1 the fresh pair activation."""
-    return broadcast(msa_act, 0, group), broadcast(pair_act, 1, group)
+class _SyncEvoformerResults(torch.autograd.Function):
+    """One node for the block's three exchanges, so both ranks issue the backward collectives in the same order whatever order the autograd
+    engine would pick for independent nodes (the two ranks hold different graphs).
+
+    fwd: msa <- rank 0, pair <- rank 1, outer <- rank 0; returns (msa, pair + outer).
+    bwd: the consumers of the outputs are split across the ranks, so their gradients are summed; the sum goes to each tensor's producer."""
+
+    @staticmethod
+    def forward(ctx, msa, pair, outer, group):
+        ctx.group = group
+        pg, ranks = group.process_group, group.ranks
+        msa, pair, outer = msa.contiguous().clone(), pair.contiguous().clone(), outer.contiguous().clone()
+        dist.broadcast(msa, src=ranks[0], group=pg)
+        dist.broadcast(pair, src=ranks[1], group=pg)
+        dist.broadcast(outer, src=ranks[0], group=pg)
+        return msa, pair + outer
+
+    @staticmethod
+    def backward(ctx, g_msa, g_pair):
+        pg, rank = ctx.group.process_group, ctx.group.rank
+        g_msa, g_pair = g_msa.contiguous().clone(), g_pair.contiguous().clone()
+        dist.all_reduce(g_msa, group=pg)
+        dist.all_reduce(g_pair, group=pg)
+        zero_m, zero_p = torch.zeros_like(g_msa), torch.zeros_like(g_pair)
+        return (g_msa if rank == 0 else zero_m), (g_pair if rank == 1 else zero_p), (g_pair if rank == 0 else zero_p), None
+
+
+def sync_evoformer_results(msa_act, pair_act, outer=None, group=None):
+    """``SyncEvoformerResults`` (reference bp.py:84-113): rank 0 owns the fresh MSA activation and the outer-product-mean update, rank 1 the
+    fresh pair activation; every rank leaves with ``(msa, pair + outer)``."""
+    g = _grp(group)
+    if outer is None:
+        outer = torch.zeros_like(pair_act)
+    if C.group_size(g) == 1 or g.process_group is None:
+        return msa_act, pair_act + outer
+    return _SyncEvoformerResults.apply(msa_act, pair_act, outer, g)
 
 
 def grad_sync(params, group=None) -> None:

@@ -26,12 +26,13 @@ from ...distributed.protein_folding.scg import scg
 class GatedAttention(nn.Module):
     """Multi-head attention with sigmoid output gating and an optional additive bias ``[b, h, q, k]`` (per leading group)."""
 
-    def __init__(self, q_dim, kv_dim, num_head, out_dim, gating=True):
+    def __init__(self, q_dim, kv_dim, num_head, out_dim, gating=True, key_dim=None):
         super().__init__()
-        self.h, self.d = num_head, q_dim // num_head
-        self.q, self.k, self.v = nn.Linear(q_dim, q_dim, bias=False), nn.Linear(kv_dim, q_dim, bias=False), nn.Linear(kv_dim, q_dim, bias=False)
-        self.o = nn.Linear(q_dim, out_dim)
-        self.g = nn.Linear(q_dim, q_dim) if gating else None
+        key_dim = key_dim or q_dim                      # total projection width (all heads)
+        self.h, self.d = num_head, key_dim // num_head
+        self.q, self.k, self.v = nn.Linear(q_dim, key_dim, bias=False), nn.Linear(kv_dim, key_dim, bias=False), nn.Linear(kv_dim, key_dim, bias=False)
+        self.o = nn.Linear(key_dim, out_dim)
+        self.g = nn.Linear(q_dim, key_dim) if gating else None
         if self.g is not None:
             nn.init.zeros_(self.g.weight); nn.init.ones_(self.g.bias)
         nn.init.zeros_(self.o.weight); nn.init.zeros_(self.o.bias)
@@ -84,6 +85,51 @@ class MSAColumnAttention(nn.Module):
         mask = msa_mask.transpose(1, 2)
         bias = (1e9 * (mask - 1.0))[:, :, None, None, :]
         return self.attn(m, m, bias).transpose(1, 2)
+
+
+class GlobalAttention(nn.Module):
+    """Global column-wise self-attention (Jumper et al. Suppl. Alg. 19): one mean query per column, keys / values shared by all heads, so
+    the cost is linear in the number of sequences — what makes the ~1-5k-row extra-MSA stack affordable."""
+
+    def __init__(self, q_dim, kv_dim, num_head, out_dim, gating=True, key_dim=None):
+        super().__init__()
+        key_dim = key_dim or q_dim
+        self.h, self.d = num_head, key_dim // num_head
+        self.q = nn.Linear(q_dim, key_dim, bias=False)
+        self.k, self.v = nn.Linear(kv_dim, self.d, bias=False), nn.Linear(kv_dim, self.d, bias=False)
+        self.o = nn.Linear(key_dim, out_dim)
+        self.g = nn.Linear(q_dim, key_dim) if gating else None
+        if self.g is not None:
+            nn.init.zeros_(self.g.weight); nn.init.ones_(self.g.bias)
+        nn.init.zeros_(self.o.weight); nn.init.zeros_(self.o.bias)
+
+    def forward(self, q_data, m_data, q_mask):
+        # q_data / m_data [b, g, n, c]; q_mask [b, g, n, 1]
+        b, g, n, _ = q_data.shape
+        q_mask = q_mask.to(q_data.dtype)
+        q_avg = (q_data * q_mask).sum(2) / (q_mask.sum(2) + 1e-10)                              # [b, g, c]
+        q = self.q(q_avg).view(b, g, self.h, self.d) * self.d ** -0.5
+        k, v = self.k(m_data), self.v(m_data)                                                   # [b, g, n, d]
+        logits = torch.einsum("bghd,bgnd->bghn", q, k) + (1e9 * (q_mask.squeeze(-1) - 1.0))[:, :, None, :]
+        avg = torch.einsum("bghn,bgnd->bghd", torch.softmax(logits.float(), -1).to(v.dtype), v)  # [b, g, h, d]
+        if self.g is not None:
+            gate = torch.sigmoid(self.g(q_data)).view(b, g, n, self.h, self.d)
+            out = (gate * avg[:, :, None]).reshape(b, g, n, self.h * self.d)
+        else:
+            out = avg.reshape(b, g, 1, self.h * self.d).expand(b, g, n, self.h * self.d)
+        return self.o(out)
+
+
+class MSAColumnGlobalAttention(nn.Module):
+    def __init__(self, c_m, num_head=8):
+        super().__init__()
+        self.ln = nn.LayerNorm(c_m)
+        self.attn = GlobalAttention(c_m, c_m, num_head, c_m)
+
+    def forward(self, msa, msa_mask):
+        m = self.ln(msa).transpose(1, 2)                          # [b, R(/n), S, c]
+        mask = msa_mask.transpose(1, 2).unsqueeze(-1)
+        return self.attn(m, m, mask).transpose(1, 2)
 
 
 class Transition(nn.Module):
@@ -169,17 +215,26 @@ class TriangleAttention(nn.Module):
 
 
 class EvoformerIteration(nn.Module):
-    def __init__(self, c_m=256, c_z=128, msa_heads=8, pair_heads=4, dropout_msa=0.15, dropout_pair=0.25, is_extra_msa=False, outer_first=False):
+    """One Evoformer block.  ``outer_position`` places the outer-product-mean MSA -> pair update (reference evoformer.py:179-420):
+
+    * ``"origin"`` — AlphaFold2 order: MSA branch, ``pair += OPM(new msa)``, pair branch.  Sequential, so no branch parallelism.
+    * ``"end"``    — MSA branch and pair branch both start from the block's inputs, ``pair = pair_branch(pair) + OPM(new msa)``.  The two
+      branches are independent, which is what branch parallelism (bp = 2) runs on two ranks; the unsharded model computes the same function.
+    """
+
+    def __init__(self, c_m=256, c_z=128, msa_heads=8, pair_heads=4, dropout_msa=0.15, dropout_pair=0.25, is_extra_msa=False, outer_position="origin"):
         super().__init__()
+        assert outer_position in ("origin", "end"), outer_position
         self.msa_row = MSARowAttentionWithPairBias(c_m, c_z, msa_heads)
-        self.msa_col = MSAColumnAttention(c_m, msa_heads)
+        self.is_extra_msa = is_extra_msa
+        self.msa_col = MSAColumnGlobalAttention(c_m, msa_heads) if is_extra_msa else MSAColumnAttention(c_m, msa_heads)
         self.msa_transition = Transition(c_m)
         self.outer = OuterProductMean(c_m, c_z)
         self.tri_mul_out, self.tri_mul_in = TriangleMultiplication(c_z, outgoing=True), TriangleMultiplication(c_z, outgoing=False)
         self.tri_att_start, self.tri_att_end = TriangleAttention(c_z, pair_heads, True), TriangleAttention(c_z, pair_heads, False)
         self.pair_transition = Transition(c_z)
         self.dm, self.dz = dropout_msa, dropout_pair
-        self.outer_first = outer_first
+        self.outer_position = outer_position
 
     def _row_dropout(self, x, p, dim):
         if not self.training or p == 0:
@@ -206,62 +261,154 @@ class EvoformerIteration(nn.Module):
         bp_size = scg.get_bp_world_size()
         if bp_size == 1:
             msa_c, mask_c = self._msa_branch(msa, pair, msa_mask)
-            pair = pair + self.outer(msa_c, mask_c)
-            msa = dap.col_to_row(msa_c)
-            return msa, self._pair_branch(pair, pair_mask)
-        # branch parallel: the outer-product-mean output of the *previous* MSA state feeds the pair branch
-        rank = scg.get_bp_rank()
-        msa_c0, mask_c0 = dap.row_to_col(msa), dap.row_to_col(msa_mask.unsqueeze(-1)).squeeze(-1)
-        if rank == 0:
-            new_msa_c, _ = self._msa_branch(msa, pair, msa_mask)
-            new_msa, new_pair = dap.col_to_row(new_msa_c), pair
+            if self.outer_position == "origin":
+                new_pair = self._pair_branch(pair + self.outer(msa_c, mask_c), pair_mask)
+            else:
+                new_pair = self._pair_branch(pair, pair_mask) + self.outer(msa_c, mask_c)
+            return dap.col_to_row(msa_c), new_pair
+        assert bp_size == 2 and self.outer_position == "end", "branch parallelism needs bp_degree 2 and outer_position='end'"
+        if scg.get_bp_rank() == 0:
+            msa_c, mask_c = self._msa_branch(msa, pair, msa_mask)
+            new_msa, outer, new_pair = dap.col_to_row(msa_c), self.outer(msa_c, mask_c), pair
         else:
-            new_pair = self._pair_branch(pair + self.outer(msa_c0, mask_c0), pair_mask)
-            new_msa = msa
-        return bp.sync_evoformer_results(new_msa, new_pair)
+            new_msa, outer, new_pair = msa, torch.zeros_like(pair), self._pair_branch(pair, pair_mask)
+        return bp.sync_evoformer_results(new_msa, new_pair, outer)
 
 
 class EmbeddingsAndEvoformer(nn.Module):
-    """Input embeddings (target / MSA features, relative positions, optional recycling) + N Evoformer blocks + single repr."""
+    """Input embeddings (target / MSA features, relative positions, recycling, templates, extra-MSA stack) + N Evoformer blocks + single
+    representation (reference evoformer.py:532-996; Jumper et al. Suppl. Alg. 2 lines 5-18).
+
+    Optional stages switch on with their inputs: the extra-MSA stack needs ``extra_msa_blocks > 0`` and ``batch['extra_msa']``; templates need
+    ``template={'enabled': True, ...}`` and the ``template_*`` features; position recycling needs ``prev['prev_pos']`` + ``batch['aatype']``."""
 
     def __init__(self, msa_feat_dim=49, target_feat_dim=22, c_m=256, c_z=128, c_s=384, num_blocks=48, max_relative_feature=32,
-                 msa_heads=8, pair_heads=4, use_recompute=False):
+                 msa_heads=8, pair_heads=4, use_recompute=False, extra_msa_channel=64, extra_msa_blocks=0, template=None,
+                 prev_pos_bins=(15, 3.25, 20.75), outer_product_mean_position="origin"):
         super().__init__()
         self.preprocess_1d, self.preprocess_msa = nn.Linear(target_feat_dim, c_m), nn.Linear(msa_feat_dim, c_m)
         self.left_single, self.right_single = nn.Linear(target_feat_dim, c_z), nn.Linear(target_feat_dim, c_z)
         self.max_rel = max_relative_feature
         self.pair_relpos = nn.Linear(2 * max_relative_feature + 1, c_z)
-        self.prev_pos_linear = nn.Linear(15, c_z)
+        self.prev_pos_bins = tuple(prev_pos_bins)
+        self.prev_pos_linear = nn.Linear(self.prev_pos_bins[0], c_z)
         self.prev_msa_ln, self.prev_pair_ln = nn.LayerNorm(c_m), nn.LayerNorm(c_z)
-        self.blocks = nn.ModuleList([EvoformerIteration(c_m, c_z, msa_heads, pair_heads) for _ in range(num_blocks)])
+        # extra-MSA stack: 23 residue classes + has_deletion + deletion_value -> c_e; blocks use global column attention
+        self.extra_msa_activations = nn.Linear(25, extra_msa_channel) if extra_msa_blocks else None
+        pos = outer_product_mean_position
+        self.extra_msa_stack = nn.ModuleList([EvoformerIteration(extra_msa_channel, c_z, msa_heads, pair_heads, is_extra_msa=True, outer_position=pos)
+                                              for _ in range(extra_msa_blocks)])
+        t = dict(template or {})
+        self.template_enabled = bool(t.pop("enabled", False))
+        self.embed_torsion_angles = bool(t.pop("embed_torsion_angles", False)) and self.template_enabled
+        if self.template_enabled:
+            from .template import TemplateEmbedding
+
+            self.template_embedding = TemplateEmbedding(c_z=c_z, use_recompute=use_recompute, **t)
+        if self.embed_torsion_angles:
+            self.template_single_embedding, self.template_projection = nn.Linear(57, c_m), nn.Linear(c_m, c_m)
+        self.blocks = nn.ModuleList([EvoformerIteration(c_m, c_z, msa_heads, pair_heads, outer_position=pos) for _ in range(num_blocks)])
         self.single = nn.Linear(c_m, c_s)
         self.use_recompute = use_recompute
 
-    def forward(self, batch, prev=None):
-        tf, mf = batch["target_feat"], batch["msa_feat"]
-        msa = self.preprocess_1d(tf)[:, None] + self.preprocess_msa(mf)
-        pair = self.left_single(tf)[:, :, None] + self.right_single(tf)[:, None]
-        res = batch["residue_index"]
-        off = (res[:, :, None] - res[:, None, :]).clamp(-self.max_rel, self.max_rel) + self.max_rel
-        pair = pair + self.pair_relpos(F.one_hot(off, 2 * self.max_rel + 1).to(pair.dtype))
-        if prev is not None:
-            msa = torch.cat([msa[:, :1] + self.prev_msa_ln(prev["prev_msa_first_row"])[:, None], msa[:, 1:]], 1)
-            pair = pair + self.prev_pair_ln(prev["prev_pair"])
-        msa_mask = batch.get("msa_mask", torch.ones(msa.shape[:3], device=msa.device, dtype=msa.dtype))
-        seq_mask = batch.get("seq_mask", torch.ones(tf.shape[:2], device=msa.device, dtype=msa.dtype))
-        pair_mask = seq_mask[:, :, None] * seq_mask[:, None, :]
-        # enter the DAP layout: MSA sharded by sequences, pair by rows
-        msa, msa_mask = dap.scatter(msa, 1), dap.scatter(msa_mask, 1)
-        pair, pair_mask = dap.scatter(pair, 1), dap.scatter(pair_mask, 1)
-        for blk in self.blocks:
+    # -- gradient synchronisation contract (the reference flags optimizer param groups with ``dap`` / ``bp``, dap.py:400-425, bp.py:126-152)
+    def dap_parameters(self):
+        """Parameters applied to DAP-*sharded* activations: each rank holds a partial gradient, summed over the dap group.  Everything else
+        sees replicated activations under DAP and already has the full gradient on every rank."""
+        mods = [self.blocks, self.extra_msa_stack]
+        if self.template_enabled:
+            mods.append(self.template_embedding.single_template_embedding.template_pair_stack)
+        return [p for m in mods for p in m.parameters()]
+
+    def bp_parameters(self):
+        """Parameters up to the trunk's exit: under branch parallelism each rank back-propagates only its branch's share into them, summed
+        over the bp group.  The single-representation head runs after the exit on every rank and is excluded."""
+        head = {id(p) for p in self.single.parameters()}
+        return [p for p in self.parameters() if id(p) not in head]
+
+    def sync_gradients(self):
+        """Call after ``backward`` (before the data-parallel reduction / optimizer step)."""
+        for group, params in ((dap, self.dap_parameters()), (bp, self.bp_parameters())):
+            live = [p for p in params if p.requires_grad]
+            for p in live:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            group.grad_sync(live)
+
+    @staticmethod
+    def pseudo_beta(aatype, all_atom_positions, all_atom_masks=None):
+        """CB position (CA for glycine) and, given masks, its validity."""
+        from . import residue_constants as rc
+
+        is_gly = aatype == rc.restype_order["G"]
+        ca, cb = rc.atom_order["CA"], rc.atom_order["CB"]
+        pos = torch.where(is_gly.unsqueeze(-1), all_atom_positions[..., ca, :], all_atom_positions[..., cb, :])
+        if all_atom_masks is None:
+            return pos
+        return pos, torch.where(is_gly, all_atom_masks[..., ca], all_atom_masks[..., cb])
+
+    def _run_stack(self, blocks, msa, pair, msa_mask, pair_mask):
+        for blk in blocks:
             if self.use_recompute and self.training:
                 from ...parallel.recompute import recompute
 
                 msa, pair = recompute(blk, msa, pair, msa_mask, pair_mask)
             else:
                 msa, pair = blk(msa, pair, msa_mask, pair_mask)
+        return msa, pair
+
+    def forward(self, batch, prev=None):
+        from .common import dgram_from_positions
+
+        tf, mf = batch["target_feat"], batch["msa_feat"]
+        msa = self.preprocess_1d(tf)[:, None] + self.preprocess_msa(mf)
+        pair = self.left_single(tf)[:, :, None] + self.right_single(tf)[:, None]
+        msa_mask = batch.get("msa_mask", torch.ones(msa.shape[:3], device=msa.device, dtype=msa.dtype))
+        seq_mask = batch.get("seq_mask", torch.ones(tf.shape[:2], device=msa.device, dtype=msa.dtype))
+        mask_2d = seq_mask[:, :, None] * seq_mask[:, None, :]
+        if prev is not None:
+            if "prev_pos" in prev and "aatype" in batch:
+                pb = self.pseudo_beta(batch["aatype"], prev["prev_pos"])
+                pair = pair + self.prev_pos_linear(dgram_from_positions(pb.to(pair.dtype), *self.prev_pos_bins))
+            if "prev_msa_first_row" in prev:
+                msa = torch.cat([msa[:, :1] + self.prev_msa_ln(prev["prev_msa_first_row"])[:, None], msa[:, 1:]], 1)
+            if "prev_pair" in prev:
+                pair = pair + self.prev_pair_ln(prev["prev_pair"])
+        res = batch["residue_index"]
+        off = (res[:, :, None] - res[:, None, :]).clamp(-self.max_rel, self.max_rel) + self.max_rel
+        pair = pair + self.pair_relpos(F.one_hot(off, 2 * self.max_rel + 1).to(pair.dtype))
+        if self.template_enabled and "template_mask" in batch:
+            tb = {k: v for k, v in batch.items() if k.startswith("template_")}
+            pair = pair + self.template_embedding(pair, tb, mask_2d)
+        if self.extra_msa_activations is not None and "extra_msa" in batch:
+            feat = torch.cat([F.one_hot(batch["extra_msa"].long(), 23).to(pair.dtype), batch["extra_has_deletion"].unsqueeze(-1).to(pair.dtype),
+                              batch["extra_deletion_value"].unsqueeze(-1).to(pair.dtype)], -1)
+            e_msa = self.extra_msa_activations(feat)
+            e_mask = batch.get("extra_msa_mask", torch.ones(e_msa.shape[:3], device=e_msa.device, dtype=e_msa.dtype))
+            e_msa, e_mask_s = dap.scatter(e_msa, 1), dap.scatter(e_mask, 1)
+            pair_s, pm_s = dap.scatter(pair, 1), dap.scatter(mask_2d, 1)
+            _, pair_s = self._run_stack(self.extra_msa_stack, e_msa, pair_s, e_mask_s, pm_s)
+            pair = dap.gather(pair_s, 1)
+        if self.embed_torsion_angles and "template_aatype" in batch:
+            from . import all_atom
+
+            ret = all_atom.atom37_to_torsion_angles(batch["template_aatype"], batch["template_all_atom_positions"].to(msa.dtype),
+                                                    batch["template_all_atom_masks"], placeholder_for_undefined=True)
+            tfeat = torch.cat([F.one_hot(batch["template_aatype"].long(), 22).to(msa.dtype), ret["torsion_angles_sin_cos"].flatten(-2),
+                               ret["alt_torsion_angles_sin_cos"].flatten(-2), ret["torsion_angles_mask"]], -1)          # 22 + 14 + 14 + 7 = 57
+            tact = self.template_projection(F.relu(self.template_single_embedding(tfeat)))
+            msa = torch.cat([msa, tact], 1)
+            msa_mask = torch.cat([msa_mask, ret["torsion_angles_mask"][..., 2].to(msa_mask.dtype)], 1)
+        # (branch parallelism needs no gradient broadcast here: each bp rank back-propagates its branch's share into the embeddings and
+        # ``bp.grad_sync`` sums the replicated-parameter gradients)
+        # enter the DAP layout: MSA sharded by sequences, pair by rows
+        msa, msa_mask = dap.scatter(msa, 1), dap.scatter(msa_mask, 1)
+        pair, pair_mask = dap.scatter(pair, 1), dap.scatter(mask_2d, 1)
+        msa, pair = self._run_stack(self.blocks, msa, pair, msa_mask, pair_mask)
         msa, pair = dap.gather(msa, 1), dap.gather(pair, 1)
-        return {"single": self.single(msa[:, 0]), "pair": pair, "msa": msa, "msa_first_row": msa[:, 0]}
+        msa, pair = bp.replicated_exit(msa), bp.replicated_exit(pair)     # heads / loss below run on every bp rank
+        n_seq = mf.shape[1]
+        return {"single": self.single(msa[:, 0]), "pair": pair, "msa": msa[:, :n_seq], "msa_first_row": msa[:, 0]}
 
 
 DistEmbeddingsAndEvoformer = EmbeddingsAndEvoformer

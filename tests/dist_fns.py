@@ -287,3 +287,55 @@ def moe_exp_ep_matches_single(rank, world):
         for p, q in zip(e.parameters(), ref.parameters()):
             # every rank contributed the same tokens -> the owner sees `world` copies of each routed token
             assert torch.allclose(p.grad, q.grad * world, atol=1e-4), (p.grad - q.grad * world).abs().max()
+
+
+# ------------------------------------------------------------------------------------------------ protein folding: DAP / BP
+def _fold_model_and_batch(seed=0, outer="origin"):
+    from paddlefleetx_b200.models.protein_folding import EmbeddingsAndEvoformer
+
+    torch.manual_seed(seed)
+    b, S, R, T, E = 1, 4, 8, 2, 6
+    evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2,
+                                 pair_heads=2, extra_msa_channel=8, extra_msa_blocks=1, outer_product_mean_position=outer,
+                                 template=dict(enabled=True, c_t=8, num_block=1, num_head=2, attn_key_dim=8, embed_torsion_angles=True,
+                                               use_template_unit_vector=True)).double()
+    for p in evo.parameters():            # zero-initialised output projections would hide layout bugs behind zeros
+        if p.abs().sum() == 0:
+            torch.nn.init.normal_(p, std=0.1)
+    evo.eval()                            # no dropout: outputs must agree exactly across layouts
+    g = torch.Generator().manual_seed(seed + 1)
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)  # noqa: E731
+    batch = dict(target_feat=r(b, R, 6), msa_feat=r(b, S, R, 9), residue_index=torch.arange(R)[None], aatype=torch.randint(0, 20, (b, R), generator=g),
+                 msa_mask=(torch.rand(b, S, R, generator=g) > 0.1).double(), seq_mask=torch.ones(b, R, dtype=torch.float64),
+                 extra_msa=torch.randint(0, 23, (b, E, R), generator=g), extra_has_deletion=torch.rand(b, E, R, generator=g).double(),
+                 extra_deletion_value=torch.rand(b, E, R, generator=g).double(), extra_msa_mask=(torch.rand(b, E, R, generator=g) > 0.1).double(),
+                 template_mask=torch.ones(b, T, dtype=torch.float64), template_aatype=torch.randint(0, 20, (b, T, R), generator=g),
+                 template_pseudo_beta=r(b, T, R, 3) * 5, template_pseudo_beta_mask=torch.ones(b, T, R, dtype=torch.float64),
+                 template_all_atom_positions=r(b, T, R, 37, 3) * 3, template_all_atom_masks=torch.ones(b, T, R, 37, dtype=torch.float64))
+    prev = dict(prev_pos=r(b, R, 37, 3), prev_msa_first_row=r(b, R, 16), prev_pair=r(b, R, R, 8))
+    return evo, batch, prev
+
+
+def _fold_loss(out):
+    return (out["single"] ** 2).sum() + (out["pair"] ** 2).sum() + (out["msa"] ** 2).sum()
+
+
+def evoformer_parallel_matches_single(rank, world, mode):
+    """DAP (activations sharded over 2 ranks) or BP (MSA branch on rank 0, pair branch on rank 1) vs the unsharded model: same outputs,
+    same parameter gradients after the group's gradient synchronisation."""
+    from paddlefleetx_b200.distributed.protein_folding.scg import scg
+
+    evo, batch, prev = _fold_model_and_batch(outer="origin" if mode == "dap" else "end")
+    ref_out = evo(batch, prev)                      # scg not initialised yet: every collective is the identity
+    _fold_loss(ref_out).backward()
+    ref_grads = {n: p.grad.clone() for n, p in evo.named_parameters()}
+    evo.zero_grad()
+    scg.init_process_group([("dp", None), ("dap", 2 if mode == "dap" else 1), ("bp", 2 if mode == "bp" else 1)])
+    assert (scg.get_dap_world_size(), scg.get_bp_world_size()) == ((2, 1) if mode == "dap" else (1, 2))
+    out = evo(batch, prev)
+    for k in ("single", "pair", "msa"):
+        torch.testing.assert_close(out[k], ref_out[k], rtol=1e-8, atol=1e-9, msg=lambda m, k=k: f"{mode} {k}: {m}")
+    _fold_loss(out).backward()
+    evo.sync_gradients()
+    for n, p in evo.named_parameters():
+        torch.testing.assert_close(p.grad, ref_grads[n], rtol=1e-6, atol=1e-8, msg=lambda m, n=n: f"{mode} grad {n}: {m}")
