@@ -13,6 +13,7 @@ import torch
 
 from . import r3
 from . import residue_constants as rc
+from .common import no_autocast
 
 
 def get_chi_atom_indices() -> List[List[List[int]]]:
@@ -25,6 +26,7 @@ def get_chi_atom_indices() -> List[List[List[int]]]:
     return out
 
 
+@no_autocast
 def atom37_to_torsion_angles(aatype: torch.Tensor, all_atom_pos: torch.Tensor, all_atom_mask: torch.Tensor,
                              placeholder_for_undefined: bool = False) -> Dict[str, torch.Tensor]:
     """aatype ``[B, T, N]`` int, all_atom_pos ``[B, T, N, 37, 3]``, all_atom_mask ``[B, T, N, 37]`` ->

@@ -8,6 +8,19 @@ import torch
 import torch.nn as nn
 
 
+def no_autocast(fn: Callable) -> Callable:
+    """Run ``fn`` with autocast off (cuda and cpu): frames, distances and angles are computed in the precision of their inputs (fp32), not in
+    the trunk's bf16 — a batched ``rot @ vec`` would otherwise be down-cast like any other mat-mul."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        with torch.autocast("cuda", enabled=False), torch.autocast("cpu", enabled=False):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
 def init_gate_linear(linear: nn.Linear) -> None:
     """Gates start open: weight 0, bias 1 (sigmoid(1) ~ 0.73)."""
     nn.init.zeros_(linear.weight)

@@ -369,7 +369,7 @@ class EmbeddingsAndEvoformer(nn.Module):
         if prev is not None:
             if "prev_pos" in prev and "aatype" in batch:
                 pb = self.pseudo_beta(batch["aatype"], prev["prev_pos"])
-                pair = pair + self.prev_pos_linear(dgram_from_positions(pb.to(pair.dtype), *self.prev_pos_bins))
+                pair = pair + self.prev_pos_linear(dgram_from_positions(pb.float(), *self.prev_pos_bins).to(pair.dtype))
             if "prev_msa_first_row" in prev:
                 msa = torch.cat([msa[:, :1] + self.prev_msa_ln(prev["prev_msa_first_row"])[:, None], msa[:, 1:]], 1)
             if "prev_pair" in prev:
@@ -392,8 +392,9 @@ class EmbeddingsAndEvoformer(nn.Module):
         if self.embed_torsion_angles and "template_aatype" in batch:
             from . import all_atom
 
-            ret = all_atom.atom37_to_torsion_angles(batch["template_aatype"], batch["template_all_atom_positions"].to(msa.dtype),
+            ret = all_atom.atom37_to_torsion_angles(batch["template_aatype"], batch["template_all_atom_positions"].float(),
                                                     batch["template_all_atom_masks"], placeholder_for_undefined=True)
+            ret = {k: v.to(msa.dtype) for k, v in ret.items()}
             tfeat = torch.cat([F.one_hot(batch["template_aatype"].long(), 22).to(msa.dtype), ret["torsion_angles_sin_cos"].flatten(-2),
                                ret["alt_torsion_angles_sin_cos"].flatten(-2), ret["torsion_angles_mask"]], -1)          # 22 + 14 + 14 + 7 = 57
             tact = self.template_projection(F.relu(self.template_single_embedding(tfeat)))

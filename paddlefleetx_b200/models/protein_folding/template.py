@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from ...distributed.protein_folding import dap
 from . import quat_affine
 from . import residue_constants as rc
-from .common import dgram_from_positions
+from .common import dgram_from_positions, no_autocast
 from .evoformer import GatedAttention, Transition, TriangleAttention, TriangleMultiplication
 
 
@@ -63,10 +63,12 @@ class TemplatePair(nn.Module):
         return act
 
 
+@no_autocast
 def template_pair_features(batch, mask_2d, dtype, dgram_bins: int = 39, min_bin: float = 3.25, max_bin: float = 50.75,
                            use_template_unit_vector: bool = False) -> torch.Tensor:
     """-> ``[B, R, R, 88]`` for ``B`` templates given ``template_aatype [B, R]``, ``template_pseudo_beta [B, R, 3]`` (+ mask),
     ``template_all_atom_positions [B, R, 37, 3]`` (+ masks)."""
+    out_dtype, dtype = dtype, torch.float32          # geometry (frames, distances) stays in fp32 whatever the trunk's compute dtype
     pb_mask = batch["template_pseudo_beta_mask"].to(dtype)
     pb_mask_2d = pb_mask[:, :, None] * pb_mask[:, None, :]
     dgram = dgram_from_positions(batch["template_pseudo_beta"].to(dtype), dgram_bins, min_bin, max_bin)
@@ -85,7 +87,7 @@ def template_pair_features(batch, mask_2d, dtype, dgram_bins: int = 39, min_bin:
     if not use_template_unit_vector:
         unit = torch.zeros_like(unit)
     feats += [unit, bb_mask_2d.unsqueeze(-1)]
-    return torch.cat(feats, dim=-1) * bb_mask_2d.unsqueeze(-1)
+    return (torch.cat(feats, dim=-1) * bb_mask_2d.unsqueeze(-1)).to(out_dtype)
 
 
 class SingleTemplateEmbedding(nn.Module):

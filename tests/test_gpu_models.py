@@ -151,11 +151,20 @@ def test_vision_multimodal_and_text_towers_on_gpu():
         o = deb(ids, mask)
     o.float().sum().backward()
     evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2,
-                                 pair_heads=2).to(dev)
+                                 pair_heads=2, extra_msa_channel=8, extra_msa_blocks=1,
+                                 template=dict(enabled=True, c_t=8, num_block=1, num_head=2, attn_key_dim=8, embed_torsion_angles=True,
+                                               use_template_unit_vector=True)).to(dev)
+    R, T = 10, 2
+    fold = dict(target_feat=torch.randn(1, R, 6, device=dev), msa_feat=torch.randn(1, 4, R, 9, device=dev), residue_index=torch.arange(R, device=dev)[None],
+                aatype=torch.randint(0, 20, (1, R), device=dev), extra_msa=torch.randint(0, 23, (1, 6, R), device=dev),
+                extra_has_deletion=torch.rand(1, 6, R, device=dev), extra_deletion_value=torch.rand(1, 6, R, device=dev),
+                template_mask=torch.ones(1, T, device=dev), template_aatype=torch.randint(0, 20, (1, T, R), device=dev),
+                template_pseudo_beta=torch.randn(1, T, R, 3, device=dev) * 5, template_pseudo_beta_mask=torch.ones(1, T, R, device=dev),
+                template_all_atom_positions=torch.randn(1, T, R, 37, 3, device=dev) * 3, template_all_atom_masks=torch.ones(1, T, R, 37, device=dev))
     with amp():
-        o = evo(dict(target_feat=torch.randn(1, 10, 6, device=dev), msa_feat=torch.randn(1, 4, 10, 9, device=dev),
-                     residue_index=torch.arange(10, device=dev)[None]))
-    o["single"].float().sum().backward()
+        o = evo(fold, dict(prev_pos=torch.randn(1, R, 37, 3, device=dev)))
+    assert o["msa"].shape == (1, 4, R, 16) and torch.isfinite(o["pair"].float()).all()
+    (o["single"].float().sum() + o["pair"].float().sum()).backward()
     torch.cuda.synchronize()
 
 
