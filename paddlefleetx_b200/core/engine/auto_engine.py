@@ -1,11 +1,29 @@
-"""``AutoEngine`` (reference core/engine/auto_engine.py:39-209 wraps Paddle's static-graph semi-auto-parallel engine).
+"""``AutoEngine`` (reference core/engine/auto_engine.py:39-209 wraps Paddle's static-graph semi-auto-parallel engine and its
+``OptimizationTuner``).
 
-There is no tracing planner here: an "auto" config describes a process mesh (pp, dp, mp) that maps one-to-one onto the
-hybrid topology, so ``AutoEngine`` is the eager engine with the mesh validated — ``tools/auto.py`` / ``tools/auto_export.py``
-keep working with the same YAML files.  ``tune`` reports the candidate layouts ranked by an analytic cost model."""
+There is no tracing planner here: an "auto" config describes a process mesh (pp, dp, mp) that maps one-to-one onto the hybrid topology, so
+``AutoEngine`` is the eager engine with the mesh validated — ``tools/auto.py`` / ``tools/auto_export.py`` keep working with the same YAML
+files.  ``tune`` covers the two things the reference's ``Tuning`` section drives:
+
+* ``Tuning.tuning_recompute`` — a *measured* search: every recompute setting (off / ``core_attn`` / ``full_attn`` / ``full``) is built on the
+  configured mesh, steps ``[profile_start_step, profile_end_step]`` are timed (device-synchronised, max over ranks) with the peak allocator
+  footprint recorded, and the fastest candidate under the memory limit is written back into the config;
+* otherwise — the analytic ranking of (dp, mp, pp, sharding) factorisations of the world (``utils/layout_planner.py``).
+"""
 from __future__ import annotations
 
+import copy
+import gc
+import time
+from typing import Dict, Iterable, List, Optional
+
+import torch
+
+from ...utils.log import logger
 from .eager_engine import EagerEngine
+
+RECOMPUTE_CANDIDATES = ({"use_recompute": False}, {"use_recompute": True, "recompute_granularity": "core_attn"},
+                        {"use_recompute": True, "recompute_granularity": "full_attn"}, {"use_recompute": True, "recompute_granularity": "full"})
 
 
 class AutoEngine(EagerEngine):
@@ -16,10 +34,81 @@ class AutoEngine(EagerEngine):
             assert list(mesh.shape) == [d.pp_degree, d.dp_degree * d.sharding.sharding_degree, d.mp_degree], "mesh / degree mismatch"
         super().__init__(configs, module, mode=mode)
 
-    def tune(self, tune_data_loader=None):
+    # ------------------------------------------------------------------ tuning
+    def tune(self, tune_data_loader: Optional[Iterable] = None) -> List[Dict]:
+        tuning = self._configs.get("Tuning", {}) or {}
+        if tuning.get("tuning_recompute", False):
+            assert tune_data_loader is not None, "Tuning.tuning_recompute measures real steps: pass the training data loader"
+            return self._tune_recompute(tune_data_loader, int(tuning.get("profile_start_step", 1)), int(tuning.get("profile_end_step", 5)),
+                                        tuning.get("memory_limit_gb"))
         from ...utils.layout_planner import rank_layouts
 
         return rank_layouts(self._configs)
+
+    def _profile_candidate(self, overrides: Dict, batches: List, start: int, end: int) -> Dict:
+        from ...distributed.apis import env
+        from ...models import build_module
+
+        cfg = copy.deepcopy(self._configs)
+        cfg.Model.update(overrides)
+        cfg.Engine.save_load.update({"save_steps": -1, "ckpt_dir": None})
+        cuda = torch.cuda.is_available() and str(cfg.Global.get("device", "gpu")) != "cpu"
+        row = dict(overrides, status="ok")
+        try:
+            env.set_seed(cfg.Global.seed)
+            engine = EagerEngine(configs=cfg, module=build_module(cfg))
+            if cuda:
+                torch.cuda.synchronize()
+                torch.cuda.reset_peak_memory_stats()
+            t0 = None
+            for i, batch in enumerate(batches[: end + 1]):
+                if i == start:
+                    if cuda:
+                        torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                loss = engine.train_step(batch)
+            if cuda:
+                torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - t0) / (end - start + 1)], dtype=torch.float64)
+            mem = torch.tensor([torch.cuda.max_memory_allocated() / 2 ** 30 if cuda else 0.0], dtype=torch.float64)
+            if env.world_size() > 1:              # a candidate is as slow / as large as its worst rank
+                import torch.distributed as dist
+
+                dev = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
+                dt, mem = dt.to(dev), mem.to(dev)
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(mem, op=dist.ReduceOp.MAX)
+            row.update(step_s=float(dt), peak_mem_gb=float(mem), final_loss=float(loss))
+            del engine
+        except torch.cuda.OutOfMemoryError:
+            row.update(status="oom", step_s=float("inf"), peak_mem_gb=float("inf"))
+        gc.collect()
+        if cuda:
+            torch.cuda.empty_cache()
+        return row
+
+    def _tune_recompute(self, loader: Iterable, start: int, end: int, memory_limit_gb: Optional[float]) -> List[Dict]:
+        assert 0 <= start <= end, "need 0 <= profile_start_step <= profile_end_step"
+        batches = []
+        for batch in loader:
+            batches.append(batch)
+            if len(batches) > end:
+                break
+        assert len(batches) > end, f"the loader yields {len(batches)} batches, profiling needs {end + 1}"
+        if memory_limit_gb is None and torch.cuda.is_available():
+            memory_limit_gb = 0.92 * torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory / 2 ** 30
+        rows = [self._profile_candidate(dict(c), batches, start, end) for c in RECOMPUTE_CANDIDATES]
+        for r in rows:
+            r["fits"] = r["status"] == "ok" and (memory_limit_gb is None or r["peak_mem_gb"] <= memory_limit_gb)
+        rows.sort(key=lambda r: (not r["fits"], r["step_s"]))
+        best = rows[0]
+        if best["fits"]:
+            self._configs.Model.update({k: best[k] for k in ("use_recompute", "recompute_granularity") if k in best})
+            logger.info(f"[tune] selected use_recompute={best['use_recompute']} granularity={best.get('recompute_granularity')} "
+                        f"({best['step_s'] * 1e3:.1f} ms/step, peak {best['peak_mem_gb']:.1f} GB)")
+        else:
+            logger.warning("[tune] no recompute setting fits the memory limit; configuration left unchanged")
+        return rows
 
     def export_from_prog(self):
         return self.export()

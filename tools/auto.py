@@ -21,11 +21,11 @@ def main(argv=None):
     module = build_module(cfg)
     config.print_config(cfg)
     engine = AutoEngine(configs=cfg, module=module)
+    train_loader = build_dataloader(cfg.Data, "Train")
     if cfg.get("Tuning", {}).get("enable", False):
-        for row in engine.tune()[:8]:
+        for row in engine.tune(train_loader)[:8]:
             print(row)
         return engine
-    train_loader = build_dataloader(cfg.Data, "Train")
     eval_loader = build_dataloader(cfg.Data, "Eval") if cfg.Engine.eval_freq and cfg.Engine.eval_freq > 0 and "Eval" in cfg.Data else None
     if cfg.Engine.save_load.ckpt_dir is not None:
         engine.load()
