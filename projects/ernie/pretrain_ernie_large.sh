@@ -1,0 +1,5 @@
+#!/bin/bash
+# ERNIE large pre-training on one GPU
+set -e
+cd "$(dirname "$0")/../.."
+python tools/train.py -c paddlefleetx_b200/configs/nlp/ernie/pretrain_ernie_large_single_card.yaml "$@"

@@ -18,7 +18,7 @@ def main():
     p.add_argument("--model_dir", default="./output")
     p.add_argument("--mp_degree", type=int, default=1)
     p.add_argument("--seq_len", type=int, default=128)
-    p.add_argument("--iters", type=int, default=10)
+    p.add_argument("--iters", "--iter", dest="iters", type=int, default=10)
     p.add_argument("--batch_sizes", default="1,2,4,8,16")
     a = p.parse_args()
     eng = InferenceEngine(a.model_dir, a.mp_degree)

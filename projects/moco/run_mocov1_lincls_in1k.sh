@@ -1,0 +1,7 @@
+#!/bin/bash
+# Linear probe of the MoCo v1 backbone on ImageNet-1k, 8 GPUs
+set -e
+cd "$(dirname "$0")/../.."
+python -m torch.distributed.run --nnodes=${NNODES:-1} --node-rank=${NODE_RANK:-0} --nproc-per-node=8 --master-addr=${MASTER_ADDR:-127.0.0.1} --master-port=${MASTER_PORT:-29500} \
+    tools/train.py -c paddlefleetx_b200/configs/vis/moco/moco_lincls_in1k_1n8c.yaml \
+    -o Model.model.base_encoder.pretrained=./pretrained/moco/mocov1_pt_imagenet2012_resnet50 "$@"

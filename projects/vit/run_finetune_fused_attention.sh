@@ -1,0 +1,7 @@
+#!/bin/bash
+# ViT-B/16 384 fine-tuning with the fused attention path
+set -e
+cd "$(dirname "$0")/../.."
+python -m torch.distributed.run --nnodes=${NNODES:-1} --node-rank=${NODE_RANK:-0} --nproc-per-node=8 --master-addr=${MASTER_ADDR:-127.0.0.1} --master-port=${MASTER_PORT:-29500} \
+    tools/train.py -c paddlefleetx_b200/configs/vis/vit/ViT_base_patch16_384_ft_in1k_2n16c_dp_fp16o2.yaml \
+    -o Model.model.use_fused_attn=True "$@"
