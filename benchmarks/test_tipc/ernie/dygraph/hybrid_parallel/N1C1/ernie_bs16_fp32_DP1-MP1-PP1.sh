@@ -1,0 +1,7 @@
+#!/bin/bash
+# ERNIE base on N1C1: dp1 x mp1 x pp1, global batch 16, fp32
+set -e
+here="$(cd "$(dirname "$0")" && pwd)"
+export model_item=ernie fp_item=fp32 dp_degree=1 mp_degree=1 pp_degree=1 bs_item=16 micro_bs=16 run_mode=DP1-MP1-PP1 device_num=N1C1
+bash "$here/../benchmark_common/prepare.sh"
+bash "$here/../benchmark_common/run_benchmark.sh" "$@"

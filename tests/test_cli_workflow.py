@@ -143,3 +143,35 @@ def test_offline_eval_cli_perplexity_and_lambada(tmp_path):
     log = _cli("tools/eval.py", "eval_gpt_345M_single_card.yaml", TINY_GPT + [f"Offline_Eval.eval_path={lam}", "Offline_Eval.cloze_eval=True", "Offline_Eval.batch_size=2",
                                                                              "Offline_Eval.max_seq_len=32"])
     assert "total examples: 6.0000E+00" in log, log[-800:]
+
+
+def test_tipc_case_script_runs_and_reports_speed(tmp_path):
+    """A benchmarks/test_tipc case script end to end on CPU: case variables -> family harness -> tipc.py -> log + speed json."""
+    import json
+    import subprocess
+
+    case = os.path.join(ROOT, "benchmarks", "test_tipc", "gpt", "dygraph", "hybrid_parallel", "N1C1", "gpt_bs16_fp32_DP1-MP1-PP1.sh")
+    tiny = ("Global.device=cpu Model.num_layers=2 Model.hidden_size=64 Model.num_attention_heads=4 Model.vocab_size=512 Model.max_position_embeddings=32 "
+            "Data.Train.dataset.max_seq_len=32 Data.Train.dataset.vocab_size=512 Global.local_batch_size=2 Global.micro_batch_size=2")
+    env = dict(os.environ, LOG_DIR=str(tmp_path), max_iter="6", skip_steps="2", TIPC_EXTRA_OPTS=tiny, DATA_DIR="")
+    r = subprocess.run(["bash", case], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    with open(tmp_path / "gpt_bs16_fp32_DP1-MP1-PP1_N1C1_speed.json") as f:
+        out = json.load(f)
+    assert out["return_code"] == 0 and out["ips"] > 0 and out["unit"] == "tokens/s" and out["samples_used"] == 4 and out["final_loss"] > 0
+    assert os.path.isfile(out["log"])
+    # every case of the matrix resolves to a launchable command
+    import glob
+
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks", "test_tipc"))
+    cases = [c for c in glob.glob(os.path.join(ROOT, "benchmarks", "test_tipc", "*", "**", "N*C*", "*.sh"), recursive=True) if "/dygraph/" in c or "/static/" in c]
+    assert len(cases) >= 60
+    for c in cases:
+        fam_sh = os.path.join(os.path.dirname(os.path.dirname(c)), "benchmark_common", "run_benchmark.sh")
+        family = open(fam_sh).read().split("--family ")[1].split()[0]
+        exports = [ln[len("export "):].split() for ln in open(c) if ln.startswith("export ")][0]
+        e = dict(os.environ, **dict(kv.split("=", 1) for kv in exports), DATA_DIR="")
+        d = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "test_tipc", "tipc.py"), "--family", family, "--dry-run"], env=e, capture_output=True, text=True)
+        assert d.returncode == 0 and "-c paddlefleetx_b200/configs/" in d.stdout, (c, d.stderr[-500:])
+        cfg = d.stdout.split("-c ")[1].split()[0]
+        assert os.path.isfile(os.path.join(ROOT, cfg)), (c, cfg)
