@@ -284,7 +284,7 @@ class LM_Eval_Dataset(torch.utils.data.Dataset):
     """Sliding-window perplexity set: windows of ``max_seq_len`` advanced by ``overlapping_eval``; only the last
     ``overlapping_eval`` targets of every non-first window are scored (reference gpt_dataset.py:484-560)."""
 
-    def __init__(self, input_dir: str, max_seq_len: int, overlapping_eval: Optional[int] = None, tokenizer=None, eos_id: int = 50256,
+    def __init__(self, input_dir: str, max_seq_len: int, overlapping_eval: Optional[int] = None, tokenizer=None, eos_id: Optional[int] = None,
                  tokens: Optional[Sequence[int]] = None, **unused):
         if tokens is None:
             with open(input_dir, "rb") as fh:
@@ -296,7 +296,8 @@ class LM_Eval_Dataset(torch.utils.data.Dataset):
             self.num_original_tokens = len(tokens)
         self.tokens = list(tokens)
         self.seq_len = max_seq_len
-        self.pad_idx = eos_id
+        # pad id of the last (short) window: explicit > the tokenizer's end-of-text id > GPT-2's 50256
+        self.pad_idx = eos_id if eos_id is not None else getattr(tokenizer, "eos_token_id", None) or 50256
         self.overlapping_eval = overlapping_eval or max_seq_len
         self.overlapping_eval = max(1, self.overlapping_eval)
         self.num_tokenized_tokens = len(self.tokens)
@@ -326,8 +327,11 @@ class Lambada_Eval_Dataset(torch.utils.data.Dataset):
     """LAMBADA last-word cloze (strict): context tokens + the BPE pieces of ``' ' + last_word``; a sample is
     correct iff every piece is the arg-max (reference gpt_dataset.py:563-655)."""
 
-    def __init__(self, input_dir: str, max_seq_len: int, tokenizer=None, eos_id: int = 50256, samples: Optional[list] = None, **unused):
-        self.seq_len, self.pad_idx = max_seq_len, eos_id
+    def __init__(self, input_dir: str, max_seq_len: int, tokenizer=None, eos_id: Optional[int] = None, samples: Optional[list] = None, **unused):
+        if samples is None:
+            tokenizer = tokenizer or _default_eval_tokenizer(unused.get("vocab_dir"))
+        self.seq_len = max_seq_len
+        self.pad_idx = eos_id if eos_id is not None else getattr(tokenizer, "eos_token_id", None) or 50256
         self.tokens, self.labels = [], []
         if samples is not None:
             for ctx, tgt in samples:
@@ -335,7 +339,6 @@ class Lambada_Eval_Dataset(torch.utils.data.Dataset):
         else:
             import json
 
-            tokenizer = tokenizer or _default_eval_tokenizer(unused.get("vocab_dir"))
             with open(input_dir, "r", encoding="utf-8") as fh:
                 for line in fh:
                     text = json.loads(line)["text"]

@@ -42,3 +42,48 @@ def test_every_project_script_points_at_an_existing_config_and_tool():
             assert os.path.isfile(os.path.join(ROOT, cfg)), (s, cfg)
         for tool in re.findall(r"((?:tools|tasks)/\S+\.py)", body):
             assert os.path.isfile(os.path.join(ROOT, tool)), (s, tool)
+
+
+def test_offline_eval_example_reports_perplexity_and_cloze_accuracy(tmp_path):
+    import json
+
+    wiki = tmp_path / "wiki.valid.tokens"
+    wiki.write_text(" = Title = \n\n The quick brown fox jumps over the lazy dog . It was a bright cold day in April , and the clocks were striking thirteen . \n" * 6)
+    lamb = tmp_path / "lambada.jsonl"
+    lamb.write_text("".join(json.dumps({"text": t}) + "\n" for t in ["the quick brown fox jumps over the lazy dog", "it was a bright cold day in april"] * 3))
+    script = "examples/transformer/models/GPT/offline-eval/run.py"
+    cfg = "examples/transformer/models/GPT/offline-eval/configs/eval_gpt_345M_single_card.yaml"
+    base = ["Global.device=cpu", "Model.num_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.ffn_hidden_size=128", "Model.vocab_size=512",
+            "Model.max_position_embeddings=32", "Engine.mix_precision.enable=False", "Offline_Eval.max_seq_len=32", "Offline_Eval.batch_size=2",
+            "Offline_Eval.overlapping_eval=8", "Offline_Eval.logging_freq=1"]
+
+    def run(extra):
+        cmd = [sys.executable, os.path.join(ROOT, script), "-c", os.path.join(ROOT, cfg)]
+        for o in base + extra:
+            cmd += ["-o", o]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+        return p.stdout + p.stderr
+
+    out = run([f"Offline_Eval.eval_path={wiki}", "Offline_Eval.cloze_eval=False"])
+    assert "ppl:" in out and "adjusted ppl:" in out and "token ratio:" in out
+    out = run([f"Offline_Eval.eval_path={lamb}", "Offline_Eval.cloze_eval=True"])
+    assert "number correct:" in out and "avg accuracy:" in out
+
+
+def test_examples_qat_helper_wraps_and_converts():
+    sys.path.insert(0, os.path.join(ROOT, "examples", "transformer"))
+    import torch
+
+    from paddlefleetx_b200.utils.config import AttrDict
+    from utils import qat
+
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+    same, quanter = qat.compress_model(AttrDict(), model)
+    assert same is model and quanter is None
+    cfg = AttrDict(Compress=AttrDict(Quantization=AttrDict(enable=True, weight_quantize_type="channel_wise_abs_max", activation_quantize_type="moving_average_abs_max")))
+    qmodel, quanter = qat.compress_model(cfg, model)
+    assert callable(quanter) and any("Quant" in type(m).__name__ for m in qmodel.modules())
+    y = qmodel(torch.randn(3, 8))
+    y.sum().backward()
+    assert y.shape == (3, 4)
