@@ -22,6 +22,14 @@ from .gpt import model as gpt
 
 
 # ------------------------------------------------------------------------------------ config post-processing
+def is_fused_matmul_bias_supported() -> bool:
+    """The reference probes for cuBLASLt's fused GEMM epilogue (language_model/utils.py); here bias / GELU epilogues are part of the native
+    tcgen05 GEMM, so the answer is whether the native library is usable on this machine."""
+    from ...ops import functional as OF
+
+    return bool(OF.native_available())
+
+
 def process_data_configs(config) -> None:
     g, eng = config.Global, config.Engine
     eval_freq = eng.eval_freq if eng.eval_freq and eng.eval_freq > 0 else max(eng.max_steps, 1)

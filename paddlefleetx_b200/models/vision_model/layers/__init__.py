@@ -46,3 +46,25 @@ class ViTPatchEmbed(nn.Module):
         from ....ops import functional as OF
 
         return OF.linear(patches.contiguous(), self.proj.weight.reshape(self.proj.weight.shape[0], -1), self.proj.bias)
+
+
+def drop_path(x: torch.Tensor, drop_prob: float = 0.0, training: bool = False) -> torch.Tensor:
+    """Stochastic depth, functional form: drop whole samples of a residual branch and rescale the survivors."""
+    if drop_prob == 0.0 or not training:
+        return x
+    keep = 1.0 - drop_prob
+    mask = torch.bernoulli(torch.full((x.shape[0],) + (1,) * (x.dim() - 1), keep, device=x.device, dtype=x.dtype))
+    return x * mask / keep
+
+
+class Identity(nn.Module):
+    def forward(self, x):
+        return x
+
+
+def xavier_uniform_2d_(weight: torch.Tensor) -> torch.Tensor:
+    """Xavier-uniform for a conv / patch-embedding kernel viewed as a 2-D matrix ``[out, in * kh * kw]`` (the ViT reference initialiser)."""
+    w2 = weight.view(weight.shape[0], -1)
+    bound = (6.0 / (w2.shape[0] + w2.shape[1])) ** 0.5
+    with torch.no_grad():
+        return weight.uniform_(-bound, bound)

@@ -260,3 +260,14 @@ def allreduce_sequence_parallel_grads(model: nn.Module) -> None:
     params = getattr(model, "_sp_params", None)
     if params:
         C.fused_allreduce_gradients(params, model._sp_group, scale=1.0)
+
+
+# sequence-parallel collectives under the reference's names (gpt/dygraph/sequence_parallel_utils.py:30-140)
+from .comm_ops import _AllGatherSeq as AllGatherOp  # noqa: E402,F401
+from .comm_ops import _GatherSeq as GatherOp  # noqa: E402,F401
+from .comm_ops import _ReduceScatterSeq as ReduceScatterOp  # noqa: E402,F401
+from .comm_ops import _ScatterSeq as ScatterOp  # noqa: E402,F401
+from .comm_ops import all_gather_seq as all_gather  # noqa: E402,F401
+from .comm_ops import reduce_scatter_seq as reduce_scatter  # noqa: E402,F401
+from .comm_ops import scatter_seq as scatter  # noqa: E402,F401
+

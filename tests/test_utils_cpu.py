@@ -199,3 +199,52 @@ def test_launcher_spawns_ranks_logs_and_restarts(tmp_path):
     log1 = (tmp_path / "log" / "workerlog.1").read_text()
     assert "hello from 1/2 attempt 0" in log1 and "hello from 1/2 attempt 1" in log1
     assert "hello from 0/2" in p.stdout
+
+
+def test_ppfleetx_alias_resolves_relocated_reference_module_paths():
+    """Import paths of the reference layout whose contents live elsewhere here (single/hybrid/auto model files, per-gate files, layer files)."""
+    import importlib
+
+    import ppfleetx  # noqa: F401
+    import paddlefleetx_b200.models.language_model.gpt.model as gpt_model
+    import paddlefleetx_b200.parallel.tp_layers as tp
+
+    cases = {
+        "ppfleetx.models.language_model.gpt.dygraph.single_model": ["GPTModel", "GPTForPretraining", "GPTPretrainingCriterion"],
+        "ppfleetx.models.language_model.gpt.dygraph.hybrid_model": ["GPTModel", "GPTForPretraining"],
+        "ppfleetx.models.language_model.gpt.dygraph.sequence_parallel_utils": ["ColumnSequenceParallelLinear", "RowSequenceParallelLinear", "ScatterOp", "GatherOp",
+                                                                               "AllGatherOp", "ReduceScatterOp", "scatter", "all_gather", "reduce_scatter",
+                                                                               "mark_as_sequence_parallel_parameter", "register_sequence_parallel_allreduce_hooks"],
+        "ppfleetx.models.language_model.gpt.dygraph.processor": ["LogitsProcessorList", "MinLengthLogitsProcessor", "RepetitionPenaltyLogitsProcessor"],
+        "ppfleetx.models.language_model.gpt.auto.auto_module": ["GPTModuleAuto", "GPTGenerationModuleAuto"],
+        "ppfleetx.models.language_model.ernie.dygraph.single_model": ["ErnieModel", "ErnieForPretraining", "ErniePretrainingCriterion"],
+        "ppfleetx.models.language_model.ernie.layers.transformer": ["TransformerEncoder", "TransformerEncoderLayer"],
+        "ppfleetx.models.language_model.ernie.auto.auto_module": ["ErnieModuleAuto"],
+        "ppfleetx.models.language_model.t5.modeling": ["T5EncoderModel"],
+        "ppfleetx.models.language_model.debertav2.modeling": ["DebertaV2Model"],
+        "ppfleetx.models.language_model.utils": ["process_configs", "process_model_configs", "process_data_configs", "process_optim_configs", "is_fused_matmul_bias_supported"],
+        "ppfleetx.models.language_model.moe.gate.naive_gate": ["NaiveGate"], "ppfleetx.models.language_model.moe.gate.gshard_gate": ["GShardGate"],
+        "ppfleetx.models.language_model.moe.gate.switch_gate": ["SwitchGate"], "ppfleetx.models.language_model.moe.gate.base_gate": ["BaseGate"],
+        "ppfleetx.models.vision_model.layers.attention": ["ViTAttention"], "ppfleetx.models.vision_model.layers.mlp": ["ViTMLP"],
+        "ppfleetx.models.vision_model.layers.droppath": ["DropPath", "drop_path"], "ppfleetx.models.vision_model.layers.embedding": ["ViTPatchEmbed"],
+        "ppfleetx.models.vision_model.layers.identity": ["Identity"], "ppfleetx.models.vision_model.layers.initializer": ["xavier_uniform_2d_"],
+        "ppfleetx.models.vision_model.loss.cross_entropy": ["CELoss", "ViTCELoss"], "ppfleetx.models.vision_model.metrics.accuracy": ["TopkAcc"],
+        "ppfleetx.models.multimodal_model.imagen.utils": ["GaussianDiffusionContinuousTimes", "resize_image_to"],
+        "ppfleetx.data.tokenizers.t5_tokenization_utils": ["PreTrainedTokenizer", "Trie"],
+        "ppfleetx.data.data_tools.ernie.preprocess.create_pretraining_data": ["main"], "ppfleetx.data.data_tools.ernie.preprocess.words_segmentation": ["main"],
+        "ppfleetx.data.utils.batch_collate_fn": ["collate_fn", "gpt_collate_fn", "ErnieCollateData", "DataCollatorWithPadding", "imagen_collate_fn"],
+        "ppfleetx.data.transforms.utils": ["transform", "create_preprocess_operators"],
+        "ppfleetx.data.dataset.ernie.dataset_utils": ["MMapIndexedDataset", "create_masked_lm_predictions", "get_samples_mapping", "make_indexed_dataset"],
+        "ppfleetx.ops.topp_sampling": ["topp_sampling"], "ppfleetx.tools.multiprocess_tool": ["main"],
+        "ppfleetx.models.protein_folding.quat_affine": ["QuatAffine"], "ppfleetx.models.protein_folding.template": ["TemplateEmbedding"],
+    }
+    for name, symbols in cases.items():
+        mod = importlib.import_module(name)
+        for s in symbols:
+            assert hasattr(mod, s), (name, s)
+    assert importlib.import_module("ppfleetx.models.language_model.gpt.dygraph.single_model").GPTModel is gpt_model.GPTModel
+    assert importlib.import_module("ppfleetx.models.language_model.gpt.dygraph.sequence_parallel_utils").ColumnSequenceParallelLinear is tp.ColumnSequenceParallelLinear
+    import pytest
+
+    with pytest.raises(ModuleNotFoundError):
+        importlib.import_module("ppfleetx.models.language_model.gpt.dygraph.no_such_module")
