@@ -16,9 +16,6 @@ B200-first differences underneath:
 from __future__ import annotations
 
 import os
-import sys
-import time
-from typing import Optional
 
 import torch
 
@@ -464,6 +461,9 @@ class EagerEngine(BasicEngine):
         if self._sharding_stage == 3 and self._sharding_degree > 1 and hasattr(model, "get_all_parameters"):
             model.get_all_parameters()
         ckpt_io.save(self._output_dir, model, self._optimizer, step=step, epoch=epoch, scaler=self._scaler)
+        if self._configs.Engine.save_load.get("save_auto_inference", False):
+            # layout-annotated copy of the weights for serving on a different tensor-parallel degree (reference: always on, eager_engine.py:750)
+            ckpt_io.save_for_auto_inference(os.path.join(self._output_dir, "auto_infer", "auto"), model)
 
     def load(self):
         if not self._ckpt_dir:

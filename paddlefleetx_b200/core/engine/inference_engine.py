@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import os
 from collections.abc import Mapping, Sequence
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import numpy as np
 import torch

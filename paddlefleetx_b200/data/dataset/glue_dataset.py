@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import csv
 import os
-from typing import Callable, List, Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch

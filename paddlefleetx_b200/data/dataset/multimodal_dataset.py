@@ -7,7 +7,6 @@ from __future__ import annotations
 import base64
 import io
 import os
-from typing import Optional
 
 import numpy as np
 import torch

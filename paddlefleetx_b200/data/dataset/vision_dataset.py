@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import os
 import pickle
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch

@@ -2,7 +2,7 @@
 (reference ppfleetx/data/sampler/collate.py:27-317, data/utils/batch_collate_fn.py:31-211)."""
 from __future__ import annotations
 
-from typing import Callable, Dict as _Dict, List, Sequence
+from typing import Callable, Dict, List
 
 import numpy as np
 import torch

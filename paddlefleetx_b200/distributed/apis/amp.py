@@ -9,7 +9,6 @@ main-grad accumulation lives in the flat optimizer (``use_main_grad``) and in th
 from __future__ import annotations
 
 import contextlib
-from typing import Optional
 
 import torch
 import torch.distributed as dist

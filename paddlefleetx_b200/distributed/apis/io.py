@@ -96,3 +96,93 @@ def load(ckpt_path: str, model: torch.nn.Module, optimizer=None, mode: str = "tr
             raise ValueError(f"No meta checkpoint file found in {d}.")
     logger.info(f"successfully load checkpoints from {d}")
     return rec
+
+
+# ---------------------------------------------------------------------------------------------------- layout-annotated weights
+def save_for_auto_inference(path_prefix: str, model: torch.nn.Module) -> Optional[str]:
+    """Write this rank's weights with their distributed attributes: ``<prefix>_dist<rank>.pdparams`` (state dict of the local shards) and
+    ``<prefix>_dist<rank>.pdattr`` (per tensor: process mesh ``[pp, mp]``, this rank's coordinates, ``dims_mapping`` = which tensor axis is split
+    over the ``mp`` mesh axis, ``-1`` elsewhere).  The reference writes the same pair after every checkpoint so a training run on any hybrid
+    layout can be served by the auto-parallel inference path on a different one (eager_engine.py:750-752 ``save_for_auto_inference``); here
+    ``load_auto_inference`` re-assembles / re-splits the tensors for whatever layout the loading model has.  Replicas (dp / sharding rank > 0)
+    write nothing."""
+    world = env.world_size()
+    if world > 1:
+        h = env.get_hcg()
+        if h.get_data_parallel_rank() != 0 or h.get_sharding_parallel_rank() != 0:
+            return None
+        mp, pp, mp_rank, pp_rank, rank = (h.get_model_parallel_world_size(), h.get_pipe_parallel_world_size(), h.get_model_parallel_rank(),
+                                          h.get_stage_id(), env.global_rank())
+    else:
+        mp = pp = 1
+        mp_rank = pp_rank = rank = 0
+    os.makedirs(os.path.dirname(os.path.abspath(path_prefix)) or ".", exist_ok=True)
+    sharded = {n: int(getattr(p, "split_axis", 0)) for n, p in model.named_parameters() if getattr(p, "tp_sharded", False)}
+    state = _cpu(model.state_dict())
+    attrs = {}
+    for name, t in state.items():
+        if not isinstance(t, torch.Tensor):
+            continue
+        mapping = [-1] * t.dim()
+        if name in sharded and mp > 1:
+            mapping[sharded[name]] = 1                      # mesh axis 1 = mp
+        attrs[name] = {"process_shape": [pp, mp], "process_coord": [pp_rank, mp_rank], "dims_mapping": mapping}
+    torch.save(state, f"{path_prefix}_dist{rank}.pdparams")
+    torch.save({"mesh": [pp, mp], "coord": [pp_rank, mp_rank], "tensors": attrs}, f"{path_prefix}_dist{rank}.pdattr")
+    logger.info(f"save auto-inference weights to {path_prefix}_dist{rank}.pdparams")
+    return f"{path_prefix}_dist{rank}.pdparams"
+
+
+def merge_auto_inference(path_prefix: str) -> dict:
+    """All ``<prefix>_dist*.pdparams`` + ``.pdattr`` files -> one full (un-sharded) state dict: tensors split over ``mp`` are concatenated along
+    their mapped axis in mesh-coordinate order, pipeline stages are unioned."""
+    import glob
+
+    files = sorted(glob.glob(f"{path_prefix}_dist*.pdattr"))
+    if not files:
+        raise FileNotFoundError(f"no {path_prefix}_dist*.pdattr files")
+    pieces: dict = {}
+    for f in files:
+        attr = torch.load(f, map_location="cpu", weights_only=False)
+        state = torch.load(f[:-len(".pdattr")] + ".pdparams", map_location="cpu", weights_only=False)
+        for name, a in attr["tensors"].items():
+            pieces.setdefault(name, []).append((a["process_coord"][1], a["dims_mapping"], state[name]))
+    full = {}
+    for name, parts in pieces.items():
+        parts.sort(key=lambda p: p[0])
+        mapping = parts[0][1]
+        axis = mapping.index(1) if 1 in mapping else None
+        if axis is None:
+            full[name] = parts[0][2]
+        else:
+            seen = {}
+            for coord, _, t in parts:
+                seen.setdefault(coord, t)             # the same shard may appear once per pipeline replica of a tied weight
+            full[name] = torch.cat([seen[c] for c in sorted(seen)], dim=axis)
+    return full
+
+
+def load_auto_inference(path_prefix: str, model: torch.nn.Module) -> None:
+    """Load layout-annotated weights into ``model`` whatever its own tensor-parallel degree: the full tensors are rebuilt, then every parameter
+    the model marks ``tp_sharded`` takes this rank's slice along its ``split_axis``."""
+    full = merge_auto_inference(path_prefix)
+    if env.world_size() > 1:
+        h = env.get_hcg()
+        mp, mp_rank = h.get_model_parallel_world_size(), h.get_model_parallel_rank()
+    else:
+        mp, mp_rank = 1, 0
+    axes = {n: int(getattr(p, "split_axis", 0)) for n, p in model.named_parameters() if getattr(p, "tp_sharded", False)}
+    own = model.state_dict()
+    out = {}
+    for name, ref in own.items():
+        if name not in full:
+            raise KeyError(f"{name} is not found in {path_prefix}_dist*.pdparams")
+        t = full[name]
+        if name in axes and mp > 1:
+            t = t.chunk(mp, dim=axes[name])[mp_rank]
+        if tuple(t.shape) != tuple(ref.shape):
+            raise ValueError(f"{name}: stored {tuple(t.shape)} does not fit {tuple(ref.shape)} at mp={mp}")
+        out[name] = t.to(ref.dtype)
+    model.load_state_dict(out, strict=True)
+    logger.info(f"loaded auto-inference weights from {path_prefix}_dist*.pdparams (mp={mp})")
+

@@ -3,7 +3,6 @@
 ``ErnieSeqClsModule`` (sequence classification fine-tune).  ``*Auto`` names map to the same eager classes."""
 from __future__ import annotations
 
-import copy
 
 import torch
 

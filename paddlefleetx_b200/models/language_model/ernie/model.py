@@ -11,7 +11,6 @@ fused flash path with a padding mask.
 """
 from __future__ import annotations
 
-import math
 from typing import List, Optional
 
 import torch

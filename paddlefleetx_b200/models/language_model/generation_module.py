@@ -3,7 +3,6 @@ YAML block, left-pads prompts, ``generate(text)`` returns decoded strings.  Hybr
 data parallel, as in the reference (language_module.py:525-526)."""
 from __future__ import annotations
 
-import copy
 from typing import List, Union
 
 import torch

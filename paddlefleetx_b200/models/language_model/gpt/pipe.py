@@ -8,7 +8,6 @@ the last stage; ``seg_method = layer:TransformerDecoderLayer`` (uniform fallback
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch

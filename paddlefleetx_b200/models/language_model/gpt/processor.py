@@ -4,7 +4,6 @@
 ``[batch, vocab]`` logits and keep everything on the device."""
 from __future__ import annotations
 
-from typing import List
 
 import torch
 

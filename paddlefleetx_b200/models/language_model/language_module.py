@@ -9,8 +9,6 @@ log line is kept verbatim because the TIPC-style harness greps it.
 from __future__ import annotations
 
 import copy
-import math
-from typing import Optional
 
 import torch
 

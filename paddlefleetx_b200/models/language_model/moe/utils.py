@@ -8,7 +8,6 @@ An expert index of -1 means "dropped".
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist

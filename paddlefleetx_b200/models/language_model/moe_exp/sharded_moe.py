@@ -6,7 +6,7 @@ split all-to-all over the expert-parallel group, so ``ep_size > 1`` really shard
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.distributed as dist

@@ -4,7 +4,6 @@ relative embeddings with layer norm, optional convolution after the first layer,
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -5,7 +5,7 @@ classifier-free guidance, low-resolution noise augmentation for the SR stages, d
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 import torch.nn as nn

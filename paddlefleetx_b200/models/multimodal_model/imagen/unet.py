@@ -5,7 +5,6 @@ and the four presets ``Unet64_397M`` / ``BaseUnet64`` / ``SRUnet256`` / ``SRUnet
 from __future__ import annotations
 
 import math
-from typing import Optional, Sequence
 
 import torch
 import torch.nn as nn

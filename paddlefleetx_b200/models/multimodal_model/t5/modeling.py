@@ -4,7 +4,6 @@ and the ``t5_11b`` / ``t5_*`` presets.  Linear layers run through the framework 
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -12,7 +12,6 @@ block, then ``sync_evoformer_results`` exchanges the outputs.
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch

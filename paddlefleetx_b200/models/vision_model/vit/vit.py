@@ -9,7 +9,6 @@ what the reference writes (``replaced_dict``, vit.py:283-420).
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -10,7 +10,6 @@ Run ``python -m paddlefleetx_b200.ops.build`` (or ``__graft_entry__.build()``).
 from __future__ import annotations
 
 import hashlib
-import os
 import shutil
 import subprocess
 import sys

@@ -11,7 +11,6 @@ LayerNorm, ``softmax_mask_fuse_upper_triangle``, ``c_softmax_with_cross_entropy`
 """
 from __future__ import annotations
 
-import math
 import os
 from typing import Optional, Tuple
 

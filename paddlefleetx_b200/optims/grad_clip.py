@@ -12,7 +12,7 @@ buffer, no host sync: the clip coefficient stays on the device and is consumed b
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional
+from typing import Iterable, List
 
 import torch
 import torch.distributed as dist

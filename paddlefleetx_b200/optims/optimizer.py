@@ -20,7 +20,7 @@ AdamW+broadcast run as peer-memory kernels over NVLink (csrc/comm_p2p.cu) instea
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, Iterable, List, Optional
+from typing import Callable, Dict, List, Optional
 
 import torch
 import torch.distributed as dist

@@ -18,8 +18,6 @@ With ``Fused.tp_comm`` enabled on NVSwitch boxes the SP linears run the fused GE
 """
 from __future__ import annotations
 
-import math
-from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -22,7 +22,7 @@ YAML block (same as the reference)::
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn as nn

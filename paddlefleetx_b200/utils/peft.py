@@ -12,7 +12,7 @@ the papers (Hu et al. 2021; Li & Liang 2021):
 from __future__ import annotations
 
 import math
-from typing import Iterable, List, Optional
+from typing import Iterable, List
 
 import torch
 import torch.nn as nn

@@ -1,5 +1,4 @@
 """Rank functions for the multi-process gloo tests (imported by name inside the spawned children)."""
-import copy
 
 import torch
 import torch.distributed as dist
@@ -339,3 +338,56 @@ def evoformer_parallel_matches_single(rank, world, mode):
     evo.sync_gradients()
     for n, p in evo.named_parameters():
         torch.testing.assert_close(p.grad, ref_grads[n], rtol=1e-6, atol=1e-8, msg=lambda m, n=n: f"{mode} grad {n}: {m}")
+
+
+def auto_inference_weights_roundtrip(rank, world, tmpdir):
+    """mp2 training model -> ``save_for_auto_inference`` -> (a) merged full tensors equal the all-gathered shards, (b) a fresh mp2 model and
+    (c) a single-process (mp1) model load them and produce the same logits."""
+    import os
+
+    from paddlefleetx_b200.distributed.apis import env, io
+    from paddlefleetx_b200.models import build_module
+    from paddlefleetx_b200.parallel.topology import HybridCommunicateGroup
+
+    ov = ["Global.global_batch_size=None", "Global.local_batch_size=2", "Global.micro_batch_size=2", f"Distributed.mp_degree={world}"]
+    cfg = tiny_gpt_config(ov, nranks=world)
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    model = build_module(cfg).model
+    prefix = os.path.join(tmpdir, "auto_infer", "auto")
+    io.save_for_auto_inference(prefix, model)
+    dist.barrier()
+    full = io.merge_auto_inference(prefix)
+    mp_group = env.get_hcg().get_model_parallel_group().process_group
+    for name, p in model.named_parameters():
+        if getattr(p, "tp_sharded", False):
+            parts = [torch.empty_like(p.data) for _ in range(world)]
+            dist.all_gather(parts, p.data.contiguous(), group=mp_group)
+            assert torch.equal(full[name], torch.cat(parts, dim=p.split_axis)), name
+        else:
+            assert torch.equal(full[name], p.data), name
+    batch = synthetic_batches(cfg, 1, seed=3)[0]
+    model.eval()
+    with torch.no_grad():
+        ref = model(batch[0], batch[1])
+    env.set_seed(cfg.Global.seed + 7)                 # different initial weights, same layout
+    again = build_module(cfg).model.eval()
+    io.load_auto_inference(prefix, again)
+    with torch.no_grad():
+        torch.testing.assert_close(again(batch[0], batch[1]), ref)
+    # single-process layout: rebuild the model as if world == 1 and load the same files
+    hcg = env.get_hcg()
+    real_ws = env.world_size
+    env.set_hcg(HybridCommunicateGroup(world_size=1, rank=0, build_groups=False))
+    env.world_size = lambda: 1
+    try:
+        single = build_module(tiny_gpt_config(["Global.global_batch_size=None", "Global.local_batch_size=2", "Global.micro_batch_size=2"], nranks=1)).model.eval()
+        io.load_auto_inference(prefix, single)
+        with torch.no_grad():
+            logits = single(batch[0], batch[1])
+    finally:
+        env.world_size = real_ws
+        env.set_hcg(hcg)
+    # the mp model returns vocabulary-parallel logits: compare this rank's slice
+    v = ref.shape[-1]
+    torch.testing.assert_close(logits[..., rank * v:(rank + 1) * v], ref, rtol=1e-4, atol=1e-5)

@@ -65,3 +65,7 @@ def test_stage3_with_recompute_and_dp():
 
 def test_moe_exp_expert_parallel_all_to_all_matches_single():
     run_distributed("dist_fns:moe_exp_ep_matches_single", 2)
+
+
+def test_auto_inference_weights_reload_on_another_tensor_parallel_degree(tmp_path):
+    run_distributed("dist_fns:auto_inference_weights_roundtrip", 2, str(tmp_path))

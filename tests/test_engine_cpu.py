@@ -118,3 +118,20 @@ def test_optimizer_state_offload_matches_resident_state():
     assert max(abs(x - y) for x, y in zip(la, lb)) < 1e-6, (la, lb)
     sd = eb.optimizer.state_dict()
     eb.optimizer.set_state_dict(sd)
+
+
+def test_save_auto_inference_flag_writes_layout_annotated_weights(tmp_path):
+    from paddlefleetx_b200.distributed.apis import io
+
+    cfg = tiny_gpt_config([f"Engine.save_load.output_dir={tmp_path}", "Engine.save_load.save_auto_inference=True"])
+    eng = build_engine(cfg)
+    eng.train_step(synthetic_batches(cfg, 1)[0])
+    eng.save(epoch=0, step=1)
+    prefix = os.path.join(tmp_path, "auto_infer", "auto")
+    assert os.path.isfile(prefix + "_dist0.pdparams") and os.path.isfile(prefix + "_dist0.pdattr")
+    attr = torch.load(prefix + "_dist0.pdattr", weights_only=False)
+    assert attr["mesh"] == [1, 1] and all(set(a["dims_mapping"]) == {-1} for a in attr["tensors"].values())
+    other = build_engine(tiny_gpt_config(["Global.seed=77"]))._module.model
+    io.load_auto_inference(prefix, other)
+    for (n, a), (_, b) in zip(eng._module.model.state_dict().items(), other.state_dict().items()):
+        assert torch.equal(a, b), n

@@ -4,7 +4,6 @@ Flow (reference tools/train.py:44-73): parse -> config -> device -> init_dist_en
 dataloaders (Train/Eval) -> inject epochs/step_each_epoch/total_steps into Optimizer.lr -> EagerEngine ->
 optional load() -> fit().  Launch multi-GPU with torchrun (one process per GPU).
 """
-import copy
 import os
 import sys
 
