@@ -54,12 +54,16 @@ class AutoEngine(EagerEngine):
         cfg.Engine.save_load.update({"save_steps": -1, "ckpt_dir": None})
         cuda = torch.cuda.is_available() and str(cfg.Global.get("device", "gpu")) != "cpu"
         row = dict(overrides, status="ok")
+        engine = loss = None
+        if cuda:                                  # whatever is resident already (this engine's own model, allocator leftovers) is not the candidate's
+            gc.collect()
+            torch.cuda.empty_cache()
+            torch.cuda.synchronize()
+            torch.cuda.reset_peak_memory_stats()
+            resident = torch.cuda.memory_allocated()
         try:
             env.set_seed(cfg.Global.seed)
             engine = EagerEngine(configs=cfg, module=build_module(cfg))
-            if cuda:
-                torch.cuda.synchronize()
-                torch.cuda.reset_peak_memory_stats()
             t0 = None
             for i, batch in enumerate(batches[: end + 1]):
                 if i == start:
@@ -70,7 +74,7 @@ class AutoEngine(EagerEngine):
             if cuda:
                 torch.cuda.synchronize()
             dt = torch.tensor([(time.perf_counter() - t0) / (end - start + 1)], dtype=torch.float64)
-            mem = torch.tensor([torch.cuda.max_memory_allocated() / 2 ** 30 if cuda else 0.0], dtype=torch.float64)
+            mem = torch.tensor([(torch.cuda.max_memory_allocated() - resident) / 2 ** 30 if cuda else 0.0], dtype=torch.float64)
             if env.world_size() > 1:              # a candidate is as slow / as large as its worst rank
                 import torch.distributed as dist
 
@@ -79,9 +83,9 @@ class AutoEngine(EagerEngine):
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
                 dist.all_reduce(mem, op=dist.ReduceOp.MAX)
             row.update(step_s=float(dt), peak_mem_gb=float(mem), final_loss=float(loss))
-            del engine
         except torch.cuda.OutOfMemoryError:
             row.update(status="oom", step_s=float("inf"), peak_mem_gb=float("inf"))
+        engine = loss = None                      # drop the candidate (model, flat optimizer buffers, hooks) before the next one is built
         gc.collect()
         if cuda:
             torch.cuda.empty_cache()

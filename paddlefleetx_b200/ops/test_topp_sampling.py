@@ -27,8 +27,12 @@ def main(batch: int = 4, vocab: int = 50304, top_p: float = 0.75, draws: int = 2
         counts.scatter_add_(1, ids.view(batch, 1).long(), torch.ones(batch, 1, device="cuda"))
     outside = float((counts * (nucleus == 0)).sum())
     tv = float(0.5 * (counts / draws - nucleus).abs().sum(-1).max())
-    print(f"draws outside the nucleus: {outside:.0f}; max total-variation distance to the nucleus distribution: {tv:.3f}")
-    return 0 if outside == 0 and tv < 0.15 else 1
+    # yardstick: the same number of exact multinomial draws from the nucleus distribution (finite-sample noise dominates on a large support)
+    ref = torch.zeros_like(probs).scatter_add_(1, torch.multinomial(nucleus, draws, replacement=True), torch.ones(batch, draws, device="cuda"))
+    tv_ref = float(0.5 * (ref / draws - nucleus).abs().sum(-1).max())
+    print(f"draws outside the nucleus: {outside:.0f}; max total-variation distance to the nucleus distribution: {tv:.3f} "
+          f"(exact sampler with the same number of draws: {tv_ref:.3f})")
+    return 0 if outside == 0 and tv <= 1.5 * tv_ref + 0.02 else 1
 
 
 if __name__ == "__main__":
