@@ -66,7 +66,7 @@ class ClockSampler:
                                          capture_output=True, text=True, timeout=5).stdout.strip()
                     if out:
                         self.rows.append([x.strip() for x in out.split(",")])
-                except Exception:
+                except (OSError, subprocess.SubprocessError):      # nvidia-smi missing / slow: the sample is simply skipped
                     pass
                 self._stop.wait(0.2)
         self._t = threading.Thread(target=run, daemon=True)

@@ -57,13 +57,10 @@ def get_samples_mapping(indexed: MMapIndexedDataset, doc_idx: np.ndarray, prefix
     else:
         while not os.path.isfile(fname):
             time.sleep(1)
-    try:
-        import torch.distributed as dist
+    import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.barrier()
-    except Exception:  # pragma: no cover
-        pass
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
     return np.load(fname, allow_pickle=True, mmap_mode="r")
 
 

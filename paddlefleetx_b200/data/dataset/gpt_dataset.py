@@ -170,15 +170,12 @@ def build_index_files(name: str, prefix: str, documents: np.ndarray, sizes: np.n
             try:
                 np.load(paths[2], allow_pickle=True, mmap_mode="r")
                 break
-            except Exception:  # still being written
+            except (OSError, ValueError, EOFError):  # still being written
                 time.sleep(1)
-    try:
-        import torch.distributed as dist
+    import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.barrier()
-    except Exception:  # pragma: no cover
-        pass
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()          # a failing barrier must surface: continuing would leave the ranks with different views of the cache
     return tuple(np.load(p, allow_pickle=True, mmap_mode="r") for p in paths)
 
 

@@ -14,7 +14,7 @@ import numpy as np
 try:
     from PIL import Image, ImageFilter
     _HAS_PIL = True
-except Exception:  # pragma: no cover
+except ImportError:  # pragma: no cover
     _HAS_PIL = False
 
 

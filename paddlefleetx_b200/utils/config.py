@@ -163,7 +163,7 @@ def world_size_hint() -> int:
 
         if dist.is_available() and dist.is_initialized():
             return dist.get_world_size()
-    except Exception:  # pragma: no cover - torch import problems surface elsewhere
+    except ImportError:  # pragma: no cover - torch import problems surface elsewhere
         pass
     return int(os.environ.get("WORLD_SIZE", os.environ.get("PADDLE_TRAINERS_NUM", "1")))
 

@@ -40,7 +40,7 @@ def _device_list(spec):
         import torch
 
         n = torch.cuda.device_count()
-    except Exception:
+    except (ImportError, RuntimeError):
         n = 0
     return [str(i) for i in range(n)] or [None]
 
