@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
+from . import comm_ops as C
 from .recompute import recompute, recompute_hybrid
 
 
@@ -241,10 +242,18 @@ class _SeqRunner:
 class _P2P:
     """Stage-boundary communication with cached tensor metadata."""
 
-    def __init__(self, hcg):
+    def __init__(self, hcg, partial: bool = False):
         self.hcg = hcg
         self.prev, self.next = hcg.prev_rank, hcg.next_rank
         self.group = hcg.get_pipe_parallel_group().process_group
+        # ``enable_partial_send_recv`` (reference: pipeline_configs, env.py:139-148): activations / activation gradients at a stage boundary are
+        # replicated across the tensor-parallel group, so every mp rank ships only its 1/mp slice to its peer in the next stage and the
+        # receiving stage all-gathers over its own mp group — the inter-stage link (the slow one when stages sit on different nodes)
+        # carries mp x less data.  Off under sequence parallelism, where boundary tensors are already sequence shards.
+        self.mp_group = hcg.get_model_parallel_group()
+        self.mp, self.mp_rank = hcg.get_model_parallel_world_size(), hcg.get_model_parallel_rank()
+        self.partial = bool(partial) and self.mp > 1
+        self.partial_transfers = 0      # sliced sends + receives so far (observability / tests)
         self._recv_meta: Dict[str, Tuple] = {}
         self._sent_meta: Dict[str, Tuple] = {}
         self._pending: List = []        # outstanding sends (request, tensor kept alive)
@@ -282,17 +291,33 @@ class _P2P:
         if recv_next:
             shape, dtype = bwd_meta
             from_next = torch.empty(shape, dtype=dtype, device=device)
-        kinds = []
+        kinds, partial_recv = [], []
+
+        def outgoing(t):
+            t = t.contiguous()
+            if not self._is_partial(t):
+                return t
+            self.partial_transfers += 1
+            return t.view(-1).chunk(self.mp)[self.mp_rank]
+
+        def incoming(full):
+            if not self._is_partial(full):
+                return full
+            piece = full.view(-1).chunk(self.mp)[self.mp_rank]      # a view: the slice lands in place, the rest is filled by the all-gather
+            partial_recv.append((full, piece))
+            self.partial_transfers += 1
+            return piece
+
         if send_prev is not None:
-            t = send_prev.contiguous()
+            t = outgoing(send_prev)
             ops.append(dist.P2POp(dist.isend, t, self.prev, self.group)); kinds.append(t)
         if recv_prev:
-            ops.append(dist.P2POp(dist.irecv, from_prev, self.prev, self.group)); kinds.append(None)
+            ops.append(dist.P2POp(dist.irecv, incoming(from_prev), self.prev, self.group)); kinds.append(None)
         if send_next is not None:
-            t = send_next.contiguous()
+            t = outgoing(send_next)
             ops.append(dist.P2POp(dist.isend, t, self.next, self.group)); kinds.append(t)
         if recv_next:
-            ops.append(dist.P2POp(dist.irecv, from_next, self.next, self.group)); kinds.append(None)
+            ops.append(dist.P2POp(dist.irecv, incoming(from_next), self.next, self.group)); kinds.append(None)
         if ops:
             reqs = dist.batch_isend_irecv(ops)
             if len(reqs) == len(ops):
@@ -306,9 +331,14 @@ class _P2P:
             else:
                 for req in reqs:      # coalesced NCCL group: wait() only orders streams, it does not block the host
                     req.wait()
+        for full, piece in partial_recv:
+            full.view(-1).copy_(C.all_gather_dim0(piece, self.mp_group))
         if len(self._pending) > 64:
             self.flush(keep_last=32)
         return from_prev, from_next
+
+    def _is_partial(self, t: torch.Tensor) -> bool:
+        return self.partial and t.is_floating_point() and t.numel() % self.mp == 0 and t.numel() >= self.mp
 
     def flush(self, keep_last: int = 0) -> None:
         while len(self._pending) > keep_last:
@@ -331,7 +361,7 @@ class PipelineParallel(nn.Module):
         self.stage_id = hcg.get_stage_id()
         self.is_first = self.stage_id == 0
         self.is_last = self.stage_id == self.num_stages - 1
-        self._p2p = _P2P(hcg)
+        self._p2p = _P2P(hcg, partial=bool(pc.get("enable_partial_send_recv", False)))
         self._num_virtual = layers.get_num_virtual_stages()
         self.optimizer = None
         self.lr_scheduler = None

@@ -155,6 +155,9 @@ def pipeline_matches_single(rank, world, pp, mp, vpp, acc):
     eng = EagerEngine(configs=cfg, module=module)
     losses = [float(eng.train_step(b)) for b in batches]
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 3e-4, (rank, losses, ref_losses)
+    # with tensor parallelism every stage-boundary tensor travels as a 1/mp slice + an all-gather on the receiving side
+    p2p = eng._module.model._p2p if hasattr(eng._module.model, "_p2p") else eng._dist_model._p2p
+    assert p2p.partial == (mp > 1) and (p2p.partial_transfers > 0) == (mp > 1), (mp, p2p.partial, p2p.partial_transfers)
     # tied embedding stays identical on first and last stage
     if "embed" in pipe.shared_layers:
         w = pipe.shared_layers["embed"].word_embeddings.weight.detach()
