@@ -45,6 +45,7 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--p2p", type=int, default=-1, help="peer-memory ZeRO kernels: -1 auto, 0 off, 1 on")
     p.add_argument("--fused-tp", type=int, default=0, help="1: all-gather->GEMM and GEMM->reduce-scatter as single kernels (TP+SP layouts)")
+    p.add_argument("--step-overlap", type=int, default=0, help="1: AdamW update issued per bucket on the side stream underneath the next forward pass")
     p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the result invalid)")
     return p.parse_args()
 
@@ -141,6 +142,8 @@ def build_config(args, world: int):
     ]
     if args.layers:
         ov.append(f"Model.num_layers={args.layers}")
+    if args.step_overlap:
+        ov.append("Optimizer.step_overlap=True")
     if args.fused_tp:
         ov.append("Fused.tp_comm=True")
     cfg_path = os.path.join(ROOT, "paddlefleetx_b200", "configs", "nlp", "gpt", spec["cfg"])
@@ -261,7 +264,7 @@ def main():
             "config": {"model": args.model if not args.layers else f"{args.model}-DEBUG-{args.layers}layers(INVALID)",
                        "global_batch": global_batch, "seq_len": seq, "parallelism": par, "local_batch": lay["local"],
                        "micro_batch": lay["micro"], "recompute": lay["recompute"], "dropout": cfg.Model.hidden_dropout_prob,
-                       "optimizer": "FusedAdamW fp32 master + clip", "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
+                       "optimizer": "FusedAdamW fp32 master + clip" + (" (update overlapped with the next forward)" if args.step_overlap else ""), "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "final_loss": final_loss,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         }

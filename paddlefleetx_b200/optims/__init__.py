@@ -63,6 +63,7 @@ def build_optimizer(config, model: torch.nn.Module, lr_scheduler=None, hcg=None,
         extra.update(sharding_stage=sh.get("sharding_stage", 1), reduce_overlap=sh.get("reduce_overlap", False),
                      broadcast_overlap=sh.get("broadcast_overlap", False), use_p2p=sh.get("use_p2p", False),
                      bucket_mb=sh.get("bucket_mb", 512), offload=bool(sh.get("sharding_offload", False)) or bool(cfg.pop("offload", False)))
+    extra["step_overlap"] = bool(cfg.pop("step_overlap", False))
     if amp_config is not None:
         extra["use_main_grad"] = bool(amp_config.get("use_main_grad", False))
     if hasattr(model, "optimizer_named_parameters"):            # ZeRO-3 wrapper: optimise the shards

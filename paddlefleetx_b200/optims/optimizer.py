@@ -49,7 +49,7 @@ class FusedAdamW:
                  named_parameters=None, apply_decay_param_fun: Optional[Callable] = None, hcg=None, sharding_stage: int = 1,
                  use_main_grad: bool = False, bucket_mb: int = 512, reduce_overlap: bool = False, broadcast_overlap: bool = False,
                  use_p2p: bool = False, lazy_init: bool = False, params_are_shards: bool = False, direct_grad: Optional[bool] = None,
-                 offload: bool = False, **unused):
+                 offload: bool = False, step_overlap: bool = False, **unused):
         self._learning_rate = learning_rate
         self.beta1, self.beta2, self.eps, self.weight_decay = float(beta1), float(beta2), float(epsilon), float(weight_decay)
         self.grad_clip = grad_clip
@@ -81,9 +81,14 @@ class FusedAdamW:
             self.sh_world, self.sh_rank = 1, 0
         self.offload = bool(offload)
         self.use_p2p = bool(use_p2p) and self.sh_world > 1 and named[0][1].is_cuda and not self.offload
+        # ``step_overlap``: the AdamW update of step t is issued bucket by bucket on the side stream in FORWARD order and each module's
+        # forward pre-hook waits only for its own buckets, so all but the first bucket's update (bandwidth-bound, ~16 B/parameter streamed)
+        # runs underneath the compute-bound GEMMs of the next forward pass instead of in front of it.  Needs direct gradient writes (no
+        # memset of the gradient buffer between step and backward) and the device-resident native update.
+        self.step_overlap = bool(step_overlap) and named[0][1].is_cuda and not self.offload and not self.use_p2p
 
         # ---- bucket assignment (reverse registration order: last layers finish backward first)
-        bucket_bytes = bucket_mb * 1024 * 1024 if self.replicas > 1 else (1 << 62)
+        bucket_bytes = bucket_mb * 1024 * 1024 if (self.replicas > 1 or self.step_overlap) else (1 << 62)
         bucket_of: Dict[int, int] = {}
         cur, cur_bytes = 0, 0
         for n, p in reversed(named):
@@ -334,6 +339,28 @@ class FusedAdamW:
         sq = self._reduce_norm(sq, moe_sq)
 
         # ---- clip coefficient / found-inf on device, fused update
+        overlapped = native_update and self.step_overlap and self.direct_grad and self._fwd_hooks_installed and self._comm_stream is not None
+        if overlapped:
+            lib.clip_coef_(sq, inv_scale, clip_norm, self._gscale, self._found_inf, self._gnorm)
+            OF._count()
+            # The side stream starts once the clip coefficient exists; buckets go out in forward order (small no-decay bucket, first
+            # layers, ..., last layers), each followed — under ZeRO — by its parameter all-gather and an event.  The compute stream is
+            # ordered after bucket k only when a module that owns parameters of bucket k runs (install_forward_hooks), so by the end of
+            # the forward pass it has waited for every bucket and the backward pass may overwrite the gradients.
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                for g in sorted(self.groups, key=lambda g: (0 if g.key[0] < 0 else 1, -g.key[0])):
+                    lo, hi = g.meta["lo"], g.meta["hi"]
+                    lp = g.param_buf[lo:hi] if g.meta["has_master"] else None
+                    lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
+                                    self.weight_decay if g.key[1] else 0.0, self._step_count, self._gscale, self._found_inf)
+                    OF._count()
+                    if self.sh_world > 1:
+                        self._all_gather_params(g)
+                    ev = torch.cuda.Event()
+                    ev.record(self._comm_stream)
+                    self._ag_events[id(g)] = ev
+            return
         if native_update:
             lib.clip_coef_(sq, inv_scale, clip_norm, self._gscale, self._found_inf, self._gnorm)
             OF._count()
@@ -398,8 +425,10 @@ class FusedAdamW:
 
     # ------------------------------------------------------------------ overlapped parameter all-gather: consumer side
     def install_forward_hooks(self, model: torch.nn.Module) -> None:
-        """Make every module wait (on the compute stream) for the all-gather of the buckets holding its own parameters."""
-        if not (self.broadcast_overlap and self.sh_world > 1 and self._comm_stream is not None) or self._fwd_hooks_installed:
+        """Make every module wait (on the compute stream) for the side-stream work — parameter all-gather and, with ``step_overlap``, the
+        AdamW update — of the buckets holding its own parameters."""
+        wanted = (self.broadcast_overlap and self.sh_world > 1) or self.step_overlap
+        if not (wanted and self._comm_stream is not None) or self._fwd_hooks_installed:
             return
         group_of = {id(p): g for g in self.groups for p in g.params}
 
@@ -412,9 +441,15 @@ class FusedAdamW:
                             torch.cuda.current_stream().wait_event(ev)
             return pre_hook
 
+        # A module waits for the buckets of the parameters it owns AND of those its direct children own: fused call sites read a child's
+        # tensors without calling the child (``OF.fused_ffn(x, self.linear1.weight, ...)``, ``OF.layer_norm(x, self.norm1.weight, ...)``), so the
+        # child's own pre-hook would never fire.  Contract: a forward() may touch parameters at most one level below itself directly.
         for mod in model.modules():
             gids = []
-            for p in mod.parameters(recurse=False):
+            owned = list(mod.parameters(recurse=False))
+            for child in mod.children():
+                owned.extend(child.parameters(recurse=False))
+            for p in owned:
                 g = group_of.get(id(p))
                 if g is not None and id(g) not in gids:
                     gids.append(id(g))
@@ -423,8 +458,8 @@ class FusedAdamW:
         self._fwd_hooks_installed = True
 
     def finish_param_sync(self) -> None:
-        """Block the compute stream until every in-flight parameter all-gather has landed (checkpointing, evaluation of
-        tied / externally-read weights)."""
+        """Block the compute stream until every in-flight side-stream update / parameter all-gather has landed (checkpointing,
+        evaluation of tied / externally-read weights, reading ``found_inf`` / parameters from the host)."""
         if self._ag_events:
             for ev in self._ag_events.values():
                 torch.cuda.current_stream().wait_event(ev)

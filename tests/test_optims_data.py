@@ -136,3 +136,54 @@ def test_mapping_helpers_shapes_and_determinism():
     di, si = np.zeros(1000, np.uint8), np.zeros(1000, np.int64)
     h.build_blending_indices(di, si, w, 3, 1000, False)
     assert abs((di == 0).mean() - 0.7) < 0.01 and si[di == 1].max() == (di == 1).sum() - 1
+
+
+def test_forward_hooks_cover_parameters_read_through_a_child(monkeypatch):
+    """Side-stream work (ZeRO all-gather / overlapped AdamW) is awaited per bucket by module pre-hooks.  Fused call sites read a child's
+    tensors without calling the child, so the parent must wait for its children's buckets too."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    from paddlefleetx_b200.optims import FusedAdamW
+
+    class Fused(nn.Module):                      # reads lin's parameters directly, never calls lin()
+        def __init__(self):
+            super().__init__()
+            self.lin = nn.Linear(8, 8)
+
+        def forward(self, x):
+            return F.linear(x, self.lin.weight, self.lin.bias)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = nn.Linear(8, 8)
+            self.blocks = nn.ModuleList([Fused(), Fused()])
+
+        def forward(self, x):
+            x = F.linear(x, self.emb.weight, self.emb.bias)
+            for b in self.blocks:
+                x = b(x)
+            return x
+
+    net = Net()
+    opt = FusedAdamW(1e-3, named_parameters=list(net.named_parameters()), step_overlap=True)
+    assert opt.step_overlap is False                       # CPU tensors: the flag is inert ...
+    opt.step_overlap, opt._comm_stream = True, object()    # ... force the hook installation path
+    waited = []
+
+    class _Stream:
+        def wait_event(self, ev):
+            waited.append(ev)
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    opt.install_forward_hooks(net)
+    assert opt._fwd_hooks_installed
+    opt._ag_events = {id(g): f"ev{i}" for i, g in enumerate(opt.groups)}
+    expected = set(opt._ag_events.values())
+    net(torch.randn(2, 8))
+    assert set(waited) == expected and not opt._ag_events   # every bucket was awaited although lin.forward never ran
+    waited.clear()
+    net(torch.randn(2, 8))
+    assert waited == []                                     # nothing in flight: hooks are free
