@@ -139,6 +139,15 @@ class EagerEngine(BasicEngine):
 
             self._module.model, self._quant_mode = compress_model(self._module.model, configs.Compress, self._device)
 
+        # parameter-efficient fine-tuning (PEFT: {method: lora | prefix, ...}): adapters go in before the optimizer is built, so only they
+        # (and PEFT.train_modules) get optimizer state
+        self._peft = None
+        if configs.get("PEFT") and configs.PEFT.get("method"):
+            from ...utils.peft import apply_peft
+
+            self._peft = apply_peft(self._module.model, configs.PEFT)
+            logger.info("PEFT {method}: {trainable:,} trainable of {total:,} parameters".format(**self._peft))
+
         if self._device.type == "cuda":
             self._module.to(self._device)
 
@@ -460,7 +469,11 @@ class EagerEngine(BasicEngine):
         model = self._module.model
         if self._sharding_stage == 3 and self._sharding_degree > 1 and hasattr(model, "get_all_parameters"):
             model.get_all_parameters()
-        ckpt_io.save(self._output_dir, model, self._optimizer, step=step, epoch=epoch, scaler=self._scaler)
+        d = ckpt_io.save(self._output_dir, model, self._optimizer, step=step, epoch=epoch, scaler=self._scaler)
+        if self._peft is not None and d is not None:
+            from ...utils.peft import adapter_state_dict
+
+            torch.save({k: v.detach().cpu() for k, v in adapter_state_dict(model).items()}, os.path.join(d, "adapter.pdparams"))
         if self._configs.Engine.save_load.get("save_auto_inference", False):
             # layout-annotated copy of the weights for serving on a different tensor-parallel degree (reference: always on, eager_engine.py:750)
             ckpt_io.save_for_auto_inference(os.path.join(self._output_dir, "auto_infer", "auto"), model)
@@ -479,6 +492,10 @@ class EagerEngine(BasicEngine):
         from ...utils.export import export_inference_model
 
         self._module.model.eval()
+        if self._peft is not None and self._peft["method"] == "lora" and self._configs.PEFT.get("merge_on_export", True):
+            from ...utils.peft import merge_lora
+
+            merge_lora(self._module.model)          # W += (alpha / r) B A: the exported model has the plain architecture
         save_dir = os.path.join(self._output_dir, f"rank_{self._dp_rank}")
         export_inference_model(self._module.model, self._module.input_spec(), save_dir, "model", configs=self._configs,
                                quant=self._quant_mode)

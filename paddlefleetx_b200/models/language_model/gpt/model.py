@@ -48,6 +48,31 @@ class LayerNorm(nn.Module):
         return OF.layer_norm(x, self.weight, self.bias, self.eps)
 
 
+class RMSNorm(nn.Module):
+    """``Model.normalization: rmsnorm`` — x / rms(x) * weight, no mean subtraction, no bias (Zhang & Sennrich 2019); runs the fused
+    sm_100a norm kernel (``OF.rms_norm``).  Not in the reference (SURVEY §2.6 "demanded by the north-star")."""
+
+    def __init__(self, hidden: int, eps: float = 1e-6, sequence_parallel: bool = False, dtype=None, device=None):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden, dtype=dtype, device=device))
+        self.bias = None
+        self.eps = eps
+        if sequence_parallel:
+            mark_as_sequence_parallel_parameter(self.weight)
+
+    def forward(self, x):
+        return OF.rms_norm(x, self.weight, self.eps)
+
+
+def make_norm(kind: Optional[str], hidden: int, sequence_parallel: bool = False, dtype=None, device=None) -> nn.Module:
+    kind = (kind or "layernorm").lower()
+    if kind in ("layernorm", "layer_norm", "ln"):
+        return LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+    if kind in ("rmsnorm", "rms_norm", "rms"):
+        return RMSNorm(hidden, 1e-6, sequence_parallel, dtype, device)
+    raise ValueError(f"Model.normalization must be layernorm or rmsnorm, got {kind!r}")
+
+
 class KVCache:
     """Pre-allocated static KV cache: in-place writes, no per-step concat/re-allocation (the reference grows
     its cache with ``concat`` every token, hybrid_model.py:198-214)."""
@@ -176,17 +201,17 @@ class TransformerDecoderLayer(nn.Module):
     def __init__(self, hidden: int, num_heads: int, ffn_hidden: int, hidden_dropout: float = 0.1, attn_dropout: float = 0.1,
                  num_layers: int = 1, sequence_parallel: bool = False, mp_group=None, init_std: float = 0.02,
                  recompute_attn: bool = False, recompute_core: bool = False, moe_layer: Optional[nn.Module] = None,
-                 fused_tp_comm: bool = False, dtype=None, device=None, **attn_kwargs):
+                 fused_tp_comm: bool = False, normalization: Optional[str] = None, dtype=None, device=None, **attn_kwargs):
         super().__init__()
         out_std = init_std / math.sqrt(2.0 * num_layers)
         self.sequence_parallel = sequence_parallel
         self.hidden_dropout = hidden_dropout
         self.recompute_attn = recompute_attn
-        self.norm1 = LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.norm1 = make_norm(normalization, hidden, sequence_parallel, dtype, device)
         self.self_attn = MultiHeadAttention(hidden, num_heads, attn_dropout, sequence_parallel=sequence_parallel, mp_group=mp_group,
                                             init_std=init_std, out_init_std=out_std, recompute_core=recompute_core,
                                             fused_tp_comm=fused_tp_comm, dtype=dtype, device=device, **attn_kwargs)
-        self.norm2 = LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.norm2 = make_norm(normalization, hidden, sequence_parallel, dtype, device)
         self.moe_mlp = moe_layer
         if moe_layer is None:
             Col = ColumnSequenceParallelLinear if sequence_parallel else ColumnParallelLinear
@@ -205,6 +230,7 @@ class TransformerDecoderLayer(nn.Module):
     def _ffn(self, h):
         l1, l2 = self.linear1, self.linear2
         if (getattr(l1, "world", 1) == 1 and not self.self_attn.sequence_parallel and getattr(l1, "int8", None) is None and l1.weight is not None
+                and not getattr(l1, "is_adapter", False) and not getattr(l2, "is_adapter", False)
                 and l1.bias is not None and getattr(l2, "skip_bias_add", False) and not _TP_OPTIONS["fp8_tp_gemm"]):
             # single tensor-parallel rank: both GEMMs in one autograd node with GELU / GELU' inside their epilogues
             return OF.fused_ffn(h, l1.weight, l1.bias, l2.weight), l2.bias
@@ -216,11 +242,12 @@ class TransformerDecoderLayer(nn.Module):
         forced = getattr(self, "_force_decode_fast", False)          # tests: run the fused-step composition through the CPU expressions
         hw = forced or (x.is_cuda and x.shape[0] <= OF.gemv_max_rows() and a.head_dim in (64, 128) and x.dtype in (torch.bfloat16, torch.float16)
                         and OF.native_available())
-        return (hw and cache is not None and cache.static_index is not None and x.shape[1] == 1
+        return (hw and isinstance(self.norm1, LayerNorm) and cache is not None and cache.static_index is not None and x.shape[1] == 1
                 and not self.training and not torch.is_grad_enabled() and self.moe_mlp is None and a.world == 1 and not a.sequence_parallel
                 and a.fuse_attn_qkv and not a.use_rope and a.use_flash_attn
                 and attn_mask is not None and attn_mask.dtype == x.dtype and attn_mask.numel() == x.shape[0] * cache.k.shape[1]
-                and getattr(a.qkv_proj, "int8", None) is None and a.qkv_proj.weight is not None)
+                and getattr(a.qkv_proj, "int8", None) is None and a.qkv_proj.weight is not None
+                and not any(getattr(m, "is_adapter", False) for m in (a.qkv_proj, a.out_proj, self.linear1, self.linear2)))
 
     def _decode_fast(self, x, attn_mask, cache):
         """One decode token through the layer in five launches: LN1+QKV GEMV, cache-append + attention, out-proj GEMV + bias + residual,
@@ -254,10 +281,11 @@ class TransformerDecoderLayer(nn.Module):
 
 class TransformerDecoder(nn.Module):
     def __init__(self, layers: List[nn.Module], hidden: int, use_recompute: bool = False, recompute_granularity: str = "full",
-                 no_recompute_layers: Optional[List[int]] = None, sequence_parallel: bool = False, dtype=None, device=None):
+                 no_recompute_layers: Optional[List[int]] = None, sequence_parallel: bool = False, dtype=None, device=None,
+                 normalization: Optional[str] = None):
         super().__init__()
         self.layers = nn.ModuleList(layers)
-        self.norm = LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.norm = make_norm(normalization, hidden, sequence_parallel, dtype, device)
         self.use_recompute = use_recompute
         self.recompute_granularity = recompute_granularity
         self.no_recompute_layers = set(no_recompute_layers or [])
@@ -307,7 +335,7 @@ class GPTModel(nn.Module):
                  fused_linear: bool = False, fuse_attn_qkv: bool = True, scale_qk_by_layer_num: bool = True,
                  sequence_parallel: bool = False, use_flash_attn: bool = True, fused_softmax_with_triangular: bool = True,
                  mp_group=None, moe_configs: Optional[dict] = None, fused_tp_comm: bool = False, use_rope: bool = False,
-                 dtype=None, device=None, **unused):
+                 normalization: Optional[str] = None, dtype=None, device=None, **unused):
         super().__init__()
         ffn_hidden_size = ffn_hidden_size or 4 * hidden_size
         recompute_granularity = recompute_granularity or "full"
@@ -332,8 +360,9 @@ class GPTModel(nn.Module):
                 recompute_core=use_recompute and recompute_granularity == "core_attn", moe_layer=moe, fused_tp_comm=fused_tp_comm,
                 dtype=dtype, device=device, fuse_attn_qkv=fuse_attn_qkv,
                 scale_qk_coeff=float(num_layers) if scale_qk_by_layer_num else 1.0, use_flash_attn=use_flash_attn,
-                fused_softmax_with_triangular=fused_softmax_with_triangular, use_rope=use_rope))
-        self.decoder = TransformerDecoder(layers, hidden_size, use_recompute, recompute_granularity, no_recompute_layers, sp, dtype, device)
+                fused_softmax_with_triangular=fused_softmax_with_triangular, use_rope=use_rope, normalization=normalization))
+        self.decoder = TransformerDecoder(layers, hidden_size, use_recompute, recompute_granularity, no_recompute_layers, sp, dtype, device,
+                                          normalization=normalization)
 
     def new_caches(self, batch: int, max_len: int) -> List[KVCache]:
         p = self.decoder.norm.weight

@@ -31,9 +31,9 @@ class EmbeddingPipe(gpt.GPTEmbeddings):
 
 
 class LayerNormPipe(nn.Module):
-    def __init__(self, hidden: int, sequence_parallel: bool, mp_group=None, dtype=None, device=None):
+    def __init__(self, hidden: int, sequence_parallel: bool, mp_group=None, dtype=None, device=None, normalization=None):
         super().__init__()
-        self.norm = gpt.LayerNorm(hidden, 1e-5, sequence_parallel, dtype, device)
+        self.norm = gpt.make_norm(normalization, hidden, sequence_parallel, dtype, device)
         self.sequence_parallel = sequence_parallel
         self.group = mp_group
 
@@ -59,7 +59,8 @@ class GPTForPretrainingPipe(PipelineLayer):
                  use_recompute: bool = False, recompute_granularity: Optional[str] = "full", no_recompute_layers=None,
                  fuse_attn_qkv: bool = True, scale_qk_by_layer_num: bool = True, sequence_parallel: bool = False,
                  use_flash_attn: bool = True, fused_softmax_with_triangular: bool = True, virtual_pp_degree: int = 1,
-                 pp_recompute_interval: int = 1, fused_tp_comm: bool = False, use_rope: bool = False, dtype=None, device=None, **unused):
+                 pp_recompute_interval: int = 1, fused_tp_comm: bool = False, use_rope: bool = False, normalization=None, dtype=None, device=None,
+                 **unused):
         ffn_hidden_size = ffn_hidden_size or 4 * hidden_size
         recompute_granularity = recompute_granularity or "full"
         sp = sequence_parallel and C.group_size(mp_group) > 1
@@ -74,8 +75,9 @@ class GPTForPretrainingPipe(PipelineLayer):
                 recompute_attn=use_recompute and recompute_granularity == "full_attn",
                 recompute_core=use_recompute and recompute_granularity == "core_attn", fused_tp_comm=fused_tp_comm, dtype=dtype,
                 device=device, fuse_attn_qkv=fuse_attn_qkv, scale_qk_coeff=float(num_layers) if scale_qk_by_layer_num else 1.0,
-                use_flash_attn=use_flash_attn, fused_softmax_with_triangular=fused_softmax_with_triangular, use_rope=use_rope))
-        descs.append(LayerDesc(LayerNormPipe, hidden_size, sp, mp_group, dtype, device))
+                use_flash_attn=use_flash_attn, fused_softmax_with_triangular=fused_softmax_with_triangular, use_rope=use_rope,
+                normalization=normalization))
+        descs.append(LayerDesc(LayerNormPipe, hidden_size, sp, mp_group, dtype, device, normalization))
         descs.append(SharedLayerDesc("embed", EmbeddingPipe, forward_func=_logits_helper, shared_weight_attr="embedding_weight", **embed_args))
         interval = pp_recompute_interval if (use_recompute and recompute_granularity == "full") else 0
         super().__init__(layers=descs, loss_fn=GPTPretrainingCriterionPipe(mp_group), hcg=hcg, seg_method="layer:TransformerDecoderLayer",

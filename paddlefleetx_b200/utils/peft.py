@@ -35,6 +35,7 @@ class LoRALinear(nn.Module):
         self.lora_B.tp_sharded = bool(getattr(w, "tp_sharded", False)) and getattr(w, "split_axis", 0) == 0
         self.lora_A.tp_sharded = bool(getattr(w, "tp_sharded", False)) and getattr(w, "split_axis", 0) == 1
         self.merged = False
+        self.is_adapter = True          # fused call sites that read ``.weight`` directly must not bypass the low-rank branch
         for p in layer.parameters():
             p.requires_grad = False
 
@@ -141,3 +142,75 @@ def _patch_attention(attn, enc: PrefixEncoder, index: int) -> None:
         return o.transpose(1, 2)
 
     attn._core = core
+
+
+# ---------------------------------------------------------------------------------------------------- config-driven entry
+def _core_gpt(model: nn.Module) -> nn.Module:
+    """The module that owns ``decoder.layers`` (GPTModel), wherever the task wrapper keeps it."""
+    for m in model.modules():
+        dec = getattr(m, "decoder", None)
+        if dec is not None and hasattr(dec, "layers"):
+            return m
+    raise ValueError("prefix tuning needs a GPT-style model (a module with ``decoder.layers``)")
+
+
+def apply_peft(model: nn.Module, cfg) -> dict:
+    """``PEFT`` section of a recipe -> adapters on ``model``; base parameters are frozen, so an optimizer built afterwards sees only the
+    adapter parameters.
+
+        PEFT: {method: lora, r: 8, alpha: 16, dropout: 0.05, target_modules: [qkv_proj, out_proj, linear1, linear2], pretrained: ./ckpt/345M}
+        PEFT: {method: prefix, num_virtual_tokens: 16, hidden: 512, reparam: True, pretrained: ./ckpt/345M}
+
+    ``pretrained`` (a ``model.pdparams`` file or its directory) is loaded into the base model first; ``train_modules`` lists name fragments of
+    base parameters that stay trainable next to the adapters (e.g. a freshly initialised classification head)."""
+    import os
+
+    method = str(cfg.get("method", "lora")).lower()
+    pretrained = cfg.get("pretrained")
+    if pretrained:
+        path = pretrained if os.path.isfile(pretrained) else os.path.join(pretrained, "model.pdparams")
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        own = model.state_dict()
+        missing = [k for k in own if k not in state]
+        model.load_state_dict({k: v.to(own[k].dtype) for k, v in state.items() if k in own and own[k].shape == v.shape}, strict=False)
+        if missing:
+            from .log import logger
+
+            logger.warning(f"PEFT.pretrained: {len(missing)} parameters not in {path} keep their initial values (e.g. {missing[:3]})")
+    def names(value, default=()):
+        """a YAML list, or the ``-o key=[a,b]`` / ``a,b`` spellings of one on the command line"""
+        if value is None:
+            return tuple(default)
+        if isinstance(value, str):
+            return tuple(v.strip().strip("'\"") for v in value.strip("[]() ").split(",") if v.strip())
+        return tuple(value)
+
+    if method == "lora":
+        adapters = apply_lora(model, r=int(cfg.get("r", 8)), alpha=float(cfg.get("alpha", 16)), dropout=float(cfg.get("dropout", 0.0)),
+                              target_modules=names(cfg.get("target_modules"), ("qkv_proj", "q_proj", "k_proj", "v_proj", "out_proj")))
+        if not adapters:
+            raise ValueError("PEFT.method=lora matched no layer: check PEFT.target_modules (tensor-parallel layers with world > 1 are not wrapped)")
+        info = {"method": "lora", "adapters": len(adapters)}
+    elif method in ("prefix", "prefix_tuning"):
+        for p in model.parameters():
+            p.requires_grad = False
+        # the encoder registers itself on the core model (``<core>.prefix_encoder``): saved with it, seen by the optimizer
+        apply_prefix_tuning(_core_gpt(model), num_virtual_tokens=int(cfg.get("num_virtual_tokens", 16)), hidden=int(cfg.get("hidden", 512)),
+                            reparam=bool(cfg.get("reparam", True)))
+        info = {"method": "prefix", "virtual_tokens": int(cfg.get("num_virtual_tokens", 16))}
+    else:
+        raise ValueError(f"unknown PEFT.method {method!r}; expected lora | prefix")
+    for frag in names(cfg.get("train_modules")):
+        for n, p in model.named_parameters():
+            if frag in n:
+                p.requires_grad = True
+    info["trainable"] = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    info["total"] = sum(p.numel() for p in model.parameters())
+    return info
+
+
+def adapter_state_dict(model: nn.Module) -> dict:
+    """Only what fine-tuning changed: every parameter that is trainable (LoRA factors, prefix encoder, ``train_modules``)."""
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    return {k: v for k, v in model.state_dict().items() if k in trainable}
+

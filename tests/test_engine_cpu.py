@@ -135,3 +135,53 @@ def test_save_auto_inference_flag_writes_layout_annotated_weights(tmp_path):
     io.load_auto_inference(prefix, other)
     for (n, a), (_, b) in zip(eng._module.model.state_dict().items(), other.state_dict().items()):
         assert torch.equal(a, b), n
+
+
+def _peft_engine(tmp_path, peft_opts, extra=()):
+    base = build_engine(tiny_gpt_config([f"Engine.save_load.output_dir={tmp_path}/base"]))
+    base.train_step(synthetic_batches(base._configs, 1)[0])
+    base.save(epoch=0, step=1)
+    ckpt = os.path.join(tmp_path, "base", "epoch_0_step_1")
+    cfg = tiny_gpt_config([f"Engine.save_load.output_dir={tmp_path}/ft", f"PEFT.pretrained={ckpt}", "Optimizer.weight_decay=0.0"] + list(peft_opts) + list(extra))
+    return base, build_engine(cfg), cfg
+
+
+def test_peft_lora_recipe_trains_only_adapters_and_exports_merged(tmp_path):
+    base, eng, cfg = _peft_engine(tmp_path, ["PEFT.method=lora", "PEFT.r=4", "PEFT.alpha=8", "PEFT.target_modules=[qkv_proj,out_proj,linear1,linear2]"])
+    model = eng._module.model
+    assert eng._peft["method"] == "lora" and eng._peft["adapters"] == 4 * cfg.Model.num_layers and 0 < eng._peft["trainable"] < 0.2 * eng._peft["total"]
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert trainable and all("lora_" in n for n in trainable)
+    assert {id(p) for p in eng._optimizer.parameters()} == {id(p) for p in model.parameters() if p.requires_grad}
+    # the base weights came from PEFT.pretrained
+    ref = base._module.model.state_dict()
+    w = dict(model.named_parameters())["gpt.decoder.layers.0.linear1.layer.weight"]
+    assert torch.equal(w, ref["gpt.decoder.layers.0.linear1.weight"])
+    frozen_before = w.detach().clone()
+    batches = synthetic_batches(cfg, 8, seed=4)
+    losses = [float(eng.train_step(b)) for b in batches[:1] * 8]       # same batch: the adapters must be able to fit it
+    assert losses[-1] < losses[0] - 1e-3, losses
+    assert torch.equal(w, frozen_before)                                # base stays frozen (and the fused-FFN path did not bypass the adapter)
+    assert any(float(p.abs().sum()) > 0 for n, p in model.named_parameters() if "lora_B" in n)
+    eng.save(epoch=0, step=8)
+    adapter = torch.load(os.path.join(tmp_path, "ft", "epoch_0_step_8", "adapter.pdparams"), weights_only=False)
+    assert adapter and all("lora_" in k for k in adapter) and len(adapter) == len(trainable)
+    # export folds the adapters into the weights: plain architecture, same function
+    model.eval()
+    with torch.no_grad():
+        want = model(batches[0][0], batches[0][1])
+    eng.export()
+    assert not any("lora_" in n for n, _ in eng._module.model.named_parameters())
+    with torch.no_grad():
+        got = eng._module.model(batches[0][0], batches[0][1])
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_peft_prefix_recipe_trains_only_the_prefix_encoder(tmp_path):
+    _, eng, cfg = _peft_engine(tmp_path, ["PEFT.method=prefix", "PEFT.num_virtual_tokens=3", "PEFT.hidden=16"], ["Model.use_flash_attn=False"])
+    model = eng._module.model
+    trainable = {n for n, p in model.named_parameters() if p.requires_grad}
+    assert trainable and all("prefix_encoder" in n for n in trainable) and eng._peft["method"] == "prefix"
+    b = synthetic_batches(cfg, 1, seed=5)[0]
+    losses = [float(eng.train_step(b)) for _ in range(8)]
+    assert losses[-1] < losses[0] - 1e-3, losses

@@ -285,3 +285,54 @@ def test_moe_exp_gating_respects_capacity_and_layer_trains():
     assert y.shape == x.shape and counts.sum() == 24 and x.grad is not None
     assert all(p.grad is not None for p in moe.fleetx_moe.experts.parameters()) and moe.gate.wg.weight.grad is not None
     assert all(getattr(p, "is_expert", False) for p in moe.fleetx_moe.experts.parameters())
+
+
+def test_gpt_rmsnorm_and_rope_options_train_and_generate():
+    """``Model.normalization: rmsnorm`` + ``Model.use_rope`` (not in the reference; north-star additions): no LayerNorm biases, no learned position
+    table, the model still trains, and the norm really is RMS normalisation."""
+    from helpers import build_engine, synthetic_batches, tiny_gpt_config
+    from paddlefleetx_b200.models.language_model.gpt.model import RMSNorm
+
+    cfg = tiny_gpt_config(["Model.normalization=rmsnorm", "Model.use_rope=True"])
+    eng = build_engine(cfg)
+    model = eng._module.model
+    names = [n for n, _ in model.named_parameters()]
+    assert not any(n.endswith("norm.bias") or n.endswith("norm1.bias") or n.endswith("norm2.bias") for n in names)
+    assert not any("position_embeddings" in n for n in names)
+    norms = [m for m in model.modules() if isinstance(m, RMSNorm)]
+    assert len(norms) == 2 * cfg.Model.num_layers + 1
+    x = torch.randn(3, 5, cfg.Model.hidden_size)
+    want = x / x.pow(2).mean(-1, keepdim=True).add(norms[0].eps).sqrt() * norms[0].weight
+    torch.testing.assert_close(norms[0](x), want, rtol=1e-5, atol=1e-6)
+    b = synthetic_batches(cfg, 1, seed=9)[0]
+    losses = [float(eng.train_step(b)) for _ in range(6)]
+    assert losses[-1] < losses[0] - 1e-2, losses
+    with pytest.raises(ValueError, match="normalization"):
+        build_engine(tiny_gpt_config(["Model.normalization=batchnorm"]))
+
+
+@pytest.mark.parametrize("recipe,marker", [("finetune_gpt_345M_single_card_lora.yaml", "lora_"), ("finetune_gpt_345M_single_card_prefix.yaml", "prefix_encoder")])
+def test_glue_finetune_with_peft_recipes(tmp_path, recipe, marker):
+    """The shipped LoRA / prefix recipes through the GLUE fine-tuning module: only adapters + the ``score`` head train."""
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.data import build_dataloader
+
+    _write_glue(str(tmp_path))
+    cfg = C.get_config(os.path.join(CFG, "nlp/gpt", recipe),
+                       TINY_MODEL + [f"Data.Train.dataset.root={tmp_path}", f"Data.Eval.dataset.root={tmp_path}", "Data.Train.sampler.batch_size=8",
+                                     "Data.Eval.sampler.batch_size=8", "Data.Train.loader.num_workers=0", "Data.Eval.loader.num_workers=0",
+                                     "Global.local_batch_size=8", "Global.micro_batch_size=8", "Engine.num_train_epochs=1", "Model.vocab_size=512",
+                                     "Model.pad_token_id=256", "PEFT.r=2", "PEFT.num_virtual_tokens=2", "PEFT.hidden=8",
+                                     f"Engine.save_load.output_dir={tmp_path}/out"], nranks=1)
+    module = _module(cfg)
+    tl, el = build_dataloader(cfg.Data, "Train"), build_dataloader(cfg.Data, "Eval")
+    cfg.Optimizer.lr.update(epochs=1, step_each_epoch=len(tl))
+    eng = EagerEngine(configs=cfg, module=module)
+    trainable = [n for n, p in module.model.named_parameters() if p.requires_grad]
+    assert trainable and all(marker in n or n.startswith("score") for n in trainable) and any(n.startswith("score") for n in trainable), trainable
+    frozen = {n: p.detach().clone() for n, p in module.model.named_parameters() if not p.requires_grad}
+    eng.fit(epoch=1, train_data_loader=tl, valid_data_loader=el)
+    for n, p in module.model.named_parameters():
+        if n in frozen:
+            assert torch.equal(p, frozen[n]), n
+    assert 0.0 <= module.best_metric <= 1.0
