@@ -497,8 +497,23 @@ class EagerEngine(BasicEngine):
 
             merge_lora(self._module.model)          # W += (alpha / r) B A: the exported model has the plain architecture
         save_dir = os.path.join(self._output_dir, f"rank_{self._dp_rank}")
+        sq = (self._configs.get("Compress") or {}).get("SmoothQuant") or {}
+        smooth = None
+        if sq.get("enable", False):
+            # post-training Shift-SmoothQuant (W8A8): calibrate per-channel activation ranges, migrate them into the weights, quantise
+            from ...utils import smoothquant as SQ
+
+            model = self._module.model
+            core = next((m for m in model.modules() if hasattr(getattr(m, "decoder", None), "layers")), model)
+            dev = next(model.parameters()).device
+            batches = SQ.calibration_batches(self._configs, int(sq.get("calib_batches", 8)), int(sq.get("calib_batch_size", 4)), sq.get("calib_seq_len"))
+            # hooks go on the exported model's own module names; the forward runs the transformer trunk, where all the linears live
+            stats = SQ.calibrate(model, batches, forward_fn=lambda _m, b: core(b[0].to(dev), b[1].to(dev)))
+            SQ.smooth_and_quantize(model, stats, alpha=float(sq.get("alpha", 0.5)), shift=bool(sq.get("shift", True)))
+            smooth = {"alpha": float(sq.get("alpha", 0.5)), "shift": bool(sq.get("shift", True)), "layers": model.smooth_quant_layers}
+            logger.info(f"Shift-SmoothQuant: {len(model.smooth_quant_layers)} linear layers quantised to W8A8 from {len(batches)} calibration batches")
         export_inference_model(self._module.model, self._module.input_spec(), save_dir, "model", configs=self._configs,
-                               quant=self._quant_mode)
+                               quant=self._quant_mode, smooth_quant=smooth)
         logger.info(f"export inference model saved in {save_dir}")
 
     def inference(self, data):

@@ -78,6 +78,10 @@ class InferenceEngine:
 
             quant_model(model, {})
             convert_to_int8(model)
+        if recipe.get("smooth_quant"):
+            from ...utils.smoothquant import install_empty
+
+            install_empty(model, recipe["smooth_quant"]["layers"], dtype=next(model.parameters()).dtype)
         state = torch.load(params, map_location="cpu", weights_only=False)
         own = model.state_dict()
         model.load_state_dict({k: v.to(own[k].dtype) if k in own and hasattr(v, "to") else v for k, v in state.items() if k in own}, strict=False)

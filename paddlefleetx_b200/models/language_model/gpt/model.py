@@ -230,7 +230,7 @@ class TransformerDecoderLayer(nn.Module):
     def _ffn(self, h):
         l1, l2 = self.linear1, self.linear2
         if (getattr(l1, "world", 1) == 1 and not self.self_attn.sequence_parallel and getattr(l1, "int8", None) is None and l1.weight is not None
-                and not getattr(l1, "is_adapter", False) and not getattr(l2, "is_adapter", False)
+                and not getattr(l1, "needs_forward", False) and not getattr(l2, "needs_forward", False)
                 and l1.bias is not None and getattr(l2, "skip_bias_add", False) and not _TP_OPTIONS["fp8_tp_gemm"]):
             # single tensor-parallel rank: both GEMMs in one autograd node with GELU / GELU' inside their epilogues
             return OF.fused_ffn(h, l1.weight, l1.bias, l2.weight), l2.bias
@@ -247,7 +247,7 @@ class TransformerDecoderLayer(nn.Module):
                 and a.fuse_attn_qkv and not a.use_rope and a.use_flash_attn
                 and attn_mask is not None and attn_mask.dtype == x.dtype and attn_mask.numel() == x.shape[0] * cache.k.shape[1]
                 and getattr(a.qkv_proj, "int8", None) is None and a.qkv_proj.weight is not None
-                and not any(getattr(m, "is_adapter", False) for m in (a.qkv_proj, a.out_proj, self.linear1, self.linear2)))
+                and not any(getattr(m, "needs_forward", False) for m in (a.qkv_proj, a.out_proj, self.linear1, self.linear2)))
 
     def _decode_fast(self, x, attn_mask, cache):
         """One decode token through the layer in five launches: LN1+QKV GEMV, cache-append + attention, out-proj GEMV + bias + residual,

@@ -28,9 +28,12 @@ def _plain(obj):
     return str(obj)
 
 
-def export_inference_model(model: torch.nn.Module, input_spec, save_dir: str, save_prefix: str = "model", configs=None, quant: bool = False) -> str:
+def export_inference_model(model: torch.nn.Module, input_spec, save_dir: str, save_prefix: str = "model", configs=None, quant: bool = False,
+                           smooth_quant: Optional[dict] = None) -> str:
     os.makedirs(save_dir, exist_ok=True)
     recipe = {"format": FORMAT, "input_spec": _plain(input_spec), "quant": bool(quant)}
+    if smooth_quant:
+        recipe["smooth_quant"] = _plain(smooth_quant)      # alpha / shift / the rewritten layers: InferenceEngine rebuilds the same structure
     if configs is not None:
         for sec in ("Model", "Generation", "Distributed", "Global", "Inference", "Data", "Offline_Eval"):
             if sec in configs:

@@ -35,7 +35,7 @@ class LoRALinear(nn.Module):
         self.lora_B.tp_sharded = bool(getattr(w, "tp_sharded", False)) and getattr(w, "split_axis", 0) == 0
         self.lora_A.tp_sharded = bool(getattr(w, "tp_sharded", False)) and getattr(w, "split_axis", 0) == 1
         self.merged = False
-        self.is_adapter = True          # fused call sites that read ``.weight`` directly must not bypass the low-rank branch
+        self.needs_forward = True       # fused call sites that read ``.weight`` directly must not bypass the low-rank branch
         for p in layer.parameters():
             p.requires_grad = False
 

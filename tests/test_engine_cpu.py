@@ -185,3 +185,37 @@ def test_peft_prefix_recipe_trains_only_the_prefix_encoder(tmp_path):
     b = synthetic_batches(cfg, 1, seed=5)[0]
     losses = [float(eng.train_step(b)) for _ in range(8)]
     assert losses[-1] < losses[0] - 1e-3, losses
+
+
+def test_export_with_shift_smoothquant_serves_int8_linears(tmp_path):
+    """``Compress.SmoothQuant`` at export: calibrate -> smooth -> W8A8; the InferenceEngine rebuilds the quantised structure from the recipe and
+    reproduces the full-precision logits within int8 error."""
+    import numpy as np
+
+    from paddlefleetx_b200.core.engine.inference_engine import InferenceEngine
+
+    cfg = tiny_gpt_config([f"Engine.save_load.output_dir={tmp_path}", "Compress.SmoothQuant.enable=True", "Compress.SmoothQuant.calib_batches=3",
+                           "Compress.SmoothQuant.calib_batch_size=2", "Compress.SmoothQuant.alpha=0.5"])
+    sq = cfg.pop("Compress")                          # train-time engine construction must not see a Compress section without pruning / QAT
+    eng = build_engine(cfg)
+    for b in synthetic_batches(cfg, 3, seed=2):
+        eng.train_step(b)
+    model = eng._module.model.eval()
+    tokens = torch.randint(0, cfg.Model.vocab_size, (2, 32))
+    pos = torch.arange(32).unsqueeze(0).expand(2, 32).contiguous()
+    with torch.no_grad():
+        ref = model(tokens, pos).float()
+    eng._configs["Compress"] = sq
+    eng.export()
+    layers = model.smooth_quant_layers
+    assert len(layers) == 4 * cfg.Model.num_layers and all(l["kind"] == "tp" for l in layers)
+    assert all(getattr(m, "int8", None) is not None and m.weight is None for n, m in model.named_modules() if n.endswith(("qkv_proj", "linear2")))
+    served = InferenceEngine(os.path.join(tmp_path), 1, device="cpu")
+    assert served.recipe["smooth_quant"]["alpha"] == 0.5 and len(served.recipe["smooth_quant"]["layers"]) == len(layers)
+    state = torch.load(os.path.join(tmp_path, "rank_0", "model.pdiparams"), weights_only=False)
+    assert any(k.endswith("int8.inner.weight_q") and v.dtype == torch.int8 for k, v in state.items())
+    out = served.predict([tokens.numpy(), pos.numpy()])["output_0"]
+    err = np.abs(out - ref.numpy()).max() / np.abs(ref.numpy()).max()
+    assert err < 0.08, err
+    top_match = (out.argmax(-1) == ref.numpy().argmax(-1)).mean()
+    assert top_match > 0.8, top_match
