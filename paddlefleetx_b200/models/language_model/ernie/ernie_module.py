@@ -14,7 +14,8 @@ from . import model as E
 
 _KEYS = ("vocab_size", "hidden_size", "num_hidden_layers", "num_layers", "num_attention_heads", "ffn_hidden_size", "intermediate_size",
          "hidden_act", "hidden_dropout_prob", "attention_probs_dropout_prob", "max_position_embeddings", "type_vocab_size",
-         "task_type_vocab_size", "task_id", "use_task_id", "initializer_range", "pad_token_id", "use_recompute", "use_flash_attn")
+         "task_type_vocab_size", "task_id", "use_task_id", "initializer_range", "pad_token_id", "use_recompute", "use_flash_attn",
+         "sequence_parallel")
 
 
 def get_model_size(l, h, v, s) -> float:
@@ -78,8 +79,13 @@ class ErnieModule(BasicModule):
             from .pipe import ErnieForPretrainingPipe
 
             return ErnieForPretrainingPipe(hcg=hcg, mp_group=mp_group, binary_head=self.binary_head, dtype=dtype, device=device, **kw)
-        ernie = E.ErnieModel(mp_group=mp_group, dtype=dtype, device=device, **kw)
-        return E.ErnieForPretraining(ernie, kw["vocab_size"], kw.get("hidden_act", "gelu"), self.binary_head)
+        ernie = E.ErnieModel(mp_group=mp_group, dtype=dtype, device=device, fused_tp_comm=bool(cfg.get("Fused", {}).get("tp_comm", False)), **kw)
+        model = E.ErnieForPretraining(ernie, kw["vocab_size"], kw.get("hidden_act", "gelu"), self.binary_head)
+        if ernie.sequence_parallel:
+            from ....parallel.tp_layers import register_sequence_parallel_allreduce_hooks
+
+            register_sequence_parallel_allreduce_hooks(model, cfg.Engine.accumulate_steps, d.get("fuse_sequence_parallel_allreduce", False), mp_group)
+        return model
 
     def get_loss_fn(self):
         d = self.configs.Distributed

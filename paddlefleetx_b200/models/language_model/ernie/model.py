@@ -22,7 +22,8 @@ from ....ops import functional as OF
 from ....parallel import comm_ops as C
 from ....parallel.recompute import recompute
 from ....parallel.rng import get_rng_state_tracker
-from ....parallel.tp_layers import (ColumnParallelLinear, ParallelCrossEntropy, RowParallelLinear, VocabParallelEmbedding, parallel_matmul)
+from ....parallel.tp_layers import (ColumnParallelLinear, ColumnSequenceParallelLinear, ParallelCrossEntropy, RowParallelLinear,
+                                    RowSequenceParallelLinear, VocabParallelEmbedding, _tp_linear, parallel_matmul)
 from ..gpt.model import LayerNorm
 
 _ACT = {"gelu": lambda x: F.gelu(x, approximate="none"), "relu": F.relu, "tanh": torch.tanh}
@@ -62,21 +63,36 @@ class ErnieEmbeddings(nn.Module):
 class ErnieSelfAttention(nn.Module):
     """Separate q/k/v column-parallel projections like the reference hybrid model (no fused QKV), row-parallel output."""
 
-    def __init__(self, hidden, heads, attn_dropout, mp_group=None, init_std=0.02, dtype=None, device=None, use_flash_attn=True):
+    def __init__(self, hidden, heads, attn_dropout, mp_group=None, init_std=0.02, dtype=None, device=None, use_flash_attn=True,
+                 sequence_parallel=False, fused_tp_comm=False):
         super().__init__()
         self.heads, self.head_dim = heads, hidden // heads
         self.local_heads = heads // C.group_size(mp_group)
+        self.group, self.sequence_parallel = mp_group, sequence_parallel
         kw = dict(mp_group=mp_group, init_std=init_std, dtype=dtype, device=device)
+        # the three projections stay separate modules (checkpoint keys of the reference); under sequence parallelism they share ONE
+        # all-gather of the sequence shards (see forward) instead of gathering three times
         self.q_proj = ColumnParallelLinear(hidden, hidden, gather_output=False, **kw)
         self.k_proj = ColumnParallelLinear(hidden, hidden, gather_output=False, **kw)
         self.v_proj = ColumnParallelLinear(hidden, hidden, gather_output=False, **kw)
-        self.out_proj = RowParallelLinear(hidden, hidden, input_is_parallel=True, **kw)
+        if sequence_parallel:
+            self.out_proj = RowSequenceParallelLinear(hidden, hidden, input_is_parallel=True, fused_comm=fused_tp_comm, **kw)
+        else:
+            self.out_proj = RowParallelLinear(hidden, hidden, input_is_parallel=True, **kw)
         self.attn_dropout = attn_dropout
         self.use_flash_attn = use_flash_attn
 
     def forward(self, x, attn_mask=None):
-        b, s, _ = x.shape
-        q, k, v = (p(x).view(b, s, self.local_heads, self.head_dim) for p in (self.q_proj, self.k_proj, self.v_proj))
+        if self.sequence_parallel:
+            # x: [s/n, b, h] -> one all-gather (backward: reduce-scatter) -> [s, b, h]; the column-parallel GEMMs then run on the gathered
+            # tensor directly (no identity/all-reduce pair: the gather's backward already sums the partial input gradients)
+            xg = C.all_gather_seq(x, self.group)
+            s, b, _ = xg.shape
+            q, k, v = (_tp_linear(xg, p.weight, p.bias, p).view(s, b, self.local_heads, self.head_dim).transpose(0, 1)
+                       for p in (self.q_proj, self.k_proj, self.v_proj))
+        else:
+            b, s, _ = x.shape
+            q, k, v = (p(x).view(b, s, self.local_heads, self.head_dim) for p in (self.q_proj, self.k_proj, self.v_proj))
         p = self.attn_dropout if self.training else 0.0
         scale = self.head_dim ** -0.5
         if self.use_flash_attn:
@@ -88,21 +104,31 @@ class ErnieSelfAttention(nn.Module):
                 o = ATT.attention(q, k, v, causal=False, dropout_p=0.0, scale=scale, attn_mask=m)
         else:
             o = ATT.core_attention(q, k, v, scale, p, self.training, attn_mask=attn_mask, causal=False)
-        return self.out_proj(o.reshape(b, s, self.local_heads * self.head_dim))
+        o = o.reshape(b, s, self.local_heads * self.head_dim)
+        if self.sequence_parallel:
+            o = o.transpose(0, 1).contiguous()               # [s, b, h/n] -> GEMM -> reduce-scatter along s -> [s/n, b, h]
+        return self.out_proj(o)
 
 
 class TransformerEncoderLayer(nn.Module):
     def __init__(self, hidden, heads, ffn, dropout=0.1, activation="gelu", attn_dropout=None, act_dropout=None, normalize_before=False,
-                 mp_group=None, init_std=0.02, dtype=None, device=None, use_flash_attn=True):
+                 mp_group=None, init_std=0.02, dtype=None, device=None, use_flash_attn=True, sequence_parallel=False, fused_tp_comm=False):
         super().__init__()
         self.normalize_before = normalize_before
+        sp = sequence_parallel
         self.self_attn = ErnieSelfAttention(hidden, heads, dropout if attn_dropout is None else attn_dropout, mp_group, init_std, dtype, device,
-                                            use_flash_attn)
+                                            use_flash_attn, sp, fused_tp_comm)
         kw = dict(mp_group=mp_group, init_std=init_std, dtype=dtype, device=device)
-        self.linear1 = ColumnParallelLinear(hidden, ffn, gather_output=False, **kw)
-        self.linear2 = RowParallelLinear(ffn, hidden, input_is_parallel=True, **kw)
-        self.norm1 = LayerNorm(hidden, 1e-12, False, dtype, device)
-        self.norm2 = LayerNorm(hidden, 1e-12, False, dtype, device)
+        if sp:          # all-gather -> GEMM and GEMM -> reduce-scatter pairs (single fused kernels with Fused.tp_comm)
+            self.linear1 = ColumnSequenceParallelLinear(hidden, ffn, gather_output=False, fused_comm=fused_tp_comm, **kw)
+            self.linear2 = RowSequenceParallelLinear(ffn, hidden, input_is_parallel=True, fused_comm=fused_tp_comm, **kw)
+        else:
+            self.linear1 = ColumnParallelLinear(hidden, ffn, gather_output=False, **kw)
+            self.linear2 = RowParallelLinear(ffn, hidden, input_is_parallel=True, **kw)
+        self.norm1 = LayerNorm(hidden, 1e-12, sp, dtype, device)
+        self.norm2 = LayerNorm(hidden, 1e-12, sp, dtype, device)
+        # hidden dropout: the same mask on every TP rank for replicated activations, per-rank masks on sequence shards
+        self.rng_name = "local_seed" if sp else "global_seed"
         self.dropout_p = dropout
         self.act_dropout_p = dropout if act_dropout is None else act_dropout
         self.activation = activation
@@ -111,15 +137,15 @@ class TransformerEncoderLayer(nn.Module):
         res = x
         if self.normalize_before:
             x = self.norm1(x)
-        x = res + OF.dropout(self.self_attn(x, attn_mask), self.dropout_p, self.training, "global_seed")
+        x = res + OF.dropout(self.self_attn(x, attn_mask), self.dropout_p, self.training, self.rng_name)
         if not self.normalize_before:
             x = self.norm1(x)
         res = x
         if self.normalize_before:
             x = self.norm2(x)
         h = _ACT[self.activation](self.linear1(x))
-        h = OF.dropout(h, self.act_dropout_p, self.training, "global_seed")
-        x = res + OF.dropout(self.linear2(h), self.dropout_p, self.training, "global_seed")
+        h = OF.dropout(h, self.act_dropout_p, self.training, "local_seed" if self.rng_name == "local_seed" else "global_seed")
+        x = res + OF.dropout(self.linear2(h), self.dropout_p, self.training, self.rng_name)
         if not self.normalize_before:
             x = self.norm2(x)
         return x
@@ -157,15 +183,20 @@ class ErnieModel(nn.Module):
                  intermediate_size=None, hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
                  max_position_embeddings=512, type_vocab_size=2, task_type_vocab_size=3, task_id=0, use_task_id=False,
                  initializer_range=0.02, pad_token_id=0, use_recompute=False, mp_group=None, use_flash_attn=True, dtype=None, device=None,
-                 num_layers=None, **unused):
+                 num_layers=None, sequence_parallel=False, fused_tp_comm=False, **unused):
         super().__init__()
+        # Megatron sequence parallelism over the tensor-parallel group (not in the reference's ERNIE): activations between the GEMM pairs
+        # live as [s/n, b, h] shards, so LayerNorm / dropout / residual work and memory drop by n and every TP collective becomes an
+        # all-gather or reduce-scatter that the fused compute+collective kernels can absorb (Fused.tp_comm)
+        self.sequence_parallel = bool(sequence_parallel) and C.group_size(mp_group) > 1
+        sp = self.sequence_parallel
         num_hidden_layers = num_layers or num_hidden_layers
         ffn = ffn_hidden_size or intermediate_size or 4 * hidden_size
         self.pad_token_id, self.initializer_range, self.hidden_size, self.mp_group = pad_token_id, initializer_range, hidden_size, mp_group
         self.embeddings = ErnieEmbeddings(vocab_size, hidden_size, hidden_dropout_prob, max_position_embeddings, type_vocab_size,
                                           task_type_vocab_size, task_id, use_task_id, initializer_range, mp_group, dtype, device)
         layers = [TransformerEncoderLayer(hidden_size, num_attention_heads, ffn, hidden_dropout_prob, hidden_act, attention_probs_dropout_prob,
-                                          0, False, mp_group, initializer_range, dtype, device, use_flash_attn)
+                                          0, False, mp_group, initializer_range, dtype, device, use_flash_attn, sp, fused_tp_comm)
                   for _ in range(num_hidden_layers)]
         self.encoder = TransformerEncoder(layers, None, use_recompute)
         self.pooler = ErniePooler(hidden_size, initializer_range, dtype, device)
@@ -177,7 +208,12 @@ class ErnieModel(nn.Module):
         elif attention_mask.dim() == 2:
             attention_mask = (1.0 - attention_mask[:, None, None, :].to(self.pooler.dense.weight.dtype)) * -1e4
         x = self.embeddings(input_ids, token_type_ids, position_ids, task_type_ids)
+        if self.sequence_parallel:
+            assert x.shape[1] % C.group_size(self.mp_group) == 0, "sequence length must divide by the tensor-parallel degree under sequence parallelism"
+            x = C.scatter_seq(x.transpose(0, 1).contiguous(), self.mp_group)          # [b, s, h] -> [s/n, b, h]
         seq = self.encoder(x, attention_mask)
+        if self.sequence_parallel:
+            seq = C.gather_seq(seq, self.mp_group).transpose(0, 1).contiguous()       # heads and pooler run replicated on the full sequence
         return seq, self.pooler(seq)
 
 

@@ -394,3 +394,70 @@ def auto_inference_weights_roundtrip(rank, world, tmpdir):
     # the mp model returns vocabulary-parallel logits: compare this rank's slice
     v = ref.shape[-1]
     torch.testing.assert_close(logits[..., rank * v:(rank + 1) * v], ref, rtol=1e-4, atol=1e-5)
+
+
+def ernie_tp_matches_single(rank, world, sequence_parallel):
+    """ERNIE encoder under tensor parallelism (optionally with sequence parallelism): same MLM / SOP scores, same parameter gradients
+    (after the sequence-parallel gradient all-reduce) as the single-process model."""
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models.language_model.ernie import model as E
+    from paddlefleetx_b200.parallel.tp_layers import allreduce_sequence_parallel_grads, register_sequence_parallel_allreduce_hooks
+
+    mp = world
+    cfg = tiny_gpt_config(["Global.global_batch_size=None", "Global.local_batch_size=2", "Global.micro_batch_size=2", f"Distributed.mp_degree={mp}"], nranks=world)
+    env.init_dist_env(cfg)
+    hcg = env.get_hcg()
+    group = hcg.get_model_parallel_group()
+    kw = dict(vocab_size=256, hidden_size=32, num_hidden_layers=2, num_attention_heads=4, ffn_hidden_size=64, max_position_embeddings=32,
+              hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, use_flash_attn=False, dtype=torch.float64)
+    torch.manual_seed(5)
+    single = E.ErnieForPretraining(E.ErnieModel(**kw), 256).double()
+    init = {k: v.detach().clone() for k, v in single.state_dict().items()}
+    par = E.ErnieForPretraining(E.ErnieModel(mp_group=group, sequence_parallel=sequence_parallel, **kw), 256).double()
+    assert par.ernie.sequence_parallel == bool(sequence_parallel)
+    with torch.no_grad():
+        for k, p in par.named_parameters():
+            p.copy_(_shard_like(init[k], p, hcg.get_model_parallel_rank(), mp))
+    if sequence_parallel:
+        sp_params = register_sequence_parallel_allreduce_hooks(par, 1, False, group)
+        assert len(sp_params) == 2 * 2 * 2 + 2 * 2          # two LayerNorms (w, b) per layer + the two row-linear biases per layer
+    g = torch.Generator().manual_seed(9)
+    ids = torch.randint(1, 256, (2, 16), generator=g)
+    seg = torch.randint(0, 2, (2, 16), generator=g)
+    masked = torch.tensor([1, 5, 9, 17, 20, 30])
+    labels = torch.randint(0, 256, (6,), generator=g)
+    single.train(); par.train()
+
+    def loss_of(model, vocab_parallel):
+        scores, rel = model(ids, seg, None, None, masked)
+        if vocab_parallel:
+            v = scores.shape[-1]
+            lo = hcg.get_model_parallel_rank() * v
+            # squared error against a one-hot target restricted to this rank's vocabulary slice: sums to the full-vocabulary loss over ranks
+            tgt = torch.zeros_like(scores)
+            for i, l in enumerate(labels.tolist()):
+                if lo <= l < lo + v:
+                    tgt[i, l - lo] = 1.0
+            part = ((scores - tgt) ** 2).sum()
+            dist.all_reduce(part, group=group.process_group)        # value only; each rank back-propagates its own slice
+            # the sentence-order branch is replicated: every rank back-propagates it in full (the TP layers' own backward collectives
+            # combine the per-rank partial input gradients), exactly like a replicated scalar loss in training
+            return scores, rel, ((scores - tgt) ** 2).sum() + (rel ** 2).sum(), part + (rel ** 2).sum().detach()
+        tgt = torch.nn.functional.one_hot(labels, scores.shape[-1]).to(scores.dtype)
+        val = ((scores - tgt) ** 2).sum() + (rel ** 2).sum()
+        return scores, rel, val, val.detach()
+
+    s1, r1, l1, v1 = loss_of(single, False)
+    l1.backward()
+    s2, r2, l2, v2 = loss_of(par, True)
+    l2.backward()
+    if sequence_parallel:
+        allreduce_sequence_parallel_grads(par)
+    v = s2.shape[-1]
+    torch.testing.assert_close(s2, s1[:, hcg.get_model_parallel_rank() * v:(hcg.get_model_parallel_rank() + 1) * v], rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(r2, r1, rtol=1e-8, atol=1e-9)
+    torch.testing.assert_close(v2, v1, rtol=1e-8, atol=1e-9)
+    ref_grads = {k: p.grad for k, p in single.named_parameters()}
+    for k, p in par.named_parameters():
+        want = _shard_like(ref_grads[k], p, hcg.get_model_parallel_rank(), mp)
+        torch.testing.assert_close(p.grad, want, rtol=1e-6, atol=1e-8, msg=lambda m, k=k: f"{k}: {m}")

@@ -69,3 +69,8 @@ def test_moe_exp_expert_parallel_all_to_all_matches_single():
 
 def test_auto_inference_weights_reload_on_another_tensor_parallel_degree(tmp_path):
     run_distributed("dist_fns:auto_inference_weights_roundtrip", 2, str(tmp_path))
+
+
+@pytest.mark.parametrize("sp", [False, True])
+def test_ernie_tensor_and_sequence_parallel_match_single(sp):
+    run_distributed("dist_fns:ernie_tp_matches_single", 2, sp)

@@ -34,6 +34,8 @@ def parse():
     p.add_argument("--layers", type=int, default=0, help="debug: override depth (marks the result invalid)")
     p.add_argument("--mp", type=int, default=0, help="ernie: tensor-parallel degree (default 4 on 8 GPUs, else min(world, 2))")
     p.add_argument("--fp8", type=int, default=0, help="ernie: fp8 forward GEMMs in the tensor-parallel linears")
+    p.add_argument("--sp", type=int, default=0, help="ernie: Megatron sequence parallelism over the tensor-parallel group")
+    p.add_argument("--fused-tp", type=int, default=0, help="ernie (with --sp 1): all-gather->GEMM / GEMM->reduce-scatter as single peer-memory kernels")
     return p.parse_args()
 
 
@@ -90,12 +92,13 @@ def main():
         seq = 512
         ov = common + [f"Global.local_batch_size={local}", f"Global.micro_batch_size={local}", "Distributed.dp_degree=1", f"Distributed.mp_degree={mp}",
                        f"Distributed.sharding.sharding_degree={sh}", "Distributed.sharding.sharding_stage=3", f"Fused.fp8_tp_gemm={bool(a.fp8)}",
-                       "Fused.tp_comm=False", f"Data.Train.dataset.max_seq_length={seq}"]
+                       f"Fused.tp_comm={bool(a.fused_tp and a.sp)}", f"Model.sequence_parallel={bool(a.sp)}", f"Data.Train.dataset.max_seq_length={seq}"]
         if a.layers:
             ov.append(f"Model.num_hidden_layers={a.layers}")
         cfg = C.get_config(os.path.join(CFG, "nlp/ernie/pretrain_ernie_10B_mp4_stage3_fp8.yaml"), ov, nranks=world)
         unit, per_step = "tokens/s", local * seq * sh
-        name = f"ERNIE 10B-class (h4096 L{cfg.Model.num_hidden_layers}), mp{mp} x ZeRO-3 sharding{sh}, {'fp8' if a.fp8 else 'bf16'} TP GEMMs"
+        name = (f"ERNIE 10B-class (h4096 L{cfg.Model.num_hidden_layers}), mp{mp} x ZeRO-3 sharding{sh}, {'fp8' if a.fp8 else 'bf16'} TP GEMMs"
+                + (", sequence parallel" if a.sp else "") + (" with fused GEMM+collective kernels" if (a.fused_tp and a.sp) else ""))
         vocab = cfg.Model.vocab_size
         n_mask = 76
 
@@ -140,7 +143,7 @@ def main():
                "valid": not a.layers}
         print(json.dumps(out), flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        tag = f"{a.workload}_{world}gpu" + ("_p2p" if a.p2p else "") + ("_fp8" if a.fp8 else "")
+        tag = f"{a.workload}_{world}gpu" + ("_p2p" if a.p2p else "") + ("_fp8" if a.fp8 else "") + ("_sp" if a.sp else "") + ("_fusedtp" if a.fused_tp and a.sp else "")
         with open(os.path.join(ROOT, "gpurun_out", f"workload_{tag}.json"), "w") as f:
             json.dump(out, f)
     if world > 1:
