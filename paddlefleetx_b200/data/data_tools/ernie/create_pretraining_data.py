@@ -1,5 +1,5 @@
 """ERNIE corpus preparation (reference ppfleetx/data/data_tools/ernie/preprocess/create_pretraining_data.py): sentence-split
-tokenisation to ``<prefix>_ids.npy`` + ``<prefix>_idx.npz`` with ``sents`` / ``docs`` boundaries, which ``ErnieDataset`` needs
+tokenisation to ``<prefix>_ids.npy`` + ``<prefix>_idx.npz`` with per-sentence ``lens`` and ``docs`` boundaries, which ``ErnieDataset`` needs
 for sentence-order prediction and span masking.  Thin front-end over the GPT tool with ``--split_sentences`` forced on."""
 import sys
 

@@ -1,5 +1,5 @@
-"""jsonl -> token-id corpus: ``<prefix>_ids.npy`` (all documents' ids, flat) + ``<prefix>_idx.npz`` (``lens`` per document and,
-with ``--split_sentences``, ``sents`` / ``docs`` boundaries) — the on-disk format ``GPTDataset`` / ``ErnieDataset`` mmap.
+"""jsonl -> token-id corpus: ``<prefix>_ids.npy`` (all documents' ids, flat) + ``<prefix>_idx.npz`` (``lens`` per document; with
+``--split_sentences`` ``lens`` per sentence + ``docs`` = document boundaries in sentences) — the on-disk format ``GPTDataset`` / ``ErnieDataset`` mmap.
 
 CLI parity with the reference tool (ppfleetx/data/data_tools/gpt/preprocess_data.py:40-125): ``--model_name``,
 ``--tokenizer_name``, ``--input_path``, ``--output_prefix``, ``--data_format JSON``, ``--json_key``, ``--split_sentences``,
@@ -44,6 +44,19 @@ def get_args(argv=None):
     return p.parse_args(argv)
 
 
+class _CorpusWordPiece:
+    """ERNIE tokenizer as the corpus tools need it: ids without the ``[CLS] ... [SEP]`` frame, documents closed by ``[SEP]``."""
+
+    def __init__(self, tok):
+        self.tok, self.eos_token_id = tok, tok.sep_token_id
+
+    def encode(self, text):
+        return self.tok.encode_plain(text)
+
+    def __len__(self):
+        return len(self.tok)
+
+
 def build_tokenizer(args):
     """``--tokenizer_name`` x ``--model_name`` (a local vocabulary directory or a cached name) -> an object with ``encode(text) -> ids``
     *without* sequence-template tokens, ``eos_token_id`` and ``__len__``."""
@@ -52,9 +65,7 @@ def build_tokenizer(args):
     if args.tokenizer_name == "ByteTokenizer":
         return GPTTokenizer.byte_fallback()
     if args.tokenizer_name == "ErnieTokenizer":
-        tok = ErnieTokenizer.from_pretrained(args.model_name)
-        tok.encode, tok.eos_token_id = tok.encode_plain, tok.sep_token_id      # corpus ids carry no [CLS]/[SEP] frame; documents end with [SEP]
-        return tok
+        return _CorpusWordPiece(ErnieTokenizer.from_pretrained(args.model_name))
     if args.tokenizer_name == "GPTChineseTokenizer":
         return GPTChineseTokenizer.from_pretrained(args.model_name)
     try:
@@ -144,11 +155,15 @@ def main(argv=None):
     ids = np.concatenate(blocks) if blocks else np.zeros(0, dtype=dtype)
     os.makedirs(os.path.dirname(os.path.abspath(a.output_prefix)) or ".", exist_ok=True)
     np.save(a.output_prefix + "_ids.npy", ids)
-    extra = {}
     if a.split_sentences:
-        extra = {"sents": np.asarray(sent_lens, dtype=np.int32), "docs": np.cumsum([0] + doc_sent_counts).astype(np.int64)}
-    np.savez(a.output_prefix + "_idx.npz", lens=np.asarray(lens, dtype=np.int32), **extra)
-    print(f"{ndocs} documents, {ids.size} tokens -> {a.output_prefix}_ids.npy / _idx.npz")
+        # sentence-addressable corpus (ERNIE; reference create_pretraining_data.py:400-405): ``lens`` = tokens per SENTENCE, ``docs`` = document
+        # boundaries counted in sentences — what MMapIndexedDataset / build_mapping read
+        np.savez(a.output_prefix + "_idx.npz", lens=np.asarray(sent_lens, dtype=np.int32), docs=np.cumsum([0] + doc_sent_counts).astype(np.int64))
+        print(f"{ndocs} documents, {len(sent_lens)} sentences, {ids.size} tokens -> {a.output_prefix}_ids.npy / _idx.npz")
+    else:
+        # document-addressable corpus (GPT): ``lens`` = tokens per document
+        np.savez(a.output_prefix + "_idx.npz", lens=np.asarray(lens, dtype=np.int32))
+        print(f"{ndocs} documents, {ids.size} tokens -> {a.output_prefix}_ids.npy / _idx.npz")
 
 
 if __name__ == "__main__":

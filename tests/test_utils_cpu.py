@@ -179,7 +179,7 @@ def test_data_tools_produce_a_corpus_gpt_dataset_can_read(tmp_path):
     create_pretraining_data.main(["--input_path", str(tmp_path / "corpus.jsonl"), "--output_prefix", str(tmp_path / "e"),
                                   "--tokenizer_name", "ByteTokenizer"])
     e = np.load(tmp_path / "e_idx.npz")
-    assert e["docs"].tolist() == [0, 3, 4] and e["sents"].sum() == np.load(tmp_path / "e_ids.npy").size
+    assert e["docs"].tolist() == [0, 3, 4] and len(e["lens"]) == 4 and e["lens"].sum() == np.load(tmp_path / "e_ids.npy").size   # lens per sentence
 
 
 def test_launcher_spawns_ranks_logs_and_restarts(tmp_path):
@@ -248,3 +248,47 @@ def test_ppfleetx_alias_resolves_relocated_reference_module_paths():
 
     with pytest.raises(ModuleNotFoundError):
         importlib.import_module("ppfleetx.models.language_model.gpt.dygraph.no_such_module")
+
+
+def test_multiprocess_tool_runs_commands_and_reports_failures(tmp_path, capsys):
+    from paddlefleetx_b200.tools import multiprocess_tool as mt
+
+    cmds = tmp_path / "cmds.txt"
+    cmds.write_text(f"# bulk job\ntouch {tmp_path}/a\ntouch {tmp_path}/b && exit 3\necho hi > {tmp_path}/c\n\n")
+    assert mt.read_commands(str(cmds)) == [f"touch {tmp_path}/a", f"touch {tmp_path}/b && exit 3", f"echo hi > {tmp_path}/c"]
+    rc = mt.main(["--num_proc", "2", "--shell_cmd_list_filename", str(cmds)])
+    out = capsys.readouterr().out
+    assert rc == 1 and "2 succeeded, 1 failed" in out and "FAILED rc=3" in out
+    assert all((tmp_path / n).exists() for n in "abc")
+    ok = tmp_path / "ok.txt"
+    ok.write_text("true\ntrue\n")
+    assert mt.main(["--num_proc", "4", "--shell_cmd_list_filename", str(ok), "--retries", "1"]) == 0
+    slow = tmp_path / "slow.txt"
+    slow.write_text("sleep 5\n")
+    assert mt.main(["--shell_cmd_list_filename", str(slow), "--timeout", "0.2"]) == 1 and "timed out" in capsys.readouterr().out
+
+
+def test_ernie_corpus_tool_with_wordpiece_vocab(tmp_path):
+    """ERNIE pipeline: jsonl -> sentence-split WordPiece ids with document / sentence boundaries (``--tokenizer_name ErnieTokenizer``)."""
+    import json
+
+    import numpy as np
+
+    from paddlefleetx_b200.data.data_tools.ernie import create_pretraining_data
+
+    vocab = tmp_path / "vocab"
+    vocab.mkdir()
+    (vocab / "vocab.txt").write_text("\n".join(["[PAD]", "[CLS]", "[SEP]", "[MASK]", "[UNK]", "the", "quick", "fox", "jump", "##s", ".", "dog", "sleep"]) + "\n")
+    corpus = tmp_path / "c.jsonl"
+    corpus.write_text(json.dumps({"text": "The quick fox jumps. The dog sleeps."}) + "\n" + json.dumps({"text": "The fox sleeps."}) + "\n")
+    create_pretraining_data.main(["--model_name", str(vocab), "--tokenizer_name", "ErnieTokenizer", "--input_path", str(corpus),
+                                  "--output_prefix", str(tmp_path / "out"), "--append_eos"])
+    ids = np.load(tmp_path / "out_ids.npy")
+    idx = np.load(tmp_path / "out_idx.npz")
+    assert ids.dtype == np.uint16 and 2 in ids.tolist() and 1 not in ids.tolist()      # [SEP] closes documents, no [CLS] frame in corpus ids
+    assert idx["lens"].tolist() == [6, 6, 6] and idx["docs"].tolist() == [0, 2, 3] and idx["lens"].sum() == len(ids)     # per sentence; docs in sentences
+    from paddlefleetx_b200.data.dataset.ernie.ernie_dataset import MMapIndexedDataset
+
+    ds = MMapIndexedDataset(str(tmp_path / "out"))
+    assert len(ds) == 3 and ds[1].tolist() == [5, 11, 12, 9, 10, 2] and ds.doc_idx.tolist() == [0, 2, 3]
+    assert ids[:5].tolist() == [5, 6, 7, 8, 9]                                          # the quick fox jump ##s
