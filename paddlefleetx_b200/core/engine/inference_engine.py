@@ -73,6 +73,11 @@ class InferenceEngine:
         module_cls.process_configs = lambda self_, c: c          # the recipe already holds post-processed values
         module = module_cls(cfg)
         model = module.model
+        prune = ((recipe.get("Compress") or {}).get("Prune") or {})
+        if prune.get("enable", False):              # a structurally pruned export: rebuild the pruned shapes before the weights are loaded
+            from ...utils.compression_helper import prune_model
+
+            prune_model(model, prune)
         if recipe.get("quant"):
             from ...utils.compression_helper import convert_to_int8, quant_model
 

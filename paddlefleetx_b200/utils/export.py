@@ -35,7 +35,7 @@ def export_inference_model(model: torch.nn.Module, input_spec, save_dir: str, sa
     if smooth_quant:
         recipe["smooth_quant"] = _plain(smooth_quant)      # alpha / shift / the rewritten layers: InferenceEngine rebuilds the same structure
     if configs is not None:
-        for sec in ("Model", "Generation", "Distributed", "Global", "Inference", "Data", "Offline_Eval"):
+        for sec in ("Model", "Generation", "Distributed", "Global", "Inference", "Data", "Offline_Eval", "Compress"):
             if sec in configs:
                 recipe[sec] = _plain(configs[sec])
         recipe["Engine"] = {"mix_precision": _plain(configs.Engine.mix_precision)}

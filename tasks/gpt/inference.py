@@ -28,7 +28,11 @@ def main(argv=None):
     outs = engine.predict([ids])
     first = next(iter(outs.values()))
     print("Prompt:", a.text)
-    print("Generation:", tok.decode([int(t) for t in first[0]], skip_special_tokens=True))
+    if first.ndim == 2 and np.issubdtype(first.dtype, np.integer):          # a generation export: token ids
+        print("Generation:", tok.decode([int(t) for t in first[0]], skip_special_tokens=True))
+    else:                                                                    # a pre-training / QAT export: logits [batch, seq, vocab]
+        nxt = int(np.asarray(first)[0, -1].argmax())
+        print(f"Logits {tuple(first.shape)}; most likely next token: {nxt} {tok.decode([nxt])!r} (export a generation recipe to sample text)")
     return outs
 
 

@@ -1,0 +1,72 @@
+"""User-level chains through the command-line tools on CPU with tiny models (subprocesses, as a user would run them):
+QAT / pruning: train -> offline eval -> export -> serve;  ViT: train -> export -> classify;  ERNIE: export -> serve with the WordPiece vocabulary."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = "paddlefleetx_b200/configs"
+CPU = ["Global.device=cpu", "Engine.mix_precision.enable=False"]
+TINY_GPT = CPU + ["Model.num_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.ffn_hidden_size=128", "Model.vocab_size=512",
+                  "Model.max_position_embeddings=32"]
+TRAIN = ["Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0", "Global.local_batch_size=2",
+         "Global.micro_batch_size=2", "Engine.max_steps=3", "Engine.eval_freq=-1", "Engine.logging_freq=1", "Engine.save_load.save_steps=3"]
+
+
+def run(script, cfg=None, opts=(), args=(), timeout=400):
+    cmd = [sys.executable, os.path.join(ROOT, script)]
+    if cfg:
+        cmd += ["-c", os.path.join(ROOT, CFG, cfg)]
+    for o in opts:
+        cmd += ["-o", o]
+    p = subprocess.run(cmd + list(args), capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert p.returncode == 0, f"{script} {cfg}\n" + p.stdout[-1500:] + p.stderr[-2500:]
+    return p.stdout + p.stderr
+
+
+@pytest.fixture(scope="module")
+def wiki(tmp_path_factory):
+    p = tmp_path_factory.mktemp("eval") / "wiki.valid.tokens"
+    p.write_text(" = T = \n\n The quick brown fox jumps over the lazy dog . It was a bright cold day in April , and the clocks were striking thirteen . \n" * 6)
+    return str(p)
+
+
+@pytest.mark.parametrize("kind,eval_cfg,gen_cfg", [("qat", "eval_qat_gpt_345M_single_card.yaml", "generation_qat_gpt_345M_single_card.yaml"),
+                                                     ("prune", "eval_pruned_gpt_345M_single_card.yaml", "generation_pruned_gpt_345M_single_card.yaml")])
+def test_compression_recipe_chain_train_eval_export_serve(tmp_path, wiki, kind, eval_cfg, gen_cfg):
+    out = run("tools/train.py", f"nlp/gpt/{kind}_gpt_345M_single_card.yaml", TINY_GPT + TRAIN + [f"Engine.save_load.output_dir={tmp_path}/train"])
+    ckpt = os.path.join(tmp_path, "train", "epoch_0_step_3")
+    assert os.path.isfile(os.path.join(ckpt, "model.pdparams")), out[-800:]
+    ev = run("tools/eval.py", f"nlp/gpt/{eval_cfg}", TINY_GPT + [f"Engine.save_load.ckpt_dir={ckpt}", f"Offline_Eval.eval_path={wiki}", "Offline_Eval.cloze_eval=False",
+                                                             "Offline_Eval.max_seq_len=32", "Offline_Eval.batch_size=2", "Offline_Eval.overlapping_eval=8"])
+    assert "validation results" in ev and "ppl:" in ev
+    ex = run("tools/export.py", f"nlp/gpt/{gen_cfg}", TINY_GPT + [f"Engine.save_load.ckpt_dir={ckpt}", f"Engine.save_load.output_dir={tmp_path}/export", "Generation.max_dec_len=4"])
+    assert "exported inference model" in ex
+    served = run("projects/gpt/inference.py", args=["--model_dir", f"{tmp_path}/export", "--text", "hello there"])
+    assert "Generation:" in served
+    if kind == "prune":
+        assert "pruned 2 decoder layers" in served          # the serving engine rebuilt the pruned shapes from the recipe
+
+
+def test_vit_chain_train_export_classify(tmp_path):
+    vit = CPU + ["Model.model.img_size=32", "Model.model.patch_size=8", "Model.model.depth=2", "Distributed.dp_degree=1"]
+    data = ["Data.Train.dataset.name=SyntheticImageDataset", "Data.Train.dataset.image_size=32", "Data.Train.dataset.num_samples=16",
+            "Data.Eval.dataset.name=SyntheticImageDataset", "Data.Eval.dataset.image_size=32", "Data.Eval.dataset.num_samples=8", "Data.Eval.dataset.class_num=10",
+            "Global.local_batch_size=4", "Global.micro_batch_size=4", "Data.Train.sampler.batch_size=4", "Data.Eval.sampler.batch_size=4",
+            "Data.Train.loader.num_workers=0", "Data.Eval.loader.num_workers=0", "Engine.num_train_epochs=1", "Engine.logging_freq=1"]
+    cfg = "vis/vit/ViT_tiny_patch16_224_ci_cifar10_1n8c_dp_fp16o2.yaml"
+    out = run("tools/train.py", cfg, vit + data + [f"Engine.save_load.output_dir={tmp_path}/train"])
+    assert "images/sec" in out and os.path.isdir(os.path.join(tmp_path, "train", "epoch_0_step_4"))
+    run("tools/export.py", cfg, vit + [f"Engine.save_load.ckpt_dir={tmp_path}/train/epoch_0_step_4", f"Engine.save_load.output_dir={tmp_path}/export"])
+    served = run("projects/vit/inference.py", args=["--model_dir", f"{tmp_path}/export", "--random", "--size", "32"])
+    assert "top-5 classes:" in served
+
+
+def test_ernie_chain_export_serve_with_wordpiece_vocab(tmp_path):
+    (tmp_path / "vocab.txt").write_text("\n".join(["[PAD]", "[CLS]", "[SEP]", "[MASK]", "[UNK]", "hello", "my", "dog", "is", "cute", ","]) + "\n")
+    ernie = CPU + ["Model.num_hidden_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.vocab_size=512", "Model.max_position_embeddings=64"]
+    run("tools/export.py", "nlp/ernie/inference_ernie_345M_single_card.yaml", ernie + [f"Engine.save_load.output_dir={tmp_path}/export"])
+    served = run("projects/ernie/inference.py", args=["--model_dir", f"{tmp_path}/export", "--vocab_dir", str(tmp_path), "--seq_len", "16", "--text", "Hello, my dog is cute"])
+    assert "output_0 (1, 16, 512)" in served and "output_1 (1, 2)" in served
