@@ -70,3 +70,36 @@ def test_ernie_chain_export_serve_with_wordpiece_vocab(tmp_path):
     run("tools/export.py", "nlp/ernie/inference_ernie_345M_single_card.yaml", ernie + [f"Engine.save_load.output_dir={tmp_path}/export"])
     served = run("projects/ernie/inference.py", args=["--model_dir", f"{tmp_path}/export", "--vocab_dir", str(tmp_path), "--seq_len", "16", "--text", "Hello, my dog is cute"])
     assert "output_0 (1, 16, 512)" in served and "output_1 (1, 2)" in served
+
+
+def test_reshard_cli_mp2_checkpoint_resumes_identically_on_one_process(tmp_path):
+    """tools/train.py on 2 tensor-parallel gloo ranks -> tools/reshard.py --mp 1 -> single-process resume reproduces the losses of resuming on mp2
+    (weights, optimizer moments, LR schedule and data position all cross the layout change)."""
+    import re
+
+    opts = TINY_GPT + ["Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0", "Global.local_batch_size=2",
+                       "Global.micro_batch_size=2", "Engine.eval_freq=-1", "Engine.logging_freq=1", "Model.hidden_dropout_prob=0.0",
+                       "Model.attention_probs_dropout_prob=0.0", "Optimizer.lr.max_lr=1e-2", "Optimizer.lr.warmup_rate=0.0"]
+    cfg = os.path.join(ROOT, CFG, "nlp/gpt/pretrain_gpt_345M_single_card.yaml")
+
+    def launch(nproc, port, extra):
+        cmd = [sys.executable]
+        if nproc > 1:
+            cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr=127.0.0.1", f"--master-port={port}"]
+        cmd += [os.path.join(ROOT, "tools/train.py"), "-c", cfg]
+        for o in opts + extra:
+            cmd += ["-o", o]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=ROOT)
+        assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-2500:]
+        return sorted(set(re.findall(r"batch: \[(\d+)/\d+\], loss: ([0-9.]+)", p.stdout + p.stderr)))
+
+    mp2 = ["Distributed.mp_degree=2"]
+    launch(2, 29541, mp2 + ["Engine.max_steps=3", "Engine.save_load.save_steps=3", f"Engine.save_load.output_dir={tmp_path}/mp2"])
+    src = os.path.join(tmp_path, "mp2", "epoch_0_step_3")
+    assert sorted(os.listdir(src)) == ["mp_00_sharding_00_pp_00", "mp_01_sharding_00_pp_00"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools/reshard.py"), "--src", src, "--dst", f"{tmp_path}/mp1", "--mp", "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and os.path.isfile(os.path.join(tmp_path, "mp1", "model.pdparams")), r.stderr[-1500:]
+    resume = ["Engine.max_steps=6", "Engine.save_load.save_steps=-1"]
+    one = launch(1, 0, resume + [f"Engine.save_load.ckpt_dir={tmp_path}/mp1", f"Engine.save_load.output_dir={tmp_path}/o1"])
+    two = launch(2, 29543, mp2 + resume + [f"Engine.save_load.ckpt_dir={src}", f"Engine.save_load.output_dir={tmp_path}/o2"])
+    assert [s for s, _ in one] == ["3", "4", "5"] and one == two, (one, two)
