@@ -100,6 +100,11 @@ def merge_checkpoint(ckpt_dir: str, with_optimizer: bool = True):
                 named, opt_extra = _named_from_flat(flat)
                 per_mp_opt.append({(_CHUNK.sub("layers.", k) if _CHUNK.match(k) else k): v for k, v in named.items()})
         for name in per_mp_model[0]:
+            if name in model:
+                # a layer shared between pipeline stages (tied embedding): the FIRST stage's copy is the authoritative one.  The word
+                # embedding is kept identical on both stages by the shared-weight gradient all-reduce, but everything else in the shared
+                # layer that only the first stage uses (position embeddings) is never trained on the last stage and would be stale.
+                continue
             axis = axes.get(name, _fallback_axis(name) if len(mps) > 1 else None)
             if len(mps) > 1 and axis is not None:
                 model[name] = torch.cat([m[name] for m in per_mp_model], dim=axis)

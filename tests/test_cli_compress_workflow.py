@@ -72,14 +72,20 @@ def test_ernie_chain_export_serve_with_wordpiece_vocab(tmp_path):
     assert "output_0 (1, 16, 512)" in served and "output_1 (1, 2)" in served
 
 
-def test_reshard_cli_mp2_checkpoint_resumes_identically_on_one_process(tmp_path):
-    """tools/train.py on 2 tensor-parallel gloo ranks -> tools/reshard.py --mp 1 -> single-process resume reproduces the losses of resuming on mp2
-    (weights, optimizer moments, LR schedule and data position all cross the layout change)."""
+@pytest.mark.parametrize("layout,degree,reshard_args,dirs", [
+    ("mp2", "Distributed.mp_degree=2", [], ["mp_00_sharding_00_pp_00", "mp_01_sharding_00_pp_00"]),
+    ("pp2", "Distributed.pp_degree=2", ["--to-plain", "--num-layers", "4"], ["mp_00_sharding_00_pp_00", "mp_00_sharding_00_pp_01"]),
+])
+def test_reshard_cli_checkpoint_resumes_identically_on_one_process(tmp_path, layout, degree, reshard_args, dirs):
+    """tools/train.py on 2 gloo ranks (tensor parallel / pipeline) -> tools/reshard.py --mp 1 [--to-plain] -> a single-process resume reproduces the
+    losses of resuming on the original layout: weights (the first stage's copy of a tied embedding layer), optimizer moments, LR schedule and
+    data position all cross the layout change."""
     import re
 
-    opts = TINY_GPT + ["Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0", "Global.local_batch_size=2",
-                       "Global.micro_batch_size=2", "Engine.eval_freq=-1", "Engine.logging_freq=1", "Model.hidden_dropout_prob=0.0",
-                       "Model.attention_probs_dropout_prob=0.0", "Optimizer.lr.max_lr=1e-2", "Optimizer.lr.warmup_rate=0.0"]
+    opts = [o for o in TINY_GPT if not o.startswith("Model.num_layers")] + [
+        "Model.num_layers=4", "Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0",
+        "Global.local_batch_size=4", "Global.micro_batch_size=2", "Engine.eval_freq=-1", "Engine.logging_freq=1", "Model.hidden_dropout_prob=0.0",
+        "Model.attention_probs_dropout_prob=0.0", "Optimizer.lr.max_lr=1e-2", "Optimizer.lr.warmup_rate=0.0", "Model.use_flash_attn=False"]
     cfg = os.path.join(ROOT, CFG, "nlp/gpt/pretrain_gpt_345M_single_card.yaml")
 
     def launch(nproc, port, extra):
@@ -93,13 +99,14 @@ def test_reshard_cli_mp2_checkpoint_resumes_identically_on_one_process(tmp_path)
         assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-2500:]
         return sorted(set(re.findall(r"batch: \[(\d+)/\d+\], loss: ([0-9.]+)", p.stdout + p.stderr)))
 
-    mp2 = ["Distributed.mp_degree=2"]
-    launch(2, 29541, mp2 + ["Engine.max_steps=3", "Engine.save_load.save_steps=3", f"Engine.save_load.output_dir={tmp_path}/mp2"])
-    src = os.path.join(tmp_path, "mp2", "epoch_0_step_3")
-    assert sorted(os.listdir(src)) == ["mp_00_sharding_00_pp_00", "mp_01_sharding_00_pp_00"]
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools/reshard.py"), "--src", src, "--dst", f"{tmp_path}/mp1", "--mp", "1"], capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and os.path.isfile(os.path.join(tmp_path, "mp1", "model.pdparams")), r.stderr[-1500:]
+    base = 29541 if layout == "mp2" else 29551
+    launch(2, base, [degree, "Engine.max_steps=3", "Engine.save_load.save_steps=3", f"Engine.save_load.output_dir={tmp_path}/src"])
+    src = os.path.join(tmp_path, "src", "epoch_0_step_3")
+    assert sorted(os.listdir(src)) == dirs
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools/reshard.py"), "--src", src, "--dst", f"{tmp_path}/plain", "--mp", "1"] + reshard_args,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and os.path.isfile(os.path.join(tmp_path, "plain", "model.pdparams")), r.stderr[-1500:]
     resume = ["Engine.max_steps=6", "Engine.save_load.save_steps=-1"]
-    one = launch(1, 0, resume + [f"Engine.save_load.ckpt_dir={tmp_path}/mp1", f"Engine.save_load.output_dir={tmp_path}/o1"])
-    two = launch(2, 29543, mp2 + resume + [f"Engine.save_load.ckpt_dir={src}", f"Engine.save_load.output_dir={tmp_path}/o2"])
+    one = launch(1, 0, resume + [f"Engine.save_load.ckpt_dir={tmp_path}/plain", f"Engine.save_load.output_dir={tmp_path}/o1"])
+    two = launch(2, base + 2, [degree] + resume + [f"Engine.save_load.ckpt_dir={src}", f"Engine.save_load.output_dir={tmp_path}/o2"])
     assert [s for s, _ in one] == ["3", "4", "5"] and one == two, (one, two)
