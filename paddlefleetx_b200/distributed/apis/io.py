@@ -146,17 +146,18 @@ def merge_auto_inference(path_prefix: str) -> dict:
         attr = torch.load(f, map_location="cpu", weights_only=False)
         state = torch.load(f[:-len(".pdattr")] + ".pdparams", map_location="cpu", weights_only=False)
         for name, a in attr["tensors"].items():
-            pieces.setdefault(name, []).append((a["process_coord"][1], a["dims_mapping"], state[name]))
+            pieces.setdefault(name, []).append((a["process_coord"][1], a["dims_mapping"], state[name], a["process_coord"][0]))
     full = {}
     for name, parts in pieces.items():
-        parts.sort(key=lambda p: p[0])
+        # tensor-parallel order first; among pipeline duplicates of a shared layer the earliest stage's copy wins (it is the trained one)
+        parts.sort(key=lambda p: (p[0], p[3]))
         mapping = parts[0][1]
         axis = mapping.index(1) if 1 in mapping else None
         if axis is None:
             full[name] = parts[0][2]
         else:
             seen = {}
-            for coord, _, t in parts:
+            for coord, _, t, _stage in parts:
                 seen.setdefault(coord, t)             # the same shard may appear once per pipeline replica of a tied weight
             full[name] = torch.cat([seen[c] for c in sorted(seen)], dim=axis)
     return full
