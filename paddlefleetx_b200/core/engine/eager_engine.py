@@ -319,11 +319,14 @@ class EagerEngine(BasicEngine):
                                                       "total_batch": total_steps, "eval_cost": ecost})
                     self._module.model.train()
                     train_start = get_timestamp()
-                if self._save_steps and self._save_steps > 0 and step % self._save_steps == 0:
+                # A checkpoint is named by the number of COMPLETED steps: ``epoch_0_step_3`` holds the state after batches 0, 1, 2, and a resumed
+                # run (which skips ``step < 3``) continues with batch 3 — bit-identical to the uninterrupted run.  (The reference saves after
+                # training batch index ``save_steps`` under the same name, so its resumed run trains that batch a second time.)
+                if self._save_steps and self._save_steps > 0 and (step + 1) % self._save_steps == 0:
                     if device.type == "cuda":
                         torch.cuda.synchronize()
-                    self.save(epoch=epoch_index, step=step)
-                    self._last_saved_step = step
+                    self.save(epoch=epoch_index, step=step + 1)
+                    self._last_saved_step = step + 1
             else:
                 skip_first = False
 

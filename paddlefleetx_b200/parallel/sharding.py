@@ -92,6 +92,8 @@ class GroupShardedStage3(nn.Module):
             full = torch.zeros(total, dtype=dtype, device=dev)
             for (_, p), o in zip(plist, offsets):
                 full[o:o + p.numel()].copy_(p.data.reshape(-1))
+                p.data = full[o:o + p.numel()].view(p.shape)      # from now on the parameter IS a view of the unit's flat buffer (what
+                # load_state_dict / get_all_parameters rely on, also for the resident unit that is never re-gathered before the first step)
             s = total // self.world
             shard = nn.Parameter(full[self.rank * s:(self.rank + 1) * s].clone())
             shard.tp_sharded = key[1]
@@ -287,8 +289,9 @@ class GroupShardedStage3(nn.Module):
         return sd
 
     def load_state_dict(self, state, strict: bool = True):
+        self._release_all(force=True)       # every parameter becomes a view of a freshly gathered flat buffer ...
         self.get_all_parameters()
-        res = self._layers.load_state_dict(state, strict)
+        res = self._layers.load_state_dict(state, strict)      # ... so the in-place load lands in those buffers
         with torch.no_grad():           # refresh the persistent shards from the loaded full tensors
             for u in self.units:
                 for g in u.groups:

@@ -110,3 +110,22 @@ def test_reshard_cli_checkpoint_resumes_identically_on_one_process(tmp_path, lay
     one = launch(1, 0, resume + [f"Engine.save_load.ckpt_dir={tmp_path}/plain", f"Engine.save_load.output_dir={tmp_path}/o1"])
     two = launch(2, base + 2, [degree] + resume + [f"Engine.save_load.ckpt_dir={src}", f"Engine.save_load.output_dir={tmp_path}/o2"])
     assert [s for s, _ in one] == ["3", "4", "5"] and one == two, (one, two)
+
+
+def test_periodic_checkpoint_resume_reproduces_the_uninterrupted_run(tmp_path):
+    """``Engine.save_load.save_steps=3`` in a 6-step run, then a second process resuming from ``epoch_0_step_3``: the checkpoint is named by the number
+    of completed steps, so the resumed run continues with batch 3 and prints exactly the losses of the uninterrupted run."""
+    import re
+
+    opts = TINY_GPT + ["Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.loader.num_workers=0", "Global.local_batch_size=2",
+                       "Global.micro_batch_size=2", "Engine.eval_freq=-1", "Engine.logging_freq=1", "Engine.max_steps=6", "Optimizer.lr.max_lr=1e-2",
+                       "Optimizer.lr.warmup_rate=0.0"]        # dropout stays on: the RNG streams are part of the checkpoint
+
+    def losses(extra):
+        out = run("tools/train.py", "nlp/gpt/pretrain_gpt_345M_single_card.yaml", opts + extra)
+        return re.findall(r"batch: \[(\d+)/\d+\], loss: ([0-9.]+)", out)
+
+    straight = losses(["Engine.save_load.save_steps=3", f"Engine.save_load.output_dir={tmp_path}/a"])
+    assert [s for s, _ in straight] == [str(i) for i in range(6)] and sorted(os.listdir(tmp_path / "a")) == ["epoch_0_step_3", "epoch_0_step_6"]
+    resumed = losses(["Engine.save_load.save_steps=-1", f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_3", f"Engine.save_load.output_dir={tmp_path}/b"])
+    assert resumed == straight[3:], (straight, resumed)

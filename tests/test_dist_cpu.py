@@ -74,3 +74,8 @@ def test_auto_inference_weights_reload_on_another_tensor_parallel_degree(tmp_pat
 @pytest.mark.parametrize("sp", [False, True])
 def test_ernie_tensor_and_sequence_parallel_match_single(sp):
     run_distributed("dist_fns:ernie_tp_matches_single", 2, sp)
+
+
+@pytest.mark.parametrize("layout", ["dp2", "zero2", "zero3"])
+def test_resume_from_checkpoint_matches_uninterrupted_run(layout):
+    run_distributed("dist_fns:resume_matches_uninterrupted", 2, layout)
