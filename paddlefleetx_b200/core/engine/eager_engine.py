@@ -230,10 +230,7 @@ class EagerEngine(BasicEngine):
         self._module.model.train()
         train_cost = 0.0
         start_epoch = self._load_recovery["epoch"]
-        if self._load_recovery.get("rng_state") is not None and torch.cuda.is_available():
-            torch.cuda.set_rng_state(self._load_recovery["rng_state"])
-        if self._load_recovery.get("rng_tracker") is not None:
-            get_rng_state_tracker().set_states_tracker(self._load_recovery["rng_tracker"])
+        self._restore_rng()
         for epoch_index in range(start_epoch, epoch):
             t0 = get_timestamp()
             self._train_one_epoch(epoch_index, train_data_loader, valid_data_loader)
@@ -253,6 +250,16 @@ class EagerEngine(BasicEngine):
         if self._heartbeat is not None:
             self._heartbeat.stop()
 
+    def _restore_rng(self) -> None:
+        """Random-number streams of the checkpoint (device generator, host generator, the named tensor-parallel streams)."""
+        rec = self._load_recovery
+        if rec.get("rng_state") is not None and torch.cuda.is_available():
+            torch.cuda.set_rng_state(rec["rng_state"])
+        if rec.get("cpu_rng_state") is not None:
+            torch.set_rng_state(rec["cpu_rng_state"])
+        if rec.get("rng_tracker") is not None:
+            get_rng_state_tracker().set_states_tracker(rec["rng_tracker"])
+
     def _train_one_epoch(self, epoch_index: int, train_data_loader, valid_data_loader):
         self._module.model.train()
         device = self._device
@@ -269,6 +276,10 @@ class EagerEngine(BasicEngine):
         for step, batch in enumerate(loader):
             if step < resume_step:
                 continue          # resume: replay the sampler and discard consumed batches (eager_engine.py:347-349)
+            if resume_step and step == resume_step:
+                # creating the loader iterator and replaying it drew from the host generator (DataLoader base seed): put the streams back to
+                # the checkpointed state right before the first step that trains, so noise (dropout, MoE routing) continues where it stopped
+                self._restore_rng()
             loss = self._fit_impl(batch)
             loss = self._fault.maybe_fire(step, loss)
             losses.append(loss)

@@ -46,17 +46,45 @@ def _cpu(obj):
     return obj
 
 
-def save(output_dir: str, model: torch.nn.Module, optimizer=None, step: int = 0, epoch: int = 0, scaler=None, sharding_stage: int = 1) -> Optional[str]:
-    if env.world_size() > 1 and env.get_hcg().get_data_parallel_rank() != 0:
+def _expert_keys(model: torch.nn.Module) -> set:
+    return {n for n, p in model.named_parameters() if getattr(p, "is_expert", False)}
+
+
+def _expert_replica_dir(d: str) -> Optional[str]:
+    """Expert parallelism spreads the experts over the DATA-parallel ranks, so replicas 1.. hold weights (and optimizer moments) that replica 0
+    does not: they get their own ``dp_XX`` sub-directory next to replica 0's files.  (The reference writes replica 0 only and cannot resume
+    an expert-parallel run.)"""
+    if env.world_size() == 1:
         return None
+    r = env.get_hcg().get_data_parallel_rank()
+    return os.path.join(d, f"dp_{r:02d}") if r != 0 else None
+
+
+def _rng_states() -> dict:
+    return {"cpu_rng_state": torch.get_rng_state(), "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
+            "rng_tracker": get_rng_state_tracker().get_states_tracker()}
+
+
+def save(output_dir: str, model: torch.nn.Module, optimizer=None, step: int = 0, epoch: int = 0, scaler=None, sharding_stage: int = 1) -> Optional[str]:
     d = ckpt_dir(output_dir, epoch, step)
+    if env.world_size() > 1 and env.get_hcg().get_data_parallel_rank() != 0:
+        # replicas 1.. only add what replica 0 cannot know: their random-number streams (dropout / routing noise differ per replica) and,
+        # under expert parallelism, their experts with the matching optimizer state
+        ed = _expert_replica_dir(d)
+        os.makedirs(ed, exist_ok=True)
+        torch.save(_rng_states(), os.path.join(ed, "meta_state.pdopt"))
+        experts = _expert_keys(model)
+        if experts:
+            torch.save({k: v for k, v in _cpu(model.state_dict()).items() if k in experts}, os.path.join(ed, "model.pdparams"))
+            if optimizer is not None:
+                torch.save(_cpu(optimizer.state_dict()), os.path.join(ed, "model_state.pdopt"))
+            logger.info(f"save this replica's experts to {ed}")
+        return ed
     os.makedirs(d, exist_ok=True)
     torch.save(_cpu(model.state_dict()), os.path.join(d, "model.pdparams"))
     if optimizer is not None:
         torch.save(_cpu(optimizer.state_dict()), os.path.join(d, "model_state.pdopt"))
-    meta = {"epoch": epoch, "step": step, "cpu_rng_state": torch.get_rng_state(),
-            "cuda_rng_state": torch.cuda.get_rng_state() if torch.cuda.is_available() else None,
-            "rng_tracker": get_rng_state_tracker().get_states_tracker(),
+    meta = {"epoch": epoch, "step": step, **_rng_states(),
             "scaler": scaler.state_dict() if scaler is not None else None,
             # tensor-parallel split axis of every sharded entry; lets utils/ckpt_convert.py merge / re-split offline
             "tp_axes": {n: int(getattr(p, "split_axis", 0)) for n, p in model.named_parameters() if getattr(p, "tp_sharded", False)},
@@ -72,6 +100,9 @@ def load(ckpt_path: str, model: torch.nn.Module, optimizer=None, mode: str = "tr
     if not os.path.isfile(mpath):
         raise ValueError(f"No model checkpoint file found in {d}.")
     state = torch.load(mpath, map_location="cpu", weights_only=False)
+    ed = _expert_replica_dir(d)
+    if ed is not None and os.path.isfile(os.path.join(ed, "model.pdparams")):          # this data-parallel replica's own experts
+        state.update(torch.load(os.path.join(ed, "model.pdparams"), map_location="cpu", weights_only=False))
     own = model.state_dict()
     for k, v in own.items():
         if k not in state:
@@ -82,12 +113,16 @@ def load(ckpt_path: str, model: torch.nn.Module, optimizer=None, mode: str = "tr
     rec = load_recovery if load_recovery is not None else {}
     if mode == "train":
         opath, meta_path = os.path.join(d, "model_state.pdopt"), os.path.join(d, "meta_state.pdopt")
+        if ed is not None and os.path.isfile(os.path.join(ed, "model_state.pdopt")):
+            opath = os.path.join(ed, "model_state.pdopt")
         if optimizer is not None:
             if not os.path.isfile(opath):
                 raise ValueError(f"No optimizer checkpoint file found in {d}.")
             optimizer.set_state_dict(torch.load(opath, map_location="cpu", weights_only=False))
         if os.path.isfile(meta_path):
             meta = torch.load(meta_path, map_location="cpu", weights_only=False)
+            if ed is not None and os.path.isfile(os.path.join(ed, "meta_state.pdopt")):      # this replica's own random-number streams
+                meta.update(torch.load(os.path.join(ed, "meta_state.pdopt"), map_location="cpu", weights_only=False))
             rec.update(step=meta["step"], epoch=meta["epoch"], rng_state=meta.get("cuda_rng_state"), cpu_rng_state=meta.get("cpu_rng_state"),
                        rng_tracker=meta.get("rng_tracker"))
             if scaler is not None and meta.get("scaler") is not None:

@@ -129,3 +129,29 @@ def test_periodic_checkpoint_resume_reproduces_the_uninterrupted_run(tmp_path):
     assert [s for s, _ in straight] == [str(i) for i in range(6)] and sorted(os.listdir(tmp_path / "a")) == ["epoch_0_step_3", "epoch_0_step_6"]
     resumed = losses(["Engine.save_load.save_steps=-1", f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_3", f"Engine.save_load.output_dir={tmp_path}/b"])
     assert resumed == straight[3:], (straight, resumed)
+
+
+def test_expert_parallel_run_resumes_identically(tmp_path):
+    """GPT-MoE on 2 data-parallel gloo ranks (experts spread over the replicas, dropout and random second-expert routing on): the checkpoint
+    carries every replica's experts, their optimizer moments and its own random-number streams, so the resumed run repeats the losses."""
+    import re
+
+    opts = TINY_GPT + ["Data.Train.dataset.name=SyntheticGPTDataset", "Data.Train.dataset.max_seq_len=32", "Data.Train.dataset.vocab_size=512",
+                       "Data.Train.loader.num_workers=0", "Global.local_batch_size=2", "Global.micro_batch_size=2", "Engine.eval_freq=-1", "Engine.logging_freq=1",
+                       "Engine.max_steps=6", "Optimizer.lr.max_lr=1e-2", "Optimizer.lr.warmup_rate=0.0", "Distributed.dp_degree=2"]
+    cfg = os.path.join(ROOT, CFG, "nlp/moe/pretrain_moe_345M_single_card.yaml")
+
+    def launch(port, extra):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr=127.0.0.1", f"--master-port={port}",
+               os.path.join(ROOT, "tools/train.py"), "-c", cfg]
+        for o in opts + extra:
+            cmd += ["-o", o]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=ROOT)
+        assert p.returncode == 0, p.stdout[-1500:] + p.stderr[-2500:]
+        return sorted(re.findall(r"batch: \[(\d+)/\d+\], loss: ([0-9.]+)", p.stdout + p.stderr))
+
+    straight = launch(29601, ["Engine.save_load.save_steps=3", f"Engine.save_load.output_dir={tmp_path}/a"])
+    ck = os.path.join(tmp_path, "a", "epoch_0_step_3", "mp_00_sharding_00_pp_00")
+    assert sorted(os.listdir(os.path.join(ck, "dp_01"))) == ["meta_state.pdopt", "model.pdparams", "model_state.pdopt"]
+    resumed = launch(29603, ["Engine.save_load.save_steps=-1", f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_3", f"Engine.save_load.output_dir={tmp_path}/b"])
+    assert len(resumed) == 6 and resumed == [x for x in straight if int(x[0]) >= 3], (straight, resumed)
