@@ -65,7 +65,10 @@ class _Prefetcher:
         self.stream = torch.cuda.Stream() if device.type == "cuda" else None
 
     def __iter__(self):
-        it = iter(self.loader)
+        # DataLoader.__iter__ draws its worker base seed from the global host generator; fork the generator around it so that creating (or, on
+        # resume, re-creating) an iterator never shifts the stream the model's own noise comes from
+        with torch.random.fork_rng(devices=[]):
+            it = iter(self.loader)
         nxt = self._load(it)
         while nxt is not None:
             if self.stream is not None:
@@ -189,6 +192,7 @@ class EagerEngine(BasicEngine):
             self._optimizer.install_forward_hooks(self._module.model)      # overlapped ZeRO parameter all-gather (no-op otherwise)
 
         self._load_recovery = {"step": 0, "epoch": 0, "rng_state": None}
+        self._rng_restore_pending = False
         self._profiler = None
         if configs.get("Profiler", {}).get("enable", False) and mode == "train":
             from ...utils.profiler import StepProfiler
@@ -276,10 +280,12 @@ class EagerEngine(BasicEngine):
         for step, batch in enumerate(loader):
             if step < resume_step:
                 continue          # resume: replay the sampler and discard consumed batches (eager_engine.py:347-349)
-            if resume_step and step == resume_step:
-                # creating the loader iterator and replaying it drew from the host generator (DataLoader base seed): put the streams back to
-                # the checkpointed state right before the first step that trains, so noise (dropout, MoE routing) continues where it stopped
+            if self._rng_restore_pending:
+                # creating loader iterators and replaying consumed batches drew from the host generator (DataLoader base seed): put the streams
+                # back to the checkpointed state right before the first step that trains — in whichever epoch that is — so noise (dropout, MoE
+                # routing) continues where it stopped
                 self._restore_rng()
+                self._rng_restore_pending = False
             loss = self._fit_impl(batch)
             loss = self._fault.maybe_fire(step, loss)
             losses.append(loss)
@@ -500,6 +506,7 @@ class EagerEngine(BasicEngine):
                            mode="train" if self.mode == "train" else "eval", scaler=self._scaler)
         if rec:
             self._load_recovery.update(rec)
+            self._rng_restore_pending = self.mode == "train"
 
     # ---------------------------------------------------------------------------------------- export / inference
     def export(self):

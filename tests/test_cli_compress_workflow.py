@@ -155,3 +155,22 @@ def test_expert_parallel_run_resumes_identically(tmp_path):
     assert sorted(os.listdir(os.path.join(ck, "dp_01"))) == ["meta_state.pdopt", "model.pdparams", "model_state.pdopt"]
     resumed = launch(29603, ["Engine.save_load.save_steps=-1", f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_3", f"Engine.save_load.output_dir={tmp_path}/b"])
     assert len(resumed) == 6 and resumed == [x for x in straight if int(x[0]) >= 3], (straight, resumed)
+
+
+def test_epoch_mode_resume_reproduces_the_second_epoch(tmp_path):
+    """ViT (epoch mode, dropout on, per-epoch shuffling): resuming from the end-of-epoch-0 checkpoint prints the epoch-1 losses of the 2-epoch run."""
+    import re
+
+    vit = CPU + ["Model.model.img_size=32", "Model.model.patch_size=8", "Model.model.depth=2", "Distributed.dp_degree=1", "Data.Train.dataset.name=SyntheticImageDataset",
+                 "Data.Train.dataset.image_size=32", "Data.Train.dataset.num_samples=16", "Data.Train.dataset.class_num=10", "Global.local_batch_size=4",
+                 "Global.micro_batch_size=4", "Data.Train.sampler.batch_size=4", "Data.Train.loader.num_workers=0", "Engine.logging_freq=1", "Engine.eval_freq=-1",
+                 "Engine.num_train_epochs=2", "Optimizer.lr.learning_rate=1e-3", "Optimizer.lr.warmup_steps=0"]
+    cfg = "vis/vit/ViT_tiny_patch16_224_ci_cifar10_1n8c_dp_fp16o2.yaml"
+
+    def losses(extra):
+        return re.findall(r"epoch: (\d+), step: \[(\d+)/\d+\].*?loss: ([0-9.]+)", run("tools/train.py", cfg, vit + extra))
+
+    straight = losses([f"Engine.save_load.output_dir={tmp_path}/a"])
+    assert len(straight) == 8 and sorted(os.listdir(tmp_path / "a")) == ["epoch_0_step_4", "epoch_1_step_4"]
+    resumed = losses([f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_4", f"Engine.save_load.output_dir={tmp_path}/b"])
+    assert resumed == [x for x in straight if x[0] == "1"], (straight, resumed)
