@@ -156,8 +156,20 @@ def pad_and_convert_to_numpy(tokens, tokentypes, positions, labels, pad_id: int,
 class ErnieDataset(torch.utils.data.Dataset):
     def __init__(self, input_dir: str, split: Sequence[float] = (949, 50, 1), max_seq_len: int = 512, max_seq_length: Optional[int] = None,
                  num_samples: Optional[int] = None, mode: str = "Train", masked_lm_prob: float = 0.15, short_seq_prob: float = 0.1, seed: int = 1234,
-                 binary_head: bool = True, vocab_size: int = 40000, cls_id: int = 1, sep_id: int = 2, mask_id: int = 3, pad_id: int = 0,
+                 binary_head: bool = True, vocab_size: Optional[int] = None, cls_id: int = 1, sep_id: int = 2, mask_id: int = 3, pad_id: int = 0,
                  max_ngrams: int = 3, favor_longer_ngram: bool = False, share_folder: bool = False, tokenizer_type=None, **unused):
+        # special ids and the id range random replacements are drawn from: the vocabulary named by ``tokenizer_type`` when it is on this
+        # machine (reference: get_ernie_tokenizer, ernie_dataset.py:57), otherwise the conventional ERNIE layout ([PAD] [CLS] [SEP] [MASK] = 0..3)
+        if tokenizer_type:
+            try:
+                from ...tokenizers import get_ernie_tokenizer
+
+                tok = get_ernie_tokenizer(tokenizer_type)
+                cls_id, sep_id, mask_id, pad_id = tok.cls_token_id, tok.sep_token_id, tok.mask_token_id, tok.pad_token_id
+                vocab_size = vocab_size or tok.vocab_size
+            except FileNotFoundError:
+                pass
+        vocab_size = vocab_size or 40000
         self.max_seq_length = max_seq_length or max_seq_len
         self.mode, self.seed, self.binary_head = mode, seed, binary_head
         self.masked_lm_prob, self.vocab_size = masked_lm_prob, vocab_size

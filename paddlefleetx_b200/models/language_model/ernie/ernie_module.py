@@ -36,6 +36,8 @@ def process_data_configs(config) -> None:
             ds["mode"] = mode
             ds.setdefault("seed", g.seed)
             ds.setdefault("binary_head", g.get("binary_head", True))
+            if ds.get("vocab_size") is None and not ds.get("tokenizer_type") and config.get("Model", {}).get("vocab_size"):
+                ds["vocab_size"] = config.Model.vocab_size          # random-replacement ids of the MLM masking stay inside the embedding table
             if "sampler" in config.Data[mode]:
                 config.Data[mode].sampler["batch_size"] = g.local_batch_size
             col = config.Data[mode].get("loader", {}).get("collate_fn")

@@ -174,3 +174,33 @@ def test_epoch_mode_resume_reproduces_the_second_epoch(tmp_path):
     assert len(straight) == 8 and sorted(os.listdir(tmp_path / "a")) == ["epoch_0_step_4", "epoch_1_step_4"]
     resumed = losses([f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_4", f"Engine.save_load.output_dir={tmp_path}/b"])
     assert resumed == [x for x in straight if x[0] == "1"], (straight, resumed)
+
+
+def test_ernie_pipeline_corpus_tools_to_pretraining(tmp_path):
+    """raw jsonl -> create_pretraining_data (WordPiece, sentence-addressable index) -> ErnieDataset (C++ sample mapping, masking with the vocabulary's
+    own special ids) -> tools/train.py: the loss is finite and the MLM random replacements stay inside the (tiny) embedding table."""
+    import json
+    import random
+    import re
+
+    random.seed(0)
+    words = ["the", "quick", "brown", "fox", "jump", "##s", "over", "lazy", "dog", "cat", "sleep", "run", "fast", "slow", "house", "tree", "river", "cloud"]
+    vocab = tmp_path / "vocab"
+    vocab.mkdir()
+    (vocab / "vocab.txt").write_text("\n".join(["[PAD]", "[CLS]", "[SEP]", "[MASK]", "[UNK]"] + words + [".", ","]) + "\n")
+    base = [w for w in words if not w.startswith("##")]
+    with open(tmp_path / "corpus.jsonl", "w") as f:
+        for _ in range(60):
+            sents = [" ".join(random.choice(base) for _ in range(random.randint(5, 12))) + " ." for _ in range(random.randint(3, 6))]
+            f.write(json.dumps({"text": " ".join(sents)}) + "\n")
+    r = subprocess.run([sys.executable, "-m", "paddlefleetx_b200.data.data_tools.ernie.create_pretraining_data", "--model_name", str(vocab), "--tokenizer_name",
+                        "ErnieTokenizer", "--input_path", str(tmp_path / "corpus.jsonl"), "--output_prefix", str(tmp_path / "data" / "c")],
+                       capture_output=True, text=True, cwd=ROOT, timeout=120)
+    assert r.returncode == 0 and "sentences" in r.stdout, r.stderr[-1500:]
+    out = run("tools/train.py", "nlp/ernie/pretrain_ernie_base.yaml", CPU + [
+        "Model.num_hidden_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.vocab_size=128", "Model.max_position_embeddings=64",
+        f"Data.Train.dataset.input_dir={tmp_path}/data", "Data.Train.dataset.max_seq_length=32", f"Data.Train.dataset.tokenizer_type={vocab}",
+        "Data.Train.loader.num_workers=0", "Global.local_batch_size=4", "Global.micro_batch_size=4", "Engine.eval_freq=-1", "Engine.logging_freq=1",
+        "Engine.max_steps=4", "Engine.save_load.save_steps=-1", f"Engine.save_load.output_dir={tmp_path}/out"])
+    losses = [float(x) for x in re.findall(r"loss: ([0-9.]+)", out)]
+    assert len(losses) >= 4 and all(0 < l < 20 for l in losses), losses
