@@ -41,8 +41,14 @@ class GlueDataset(torch.utils.data.Dataset):
             except FileNotFoundError:
                 tokenizer = GPTTokenizer.byte_fallback()
         self.tokenizer = tokenizer
-        fname = train_f if split == "train" else (dev_file or dev_f)
-        path = os.path.join(root, d, fname) if os.path.isdir(os.path.join(root, d)) else os.path.join(root, fname)
+        base = os.path.join(root, d) if os.path.isdir(os.path.join(root, d)) else root
+        if split == "train":
+            names = [train_f, os.path.join("raw", "in_domain_train.tsv")]
+        elif split in ("dev", "eval", "validation"):
+            names = [dev_file or dev_f, "dev.tsv", os.path.join("raw", "in_domain_dev.tsv")]
+        else:                         # test, dev_matched, dev_mismatched, ...: the split names its own file
+            names = [dev_file or f"{split}.tsv", dev_f]
+        path = next((os.path.join(base, n) for n in names if n and os.path.isfile(os.path.join(base, n))), os.path.join(base, names[0]))
         self.samples = []
         with open(path, encoding="utf-8") as f:
             rows = list(csv.reader(f, delimiter="\t", quoting=csv.QUOTE_NONE))

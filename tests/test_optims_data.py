@@ -187,3 +187,22 @@ def test_forward_hooks_cover_parameters_read_through_a_child(monkeypatch):
     waited.clear()
     net(torch.randn(2, 8))
     assert waited == []                                     # nothing in flight: hooks are free
+
+
+def test_glue_split_names_select_their_files(tmp_path):
+    """``split`` values the recipes / scripts use: train, dev, test, dev_matched, dev_mismatched; CoLA also in its public ``raw/in_domain_*`` layout."""
+    from paddlefleetx_b200.data.dataset import glue_dataset as G
+
+    d = tmp_path / "MNLI"
+    d.mkdir()
+    hdr = "\t".join(f"c{i}" for i in range(12))
+    row = lambda lab, t: "\t".join(["x"] * 8 + [f"premise {t}", f"hypothesis {t}", "x", lab])  # noqa: E731
+    for fn, t in (("train.tsv", "tr"), ("dev_matched.tsv", "m"), ("dev_mismatched.tsv", "mm")):
+        (d / fn).write_text(hdr + "\n" + row("entailment", t) + "\n" + row("neutral", t) + "\n")
+    got = {split: G.MNLI(root=str(tmp_path), split=split).samples[0][0] for split in ("train", "dev", "dev_matched", "dev_mismatched")}
+    assert got == {"train": "premise tr", "dev": "premise m", "dev_matched": "premise m", "dev_mismatched": "premise mm"}
+    raw = tmp_path / "cola_public" / "raw"
+    raw.mkdir(parents=True)
+    (raw / "in_domain_train.tsv").write_text("s\t1\t*\tgood sentence\ns\t0\t*\tbad sentence\n")
+    (raw / "in_domain_dev.tsv").write_text("s\t1\t*\tdev sentence\n")
+    assert len(G.CoLA(root=str(tmp_path / "cola_public"), split="train")) == 2 and len(G.CoLA(root=str(tmp_path / "cola_public"), split="dev")) == 1
