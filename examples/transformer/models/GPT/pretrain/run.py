@@ -41,7 +41,7 @@ def main():
         rec = io.load(config.Engine.save_load.ckpt_dir, model, optimizer, "train", scaler=scaler)
         start_step = rec.get("step", 0)
     else:
-        start_step = 0
+        rec, start_step = None, 0
 
     train_loader = cpn.build_dataloader(config.Data, "Train")
     valid_loader = cpn.build_dataloader(config.Data, "Eval") if config.Data.get("Eval") else None
@@ -54,6 +54,9 @@ def main():
             continue
         if step >= eng.max_steps:
             break
+        if rec is not None:           # first step after a resume: dropout / routing noise continues from the checkpointed streams
+            io.restore_rng(rec)
+            rec = None
         batch = [t.to(device, non_blocking=True) for t in batch]
         losses.append(impls.fit_impl(config, batch, model, loss_fn, optimizer, scaler))
         lr.step()

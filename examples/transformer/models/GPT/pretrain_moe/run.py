@@ -30,11 +30,19 @@ def main():
     if env.world_size() > 1:
         model, optimizer, _ = strategy.wrap_with_fleet(config.Distributed, model, optimizer, None)
     device = next(model.parameters()).device
+    ckpt = config.Engine.save_load.get("ckpt_dir")
+    rec = io.load(ckpt, model, optimizer, "train") if ckpt else None     # each dp replica reads its own experts / optimizer slice / RNG
+    start_step = rec.get("step", 0) if rec else 0
     loader = cpn.build_dataloader(config.Data, "Train")
     t0 = time.time()
     for step, batch in enumerate(loader):
+        if step < start_step:
+            continue
         if step >= config.Engine.max_steps:
             break
+        if rec is not None:           # the gate's noise and dropout continue from the checkpointed streams
+            io.restore_rng(rec)
+            rec = None
         loss = impls.fit_impl(config, [t.to(device) for t in batch], module, optimizer)
         lr.step()
         if (step + 1) % config.Engine.logging_freq == 0:

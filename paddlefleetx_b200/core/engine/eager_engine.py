@@ -256,13 +256,7 @@ class EagerEngine(BasicEngine):
 
     def _restore_rng(self) -> None:
         """Random-number streams of the checkpoint (device generator, host generator, the named tensor-parallel streams)."""
-        rec = self._load_recovery
-        if rec.get("rng_state") is not None and torch.cuda.is_available():
-            torch.cuda.set_rng_state(rec["rng_state"])
-        if rec.get("cpu_rng_state") is not None:
-            torch.set_rng_state(rec["cpu_rng_state"])
-        if rec.get("rng_tracker") is not None:
-            get_rng_state_tracker().set_states_tracker(rec["rng_tracker"])
+        ckpt_io.restore_rng(self._load_recovery)
 
     def _train_one_epoch(self, epoch_index: int, train_data_loader, valid_data_loader):
         self._module.model.train()

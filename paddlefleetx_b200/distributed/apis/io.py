@@ -65,6 +65,17 @@ def _rng_states() -> dict:
             "rng_tracker": get_rng_state_tracker().get_states_tracker()}
 
 
+def restore_rng(rec: dict) -> None:
+    """Put the random-number streams recorded in a checkpoint (``load`` returns them in its recovery dict) back: device generator, host generator,
+    the named tensor-parallel streams.  Call it right before the first step that trains."""
+    if rec.get("rng_state") is not None and torch.cuda.is_available():
+        torch.cuda.set_rng_state(rec["rng_state"])
+    if rec.get("cpu_rng_state") is not None:
+        torch.set_rng_state(rec["cpu_rng_state"])
+    if rec.get("rng_tracker") is not None:
+        get_rng_state_tracker().set_states_tracker(rec["rng_tracker"])
+
+
 def save(output_dir: str, model: torch.nn.Module, optimizer=None, step: int = 0, epoch: int = 0, scaler=None, sharding_stage: int = 1) -> Optional[str]:
     d = ckpt_dir(output_dir, epoch, step)
     if env.world_size() > 1 and env.get_hcg().get_data_parallel_rank() != 0:

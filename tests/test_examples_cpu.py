@@ -30,6 +30,26 @@ def test_explicit_loop_examples_train(script, cfg):
     assert "[train] step: 4/4" in out
 
 
+def _losses(out):
+    import re
+
+    return {int(m.group(1)): m.group(2) for m in re.finditer(r"\[train\] step: (\d+)/\d+, loss: ([0-9.]+)", out)}
+
+
+@pytest.mark.parametrize("script,cfg", [
+    ("examples/transformer/models/GPT/pretrain/run.py", "examples/transformer/models/GPT/pretrain/configs/pretrain_gpt_345M_single_card.yaml"),
+    ("examples/transformer/models/GPT/pretrain_moe/run.py", "examples/transformer/models/GPT/pretrain_moe/configs/pretrain_moe_345M_single_card.yaml"),
+])
+def test_explicit_loop_resume_continues_the_uninterrupted_run(script, cfg, tmp_path):
+    """Dropout is on (recipe default): a run resumed from the step-3 checkpoint prints the same losses as the run that never stopped."""
+    common = ["Engine.max_steps=6", "Engine.logging_freq=1", "Optimizer.lr.max_lr=1e-2", "Optimizer.lr.warmup_rate=0.0"]
+    straight = _losses(_run(script, cfg, common + ["Engine.save_load.save_steps=3", f"Engine.save_load.output_dir={tmp_path}/a"]))
+    resumed = _losses(_run(script, cfg, common + ["Engine.save_load.save_steps=-1", f"Engine.save_load.output_dir={tmp_path}/b",
+                                                  f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_3"]))
+    assert sorted(resumed) == [4, 5, 6] and sorted(straight) == [1, 2, 3, 4, 5, 6]
+    assert all(resumed[k] == straight[k] for k in resumed), (straight, resumed)
+
+
 def test_every_project_script_points_at_an_existing_config_and_tool():
     import glob
     import re
