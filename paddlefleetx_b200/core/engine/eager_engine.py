@@ -123,6 +123,7 @@ class EagerEngine(BasicEngine):
         self._save_epoch = eng.save_load.save_epoch
         self._output_dir = eng.save_load.output_dir
         self._ckpt_dir = eng.save_load.ckpt_dir
+        self._resume_replay = bool(eng.save_load.get("resume_replay", False))
         self._global_batch_size = g.global_batch_size
         self._local_batch_size = g.local_batch_size
         self._micro_batch_size = g.micro_batch_size
@@ -271,9 +272,15 @@ class EagerEngine(BasicEngine):
             ev0.record()
         resume_step = self._load_recovery["step"] if epoch_index == self._load_recovery["epoch"] else 0
         last_step = None
-        for step, batch in enumerate(loader):
+        first = 0
+        sampler = getattr(train_data_loader, "batch_sampler", None)
+        if resume_step and not self._resume_replay and hasattr(sampler, "skip_batches"):
+            # resume: the sampler starts ``resume_step`` batches in, so consumed data is never read (the reference replays and discards it,
+            # eager_engine.py:347-349 — ``Engine.save_load.resume_replay: True`` keeps that, e.g. to reproduce host-side augmentation draws)
+            sampler.skip_batches = first = resume_step
+        for step, batch in enumerate(loader, first):
             if step < resume_step:
-                continue          # resume: replay the sampler and discard consumed batches (eager_engine.py:347-349)
+                continue          # replayed batch of a resumed run
             if self._rng_restore_pending:
                 # creating loader iterators and replaying consumed batches drew from the host generator (DataLoader base seed): put the streams
                 # back to the checkpointed state right before the first step that trains — in whichever epoch that is — so noise (dropout, MoE

@@ -29,6 +29,7 @@ class GPTBatchSampler(torch.utils.data.Sampler):
         self.shuffle = shuffle          # intentionally unused
         self.epoch = 0
         self.consumed_samples = int(consumed_samples)
+        self.skip_batches = 0           # one-shot: the next ``__iter__`` starts this many local batches in (resume without loading consumed data)
         self.total_size = len(dataset)
         per = self.total_size / self.nranks
         self.num_samples = int(math.floor(per) if drop_last else math.ceil(per))
@@ -40,7 +41,8 @@ class GPTBatchSampler(torch.utils.data.Sampler):
     def __iter__(self) -> Iterator[List[int]]:
         window = self.batch_size * self.nranks
         lo = self.local_rank * self.batch_size
-        pos = self.consumed_samples
+        skip, self.skip_batches = self.skip_batches, 0
+        pos = self.consumed_samples + skip * window
         while pos + window <= self.total_size:
             yield list(range(pos + lo, pos + lo + self.batch_size))
             pos += window
@@ -67,6 +69,7 @@ class DistributedBatchSampler(torch.utils.data.Sampler):
         self.nranks = env.get_data_world_size() if num_replicas is None else int(num_replicas)
         self.local_rank = env.get_data_world_rank() if rank is None else int(rank)
         self.epoch = 0
+        self.skip_batches = 0           # one-shot, as in GPTBatchSampler
         self.num_samples = int(math.ceil(len(dataset) / self.nranks))
         self.total_size = self.num_samples * self.nranks
 
@@ -83,6 +86,8 @@ class DistributedBatchSampler(torch.utils.data.Sampler):
             idx = list(range(n))
         idx += idx[: self.total_size - n]
         idx = idx[self.local_rank:self.total_size:self.nranks]
+        skip, self.skip_batches = self.skip_batches, 0
+        idx = idx[skip * self.batch_size:]
         batch = []
         for i in idx:
             batch.append(i)

@@ -206,3 +206,19 @@ def test_glue_split_names_select_their_files(tmp_path):
     (raw / "in_domain_train.tsv").write_text("s\t1\t*\tgood sentence\ns\t0\t*\tbad sentence\n")
     (raw / "in_domain_dev.tsv").write_text("s\t1\t*\tdev sentence\n")
     assert len(G.CoLA(root=str(tmp_path / "cola_public"), split="train")) == 2 and len(G.CoLA(root=str(tmp_path / "cola_public"), split="dev")) == 1
+
+
+def test_samplers_skip_consumed_batches_once():
+    """Resume support: ``skip_batches`` makes the next pass start that many local batches in (nothing before it is ever indexed); the pass after is full again."""
+    from paddlefleetx_b200.data.sampler.batch_sampler import DistributedBatchSampler, GPTBatchSampler
+
+    data = list(range(40))
+    for make in (lambda: GPTBatchSampler(data, batch_size=3, num_replicas=2, rank=1),
+                 lambda: DistributedBatchSampler(data, batch_size=3, num_replicas=2, rank=1, shuffle=True, seed=5)):
+        s = make()
+        full = list(s)
+        s.skip_batches = 2
+        assert list(s) == full[2:]
+        assert list(s) == full and len(s) == len(full)
+        s.skip_batches = len(full) + 3
+        assert list(s) == []
