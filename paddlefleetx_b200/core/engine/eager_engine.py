@@ -235,6 +235,10 @@ class EagerEngine(BasicEngine):
         self._module.model.train()
         train_cost = 0.0
         start_epoch = self._load_recovery["epoch"]
+        if self._run_mode == "epoch" and train_data_loader is not None and 0 < len(train_data_loader) <= self._load_recovery["step"]:
+            # an end-of-epoch checkpoint: that epoch (its evaluation, LR epoch step and save included) is done — continue with the next one
+            start_epoch += 1
+            self._load_recovery.update(epoch=start_epoch, step=0)
         self._restore_rng()
         for epoch_index in range(start_epoch, epoch):
             t0 = get_timestamp()

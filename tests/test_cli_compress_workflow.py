@@ -64,6 +64,25 @@ def test_vit_chain_train_export_classify(tmp_path):
     assert "top-5 classes:" in served
 
 
+def test_vit_resume_from_end_of_epoch_checkpoint_starts_the_next_epoch(tmp_path):
+    import re
+
+    vit = CPU + ["Model.model.img_size=32", "Model.model.patch_size=8", "Model.model.depth=2", "Distributed.dp_degree=1",
+                 "Data.Train.dataset.name=SyntheticImageDataset", "Data.Train.dataset.image_size=32", "Data.Train.dataset.num_samples=16",
+                 "Data.Eval.dataset.name=SyntheticImageDataset", "Data.Eval.dataset.image_size=32", "Data.Eval.dataset.num_samples=8", "Data.Eval.dataset.class_num=10",
+                 "Global.local_batch_size=4", "Global.micro_batch_size=4", "Data.Train.sampler.batch_size=4", "Data.Eval.sampler.batch_size=4",
+                 "Data.Train.loader.num_workers=0", "Data.Eval.loader.num_workers=0", "Engine.num_train_epochs=3", "Engine.logging_freq=1", "Engine.save_load.save_epoch=1"]
+    cfg = "vis/vit/ViT_tiny_patch16_224_ci_cifar10_1n8c_dp_fp16o2.yaml"
+
+    def losses(out):
+        return re.findall(r"\[train\] epoch: (\d+), step: \[(\d+)/4\].*?loss: ([0-9.]+)", out)
+
+    straight = losses(run("tools/train.py", cfg, vit + [f"Engine.save_load.output_dir={tmp_path}/a"]))
+    out = run("tools/train.py", cfg, vit + [f"Engine.save_load.output_dir={tmp_path}/b", f"Engine.save_load.ckpt_dir={tmp_path}/a/epoch_0_step_4"])
+    assert losses(out) == straight[4:] and len(straight) == 12
+    assert "[eval] epoch: 0" not in out and sorted(os.listdir(tmp_path / "b")) == ["epoch_1_step_4", "epoch_2_step_4"]
+
+
 def test_ernie_chain_export_serve_with_wordpiece_vocab(tmp_path):
     (tmp_path / "vocab.txt").write_text("\n".join(["[PAD]", "[CLS]", "[SEP]", "[MASK]", "[UNK]", "hello", "my", "dog", "is", "cute", ","]) + "\n")
     ernie = CPU + ["Model.num_hidden_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.vocab_size=512", "Model.max_position_embeddings=64"]
