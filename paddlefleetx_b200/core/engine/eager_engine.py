@@ -251,7 +251,10 @@ class EagerEngine(BasicEngine):
                 if self._lr_scheduler_mode == "epoch" and isinstance(self._lr_scheduler, LRScheduler):
                     self._lr_scheduler.step()
                 if valid_data_loader is not None and self._eval_freq and epoch_index % max(self._eval_freq, 1) == 0 and self._eval_freq > 0:
+                    e0 = get_timestamp()
                     self._evaluate_one_epoch(epoch_index, valid_data_loader)
+                    self._module.validation_epoch_end({"epoch": epoch_index, "eval_cost": get_timestamp() - e0})   # metric report (accuracy, F1, ...)
+                    self._module.model.train()
                 if self._save_epoch and (epoch_index + 1) % self._save_epoch == 0:
                     self.save(epoch=epoch_index, step=len(train_data_loader) if train_data_loader is not None else 0)
         if self._profiler is not None:
@@ -448,6 +451,10 @@ class EagerEngine(BasicEngine):
                 t0, losses = get_timestamp(), []
             if self._run_mode == "step" and self._eval_iters and step >= self._eval_iters - 1:
                 break
+        if losses:        # batches after the last full logging window (or an evaluation set shorter than one window)
+            vals = [float(l) for l in losses]
+            self._module.validation_step_end({"loss": sum(vals) / len(vals), "epoch": epoch_index, "batch": step, "total_batch": total,
+                                              "eval_cost": (get_timestamp() - t0) / len(vals)})
 
     @torch.no_grad()
     def _evaluate_impl(self, batch):

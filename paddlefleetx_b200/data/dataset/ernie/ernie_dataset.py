@@ -228,12 +228,19 @@ class SyntheticErnieDataset(torch.utils.data.Dataset):
 
 
 class ErnieSeqClsDataset(torch.utils.data.Dataset):
-    """TSV ``text[\\ttext_b]\\tlabel`` classification data, tokenised with a byte-level fallback when no vocab is configured."""
+    """TSV ``text[\\ttext_b]\\tlabel`` classification data.  ``tokenizer_type`` (a vocabulary directory or cached name, reference
+    ernie_dataset.py:328-334) selects the WordPiece tokenizer — rows then go through its pair encoding (``[CLS] a [SEP] b [SEP]``, longest-first
+    truncation); without it a byte-level fallback keeps the recipe runnable on a box with no vocabulary."""
 
     def __init__(self, dataset_type: str = "chnsenticorp_v2", input_dir: Optional[str] = None, path: Optional[str] = None, mode: str = "Train",
-                 max_seq_len: int = 128, tokenizer=None, cls_id: int = 1, sep_id: int = 2, pad_id: int = 0, **unused):
+                 max_seq_len: int = 128, tokenizer=None, tokenizer_type: Optional[str] = None, cls_id: int = 1, sep_id: int = 2, pad_id: int = 0, **unused):
         path = path or os.path.join(input_dir, {"Train": "train.tsv", "Eval": "dev.tsv", "Test": "test.tsv"}[mode])
         self.max_seq_len, self.cls_id, self.sep_id, self.pad_id = max_seq_len, cls_id, sep_id, pad_id
+        self.wordpiece = None
+        if tokenizer is None and tokenizer_type:
+            from ...tokenizers import get_ernie_tokenizer
+
+            self.wordpiece = tokenizer = get_ernie_tokenizer(tokenizer_type)
         if tokenizer is None:
             from ...tokenizers import GPTTokenizer
 
@@ -252,6 +259,9 @@ class ErnieSeqClsDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, i):
         a, b, y = self.rows[i]
+        if self.wordpiece is not None:
+            enc = self.wordpiece(a, text_pair=b, max_length=self.max_seq_len, truncation=True, return_token_type_ids=True)
+            return {"input_ids": np.asarray(enc["input_ids"], np.int64), "token_type_ids": np.asarray(enc["token_type_ids"], np.int64), "labels": np.asarray(y, np.int64)}
         ia = [t + 4 for t in self.tok.encode(a)]
         ib = [t + 4 for t in self.tok.encode(b)] if b else []
         budget = self.max_seq_len - (3 if ib else 2)

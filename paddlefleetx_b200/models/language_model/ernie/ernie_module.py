@@ -165,6 +165,33 @@ class ErnieSeqClsModule(ErnieModule):
             ids, seg, labels = batch[0], batch[1] if len(batch) > 2 else None, batch[-1]
         return self.loss_fn(self.model(ids, seg), labels)
 
+    def validation_step(self, batch):
+        """Loss like training, plus running accuracy reported once per evaluation pass (the reference module only trains,
+        ernie_module.py:344; a fine-tune without a dev-set score is hard to use)."""
+        if isinstance(batch, dict):
+            ids, seg, labels = batch["input_ids"], batch.get("token_type_ids"), batch["labels"]
+        else:
+            ids, seg, labels = batch[0], batch[1] if len(batch) > 2 else None, batch[-1]
+        logits = self.model(ids, seg)
+        hit = (logits.argmax(-1) == labels.reshape(-1)).sum()
+        self._hits = getattr(self, "_hits", 0) + hit
+        self._seen = getattr(self, "_seen", 0) + labels.numel()
+        return self.loss_fn(logits, labels)
+
+    def validation_epoch_end(self, log_dict):
+        seen = getattr(self, "_seen", 0)
+        if not seen:
+            return
+        stat = torch.stack([self._hits.double(), torch.tensor(float(seen), dtype=torch.float64, device=self._hits.device)])
+        if env.world_size() > 1 and env.get_data_world_size() > 1:      # every data replica scored its own slice of the dev set
+            from ....parallel import collective as C
+
+            C.all_reduce(stat, group=env.get_hcg().get_dp_sharding_group())
+        acc = float(stat[0] / stat[1])
+        self.best_metric = max(getattr(self, "best_metric", 0.0), acc)
+        logger.eval("[Eval] epoch: %d, total time: %.5f sec, accuracy: %.5f, best: %.5f" % (log_dict["epoch"], log_dict["eval_cost"], acc, self.best_metric))
+        self._hits, self._seen = 0, 0
+
 
 ErnieModuleAuto = ErnieModule
 ErnieSeqClsModuleAuto = ErnieSeqClsModule

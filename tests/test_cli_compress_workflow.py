@@ -83,6 +83,40 @@ def test_vit_resume_from_end_of_epoch_checkpoint_starts_the_next_epoch(tmp_path)
     assert "[eval] epoch: 0" not in out and sorted(os.listdir(tmp_path / "b")) == ["epoch_1_step_4", "epoch_2_step_4"]
 
 
+def test_ernie_finetune_cli_learns_a_tsv_task_and_reports_dev_accuracy(tmp_path):
+    """WordPiece vocabulary directory + ``text\\tlabel`` TSVs -> tools/train.py on the ERNIE fine-tune recipe: the schedule spans the epochs actually
+    run (not the pre-training base recipe's max_steps), the loss falls and every epoch ends with a dev-set accuracy line."""
+    import random
+    import re
+
+    rnd = random.Random(0)
+    words = ["good", "bad", "great", "awful", "movie", "film", "plot", "acting", "the", "was", "is", "very", "not", "i", "liked", "hated", "it"]
+    (tmp_path / "vocab").mkdir()
+    (tmp_path / "vocab" / "vocab.txt").write_text("\n".join(["[PAD]", "[CLS]", "[SEP]", "[MASK]", "[UNK]"] + words) + "\n")
+
+    def row():
+        pos = rnd.random() < 0.5
+        w = [rnd.choice(words[4:]) for _ in range(6)] + [rnd.choice(["good", "great", "liked"] if pos else ["bad", "awful", "hated"])]
+        rnd.shuffle(w)
+        return " ".join(w) + "\t" + str(int(pos))
+
+    (tmp_path / "data").mkdir()
+    for name, n in (("train.tsv", 64), ("dev.tsv", 16)):
+        (tmp_path / "data" / name).write_text("text_a\tlabel\n" + "\n".join(row() for _ in range(n)) + "\n")
+    opts = CPU + ["Model.num_hidden_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.vocab_size=64", "Model.max_position_embeddings=64",
+                  "Model.hidden_dropout_prob=0.0", "Model.attention_probs_dropout_prob=0.0", "Global.local_batch_size=8", "Global.micro_batch_size=8",
+                  "Engine.num_train_epochs=6", "Engine.logging_freq=8", "Optimizer.lr.learning_rate=3e-3", f"Engine.save_load.output_dir={tmp_path}/out"]
+    for split in ("Train", "Eval"):
+        opts += [f"Data.{split}.dataset.input_dir={tmp_path}/data", f"Data.{split}.dataset.tokenizer_type={tmp_path}/vocab", f"Data.{split}.dataset.max_seq_len=32",
+                 f"Data.{split}.sampler.batch_size=8", f"Data.{split}.loader.num_workers=0"]
+    out = run("tools/train.py", "nlp/ernie/finetune_ernie_345M_single_card.yaml", opts)
+    losses = [float(x) for x in re.findall(r"\[train\] epoch: \d+, batch: 7, loss: ([0-9.]+)", out)]
+    accs = [float(x) for x in re.findall(r"\[Eval\] epoch: \d+, .*accuracy: ([0-9.]+)", out)]
+    lrs = [float(x) for x in re.findall(r"learning rate: ([0-9.e+-]+)", out)]
+    assert len(losses) == 6 and len(accs) == 6 and losses[-1] < 0.6 < losses[0] and max(accs) >= 0.75
+    assert lrs[0] > 1e-3 and lrs[-1] == 0.0          # warm-up finished inside epoch 0; linear decay reaches zero at the last step
+
+
 def test_ernie_chain_export_serve_with_wordpiece_vocab(tmp_path):
     (tmp_path / "vocab.txt").write_text("\n".join(["[PAD]", "[CLS]", "[SEP]", "[MASK]", "[UNK]", "hello", "my", "dog", "is", "cute", ","]) + "\n")
     ernie = CPU + ["Model.num_hidden_layers=2", "Model.hidden_size=64", "Model.num_attention_heads=4", "Model.vocab_size=512", "Model.max_position_embeddings=64"]

@@ -28,8 +28,13 @@ def main(argv=None):
     train_loader = build_dataloader(cfg.Data, "Train")
     eval_loader = build_dataloader(cfg.Data, "Eval") if cfg.Engine.eval_freq and cfg.Engine.eval_freq > 0 and "Eval" in cfg.Data else None
     if isinstance(cfg.Optimizer.get("lr"), dict):
-        cfg.Optimizer.lr.update({"epochs": cfg.Engine.num_train_epochs, "step_each_epoch": len(train_loader),
-                                 "total_steps": cfg.Engine.max_steps})
+        total = cfg.Engine.max_steps
+        if cfg.Engine.get("run_mode", "step") == "epoch":
+            # an epoch-mode run ends after num_train_epochs passes: schedules must span that, not a max_steps inherited from a pre-training base
+            # recipe (the reference passes max_steps through unconditionally, tools/train.py:60-64, and the warm-up then never finishes)
+            span = cfg.Engine.num_train_epochs * len(train_loader)
+            total = min(total, span) if total and total > 0 else span
+        cfg.Optimizer.lr.update({"epochs": cfg.Engine.num_train_epochs, "step_each_epoch": len(train_loader), "total_steps": total})
         known = {"CosineAnnealingWithWarmupDecay": ("epochs", "step_each_epoch", "total_steps")}
         for k in known.get(cfg.Optimizer.lr.get("name"), ()):
             cfg.Optimizer.lr.pop(k, None)
