@@ -23,7 +23,8 @@ def main(argv=None):
     engine = EagerEngine(configs=cfg, module=module, mode="eval")
     if cfg.Engine.save_load.ckpt_dir is not None:
         engine.load()
-    engine.evaluate(valid_data_loader=loader, epoch=cfg.Engine.num_train_epochs)
+    # one pass: the checkpoint is fixed, so the reference's ``epoch=num_train_epochs`` (tools/eval.py:53) just repeats the same numbers
+    engine.evaluate(valid_data_loader=loader, epoch=int(cfg.Engine.get("eval_epochs", 1)))
     return engine
 
 
