@@ -171,7 +171,8 @@ class EagerEngine(BasicEngine):
             self._lr_scheduler_mode = "step"
             lr_cfg = configs.Optimizer.get("lr")
             if isinstance(lr_cfg, dict):
-                self._lr_scheduler_mode = lr_cfg.pop("run_mode", "step")
+                # per-epoch schedules say so with ``run_mode: epoch`` (reference moco recipes) — or just ``update_unit: epoch``
+                self._lr_scheduler_mode = lr_cfg.pop("run_mode", None) or ("epoch" if lr_cfg.get("update_unit") == "epoch" else "step")
                 lr_cfg_clean = {k: v for k, v in lr_cfg.items() if k not in ("_scaled_by_batch",)}
             else:
                 lr_cfg_clean = lr_cfg

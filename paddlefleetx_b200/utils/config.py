@@ -295,7 +295,10 @@ def print_config(cfg: AttrDict) -> None:
             elif isinstance(v, list) and v and isinstance(v[0], dict):
                 logger.info(f"{pad}{k} : ")
                 for item in v:
-                    walk(item, indent + 4)
+                    if isinstance(item, dict):
+                        walk(item, indent + 4)
+                    else:          # a bare op name among ``{op: {args}}`` entries (``- ToCHWImage``)
+                        logger.info(f"{pad}    {item}")
             else:
                 logger.info(f"{pad}{k} : {v}")
             if indent == 0:

@@ -83,6 +83,33 @@ def test_vit_resume_from_end_of_epoch_checkpoint_starts_the_next_epoch(tmp_path)
     assert "[eval] epoch: 0" not in out and sorted(os.listdir(tmp_path / "b")) == ["epoch_1_step_4", "epoch_2_step_4"]
 
 
+def test_moco_chain_pretrain_on_image_folder_then_linear_probe(tmp_path):
+    """PNG class folders -> MoCo v2 pre-training (two augmented views through the recipe's real transform stack, cosine LR advanced once per EPOCH)
+    -> linear probe on the frozen pre-trained backbone with a per-epoch top-1 report."""
+    import re
+
+    import numpy as np
+    from PIL import Image
+
+    rng = np.random.default_rng(0)
+    for split, n in (("train", 8), ("val", 4)):
+        for cls, col in (("cat", (200, 60, 60)), ("dog", (60, 60, 200))):
+            os.makedirs(tmp_path / "data" / split / cls)
+            for i in range(n):
+                px = np.clip(np.array(col)[None, None] + rng.normal(0, 30, (48, 56, 3)), 0, 255).astype(np.uint8)
+                Image.fromarray(px).save(tmp_path / "data" / split / cls / f"{i}.png")
+    base = CPU + ["Distributed.dp_degree=1", "Global.local_batch_size=4", "Global.micro_batch_size=4", "Data.Train.sampler.batch_size=4", "Data.Train.loader.num_workers=0",
+                  "Model.model.backbone=resnet18", "Engine.logging_freq=4", f"Data.Train.dataset.root={tmp_path}/data/train", "Data.Train.dataset.transform_ops.1.RandCropImage.size=32"]
+    out = run("tools/train.py", "vis/moco/mocov2_pt_in1k_1n8c.yaml", base + ["Model.model.K=16", "Model.model.dim=8", "Engine.num_train_epochs=3", "Engine.save_load.save_epoch=3",
+                                                                        f"Engine.save_load.output_dir={tmp_path}/pt"])
+    assert re.findall(r"learning rate: ([0-9.]+)", out) == ["0.0300000", "0.0225000", "0.0075000"]
+    out = run("tools/train.py", "vis/moco/moco_lincls_in1k_1n8c.yaml", base + [
+        "Data.Eval.sampler.batch_size=4", "Data.Eval.loader.num_workers=0", f"Data.Eval.dataset.root={tmp_path}/data/val", "Data.Eval.dataset.transform_ops.1.ResizeImage.resize_short=36",
+        "Data.Eval.dataset.transform_ops.2.CenterCropImage.size=32", "Model.model.class_num=2", f"Model.model.pretrained={tmp_path}/pt/epoch_2_step_4/model.pdparams",
+        "Optimizer.lr.learning_rate=0.001", "Engine.num_train_epochs=2", f"Engine.save_load.output_dir={tmp_path}/lc"])
+    assert len(re.findall(r"\[Eval\] epoch: \d, \{'top1'", out)) == 2 and set(re.findall(r"learning rate: ([0-9.]+)", out)) == {"0.0010000"}
+
+
 def test_ernie_finetune_cli_learns_a_tsv_task_and_reports_dev_accuracy(tmp_path):
     """WordPiece vocabulary directory + ``text\\tlabel`` TSVs -> tools/train.py on the ERNIE fine-tune recipe: the schedule spans the epochs actually
     run (not the pre-training base recipe's max_steps), the loss falls and every epoch ends with a dev-set accuracy line."""
