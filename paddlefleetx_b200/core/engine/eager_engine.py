@@ -57,6 +57,17 @@ def _split_micro(batch, n: int):
     return [batch] * n
 
 
+def _flatten_tensors(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _flatten_tensors(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _flatten_tensors(v)
+
+
 class _Prefetcher:
     """Wraps a host dataloader: batch i+1 is copied H2D on a side stream while step i computes."""
 
@@ -74,6 +85,13 @@ class _Prefetcher:
             if self.stream is not None:
                 torch.cuda.current_stream().wait_stream(self.stream)
             cur = nxt
+            if self.stream is not None:
+                # allocated on the side stream, consumed on the compute stream: tell the caching allocator, otherwise the side stream may
+                # recycle the block for a later batch while a backward kernel (embedding scatter) still reads it
+                compute = torch.cuda.current_stream()
+                for t in _flatten_tensors(cur):
+                    if t.is_cuda:
+                        t.record_stream(compute)
             nxt = self._load(it)
             yield cur
 
@@ -282,6 +300,8 @@ class EagerEngine(BasicEngine):
         last_step = None
         first = 0
         sampler = getattr(train_data_loader, "batch_sampler", None)
+        if hasattr(sampler, "set_epoch"):
+            sampler.set_epoch(epoch_index)      # a new shuffle every epoch (paddle.io.DistributedBatchSampler advances its epoch per pass)
         if resume_step and not self._resume_replay and hasattr(sampler, "skip_batches"):
             # resume: the sampler starts ``resume_step`` batches in, so consumed data is never read (the reference replays and discards it,
             # eager_engine.py:347-349 — ``Engine.save_load.resume_replay: True`` keeps that, e.g. to reproduce host-side augmentation draws)
@@ -300,16 +320,17 @@ class EagerEngine(BasicEngine):
             losses.append(loss)
             if self._heartbeat is not None:
                 self._heartbeat.beat(step)
+            found_inf = self._scaler.found_inf if (self._scaler is not None and self._amp_dtype == "float16") else False
+            if self._lr_scheduler_mode == "step" and isinstance(self._lr_scheduler, LRScheduler) and not found_inf:
+                self._lr_scheduler.step(epoch=self._global_batch_size if self._use_increments else None)
             if self._wd.emergency_requested():
                 if device.type == "cuda":
                     torch.cuda.synchronize()
                 logger.warning(f"emergency checkpoint at epoch {epoch_index} step {step + 1}, then stopping")
+                self._optimizer.clear_grad()
                 self.save(epoch=epoch_index, step=step + 1)
                 self._stop_requested = True
                 return
-            found_inf = self._scaler.found_inf if (self._scaler is not None and self._amp_dtype == "float16") else False
-            if self._lr_scheduler_mode == "step" and isinstance(self._lr_scheduler, LRScheduler) and not found_inf:
-                self._lr_scheduler.step(epoch=self._global_batch_size if self._use_increments else None)
 
             if (step + 1) % self._logging_freq == 0:
                 now = get_timestamp()
@@ -390,6 +411,8 @@ class EagerEngine(BasicEngine):
             with self._amp_ctx():
                 self._module.model._prepare_training(batch, self._optimizer, self._lr_scheduler)
                 loss = self._module.model.forward_backward_pipeline(batch, self._scaler)
+            if self._mp_degree > 1 and self._configs.Model.get("sequence_parallel", False):
+                allreduce_sequence_parallel_grads(self._module.model)      # LayerNorm / row-bias grads are sequence-partial on every stage
         self._optim_update_params()
         return loss
 

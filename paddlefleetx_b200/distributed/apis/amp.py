@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 class GradScaler:
     def __init__(self, enable: bool = True, init_loss_scaling: float = 32768.0, use_dynamic_loss_scaling: bool = True,
-                 incr_ratio: float = 2.0, decr_ratio: float = 0.5, incr_every_n_steps: int = 1000, decr_every_n_nan_or_inf: int = 2,
+                 incr_ratio: float = 2.0, decr_ratio: float = 0.5, incr_every_n_steps: int = 2000, decr_every_n_nan_or_inf: int = 1,
                  hcg=None):
         self._enable = enable
         self._scale = float(init_loss_scaling) if enable else 1.0

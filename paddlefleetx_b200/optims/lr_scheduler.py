@@ -60,7 +60,7 @@ class CosineAnnealingWithWarmupDecay(LRScheduler):
 
 
 class LinearDecayWithWarmup(LRScheduler):
-    """Linear warm-up to ``learning_rate`` over ``warmup`` (fraction if <1, else steps), then linear to 0 at
+    """Linear warm-up to ``learning_rate`` over ``warmup`` (fraction if <1, else steps), then ``lr * (1 - t / total_steps)``: linear to 0 at
     ``total_steps`` (= ``step_each_epoch * epochs`` injected by tools/train.py)."""
 
     def __init__(self, learning_rate: float, step_each_epoch: int = 1, epochs: int = 1, warmup: float = 0.0, total_steps: Optional[int] = None,
@@ -73,7 +73,7 @@ class LinearDecayWithWarmup(LRScheduler):
         t = self.last_epoch
         if self.warmup_steps > 0 and t < self.warmup_steps:
             return self.base_lr * t / self.warmup_steps
-        return self.base_lr * max(0.0, (self.total - t) / max(1, self.total - self.warmup_steps))
+        return self.base_lr * max(0.0, 1.0 - t / max(1, self.total))      # reference formula (optims/lr_scheduler.py:96-100): 1 - t/T_max
 
 
 class ViTLRScheduler(LRScheduler):

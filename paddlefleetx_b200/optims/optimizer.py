@@ -157,6 +157,7 @@ class FusedAdamW:
         self._found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._comm_stream = torch.cuda.Stream() if dev.type == "cuda" else None
+        C.register_side_stream(self._comm_stream)
         self._hooks = []
         if self.replicas > 1 or self.direct_grad:
             self._register_hooks()

@@ -231,11 +231,30 @@ def broadcast_params(module: torch.nn.Module, group, src_rank: int, skip_distrib
         dist.broadcast(t.data, src=src_rank, group=_pg(group))
 
 
+_SIDE_STREAMS: list = []      # communication streams whose in-flight gradient reductions touch the same buffers (optimizer bucket reducers)
+
+
+def register_side_stream(stream) -> None:
+    if stream is not None and stream not in _SIDE_STREAMS:
+        _SIDE_STREAMS.append(stream)
+
+
+def wait_side_streams() -> None:
+    """Order the current stream after every registered communication stream.  Post-backward collectives on gradient buffers
+    (tied-embedding all-reduce, sequence-parallel gradient all-reduce) call this first: with ``reduce_overlap`` the bucket
+    reduce-scatter / all-reduce of the same buffer may still be running on the side stream."""
+    if _SIDE_STREAMS and torch.cuda.is_available():
+        cur = torch.cuda.current_stream()
+        for s in _SIDE_STREAMS:
+            cur.wait_stream(s)
+
+
 def fused_allreduce_gradients(params, group, scale: Optional[float] = None) -> None:
     """Coalesced grad all-reduce (÷ nranks by default) — reference
     ``fused_allreduce_gradients[_with_group]`` (eager_engine.py:491-504)."""
     if not _active(group):
         return
+    wait_side_streams()
     grads = [p.grad if getattr(p, "main_grad", None) is None else p.main_grad for p in params]
     grads = [g for g in grads if g is not None]
     if not grads:

@@ -182,6 +182,7 @@ class PipelineLayer(nn.Module):
                 dist.broadcast(w.data, src=grp.ranks[0], group=grp.process_group)
 
     def allreduce_shared_weight_gradients(self) -> None:
+        C.wait_side_streams()       # an overlapped bucket reduction of the same gradient buffer may still be in flight
         for key, (grp, w) in self._shared_comm.items():
             if grp is None or grp.process_group is None:
                 continue

@@ -208,6 +208,13 @@ class GroupShardedStage3(nn.Module):
             self._release(u)
 
     def _reduce_unit(self, u: _Unit) -> None:
+        mp = self.hcg.get_model_parallel_group() if self.hcg is not None else None
+        if C.group_size(mp) > 1:
+            # sequence-parallel replicated parameters (LayerNorm, row-linear bias) hold sequence-partial gradients: sum them over the
+            # mp group while they are still attached (after the reduce-scatter ``p.grad`` is None and the engine-level pass skips them)
+            sp = [p for g in u.groups for p in g["params"] if getattr(p, "sequence_parallel", False) and p.grad is not None]
+            if sp:
+                C.fused_allreduce_gradients(sp, mp, scale=1.0)
         for g in u.groups:
             gf = g["grad_full"]
             if gf is None:

@@ -58,10 +58,25 @@ def _mark(p: nn.Parameter, **attrs) -> nn.Parameter:
 
 
 def _init_normal_sharded(weight: torch.Tensor, std: float, full_shape, shard_dim: int, group) -> None:
-    """Every TP rank draws its slice from its own RNG position (the reference seeds TP init per rank through
-    ``tensor_init_seed``); layouts are therefore equivalent in distribution, not bitwise."""
+    """Every TP rank draws its slice from its OWN stream: the tracker's ``local_seed`` (which ``env.set_seed`` derives from the mp
+    rank — the reference creates these weights inside the model-parallel RNG tracker, hybrid_model.py:139-196), or, when no tracker
+    stream is registered, a generator forked from the default seed by mp rank.  Drawing from the default generator would hand every
+    mp rank bit-identical shards (``global_seed`` does not depend on the mp rank and the initial broadcast skips TP-sharded tensors),
+    i.e. mp-fold duplicated neurons.  Layouts are equivalent in distribution, not bitwise."""
+    from .rng import get_rng_state_tracker
+
     with torch.no_grad():
-        weight.normal_(mean=0.0, std=std)
+        if C.group_size(group) == 1:
+            weight.normal_(mean=0.0, std=std)
+            return
+        tracker = get_rng_state_tracker()
+        if tracker.has("local_seed"):
+            with tracker.rng_state("local_seed"):
+                weight.normal_(mean=0.0, std=std)
+        else:
+            gen = torch.Generator(device=weight.device)
+            gen.manual_seed((torch.initial_seed() + 7919 * (C.group_rank(group) + 1)) & 0x7FFFFFFFFFFFFFFF)
+            weight.normal_(mean=0.0, std=std, generator=gen)
 
 
 class ColumnParallelLinear(nn.Module):
@@ -194,8 +209,7 @@ class VocabParallelEmbedding(nn.Module):
         self.per_rank = num_embeddings // self.world
         self.vocab_start = C.group_rank(mp_group) * self.per_rank
         self.weight = nn.Parameter(torch.empty(self.per_rank, embedding_dim, dtype=dtype, device=device))
-        with torch.no_grad():
-            self.weight.normal_(0.0, init_std)
+        _init_normal_sharded(self.weight, init_std, (num_embeddings, embedding_dim), 0, mp_group)
         _mark(self.weight, tp_sharded=self.world > 1, split_axis=0)
 
     def forward(self, ids: torch.Tensor) -> torch.Tensor:

@@ -117,8 +117,37 @@ def tp_matches_single(rank, world, sequence_parallel):
         assert torch.allclose(p.detach(), want, atol=1e-4, rtol=1e-3), (k, (p.detach() - want).abs().max())
 
 
-def pipeline_matches_single(rank, world, pp, mp, vpp, acc):
-    """pp (x mp) pipeline with tied embeddings reproduces the single-process loss curve."""
+def tp_shards_differ_across_ranks(rank, world):
+    """From-scratch tensor-parallel init: every mp rank must draw a DIFFERENT slice (identical shards = duplicated neurons)."""
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models import build_module
+
+    cfg = tiny_gpt_config(["Global.global_batch_size=None", "Global.local_batch_size=2", "Global.micro_batch_size=2",
+                           f"Distributed.mp_degree={world}"], nranks=world)
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    module = build_module(cfg)
+    checked = 0
+    for n, p in module.model.named_parameters():
+        if not getattr(p, "tp_sharded", False) or p.ndim < 2:
+            continue
+        parts = [torch.empty_like(p.detach()) for _ in range(world)]
+        dist.all_gather(parts, p.detach().contiguous())
+        assert not torch.equal(parts[0], parts[1]), f"{n}: identical shards on mp ranks 0 and 1"
+        checked += 1
+    assert checked >= 4, checked
+    # replicated tensors still agree inside the mp group
+    for n, p in module.model.named_parameters():
+        if getattr(p, "tp_sharded", False):
+            continue
+        parts = [torch.empty_like(p.detach()) for _ in range(world)]
+        dist.all_gather(parts, p.detach().contiguous())
+        assert torch.equal(parts[0], parts[1]), n
+
+
+def pipeline_matches_single(rank, world, pp, mp, vpp, acc, sp=False):
+    """pp (x mp, optionally with Megatron sequence parallelism) pipeline with tied embeddings reproduces the single-process loss curve
+    AND the single-process weights (sequence-partial LayerNorm / bias gradients must be summed over the mp group on every stage)."""
     from paddlefleetx_b200.core import EagerEngine
     from paddlefleetx_b200.distributed.apis import env
     from paddlefleetx_b200.models import build_module
@@ -132,6 +161,8 @@ def pipeline_matches_single(rank, world, pp, mp, vpp, acc):
                    f"Distributed.pp_degree={pp}", f"Distributed.mp_degree={mp}"]
     if vpp > 1:
         ov.append(f"Model.virtual_pp_degree={vpp}")
+    if sp:
+        ov.append("Model.sequence_parallel=True")
     cfg = tiny_gpt_config(ov, nranks=world)
     env.init_dist_env(cfg)
     env.set_seed(cfg.Global.seed)
@@ -157,7 +188,16 @@ def pipeline_matches_single(rank, world, pp, mp, vpp, acc):
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 3e-4, (rank, losses, ref_losses)
     # with tensor parallelism every stage-boundary tensor travels as a 1/mp slice + an all-gather on the receiving side
     p2p = eng._module.model._p2p if hasattr(eng._module.model, "_p2p") else eng._dist_model._p2p
-    assert p2p.partial == (mp > 1) and (p2p.partial_transfers > 0) == (mp > 1), (mp, p2p.partial, p2p.partial_transfers)
+    if not sp:       # SP activations are already sequence shards: partial send/recv is off (reference utils/config.py:112-119)
+        assert p2p.partial == (mp > 1) and (p2p.partial_transfers > 0) == (mp > 1), (mp, p2p.partial, p2p.partial_transfers)
+    # every parameter of this stage (replicated LayerNorm / bias included) followed the single-process trajectory
+    ref_pipe = gpt_plain_to_pipe(ref_state, L)
+    for n, p in pipe.named_parameters():
+        key = re.sub(r"^_model_chunks\.\d+\.", "layers.", n)
+        if n.startswith("shared_layers.") and "word_embeddings" not in n and hcg.get_stage_id() != 0:
+            continue      # the last stage's copy of the embedding block only lends its (tied) word-embedding matrix to the LM head
+        want = _shard_like(ref_pipe[key], p, hcg.get_model_parallel_rank(), mp)
+        assert torch.allclose(p.detach(), want, atol=1e-4, rtol=1e-3), (n, (p.detach() - want).abs().max())
     # tied embedding stays identical on first and last stage
     if "embed" in pipe.shared_layers:
         w = pipe.shared_layers["embed"].word_embeddings.weight.detach()

@@ -42,6 +42,14 @@ def test_pipeline_pp2_mp2_matches_single():
     run_distributed("dist_fns:pipeline_matches_single", 4, 2, 2, 1, 4)
 
 
+def test_pipeline_pp2_mp2_sequence_parallel_matches_single():
+    run_distributed("dist_fns:pipeline_matches_single", 4, 2, 2, 1, 4, True)
+
+
+def test_tensor_parallel_init_differs_across_mp_ranks():
+    run_distributed("dist_fns:tp_shards_differ_across_ranks", 2)
+
+
 def test_pipeline_interleaved_pp2_vpp2_matches_single():
     run_distributed("dist_fns:pipeline_matches_single", 2, 2, 1, 2, 4)
 

@@ -29,7 +29,7 @@ def test_fixed_schedulers():
     vals = []
     for _ in range(100):
         vals.append(lin()); lin.step()
-    assert vals[0] == 0.0 and abs(vals[10] - 1.0) < 1e-9 and vals[-1] < 0.02
+    assert vals[0] == 0.0 and abs(vals[10] - 0.9) < 1e-9 and vals[-1] < 0.02      # reference: lr * (1 - t / T_max) after warm-up
     cd = L.CosineDecay(1.0, step_each_epoch=5, epochs=4, update_unit="step", warmups=1)
     assert cd() == pytest.approx(1 / 5)
     ms = L.MultiStepDecay(1.0, [2, 4], 0.1)
