@@ -35,7 +35,9 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_library"],
+                   help="reference = the unmodified PaddleFleetX tree (needs Paddle); torch_library = a clearly-labelled stock-PyTorch arm "
+                        "(cuBLAS + SDPA + torch fused AdamW + NCCL DDP) of the same model/config, NOT a substitute for the reference")
     p.add_argument("--model", default="gpt-6.7b", choices=sorted(MODELS))
     p.add_argument("--layout", default="auto", help="auto | sharding | mp2_pp2_sharding2 | dp | mpN")
     p.add_argument("--local-batch", type=int, default=8)
@@ -43,9 +45,9 @@ def parse():
     p.add_argument("--recompute", default="auto", help="auto | none | full | full_attn | core_attn")
     p.add_argument("--seq-len", type=int, default=1024)
     p.add_argument("--no-e2e", action="store_true")
-    p.add_argument("--p2p", type=int, default=-1, help="peer-memory ZeRO kernels: -1 auto, 0 off, 1 on")
+    p.add_argument("--p2p", type=int, default=-1, help="ZeRO traffic through our symmetric-memory kernels (NVLS multimem / peer stores): -1 auto (on for N > 1), 0 = NCCL, 1 on")
     p.add_argument("--fused-tp", type=int, default=0, help="1: all-gather->GEMM and GEMM->reduce-scatter as single kernels (TP+SP layouts)")
-    p.add_argument("--step-overlap", type=int, default=0, help="1: AdamW update issued per bucket on the side stream underneath the next forward pass")
+    p.add_argument("--step-overlap", type=int, default=-1, help="AdamW update issued per bucket on the side stream underneath the next forward pass: -1 auto (on), 0 off, 1 on")
     p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the result invalid)")
     return p.parse_args()
 
@@ -133,7 +135,7 @@ def build_config(args, world: int):
         f"Global.local_batch_size={local}", f"Global.micro_batch_size={micro}", "Global.global_batch_size=None",
         f"Distributed.dp_degree={dp}", f"Distributed.mp_degree={mp}", f"Distributed.pp_degree={pp}",
         f"Distributed.sharding.sharding_degree={sharding}", f"Distributed.sharding.sharding_stage={stage}",
-        f"Distributed.sharding.reduce_overlap={world > 1}", f"Distributed.sharding.broadcast_overlap={world > 1}", f"Distributed.sharding.use_p2p={bool(args.p2p) if args.p2p >= 0 else False}",
+        f"Distributed.sharding.reduce_overlap={world > 1}", f"Distributed.sharding.broadcast_overlap={world > 1}", f"Distributed.sharding.use_p2p={bool(args.p2p) if args.p2p >= 0 else world > 1}",
         f"Model.use_recompute={recompute != 'none'}", f"Model.recompute_granularity={'full' if recompute == 'none' else recompute}",
         f"Model.sequence_parallel={mp > 1}",
         "Engine.max_steps=1000000", "Engine.eval_freq=-1", "Engine.eval_iters=0", "Engine.logging_freq=1000000",
@@ -142,7 +144,7 @@ def build_config(args, world: int):
     ]
     if args.layers:
         ov.append(f"Model.num_layers={args.layers}")
-    if args.step_overlap:
+    if args.step_overlap != 0:
         ov.append("Optimizer.step_overlap=True")
     if args.fused_tp:
         ov.append("Fused.tp_comm=True")
@@ -159,6 +161,10 @@ def main():
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.impl == "torch_library":
+        from tools.torch_library_baseline import run as run_library
+
+        return run_library(args, MODELS[args.model], ClockSampler)
     import torch
     import torch.distributed as dist
 
@@ -216,8 +222,11 @@ def main():
     if sampler:
         sampler.start()
     OF.reset_launch_count()
+    opt = engine._optimizer
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if hasattr(opt, "comm_meter_start"):
+        opt.comm_meter_start()
     e0.record()
     for i in range(args.steps):
         loss = device_step(i)
@@ -225,6 +234,11 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = OF.native_launch_count()
+    exposed = opt.comm_meter_read() / args.steps if hasattr(opt, "comm_meter_read") else None
+    if exposed is not None and world > 1:
+        te = torch.tensor([exposed], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        exposed = float(te.item())
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,6 +264,15 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
     clocks = sampler.stop() if sampler else None
 
+    symm = getattr(opt, "_symm", None)
+    if world == 1:
+        collective = "none (1 GPU); exposed_comm = compute-stream waits on the side-stream AdamW update"
+    elif getattr(opt, "use_p2p", False):
+        collective = ("own kernels over symmetric memory: " + ("NVLS multimem.ld_reduce reduce-scatter + AdamW with multimem.st broadcast"
+                      if getattr(symm, "multicast", False) else "unicast peer pull reduce-scatter + AdamW with peer-store broadcast")
+                      + "; NCCL only for the scalar grad-norm all-reduce" + (" and TP/PP traffic" if lay["mp"] > 1 or lay["pp"] > 1 else ""))
+    else:
+        collective = "NCCL"
     if rank == 0:
         tokens = global_batch * seq * args.steps
         par = {"single": "single", "sharding": f"sharding{world}_stage1", "dp": f"dp{world}",
@@ -264,8 +287,9 @@ def main():
             "config": {"model": args.model if not args.layers else f"{args.model}-DEBUG-{args.layers}layers(INVALID)",
                        "global_batch": global_batch, "seq_len": seq, "parallelism": par, "local_batch": lay["local"],
                        "micro_batch": lay["micro"], "recompute": lay["recompute"], "dropout": cfg.Model.hidden_dropout_prob,
-                       "optimizer": "FusedAdamW fp32 master + clip" + (" (update overlapped with the next forward)" if args.step_overlap else ""), "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
+                       "optimizer": "FusedAdamW fp32 master + clip" + (" (update overlapped with the next forward)" if getattr(opt, "step_overlap", False) else ""), "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "final_loss": final_loss,
+            "collective": collective, "exposed_comm_ms_per_step": exposed,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         }
         print(json.dumps(out))

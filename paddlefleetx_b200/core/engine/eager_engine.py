@@ -26,6 +26,7 @@ from ...distributed.apis.strategy import wrap_with_fleet
 from ...optims import build_lr_scheduler, build_optimizer
 from ...optims.lr_scheduler import LRScheduler
 from ...parallel.rng import get_rng_state_tracker
+from ...parallel import comm_ops as C
 from ...parallel.tp_layers import allreduce_sequence_parallel_grads
 from ...utils.log import get_timestamp, logger
 from ..module.basic_module import BasicModule
@@ -433,6 +434,7 @@ class EagerEngine(BasicEngine):
                 if n > 1:
                     loss_bw = loss_bw / n
                 bw_ctx = self._module.model.backward_phase() if hasattr(self._module.model, "backward_phase") else _Null()
+                C.run_pre_backward()       # leftover side-stream parameter updates (modules that did not run this step) finish first
                 with bw_ctx:
                     self._module.backward(loss_bw)
             d = loss.detach()

@@ -8,6 +8,7 @@
 
 #include "pfx_gemm.h"
 #include "pfx_kernels.h"
+#include "pfx_symm.h"
 
 namespace {
 
@@ -460,6 +461,88 @@ void adamw_p2p_broadcast_(const std::vector<int64_t>& peer_param_bufs, int64_t s
                                           dtype_code(grad), (int)lp_dtype, (int)peer_param_bufs.size(), (int)num_ctas, cur_stream()));
 }
 
+// ------------------------------------------------------------------------------- symmetric memory (cuMem VMM + multicast)
+py::dict vmm_caps() {
+  const pfx::vmm::Caps c = pfx::vmm::query_caps();
+  py::dict d;
+  d["vmm"] = c.vmm; d["fd_export"] = c.fd_export; d["multicast"] = c.multicast; d["granularity"] = (int64_t)c.granularity;
+  return d;
+}
+int64_t vmm_mc_granularity(int64_t world, int64_t bytes, bool recommended) {
+  return (int64_t)pfx::vmm::multicast_granularity((int)world, (size_t)bytes, recommended);
+}
+py::tuple vmm_arena_alloc(int64_t bytes) {
+  int64_t ptr = 0; int fd = -1; std::string err;
+  TORCH_CHECK(pfx::vmm::arena_alloc((size_t)bytes, &ptr, &fd, &err), "pfx vmm: ", err);
+  return py::make_tuple(ptr, (int64_t)fd);
+}
+int64_t vmm_arena_import(int64_t fd, int64_t bytes) {
+  int64_t ptr = 0; std::string err;
+  TORCH_CHECK(pfx::vmm::arena_import((int)fd, (size_t)bytes, &ptr, &err), "pfx vmm: ", err);
+  return ptr;
+}
+py::tuple vmm_mc_create(int64_t bytes, int64_t world) {
+  int64_t id = 0; int fd = -1; std::string err;
+  TORCH_CHECK(pfx::vmm::mc_create((size_t)bytes, (int)world, &id, &fd, &err), "pfx vmm: ", err);
+  return py::make_tuple(id, (int64_t)fd);
+}
+int64_t vmm_mc_import(int64_t fd) {
+  int64_t id = 0; std::string err;
+  TORCH_CHECK(pfx::vmm::mc_import((int)fd, &id, &err), "pfx vmm: ", err);
+  return id;
+}
+void vmm_mc_add_device(int64_t id) {
+  std::string err;
+  TORCH_CHECK(pfx::vmm::mc_add_device(id, &err), "pfx vmm: ", err);
+}
+int64_t vmm_mc_bind_and_map(int64_t id, int64_t arena_ptr, int64_t bytes) {
+  int64_t ptr = 0; std::string err;
+  TORCH_CHECK(pfx::vmm::mc_bind_and_map(id, arena_ptr, (size_t)bytes, &ptr, &err), "pfx vmm: ", err);
+  return ptr;
+}
+void vmm_unmap(int64_t ptr) { pfx::vmm::unmap(ptr); }
+
+static std::vector<void*> to_ptrs2(const std::vector<int64_t>& v) {
+  std::vector<void*> out;
+  for (auto x : v) out.push_back(reinterpret_cast<void*>((uintptr_t)x));
+  return out;
+}
+void nvls_barrier(int64_t mc_flag, int64_t local_flag, int64_t target) {
+  PFX_CUDA_CHECK(pfx::nvls_barrier(reinterpret_cast<uint32_t*>((uintptr_t)mc_flag), reinterpret_cast<uint32_t*>((uintptr_t)local_flag),
+                                   (uint32_t)target, cur_stream()));
+}
+void p2p_flag_barrier(const std::vector<int64_t>& peer_flags, int64_t rank, int64_t epoch) {
+  auto pp = to_ptrs2(peer_flags);
+  PFX_CUDA_CHECK(pfx::p2p_flag_barrier(reinterpret_cast<uint32_t**>(pp.data()), (int)rank, (int)pp.size(), (uint32_t)epoch, cur_stream()));
+}
+// out = scale * sum over ranks of bucket[shard_offset : shard_offset + out.numel()]; mc_src = 0 selects the unicast pull
+void symm_reduce_scatter(int64_t mc_src, const std::vector<int64_t>& peer_src, int64_t shard_offset, at::Tensor& out, int64_t rank, int64_t in_dtype,
+                         double scale, bool accumulate, c10::optional<at::Tensor> sumsq, int64_t num_ctas) {
+  auto pp = to_ptrs2(peer_src);
+  float* sq = (sumsq.has_value() && sumsq->defined()) ? sumsq->data_ptr<float>() : nullptr;
+  PFX_CUDA_CHECK(pfx::symm_reduce_scatter(reinterpret_cast<const void*>((uintptr_t)mc_src), pp.empty() ? nullptr : pp.data(), (size_t)shard_offset,
+                                          out.data_ptr(), (size_t)out.numel(), (int)rank, (int)pp.size(), (int)in_dtype, dtype_code(out),
+                                          (float)scale, accumulate, sq, (int)num_ctas, cur_stream()));
+}
+void symm_all_gather(int64_t mc_dst, const std::vector<int64_t>& peer_dst, int64_t dst_offset_bytes, const at::Tensor& src, int64_t rank,
+                     int64_t num_ctas) {
+  auto pp = to_ptrs2(peer_dst);
+  PFX_CUDA_CHECK(pfx::symm_all_gather(reinterpret_cast<void*>((uintptr_t)mc_dst), pp.empty() ? nullptr : pp.data(), (size_t)dst_offset_bytes,
+                                      src.data_ptr(), (size_t)src.numel() * src.element_size(), (int)rank, (int)pp.size(), (int)num_ctas, cur_stream()));
+}
+void adamw_symm_broadcast_(int64_t mc_params, const std::vector<int64_t>& peer_params, int64_t shard_offset, at::Tensor& master, const at::Tensor& grad,
+                           at::Tensor& m, at::Tensor& v, double lr, double beta1, double beta2, double eps, double wd, int64_t step,
+                           c10::optional<at::Tensor> gscale, c10::optional<at::Tensor> found_inf, int64_t lp_dtype, int64_t rank, int64_t num_ctas) {
+  auto pp = to_ptrs2(peer_params);
+  const float bc1 = 1.0 - std::pow(beta1, (double)step), bc2 = 1.0 - std::pow(beta2, (double)step);
+  PFX_CUDA_CHECK(pfx::adamw_symm_broadcast(reinterpret_cast<void*>((uintptr_t)mc_params), pp.empty() ? nullptr : pp.data(), (size_t)shard_offset,
+                                           master.data_ptr<float>(), grad.data_ptr(), m.data_ptr<float>(), v.data_ptr<float>(), (size_t)master.numel(),
+                                           (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, bc1, bc2,
+                                           (gscale.has_value() && gscale->defined()) ? gscale->data_ptr<float>() : nullptr,
+                                           (found_inf.has_value() && found_inf->defined()) ? found_inf->data_ptr<float>() : nullptr,
+                                           dtype_code(grad), (int)lp_dtype, (int)rank, (int)pp.size(), (int)num_ctas, cur_stream()));
+}
+
 at::Tensor gemv_skinny(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> bias) {
   TORCH_CHECK(x.is_cuda() && x.dim() == 2 && w.dim() == 2 && x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1), "gemv_skinny: x [M,K], w [N,K]");
   TORCH_CHECK(x.scalar_type() == w.scalar_type(), "gemv_skinny: dtype mismatch");
@@ -651,4 +734,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("moe_dispatch", &moe_dispatch);
   m.def("moe_combine", &moe_combine);
   m.def("adamw_p2p_broadcast_", &adamw_p2p_broadcast_);
+  m.def("vmm_caps", &vmm_caps);
+  m.def("vmm_mc_granularity", &vmm_mc_granularity);
+  m.def("vmm_arena_alloc", &vmm_arena_alloc);
+  m.def("vmm_arena_import", &vmm_arena_import);
+  m.def("vmm_mc_create", &vmm_mc_create);
+  m.def("vmm_mc_import", &vmm_mc_import);
+  m.def("vmm_mc_add_device", &vmm_mc_add_device);
+  m.def("vmm_mc_bind_and_map", &vmm_mc_bind_and_map);
+  m.def("vmm_unmap", &vmm_unmap);
+  m.def("nvls_barrier", &nvls_barrier);
+  m.def("p2p_flag_barrier", &p2p_flag_barrier);
+  m.def("symm_reduce_scatter", &symm_reduce_scatter);
+  m.def("symm_all_gather", &symm_all_gather);
+  m.def("adamw_symm_broadcast_", &adamw_symm_broadcast_);
 }

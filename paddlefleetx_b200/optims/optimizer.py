@@ -14,8 +14,11 @@ Layout: parameters are packed by ``parallel/flat_buffer.py`` into buckets; every
 the sharding group, rank r owning slice r of every bucket (so a bucket can be reduce-scattered as soon as its
 gradients are complete, while backward is still running).  On CUDA one step is, per bucket: [reduce-scatter]
 -> sumsq kernel -> (one tiny all-reduce) -> clip-coefficient kernel -> fused AdamW kernel -> [all-gather];
-the clip coefficient and found-inf flag never visit the host.  With ``use_p2p`` the reduce-scatter and the
-AdamW+broadcast run as peer-memory kernels over NVLink (csrc/comm_p2p.cu) instead of NCCL calls.
+the clip coefficient and found-inf flag never visit the host.  With ``use_p2p`` (the CUDA multi-GPU default) the buckets live in
+symmetric memory (parallel/symmetric_memory.py) and the ZeRO traffic runs through our own kernels (csrc/comm_nvls.cu): the
+reduce-scatter is an in-switch reduction (``multimem.ld_reduce``) that also emits the gradient-norm partial, and AdamW stores the
+new low-precision weights once to the multicast address (update + all-gather in one kernel), bucket by bucket underneath the next
+forward pass.  Those kernels fit on an SM next to a persistent GEMM CTA, which NCCL's do not.
 """
 from __future__ import annotations
 
@@ -32,6 +35,9 @@ from ..parallel.flat_buffer import FlatGroup, attach_grad_views, build_flat_grou
 from ..utils.log import logger
 from .grad_clip import ClipGradByGlobalNorm, ClipGradForMOEByGlobalNorm
 from .lr_scheduler import LRScheduler
+
+
+_DTYPE_CODE = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 3}
 
 
 def default_decay_fn(name: str, p: torch.nn.Parameter) -> bool:
@@ -85,7 +91,11 @@ class FusedAdamW:
         # forward pre-hook waits only for its own buckets, so all but the first bucket's update (bandwidth-bound, ~16 B/parameter streamed)
         # runs underneath the compute-bound GEMMs of the next forward pass instead of in front of it.  Needs direct gradient writes (no
         # memset of the gradient buffer between step and backward) and the device-resident native update.
-        self.step_overlap = bool(step_overlap) and named[0][1].is_cuda and not self.offload and not self.use_p2p
+        self.step_overlap = (bool(step_overlap) or self.use_p2p) and named[0][1].is_cuda and not self.offload
+        import os as _os
+
+        self._rs_ctas = int(_os.environ.get("PFX_RS_CTAS", "64"))
+        self._bcast_ctas = int(_os.environ.get("PFX_BCAST_CTAS", "296"))
 
         # ---- bucket assignment (reverse registration order: last layers finish backward first)
         bucket_bytes = bucket_mb * 1024 * 1024 if (self.replicas > 1 or self.step_overlap) else (1 << 62)
@@ -109,9 +119,9 @@ class FusedAdamW:
         alloc = None
         self._symm = None
         if self.use_p2p:
-            from ..parallel.symmetric_memory import SymmetricAllocator
+            from ..parallel.symmetric_memory import get_allocator
 
-            self._symm = SymmetricAllocator(self.sh_group)
+            self._symm = get_allocator(self.sh_group)
             alloc = self._symm.alloc_tensor
         self.groups: List[FlatGroup] = build_flat_groups(params, key_fn, pad_multiple=self.sh_world, grad_dtype=grad_dtype, alloc_fn=alloc)
         self.groups.sort(key=lambda g: (g.key[0] if g.key[0] >= 0 else 1 << 30))
@@ -152,17 +162,51 @@ class FusedAdamW:
             if self.use_p2p:
                 g.meta["peer_grads"] = self._symm.peer_ptrs(g.grad_buf)
                 g.meta["peer_params"] = self._symm.peer_ptrs(g.param_buf)
+                g.meta["mc_grads"] = self._symm.mc_ptr(g.grad_buf)        # 0 when the fabric has no NVLS: unicast pull / push
+                g.meta["mc_params"] = self._symm.mc_ptr(g.param_buf)
         self._sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gscale = torch.ones(1, dtype=torch.float32, device=dev)
         self._found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self._comm_stream = torch.cuda.Stream() if dev.type == "cuda" else None
         C.register_side_stream(self._comm_stream)
+        C.register_pre_backward(self.finish_param_sync)
         self._hooks = []
         if self.replicas > 1 or self.direct_grad:
             self._register_hooks()
         self._ag_events: Dict[int, "torch.cuda.Event"] = {}
         self._fwd_hooks_installed = False
+
+    # ------------------------------------------------------------------ exposed-communication accounting
+    def comm_meter_start(self) -> None:
+        """Start measuring how long the COMPUTE stream is blocked on the communication stream (gradient reduce-scatter not finished
+        when the step needs it, parameter update / all-gather of a bucket not landed when its layer runs).  Every such wait is
+        bracketed by two CUDA events on the compute stream: the first completes when the preceding compute work is done, the second when
+        the wait is satisfied, so their distance is pure exposed time — 0 when the side stream was ahead."""
+        self._meter = []
+
+    def comm_meter_read(self) -> float:
+        """Milliseconds of exposed waits since ``comm_meter_start`` (synchronises the device) and stops the meter."""
+        pairs, self._meter = (self._meter or []), None
+        if pairs:
+            torch.cuda.synchronize()
+        return float(sum(a.elapsed_time(b) for a, b in pairs))
+
+    def _wait(self, what) -> None:
+        """Make the current (compute) stream wait for a stream or event; metered when the meter is on."""
+        cur = torch.cuda.current_stream()
+        meter = getattr(self, "_meter", None)
+        if meter is not None:
+            a = torch.cuda.Event(enable_timing=True)
+            a.record(cur)
+        if isinstance(what, torch.cuda.Stream):
+            cur.wait_stream(what)
+        else:
+            cur.wait_event(what)
+        if meter is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record(cur)
+            meter.append((a, b))
 
     # ------------------------------------------------------------------ basic API
     @property
@@ -259,14 +303,17 @@ class FusedAdamW:
             stream_ctx.__enter__()
         try:
             if self.sh_world > 1:
-                if self.use_p2p and g.grad_buf.dtype != torch.float32:
-                    # pull reduce-scatter over NVLink: rank r reads slice r of every peer's bucket and writes the
-                    # fp32-accumulated sum back into slice r of its own bucket (nobody else reads that slice)
+                if self.use_p2p:
+                    # rank r reduces slice r of every rank's bucket — in the switch (multimem.ld_reduce) or by pulling over the
+                    # unicast mappings — and writes the sum back into slice r of its own bucket (nobody else reads that slice).
+                    # One barrier in front (every rank's gradients of this bucket are complete); the barrier behind every AdamW
+                    # broadcast of the same step is what protects the buckets against the next backward pass.
                     self._symm.barrier()
-                    _native.require().p2p_reduce_scatter(g.meta["peer_grads"], g.grad_buf[lo:hi], self.sh_rank,
-                                                         1 if g.grad_buf.dtype == torch.bfloat16 else 0, False, 1.0, 128)
-                    self._symm.barrier()
-                    OF._count(3)
+                    fuse_sq = self._norm_counted(g) and self.dp_world == 1
+                    _native.require().symm_reduce_scatter(g.meta["mc_grads"], g.meta["peer_grads"], lo, g.grad_buf[lo:hi], self.sh_rank,
+                                                          _DTYPE_CODE[g.grad_buf.dtype], 1.0, False, self._sq if fuse_sq else None, self._rs_ctas)
+                    g.meta["sq_fused"] = fuse_sq
+                    OF._count(2)
                 else:
                     self._nccl_rs(g)
             if self.dp_world > 1 and self.dp_group.process_group is not None:
@@ -275,6 +322,12 @@ class FusedAdamW:
             if stream_ctx is not None:
                 stream_ctx.__exit__(None, None, None)
         g.meta["synced"] = True
+
+    def _norm_counted(self, g: FlatGroup) -> bool:
+        """Does this group enter the (dense) global gradient norm on this rank?  TP-sharded tensors count on every mp rank,
+        replicated ones on mp rank 0 only, tied pipeline duplicates never; expert groups have their own norm."""
+        mp_rank = self.hcg.get_model_parallel_rank() if self.hcg is not None else 0
+        return bool((g.key[2] or mp_rank == 0) and not g.key[4] and not g.key[3])
 
     def _nccl_rs(self, g: FlatGroup) -> None:
         lo, hi = g.meta["lo"], g.meta["hi"]
@@ -302,7 +355,7 @@ class FusedAdamW:
         lr = self.get_lr()
         self._step_count += 1
         if self._comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            self._wait(self._comm_stream)
         for g in self.groups:
             self._sync_group_grads(g)
         native = self._dev.type == "cuda" and _native.use_native(self.groups[0].param_buf)
@@ -310,15 +363,13 @@ class FusedAdamW:
         inv_scale = 1.0 / (self.loss_scale * self.replicas)
         clip_norm = self.grad_clip.clip_norm if self.grad_clip is not None else 0.0
 
-        # ---- global grad norm over the local shards (+ groups)
-        mp_rank = self.hcg.get_model_parallel_rank() if self.hcg is not None else 0
+        # ---- global grad norm over the local shards (+ groups).  ``self._sq`` is zeroed right after it was consumed (end of the
+        # previous step), so the symmetric-memory reduce-scatter kernels of THIS step have already added their shards' partials.
         moe_sq = None
         if native:
             lib = _native.require()
-            self._sq.zero_()
             for g in self.groups:
-                counted = (g.key[2] or g.key[3] or mp_rank == 0) and not g.key[4]
-                if counted and not g.key[3]:
+                if self._norm_counted(g) and not g.meta.pop("sq_fused", False):
                     lib.sumsq_(g.grad_buf[g.meta["lo"]:g.meta["hi"]], self._sq, True)
                     OF._count(2)
             sq = self._sq
@@ -328,6 +379,7 @@ class FusedAdamW:
                     if g.key[3]:
                         lib.sumsq_(g.grad_buf[g.meta["lo"]:g.meta["hi"]], moe_sq, True)
         else:
+            mp_rank = self.hcg.get_model_parallel_rank() if self.hcg is not None else 0
             sq = torch.zeros(1, dtype=torch.float32, device=self._dev)
             for g in self.groups:
                 if g.key[4]:
@@ -340,45 +392,62 @@ class FusedAdamW:
         sq = self._reduce_norm(sq, moe_sq)
 
         # ---- clip coefficient / found-inf on device, fused update
-        overlapped = native_update and self.step_overlap and self.direct_grad and self._fwd_hooks_installed and self._comm_stream is not None
+        overlapped = native_update and self.step_overlap and self.direct_grad and self._comm_stream is not None
         if overlapped:
             lib.clip_coef_(sq, inv_scale, clip_norm, self._gscale, self._found_inf, self._gnorm)
+            self._sq.zero_()
             OF._count()
             # The side stream starts once the clip coefficient exists; buckets go out in forward order (small no-decay bucket, first
-            # layers, ..., last layers), each followed — under ZeRO — by its parameter all-gather and an event.  The compute stream is
-            # ordered after bucket k only when a module that owns parameters of bucket k runs (install_forward_hooks), so by the end of
-            # the forward pass it has waited for every bucket and the backward pass may overwrite the gradients.
+            # layers, ..., last layers).  Under ZeRO the update kernel also delivers the new low-precision weights to every rank
+            # (multimem.st / peer stores) and is followed by a group barrier ("every rank's part of this bucket has landed") and an
+            # event.  The compute stream is ordered after bucket k only when a module that owns parameters of bucket k runs
+            # (install_forward_hooks), so the update of the later layers runs underneath the forward pass of the earlier ones.
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._comm_stream):
                 for g in sorted(self.groups, key=lambda g: (0 if g.key[0] < 0 else 1, -g.key[0])):
                     lo, hi = g.meta["lo"], g.meta["hi"]
+                    wd = self.weight_decay if g.key[1] else 0.0
                     lp = g.param_buf[lo:hi] if g.meta["has_master"] else None
-                    lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
-                                    self.weight_decay if g.key[1] else 0.0, self._step_count, self._gscale, self._found_inf)
-                    OF._count()
-                    if self.sh_world > 1:
-                        self._all_gather_params(g)
+                    shared = self.sh_world > 1 and not g.key[3]
+                    if self.use_p2p and shared and g.meta["has_master"]:
+                        lib.adamw_symm_broadcast_(g.meta["mc_params"], g.meta["peer_params"], lo, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"],
+                                                  g.meta["v"], lr, self.beta1, self.beta2, self.eps, wd, self._step_count, self._gscale,
+                                                  self._found_inf, _DTYPE_CODE[g.param_buf.dtype], self.sh_rank, self._bcast_ctas)
+                        self._symm.barrier()
+                        OF._count(2)
+                    else:
+                        lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
+                                        wd, self._step_count, self._gscale, self._found_inf)
+                        OF._count()
+                        if shared:
+                            if self.use_p2p:
+                                lib.symm_all_gather(g.meta["mc_params"], g.meta["peer_params"], lo * g.param_buf.element_size(),
+                                                    g.param_buf[lo:hi], self.sh_rank, self._rs_ctas)
+                                self._symm.barrier()
+                                OF._count(2)
+                            else:
+                                self._all_gather_params(g)
                     ev = torch.cuda.Event()
                     ev.record(self._comm_stream)
                     self._ag_events[id(g)] = ev
+            if not self._fwd_hooks_installed:
+                self.finish_param_sync()
             return
         if native_update:
             lib.clip_coef_(sq, inv_scale, clip_norm, self._gscale, self._found_inf, self._gnorm)
+            self._sq.zero_()
             OF._count()
             for g in self.groups:
                 lo, hi = g.meta["lo"], g.meta["hi"]
                 wd = self.weight_decay if g.key[1] else 0.0
                 lp = g.param_buf[lo:hi] if g.meta["has_master"] else None
-                if self.use_p2p and g.meta["has_master"]:
-                    lp_code = 1 if g.param_buf.dtype == torch.bfloat16 else 0
-                    lib.adamw_p2p_broadcast_(g.meta["peer_params"], lo, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr,
-                                             self.beta1, self.beta2, self.eps, wd, self._step_count, self._gscale, self._found_inf, lp_code, 296)
-                else:
-                    lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
-                                    wd, self._step_count, self._gscale, self._found_inf)
+                lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
+                                wd, self._step_count, self._gscale, self._found_inf)
                 OF._count()
         else:
             norm = sq.sqrt() * inv_scale
+            if native:
+                self._sq.zero_()          # consumed (``norm`` is a new tensor); the next step's kernels accumulate from zero
             bad = not bool(torch.isfinite(norm))
             coef = 1.0
             if clip_norm > 0 and not bad:
@@ -407,9 +476,7 @@ class FusedAdamW:
 
         # ---- parameter all-gather (ZeRO) — optionally overlapped with the next forward
         if self.sh_world > 1:
-            if self.use_p2p and native:
-                self._symm.barrier()          # peers' stores have landed before anyone reads its params
-            elif self.broadcast_overlap and self._comm_stream is not None and self._fwd_hooks_installed:
+            if self.broadcast_overlap and self._comm_stream is not None and self._fwd_hooks_installed:
                 # all-gathers run on the communication stream in FORWARD order (small no-decay bucket, then the buckets of
                 # the first layers ...); each module's forward pre-hook waits only for the buckets it reads, so layer 0 starts
                 # while the gathers of the later layers are still in flight
@@ -428,7 +495,7 @@ class FusedAdamW:
     def install_forward_hooks(self, model: torch.nn.Module) -> None:
         """Make every module wait (on the compute stream) for the side-stream work — parameter all-gather and, with ``step_overlap``, the
         AdamW update — of the buckets holding its own parameters."""
-        wanted = (self.broadcast_overlap and self.sh_world > 1) or self.step_overlap
+        wanted = (self.broadcast_overlap and self.sh_world > 1) or self.step_overlap or self.use_p2p
         if not (wanted and self._comm_stream is not None) or self._fwd_hooks_installed:
             return
         group_of = {id(p): g for g in self.groups for p in g.params}
@@ -439,7 +506,7 @@ class FusedAdamW:
                     for gid in gids:
                         ev = self._ag_events.pop(gid, None)
                         if ev is not None:
-                            torch.cuda.current_stream().wait_event(ev)
+                            self._wait(ev)
             return pre_hook
 
         # A module waits for the buckets of the parameters it owns AND of those its direct children own: fused call sites read a child's
@@ -463,7 +530,7 @@ class FusedAdamW:
         evaluation of tied / externally-read weights, reading ``found_inf`` / parameters from the host)."""
         if self._ag_events:
             for ev in self._ag_events.values():
-                torch.cuda.current_stream().wait_event(ev)
+                self._wait(ev)
             self._ag_events.clear()
 
     def _reduce_norm(self, sq: torch.Tensor, moe_sq: Optional[torch.Tensor]) -> torch.Tensor:

@@ -249,6 +249,29 @@ def wait_side_streams() -> None:
             cur.wait_stream(s)
 
 
+_PRE_BACKWARD: list = []      # weak references to bound methods (an optimizer must not be kept alive by this registry)
+
+
+def register_pre_backward(fn) -> None:
+    """Callbacks run right before any backward pass starts writing gradients (the engine and the pipeline runtime call
+    ``run_pre_backward``): the overlapped optimizer uses it to make sure no side-stream update still reads the gradient buffers."""
+    import weakref
+
+    _PRE_BACKWARD.append(weakref.WeakMethod(fn) if hasattr(fn, "__self__") else (lambda fn=fn: fn))
+
+
+def run_pre_backward() -> None:
+    dead = False
+    for ref in _PRE_BACKWARD:
+        fn = ref()
+        if fn is None:
+            dead = True
+        else:
+            fn()
+    if dead:
+        _PRE_BACKWARD[:] = [r for r in _PRE_BACKWARD if r() is not None]
+
+
 def fused_allreduce_gradients(params, group, scale: Optional[float] = None) -> None:
     """Coalesced grad all-reduce (÷ nranks by default) — reference
     ``fused_allreduce_gradients[_with_group]`` (eager_engine.py:491-504)."""

@@ -416,6 +416,7 @@ class PipelineParallel(nn.Module):
     def _backward_step(inp, out, out_grad, scaler=None):
         if inp is not None and isinstance(inp, torch.Tensor) and inp.requires_grad:
             inp.retain_grad()
+        C.run_pre_backward()
         if out_grad is None:                      # last stage: ``out`` is the (scaled) loss
             (scaler.scale(out) if scaler is not None else out).backward()
         else:

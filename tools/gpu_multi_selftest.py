@@ -52,6 +52,23 @@ def main():
         if rank == 0:
             print("RESULT " + json.dumps(dict(check=name, **kw)), flush=True)
 
+    only = set(filter(None, os.environ.get("PFX_MULTI_ONLY", "").split(",")))
+
+    def section(name):
+        return not only or name in only
+
+    # ---------------------------------------------------------------- cuMem-VMM symmetric memory + NVLS (multimem) kernels
+    if section("nvls"):
+        try:
+            nvls_section(lib, grp, rank, world, report)
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            report("nvls_section", ok=False, error=repr(e), tb=traceback.format_exc()[-1500:])
+    if only and only <= {"nvls"}:
+        dist.barrier()
+        finish(res, rank, world)
+        return
+
     # ---------------------------------------------------------------- barrier + raw P2P
     sm = SymmetricAllocator(grp)
     n = 1 << 24
@@ -223,6 +240,10 @@ def main():
            shape=dict(tokens=tok, hidden=hm, experts_per_rank=e_local, topk=2))
 
     dist.barrier()
+    finish(res, rank, world)
+
+
+def finish(res, rank, world):
     if rank == 0:
         n_ok = sum(1 for v in res.values() if v.get("ok"))
         print(f"MULTI_SELFTEST {n_ok}/{len(res)} ok")
@@ -230,6 +251,142 @@ def main():
         with open(os.path.join(ROOT, "gpurun_out", f"multi_selftest_{world}gpu.json"), "w") as f:
             json.dump(res, f, indent=1)
     dist.destroy_process_group()
+
+
+def nvls_section(lib, grp, rank, world, report):
+    """Symmetric memory on cuMem VMM, multicast (NVLS) and unicast variants of the ZeRO kernels against NCCL, and the experiment the
+    design rests on: does a communication kernel overlap with a stream of persistent tcgen05 GEMMs, or serialise with it?"""
+    from paddlefleetx_b200.parallel.symmetric_memory import VmmSymmetricAllocator
+
+    caps = lib.vmm_caps()
+    report("vmm_caps", ok=bool(caps["vmm"] and caps["fd_export"]), **{k: (int(v) if not isinstance(v, bool) else v) for k, v in caps.items()},
+           mc_gran_min=int(lib.vmm_mc_granularity(world, 2 << 20, False)), mc_gran_rec=int(lib.vmm_mc_granularity(world, 2 << 20, True)))
+    sm = VmmSymmetricAllocator(grp)
+    report("vmm_allocator", ok=True, multicast=bool(sm.multicast), granularity=sm._gran)
+    n = 1 << 25                              # elements per shard: 64 MiB of bf16 per rank-shard, bucket = world x that
+    buf = sm.alloc_tensor(n * world, torch.bfloat16)
+    torch.manual_seed(100 + rank)
+    local = (torch.randn(n * world, device="cuda") * 0.1).bfloat16()
+    buf.copy_(local)
+    torch.cuda.synchronize(); sm.barrier(); torch.cuda.synchronize()
+    report("symm_barrier", ok=True, kind="nvls" if sm.multicast else "p2p")
+    t_bar = timed(lambda: sm.barrier(), iters=50)
+    report("symm_barrier_perf", ok=True, us=t_bar * 1e3)
+
+    ref = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    dist.reduce_scatter_tensor(ref, local.clone())
+    peers, mc = sm.peer_ptrs(buf), sm.mc_ptr(buf)
+    variants = [("unicast", 0)] + ([("nvls", mc)] if mc else [])
+    scratch = local.clone()
+    t_nccl = timed(lambda: dist.reduce_scatter_tensor(ref, scratch))
+    moved_in = n * 2 * (world - 1)
+    for name, mcp in variants:
+        out = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+        sq = torch.zeros(1, device="cuda")
+        lib.symm_reduce_scatter(mcp, peers, rank * n, out, rank, 1, 1.0, False, sq, 64)
+        torch.cuda.synchronize(); sm.barrier(); torch.cuda.synchronize()
+        want_sq = float(out.float().pow(2).sum())
+        e = relerr(out, ref)
+        report(f"symm_reduce_scatter_{name}", err=e, sumsq_rel=abs(float(sq) - want_sq) / max(want_sq, 1e-9), ok=e < 1e-2 and abs(float(sq) - want_sq) < 1e-3 * want_sq)
+        # fp32 output + accumulate
+        o32 = torch.ones(n, dtype=torch.float32, device="cuda")
+        lib.symm_reduce_scatter(mcp, peers, rank * n, o32, rank, 1, 0.5, True, None, 64)
+        torch.cuda.synchronize(); sm.barrier(); torch.cuda.synchronize()
+        e2 = relerr(o32 - 1.0, ref.float() * 0.5)
+        report(f"symm_reduce_scatter_{name}_f32acc", err=e2, ok=e2 < 1e-2)
+        perf = {}
+        for ctas in (16, 32, 64, 128, 296):
+            perf[str(ctas)] = timed(lambda: (sm.barrier(), lib.symm_reduce_scatter(mcp, peers, rank * n, out, rank, 1, 1.0, False, None, ctas)))
+        best = min(perf.values())
+        report(f"symm_reduce_scatter_{name}_perf", ms_by_ctas=perf, nccl_ms=t_nccl, shard_mib=n * 2 / 2 ** 20,
+               gbs_link_out=moved_in / best / 1e6, frac_of_770=moved_in / best / 1e6 / 770.0, ok=True)
+
+    # all-gather
+    shard = ((torch.arange(n, device="cuda") % 251) + rank).bfloat16()
+    gath = torch.empty(n * world, dtype=torch.bfloat16, device="cuda")
+    t_ag_nccl = timed(lambda: dist.all_gather_into_tensor(gath, shard))
+    for name, mcp in variants:
+        buf.zero_()
+        torch.cuda.synchronize(); sm.barrier()
+        lib.symm_all_gather(mcp, peers, rank * n * 2, shard, rank, 64)
+        sm.barrier(); torch.cuda.synchronize()
+        ok = all(bool(torch.equal(buf[r * n:(r + 1) * n], ((torch.arange(n, device="cuda") % 251) + r).bfloat16())) for r in range(world))
+        perf = {}
+        for ctas in (16, 32, 64, 128):
+            perf[str(ctas)] = timed(lambda: (lib.symm_all_gather(mcp, peers, rank * n * 2, shard, rank, ctas), sm.barrier()))
+        best = min(perf.values())
+        report(f"symm_all_gather_{name}", ok=ok, ms_by_ctas=perf, nccl_ms=t_ag_nccl, gbs_link_in=moved_in / best / 1e6, frac_of_770=moved_in / best / 1e6 / 770.0)
+
+    # AdamW + broadcast vs adamw_flat_ + NCCL all-gather
+    for name, mcp in variants:
+        torch.manual_seed(5)
+        pfull = sm.alloc_tensor(n * world, torch.bfloat16)
+        master = torch.randn(n, device="cuda") * 0.02 + rank
+        g = (torch.randn(n, device="cuda") * 0.01).bfloat16()
+        m0, v0 = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        gs, fi = torch.ones(1, device="cuda"), torch.zeros(1, device="cuda")
+        ref_master, ref_m, ref_v = master.clone(), m0.clone(), v0.clone()
+        ref_lp = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+        lib.adamw_flat_(ref_lp, ref_master, g, ref_m, ref_v, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, gs, fi)
+        ref_full = torch.empty(n * world, dtype=torch.bfloat16, device="cuda")
+        dist.all_gather_into_tensor(ref_full, ref_lp)
+        torch.cuda.synchronize(); sm.barrier()
+        lib.adamw_symm_broadcast_(sm.mc_ptr(pfull) if mcp else 0, sm.peer_ptrs(pfull), rank * n, master, g, m0, v0, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, gs, fi, 1, rank, 296)
+        sm.barrier(); torch.cuda.synchronize()
+        ok = bool(torch.equal(pfull, ref_full)) and bool(torch.equal(master, ref_master))
+        t = timed(lambda: (lib.adamw_symm_broadcast_(sm.mc_ptr(pfull) if mcp else 0, sm.peer_ptrs(pfull), rank * n, master, g, m0, v0, 1e-3, 0.9, 0.999,
+                                                     1e-8, 0.01, 2, gs, fi, 1, rank, 296), sm.barrier()))
+        t_ref = timed(lambda: (lib.adamw_flat_(ref_lp, ref_master, g, ref_m, ref_v, 1e-3, 0.9, 0.999, 1e-8, 0.01, 2, gs, fi),
+                               dist.all_gather_into_tensor(ref_full, ref_lp)))
+        report(f"adamw_symm_broadcast_{name}", ok=ok, ms=t, adamw_plus_nccl_ag_ms=t_ref, shard_melems=n / 1e6)
+
+    # ---- overlap experiment: a stream of persistent GEMMs with a reduce-scatter running beside it
+    M, N, K = 8192, 16384, 4096
+    a = (torch.randn(M, K, device="cuda") * 0.05).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    c = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    side = torch.cuda.Stream()
+    n_gemm = 24
+
+    def gemms():
+        for _ in range(n_gemm):
+            lib.gemm(a, w, None, c, True, True, 0, 0, 0)
+
+    big = sm.alloc_tensor(n * world * 2, torch.bfloat16)        # 128 MiB x world bucket
+    big.normal_()
+    bpeers, bmc = sm.peer_ptrs(big), sm.mc_ptr(big)
+    bout = torch.empty(n * 2, dtype=torch.bfloat16, device="cuda")
+    nccl_in = torch.randn(n * world * 2, device="cuda").bfloat16()
+    reps = 4
+
+    def comm_ours(ctas):
+        def f():
+            for _ in range(reps):
+                sm.barrier()
+                lib.symm_reduce_scatter(bmc, bpeers, rank * n * 2, bout, rank, 1, 1.0, False, None, ctas)
+        return f
+
+    def comm_nccl():
+        for _ in range(reps):
+            dist.reduce_scatter_tensor(bout, nccl_in)
+
+    def both(comm):
+        def f():
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                comm()
+            gemms()
+            torch.cuda.current_stream().wait_stream(side)
+        return f
+
+    t_g = timed(gemms, iters=3, warmup=1)
+    res_ov = {"gemm_only_ms": t_g, "n_gemm": n_gemm, "bucket_mib": n * world * 4 / 2 ** 20, "reps": reps}
+    for ctas in (32, 64, 148):
+        res_ov[f"ours{ctas}_only_ms"] = timed(comm_ours(ctas), iters=3, warmup=1)
+        res_ov[f"ours{ctas}_both_ms"] = timed(both(comm_ours(ctas)), iters=3, warmup=1)
+    res_ov["nccl_only_ms"] = timed(comm_nccl, iters=3, warmup=1)
+    res_ov["nccl_both_ms"] = timed(both(comm_nccl), iters=3, warmup=1)
+    report("overlap_gemm_reduce_scatter", ok=True, **res_ov)
 
 
 if __name__ == "__main__":
