@@ -269,7 +269,7 @@ def main():
         collective = "none (1 GPU); exposed_comm = compute-stream waits on the side-stream AdamW update"
     elif getattr(opt, "use_p2p", False):
         collective = ("own kernels over symmetric memory: " + ("NVLS multimem.ld_reduce reduce-scatter + AdamW with multimem.st broadcast"
-                      if getattr(symm, "multicast", False) else "unicast peer pull reduce-scatter + AdamW with peer-store broadcast")
+                      if (getattr(symm, "multicast", False) and any(g.meta.get("mc_grads") for g in opt.groups)) else "unicast peer pull reduce-scatter + AdamW with peer-store broadcast")
                       + "; NCCL only for the scalar grad-norm all-reduce" + (" and TP/PP traffic" if lay["mp"] > 1 or lay["pp"] > 1 else ""))
     else:
         collective = "NCCL"

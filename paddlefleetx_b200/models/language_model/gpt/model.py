@@ -179,6 +179,31 @@ class MultiHeadAttention(nn.Module):
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, cache: Optional[KVCache] = None,
                 positions: Optional[torch.Tensor] = None):
+        if (self.fuse_attn_qkv and self.use_flash_attn and not self.use_rope and cache is None and attn_mask is None and x.is_cuda
+                and not (self.recompute_core and self.training)):
+            # fused projection output [.., heads, 3, d] goes to the flash kernels as it is: q / k / v are read in place (TMA views), the
+            # backward writes one packed gradient — no unbind / transpose / cat copies around the attention
+            mix = self.qkv_proj(x)
+            mix = mix.view(*mix.shape[:-1], self.local_heads, 3, self.head_dim)
+            if self.sequence_parallel:
+                mix = mix.transpose(0, 1)
+            if mix.shape[1] > 1:
+                p = self.attn_dropout if self.training else 0.0
+                scale = 1.0 / math.sqrt(self.head_dim)
+                if p > 0:
+                    with get_rng_state_tracker().rng_state("local_seed"):
+                        out = ATT.flash_attention_packed(mix, causal=True, dropout_p=p, scale=scale)
+                else:
+                    out = ATT.flash_attention_packed(mix, causal=True, dropout_p=0.0, scale=scale)
+            else:
+                out = None
+            if out is None:
+                q, k, v = mix.unbind(-2)
+                out = self._core(q, k, v, None)
+            out = out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim)
+            if self.sequence_parallel:
+                out = out.transpose(0, 1).contiguous()
+            return self.out_proj(out)
         q, k, v = self._qkv(x)
         if self.use_rope:
             pos = positions

@@ -22,7 +22,7 @@ CSRC = HERE / "csrc"
 BUILD_DIR = HERE / "csrc" / "build"
 MODULE_NAME = "_pfx_native"
 CUDA_SOURCES = ["gemm_sm100.cu", "norm_act.cu", "loss_optim.cu", "sampling_attn_misc.cu", "comm_p2p.cu",
-                "gemm_lowp_sm100.cu", "quant_kernels.cu", "moe_kernels.cu", "gemv_skinny.cu", "gemm_smallm_sm100.cu", "attention_decode.cu", "attention_fwd_sm100.cu", "comm_nvls.cu"]
+                "gemm_lowp_sm100.cu", "quant_kernels.cu", "moe_kernels.cu", "gemv_skinny.cu", "gemm_smallm_sm100.cu", "attention_decode.cu", "attention_fwd_sm100.cu", "comm_nvls.cu", "attention_bwd_sm100.cu"]
 CPP_SOURCES = ["bindings.cpp", "symm_vmm.cpp"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -90,10 +90,14 @@ def build(force: bool = False, verbose: bool = True) -> Path:
         list(pool.map(lambda j: _run(j[0], verbose), jobs))
 
     torch_lib = Path(torch.__file__).parent / "lib"
-    link = ["g++", "-shared", "-o", str(lib_path()), *[str(o) for _, o in jobs],
+    tmp_lib = BUILD_DIR / (lib_path().name + ".tmp")      # link beside, then rename: a concurrent reader (gpurun snapshot) never sees half a file
+    link = ["g++", "-shared", "-o", str(tmp_lib), *[str(o) for _, o in jobs],
             f"-L{torch_lib}", f"-L{cuda_home}/lib64", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
             "-ltorch_python", "-lcudart", f"-Wl,-rpath,{torch_lib}", f"-Wl,-rpath,{cuda_home}/lib64"]
     _run(link, verbose)
+    import os
+
+    os.replace(tmp_lib, lib_path())
     (HERE / f"{MODULE_NAME}.hash").write_text(_hash_sources())
     return lib_path()
 

@@ -9,6 +9,7 @@
 #include "pfx_gemm.h"
 #include "pfx_kernels.h"
 #include "pfx_symm.h"
+#include "pfx_attn.h"
 
 namespace {
 
@@ -623,6 +624,45 @@ std::vector<at::Tensor> attention_fwd(const at::Tensor& q, const at::Tensor& k, 
   return {out, lse};
 }
 
+static pfx::AttnView attn_view(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.dim() == 4 && t.scalar_type() == at::kBFloat16 && t.stride(3) == 1, name, ": [B,S,H,D] bf16 CUDA view with contiguous D expected");
+  TORCH_CHECK(t.stride(0) % 8 == 0 && t.stride(1) % 8 == 0 && t.stride(2) % 8 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) % 16) == 0,
+              name, ": strides must be multiples of 8 elements and the base 16-byte aligned");
+  return pfx::AttnView{t.data_ptr(), t.stride(0), t.stride(1), t.stride(2)};
+}
+
+// Flash attention forward on [B,S,H,D] bf16 views (no copies for packed-QKV slices / sequence-major storage); optional dropout keyed by `seed`.
+std::vector<at::Tensor> attention_fwd_v2(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, bool causal, double scale, double dropout_p,
+                                         int64_t seed) {
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && k.sizes() == v.sizes() && q.size(0) == k.size(0) && q.size(2) == k.size(2) && q.size(3) == k.size(3),
+              "attention_fwd_v2: shape mismatch");
+  const c10::cuda::CUDAGuard guard(q.device());
+  auto out = at::empty({q.size(0), q.size(1), q.size(2), q.size(3)}, q.options());
+  auto lse = at::empty({q.size(0), q.size(2), q.size(1)}, q.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::attention_fwd_v2(attn_view(q, "q"), attn_view(k, "k"), attn_view(v, "v"), attn_view(out, "out"), lse.data_ptr<float>(),
+                                       (int)q.size(0), (int)q.size(1), (int)k.size(1), (int)q.size(2), (int)q.size(3), (float)scale, causal,
+                                       pfx::AttnDropout{(float)dropout_p, (uint64_t)seed}, cur_stream()));
+  return {out, lse};
+}
+
+// Flash attention backward (head_dim 128): writes dq / dk / dv into the given (possibly strided) views.
+void attention_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse,
+                   at::Tensor& dq, at::Tensor& dk, at::Tensor& dv, bool causal, double scale, double dropout_p, int64_t seed) {
+  TORCH_CHECK(q.dim() == 4 && k.sizes() == v.sizes() && q.sizes() == out.sizes() && q.sizes() == dout.sizes() && q.sizes() == dq.sizes() &&
+              k.sizes() == dk.sizes() && k.sizes() == dv.sizes() && q.size(3) == 128, "attention_bwd: shape mismatch (head_dim must be 128)");
+  TORCH_CHECK(lse.is_cuda() && lse.is_contiguous() && lse.scalar_type() == at::kFloat && lse.numel() == q.size(0) * q.size(1) * q.size(2), "attention_bwd: lse");
+  const c10::cuda::CUDAGuard guard(q.device());
+  const int64_t B = q.size(0), Sq = q.size(1), Sk = k.size(1), H = q.size(2), D = q.size(3);
+  const int64_t sq_pad = (Sq + 63) / 64 * 64;
+  auto f32 = q.options().dtype(at::kFloat);
+  auto dq_acc = at::empty({B, Sq, H, D}, f32);
+  auto stats = at::empty({2, B * H * sq_pad}, f32);
+  PFX_CUDA_CHECK(pfx::attention_bwd(attn_view(q, "q"), attn_view(k, "k"), attn_view(v, "v"), attn_view(out, "out"), attn_view(dout, "dout"),
+                                    lse.data_ptr<float>(), attn_view(dq, "dq"), attn_view(dk, "dk"), attn_view(dv, "dv"), dq_acc.data_ptr<float>(),
+                                    stats[0].data_ptr<float>(), stats[1].data_ptr<float>(), (int)B, (int)Sq, (int)Sk, (int)H, (int)D, (float)scale,
+                                    causal, pfx::AttnDropout{(float)dropout_p, (uint64_t)seed}, cur_stream()));
+}
+
 at::Tensor attention_decode_packed(const at::Tensor& qkv, at::Tensor& k, at::Tensor& v, c10::optional<at::Tensor> mask, const at::Tensor& write_idx,
                                    double scale) {
   // qkv [B,1,H,3,D] (fused projection output); appends this step's K/V at cache position write_idx[0] and attends over the whole cache
@@ -721,6 +761,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("attention_fwd", &attention_fwd);
+  m.def("attention_fwd_v2", &attention_fwd_v2);
+  m.def("attention_bwd", &attention_bwd);
   m.def("attention_decode", &attention_decode);
   m.def("attention_decode_packed", &attention_decode_packed);
   m.def("gemm_bias_gelu_dual", &gemm_bias_gelu_dual);

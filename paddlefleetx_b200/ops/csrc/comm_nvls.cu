@@ -11,8 +11,8 @@
 //   * all-gather       same store path for plain shards (ZeRO-3 parameter gather, tests).
 //   * barrier          one multimem.red (+1 on every rank's flag word) + a local acquire spin.
 //
-// Every kernel is 256 threads, <= 64 registers, no dynamic shared memory: a CTA fits next to a persistent tcgen05 GEMM
-// CTA (256 threads x <= 160 registers, ~220 KB smem) on the same SM, so communication CTAs neither wait for a GEMM wave to
+// Every kernel is 256 threads, <= 72 registers and ZERO shared memory (static included): a CTA fits next to a persistent tcgen05 GEMM
+// CTA (256 threads x <= 160 registers; the GEMM leaves 12 KB of the SM's shared memory free for exactly this) on the same SM, so communication CTAs neither wait for a GEMM wave to
 // drain nor park GEMM clusters behind themselves — which is what happens with NCCL's kernels (their shared-memory
 // footprint does not fit beside the GEMM) and what round 1 measured as a fixed ~12 ms / step scaling loss.
 //
@@ -99,17 +99,11 @@ __device__ __forceinline__ void store_elems(TOut* dst, const float (&f)[kElems],
   }
 }
 
-__device__ __forceinline__ void block_atomic_add(float v, float* out) {
-  __shared__ float s_part[8];
+// One atomic per warp and NO shared memory: a single byte of static shared memory would make the CTA need a second kilobyte next
+// to the one the system reserves per CTA, and then it no longer fits beside a GEMM CTA (measured: serialisation instead of overlap).
+__device__ __forceinline__ void warp_atomic_add(float v, float* out) {
   v = warp_sum(v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) s_part[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    float t = lane < (int)(blockDim.x >> 5) ? s_part[lane] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0 && t != 0.f) atomicAdd(out, t);
-  }
+  if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(out, v);
 }
 
 // ------------------------------------------------------------------ barriers
@@ -193,7 +187,7 @@ __global__ void __launch_bounds__(256) symm_reduce_scatter_kernel(const TIn* __r
       store_elems<TOut, kE>(out + i * kE, acc[u], accumulate);
     }
   }
-  if (sumsq != nullptr) block_atomic_add(sq, sumsq);
+  if (sumsq != nullptr) warp_atomic_add(sq, sumsq);
 }
 
 // ------------------------------------------------------------------ all-gather

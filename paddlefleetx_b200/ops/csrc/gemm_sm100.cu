@@ -47,7 +47,10 @@ struct GemmSmem {
   static constexpr int kEpiBytes = kBlockM * kStoreCols * 2;   // one store box
   static constexpr int kNumEpiBufs = 2;
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kBudget = 227 * 1024 - 1024 /*align slack*/ - kBarrierBytes - kNumEpiBufs * kEpiBytes;
+  // 12 KB of the SM's 228 KB stay free: a co-resident communication / optimizer CTA needs its own 1 KB system reservation (plus any static
+  // shared memory), and a GEMM that fills the SM to the last kilobyte serialises with every kernel on the side streams instead of sharing it.
+  static constexpr int kHeadroom = 12 * 1024;
+  static constexpr int kBudget = 227 * 1024 - kHeadroom - 1024 /*align slack*/ - kBarrierBytes - kNumEpiBufs * kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kTotal = 1024 + kStages * kStageBytes + kNumEpiBufs * kEpiBytes + kBarrierBytes;
 };
@@ -440,6 +443,23 @@ bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_c
   CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   (void)elem_bytes;
+  return r == CUDA_SUCCESS;
+}
+
+bool make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype_code, uint64_t inner, uint64_t S, uint64_t B, uint64_t s_stride_bytes,
+                    uint64_t b_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool* swapped) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  const CUtensorMapDataType dt = dtype_code == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const bool sw = B > 1 && b_stride_bytes < s_stride_bytes;
+  cuuint64_t dims[3] = {inner, sw ? B : S, sw ? S : B};
+  cuuint64_t strides[2] = {sw ? b_stride_bytes : s_stride_bytes, sw ? s_stride_bytes : b_stride_bytes};
+  if (B == 1) strides[1] = strides[0] * dims[1];      // a unit dimension: any legal stride
+  cuuint32_t box[3] = {box_cols, sw ? 1u : box_rows, sw ? box_rows : 1u};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(map, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (swapped) *swapped = sw;
   return r == CUDA_SUCCESS;
 }
 

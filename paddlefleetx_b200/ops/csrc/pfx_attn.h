@@ -1,0 +1,30 @@
+// Flash-attention kernels (attention_fwd_sm100.cu, attention_bwd_sm100.cu): host interface and the shared dropout generator.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace pfx {
+
+// A [B, S, H, D] bf16 view with D contiguous; strides in elements.  Covers contiguous tensors, the q / k / v slices of a packed
+// [B, S, H, 3, D] projection output and sequence-major ([S, B, ...]) storage without any copy.
+struct AttnView {
+  const void* ptr;
+  int64_t sb, ss, sh;
+};
+
+struct AttnDropout {
+  float p;            // drop probability (0 = off)
+  uint64_t seed;      // counter-hash key; the element (b, h, q, k) keeps iff hash16(seed, b*H+h, q, k) >= p * 65536
+};
+
+// O = softmax(scale * Q K^T + causal) (dropout) V;  lse = row-wise log-sum-exp (natural log) [B, H, Sq] fp32
+cudaError_t attention_fwd_v2(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& out, float* lse, int B, int Sq, int Sk, int H,
+                             int D, float scale, bool causal, AttnDropout drop, cudaStream_t st);
+
+// Backward.  Workspace: dq_acc fp32 [B, Sq, H, D] (zeroed by the call), lse2 / delta fp32 [B, H, round_up(Sq, 64)].
+// dq / dk / dv may be strided views (e.g. slices of one packed [B, S, H, 3, D] gradient buffer).  D must be 128.
+cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& out, const AttnView& dout, const float* lse,
+                          const AttnView& dq, const AttnView& dk, const AttnView& dv, float* dq_acc, float* lse2, float* delta, int B, int Sq,
+                          int Sk, int H, int D, float scale, bool causal, AttnDropout drop, cudaStream_t st);
+
+}  // namespace pfx

@@ -162,8 +162,12 @@ class FusedAdamW:
             if self.use_p2p:
                 g.meta["peer_grads"] = self._symm.peer_ptrs(g.grad_buf)
                 g.meta["peer_params"] = self._symm.peer_ptrs(g.param_buf)
-                g.meta["mc_grads"] = self._symm.mc_ptr(g.grad_buf)        # 0 when the fabric has no NVLS: unicast pull / push
-                g.meta["mc_params"] = self._symm.mc_ptr(g.param_buf)
+                # Multicast includes the sender: an NVLS reduce-scatter / broadcast moves world/(world-1) x the unicast bytes over the
+                # busier link direction but needs 1/(world-1) of the load / store instructions (measured at world 2: 0.215 vs 0.126 ms on a
+                # 64 MiB shard).  From world 4 the instruction saving wins; below that — or without NVLS — the unicast kernels run (mc = 0).
+                use_mc = self.sh_world >= int(_os.environ.get("PFX_NVLS_MIN_WORLD", "4"))
+                g.meta["mc_grads"] = self._symm.mc_ptr(g.grad_buf) if use_mc else 0
+                g.meta["mc_params"] = self._symm.mc_ptr(g.param_buf) if use_mc else 0
         self._sq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gscale = torch.ones(1, dtype=torch.float32, device=dev)
         self._found_inf = torch.zeros(1, dtype=torch.float32, device=dev)

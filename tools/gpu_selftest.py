@@ -363,6 +363,113 @@ def check_attention_fwd():
     return dict(ok=ok, shapes=res)
 
 
+def _attn_reference(q, k, v, scale, causal, keep, p):
+    """fp32 attention with an explicit keep mask [B,H,Sq,Sk] (or None); returns out and, with autograd, the input grads."""
+    import torch
+    s = torch.einsum("bqhd,bkhd->bhqk", q, k) * scale
+    Sq, Sk = q.shape[1], k.shape[1]
+    if causal:
+        mask = torch.ones(Sq, Sk, dtype=torch.bool, device=q.device).tril(Sk - Sq)
+        s = s.masked_fill(~mask, float("-inf"))
+    pr = torch.softmax(s, -1)
+    if keep is not None:
+        pr = pr * keep.to(pr.dtype) / (1.0 - p)
+    return torch.einsum("bhqk,bkhd->bqhd", pr, v)
+
+
+def check_attention_train(perf=False):
+    """forward (with dropout) + backward of the flash kernels against fp32 autograd with the SAME dropout mask, on contiguous, packed-QKV and
+    sequence-major layouts; optional timing against library SDPA."""
+    import torch
+    import torch.nn.functional as F
+    from paddlefleetx_b200.ops import attention as ATT
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    cases = [  # B, Sq, Sk, H, causal, p, layout
+        (1, 128, 128, 1, True, 0.0, "plain"), (2, 256, 256, 2, True, 0.0, "plain"), (1, 320, 320, 2, True, 0.1, "plain"),
+        (2, 200, 200, 3, False, 0.0, "plain"), (1, 128, 256, 2, True, 0.0, "plain"), (2, 512, 512, 4, True, 0.1, "packed"),
+        (2, 384, 384, 2, True, 0.1, "seq_major"), (1, 1024, 1024, 4, True, 0.0, "packed")]
+    D = 128
+    for (B, Sq, Sk, H, causal, p, layout) in cases:
+        scale = D ** -0.5
+        if layout == "plain":
+            q = torch.randn(B, Sq, H, D, device="cuda").bfloat16(); k = torch.randn(B, Sk, H, D, device="cuda").bfloat16(); v = torch.randn(B, Sk, H, D, device="cuda").bfloat16()
+            dq = torch.empty_like(q); dk = torch.empty_like(k); dv = torch.empty_like(v)
+        elif layout == "packed":
+            mix = torch.randn(B, Sq, H, 3, D, device="cuda").bfloat16(); q, k, v = mix.unbind(3)
+            dmix = torch.empty_like(mix); dq, dk, dv = dmix.unbind(3)
+        else:
+            mix = torch.randn(Sq, B, H, 3, D, device="cuda").bfloat16().transpose(0, 1); q, k, v = mix.unbind(3)
+            dmix = torch.empty(Sq, B, H, 3, D, device="cuda", dtype=torch.bfloat16).transpose(0, 1); dq, dk, dv = dmix.unbind(3)
+        seed = 0x1234567 + 977 * Sq
+        out, lse = lib.attention_fwd_v2(q, k, v, causal, scale, p, seed)
+        go = (torch.randn(B, Sq, H, D, device="cuda") * 0.5).bfloat16()
+        lib.attention_bwd(q, k, v, out, go, lse, dq, dk, dv, causal, scale, p, seed)
+        torch.cuda.synchronize()
+        keep = ATT.attn_keep_mask(seed, B, H, Sq, Sk, p, "cuda") if p > 0 else None
+        qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+        ref = _attn_reference(qr, kr, vr, scale, causal, keep, p)
+        ref.backward(go.float())
+        errs = dict(out=_relerr(out, ref), dq=_relerr(dq, qr.grad), dk=_relerr(dk, kr.grad), dv=_relerr(dv, vr.grad))
+        if keep is not None:
+            errs["keep_rate"] = round(float(keep.float().mean()), 4)
+        good = all(errs[n] < 2e-2 for n in ("out", "dq", "dk", "dv"))
+        ok = ok and good
+        res[f"B{B}_Sq{Sq}_Sk{Sk}_H{H}_{'causal' if causal else 'full'}_p{p}_{layout}"] = {n: round(float(e), 5) for n, e in errs.items()}
+    out_d = dict(ok=ok, shapes=res)
+    if perf:
+        for (B, S, H) in [(8, 1024, 32), (2, 4096, 32)]:
+            mix = torch.randn(B, S, H, 3, D, device="cuda").bfloat16(); q, k, v = mix.unbind(3)
+            dmix = torch.empty_like(mix); dq, dk, dv = dmix.unbind(3)
+            go = torch.randn(B, S, H, D, device="cuda").bfloat16()
+            scale = D ** -0.5
+            for p in (0.0, 0.1):
+                out, lse = lib.attention_fwd_v2(q, k, v, True, scale, p, 7)
+                t_f, _ = _time(lambda: lib.attention_fwd_v2(q, k, v, True, scale, p, 7))
+                t_b, _ = _time(lambda: lib.attention_bwd(q, k, v, out, go, lse, dq, dk, dv, True, scale, p, 7))
+                qt, kt, vt = (t.transpose(1, 2).detach().requires_grad_(True) for t in (q.contiguous(), k.contiguous(), v.contiguous()))
+                got = go.transpose(1, 2)
+                t_sf, _ = _time(lambda: F.scaled_dot_product_attention(qt, kt, vt, is_causal=True, dropout_p=p, scale=scale))
+
+                def sd_fb():
+                    o = F.scaled_dot_product_attention(qt, kt, vt, is_causal=True, dropout_p=p, scale=scale)
+                    o.backward(got)
+                    qt.grad = kt.grad = vt.grad = None
+                t_sfb, _ = _time(sd_fb)
+                fl = 4.0 * B * H * S * S * D * 0.5
+                out_d[f"perf_B{B}_S{S}_H{H}_p{p}"] = dict(fwd_ms=round(t_f, 4), fwd_tflops=round(fl / t_f / 1e9, 1), bwd_ms=round(t_b, 4),
+                                                         bwd_tflops=round(2.5 * fl / t_b / 1e9, 1), sdpa_fwd_ms=round(t_sf, 4),
+                                                         sdpa_fwd_bwd_ms=round(t_sfb, 4), ours_fwd_bwd_ms=round(t_f + t_b, 4))
+    return out_d
+
+
+def check_attention_autograd():
+    """The autograd wrappers (plain and packed) against fp32 autograd; no dropout (mask replication is covered by attention_train)."""
+    import torch
+    from paddlefleetx_b200.ops import attention as ATT
+    torch.manual_seed(1)
+    B, S, H, D = 2, 256, 4, 128
+    mix = torch.randn(B, S, H, 3, D, device="cuda").bfloat16().requires_grad_(True)
+    go = torch.randn(B, S, H, D, device="cuda").bfloat16()
+    out = ATT.flash_attention_packed(mix, causal=True)
+    assert out is not None
+    out.backward(go)
+    q, k, v = (t.detach().float().requires_grad_(True) for t in mix.detach().unbind(3))
+    ref = _attn_reference(q, k, v, D ** -0.5, True, None, 0.0)
+    ref.backward(go.float())
+    gref = torch.stack([q.grad, k.grad, v.grad], dim=3)
+    e1, e2 = _relerr(out, ref), _relerr(mix.grad, gref)
+    q2, k2, v2 = (torch.randn(B, S, H, D, device="cuda").bfloat16().requires_grad_(True) for _ in range(3))
+    o2 = ATT.attention(q2, k2, v2, causal=False)
+    o2.backward(go)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q2, k2, v2))
+    r2 = _attn_reference(qf, kf, vf, D ** -0.5, False, None, 0.0)
+    r2.backward(go.float())
+    e3 = max(_relerr(q2.grad, qf.grad), _relerr(k2.grad, kf.grad), _relerr(v2.grad, vf.grad), _relerr(o2, r2))
+    return dict(ok=bool(max(e1, e2, e3) < 2e-2), err_out=e1, err_packed_grad=e2, err_plain=e3)
+
+
 def check_fused_ffn():
     """Dual-output bias+GELU epilogue, dGELU epilogue and the FFN autograd node built on them vs fp32 PyTorch; timing vs the unfused chain."""
     import torch
@@ -535,7 +642,26 @@ def check_attention_decode():
     return dict(ok=ok, shapes=res)
 
 
+def check_gemm_big_sweep():
+    """Multi-tile shapes (several tiles per CTA, both TMEM accumulator buffers alternating, dozens of k-blocks, ragged edges) for every
+    (CTA-group, operand majors, output mode) against fp32."""
+    worst, rows, ok = 0.0, {}, True
+    for cfg in (1, 2, 3, 4):
+        for (a_k, b_k) in ((True, True), (True, False), (False, False), (False, True)):
+            for out_mode in (0, 1, 2):
+                M, N, K = (4096 + 128, 2048 + 64, 1536) if cfg in (1, 2) else (3072, 1024 + 128, 2048)
+                r = check_gemm(a_k, b_k, cfg, M, N, K, out_mode=out_mode, epilogue=1 if out_mode == 0 else 0)
+                rows[f"cfg{cfg}_{'K' if a_k else 'M'}{'K' if b_k else 'N'}_out{out_mode}"] = round(r["err"], 5)
+                worst = max(worst, r["err"])
+                ok = ok and r["ok"]
+    return dict(ok=ok, worst=worst, cases=rows)
+
+
 CHECKS = {
+    "attention_train": check_attention_train,
+    "attention_train_perf": lambda: check_attention_train(perf=True),
+    "attention_autograd": check_attention_autograd,
+    "gemm_big_sweep": check_gemm_big_sweep,
     "attention_decode": check_attention_decode,
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
@@ -599,7 +725,7 @@ def main():
             print(json.dumps(dict(check=name, ok=False, error="skipped after repeated timeouts")), flush=True)
             continue
         try:
-            p = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=90)
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True, timeout=180)
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             res = json.loads(line[-1][7:]) if line else dict(check=name, ok=False, rc=p.returncode,
                                                              tail=(p.stdout[-600:] + p.stderr[-1200:]))
