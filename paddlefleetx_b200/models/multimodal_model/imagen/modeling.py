@@ -77,32 +77,63 @@ def resize_image_to(img, size):
 
 
 class ImagenModel(nn.Module):
-    def __init__(self, unets: Sequence, image_sizes: Sequence[int] = (64,), text_encoder_name: Optional[str] = None, text_embed_dim: int = 1024,
-                 in_chans: int = 3, timesteps: int = 1000, cond_drop_prob: float = 0.1, noise_schedules="cosine", pred_objectives="noise",
-                 lowres_noise_schedule: str = "linear", lowres_sample_noise_level: float = 0.2, dynamic_thresholding: bool = True,
-                 dynamic_thresholding_percentile: float = 0.95, p2_loss_weight_gamma: float = 0.5, p2_loss_weight_k: float = 1.0,
-                 unet_number: int = 1, text_encoder=None, **unused):
+    """``unets``: one U-Net per cascade stage (modules, or ``{"name": <preset>, ...}`` dicts).  ``image_sizes[k]`` is stage k's
+    resolution; a stage trained on its own with low-resolution conditioning lists the conditioning resolution after its own —
+    ``image_sizes=(256, 64)`` with one ``lowres_cond`` U-Net, the form of the reference's super-resolution recipes
+    (modeling.py:1000-1026).  Every keyword of the reference constructor is accepted; unknown ones raise."""
+
+    def __init__(self, unets: Sequence, image_sizes: Sequence[int] = (64,), text_encoder_name: Optional[str] = None, text_embed_dim: Optional[int] = 1024,
+                 in_chans: Optional[int] = None, channels: int = 3, timesteps: int = 1000, cond_drop_prob: float = 0.1, noise_schedules="cosine",
+                 pred_objectives="noise", lowres_noise_schedule: str = "linear", lowres_sample_noise_level: float = 0.2,
+                 per_sample_random_aug_noise_level: bool = False, condition_on_text: bool = True, auto_normalize_img: bool = True,
+                 dynamic_thresholding: bool = True, dynamic_thresholding_percentile: float = 0.95, p2_loss_weight_gamma: float = 0.5,
+                 p2_loss_weight_k: float = 1.0, unet_number: Optional[int] = None, only_train_unet_number: Optional[int] = None, is_sr: bool = False,
+                 text_encoder=None):
         super().__init__()
-        self.unets = nn.ModuleList([u if isinstance(u, nn.Module) else getattr(U, u["name"])(**{k: v for k, v in u.items() if k != "name"},
-                                                                                             text_embed_dim=text_embed_dim) for u in unets])
+        if isinstance(unets, nn.Module):
+            unets = [unets]
+        text_embed_dim = text_embed_dim or 1024
+        built = [u if isinstance(u, nn.Module) else getattr(U, u["name"])(**{k: v for k, v in u.items() if k != "name"}, text_embed_dim=text_embed_dim)
+                 for u in unets]
+        in_chans = channels if in_chans is None else in_chans
+        for k, u in enumerate(built):
+            # every stage agrees with the cascade on channels / text conditioning; stages after the first condition on the previous stage's image
+            want_lowres = u.lowres_cond or k > 0
+            if (u.channels != in_chans or u.cond_on_text != condition_on_text or u._locals["text_embed_dim"] != text_embed_dim
+                    or u.lowres_cond != want_lowres):
+                built[k] = u.__class__(**{**u._locals, "channels": in_chans, "channels_out": u._locals["channels_out"], "cond_on_text": condition_on_text,
+                                          "text_embed_dim": text_embed_dim, "lowres_cond": want_lowres})
+        self.unets = nn.ModuleList(built)
         n = len(self.unets)
         self.image_sizes = list(image_sizes)
+        assert len(self.image_sizes) >= n, "one image size per U-Net (plus the conditioning size of a stand-alone super-resolution stage)"
         ns = [noise_schedules] * n if isinstance(noise_schedules, str) else list(noise_schedules)
         self.noise_schedulers = nn.ModuleList([GaussianDiffusionContinuousTimes(s, timesteps) for s in ns])
         self.lowres_noise_schedule = GaussianDiffusionContinuousTimes(lowres_noise_schedule)
         self.pred_objectives = [pred_objectives] * n if isinstance(pred_objectives, str) else list(pred_objectives)
         self.cond_drop_prob, self.lowres_sample_noise_level = cond_drop_prob, lowres_sample_noise_level
+        self.per_sample_random_aug_noise_level = per_sample_random_aug_noise_level
+        self.condition_on_text, self.auto_normalize_img, self.is_sr = condition_on_text, auto_normalize_img, is_sr
         self.dynamic_thresholding, self.dt_pct = dynamic_thresholding, dynamic_thresholding_percentile
         self.p2_gamma, self.p2_k = p2_loss_weight_gamma, p2_loss_weight_k
-        self.unet_number, self.in_chans = unet_number, in_chans
+        self.unet_number = unet_number or only_train_unet_number or 1
+        self.in_chans = in_chans
         self.text_encoder = text_encoder           # frozen T5 / DeBERTa, optional (pre-computed embeddings are accepted too)
-        self.text_encoder_name = text_encoder_name
+        self.text_encoder_name = None if text_encoder_name in (None, "None", "") else text_encoder_name
         from ....data.tokenizers import get_text_tokenizer
 
-        self.tokenizer = get_text_tokenizer(text_encoder_name)      # None when the vocabulary is not on this (offline) machine
+        self.tokenizer = get_text_tokenizer(self.text_encoder_name)      # None when the vocabulary is not on this (offline) machine
         if self.text_encoder is not None:
             for p in self.text_encoder.parameters():
                 p.requires_grad = False
+
+    def _prev_size(self, k: int) -> Optional[int]:
+        """Resolution of the image stage ``k`` is conditioned on (None for an unconditioned base stage)."""
+        if k > 0:
+            return self.image_sizes[k - 1]
+        if self.unets[k].lowres_cond and len(self.image_sizes) > len(self.unets):
+            return self.image_sizes[len(self.unets)]
+        return None
 
     def encode_text(self, input_ids, attention_mask):
         with torch.no_grad():
@@ -117,13 +148,13 @@ class ImagenModel(nn.Module):
         return enc.input_ids.to(dev), enc.attention_mask.to(dev)
 
     def p_losses(self, unet, x0, times, scheduler, objective, text_embeds=None, text_mask=None, lowres_cond_img=None, lowres_aug_times=None, noise=None):
-        x0 = x0 * 2 - 1
+        norm = (lambda im: im * 2 - 1) if self.auto_normalize_img else (lambda im: im)
+        x0 = norm(x0)
         noise = torch.randn_like(x0) if noise is None else noise
         xt, log_snr, _, _ = scheduler.q_sample(x0, times, noise)
         lowres_noisy = None
         if lowres_cond_img is not None:
-            lowres_cond_img = lowres_cond_img * 2 - 1
-            lowres_noisy, _, _, _ = self.lowres_noise_schedule.q_sample(lowres_cond_img, lowres_aug_times)
+            lowres_noisy, _, _, _ = self.lowres_noise_schedule.q_sample(norm(lowres_cond_img), lowres_aug_times)
         pred = unet(xt, scheduler.log_snr(times), lowres_cond_img=lowres_noisy,
                     lowres_noise_times=None if lowres_aug_times is None else self.lowres_noise_schedule.log_snr(lowres_aug_times),
                     text_embeds=text_embeds, text_mask=text_mask, cond_drop_prob=self.cond_drop_prob)
@@ -138,10 +169,12 @@ class ImagenModel(nn.Module):
         b = images.shape[0]
         times = sched.sample_random_times(b, images.device)
         lowres, aug_t = None, None
-        if k > 0:
-            prev = self.image_sizes[k - 1]
+        prev = self._prev_size(k)
+        if prev is not None:
             lowres = resize_image_to(resize_image_to(images, prev), size)
-            aug_t = self.lowres_noise_schedule.sample_random_times(1, images.device).expand(b)
+            aug_t = self.lowres_noise_schedule.sample_random_times(b if self.per_sample_random_aug_noise_level else 1, images.device).expand(b)
+        if not self.condition_on_text:
+            text_embeds = text_masks = None
         x0 = resize_image_to(images, size)
         return self.p_losses(unet, x0, times, sched, obj, text_embeds, text_masks, lowres, aug_t)
 
@@ -193,17 +226,24 @@ class ImagenCriterion(nn.Module):
         return losses.mean()
 
 
-def _preset(unet_names, sizes, **fixed):
+def _cascade(unet_builders, sizes):
+    """Preset factory with the keyword surface of the reference constructors (modeling.py:952-1026): ``use_recompute`` goes to the
+    U-Nets, ``lowres_cond`` to a stand-alone stage, the rest to ``ImagenModel``."""
     def build(**kw):
-        cfg = {**fixed, **kw}
-        ted = cfg.get("text_embed_dim", 1024)
-        unets = [getattr(U, n)(text_embed_dim=ted) for n in unet_names]
-        return ImagenModel(unets, image_sizes=sizes, **cfg)
+        use_recompute = bool(kw.pop("use_recompute", False))
+        kw.pop("recompute_granularity", None)
+        lowres_cond = bool(kw.pop("lowres_cond", False))
+        ted = kw.get("text_embed_dim") or 1024
+        unets = [b(text_embed_dim=ted, use_recompute=use_recompute, **({"lowres_cond": True} if (lowres_cond and len(unet_builders) == 1) else {}))
+                 for b in unet_builders]
+        return ImagenModel(unets, image_sizes=sizes if (lowres_cond or len(sizes) == len(unets)) else sizes[:len(unets)], **kw)
     return build
 
 
-imagen_397M_text2im_64 = _preset(["Unet64_397M"], [64])
-imagen_2B_text2im_64 = _preset(["BaseUnet64"], [64])
-imagen_text2im_64_debertav2 = _preset(["Unet64_397M"], [64], text_embed_dim=1536)
-imagen_SR256 = _preset(["Unet64_397M", "SRUnet256"], [64, 256], unet_number=2)
-imagen_SR1024 = _preset(["Unet64_397M", "SRUnet256", "SRUnet1024"], [64, 256, 1024], unet_number=3)
+imagen_397M_text2im_64 = _cascade([U.Unet64_397M], (64,))
+imagen_text2im_64 = _cascade([U.BaseUnet64], (64,))
+imagen_2B_text2im_64 = imagen_text2im_64
+imagen_text2im_64_debertav2 = _cascade([lambda **k: U.BaseUnet64(dim=360, **k)], (64,))
+imagen_text2im_64_SR256 = _cascade([U.BaseUnet64, U.SRUnet256], (64, 256))
+imagen_SR256 = _cascade([U.SRUnet256], (256, 64))
+imagen_SR1024 = _cascade([lambda **k: U.SRUnet1024(dim=128, **k)], (1024, 256))

@@ -35,9 +35,8 @@ class ImagenModule(MultiModalModule):
         cfg.pop("module", None)
         name = cfg.pop("name")
         self._loss_cfg = dict(self.configs.get("Loss", {"name": "mse_loss", "p2_loss_weight_k": 1.0}))
-        for k in ("fused_linear", "use_recompute"):
-            cfg.pop(k, None)
-        return getattr(imagen, name)(**cfg).to(_device(self.configs))
+        cfg.pop("fused_linear", None)
+        return getattr(imagen, name)(**cfg).to(_device(self.configs))      # unknown Model keys raise in the constructor: nothing is dropped silently
 
     def get_loss_fn(self):
         c = dict(self._loss_cfg)

@@ -133,7 +133,7 @@ def test_vision_multimodal_and_text_towers_on_gpu():
         lg, _ = moco(torch.randn(4, 3, 32, 32, device=dev), torch.randn(4, 3, 32, 32, device=dev))
     lg.float().logsumexp(1).mean().backward()
     u = U.Unet(dim=16, text_embed_dim=12, dim_mults=(1, 2), layer_attns=(False, True), layer_cross_attns=(False, True), attn_heads=2,
-               attn_dim_head=8, max_text_len=6, num_latents=2).to(dev)
+               attn_dim_head=8, max_text_len=6, attn_pool_num_latents=2).to(dev)
     m = I.ImagenModel([u], image_sizes=[16], text_embed_dim=12, timesteps=2).to(dev)
     with amp():
         out = m(torch.rand(2, 3, 16, 16, device=dev), text_embeds=torch.randn(2, 4, 12, device=dev), text_masks=torch.ones(2, 4, device=dev))

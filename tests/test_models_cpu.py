@@ -160,7 +160,7 @@ def test_vit_moco_imagen_modules_train_one_step():
     lg, lb = moco(torch.randn(4, 3, 32, 32), torch.randn(4, 3, 32, 32))
     assert lg.shape == (4, 17) and int(moco.queue_ptr) == 4
     u = U.Unet(dim=8, text_embed_dim=12, dim_mults=(1, 2), layer_attns=(False, True), layer_cross_attns=(False, True), attn_heads=2, attn_dim_head=4,
-               max_text_len=6, num_latents=2)
+               max_text_len=6, attn_pool_num_latents=2, resnet_groups=4)
     m = I.ImagenModel([u], image_sizes=[8], text_embed_dim=12, timesteps=2)
     out = m(torch.rand(2, 3, 8, 8), text_embeds=torch.randn(2, 4, 12), text_masks=torch.ones(2, 4))
     assert torch.isfinite(I.ImagenCriterion()(*out))
