@@ -49,6 +49,8 @@ def parse():
     p.add_argument("--fused-tp", type=int, default=0, help="1: all-gather->GEMM and GEMM->reduce-scatter as single kernels (TP+SP layouts)")
     p.add_argument("--step-overlap", type=int, default=-1, help="AdamW update issued per bucket on the side stream underneath the next forward pass: -1 auto (on), 0 off, 1 on")
     p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the result invalid)")
+    p.add_argument("--profile", type=int, default=0, help="after the timed region, run this many extra steps under the CUPTI profiler and write "
+                                                          "gpurun_out/bench_trace_n<N>_rank0.json.gz (kernel timeline; never part of the reported numbers)")
     return p.parse_args()
 
 
@@ -105,6 +107,34 @@ def reference_arm(args):
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
+
+
+def _profile_steps(args, device_step, barrier, rank, world):
+    """Kernel timeline of a few steps (rank 0): name, stream, start, duration of every kernel — compact json.gz for offline analysis."""
+    import gzip
+
+    import torch
+
+    barrier()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for i in range(args.profile):
+            device_step(i)
+        torch.cuda.synchronize()
+    barrier()
+    if rank != 0:
+        return
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    tmp = os.path.join(out_dir, f"_trace_tmp_{os.getpid()}.json")
+    prof.export_chrome_trace(tmp)
+    with open(tmp) as f:
+        trace = json.load(f)
+    os.remove(tmp)
+    rows = [[e.get("name", "")[:120], int(e.get("args", {}).get("stream", -1)), float(e["ts"]), float(e.get("dur", 0.0))]
+            for e in trace.get("traceEvents", []) if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "ts" in e]
+    rows.sort(key=lambda r: r[2])
+    with gzip.open(os.path.join(out_dir, f"bench_trace_n{world}_rank0.json.gz"), "wt") as f:
+        json.dump({"steps": args.profile, "model": args.model, "n_gpus": world, "columns": ["name", "stream", "ts_us", "dur_us"], "kernels": rows}, f)
 
 
 def build_config(args, world: int):
@@ -263,6 +293,8 @@ def main():
         e2e = {"value": global_batch * seq * args.steps / (float(t2.item()) / 1e3), "unit": "tokens/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
     clocks = sampler.stop() if sampler else None
+    if args.profile > 0:
+        _profile_steps(args, device_step, barrier, rank, world)
 
     symm = getattr(opt, "_symm", None)
     if world == 1:

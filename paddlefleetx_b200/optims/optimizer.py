@@ -23,6 +23,7 @@ forward pass.  Those kernels fit on an SM next to a persistent GEMM CTA, which N
 from __future__ import annotations
 
 import math
+import os as _os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -92,8 +93,6 @@ class FusedAdamW:
         # runs underneath the compute-bound GEMMs of the next forward pass instead of in front of it.  Needs direct gradient writes (no
         # memset of the gradient buffer between step and backward) and the device-resident native update.
         self.step_overlap = (bool(step_overlap) or self.use_p2p) and named[0][1].is_cuda and not self.offload
-        import os as _os
-
         self._rs_ctas = int(_os.environ.get("PFX_RS_CTAS", "64"))
         self._bcast_ctas = int(_os.environ.get("PFX_BCAST_CTAS", "296"))
 
@@ -123,13 +122,22 @@ class FusedAdamW:
 
             self._symm = get_allocator(self.sh_group)
             alloc = self._symm.alloc_tensor
-        self.groups: List[FlatGroup] = build_flat_groups(params, key_fn, pad_multiple=self.sh_world, grad_dtype=grad_dtype, alloc_fn=alloc)
-        self.groups.sort(key=lambda g: (g.key[0] if g.key[0] >= 0 else 1 << 30))
         # Direct gradient writes: autograd never owns a view of the flat grad buffer.  ``p.main_grad`` (bf16 or fp32 view) is
         # the only persistent gradient; the wgrad GEMM stores straight into it (first touch after clear_grad = plain store, no
         # zero-fill pass and no read-modify-write), every other parameter's grad is moved in by the post-accumulate hook.
         # That removes the per-parameter ``grad += new`` passes and the whole-buffer memset of the classic layout.
         self.direct_grad = bool(use_main_grad or ((params[0].is_cuda if direct_grad is None else direct_grad) and not params_are_shards))
+        # ZeRO stage 2: the full-size gradient of a bucket exists only while its layers are in backward.  Bucketed groups write into a
+        # small RING of bucket-sized buffers (bucket i uses slot i % K); when the last gradient of a bucket has arrived it is
+        # reduce-scattered into the rank's persistent 1/N gradient shard and the slot is reused K buckets later.  Needs direct gradient
+        # writes (a reused slot holds another bucket's data: the first write must be a store, not an accumulation).
+        self.grad_ring = bool(self.sharding_stage == 2 and self.sh_world > 1 and self.direct_grad and not params_are_shards and not self.offload
+                              and _os.environ.get("PFX_ZERO2_RING", "1") != "0")
+        self.groups: List[FlatGroup] = build_flat_groups(params, key_fn, pad_multiple=self.sh_world, grad_dtype=grad_dtype, alloc_fn=alloc,
+                                                         allocate_grads=not self.grad_ring)
+        self.groups.sort(key=lambda g: (g.key[0] if g.key[0] >= 0 else 1 << 30))
+        if self.grad_ring:
+            self._build_grad_ring(grad_dtype, alloc)
         if self.direct_grad:
             for g in self.groups:
                 attach_grad_views(g, main_grad=True)
@@ -181,6 +189,44 @@ class FusedAdamW:
         self._ag_events: Dict[int, "torch.cuda.Event"] = {}
         self._fwd_hooks_installed = False
 
+    # ------------------------------------------------------------------ ZeRO-2 gradient ring
+    def _build_grad_ring(self, grad_dtype, alloc) -> None:
+        slots = int(_os.environ.get("PFX_ZERO2_SLOTS", "3"))
+        dev = self.groups[0].param_buf.device
+        mk = alloc or (lambda n, dt, d: torch.zeros(n, dtype=dt, device=d))
+        ring_groups = [g for g in self.groups if g.key[0] >= 0 and not g.key[3]]          # bucketed, not expert-private
+        by_dtype: Dict[torch.dtype, List[FlatGroup]] = {}
+        for g in ring_groups:
+            by_dtype.setdefault(grad_dtype or g.param_buf.dtype, []).append(g)
+        self._ring: Dict[torch.dtype, List[torch.Tensor]] = {}
+        for g in self.groups:
+            gd = grad_dtype or g.param_buf.dtype
+            peers = by_dtype.get(gd, [])
+            if g in peers and len(peers) > slots:
+                if gd not in self._ring:
+                    size = max(x.numel for x in peers)
+                    self._ring[gd] = [mk(size, gd, dev) for _ in range(slots)]
+                idx = peers.index(g)                                  # backward completes buckets in this order
+                g.grad_buf = self._ring[gd][idx % slots][:g.numel]
+                lo, hi = g.shard_range(self.sh_rank, self.sh_world)
+                g.meta["grad_shard"] = torch.zeros(hi - lo, dtype=gd, device=dev)
+                g.meta["ring_idx"], g.meta["ring_dtype"], g.meta["shard_fresh"] = idx, gd, True
+            else:
+                g.grad_buf = mk(g.numel, gd, dev)                     # small / private groups keep a full buffer of their own
+        self._ring_order = {gd: [x for x in gs if "ring_idx" in x.meta] for gd, gs in by_dtype.items()}
+        self._ring_slots = slots
+        n_ring = sum(len(v) for v in self._ring_order.values())
+        if n_ring:
+            full = sum(x.numel * x.grad_buf.element_size() for v in self._ring_order.values() for x in v)
+            held = sum(t.numel() * t.element_size() for v in self._ring.values() for t in v) + sum(
+                x.meta["grad_shard"].numel() * x.meta["grad_shard"].element_size() for v in self._ring_order.values() for x in v)
+            logger.info(f"ZeRO-2: {n_ring} gradient buckets share {slots} ring slots: {held / 2 ** 20:.0f} MiB of gradient memory instead of {full / 2 ** 20:.0f} MiB")
+
+    def _grad_for_update(self, g: FlatGroup) -> torch.Tensor:
+        """This rank's reduced gradient shard of the group."""
+        sh = g.meta.get("grad_shard")
+        return sh if sh is not None else g.grad_buf[g.meta["lo"]:g.meta["hi"]]
+
     # ------------------------------------------------------------------ exposed-communication accounting
     def comm_meter_start(self) -> None:
         """Start measuring how long the COMPUTE stream is blocked on the communication stream (gradient reduce-scatter not finished
@@ -231,6 +277,8 @@ class FusedAdamW:
         for g in self.groups:
             g.meta["synced"] = False
             g.meta["pending"] = len(g.params)
+            if "grad_shard" in g.meta:
+                g.meta["shard_fresh"] = True
             if self.direct_grad:
                 for p in g.params:          # lazy zero: the first writer of the step overwrites (see _finalize_fresh)
                     p.grad = None
@@ -271,11 +319,16 @@ class FusedAdamW:
                 param._grad_fresh = False
                 param.grad_added_to_main_grad = False
                 param.grad = None
-            if self._accumulating or not self.reduce_overlap:
+            ring = "ring_idx" in g.meta
+            if not ring and (self._accumulating or not self.reduce_overlap):
                 return
             g.meta["pending"] -= 1
             if g.meta["pending"] == 0 and self.replicas > 1:
-                self._sync_group_grads(g, async_op=True)
+                # a ring bucket must leave its slot now — also in the middle of gradient accumulation (its shard accumulates instead)
+                self._sync_group_grads(g, async_op=self.reduce_overlap)
+                if ring:
+                    g.meta["pending"] = len(g.params)
+                    g.meta["synced"] = not self._accumulating
         return hook
 
     class _NoSync:
@@ -300,12 +353,16 @@ class FusedAdamW:
             g.meta["synced"] = True      # expert parameters are private to their rank: no replica reduction
             return
         lo, hi = g.meta["lo"], g.meta["hi"]
+        ring = "ring_idx" in g.meta
+        shard = g.meta.get("grad_shard")
+        acc = bool(ring and not g.meta["shard_fresh"])       # later micro-batches of an accumulation step add to the shard
         stream_ctx = None
         if async_op and self._comm_stream is not None:
             self._comm_stream.wait_stream(torch.cuda.current_stream())
             stream_ctx = torch.cuda.stream(self._comm_stream)
             stream_ctx.__enter__()
         try:
+            out = shard if ring else g.grad_buf[lo:hi]
             if self.sh_world > 1:
                 if self.use_p2p:
                     # rank r reduces slice r of every rank's bucket — in the switch (multimem.ld_reduce) or by pulling over the
@@ -313,19 +370,56 @@ class FusedAdamW:
                     # One barrier in front (every rank's gradients of this bucket are complete); the barrier behind every AdamW
                     # broadcast of the same step is what protects the buckets against the next backward pass.
                     self._symm.barrier()
-                    fuse_sq = self._norm_counted(g) and self.dp_world == 1
-                    _native.require().symm_reduce_scatter(g.meta["mc_grads"], g.meta["peer_grads"], lo, g.grad_buf[lo:hi], self.sh_rank,
-                                                          _DTYPE_CODE[g.grad_buf.dtype], 1.0, False, self._sq if fuse_sq else None, self._rs_ctas)
+                    fuse_sq = self._norm_counted(g) and self.dp_world == 1 and not ring
+                    _native.require().symm_reduce_scatter(self._symm.mc_ptr(g.grad_buf) if g.meta["mc_grads"] else 0, self._symm.peer_ptrs(g.grad_buf) if ring
+                                                          else g.meta["peer_grads"], lo, out, self.sh_rank, _DTYPE_CODE[g.grad_buf.dtype], 1.0, acc,
+                                                          self._sq if fuse_sq else None, self._rs_ctas)
                     g.meta["sq_fused"] = fuse_sq
+                    if ring:
+                        self._symm.barrier()        # the slot is rewritten by another bucket soon: every peer must have finished reading it
                     OF._count(2)
+                elif ring:
+                    self._nccl_rs_into(g, out, acc)
                 else:
                     self._nccl_rs(g)
             if self.dp_world > 1 and self.dp_group.process_group is not None:
-                dist.all_reduce(g.grad_buf[lo:hi], group=self.dp_group.process_group)
+                if acc:
+                    raise RuntimeError("ZeRO-2 gradient ring with gradient accumulation needs dp_degree == 1 (the dp all-reduce would re-reduce the accumulated shard)")
+                dist.all_reduce(out, group=self.dp_group.process_group)
+            if ring:
+                ev = None
+                if g.grad_buf.is_cuda:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                g.meta["rs_done"] = ev
+                g.meta["shard_fresh"] = False
+                for p in g.params:                   # the slot now belongs to the next bucket: this bucket's next write is a store again
+                    p._grad_fresh = True
         finally:
             if stream_ctx is not None:
                 stream_ctx.__exit__(None, None, None)
+        if ring and g.grad_buf.is_cuda:
+            # slot reuse: bucket i+2 writes where bucket i+2-K lived; make the compute stream wait for that reduction now (one bucket of
+            # slack against gradients that arrive slightly out of bucket order)
+            order = self._ring_order[g.meta["ring_dtype"]]
+            j = g.meta["ring_idx"] + 2 - self._ring_slots
+            if 0 <= j < len(order) and order[j].meta.get("rs_done") is not None:
+                self._wait(order[j].meta["rs_done"])
         g.meta["synced"] = True
+
+    def _nccl_rs_into(self, g: FlatGroup, out: torch.Tensor, accumulate: bool) -> None:
+        lo, hi = g.meta["lo"], g.meta["hi"]
+        pg = self.sh_group.process_group
+        if g.grad_buf.is_cuda:
+            dst = torch.empty_like(out) if accumulate else out
+            dist.reduce_scatter_tensor(dst, g.grad_buf, group=pg)
+        else:   # gloo: no reduce-scatter
+            dist.all_reduce(g.grad_buf, group=pg)
+            dst = g.grad_buf[lo:hi]
+        if accumulate:
+            out.add_(dst)
+        elif dst is not out:
+            out.copy_(dst)
 
     def _norm_counted(self, g: FlatGroup) -> bool:
         """Does this group enter the (dense) global gradient norm on this rank?  TP-sharded tensors count on every mp rank,
@@ -374,21 +468,21 @@ class FusedAdamW:
             lib = _native.require()
             for g in self.groups:
                 if self._norm_counted(g) and not g.meta.pop("sq_fused", False):
-                    lib.sumsq_(g.grad_buf[g.meta["lo"]:g.meta["hi"]], self._sq, True)
+                    lib.sumsq_(self._grad_for_update(g), self._sq, True)
                     OF._count(2)
             sq = self._sq
             if any(g.key[3] for g in self.groups):
                 moe_sq = torch.zeros_like(self._sq)
                 for g in self.groups:
                     if g.key[3]:
-                        lib.sumsq_(g.grad_buf[g.meta["lo"]:g.meta["hi"]], moe_sq, True)
+                        lib.sumsq_(self._grad_for_update(g), moe_sq, True)
         else:
             mp_rank = self.hcg.get_model_parallel_rank() if self.hcg is not None else 0
             sq = torch.zeros(1, dtype=torch.float32, device=self._dev)
             for g in self.groups:
                 if g.key[4]:
                     continue
-                s = g.grad_buf[g.meta["lo"]:g.meta["hi"]].float().pow(2).sum()
+                s = self._grad_for_update(g).float().pow(2).sum()
                 if g.key[3]:
                     moe_sq = s.reshape(1) if moe_sq is None else moe_sq + s
                 elif g.key[2] or mp_rank == 0:
@@ -414,13 +508,13 @@ class FusedAdamW:
                     lp = g.param_buf[lo:hi] if g.meta["has_master"] else None
                     shared = self.sh_world > 1 and not g.key[3]
                     if self.use_p2p and shared and g.meta["has_master"]:
-                        lib.adamw_symm_broadcast_(g.meta["mc_params"], g.meta["peer_params"], lo, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"],
+                        lib.adamw_symm_broadcast_(g.meta["mc_params"], g.meta["peer_params"], lo, g.meta["master"], self._grad_for_update(g), g.meta["m"],
                                                   g.meta["v"], lr, self.beta1, self.beta2, self.eps, wd, self._step_count, self._gscale,
                                                   self._found_inf, _DTYPE_CODE[g.param_buf.dtype], self.sh_rank, self._bcast_ctas)
                         self._symm.barrier()
                         OF._count(2)
                     else:
-                        lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
+                        lib.adamw_flat_(lp, g.meta["master"], self._grad_for_update(g), g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
                                         wd, self._step_count, self._gscale, self._found_inf)
                         OF._count()
                         if shared:
@@ -445,7 +539,7 @@ class FusedAdamW:
                 lo, hi = g.meta["lo"], g.meta["hi"]
                 wd = self.weight_decay if g.key[1] else 0.0
                 lp = g.param_buf[lo:hi] if g.meta["has_master"] else None
-                lib.adamw_flat_(lp, g.meta["master"], g.grad_buf[lo:hi], g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
+                lib.adamw_flat_(lp, g.meta["master"], self._grad_for_update(g), g.meta["m"], g.meta["v"], lr, self.beta1, self.beta2, self.eps,
                                 wd, self._step_count, self._gscale, self._found_inf)
                 OF._count()
         else:
@@ -463,7 +557,7 @@ class FusedAdamW:
                 bc2 = 1.0 - self.beta2 ** self._step_count
                 for g in self.groups:
                     lo, hi = g.meta["lo"], g.meta["hi"]
-                    grad = g.grad_buf[lo:hi].float() * (inv_scale * coef)
+                    grad = self._grad_for_update(g).float() * (inv_scale * coef)
                     m, v, w = g.meta["m"], g.meta["v"], g.meta["master"]
                     if self.offload:
                         grad = grad.to(m.device)              # D2H: the update runs where the state lives

@@ -68,6 +68,43 @@ def dp_sharding_matches_single(rank, world, dp, sharding, stage, extra=()):
         assert g.meta["m"].numel() == g.numel // sharding
 
 
+def zero2_ring_matches_single(rank, world, micro):
+    """ZeRO stage 2 with the gradient ring (many small buckets sharing 2 slots), with and without gradient accumulation: same losses and
+    weights as one process, and the full-size gradient really is gone (buckets alias the ring, each keeps a 1/N shard)."""
+    import os
+
+    os.environ["PFX_ZERO2_SLOTS"] = "2"
+    gb = 8
+    _, batches, ref_losses, ref_state, init = _reference_losses_and_state(
+        ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}", "Model.num_layers=4"], 3)
+    cfg = tiny_gpt_config(["Model.num_layers=4", f"Global.global_batch_size={gb}", "Global.local_batch_size=None", f"Global.micro_batch_size={micro}",
+                           "Distributed.sharding.sharding_degree=2", "Distributed.sharding.sharding_stage=2", "Distributed.sharding.bucket_mb=0.02",
+                           "Distributed.sharding.reduce_overlap=True", "Optimizer.direct_grad=True"], nranks=world)
+    from paddlefleetx_b200.core import EagerEngine
+    from paddlefleetx_b200.distributed.apis import env
+    from paddlefleetx_b200.models import build_module
+
+    env.init_dist_env(cfg)
+    env.set_seed(cfg.Global.seed)
+    module = build_module(cfg)
+    module.model.load_state_dict(init)
+    eng = EagerEngine(configs=cfg, module=module)
+    opt = eng.optimizer
+    ring = [g for g in opt.groups if "ring_idx" in g.meta]
+    assert opt.grad_ring and len(ring) >= 4, (opt.grad_ring, len(ring), len(opt.groups))
+    assert ring[0].grad_buf.data_ptr() == ring[2].grad_buf.data_ptr() != ring[1].grad_buf.data_ptr()
+    assert all(g.meta["grad_shard"].numel() == g.numel // 2 for g in ring)
+    dr, dw = env.get_data_world_rank(), env.get_data_world_size()
+    losses = []
+    for b in batches:
+        l = eng.train_step(_slice(b, dr, dw)).detach().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)
+    assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
+    for k, v in eng.module.model.state_dict().items():
+        assert torch.allclose(v, ref_state[k], atol=5e-5, rtol=1e-4), k
+
+
 def _shard_like(full: torch.Tensor, p: torch.nn.Parameter, mp_rank: int, mp: int) -> torch.Tensor:
     if getattr(p, "tp_sharded", False):
         return full.chunk(mp, dim=p.split_axis)[mp_rank].clone()

@@ -22,6 +22,11 @@ def test_sharding2_stage2_direct_grad_overlap_matches_single():
                     ("Optimizer.direct_grad=True", "Distributed.sharding.reduce_overlap=True"))
 
 
+@pytest.mark.parametrize("micro", [4, 2])
+def test_sharding2_stage2_gradient_ring_matches_single(micro):
+    run_distributed("dist_fns:zero2_ring_matches_single", 2, micro)
+
+
 def test_dp2_x_sharding2_matches_single():
     run_distributed("dist_fns:dp_sharding_matches_single", 4, 2, 2, 1)
 
