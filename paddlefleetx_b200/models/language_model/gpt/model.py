@@ -341,11 +341,15 @@ class GPTEmbeddings(nn.Module):
         self.group = mp_group
 
     def forward(self, input_ids: torch.Tensor, position_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
-        x = self.word_embeddings(input_ids)
-        if not self.use_rope:
-            if position_ids is None:
-                position_ids = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0).expand_as(input_ids)
-            x = x + self.position_embeddings(position_ids)
+        if not self.use_rope and position_ids is None:
+            position_ids = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0).expand_as(input_ids)
+        if not self.use_rope and self.word_embeddings.world == 1:
+            # word + position look-up and their sum in one kernel (csrc/embedding.cu); backward scatters into both tables deterministically
+            x = self.word_embeddings(input_ids, position_ids.contiguous(), self.position_embeddings.weight)
+        else:
+            x = self.word_embeddings(input_ids)
+            if not self.use_rope:
+                x = x + self.position_embeddings(position_ids)
         if self.sequence_parallel:
             x = C.scatter_seq(x.transpose(0, 1).contiguous(), self.group)     # [s/n, b, h]
             return OF.dropout(x, self.hidden_dropout, self.training, "local_seed")

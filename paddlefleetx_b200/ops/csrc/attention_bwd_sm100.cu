@@ -15,8 +15,10 @@
 //
 // The same shared-memory tiles serve as K-major and MN-major operands (a 128-byte-swizzled [rows x 64] panel is both), so Q_i,
 // dO_i, K_j, V_j are loaded once by TMA straight from the framework layout ([B, S, H, D] views, packed QKV included) and P^T / dS^T
-// are written once by the threads that produce them.  dQ is accumulated across key tiles with fp32 reductions into a workspace
-// and converted to bf16 afterwards; lse (log2 units) and delta = rowsum(dO o O) come from a small preprocessing kernel.
+// are written once by the threads that produce them.  dQ is accumulated across key tiles in an fp32 workspace: the drain warps move
+// each dQ^T tile TMEM -> registers -> (transposed) shared memory and ONE TMA reduce-add (cp.reduce.async.bulk.tensor) folds it into
+// global memory — per-lane red.global instructions cost ~1.3 cycles per lane on the SM and were 5x the tensor-core time of a tile
+// (first version: 0.55 ms at B8 S1024 H32); the workspace is converted to bf16 afterwards; lse (log2 units) and delta = rowsum(dO o O) come from a small preprocessing kernel.
 //
 // Warp roles (448 threads): warp 0 TMA producer (K/V once, then a 2-stage ring of Q_i / dO_i / lse_i / delta_i), warp 1 MMA
 // issuer, warps 2-9 softmax-gradient math (two threads per key row, 32 query columns each), warps 10-13 drain dQ^T.
@@ -49,7 +51,9 @@ struct BwSmem {
   static constexpr int kOffDo = kOffQ + 2 * kQBytes;     // 2 stages
   static constexpr int kOffP = kOffDo + 2 * kQBytes;
   static constexpr int kOffDs = kOffP + kPBytes;
-  static constexpr int kOffStat = kOffDs + kPBytes;      // 2 stages
+  static constexpr int kDqBytes = kQt * kHd * 4;         // 32 KB: dQ tile [64 q][128 d] fp32, row-major (TMA reduce source)
+  static constexpr int kOffDq = kOffDs + kPBytes;
+  static constexpr int kOffStat = kOffDq + kDqBytes;     // 2 stages
   static constexpr int kOffBar = kOffStat + 2 * kStatBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kUsed = kOffBar + kBarBytes;
@@ -80,13 +84,14 @@ __device__ __forceinline__ void tma_tile(const CUtensorMap* m, bool swapped, uin
 
 __global__ void __launch_bounds__(kBwThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-                     const __grid_constant__ CUtensorMap tmap_do, const __grid_constant__ BwParams prm) {
+                     const __grid_constant__ CUtensorMap tmap_do, const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ BwParams prm) {
   using S = BwSmem;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t s_k = smem_base + S::kOffK, s_v = smem_base + S::kOffV, s_q = smem_base + S::kOffQ, s_do = smem_base + S::kOffDo;
-  const uint32_t s_p = smem_base + S::kOffP, s_ds = smem_base + S::kOffDs, s_stat = smem_base + S::kOffStat, s_bar = smem_base + S::kOffBar;
+  const uint32_t s_p = smem_base + S::kOffP, s_ds = smem_base + S::kOffDs, s_dq = smem_base + S::kOffDq, s_stat = smem_base + S::kOffStat;
+  const uint32_t s_bar = smem_base + S::kOffBar;
   auto bar = [&](int i) { return s_bar + 8u * i; };
   const uint32_t kv_full = bar(0);
   auto q_full = [&](int s) { return bar(1 + s); };
@@ -108,7 +113,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const int n_iter = n_q_tiles - i_begin;         // >= 1 for every key tile that holds a valid key
 
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_dq);
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -341,10 +346,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
     tcgen05_fence_before();
   } else {
-    // ======================================================================================= dQ^T drain: TMEM -> fp32 reductions in global memory
+    // ======================================================================================= dQ^T drain: TMEM -> smem (transposed) -> TMA reduce-add
     const uint32_t quarter = warp & 3u;
     const int d = (int)(quarter * 32u + lane);                  // channel == TMEM lane
     const uint32_t lane_addr = (quarter * 32u) << 16;
+    const bool leader = warp == 10 && lane == 0;
     for (int it = 0; it < n_iter; ++it) {
       const int q0 = (i_begin + it) * kQt;
       mbar_wait(dq_full, (uint32_t)it & 1u);
@@ -356,15 +362,22 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_free);
-      float* base = prm.dq_acc + (((size_t)b * prm.Sq + q0) * prm.H + h) * kHd + d;
-      const size_t q_stride = (size_t)prm.H * kHd;
+      if (leader) tma_store_wait_read<0>();                     // the previous tile's reduce has finished reading the staging buffer
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t col = s_dq + (uint32_t)d * 4u;             // staging tile [64 q][128 d] fp32: a warp writes 32 consecutive floats of one row
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (q0 + c < prm.Sq) red_add_f32(base + (size_t)c * q_stride, __uint_as_float(r0[c]));
+      for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + (uint32_t)c * 512u), "r"(r0[c]) : "memory");
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (q0 + 32 + c < prm.Sq) red_add_f32(base + (size_t)(32 + c) * q_stride, __uint_as_float(r1[c]));
+      for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + (uint32_t)(32 + c) * 512u), "r"(r1[c]) : "memory");
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (leader) {
+        // rows of the 2-D [B*Sq, H*128] view; query rows past Sq of a ragged tile carry exact zeros (P = 0 there), rows past the tensor are dropped
+        tma_reduce_add_2d(&tmap_dq, s_dq, h * kHd, b * prm.Sq + q0);
+        tma_store_commit();
+      }
     }
+    if (leader) tma_store_wait<0>();
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc<1>(tmem, 512);
@@ -444,10 +457,11 @@ cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& 
         (const __nv_bfloat16*)out.ptr, out.sb, out.ss, out.sh, (const __nv_bfloat16*)dout.ptr, dout.sb, dout.ss, dout.sh, lse, lse2, delta, B, Sq, H, Sq_pad);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq;
   bool sq = false, sk = false, sv = false, sdo = false;
   bool ok = make_map(&tq, q, B, Sq, H, D, kQt, &sq) && make_map(&tk, k, B, Sk, H, D, kKv, &sk) && make_map(&tv, v, B, Sk, H, D, kKv, &sv) &&
-            make_map(&tdo, dout, B, Sq, H, D, kQt, &sdo);
+            make_map(&tdo, dout, B, Sq, H, D, kQt, &sdo) &&
+            make_tmap_2d_plain(&tdq, dq_acc, 3, (uint64_t)H * kHd, (uint64_t)B * Sq, (uint64_t)H * kHd * 4, kHd, kQt);
   if (!ok) return cudaErrorInvalidValue;
   BwParams prm{};
   prm.lse2 = lse2; prm.delta = delta; prm.dq_acc = dq_acc;
@@ -467,7 +481,7 @@ cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& 
     attr_set = true;
   }
   const int n_kv = (Sk + kKv - 1) / kKv;
-  attention_bwd_kernel<<<(unsigned)(n_kv * B * H), kBwThreads, BwSmem::kTotal, st>>>(tq, tk, tv, tdo, prm);
+  attention_bwd_kernel<<<(unsigned)(n_kv * B * H), kBwThreads, BwSmem::kTotal, st>>>(tq, tk, tv, tdo, tdq, prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   attn_bwd_dq_convert_kernel<<<1184, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)const_cast<void*>(dq.ptr), dq.sb, dq.ss, dq.sh, B, Sq, H);
   return cudaGetLastError();

@@ -339,7 +339,9 @@ void clip_coef_(const at::Tensor& sq, double inv_loss_scale, double clip_norm, a
 }
 void adamw_flat_(c10::optional<at::Tensor> p_lp, at::Tensor& master, const at::Tensor& grad, at::Tensor& m, at::Tensor& v, double lr,
                  double beta1, double beta2, double eps, double wd, int64_t step, c10::optional<at::Tensor> gscale,
-                 c10::optional<at::Tensor> found_inf) {
+                 c10::optional<at::Tensor> found_inf, int64_t cta_budget) {
+  // cta_budget > 0: grid size cap (the kernel is launched with cta_budget CTAs instead of 8 per SM) — used when the update runs on a side
+  // stream underneath GEMMs and must not take the whole memory system
   PFX_CHECK_CUDA_CONTIG(master); PFX_CHECK_CUDA_CONTIG(grad);
   const c10::cuda::CUDAGuard guard(master.device());
   const size_t n = master.numel();
@@ -350,7 +352,7 @@ void adamw_flat_(c10::optional<at::Tensor> p_lp, at::Tensor& master, const at::T
                                  v.data_ptr<float>(), n, (float)lr, (float)beta1, (float)beta2, (float)eps, (float)wd, bc1, bc2,
                                  (gscale.has_value() && gscale->defined()) ? gscale->data_ptr<float>() : nullptr,
                                  (found_inf.has_value() && found_inf->defined()) ? found_inf->data_ptr<float>() : nullptr,
-                                 dtype_code(grad), has_lp ? dtype_code(*p_lp) : 3, num_sms(), cur_stream()));
+                                 dtype_code(grad), has_lp ? dtype_code(*p_lp) : 3, cta_budget > 0 ? (int)((cta_budget + 7) / 8) : num_sms(), cur_stream()));
 }
 void accumulate_f32_(at::Tensor& dst, const at::Tensor& src, double scale) {
   const c10::cuda::CUDAGuard guard(dst.device());
@@ -624,6 +626,36 @@ std::vector<at::Tensor> attention_fwd(const at::Tensor& q, const at::Tensor& k, 
   return {out, lse};
 }
 
+// out[t] = w[ids[t] - vocab_start] (zero for foreign ids) (+ pos_w[pos[t]])
+at::Tensor embedding_fwd(const at::Tensor& ids, const at::Tensor& w, c10::optional<at::Tensor> pos, c10::optional<at::Tensor> pos_w, int64_t vocab_start) {
+  PFX_CHECK_CUDA_CONTIG(ids); PFX_CHECK_CUDA_CONTIG(w);
+  TORCH_CHECK(ids.scalar_type() == at::kLong && w.dim() == 2, "embedding_fwd: int64 ids, 2-D weight");
+  const bool with_pos = pos.has_value() && pos->defined();
+  if (with_pos) {
+    TORCH_CHECK(pos_w.has_value() && pos_w->defined() && pos->is_contiguous() && pos_w->is_contiguous() && pos->numel() == ids.numel() &&
+                pos->scalar_type() == at::kLong && pos_w->scalar_type() == w.scalar_type() && pos_w->size(1) == w.size(1), "embedding_fwd: position operands");
+  }
+  const c10::cuda::CUDAGuard guard(w.device());
+  auto sizes = ids.sizes().vec();
+  sizes.push_back(w.size(1));
+  auto out = at::empty(sizes, w.options());
+  PFX_CUDA_CHECK(pfx::embedding_fwd(ids.data_ptr<int64_t>(), w.data_ptr(), with_pos ? pos->data_ptr<int64_t>() : nullptr, with_pos ? pos_w->data_ptr() : nullptr,
+                                    out.data_ptr(), ids.numel(), (int)w.size(1), vocab_start, w.size(0), dtype_code(w), cur_stream()));
+  return out;
+}
+int64_t embedding_bwd_max_tokens() { return pfx::embedding_bwd_max_tokens(); }
+// dw[ids[t] - vocab_start] (+)= sum over equal ids of dout[t]   (rows that do not occur are left untouched)
+void embedding_bwd_(const at::Tensor& ids, const at::Tensor& dout, at::Tensor& dw, int64_t vocab_start, bool accumulate) {
+  PFX_CHECK_CUDA_CONTIG(ids); PFX_CHECK_CUDA_CONTIG(dout); PFX_CHECK_CUDA_CONTIG(dw);
+  TORCH_CHECK(ids.scalar_type() == at::kLong && dw.dim() == 2 && dout.numel() == ids.numel() * dw.size(1), "embedding_bwd_: shape mismatch");
+  const c10::cuda::CUDAGuard guard(dw.device());
+  int64_t n2 = 2;
+  while (n2 < ids.numel()) n2 <<= 1;
+  auto ws = at::empty({n2}, ids.options());
+  PFX_CUDA_CHECK(pfx::embedding_bwd(ids.data_ptr<int64_t>(), dout.data_ptr(), dw.data_ptr(), reinterpret_cast<unsigned long long*>(ws.data_ptr<int64_t>()),
+                                    ids.numel(), (int)dw.size(1), vocab_start, dw.size(0), dtype_code(dout), dtype_code(dw), accumulate, cur_stream()));
+}
+
 static pfx::AttnView attn_view(const at::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.dim() == 4 && t.scalar_type() == at::kBFloat16 && t.stride(3) == 1, name, ": [B,S,H,D] bf16 CUDA view with contiguous D expected");
   TORCH_CHECK(t.stride(0) % 8 == 0 && t.stride(1) % 8 == 0 && t.stride(2) % 8 == 0 && (reinterpret_cast<uintptr_t>(t.data_ptr()) % 16) == 0,
@@ -746,7 +778,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ce_bwd_", &ce_bwd_);
   m.def("sumsq_", &sumsq_);
   m.def("clip_coef_", &clip_coef_);
-  m.def("adamw_flat_", &adamw_flat_);
+  m.def("adamw_flat_", &adamw_flat_, py::arg("p_lp"), py::arg("master"), py::arg("grad"), py::arg("m"), py::arg("v"), py::arg("lr"), py::arg("beta1"),
+        py::arg("beta2"), py::arg("eps"), py::arg("wd"), py::arg("step"), py::arg("gscale") = py::none(), py::arg("found_inf") = py::none(),
+        py::arg("cta_budget") = 0);
   m.def("accumulate_f32_", &accumulate_f32_);
   m.def("topp_sampling", &topp_sampling);
   m.def("rope", &rope);
@@ -761,6 +795,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("attention_fwd", &attention_fwd);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd_", &embedding_bwd_);
+  m.def("embedding_bwd_max_tokens", &embedding_bwd_max_tokens);
   m.def("attention_fwd_v2", &attention_fwd_v2);
   m.def("attention_bwd", &attention_bwd);
   m.def("attention_decode", &attention_decode);

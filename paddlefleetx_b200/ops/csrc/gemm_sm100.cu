@@ -446,6 +446,19 @@ bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_c
   return r == CUDA_SUCCESS;
 }
 
+bool make_tmap_2d_plain(CUtensorMap* map, const void* ptr, int dtype_code, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  const CUtensorMapDataType dt = dtype_code == 3 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (dtype_code == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype_code, uint64_t inner, uint64_t S, uint64_t B, uint64_t s_stride_bytes,
                     uint64_t b_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool* swapped) {
   auto fn = get_encode_fn();

@@ -61,6 +61,10 @@ cudaError_t gemm_lowp_tcgen05(const LowpGemmArgs& args, cudaStream_t stream);
 bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_code, uint64_t inner, uint64_t outer,
                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
+// 2-D row-major tensor without shared-memory swizzle (plain row-major box in smem): fp32 reduction targets.
+bool make_tmap_2d_plain(CUtensorMap* map, const void* ptr, int dtype_code, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer);
+
 // 3-D tensor map over a [B, S, H, D] activation view (D contiguous, `inner` = columns spanned by one (b, s) row): dims are
 // {inner, S, B} or — when the batch stride is the smaller one (sequence-major [S, B, ...] storage) — {inner, B, S}; `*swapped`
 // tells the kernel which coordinate order to pass.  Box = {box_cols, box_rows along S, 1}, 128-byte swizzle.

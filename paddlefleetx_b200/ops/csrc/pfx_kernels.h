@@ -72,6 +72,13 @@ cudaError_t attention_fwd(const void* q, const void* k, const void* v, void* out
 cudaError_t attention_decode(const void* q, void* k, void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
                              float scale, int dtype, cudaStream_t st, const int64_t* write_idx = nullptr);
 
+// embedding.cu — fused word (+ position) look-up; deterministic sorted scatter-add gradient (workspace: next_pow2(tokens) 64-bit keys)
+cudaError_t embedding_fwd(const int64_t* ids, const void* w, const int64_t* pos, const void* pw, void* out, int64_t tokens, int hidden,
+                          int64_t vocab_start, int64_t rows, int dtype, cudaStream_t st);
+int embedding_bwd_max_tokens();
+cudaError_t embedding_bwd(const int64_t* ids, const void* dout, void* dw, unsigned long long* workspace, int64_t tokens, int hidden,
+                          int64_t vocab_start, int64_t rows, int dtype, int grad_dtype, bool accumulate, cudaStream_t st);
+
 // moe_kernels.cu — expert-parallel dispatch / combine over peer memory
 cudaError_t moe_route(const int64_t* gate_idx, int num_slots, int total_experts, int* slot_rank, int* counts, cudaStream_t st);
 cudaError_t moe_dispatch(const void* src, const float* scale, const int64_t* gate_idx, const int* slot_rank, const int* counts, int* slot_loc,

@@ -199,6 +199,75 @@ def native_available() -> bool:
     return _native.available()
 
 
+class _EmbeddingFn(torch.autograd.Function):
+    """out = W[ids - vocab_start] (zero rows for ids of other vocab shards) (+ P[pos]).  Backward: deterministic sorted scatter-add
+    (csrc/embedding.cu) straight into the flat optimizer's ``main_grad`` rows when present — the tied LM head has usually written that
+    buffer already, so only the rows that occur are touched — or into a dense gradient otherwise."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, vocab_start, pos_ids, pos_weight):
+        lib = _native.require()
+        ids_c = ids.contiguous()
+        pos_c = pos_ids.contiguous() if pos_ids is not None else None
+        out = lib.embedding_fwd(ids_c, weight, pos_c, pos_weight, int(vocab_start))
+        _count()
+        ctx.save_for_backward(ids_c, pos_c if pos_c is not None else ids_c)
+        ctx.weights = (weight, pos_weight)
+        ctx.vocab_start = int(vocab_start)
+        return out
+
+    @staticmethod
+    def _scatter(lib, ids, dout2, weight, vocab_start):
+        main_grad = getattr(weight, "main_grad", None)
+        if main_grad is not None:
+            if getattr(weight, "_grad_fresh", False):
+                main_grad.zero_()
+            target, ret = main_grad, torch.empty_like(weight)      # placeholder: the optimizer hook drops it (see _wgrad)
+            weight._grad_fresh = False
+            weight.grad_added_to_main_grad = True
+        else:
+            target = ret = torch.zeros_like(weight)
+        flat = ids.reshape(-1)
+        step = int(lib.embedding_bwd_max_tokens())
+        for a in range(0, flat.numel(), step):                     # one sorted pass per <= 16 K tokens, in token order: deterministic
+            lib.embedding_bwd_(flat[a:a + step], dout2[a:a + step], target, vocab_start, True)
+            _count(2)
+        return ret
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _native.require()
+        ids, pos = ctx.saved_tensors
+        weight, pos_weight = ctx.weights
+        d2 = dout.reshape(-1, dout.shape[-1])
+        if not d2.is_contiguous():
+            d2 = d2.contiguous()
+        gw = gp = None
+        if ctx.needs_input_grad[1]:
+            gw = _EmbeddingFn._scatter(lib, ids, d2, weight, ctx.vocab_start)
+        if pos_weight is not None and ctx.needs_input_grad[4]:
+            gp = _EmbeddingFn._scatter(lib, pos, d2, pos_weight, 0)
+        return None, gw, None, None, gp
+
+
+def embedding(ids: torch.Tensor, weight: torch.Tensor, vocab_start: int = 0, pos_ids: Optional[torch.Tensor] = None,
+              pos_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Word (+ position) embedding look-up; ``vocab_start`` selects this rank's rows of a vocabulary-parallel table (foreign ids give zero rows)."""
+    if (weight.is_cuda and weight.dtype in (torch.bfloat16, torch.float16) and weight.shape[1] % 8 == 0 and weight.is_contiguous() and ids.dtype == torch.int64
+            and (pos_weight is None or (pos_weight.dtype == weight.dtype and pos_weight.is_contiguous() and pos_ids is not None and pos_ids.dtype == torch.int64
+                                        and pos_ids.shape == ids.shape)) and _native.use_native(weight)):
+        return _EmbeddingFn.apply(ids, weight, vocab_start, pos_ids, pos_weight)
+    local = ids - vocab_start
+    if vocab_start != 0 or bool(((local < 0) | (local >= weight.shape[0])).any()):
+        oob = (local < 0) | (local >= weight.shape[0])
+        out = F.embedding(local.masked_fill(oob, 0), weight).masked_fill(oob.unsqueeze(-1), 0.0)
+    else:
+        out = F.embedding(ids, weight)
+    if pos_weight is not None:
+        out = out + F.embedding(pos_ids, pos_weight)
+    return out
+
+
 def gemv_max_rows() -> int:
     return _GEMV_MAX_ROWS
 

@@ -212,13 +212,13 @@ class VocabParallelEmbedding(nn.Module):
         _init_normal_sharded(self.weight, init_std, (num_embeddings, embedding_dim), 0, mp_group)
         _mark(self.weight, tp_sharded=self.world > 1, split_axis=0)
 
-    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+    def forward(self, ids: torch.Tensor, pos_ids=None, pos_weight=None) -> torch.Tensor:
+        """``pos_ids`` / ``pos_weight``: optional (replicated) position table added in the same kernel (single-rank vocabulary only: under
+        vocabulary parallelism the partial look-ups are summed over the group and the caller adds positions afterwards)."""
         if self.world == 1:
-            return torch.nn.functional.embedding(ids, self.weight)
-        local = ids - self.vocab_start
-        oob = (local < 0) | (local >= self.per_rank)
-        out = torch.nn.functional.embedding(local.masked_fill(oob, 0), self.weight)
-        out = out.masked_fill(oob.unsqueeze(-1), 0.0)
+            return OF.embedding(ids, self.weight, 0, pos_ids, pos_weight)
+        assert pos_weight is None, "fused position look-up needs an unsharded vocabulary"
+        out = OF.embedding(ids, self.weight, self.vocab_start)
         return C.reduce_from_group(out, self.group)
 
 

@@ -48,6 +48,7 @@ def main():
     span = (t1 - t0) / steps
     by_name, by_stream = defaultdict(lambda: [0.0, 0]), defaultdict(list)
     for name, stream, ts, dur in ks:
+        name = name.replace("(anonymous namespace)::", "")
         key = name.split("<")[0].split("(")[0][:70] if not name.startswith("void pfx::gemm") else name[:60]
         by_name[key][0] += dur
         by_name[key][1] += 1

@@ -642,6 +642,54 @@ def check_attention_decode():
     return dict(ok=ok, shapes=res)
 
 
+def check_embedding():
+    """Fused word + position look-up and the sorted scatter-add gradient against F.embedding autograd in fp32 (repeated ids, a vocabulary shard
+    with foreign ids, the main_grad store / accumulate protocol, > 16 K tokens)."""
+    import torch
+    import torch.nn.functional as F
+    from paddlefleetx_b200.ops import functional as OF
+    torch.manual_seed(0)
+    res, ok = {}, True
+    for (V, H, B, S, start, with_pos) in [(1000, 256, 4, 128, 0, True), (512, 1024, 2, 64, 256, False), (50304, 512, 20, 1024, 0, True)]:
+        w = (torch.randn(V if start == 0 else 256, H, device="cuda") * 0.1).bfloat16().requires_grad_(True)
+        pw = (torch.randn(S, H, device="cuda") * 0.1).bfloat16().requires_grad_(True) if with_pos else None
+        ids = torch.randint(0, V, (B, S), device="cuda")
+        ids[0, :8] = ids[0, 0]                        # a run of repeats
+        pos = torch.arange(S, device="cuda").expand(B, S).contiguous()
+        go = torch.randn(B, S, H, device="cuda").bfloat16()
+        out = OF.embedding(ids, w, start, pos if with_pos else None, pw)
+        out.backward(go)
+        wr = w.detach().float().requires_grad_(True)
+        local = ids - start
+        oob = (local < 0) | (local >= wr.shape[0])
+        ref = F.embedding(local.masked_fill(oob, 0), wr).masked_fill(oob.unsqueeze(-1), 0.0)
+        if with_pos:
+            pr = pw.detach().float().requires_grad_(True)
+            ref = ref + F.embedding(pos, pr)
+        ref.backward(go.float())
+        errs = dict(out=_relerr(out, ref), dw=_relerr(w.grad, wr.grad))
+        if with_pos:
+            errs["dpos"] = _relerr(pw.grad, pr.grad)
+        good = all(e < 1e-2 for e in errs.values())
+        ok = ok and good
+        res[f"V{V}_H{H}_T{B * S}_start{start}"] = {k: round(float(v), 5) for k, v in errs.items()}
+    # main_grad protocol: fresh -> zero + rows; then accumulate on top of an existing gradient
+    w = (torch.randn(300, 128, device="cuda") * 0.1).bfloat16().requires_grad_(True)
+    w.main_grad = torch.full((300, 128), 7.0, device="cuda", dtype=torch.float32)
+    w._grad_fresh = True
+    ids = torch.randint(0, 300, (3, 50), device="cuda")
+    go = torch.randn(3, 50, 128, device="cuda").bfloat16()
+    OF.embedding(ids, w).backward(go)
+    want = torch.zeros(300, 128, device="cuda").index_add_(0, ids.reshape(-1), go.float().reshape(-1, 128))
+    e1 = _relerr(w.main_grad, want)
+    w.grad = None
+    OF.embedding(ids, w).backward(go)                  # second micro-batch: accumulates
+    e2 = _relerr(w.main_grad, 2 * want)
+    ok = ok and e1 < 1e-5 and e2 < 1e-5 and not w._grad_fresh
+    res["main_grad"] = dict(store=e1, accumulate=e2)
+    return dict(ok=ok, cases=res)
+
+
 def check_gemm_big_sweep():
     """Multi-tile shapes (several tiles per CTA, both TMEM accumulator buffers alternating, dozens of k-blocks, ragged edges) for every
     (CTA-group, operand majors, output mode) against fp32."""
@@ -662,6 +710,7 @@ CHECKS = {
     "attention_train_perf": lambda: check_attention_train(perf=True),
     "attention_autograd": check_attention_autograd,
     "gemm_big_sweep": check_gemm_big_sweep,
+    "embedding": check_embedding,
     "attention_decode": check_attention_decode,
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
