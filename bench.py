@@ -49,6 +49,9 @@ def parse():
     p.add_argument("--fused-tp", type=int, default=0, help="1: all-gather->GEMM and GEMM->reduce-scatter as single kernels (TP+SP layouts)")
     p.add_argument("--step-overlap", type=int, default=-1, help="AdamW update issued per bucket on the side stream underneath the next forward pass: -1 auto (on), 0 off, 1 on")
     p.add_argument("--layers", type=int, default=0, help="debug only: override layer count (marks the result invalid)")
+    p.add_argument("--named-layout", default="auto", help="at 8 GPUs also measure BASELINE config #2 (mp2 x pp2 x sharding2, fused TP kernels) in a child job after "
+                                                         "the headline run and embed its line under \"named_layout\": auto (on at N = 8) | off")
+    p.add_argument("--inner", action="store_true", help=argparse.SUPPRESS)
     p.add_argument("--profile", type=int, default=0, help="after the timed region, run this many extra steps under the CUPTI profiler and write "
                                                           "gpurun_out/bench_trace_n<N>_rank0.json.gz (kernel timeline; never part of the reported numbers)")
     return p.parse_args()
@@ -135,6 +138,27 @@ def _profile_steps(args, device_step, barrier, rank, world):
     rows.sort(key=lambda r: r[2])
     with gzip.open(os.path.join(out_dir, f"bench_trace_n{world}_rank0.json.gz"), "wt") as f:
         json.dump({"steps": args.profile, "model": args.model, "n_gpus": world, "columns": ["name", "stream", "ts_us", "dur_us"], "kernels": rows}, f)
+
+
+def _run_named_layout(args, rank):
+    """BASELINE config #2 (GPT-6.7B, mp2 x pp2 x sharding2) as a child job on the same 8 GPUs: one child per rank, its own rendezvous port, a hard
+    timeout; returns the child's JSON line (rank 0) or a dict with the failure reason.  Never raises: the headline line must survive."""
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 17)
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "8", "--layout", "mp2_pp2_sharding2", "--fused-tp", "1", "--steps", str(max(args.steps // 2, 3)),
+           "--warmup", "3", "--no-e2e", "--inner", "--model", args.model, "--seq-len", str(args.seq_len), "--local-batch", str(args.local_batch)]
+    try:
+        p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
+        if rank != 0:
+            return None
+        for line in reversed(p.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": f"child exited {p.returncode} without a result", "stderr_tail": p.stderr[-400:]}
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "child job timed out after 420 s"} if rank == 0 else None
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:300]} if rank == 0 else None
 
 
 def build_config(args, world: int):
@@ -305,6 +329,17 @@ def main():
                       + "; NCCL only for the scalar grad-norm all-reduce" + (" and TP/PP traffic" if lay["mp"] > 1 or lay["pp"] > 1 else ""))
     else:
         collective = "NCCL"
+    opt_overlapped = bool(getattr(opt, "step_overlap", False))
+    named = None
+    if world == 8 and args.named_layout != "off" and args.layout == "auto" and not args.inner and not args.layers:
+        # release this job's device memory, then every rank starts the same rank of a child job (fresh process groups, fresh topology)
+        del loss
+        engine = module = opt = dev_pool = None
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        named = _run_named_layout(args, rank)
     if rank == 0:
         tokens = global_batch * seq * args.steps
         par = {"single": "single", "sharding": f"sharding{world}_stage1", "dp": f"dp{world}",
@@ -319,9 +354,9 @@ def main():
             "config": {"model": args.model if not args.layers else f"{args.model}-DEBUG-{args.layers}layers(INVALID)",
                        "global_batch": global_batch, "seq_len": seq, "parallelism": par, "local_batch": lay["local"],
                        "micro_batch": lay["micro"], "recompute": lay["recompute"], "dropout": cfg.Model.hidden_dropout_prob,
-                       "optimizer": "FusedAdamW fp32 master + clip" + (" (update overlapped with the next forward)" if getattr(opt, "step_overlap", False) else ""), "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
+                       "optimizer": "FusedAdamW fp32 master + clip" + (" (update overlapped with the next forward)" if opt_overlapped else ""), "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "final_loss": final_loss,
-            "collective": collective, "exposed_comm_ms_per_step": exposed,
+            "collective": collective, "exposed_comm_ms_per_step": exposed, "named_layout": named,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         }
         print(json.dumps(out))

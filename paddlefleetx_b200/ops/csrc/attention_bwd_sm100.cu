@@ -244,19 +244,30 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_wait(q_full(st), ((uint32_t)it >> 1) & 1u);           // lse / delta of this stage have landed (TMA completes on the same barrier)
       const float4* lse4 = reinterpret_cast<const float4*>(smem_gen + (s_stat - smem_base) + st * S::kStatBytes) + 8 * half;
       const float4* dl4 = lse4 + kQt / 4;
-      float p[32];
+      float p[32];                                                 // P * scale (the softmax scale is folded in here once)
       uint32_t keep = 0xFFFFFFFFu;
-      const bool need_mask = prm.causal && (kg > q0 + off);       // some of this thread's 32 queries precede its key
+      // masks are decided per tile (warp-uniform branches): only diagonal / ragged tiles pay per-element compares
+      const bool tile_mask = (prm.causal && (k0 + kKv - 1 > q0 + off)) || (k0 + kKv > prm.Sk);
+      if (tile_mask) {
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 l = lse4[c4];
-        const float ls[4] = {l.x, l.y, l.z, l.w};
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 l = lse4[c4];
+          const float ls[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = c4 * 4 + e;
-          float v = exp2f(__uint_as_float(r[c]) * prm.scale_log2 - ls[e]);
-          if (!k_valid || (need_mask && kg > q0 + c + off)) v = 0.f;
-          p[c] = v;
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            float v = exp2f(fmaf(__uint_as_float(r[c]), prm.scale_log2, -ls[e])) * prm.scale;
+            if (!k_valid || (prm.causal && kg > q0 + c + off)) v = 0.f;
+            p[c] = v;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 l = lse4[c4];
+          const float ls[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) p[c4 * 4 + e] = exp2f(fmaf(__uint_as_float(r[c4 * 4 + e]), prm.scale_log2, -ls[e])) * prm.scale;
         }
       }
       if (drop) {
@@ -267,7 +278,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           keep |= (attn_keep(bits, (uint32_t)kg, prm.drop_thresh16) ? 1u : 0u) << c;
         }
       }
-      // P_drop^T -> shared memory (A operand of the dV product)
+      // P_drop^T -> shared memory (A operand of the dV product); p[] carries the softmax scale, so un-scale together with 1/(1-p)
+      const float p_to_pdrop = prm.inv_keep / prm.scale;
       mbar_wait(p_free, ((uint32_t)it & 1u) ^ 1u);
       {
         const uint32_t dst_row = s_p + row_off;
@@ -275,7 +287,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int g = 0; g < 4; ++g) {
           float w[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { const int c = g * 8 + e; w[e] = ((keep >> c) & 1u) ? p[c] * prm.inv_keep : 0.f; }
+          for (int e = 0; e < 8; ++e) { const int c = g * 8 + e; w[e] = ((keep >> c) & 1u) ? p[c] * p_to_pdrop : 0.f; }
           const uint32_t chunk = (uint32_t)(4 * half + g) ^ (uint32_t)(k_row % 8);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_row + chunk * 16u), "r"(pack_bf16x2(w[0], w[1])), "r"(pack_bf16x2(w[2], w[3])),
                        "r"(pack_bf16x2(w[4], w[5])), "r"(pack_bf16x2(w[6], w[7])) : "memory");
@@ -284,7 +296,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      // dS^T = P o (drop(dP) - delta) * scale
+      // dS^T * scale = (P scale) o (drop(dP) - delta)
       mbar_wait(dp_full, (uint32_t)it & 1u);
       tcgen05_fence_after();
       tmem_ld_32x32b_x32(t_dp + lane_addr + 32 * half, r);
@@ -292,15 +304,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dp_free);
+      if (drop) {
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 d = dl4[c4];
-        const float dl[4] = {d.x, d.y, d.z, d.w};
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 d = dl4[c4];
+          const float dl[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = c4 * 4 + e;
-          const float dpe = ((keep >> c) & 1u) ? __uint_as_float(r[c]) * prm.inv_keep : 0.f;
-          p[c] = p[c] * (dpe - dl[e]) * prm.scale;
+          for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            const float dpe = ((keep >> c) & 1u) ? __uint_as_float(r[c]) * prm.inv_keep : 0.f;
+            p[c] *= dpe - dl[e];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 d = dl4[c4];
+          const float dl[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const int c = c4 * 4 + e; p[c] *= __uint_as_float(r[c]) - dl[e]; }
         }
       }
       mbar_wait(ds_free, ((uint32_t)it & 1u) ^ 1u);

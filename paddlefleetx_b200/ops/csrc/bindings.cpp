@@ -626,6 +626,16 @@ std::vector<at::Tensor> attention_fwd(const at::Tensor& q, const at::Tensor& k, 
   return {out, lse};
 }
 
+at::Tensor probe_tmem_a(const at::Tensor& a, const at::Tensor& b) {
+  PFX_CHECK_CUDA_CONTIG(a); PFX_CHECK_CUDA_CONTIG(b);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && a.size(0) == 128 && a.size(1) == 128 && b.size(0) == 64 && b.size(1) == 128,
+              "probe_tmem_a: a [128,128], b [64,128] bf16");
+  const c10::cuda::CUDAGuard guard(a.device());
+  auto d = at::empty({128, 64}, a.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::probe_tmem_a(a.data_ptr(), b.data_ptr(), d.data_ptr<float>(), cur_stream()));
+  return d;
+}
+
 // out[t] = w[ids[t] - vocab_start] (zero for foreign ids) (+ pos_w[pos[t]])
 at::Tensor embedding_fwd(const at::Tensor& ids, const at::Tensor& w, c10::optional<at::Tensor> pos, c10::optional<at::Tensor> pos_w, int64_t vocab_start) {
   PFX_CHECK_CUDA_CONTIG(ids); PFX_CHECK_CUDA_CONTIG(w);
@@ -795,6 +805,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_reduce_scatter", &p2p_reduce_scatter);
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("attention_fwd", &attention_fwd);
+  m.def("probe_tmem_a", &probe_tmem_a);
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);
   m.def("embedding_bwd_max_tokens", &embedding_bwd_max_tokens);

@@ -72,6 +72,9 @@ cudaError_t attention_fwd(const void* q, const void* k, const void* v, void* out
 cudaError_t attention_decode(const void* q, void* k, void* v, const void* mask, void* out, int B, int H, int D, int L, int Lmax,
                              float scale, int dtype, cudaStream_t st, const int64_t* write_idx = nullptr);
 
+// probe_kernels.cu — hardware semantics probes (run by tools/gpu_selftest.py)
+cudaError_t probe_tmem_a(const void* a, const void* b, float* d, cudaStream_t st);
+
 // embedding.cu — fused word (+ position) look-up; deterministic sorted scatter-add gradient (workspace: next_pow2(tokens) 64-bit keys)
 cudaError_t embedding_fwd(const int64_t* ids, const void* w, const int64_t* pos, const void* pw, void* out, int64_t tokens, int hidden,
                           int64_t vocab_start, int64_t rows, int dtype, cudaStream_t st);

@@ -82,12 +82,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if PFX_HANG_GUARD
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  // try_wait suspends the warp for a hardware time slice per attempt; the guard only counts attempts (one IADD + one compare per poll — a
+  // clock read per poll showed up as ~10 % of all issued instructions in the attention kernels) and looks at the clock every 4096 polls
+  uint32_t polls = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) {  // ~2 s at B200 clocks: a lost arrival, not a slow producer
-      printf("pfx: mbarrier timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
+    if ((++polls & 0xFFFu) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) {  // ~2 s at B200 clocks: a lost arrival, not a slow producer
+        printf("pfx: mbarrier timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+        __trap();
+      }
     }
   }
 #else

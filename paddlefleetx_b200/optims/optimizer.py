@@ -96,7 +96,9 @@ class FusedAdamW:
         # measured on 2 x B200 (6.7B step): 16 / 64 / 296 reduce-scatter CTAs -> 368.9 / 321.5 / 315.6 ms per step: the kernels co-reside with the
         # GEMMs, and the shorter they run the less GEMM time they perturb
         self._rs_ctas = int(_os.environ.get("PFX_RS_CTAS", "296"))
-        self._adamw_ctas = int(_os.environ.get("PFX_ADAMW_CTAS", "0"))       # grid cap of the side-stream AdamW (0 = 8 CTAs per SM)
+        # grid cap of the side-stream AdamW (0 = 8 CTAs per SM).  At full width the update takes the whole memory system and the forward GEMMs
+        # beside it run 2-3x slower; 2 CTAs per SM measured best on one B200 (6.7B step: 339.9 ms uncapped / 336.5 @148 / 328.9 @296, same box)
+        self._adamw_ctas = int(_os.environ.get("PFX_ADAMW_CTAS", "296"))
         self._bcast_ctas = int(_os.environ.get("PFX_BCAST_CTAS", "296"))
 
         # ---- bucket assignment (reverse registration order: last layers finish backward first)

@@ -100,6 +100,41 @@ def gemm_rs(a: torch.Tensor, w: torch.Tensor, group, a_kmajor: bool = True, b_km
     return out
 
 
+_side_stream = [None]
+
+
+def _regather_async(x_shard: torch.Tensor, group):
+    """All-gather ``x_shard`` [rows, K] over the group with OUR kernel (multimem / peer stores) on a side stream; returns the gathered
+    [rows * n, K] buffer (symmetric, two alternating per shape) and the event the consumer has to wait for.  Barrier channel 1: the main
+    stream's fused kernels synchronise on channel 0 at the same time."""
+    lib = _native.require()
+    rows, K = x_shard.shape
+    key = ("regather", id(group), rows, K, x_shard.dtype)
+    if key not in _bufs:
+        sm = get_allocator(group)
+        sets = [sm.empty((rows * group.nranks, K), x_shard.dtype) for _ in range(2)]
+        torch.cuda.synchronize()
+        sm.barrier()
+        _bufs[key] = dict(sm=sm, sets=sets, calls=0)
+    b = _bufs[key]
+    buf = b["sets"][b["calls"] % 2]
+    b["calls"] += 1
+    sm = b["sm"]
+    if _side_stream[0] is None:
+        _side_stream[0] = torch.cuda.Stream()
+    side, cur = _side_stream[0], torch.cuda.current_stream()
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        sm.barrier(channel=1)        # every rank is past the previous use of this buffer set (two calls ago) and x_shard is final
+        lib.symm_all_gather(sm.mc_ptr(buf) if group.nranks >= 4 else 0, sm.peer_ptrs(buf), group.rank * rows * K * x_shard.element_size(), x_shard, group.rank, 64)
+        sm.barrier(channel=1)        # all shards have landed
+        ev = torch.cuda.Event()
+        ev.record(side)
+    x_shard.record_stream(side)
+    OF._count(3)
+    return buf, ev
+
+
 class _AllGatherLinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, group):
@@ -117,13 +152,15 @@ class _AllGatherLinear(torch.autograd.Function):
         group = ctx.group
         s_local, bsz, h = ctx.shape
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
+        # dW = dY^T @ X_full needs the gathered input again (the forward's gather buffer has been reused by later layers): our all-gather
+        # kernel re-gathers it on the side stream, underneath the dgrad GEMM -> reduce-scatter below
+        x_full, ready = _regather_async(x2, group)
         # dX shard = reduce_scatter(dY @ W): fused GEMM -> RS (B operand MN-major, no transpose copy)
         gx = gemm_rs(g2, weight, group, True, False).view(s_local, bsz, h)
-        # dW = dY^T @ X_full: re-gather X (NCCL) — the forward's gather buffer has been reused by later layers
-        x_full = C.all_gather_dim0(x2, group)
-        gw = lib.gemm(g2, x_full, None, None, False, False, 0, 0, 0)
+        torch.cuda.current_stream().wait_event(ready)
+        gw = OF._wgrad(lib, g2, x_full, weight)          # straight into the flat optimizer's main_grad when there is one
         gb = lib.colsum(g2, False) if ctx.has_bias else None
-        OF._count(3)
+        OF._count(2)
         return gx, gw, gb, None
 
 
@@ -148,15 +185,14 @@ class _LinearReduceScatter(torch.autograd.Function):
         g2 = gy.reshape(-1, gy.shape[-1]).contiguous()
         # dX = all_gather(dY) @ W: fused AG -> GEMM; the gathered dY is then reused for the weight gradient
         gx, g_full = ag_gemm(g2, weight, None, group, b_kmajor=False)
-        gw = lib.gemm(g_full, x2, None, None, False, False, 0, 0, 0)
-        OF._count()
+        gw = OF._wgrad(lib, g_full, x2, weight)
         return gx.view(s, bsz, k), gw, None
 
 
 def all_gather_linear(x: torch.Tensor, weight: torch.Tensor, bias, group) -> torch.Tensor:
     """x: [s/n, b, h] (sequence shard) -> [s, b, out/n]."""
     rows = x.shape[0] * x.shape[1]
-    if not fused_ok(x, group, rows) or x.shape[1] * 0 != 0:
+    if not fused_ok(x, group, rows):
         return OF.linear(C.all_gather_seq(x, group), weight, bias)
     # rows of the gathered matrix must be rank-contiguous: [s/n, b, h] flattened is (s_local, b) row-major per rank -> OK
     return _AllGatherLinear.apply(x.contiguous(), weight, bias, group)

@@ -12,7 +12,11 @@ optimizer (``optims/optimizer.py``); this module adds the parameter dimension:
     has its gradient the flat gradient is reduce-scattered into the shard gradient and the unit is released,
   * activation recompute composes: the re-forward inside backward gathers through the same hook and the unit stays
     resident until its gradients are reduced,
-  * unlike the reference, stage 3 composes with tensor parallelism (BASELINE config #3: mp x stage-3).
+  * unlike the reference, stage 3 composes with tensor parallelism (BASELINE config #3: mp x stage-3),
+  * on CUDA the gathers and the gradient reduce-scatter are OUR kernels over symmetric memory (csrc/comm_nvls.cu): every rank stores its
+    shard once through the NVLink-SHARP multicast address (``multimem.st``: the switch replicates it into all ranks' copy of the unit
+    buffer) and reduces its gradient slice in the switch (``multimem.ld_reduce``); the full-size unit buffers come from a pool of
+    symmetric buffers that is reused layer after layer.  ``PFX_ZERO3_NCCL=1`` (or CPU / gloo) selects the plain collectives.
 """
 from __future__ import annotations
 
@@ -53,6 +57,18 @@ class GroupShardedStage3(nn.Module):
         self._in_backward = False
         self._accumulating = False
         self._comm_stream = torch.cuda.Stream() if next(model.parameters()).is_cuda else None
+        import os
+
+        self._symm = None
+        self._pool: Dict[Tuple, List[torch.Tensor]] = {}
+        if self._comm_stream is not None and self.world > 1 and self.group.process_group is not None and os.environ.get("PFX_ZERO3_NCCL", "0") != "1":
+            from ..ops import _native
+
+            if _native.available():
+                from .symmetric_memory import get_allocator
+
+                self._symm = get_allocator(self.group)
+                self._lib = _native.require()
         self.units: List[_Unit] = []
         self._build_units(unit_classes)
         self.prefetch = True
@@ -117,7 +133,33 @@ class GroupShardedStage3(nn.Module):
                 p.register_post_accumulate_grad_hook(lambda param, u=u: self._grad_ready(u))
 
     def _alloc_full(self, g: dict) -> torch.Tensor:
-        return torch.empty(g["total"], dtype=g["shard"].dtype, device=g["shard"].device)
+        if self._symm is None:
+            return torch.empty(g["total"], dtype=g["shard"].dtype, device=g["shard"].device)
+        return self._pool_take(g["total"], g["shard"].dtype)
+
+    # symmetric unit buffers: taken / returned in the same order on every rank (the program is SPMD), so the collective allocation of a
+    # new buffer — when the free list of that size is empty — happens on all ranks together
+    def _pool_take(self, numel: int, dtype) -> torch.Tensor:
+        free = self._pool.setdefault((numel, dtype), [])
+        return free.pop() if free else self._symm.alloc_tensor(numel, dtype)
+
+    def _pool_give(self, t: Optional[torch.Tensor]) -> None:
+        if t is not None and self._symm is not None and t.numel() > 0:
+            self._pool.setdefault((t.numel(), t.dtype), []).append(t)
+
+    def _chan(self) -> int:
+        """Barrier channel by issuing stream (prefetches run on the communication stream, everything else on the compute stream): two
+        streams must never share a channel's arrival counter."""
+        return 2 if (self._comm_stream is not None and torch.cuda.current_stream() == self._comm_stream) else 3
+
+    def _symm_all_gather(self, full: torch.Tensor, shard: torch.Tensor) -> None:
+        """full[r * s : (r + 1) * s] = rank r's shard, on every rank: barrier (every rank is done with this buffer's previous contents and
+        its shard is final) -> one multimem / peer store pass -> barrier (everything has landed)."""
+        sm, ch = self._symm, self._chan()
+        sm.barrier(channel=ch)
+        self._lib.symm_all_gather(sm.mc_ptr(full) if self.world >= 4 else 0, sm.peer_ptrs(full), self.rank * shard.numel() * shard.element_size(),
+                                  shard, self.rank, 64)
+        sm.barrier(channel=ch)
 
     def _gather(self, u: _Unit, prefetch: bool = False) -> None:
         """All-gather the unit's parameters.  ``prefetch`` issues the collective on the communication stream and returns at once;
@@ -131,7 +173,9 @@ class GroupShardedStage3(nn.Module):
             for g in u.groups:
                 full = self._alloc_full(g)
                 if self.world > 1 and self.group.process_group is not None:
-                    if full.is_cuda:
+                    if self._symm is not None:
+                        self._symm_all_gather(full, g["shard"].data)
+                    elif full.is_cuda:
                         dist.all_gather_into_tensor(full, g["shard"].data, group=self.group.process_group)
                     else:
                         parts = [torch.empty_like(g["shard"].data) for _ in range(self.world)]
@@ -172,6 +216,7 @@ class GroupShardedStage3(nn.Module):
         for g in u.groups:
             for p in g["params"]:
                 p.data = torch.empty(0, dtype=p.dtype, device=p.device)
+            self._pool_give(g["full"])
             g["full"] = None
         u.gathered = False
 
@@ -189,7 +234,11 @@ class GroupShardedStage3(nn.Module):
         if u.grads_attached:
             return
         for g in u.groups:
-            g["grad_full"] = torch.zeros(g["total"], dtype=g["shard"].dtype, device=g["shard"].device)
+            if self._symm is not None and not g["key"][2]:
+                g["grad_full"] = self._pool_take(g["total"], g["shard"].dtype)
+                g["grad_full"].zero_()
+            else:
+                g["grad_full"] = torch.zeros(g["total"], dtype=g["shard"].dtype, device=g["shard"].device)
             for p, o, shp in zip(g["params"], g["offsets"], g["shapes"]):
                 p.grad = g["grad_full"][o:o + shp.numel()].view(shp)
         u.pending_grads = sum(len(g["params"]) for g in u.groups)
@@ -223,7 +272,17 @@ class GroupShardedStage3(nn.Module):
             if g["key"][2]:                          # expert params: rank-private, no reduction
                 piece = gf[self.rank * s:(self.rank + 1) * s]
             elif self.world > 1 and self.group.process_group is not None:
-                if gf.is_cuda:
+                if self._symm is not None:
+                    # in-switch (or peer-pull) reduction of this rank's slice of every rank's unit gradient; the buffer returns to the pool
+                    # only after every rank has finished reading it
+                    piece = torch.empty(s, dtype=gf.dtype, device=gf.device)
+                    sm, ch = self._symm, self._chan()
+                    sm.barrier(channel=ch)
+                    self._lib.symm_reduce_scatter(sm.mc_ptr(gf) if self.world >= 4 else 0, sm.peer_ptrs(gf), self.rank * s, piece, self.rank,
+                                                  {torch.float16: 0, torch.bfloat16: 1, torch.float32: 3}[gf.dtype], 1.0, False, None, 148)
+                    sm.barrier(channel=ch)
+                    self._pool_give(gf)
+                elif gf.is_cuda:
                     piece = torch.empty(s, dtype=gf.dtype, device=gf.device)
                     dist.reduce_scatter_tensor(piece, gf, group=self.group.process_group)
                 else:

@@ -83,8 +83,9 @@ class SymmetricAllocator:
         return self.lib.tensor_from_ptr(self.peer_ptrs(t)[peer], list(t.shape), t.dtype, self.device.index or 0)
 
     # ---------------------------------------------------------------- synchronisation
-    def barrier(self) -> None:
-        """Device-side barrier on the current stream: all ranks' prior work on their streams is visible after it."""
+    def barrier(self, channel: int = 0) -> None:
+        """Device-side barrier on the current stream: all ranks' prior work on their streams is visible after it.  (One channel only: use
+        the VMM back-end when barriers are issued from several streams.)"""
         self.lib.p2p_barrier(self._pad_ptrs, self.rank, self._slot)
         self._slot = (self._slot + 1) % 8
 
@@ -186,7 +187,7 @@ class VmmSymmetricAllocator:
         # flag words: [0] = multicast barrier counter, [64 + r] = unicast barrier slots
         flags = self._new_arena(self._gran, small=True)
         self._flags = flags
-        self._bar_count = 0
+        self._bar_counts: Dict[int, int] = {}
         logger.info(f"symmetric memory: cuMem VMM arenas, granularity {self._gran >> 20} MiB, multicast (NVLS) {'on' if self.multicast else 'off'}")
 
     # ---------------------------------------------------------------- collective helpers
@@ -305,15 +306,19 @@ class VmmSymmetricAllocator:
         return self.lib.tensor_from_ptr(self.peer_ptrs(t)[peer], list(t.shape), t.dtype, self.device.index or 0)
 
     # ---------------------------------------------------------------- synchronisation
-    def barrier(self) -> None:
+    def barrier(self, channel: int = 0) -> None:
         """Device-side barrier on the current stream (release / acquire at system scope): everything the ranks wrote before it
-        — locally, to peers or through the switch — is visible to every rank's kernels after it."""
-        self._bar_count += 1
+        — locally, to peers or through the switch — is visible to every rank's kernels after it.  Barriers issued from DIFFERENT
+        streams must use different ``channel`` s (0..7): each channel has its own flag words and arrival counter, so two streams can
+        never satisfy each other's barrier, whatever order the ranks' schedulers run them in."""
+        assert 0 <= channel < 8
+        cnt = self._bar_counts[channel] = self._bar_counts.get(channel, 0) + 1
         f = self._flags
+        off = channel * 1024                                   # bytes: [0, 256) multicast counter word, [256, 1024) unicast slots
         if self.multicast and f["mc"]:
-            self.lib.nvls_barrier(f["mc"], f["base"], (self._bar_count * self.world) & 0xFFFFFFFF)
+            self.lib.nvls_barrier(f["mc"] + off, f["base"] + off, (cnt * self.world) & 0xFFFFFFFF)
         else:
-            self.lib.p2p_flag_barrier([p + 256 for p in f["peers"]], self.rank, self._bar_count & 0xFFFFFFFF)
+            self.lib.p2p_flag_barrier([p + off + 256 for p in f["peers"]], self.rank, cnt & 0xFFFFFFFF)
 
 
 _ALLOCATORS: Dict[int, object] = {}

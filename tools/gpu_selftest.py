@@ -690,6 +690,20 @@ def check_embedding():
     return dict(ok=ok, cases=res)
 
 
+def check_probe_tmem_a():
+    """tcgen05.mma with the A operand in tensor memory (packed there by tcgen05.st, one row per lane) == A . B^T."""
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    a = torch.randn(128, 128, device="cuda").bfloat16()
+    b = torch.randn(64, 128, device="cuda").bfloat16()
+    d = lib.probe_tmem_a(a, b)
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    err = _relerr(d, ref)
+    return dict(ok=bool(err < 1e-3), err=err)
+
+
 def check_gemm_big_sweep():
     """Multi-tile shapes (several tiles per CTA, both TMEM accumulator buffers alternating, dozens of k-blocks, ragged edges) for every
     (CTA-group, operand majors, output mode) against fp32."""
@@ -711,6 +725,7 @@ CHECKS = {
     "attention_autograd": check_attention_autograd,
     "gemm_big_sweep": check_gemm_big_sweep,
     "embedding": check_embedding,
+    "probe_tmem_a": check_probe_tmem_a,
     "attention_decode": check_attention_decode,
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
