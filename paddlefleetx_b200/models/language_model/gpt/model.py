@@ -47,6 +47,10 @@ class LayerNorm(nn.Module):
     def forward(self, x):
         return OF.layer_norm(x, self.weight, self.bias, self.eps)
 
+    def forward_res(self, x):
+        """(norm(x), residual alias of x): see ``OF.norm_with_residual``."""
+        return OF.norm_with_residual(x, self.weight, self.bias, self.eps, False)
+
 
 class RMSNorm(nn.Module):
     """``Model.normalization: rmsnorm`` — x / rms(x) * weight, no mean subtraction, no bias (Zhang & Sennrich 2019); runs the fused
@@ -62,6 +66,9 @@ class RMSNorm(nn.Module):
 
     def forward(self, x):
         return OF.rms_norm(x, self.weight, self.eps)
+
+    def forward_res(self, x):
+        return OF.norm_with_residual(x, self.weight, None, self.eps, True)
 
 
 def make_norm(kind: Optional[str], hidden: int, sequence_parallel: bool = False, dtype=None, device=None) -> nn.Module:
@@ -249,7 +256,8 @@ class TransformerDecoderLayer(nn.Module):
         self.rng_name = "local_seed" if sequence_parallel else "global_seed"
 
     def _attn_block(self, x, attn_mask, cache, positions):
-        y, b = self.self_attn(self.norm1(x), attn_mask, cache, positions)
+        h, x = self.norm1.forward_res(x)
+        y, b = self.self_attn(h, attn_mask, cache, positions)
         return OF.bias_dropout_add(y, b, x, self.hidden_dropout, self.training, self.rng_name)
 
     def _ffn(self, h):
@@ -296,7 +304,7 @@ class TransformerDecoderLayer(nn.Module):
             x = recompute(self._attn_block, x, attn_mask, None, positions)
         else:
             x = self._attn_block(x, attn_mask, cache, positions)
-        h = self.norm2(x)
+        h, x = self.norm2.forward_res(x)
         if self.moe_mlp is not None:
             y = self.moe_mlp(h)
             return OF.bias_dropout_add(y, None, x, self.hidden_dropout, self.training, self.rng_name)

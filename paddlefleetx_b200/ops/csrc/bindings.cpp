@@ -228,8 +228,11 @@ std::vector<at::Tensor> norm_fwd(const at::Tensor& x, const at::Tensor& w, c10::
 }
 
 std::vector<at::Tensor> norm_bwd(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& w, const at::Tensor& mean,
-                                 const at::Tensor& rstd, bool rms, bool has_bias) {
+                                 const at::Tensor& rstd, bool rms, bool has_bias, c10::optional<at::Tensor> dres) {
+  // dres: gradient of the residual branch that bypasses the norm (pre-norm block): dx = norm_bwd(dy) + dres in the same pass
   PFX_CHECK_CUDA_CONTIG(dy); PFX_CHECK_CUDA_CONTIG(x);
+  const bool with_res = dres.has_value() && dres->defined();
+  if (with_res) TORCH_CHECK(dres->is_contiguous() && dres->sizes() == x.sizes() && dres->scalar_type() == x.scalar_type(), "norm_bwd: dres");
   const c10::cuda::CUDAGuard guard(x.device());
   const int64_t cols = x.size(-1), rows = x.numel() / cols;
   auto dx = at::empty_like(x);
@@ -239,7 +242,7 @@ std::vector<at::Tensor> norm_bwd(const at::Tensor& dy, const at::Tensor& x, cons
   auto ws = at::empty({2 * (int64_t)parts * cols}, x.options().dtype(at::kFloat));
   PFX_CUDA_CHECK(pfx::norm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), rms ? nullptr : mean.data_ptr<float>(), rstd.data_ptr<float>(),
                                dx.data_ptr(), dw.data_ptr(), (has_bias && !rms) ? db.data_ptr() : nullptr, ws.data_ptr<float>(), (int)rows,
-                               (int)cols, dtype_code(x), rms, num_sms(), cur_stream()));
+                               (int)cols, dtype_code(x), rms, num_sms(), cur_stream(), with_res ? dres->data_ptr() : nullptr));
   return {dx, dw, db};
 }
 
@@ -778,7 +781,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_lowp", &gemm_lowp, py::arg("a"), py::arg("b"), py::arg("row_scale") = py::none(), py::arg("col_scale") = py::none(),
         py::arg("bias") = py::none(), py::arg("config") = 0);
   m.def("norm_fwd", &norm_fwd);
-  m.def("norm_bwd", &norm_bwd);
+  m.def("norm_bwd", &norm_bwd, py::arg("dy"), py::arg("x"), py::arg("w"), py::arg("mean"), py::arg("rstd"), py::arg("rms"), py::arg("has_bias"),
+        py::arg("dres") = py::none());
   m.def("bias_gelu_fwd", &bias_gelu_fwd);
   m.def("bias_gelu_bwd", &bias_gelu_bwd);
   m.def("bias_dropout_add_fwd", &bias_dropout_add_fwd);

@@ -85,7 +85,7 @@ __device__ __forceinline__ float2 block_sum2(float a, float b, float2* scratch) 
 template <typename T, bool kRms, int kVPT, int kThreads>
 __global__ void __launch_bounds__(kThreads) norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ w,
                                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in, T* __restrict__ dx,
-                                float* __restrict__ dw_part, float* __restrict__ db_part, int rows, int cols) {
+                                float* __restrict__ dw_part, float* __restrict__ db_part, int rows, int cols, const T* __restrict__ dres) {
   __shared__ float2 scratch[33];
   const int nvec = cols >> 3;
   float dwp[kVPT][8], dbp[kVPT][8];
@@ -160,6 +160,12 @@ __global__ void __launch_bounds__(kThreads) norm_bwd_kernel(const T* __restrict_
         unpack8<T>(wraw[i], wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[j] * wv[j] - c1 - (xv[j] - mean) * rstd * c2);
+        if (dres != nullptr) {      // pre-norm block: the residual branch's gradient joins here instead of in a separate add pass
+          float rv[8];
+          unpack8<T>(ld_stream(reinterpret_cast<const uint4*>(dres + (size_t)row * cols) + vi), rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += rv[j];
+        }
         st_stream(dxr + vi, pack8<T>(o));
       }
     }
@@ -235,7 +241,7 @@ int norm_bwd_num_parts(int rows, int num_sms) { int g = num_sms * 2; return rows
 
 template <typename T>
 static cudaError_t norm_bwd_t(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, void* dw,
-                              void* db, float* workspace, int rows, int cols, bool rms, int num_sms, cudaStream_t st) {
+                              void* db, float* workspace, int rows, int cols, bool rms, int num_sms, cudaStream_t st, const void* dres) {
   if (cols % 8 || cols > 32768) return cudaErrorInvalidValue;
   const int nvec = cols / 8;
   const int parts = norm_bwd_num_parts(rows, num_sms);
@@ -244,9 +250,9 @@ static cudaError_t norm_bwd_t(const void* dy, const void* x, const void* w, cons
 #define PFX_NB(VPT, THREADS)                                                                                                              \
   do {                                                                                                                                    \
     if (rms) norm_bwd_kernel<T, true, VPT, THREADS><<<parts, THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, nullptr, rstd,      \
-                                                                              (T*)dx, dwp, dbp, rows, cols);                              \
+                                                                              (T*)dx, dwp, dbp, rows, cols, (const T*)dres);              \
     else norm_bwd_kernel<T, false, VPT, THREADS><<<parts, THREADS, 0, st>>>((const T*)dy, (const T*)x, (const T*)w, mean, rstd, (T*)dx,    \
-                                                                           dwp, dbp, rows, cols);                                         \
+                                                                           dwp, dbp, rows, cols, (const T*)dres);                         \
   } while (0)
   if (nvec <= 128) PFX_NB(1, 128);
   else if (nvec <= 256) PFX_NB(1, 256);
@@ -262,10 +268,10 @@ static cudaError_t norm_bwd_t(const void* dy, const void* x, const void* w, cons
 }
 
 cudaError_t norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, void* dw, void* db,
-                     float* workspace, int rows, int cols, int dtype, bool rms, int num_sms, cudaStream_t st) {
+                     float* workspace, int rows, int cols, int dtype, bool rms, int num_sms, cudaStream_t st, const void* dres) {
   if (rows == 0) return cudaSuccess;
-  return dtype == 1 ? norm_bwd_t<__nv_bfloat16>(dy, x, w, mean, rstd, dx, dw, db, workspace, rows, cols, rms, num_sms, st)
-                    : norm_bwd_t<__half>(dy, x, w, mean, rstd, dx, dw, db, workspace, rows, cols, rms, num_sms, st);
+  return dtype == 1 ? norm_bwd_t<__nv_bfloat16>(dy, x, w, mean, rstd, dx, dw, db, workspace, rows, cols, rms, num_sms, st, dres)
+                    : norm_bwd_t<__half>(dy, x, w, mean, rstd, dx, dw, db, workspace, rows, cols, rms, num_sms, st, dres);
 }
 
 // --------------------------------------------------------------------------- bias + GELU

@@ -10,7 +10,7 @@ cudaError_t norm_fwd(const void* x, const void* w, const void* b, void* y, float
                      int dtype, bool rms, cudaStream_t st);
 int norm_bwd_num_parts(int rows, int num_sms);
 cudaError_t norm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx, void* dw, void* db,
-                     float* workspace, int rows, int cols, int dtype, bool rms, int num_sms, cudaStream_t st);
+                     float* workspace, int rows, int cols, int dtype, bool rms, int num_sms, cudaStream_t st, const void* dres = nullptr);
 
 cudaError_t bias_gelu(const void* x, const void* bias, const void* dy, void* out, size_t rows, int cols, int dtype, bool bwd, int num_sms,
                       cudaStream_t st, bool exact = false);

@@ -409,34 +409,50 @@ def dropout(x: torch.Tensor, p: float, training: bool, rng_name: Optional[str] =
 
 # =============================================================================== layer / rms norm
 class _NormFn(torch.autograd.Function):
+    """``with_res``: also hand the input back as a second output (an alias).  A pre-norm block takes its residual from THAT tensor, so
+    the gradient of the residual branch arrives in this backward next to dy and the kernel writes ``norm_bwd(dy) + d_residual`` in one
+    pass — otherwise autograd sums the two contributions with a separate full-size add (2 per transformer layer)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, rms):
+    def forward(ctx, x, weight, bias, eps, rms, with_res):
         lib = _native.require()
         x = x.contiguous()
         y, mean, rstd = lib.norm_fwd(x, weight, bias, eps, rms)
         _count()
         ctx.save_for_backward(x, weight, mean, rstd)
         ctx.rms, ctx.has_bias = rms, bias is not None
+        if with_res:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gres=None):
         lib = _native.require()
         x, weight, mean, rstd = ctx.saved_tensors
-        dx, dw, db = lib.norm_bwd(gy.contiguous(), x, weight, mean, rstd, ctx.rms, ctx.has_bias)
+        if gy is None:            # only the residual alias was used
+            return gres, None, None, None, None, None
+        dx, dw, db = lib.norm_bwd(gy.contiguous(), x, weight, mean, rstd, ctx.rms, ctx.has_bias, None if gres is None else gres.contiguous())
         _count(3 if ctx.has_bias else 2)
-        return dx, dw, (db if ctx.has_bias else None), None, None
+        return dx, dw, (db if ctx.has_bias else None), None, None, None
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
     if _native_ok(x, weight) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 32768 and weight.dtype == x.dtype:
-        return _NormFn.apply(x, weight, bias, eps, False)
+        return _NormFn.apply(x, weight, bias, eps, False, False)
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+def norm_with_residual(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float, rms: bool = False):
+    """``(norm(x), x_res)`` for pre-norm blocks: use ``x_res`` (an alias of ``x``) as the residual operand and the backward adds the
+    residual gradient inside the norm-backward kernel.  Falls back to ``(norm(x), x)`` off the native path."""
+    if _native_ok(x, weight) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 32768 and weight.dtype == x.dtype and torch.is_grad_enabled() and x.requires_grad:
+        return _NormFn.apply(x, weight, bias, eps, rms, True)
+    return (rms_norm(x, weight, eps) if rms else layer_norm(x, weight, bias, eps)), x
 
 
 def rms_norm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     if _native_ok(x, weight) and x.shape[-1] % 8 == 0 and x.shape[-1] <= 32768 and weight.dtype == x.dtype:
-        return _NormFn.apply(x, weight, None, eps, True)
+        return _NormFn.apply(x, weight, None, eps, True, False)
     xf = x.float()
     return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * weight
 

@@ -144,8 +144,13 @@ class GroupShardedStage3(nn.Module):
         return free.pop() if free else self._symm.alloc_tensor(numel, dtype)
 
     def _pool_give(self, t: Optional[torch.Tensor]) -> None:
-        if t is not None and self._symm is not None and t.numel() > 0:
-            self._pool.setdefault((t.numel(), t.dtype), []).append(t)
+        if t is None or self._symm is None or t.numel() == 0:
+            return
+        try:
+            self._symm.peer_ptrs(t)        # the construction-time full buffers are ordinary tensors: they must not enter the pool
+        except ValueError:
+            return
+        self._pool.setdefault((t.numel(), t.dtype), []).append(t)
 
     def _chan(self) -> int:
         """Barrier channel by issuing stream (prefetches run on the communication stream, everything else on the compute stream): two

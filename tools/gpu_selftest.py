@@ -690,6 +690,34 @@ def check_embedding():
     return dict(ok=ok, cases=res)
 
 
+def check_norm_residual():
+    """Pre-norm block pattern: out = x_res + f(norm(x)); the residual gradient is added inside the norm-backward kernel."""
+    import torch
+    from paddlefleetx_b200.ops import functional as OF
+    torch.manual_seed(0)
+    ok, res = True, {}
+    for rms in (False, True):
+        x = torch.randn(512, 1024, device="cuda").bfloat16().requires_grad_(True)
+        w = (1 + 0.1 * torch.randn(1024, device="cuda")).bfloat16().requires_grad_(True)
+        b = None if rms else (0.1 * torch.randn(1024, device="cuda")).bfloat16().requires_grad_(True)
+        g = torch.randn(512, 1024, device="cuda").bfloat16()
+        OF.reset_launch_count()
+        h, xr = OF.norm_with_residual(x, w, b, 1e-5, rms)
+        out = xr + torch.tanh(h)
+        out.backward(g)
+        xf, wf = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+        if rms:
+            hf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+        else:
+            bf = b.detach().float().requires_grad_(True)
+            hf = torch.nn.functional.layer_norm(xf, (1024,), wf, bf, 1e-5)
+        (xf + torch.tanh(hf)).backward(g.float())
+        e = dict(dx=_relerr(x.grad, xf.grad), dw=_relerr(w.grad, wf.grad))
+        ok = ok and max(e.values()) < 2e-2
+        res["rms" if rms else "ln"] = {k: round(float(v), 5) for k, v in e.items()}
+    return dict(ok=ok, cases=res)
+
+
 def check_probe_tmem_a():
     """tcgen05.mma with the A operand in tensor memory (packed there by tcgen05.st, one row per lane) == A . B^T."""
     import torch
@@ -726,6 +754,7 @@ CHECKS = {
     "gemm_big_sweep": check_gemm_big_sweep,
     "embedding": check_embedding,
     "probe_tmem_a": check_probe_tmem_a,
+    "norm_residual": check_norm_residual,
     "attention_decode": check_attention_decode,
     "gemv_w8a8": check_gemv_w8a8,
     "decode_fused": check_decode_fused,
