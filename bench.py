@@ -145,18 +145,41 @@ def _run_named_layout(args, rank):
     timeout; returns the child's JSON line (rank 0) or a dict with the failure reason.  Never raises: the headline line must survive."""
     env = dict(os.environ)
     env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 17)
-    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "8", "--layout", "mp2_pp2_sharding2", "--fused-tp", "1", "--steps", str(max(args.steps // 2, 3)),
+    # under torchrun the env:// rendezvous connects to the elastic AGENT's store instead of creating one; nobody serves the child's port,
+    # so without this every child rank waits for a store that never comes up (this is what timed out in profiles/r2/c5_bench_n8)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)
+    env.pop("TORCHELASTIC_RUN_ID", None)
+    forced = os.environ.get("PFX_NAMED_LAYOUT_FORCE")      # test hook: exercise the child-job path at another world size / layout (e.g. mp2 on 2 GPUs)
+    cmd = [sys.executable, os.path.abspath(__file__), "--gpus", env.get("WORLD_SIZE", "8"), "--layout", forced or "mp2_pp2_sharding2", "--fused-tp", "1", "--steps", str(max(args.steps // 2, 3)),
            "--warmup", "3", "--no-e2e", "--inner", "--model", args.model, "--seq-len", str(args.seq_len), "--local-batch", str(args.local_batch)]
+    if args.layers:
+        cmd += ["--layers", str(args.layers)]
+    os.makedirs("gpurun_out", exist_ok=True)
+    log_path = os.path.join("gpurun_out", f"named_layout_child_rank{rank}.log")
+    limit = float(os.environ.get("PFX_NAMED_LAYOUT_TIMEOUT", "300"))
+
+    def tail():
+        try:
+            with open(log_path, "r", errors="replace") as f:
+                return f.read()[-600:]
+        except OSError:
+            return ""
+
     try:
-        p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
+        with open(log_path, "w") as log:
+            p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=log, text=True)
+            try:
+                out, _ = p.communicate(timeout=limit)
+            except subprocess.TimeoutExpired:
+                p.kill()                      # this exact child, by handle
+                p.communicate()
+                return {"unavailable": f"child job timed out after {limit:.0f} s", "stderr_tail": tail()} if rank == 0 else None
         if rank != 0:
             return None
-        for line in reversed(p.stdout.strip().splitlines()):
+        for line in reversed(out.strip().splitlines()):
             if line.startswith("{"):
                 return json.loads(line)
-        return {"unavailable": f"child exited {p.returncode} without a result", "stderr_tail": p.stderr[-400:]}
-    except subprocess.TimeoutExpired:
-        return {"unavailable": "child job timed out after 420 s"} if rank == 0 else None
+        return {"unavailable": f"child exited {p.returncode} without a result", "stderr_tail": tail()}
     except Exception as e:  # noqa: BLE001
         return {"unavailable": repr(e)[:300]} if rank == 0 else None
 
@@ -331,7 +354,7 @@ def main():
         collective = "NCCL"
     opt_overlapped = bool(getattr(opt, "step_overlap", False))
     named = None
-    if world == 8 and args.named_layout != "off" and args.layout == "auto" and not args.inner and not args.layers:
+    if (world == 8 or os.environ.get("PFX_NAMED_LAYOUT_FORCE")) and args.named_layout != "off" and args.layout == "auto" and not args.inner and (not args.layers or os.environ.get("PFX_NAMED_LAYOUT_FORCE")):
         # release this job's device memory, then every rank starts the same rank of a child job (fresh process groups, fresh topology)
         del loss
         engine = module = opt = dev_pool = None

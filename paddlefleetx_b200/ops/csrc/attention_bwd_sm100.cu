@@ -6,16 +6,19 @@
 // buffered), dP^T, dQ^T and the two persistent accumulators dV, dK share the 512 TMEM columns:
 //
 //     S^T  = K_j Q_i^T                      [128 k x 64 q]    A = K_j  (K-major),   B = Q_i  (K-major)       cols   0..127 (2 buffers)
-//     dP^T = V_j dO_i^T                     [128 k x 64 q]    A = V_j  (K-major),   B = dO_i (K-major)       cols 128..191
-//     P^T  = exp2(S^T * c - lse_i)   masked, dropout applied on the way to shared memory (bf16, swizzled)
-//     dS^T = P^T o (drop(dP^T) - delta_i) * scale
-//     dV  += P_drop^T dO_i                  [128 k x 128 d]   A = P^T  (K-major),   B = dO_i (MN-major)      cols 256..383
+//     dP^T = V_j dO_i^T                     [128 k x 64 q]    A = V_j  (K-major),   B = dO_i (K-major)       cols 128..255 (2 buffers)
+//     P^T  = exp2(S^T * c - lse_i)   masked, dropout applied; written as packed bf16 over the first 32 columns of its S^T buffer
+//     dS^T = P^T o (drop(dP^T) - delta_i) * scale     -> shared memory (bf16, swizzled, 2 buffers)
+//     dV  += P_drop^T dO_i                  [128 k x 128 d]   A = P^T  (TENSOR MEMORY),  B = dO_i (MN-major)  cols 256..383
 //     dK  += dS^T Q_i                       [128 k x 128 d]   A = dS^T (K-major),   B = Q_i  (MN-major)      cols 384..511
-//     dQ^T = K_j^T dS^T                     [128 d x 64 q]    A = K_j  (MN-major),  B = dS^T (MN-major)      cols 192..255
+//     dQ^T = K_j^T dS^T                     [128 d x 64 q]    A = K_j  (MN-major),  B = dS^T (MN-major)      into the S^T buffer of tile i
+// The MMA warp runs TWO query tiles ahead (S^T / dP^T of tile i+2 are issued right behind the three products of tile i; Q_i / dO_i ride a
+// 3-stage ring), so the tensor core and the math warps only meet on data, not on each other's schedule — the first version alternated
+// them and spent ~7000 cycles per tile against 1280 cycles of tensor work.
 //
 // The same shared-memory tiles serve as K-major and MN-major operands (a 128-byte-swizzled [rows x 64] panel is both), so Q_i,
 // dO_i, K_j, V_j are loaded once by TMA straight from the framework layout ([B, S, H, D] views, packed QKV included) and P^T / dS^T
-// are written once by the threads that produce them.  dQ is accumulated across key tiles in an fp32 workspace: the drain warps move
+// are written once by the threads that produce them (P^T never leaves the tensor-memory / register domain).  dQ is accumulated across key tiles in an fp32 workspace: the drain warps move
 // each dQ^T tile TMEM -> registers -> (transposed) shared memory and ONE TMA reduce-add (cp.reduce.async.bulk.tensor) folds it into
 // global memory — per-lane red.global instructions cost ~1.3 cycles per lane on the SM and were 5x the tensor-core time of a tile
 // (first version: 0.55 ms at B8 S1024 H32); the workspace is converted to bf16 afterwards; lse (log2 units) and delta = rowsum(dO o O) come from a small preprocessing kernel.
@@ -43,18 +46,18 @@ constexpr int kHd = 128;            // head dim
 struct BwSmem {
   static constexpr int kKBytes = kKv * kHd * 2;          // 32 KB: two [128 x 64] panels
   static constexpr int kQBytes = kQt * kHd * 2;          // 16 KB: two [64 x 64] panels
-  static constexpr int kPBytes = kKv * kQt * 2;          // 16 KB: one [128 x 64] panel
+  static constexpr int kDsBytes = kKv * kQt * 2;         // 16 KB: one [128 x 64] panel
   static constexpr int kStatBytes = 2 * kQt * 4;         // lse2 + delta of one query tile
+  static constexpr int kStages = 3;                      // Q_i / dO_i / stats ring: the MMA warp runs two query tiles ahead of the math warps
+  static constexpr int kDqBytes = kQt * kHd * 4;         // 32 KB: dQ tile [64 q][128 d] fp32, row-major (TMA reduce source)
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kOffK + kKBytes;
-  static constexpr int kOffQ = kOffV + kKBytes;          // 2 stages
-  static constexpr int kOffDo = kOffQ + 2 * kQBytes;     // 2 stages
-  static constexpr int kOffP = kOffDo + 2 * kQBytes;
-  static constexpr int kOffDs = kOffP + kPBytes;
-  static constexpr int kDqBytes = kQt * kHd * 4;         // 32 KB: dQ tile [64 q][128 d] fp32, row-major (TMA reduce source)
-  static constexpr int kOffDq = kOffDs + kPBytes;
-  static constexpr int kOffStat = kOffDq + kDqBytes;     // 2 stages
-  static constexpr int kOffBar = kOffStat + 2 * kStatBytes;
+  static constexpr int kOffQ = kOffV + kKBytes;
+  static constexpr int kOffDo = kOffQ + kStages * kQBytes;
+  static constexpr int kOffDs = kOffDo + kStages * kQBytes;      // 2 buffers
+  static constexpr int kOffDq = kOffDs + 2 * kDsBytes;
+  static constexpr int kOffStat = kOffDq + kDqBytes;
+  static constexpr int kOffBar = kOffStat + kStages * kStatBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kUsed = kOffBar + kBarBytes;
   static constexpr int kTotal = kUsed + 1024;            // alignment slack
@@ -90,16 +93,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t s_k = smem_base + S::kOffK, s_v = smem_base + S::kOffV, s_q = smem_base + S::kOffQ, s_do = smem_base + S::kOffDo;
-  const uint32_t s_p = smem_base + S::kOffP, s_ds = smem_base + S::kOffDs, s_dq = smem_base + S::kOffDq, s_stat = smem_base + S::kOffStat;
+  const uint32_t s_ds = smem_base + S::kOffDs, s_dq = smem_base + S::kOffDq, s_stat = smem_base + S::kOffStat;
   const uint32_t s_bar = smem_base + S::kOffBar;
   auto bar = [&](int i) { return s_bar + 8u * i; };
-  const uint32_t kv_full = bar(0);
-  auto q_full = [&](int s) { return bar(1 + s); };
-  auto q_empty = [&](int s) { return bar(3 + s); };
-  auto s_full = [&](int b) { return bar(5 + b); };
-  auto s_free = [&](int b) { return bar(7 + b); };
-  const uint32_t dp_full = bar(9), dp_free = bar(10), p_ready = bar(11), p_free = bar(12), ds_ready = bar(13), ds_free = bar(14);
-  const uint32_t dq_full = bar(15), dq_free = bar(16), dkv_full = bar(17), tmem_slot = bar(18);
+  const uint32_t kv_full = bar(0), dkv_full = bar(1), tmem_slot = bar(2);
+  auto q_full = [&](int s) { return bar(3 + s); };           // 3 stages
+  auto q_empty = [&](int s) { return bar(6 + s); };
+  auto s_full = [&](int b) { return bar(9 + b); };           // everything below: 2 buffers, indexed by (iteration & 1)
+  auto dp_full = [&](int b) { return bar(11 + b); };
+  auto dp_free = [&](int b) { return bar(13 + b); };
+  auto p_ready = [&](int b) { return bar(15 + b); };
+  auto ds_ready = [&](int b) { return bar(17 + b); };
+  auto ds_free = [&](int b) { return bar(19 + b); };
+  auto dq_full = [&](int b) { return bar(21 + b); };
+  auto dq_free = [&](int b) { return bar(23 + b); };
 
   const uint32_t warp = warp_id(), lane = lane_id();
   const int bh_count = prm.B * prm.H;
@@ -117,10 +124,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
   if (warp == 1) {
     if (elect_one()) {
-      mbar_init(kv_full, 1);
-      for (int s = 0; s < 2; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); mbar_init(s_full(s), 1); mbar_init(s_free(s), 8); }
-      mbar_init(dp_full, 1); mbar_init(dp_free, 8); mbar_init(p_ready, 8); mbar_init(p_free, 1); mbar_init(ds_ready, 8); mbar_init(ds_free, 1);
-      mbar_init(dq_full, 1); mbar_init(dq_free, 4); mbar_init(dkv_full, 1);
+      mbar_init(kv_full, 1); mbar_init(dkv_full, 1);
+      for (int s = 0; s < S::kStages; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(s_full(s), 1); mbar_init(dp_full(s), 1); mbar_init(dp_free(s), 8); mbar_init(p_ready(s), 8);
+        mbar_init(ds_ready(s), 8); mbar_init(ds_free(s), 1); mbar_init(dq_full(s), 1); mbar_init(dq_free(s), 4);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -131,7 +140,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-  const uint32_t t_s = tmem, t_dp = tmem + 128, t_dq = tmem + 192, t_dv = tmem + 256, t_dk = tmem + 384;
+  // TMEM columns: S^T[2] (each also hosts P^T as packed bf16 in its first 32 columns, and later the dQ^T of the same query tile), dP^T[2], dV, dK
+  auto t_s = [&](int x) { return tmem + 64u * x; };
+  auto t_dp = [&](int x) { return tmem + 128u + 64u * x; };
+  const uint32_t t_dv = tmem + 256, t_dk = tmem + 384;
 
   if (warp == 0) {
     // ======================================================================================= TMA producer
@@ -142,8 +154,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         tma_tile(&tmap_v, prm.swapped & 4u, kv_full, s_v + p * 16384, h * prm.hs_v + p * 64, k0, b);
       }
       for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1, q0 = (i_begin + it) * kQt;
-        mbar_wait(q_empty(st), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        const int st = it % S::kStages, q0 = (i_begin + it) * kQt;
+        mbar_wait(q_empty(st), (((uint32_t)(it / S::kStages)) & 1u) ^ 1u);
         mbar_arrive_expect_tx(q_full(st), 2 * S::kQBytes + S::kStatBytes);
         for (int p = 0; p < 2; ++p) {
           tma_tile(&tmap_q, prm.swapped & 1u, q_full(st), s_q + st * S::kQBytes + p * 8192, h * prm.hs_q + p * 64, q0, b);
@@ -156,65 +168,64 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else if (warp == 1) {
     // ======================================================================================= MMA issuer
+    // Software pipeline, two query tiles deep: while the math warps turn S^T_i / dP^T_i into P^T_i / dS^T_i, the tensor core already holds
+    // S^T_{i+1} / dP^T_{i+1}, and it computes S^T_{i+2} / dP^T_{i+2} right behind the three products of tile i.
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc(1, 1, 1, false, false, kKv, kQt);      // S^T, dP^T: both operands K-major
-      const uint32_t idesc_acc = umma_idesc(1, 1, 1, false, true, kKv, kHd);     // dV, dK: A K-major, B MN-major
+      const uint32_t idesc_acc = umma_idesc(1, 1, 1, false, true, kKv, kHd);     // dV, dK: A K-major (tensor / shared memory), B MN-major
       const uint32_t idesc_dq = umma_idesc(1, 1, 1, true, true, kHd, kQt);       // dQ^T: both MN-major
       constexpr uint64_t kDescK = umma_desc_hi_lo(16, 1024);
       constexpr uint64_t kDescMN8 = umma_desc_hi_lo(8192, 1024);                 // 64-wide MN chunks 8 KB apart (Q_i / dO_i panels)
       constexpr uint64_t kDescMN16 = umma_desc_hi_lo(16384, 1024);               // ... 16 KB apart (K_j panels; dS^T has a single chunk)
-      auto issue_s = [&](int it) {
-        const int st = it & 1;
-        const uint32_t sq = s_q + st * S::kQBytes;
+      auto issue_s_dp = [&](int it) {                    // S^T_it and dP^T_it into buffer it & 1 (stage it % 3 has landed)
+        const int x = it & 1, st = it % S::kStages;
+        const uint32_t sq = s_q + st * S::kQBytes, sdo = s_do + st * S::kQBytes;
 #pragma unroll
         for (int kk = 0; kk < kHd / 16; ++kk)
-          umma_f16<1>(t_s + 64 * st, umma_desc(s_k + (kk / 4) * 16384 + (kk % 4) * 32, kDescK), umma_desc(sq + (kk / 4) * 8192 + (kk % 4) * 32, kDescK),
+          umma_f16<1>(t_s(x), umma_desc(s_k + (kk / 4) * 16384 + (kk % 4) * 32, kDescK), umma_desc(sq + (kk / 4) * 8192 + (kk % 4) * 32, kDescK),
                       idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit<1>(s_full(st));
+        umma_commit<1>(s_full(x));
+#pragma unroll
+        for (int kk = 0; kk < kHd / 16; ++kk)
+          umma_f16<1>(t_dp(x), umma_desc(s_v + (kk / 4) * 16384 + (kk % 4) * 32, kDescK), umma_desc(sdo + (kk / 4) * 8192 + (kk % 4) * 32, kDescK),
+                      idesc_s, kk != 0 ? 1u : 0u);
+        umma_commit<1>(dp_full(x));
       };
       mbar_wait(kv_full, 0);
-      mbar_wait(q_full(0), 0);
-      tcgen05_fence_after();
-      issue_s(0);
+      for (int it = 0; it < 2 && it < n_iter; ++it) {
+        mbar_wait(q_full(it), 0);
+        tcgen05_fence_after();
+        issue_s_dp(it);
+      }
       for (int it = 0; it < n_iter; ++it) {
-        const int st = it & 1;
-        const uint32_t sdo = s_do + st * S::kQBytes, sq = s_q + st * S::kQBytes;
-        // dP^T_it = V dO^T
-        mbar_wait(dp_free, ((uint32_t)it & 1u) ^ 1u);
-        tcgen05_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < kHd / 16; ++kk)
-          umma_f16<1>(t_dp, umma_desc(s_v + (kk / 4) * 16384 + (kk % 4) * 32, kDescK), umma_desc(sdo + (kk / 4) * 8192 + (kk % 4) * 32, kDescK),
-                      idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit<1>(dp_full);
-        // S^T of the next query tile while the math warps work on this one
-        if (it + 1 < n_iter) {
-          const int nb = (it + 1) & 1;
-          mbar_wait(q_full(nb), (((uint32_t)(it + 1)) >> 1) & 1u);
-          mbar_wait(s_free(nb), ((((uint32_t)(it + 1)) >> 1) & 1u) ^ 1u);
-          tcgen05_fence_after();
-          issue_s(it + 1);
-        }
-        // dV += P_drop^T dO
-        mbar_wait(p_ready, (uint32_t)it & 1u);
+        const int x = it & 1, st = it % S::kStages;
+        const uint32_t ph = ((uint32_t)it >> 1) & 1u;
+        const uint32_t sdo = s_do + st * S::kQBytes, sq = s_q + st * S::kQBytes, sds = s_ds + x * S::kDsBytes;
+        // dV += P_drop^T dO   (A = P^T read from tensor memory: packed bf16 in the first 32 columns of S^T[x])
+        mbar_wait(p_ready(x), ph);
         tcgen05_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kQt / 16; ++kk)
-          umma_f16<1>(t_dv, umma_desc(s_p + kk * 32, kDescK), umma_desc(sdo + kk * 2048, kDescMN8), idesc_acc, (it | kk) != 0 ? 1u : 0u);
-        umma_commit<1>(p_free);
-        // dK += dS^T Q ; dQ^T = K^T dS^T
-        mbar_wait(ds_ready, (uint32_t)it & 1u);
-        mbar_wait(dq_free, ((uint32_t)it & 1u) ^ 1u);
+          umma_f16_ts(t_dv, t_s(x) + kk * 8, umma_desc(sdo + kk * 2048, kDescMN8), idesc_acc, (it | kk) != 0 ? 1u : 0u);
+        // dK += dS^T Q ; dQ^T = K^T dS^T  (into S^T[x]: its scores and P^T have been consumed by the products issued above)
+        mbar_wait(ds_ready(x), ph);
         tcgen05_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kQt / 16; ++kk)
-          umma_f16<1>(t_dk, umma_desc(s_ds + kk * 32, kDescK), umma_desc(sq + kk * 2048, kDescMN8), idesc_acc, (it | kk) != 0 ? 1u : 0u);
+          umma_f16<1>(t_dk, umma_desc(sds + kk * 32, kDescK), umma_desc(sq + kk * 2048, kDescMN8), idesc_acc, (it | kk) != 0 ? 1u : 0u);
 #pragma unroll
         for (int kk = 0; kk < kKv / 16; ++kk)
-          umma_f16<1>(t_dq, umma_desc(s_k + kk * 2048, kDescMN16), umma_desc(s_ds + kk * 2048, kDescMN16), idesc_dq, kk != 0 ? 1u : 0u);
-        umma_commit<1>(dq_full);
-        umma_commit<1>(ds_free);
+          umma_f16<1>(t_s(x), umma_desc(s_k + kk * 2048, kDescMN16), umma_desc(sds + kk * 2048, kDescMN16), idesc_dq, kk != 0 ? 1u : 0u);
+        umma_commit<1>(dq_full(x));
+        umma_commit<1>(ds_free(x));
         umma_commit<1>(q_empty(st));
+        if (it + 2 < n_iter) {
+          mbar_wait(q_full((it + 2) % S::kStages), ((uint32_t)((it + 2) / S::kStages)) & 1u);
+          mbar_wait(dq_free(x), ph);                  // the drain warps have read dQ^T_it out of S^T[x]
+          mbar_wait(dp_free(x), ph);                  // the math warps have read dP^T_it
+          tcgen05_fence_after();
+          issue_s_dp(it + 2);
+        }
       }
       umma_commit<1>(dkv_full);
     }
@@ -230,18 +241,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t pairs = ((uint32_t)prm.Sk + 1u) >> 1;
     const uint32_t key = attn_rng_key(prm.seed, (uint32_t)bh);
     const bool drop = prm.drop_thresh16 != 0;
+    const float p_to_pdrop = prm.inv_keep / prm.scale;
     for (int it = 0; it < n_iter; ++it) {
-      const int st = it & 1;
+      const int x = it & 1, st = it % S::kStages;
+      const uint32_t ph = ((uint32_t)it >> 1) & 1u;
       const int q0 = (i_begin + it) * kQt + 32 * half;
-      mbar_wait(s_full(st), ((uint32_t)it >> 1) & 1u);
+      mbar_wait(s_full(x), ph);
       tcgen05_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32b_x32(t_s + lane_addr + 64 * st + 32 * half, r);
+      tmem_ld_32x32b_x32(t_s(x) + lane_addr + 32 * half, r);
       tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free(st));
-      mbar_wait(q_full(st), ((uint32_t)it >> 1) & 1u);           // lse / delta of this stage have landed (TMA completes on the same barrier)
+      mbar_wait(q_full(st), ((uint32_t)(it / S::kStages)) & 1u);   // lse / delta of this stage have landed (same barrier as the TMA tiles)
       const float4* lse4 = reinterpret_cast<const float4*>(smem_gen + (s_stat - smem_base) + st * S::kStatBytes) + 8 * half;
       const float4* dl4 = lse4 + kQt / 4;
       float p[32];                                                 // P * scale (the softmax scale is folded in here once)
@@ -278,32 +288,28 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           keep |= (attn_keep(bits, (uint32_t)kg, prm.drop_thresh16) ? 1u : 0u) << c;
         }
       }
-      // P_drop^T -> shared memory (A operand of the dV product); p[] carries the softmax scale, so un-scale together with 1/(1-p)
-      const float p_to_pdrop = prm.inv_keep / prm.scale;
-      mbar_wait(p_free, ((uint32_t)it & 1u) ^ 1u);
+      // P_drop^T -> tensor memory, over the first 32 columns of S^T[x] (this thread: 32 queries = 16 packed words).  Both threads of a key row
+      // must have read their scores before either overwrites them: the two warps of a lane quarter meet on a named barrier.
+      asm volatile("bar.sync %0, 64;" ::"r"(2u + quarter) : "memory");
       {
-        const uint32_t dst_row = s_p + row_off;
+        uint32_t pw[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float w[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { const int c = g * 8 + e; w[e] = ((keep >> c) & 1u) ? p[c] * p_to_pdrop : 0.f; }
-          const uint32_t chunk = (uint32_t)(4 * half + g) ^ (uint32_t)(k_row % 8);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst_row + chunk * 16u), "r"(pack_bf16x2(w[0], w[1])), "r"(pack_bf16x2(w[2], w[3])),
-                       "r"(pack_bf16x2(w[4], w[5])), "r"(pack_bf16x2(w[6], w[7])) : "memory");
-        }
+        for (int c = 0; c < 32; c += 2)
+          pw[c >> 1] = pack_bf16x2(((keep >> c) & 1u) ? p[c] * p_to_pdrop : 0.f, ((keep >> (c + 1)) & 1u) ? p[c + 1] * p_to_pdrop : 0.f);
+        tmem_st_32x32b_x16(t_s(x) + lane_addr + 16 * half, pw);
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();
+      tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(p_ready(x));
       // dS^T * scale = (P scale) o (drop(dP) - delta)
-      mbar_wait(dp_full, (uint32_t)it & 1u);
+      mbar_wait(dp_full(x), ph);
       tcgen05_fence_after();
-      tmem_ld_32x32b_x32(t_dp + lane_addr + 32 * half, r);
+      tmem_ld_32x32b_x32(t_dp(x) + lane_addr + 32 * half, r);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dp_free);
+      if (lane == 0) mbar_arrive(dp_free(x));
       if (drop) {
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
@@ -325,9 +331,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           for (int e = 0; e < 4; ++e) { const int c = c4 * 4 + e; p[c] *= __uint_as_float(r[c]) - dl[e]; }
         }
       }
-      mbar_wait(ds_free, ((uint32_t)it & 1u) ^ 1u);
+      mbar_wait(ds_free(x), ph ^ 1u);                 // the products of tile it - 2 have finished reading this dS^T buffer
       {
-        const uint32_t dst_row = s_ds + row_off;
+        const uint32_t dst_row = s_ds + x * S::kDsBytes + row_off;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t chunk = (uint32_t)(4 * half + g) ^ (uint32_t)(k_row % 8);
@@ -338,7 +344,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
+      if (lane == 0) mbar_arrive(ds_ready(x));
     }
     // ---- epilogue: dV and dK of this key tile (this thread: its key row, channels [64*half, 64*half + 64))
     mbar_wait(dkv_full, 0);
@@ -374,16 +380,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const uint32_t lane_addr = (quarter * 32u) << 16;
     const bool leader = warp == 10 && lane == 0;
     for (int it = 0; it < n_iter; ++it) {
+      const int x = it & 1;
       const int q0 = (i_begin + it) * kQt;
-      mbar_wait(dq_full, (uint32_t)it & 1u);
+      mbar_wait(dq_full(x), ((uint32_t)it >> 1) & 1u);
       tcgen05_fence_after();
       uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(t_dq + lane_addr, r0);
-      tmem_ld_32x32b_x32(t_dq + lane_addr + 32, r1);
+      tmem_ld_32x32b_x32(t_s(x) + lane_addr, r0);
+      tmem_ld_32x32b_x32(t_s(x) + lane_addr + 32, r1);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);
+      if (lane == 0) mbar_arrive(dq_free(x));
       if (leader) tma_store_wait_read<0>();                     // the previous tile's reduce has finished reading the staging buffer
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t col = s_dq + (uint32_t)d * 4u;             // staging tile [64 q][128 d] fp32: a warp writes 32 consecutive floats of one row

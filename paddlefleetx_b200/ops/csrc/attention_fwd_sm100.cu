@@ -1,25 +1,24 @@
-// Flash-style attention forward on tcgen05 / TMEM / TMA (sm_100a), bf16, head_dim 64 or 128, causal or full.
+// Flash-style attention forward on tcgen05 / TMEM / TMA (sm_100a), bf16, head_dim 64 or 128, causal or full, optional dropout.
 //
-//   O[b, s, h, :] = softmax(scale * Q[b, s, h, :] . K[b, :, h, :]^T (+ causal mask)) @ V[b, :, h, :]
-//
-// Tensors stay in the framework layout [B, S, H, D] (no transposes): a 2-D tensor map over [B*S, H*D] addresses the
-// (128 rows x D) tile of one head directly.  One CTA owns a 128-query tile of one (batch, head):
-//   warp 0   TMA producer: Q once, then K / V tiles of 128 keys through a 2-stage ring
-//   warp 1   MMA issuer:   S = Q K^T  (UMMA 128x128x16, both operands K-major)   -> TMEM columns [0, 128)
-//                          PV = P V   (UMMA 128xDx16, P K-major from smem, V MN-major) -> TMEM columns [128, 128 + D)
-//   warps 2-9 softmax:     two threads per query row (each reads its TMEM lane; one takes score columns 0-63 and output channels
-//                          0..D/2, the other the rest): scores drained from TMEM in one pass, row max exchanged through shared
-//                          memory, exp2 with the running max, P written as bf16 in the 128-byte-swizzled K-major layout the second
-//                          MMA consumes; O stays in TMEM (the PV MMA accumulates across tiles) and is rescaled only when the running
-//                          maximum has moved by more than 2^8 (lazy rescale), so no softmax thread waits for a PV MMA per tile
-// S for tile j+1 is issued as soon as the softmax warps have drained S_j from TMEM, so the tensor core computes the next
-// scores while the softmax of the current tile is in its exp / store phase.  Causal tiles above the diagonal are never loaded.
-// Output O (bf16) and the row-wise log-sum-exp (fp32, [B, H, S]) are written straight from registers.
+//   O[b, s, h, :] = softmax(scale * Q[b, s, h, :] . K[b, :, h, :]^T (+ causal mask)) (dropout) @ V[b, :, h, :]
 //
 // Inputs / output are [B, S, H, D] VIEWS (3-D tensor maps over {columns, S, B}): contiguous tensors, the q / k / v slices of a packed
-// projection output and sequence-major storage are all read in place.  Optional dropout on the probabilities uses the counter hash of
-// pfx_attn.cuh, regenerated by the backward kernel (attention_bwd_sm100.cu) — no mask is ever stored.
-// Reference call site: flash_attention in hybrid_model.py:284-301 (FlashAttention-2 library on Ampere mma.sync).
+// projection output and sequence-major storage are all read in place.
+//
+// One CTA owns TWO adjacent 128-query tiles of one (batch, head) and streams the K / V tiles they share.  The two tiles ping-pong:
+// while the eight softmax warps work on the scores of one tile, the tensor core runs P V of the other tile and its next Q K^T, so
+// neither side waits for the other in steady state (the first version, one tile per CTA, alternated the two and sat at 15 % tensor
+// activity / 335 TFLOP/s at S = 1024):
+//   warp 0    TMA producer: both Q tiles once per work item, then K / V tiles of 128 keys through a 2-stage ring
+//   warp 1    MMA issuer:   S_x = Q_x K^T (UMMA 128x128x16, operands from shared memory) -> TMEM; P_x V (UMMA 128xDx16 with the A operand
+//                           read from TENSOR MEMORY: P_x is written by the softmax threads as packed bf16 over the first 64 columns of S_x
+//                           — layout verified by probe_kernels.cu — so probabilities never touch shared memory); O_x accumulates in TMEM
+//   warps 2-9 softmax:      two threads per query row (TMEM lane): scores -> running max (exchanged through shared memory) -> exp2 with the
+//                           scale folded into one FFMA -> dropout (counter hash, pfx_attn.cuh) -> P to TMEM; O is rescaled lazily (only
+//                           when the running maximum moved by more than 2^8), so no softmax thread waits for a P V product per tile
+// TMEM: S_0 / P_0 [0, 128), S_1 / P_1 [128, 256), O_0 [256, 256 + D), O_1 [384, 384 + D).  Causal tiles above the diagonal are never loaded;
+// masks are applied only on diagonal / ragged tiles.  Output O (bf16) and the row-wise log-sum-exp (fp32, [B, H, S]) are written from
+// registers.  Reference call site: flash_attention in hybrid_model.py:284-301 (FlashAttention-2 library on Ampere mma.sync).
 #include <cstdio>
 
 #include "pfx_ptx.cuh"
@@ -34,20 +33,19 @@ namespace pfx {
 namespace {
 
 constexpr int kFaThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two column halves x four TMEM lane quarters)
-constexpr int kFaTile = 128;          // queries per CTA, keys per KV tile
+constexpr int kFaTile = 128;          // queries per tile, keys per KV tile
 
 template <int kD>
 struct FaSmem {
-  static constexpr int kQBytes = kFaTile * kD * 2;
+  static constexpr int kQBytes = kFaTile * kD * 2;            // one query tile
   static constexpr int kKBytes = kFaTile * kD * 2;
   static constexpr int kVBytes = kFaTile * kD * 2;
   static constexpr int kStageBytes = kKBytes + kVBytes;
-  static constexpr int kPBytes = kFaTile * kFaTile * 2;
   static constexpr int kStages = 2;
   static constexpr int kBarBytes = 128;
-  static constexpr int kXchgBytes = 2 * 2 * kFaTile * 4;      // row-statistic exchange between the two threads of a row
-  static constexpr int kAlignSlack = 768;                     // dynamic smem starts 1 KB-aligned when the kernel has no static smem; checked at run time
-  static constexpr int kUsed = 2 * kQBytes + kStages * kStageBytes + kPBytes + kBarBytes + kXchgBytes;   // Q is double-buffered across work items
+  static constexpr int kXchgBytes = 2 * 2 * kFaTile * 4;      // row-statistic exchange between the two threads of a row (double buffered)
+  static constexpr int kAlignSlack = 1024;
+  static constexpr int kUsed = 2 * kQBytes + kStages * kStageBytes + kBarBytes + kXchgBytes;
   static constexpr int kTotal = kAlignSlack + kUsed;
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
@@ -56,9 +54,7 @@ __device__ __forceinline__ void tma3(const CUtensorMap* m, bool swapped, uint32_
   if (swapped) tma_load_3d(m, bar, dst, col, b, s); else tma_load_3d(m, bar, dst, col, s, b);
 }
 
-// Persistent kernel: one CTA per SM walks a list of (query tile, head, batch) work items, longest first, so that barrier / TMEM
-// set-up happens once and the loads of the next item (Q into the other Q buffer, its first K/V tiles) are in flight while the
-// current item finishes; measured per-CTA set-up + drain was ~6 us against ~1.8 us per KV tile in the one-CTA-per-tile version.
+
 template <int kD, bool kCausal>
 __global__ void __launch_bounds__(kFaThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
@@ -66,34 +62,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                      float scale_log2, int hs_q, int hs_k, int hs_v, uint32_t swapped, uint32_t drop_thresh16, float inv_keep, uint64_t seed) {
   using S = FaSmem<kD>;
   constexpr int kPanels = kD / 64;                 // 64-element (128-byte) column panels of a D-wide tile
-  constexpr int kTmemCols = 256;                   // S: [0,128), O: [128, 128 + kD)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_q = smem_base;
+  const uint32_t smem_q = smem_base;                                  // two query tiles
   const uint32_t smem_kv = smem_q + 2 * S::kQBytes;
-  const uint32_t smem_p = smem_kv + S::kStages * S::kStageBytes;
-  const uint32_t smem_bar = smem_p + S::kPBytes;
+  const uint32_t smem_bar = smem_kv + S::kStages * S::kStageBytes;
   const uint32_t smem_xchg = smem_bar + S::kBarBytes;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  if (smem_base - smem_u32(smem_raw) > (uint32_t)S::kAlignSlack) {
-    if (threadIdx.x == 0) printf("pfx attention_fwd: dynamic shared memory base is misaligned by %u bytes\n", smem_base - smem_u32(smem_raw));
-    __trap();
-  }
-  auto q_full = [&](int i) { return smem_bar + 8u * i; };
-  auto q_empty = [&](int i) { return smem_bar + 8u * (2 + i); };
-  auto kv_full = [&](int s) { return smem_bar + 8u * (4 + s); };
-  auto kv_empty = [&](int s) { return smem_bar + 8u * (6 + s); };
-  const uint32_t s_full = smem_bar + 8u * 8, s_free = smem_bar + 8u * 9, p_full = smem_bar + 8u * 10, pv_full = smem_bar + 8u * 11;
+  const uint32_t q_full = smem_bar, q_empty = smem_bar + 8;
+  auto kv_full = [&](int s) { return smem_bar + 8u * (2 + s); };
+  auto kv_empty = [&](int s) { return smem_bar + 8u * (4 + s); };
+  auto s_full = [&](int x) { return smem_bar + 8u * (6 + x); };
+  auto p_full = [&](int x) { return smem_bar + 8u * (8 + x); };
+  auto pv_full = [&](int x) { return smem_bar + 8u * (10 + x); };
   const uint32_t tmem_slot = smem_bar + 8u * 12;
 
   const uint32_t warp = warp_id(), lane = lane_id();
   const int n_q_tiles = (Sq + kFaTile - 1) / kFaTile;
+  const int n_pairs = (n_q_tiles + 1) / 2;
   const int n_kv_all = (Sk + kFaTile - 1) / kFaTile;
   const int hb_count = H * B;
-  const int n_items = n_q_tiles * hb_count;
-  // item w -> (q_tile, h, b): all (h, b) of the longest query tile first, then the next shorter one, ...
-  auto item_q_tile = [&](int w) { return n_q_tiles - 1 - w / hb_count; };
-  auto item_n_kv = [&](int q_tile) {
+  const int n_items = n_pairs * hb_count;
+  // item w -> (query-tile pair, h, b): all (h, b) of the longest pair first, then the next shorter one, ...
+  auto item_pair = [&](int w) { return n_pairs - 1 - w / hb_count; };
+  auto tile_n_kv = [&](int q_tile) {                 // key tiles a query tile attends to (0 for the phantom second tile of an odd count)
+    if (q_tile >= n_q_tiles) return 0;
     return kCausal ? min(n_kv_all, (q_tile * kFaTile + kFaTile - 1 + (Sk - Sq)) / kFaTile + 1) : n_kv_all;
   };
 
@@ -102,20 +95,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
   if (warp == 1) {
     if (elect_one()) {
-      for (int i = 0; i < 2; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1); }
+      mbar_init(q_full, 1); mbar_init(q_empty, 1);
       for (int s2 = 0; s2 < S::kStages; ++s2) { mbar_init(kv_full(s2), 1); mbar_init(kv_empty(s2), 1); }
-      mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(p_full, 8); mbar_init(pv_full, 1);
+      for (int x = 0; x < 2; ++x) { mbar_init(s_full(x), 1); mbar_init(p_full(x), 8); mbar_init(pv_full(x), 1); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc<1>(tmem_slot, kTmemCols);
+    tmem_alloc<1>(tmem_slot, 512);
     tmem_relinquish<1>();
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
-  const uint32_t tmem_s = tmem_base, tmem_pv = tmem_base + 128;
+  auto tmem_s = [&](int x) { return tmem_base + 128u * x; };
+  auto tmem_o = [&](int x) { return tmem_base + 256u + 128u * x; };
 
   if (warp == 0) {
     // ======================================================================================= TMA producer
@@ -123,13 +117,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       uint32_t t = 0;                                   // KV tiles issued so far (all items): ring stage / phase
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-        const int q_tile = item_q_tile(w), hb = w % hb_count, h = hb % H, b = hb / H;
-        const int n_kv = item_n_kv(q_tile);
-        const int qb = it & 1;
-        mbar_wait(q_empty(qb), (((uint32_t)it >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(q_full(qb), S::kQBytes);
-        for (int p = 0; p < kPanels; ++p)
-          tma3(&tmap_q, swapped & 1u, q_full(qb), smem_q + qb * S::kQBytes + p * (kFaTile * 128), h * hs_q + p * 64, q_tile * kFaTile, b);
+        const int pair = item_pair(w), hb = w % hb_count, h = hb % H, b = hb / H;
+        const int n_kv = max(tile_n_kv(2 * pair), tile_n_kv(2 * pair + 1));
+        mbar_wait(q_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(q_full, 2 * S::kQBytes);
+        for (int x = 0; x < 2; ++x)
+          for (int p = 0; p < kPanels; ++p)
+            tma3(&tmap_q, swapped & 1u, q_full, smem_q + x * S::kQBytes + p * (kFaTile * 128), h * hs_q + p * 64, (2 * pair + x) * kFaTile, b);
         for (int j = 0; j < n_kv; ++j, ++t) {
           const int stage = t & 1;
           mbar_wait(kv_empty(stage), ((t >> 1) & 1u) ^ 1u);
@@ -150,192 +144,198 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const uint32_t idesc_pv = umma_idesc(1, 1, 1, false, true, kFaTile, kD);
       constexpr uint64_t kDescK = umma_desc_hi_lo(16, 1024);        // K-major, 128-byte swizzle
       constexpr uint64_t kDescMN = umma_desc_hi_lo(8192, 1024);     // MN-major: 64-channel chunks 8 KB apart
-      uint32_t t = 0;
+      uint32_t t = 0;                                   // global KV tile counter (ring position)
+      uint32_t cnt[2] = {0, 0};                         // tiles processed per slot x: phases of s_full / p_full / pv_full
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-        const int n_kv = item_n_kv(item_q_tile(w));
-        const int qb = it & 1;
-        const uint32_t sq = smem_q + qb * S::kQBytes;
-        mbar_wait(q_full(qb), ((uint32_t)it >> 1) & 1u);
-        auto issue_s = [&](uint32_t tt) {              // S = Q K^T for global tile tt
+        const int pair = item_pair(w);
+        const int nk[2] = {tile_n_kv(2 * pair), tile_n_kv(2 * pair + 1)};
+        const int n_kv = max(nk[0], nk[1]);
+        mbar_wait(q_full, (uint32_t)it & 1u);
+        auto issue_s = [&](int x, uint32_t tt) {          // S_x = Q_x K^T for ring position tt
           const int stage = tt & 1;
-          mbar_wait(kv_full(stage), (tt >> 1) & 1u);
-          mbar_wait(s_free, (tt & 1u) ^ 1u);
-          tcgen05_fence_after();
-          const uint32_t sk = smem_kv + stage * S::kStageBytes;
+          const uint32_t sq = smem_q + x * S::kQBytes, sk = smem_kv + stage * S::kStageBytes;
 #pragma unroll
           for (int k = 0; k < kD / 16; ++k) {
             const uint32_t off = (k / 4) * (kFaTile * 128) + (k % 4) * 32;
-            umma_f16<1>(tmem_s, umma_desc(sq + off, kDescK), umma_desc(sk + off, kDescK), idesc_s, k != 0 ? 1u : 0u);
+            umma_f16<1>(tmem_s(x), umma_desc(sq + off, kDescK), umma_desc(sk + off, kDescK), idesc_s, k != 0 ? 1u : 0u);
           }
-          umma_commit<1>(s_full);
+          umma_commit<1>(s_full(x));
         };
-        issue_s(t);
+        mbar_wait(kv_full(t & 1), (t >> 1) & 1u);
+        tcgen05_fence_after();
+        for (int x = 0; x < 2; ++x) if (nk[x] > 0) issue_s(x, t);
         for (int j = 0; j < n_kv; ++j, ++t) {
-          if (j + 1 < n_kv) issue_s(t + 1);          // next scores while the softmax of this tile runs
-          else umma_commit<1>(q_empty(qb));          // every S MMA of this item has been issued: its Q buffer frees when they finish
           const int stage = t & 1;
-          mbar_wait(p_full, t & 1u);                 // P is in shared memory AND O has been rescaled to this tile's reference maximum
-          tcgen05_fence_after();
           const uint32_t sv = smem_kv + stage * S::kStageBytes + S::kKBytes;
+          for (int x = 0; x < 2; ++x) {
+            if (j >= nk[x]) continue;
+            mbar_wait(p_full(x), cnt[x] & 1u);          // P_x is in tensor memory AND O_x has been rescaled to this tile's reference maximum
+            tcgen05_fence_after();
 #pragma unroll
-          for (int k = 0; k < kFaTile / 16; ++k) {
-            const uint32_t a_off = (k / 4) * (kFaTile * 128) + (k % 4) * 32;                 // P: two 64-key panels
-            const uint32_t b_off = (k / 4) * (kPanels * 8192) + (k % 4) * 2048;              // V: 64-key blocks, 16 keys = 2 KB
-            umma_f16<1>(tmem_pv, umma_desc(smem_p + a_off, kDescK), umma_desc(sv + b_off, kDescMN), idesc_pv, (j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kFaTile / 16; ++k) {
+              const uint32_t b_off = (k / 4) * (kPanels * 8192) + (k % 4) * 2048;              // V: 64-key blocks, 16 keys = 2 KB
+              umma_f16_ts(tmem_o(x), tmem_s(x) + k * 8, umma_desc(sv + b_off, kDescMN), idesc_pv, (j | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<1>(pv_full(x));
+            ++cnt[x];
+            if (j + 1 < nk[x]) {                        // next scores of this tile right behind its P V: the other tile's softmax is running now
+              mbar_wait(kv_full((t + 1) & 1), ((t + 1) >> 1) & 1u);
+              tcgen05_fence_after();
+              issue_s(x, t + 1);
+            }
           }
-          umma_commit<1>(pv_full);
-          umma_commit<1>(kv_empty(stage));
+          umma_commit<1>(kv_empty(stage));              // every product that reads this stage has been issued
         }
+        umma_commit<1>(q_empty);                        // ... and every product that reads the two Q tiles
       }
     }
   } else {
     // ======================================================================================= softmax / epilogue
-    // Two threads per query row: warps 2-5 own score columns [0, 64) and output channels [0, D/2), warps 6-9 the other halves (both
-    // groups map onto the same four TMEM lane quarters).  The row maximum is exchanged through shared memory once per KV tile.
     float (*s_xchg)[2][kFaTile] = reinterpret_cast<float (*)[2][kFaTile]>(smem_gen + (smem_xchg - smem_base));
     const uint32_t q = warp & 3u;
     const int half = (int)((warp - 2u) >> 2);
     const int row = (int)(q * 32u + lane);               // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (q * 32u) << 16;
     constexpr int kDH = kD / 2;
-    // O is accumulated by the tensor core in TMEM across all KV tiles (FlashAttention-4 style).  Probabilities are taken relative
-    // to a reference maximum m_ref that is only advanced — and O / l rescaled — when the true running maximum has moved by more
-    // than 2^8, so the rescale (a TMEM load + store of this thread's D/2 channels) is rare after the first tiles and nothing in
-    // the per-tile critical path waits for the PV MMA.
     constexpr float kRescaleThreshold = 8.f;
-    uint8_t* p_row = smem_gen + (smem_p - smem_base) + half * (kFaTile * 128) + (row / 8) * 1024 + (row % 8) * 128;
-    uint32_t t = 0, x = 0;                              // global tile counter, exchange-buffer counter
+    uint32_t xc = 0;                                     // exchange-buffer counter
+    uint32_t cnt[2] = {0, 0};
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int q_tile = item_q_tile(w), hb = w % hb_count, h = hb % H, b = hb / H;
-      const int n_kv = item_n_kv(q_tile);
-      const int row_g = q_tile * kFaTile + row;
-      float m_ref = -INFINITY, l = 0.f;
+      const int pair = item_pair(w), hb = w % hb_count, h = hb % H, b = hb / H;
+      const int nk[2] = {tile_n_kv(2 * pair), tile_n_kv(2 * pair + 1)};
+      const int n_kv = max(nk[0], nk[1]);
+      float m_ref[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
       const uint32_t rng_key = attn_rng_key(seed, (uint32_t)(b * H + h));
       const uint32_t rng_pairs = ((uint32_t)Sk + 1u) >> 1;
-      for (int j = 0; j < n_kv; ++j, ++t, ++x) {
-        const int col0 = j * kFaTile + half * 64;
-        mbar_wait(s_full, t & 1u);
-        tcgen05_fence_after();
-        // masking is decided per TILE (uniform for the CTA half): only the diagonal tile of a causal item and a ragged last tile pay for the
-        // per-element compares; raw scores are kept and scaled inside the exp2 FFMA (scale > 0: the row maximum commutes with it)
-        const bool need_mask = (kCausal && col0 + 63 > q_tile * kFaTile + (Sk - Sq)) || (col0 + 64 > Sk);
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + half * 64, r0);
-        tmem_ld_32x32b_x32(tmem_s + lane_addr + half * 64 + 32, r1);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);            // S drained into registers: the next QK^T may overwrite it
-        float sc[64];
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        if (need_mask) {
+      for (int j = 0; j < n_kv; ++j) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-            const int cg = col0 + i;
-            if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) v = -INFINITY;
-            sc[i] = v;
-            mx[i & 3] = fmaxf(mx[i & 3], v);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-            sc[i] = v;
-            mx[i & 3] = fmaxf(mx[i & 3], v);
-          }
-        }
-        const float m_part = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;     // log2 units from here on
-        s_xchg[x & 1][half][row] = m_part;
-        // only the two warps that share these 32 rows have to meet (named barrier 2 + lane quarter, 64 threads)
-        asm volatile("bar.sync %0, 64;" ::"r"(2u + q) : "memory");
-        const float m_new = fmaxf(m_part, s_xchg[x & 1][half ^ 1][row]);      // this tile's row maximum (identical in both halves)
-        const bool want = (m_new > m_ref + kRescaleThreshold) || (m_ref == -INFINITY && m_new != -INFINITY);
-        const bool rescale = __any_sync(0xffffffffu, want);
-        if (j > 0) {                                   // PV of the previous tile must be complete before O is touched or P is overwritten
-          mbar_wait(pv_full, (t - 1) & 1u);
+        for (int x = 0; x < 2; ++x) {
+          if (j >= nk[x]) continue;
+          const int q_tile = 2 * pair + x;
+          const int row_g = q_tile * kFaTile + row;
+          const int col0 = j * kFaTile + half * 64;
+          mbar_wait(s_full(x), cnt[x] & 1u);
           tcgen05_fence_after();
-        }
-        if (rescale) {
-          const float m_next = fmaxf(m_ref, m_new);
-          const float f = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_next);
-          if (j > 0) {
+          const bool need_mask = (kCausal && col0 + 63 > q_tile * kFaTile + (Sk - Sq)) || (col0 + 64 > Sk);
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(tmem_s(x) + lane_addr + half * 64, r0);
+          tmem_ld_32x32b_x32(tmem_s(x) + lane_addr + half * 64 + 32, r1);
+          tmem_ld_wait();
+          float sc[64];
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (need_mask) {
 #pragma unroll
-            for (int c = 0; c < kDH; c += 32) {
-              uint32_t r[32];
-              tmem_ld_32x32b_x32(tmem_pv + lane_addr + half * kDH + c, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-              tmem_st_32x32b_x32(tmem_pv + lane_addr + half * kDH + c, r);
+            for (int i = 0; i < 64; ++i) {
+              float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+              const int cg = col0 + i;
+              if (cg >= Sk || (kCausal && cg > row_g + (Sk - Sq))) v = -INFINITY;
+              sc[i] = v;
+              mx[i & 3] = fmaxf(mx[i & 3], v);
             }
-            tmem_st_wait();
-          }
-          l *= f;
-          m_ref = m_next;
-        }
-        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+          } else {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {                  // eight 16-byte chunks (8 keys each) of this half's 64-key panel
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { pv[i] = exp2f(fmaf(sc[g * 8 + i], scale_log2, -m_use)); ls[i & 3] += pv[i]; }
-          if (drop_thresh16 != 0u) {               // the row sum keeps every probability; only the P V product sees the mask
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const uint32_t kg = (uint32_t)(col0 + g * 8 + i);
-              const uint32_t bits = attn_rng_pair(rng_key, (uint32_t)row_g, kg >> 1, rng_pairs);
-              if ((bits & 0xFFFFu) < drop_thresh16) pv[i] = 0.f;
-              if ((bits >> 16) < drop_thresh16) pv[i + 1] = 0.f;
+            for (int i = 0; i < 64; ++i) {
+              const float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+              sc[i] = v;
+              mx[i & 3] = fmaxf(mx[i & 3], v);
             }
           }
-          const int chunk = g ^ (row % 8);
-          uint4 v;
-          v.x = pack_bf16x2(pv[0], pv[1]); v.y = pack_bf16x2(pv[2], pv[3]); v.z = pack_bf16x2(pv[4], pv[5]); v.w = pack_bf16x2(pv[6], pv[7]);
-          *reinterpret_cast<uint4*>(p_row + chunk * 16) = v;
+          const float m_part = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2;     // log2 units from here on
+          s_xchg[xc & 1][half][row] = m_part;
+          // only the two warps that share these 32 rows have to meet (named barrier 2 + lane quarter, 64 threads); it also orders the two
+          // halves' TMEM reads of S_x before either half overwrites its part of the aliased P_x columns
+          asm volatile("bar.sync %0, 64;" ::"r"(2u + q) : "memory");
+          const float m_new = fmaxf(m_part, s_xchg[xc & 1][half ^ 1][row]);      // this tile's row maximum (identical in both halves)
+          ++xc;
+          const bool want = (m_new > m_ref[x] + kRescaleThreshold) || (m_ref[x] == -INFINITY && m_new != -INFINITY);
+          const bool rescale = __any_sync(0xffffffffu, want);
+          if (rescale) {
+            const float m_next = fmaxf(m_ref[x], m_new);
+            const float f = (m_ref[x] == -INFINITY) ? 0.f : exp2f(m_ref[x] - m_next);
+            if (j > 0) {
+              mbar_wait(pv_full(x), (cnt[x] - 1u) & 1u);           // the previous P V of this tile has landed in O_x
+              tcgen05_fence_after();
+#pragma unroll
+              for (int c = 0; c < kDH; c += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_o(x) + lane_addr + half * kDH + c, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                tmem_st_32x32b_x32(tmem_o(x) + lane_addr + half * kDH + c, r);
+              }
+            }
+            l[x] *= f;
+            m_ref[x] = m_next;
+          }
+          const float m_use = (m_ref[x] == -INFINITY) ? 0.f : m_ref[x];
+          float ls[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t pw[32];                                // this half's 64 probabilities as packed bf16
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { pv[i] = exp2f(fmaf(sc[g * 8 + i], scale_log2, -m_use)); ls[i & 3] += pv[i]; }
+            if (drop_thresh16 != 0u) {               // the row sum keeps every probability; only the P V product sees the mask
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) {
+                const uint32_t kg = (uint32_t)(col0 + g * 8 + i);
+                const uint32_t bits = attn_rng_pair(rng_key, (uint32_t)row_g, kg >> 1, rng_pairs);
+                if ((bits & 0xFFFFu) < drop_thresh16) pv[i] = 0.f;
+                if ((bits >> 16) < drop_thresh16) pv[i + 1] = 0.f;
+              }
+            }
+            pw[g * 4 + 0] = pack_bf16x2(pv[0], pv[1]); pw[g * 4 + 1] = pack_bf16x2(pv[2], pv[3]);
+            pw[g * 4 + 2] = pack_bf16x2(pv[4], pv[5]); pw[g * 4 + 3] = pack_bf16x2(pv[6], pv[7]);
+          }
+          l[x] += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+          tmem_st_32x32b_x32(tmem_s(x) + lane_addr + half * 32, pw);       // P_x over the first 64 columns of S_x: keys [64 half, 64 half + 64)
+          tmem_st_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_full(x));
+          ++cnt[x];
         }
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-        tcgen05_fence_before();
-        fence_proxy_async_smem();                    // generic-proxy stores of P -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
       }
-      // item epilogue: wait for the last PV, read this thread's half of O once, normalise by the full row sum.  The next item's
-      // loads and first QK^T are already running underneath.
-      mbar_wait(pv_full, (t - 1) & 1u);
-      tcgen05_fence_after();
-      s_xchg[x & 1][half][row] = l;
-      asm volatile("bar.sync %0, 64;" ::"r"(2u + q) : "memory");
-      const float l_all = l + s_xchg[x & 1][half ^ 1][row];
-      ++x;
-      const float inv = l_all > 0.f ? inv_keep / l_all : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * o_sb + (size_t)row_g * o_ss + (size_t)h * o_sh + half * kDH);
+      // item epilogue: wait for the last P V of each tile, read this thread's half of O once, normalise by the full row sum
 #pragma unroll
-      for (int c = 0; c < kDH; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_pv + lane_addr + half * kDH + c, r);
-        tmem_ld_wait();
-        if (row_g < Sq) {
+      for (int x = 0; x < 2; ++x) {
+        if (nk[x] == 0) continue;
+        const int row_g = (2 * pair + x) * kFaTile + row;
+        mbar_wait(pv_full(x), (cnt[x] - 1u) & 1u);
+        tcgen05_fence_after();
+        s_xchg[xc & 1][half][row] = l[x];
+        asm volatile("bar.sync %0, 64;" ::"r"(2u + q) : "memory");
+        const float l_all = l[x] + s_xchg[xc & 1][half ^ 1][row];
+        ++xc;
+        const float inv = l_all > 0.f ? inv_keep / l_all : 0.f;
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * o_sb + (size_t)row_g * o_ss + (size_t)h * o_sh + half * kDH);
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 v;
-            v.x = pack_bf16x2(__uint_as_float(r[i + 0]) * inv, __uint_as_float(r[i + 1]) * inv);
-            v.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
-            v.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
-            v.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
-            dst[(c + i) / 8] = v;
+        for (int c = 0; c < kDH; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_o(x) + lane_addr + half * kDH + c, r);
+          tmem_ld_wait();
+          if (row_g < Sq) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(r[i + 0]) * inv, __uint_as_float(r[i + 1]) * inv);
+              v.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv);
+              v.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv);
+              v.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv);
+              dst[(c + i) / 8] = v;
+            }
           }
         }
+        if (row_g < Sq && lse != nullptr && half == 0)
+          lse[((size_t)b * H + h) * Sq + row_g] = (l_all > 0.f) ? (m_ref[x] + log2f(l_all)) * 0.6931471805599453f : -INFINITY;
       }
-      if (row_g < Sq && lse != nullptr && half == 0)
-        lse[((size_t)b * H + h) * Sq + row_g] = (l_all > 0.f) ? (m_ref + log2f(l_all)) * 0.6931471805599453f : -INFINITY;
       tcgen05_fence_before();
     }
   }
   __syncthreads();
-  if (warp == 1) tmem_dealloc<1>(tmem_base, kTmemCols);
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
 template <int kD, bool kCausal>
@@ -359,7 +359,7 @@ cudaError_t launch_fa(const AttnView& q, const AttnView& k, const AttnView& v, c
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long items = (long)((Sq + kFaTile - 1) / kFaTile) * H * B;
+  const long items = (long)(((Sq + kFaTile - 1) / kFaTile + 1) / 2) * H * B;        // one work item = a pair of query tiles
   const int grid = (int)(items < sms ? items : sms);
   const uint32_t thresh = drop.p > 0.f ? (uint32_t)(drop.p * 65536.f + 0.5f) : 0u;
   const float inv_keep = drop.p > 0.f ? 1.f / (1.f - drop.p) : 1.f;

@@ -810,6 +810,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("attention_fwd", &attention_fwd);
   m.def("probe_tmem_a", &probe_tmem_a);
+  m.def("tmap_cache_stats", []() { uint64_t h = 0, ms = 0; pfx::tmap_cache_stats(&h, &ms); return std::make_pair((int64_t)h, (int64_t)ms); });
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);
   m.def("embedding_bwd_max_tokens", &embedding_bwd_max_tokens);

@@ -58,6 +58,9 @@ struct LowpGemmArgs {
 };
 cudaError_t gemm_lowp_tcgen05(const LowpGemmArgs& args, cudaStream_t stream);
 
+// hit / miss counters of the tensor-map descriptor cache (diagnostics)
+void tmap_cache_stats(uint64_t* hits, uint64_t* misses);
+
 bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_code, uint64_t inner, uint64_t outer,
                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 

@@ -12,13 +12,6 @@ namespace pfx {
 
 namespace {
 
-// A from TMEM: tcgen05.mma.cta_group::1.kind::f16 [d], [a_tmem], b_desc, idesc, p
-__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 
 template <int kN, int kK>
 __global__ void __launch_bounds__(128, 1) probe_tmem_a_kernel(const __nv_bfloat16* __restrict__ a, const __grid_constant__ CUtensorMap tmap_b,
