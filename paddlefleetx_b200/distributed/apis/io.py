@@ -47,7 +47,16 @@ def _cpu(obj):
 
 
 def _expert_keys(model: torch.nn.Module) -> set:
-    return {n for n, p in model.named_parameters() if getattr(p, "is_expert", False)}
+    """State-dict keys of expert parameters.  Stacked expert parameters (moe/grouped_experts.py) appear in checkpoints under their per-expert
+    names, so those are generated from the owning layer."""
+    keys = {n for n, p in model.named_parameters() if getattr(p, "is_expert", False)}
+    for name, mod in model.named_modules():
+        ge = getattr(mod, "grouped", None)
+        if ge is not None and hasattr(ge, "NAMES"):
+            prefix = name + "." if name else ""
+            for _, lin, attr in ge.NAMES:
+                keys.update(f"{prefix}experts.{e}.{lin}.{attr}" for e in range(ge.num_expert))
+    return keys
 
 
 def _expert_replica_dir(d: str) -> Optional[str]:

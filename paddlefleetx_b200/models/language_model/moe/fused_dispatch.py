@@ -22,7 +22,7 @@ import torch
 from ....ops import _native
 from ....parallel.symmetric_memory import get_allocator
 
-ALIGN = 128
+ALIGN = 256      # expert blocks start on 256-row boundaries: a 2-CTA (256-row) GEMM tile never straddles two experts
 
 
 class MoEDispatcher:
@@ -43,6 +43,11 @@ class MoEDispatcher:
         self.stage_out: Optional[torch.Tensor] = None
         self.layer_bufs: Dict[int, torch.Tensor] = {}
         self.epoch = 0
+        # receive-buffer overflow of the sync-free path: a sticky device flag, mirrored to pinned memory asynchronously and examined one
+        # step late (the host never waits for the routing result)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._ovf_event = None
         props = torch.cuda.get_device_properties(dev)
         self.num_ctas = num_ctas or 2 * props.multi_processor_count
         torch.cuda.synchronize()
@@ -66,6 +71,21 @@ class MoEDispatcher:
             self.layer_bufs[layer_key] = self.alloc.empty((self.cap_rows, self.hidden), self.dtype)
         return self.layer_bufs[layer_key]
 
+    def poll_overflow(self):
+        ev = self._ovf_event
+        if ev is not None:
+            if not ev.query():
+                return
+            self._ovf_event = None
+            if int(self._ovf_host[0]):
+                raise RuntimeError(f"MoE receive buffer overflow (capacity {self.cap_rows} rows per rank): raise moe p2p_capacity_factor")
+        self._ovf_host.copy_(self.overflow, non_blocking=True)
+        self._ovf_event = torch.cuda.Event()
+        self._ovf_event.record()
+
+    def tile_table(self, seg: torch.Tensor):
+        return self.lib.moe_tile_table(seg, self.e_local, ALIGN, self.cap_rows, self.overflow)
+
     # -- kernels ----------------------------------------------------------------------------------
     def route(self, gate_idx: torch.Tensor):
         return self.lib.moe_route(gate_idx.reshape(-1).contiguous(), self.world * self.e_local)
@@ -87,15 +107,22 @@ class MoEDispatcher:
 
 class _Plan:
     """Routing state shared by the dispatch and combine halves of one MoE layer invocation."""
-    __slots__ = ("disp", "gate_flat", "slot_rank", "counts", "slot_loc", "seg", "topk", "tokens", "rows_total")
+    __slots__ = ("disp", "gate_flat", "slot_rank", "counts", "slot_loc", "seg", "topk", "tokens", "rows_total", "tile_group", "seg2", "sync_free")
 
 
 class FusedDispatch(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, plan: _Plan, layer_key):
+    def forward(ctx, x, plan: _Plan, layer_key, sync_free=False):
         d = plan.disp
         recv = d.recv_buffer(layer_key)
         plan.slot_loc, plan.seg = d.dispatch(x.contiguous(), None, plan.gate_flat, plan.slot_rank, plan.counts, recv, plan.topk)
+        plan.sync_free = sync_free
+        ctx.plan = plan
+        if sync_free:
+            # grouped expert GEMMs: the whole fixed-capacity buffer goes on, the per-block expert table stays on the device
+            plan.tile_group, plan.seg2 = d.tile_table(plan.seg)
+            plan.rows_total = d.cap_rows
+            return recv[:d.cap_rows], None
         seg = plan.seg.tolist()                     # host sync: sizes the expert loop
         if seg[-1]:
             raise RuntimeError(f"MoE receive buffer overflow: need {seg[-2]} rows, capacity {d.cap_rows}; raise moe capacity_factor")
@@ -107,16 +134,18 @@ class FusedDispatch(torch.autograd.Function):
     def backward(ctx, g_rows, _):
         plan = ctx.plan
         d = plan.disp
-        d.stage_out[:plan.rows_total].copy_(g_rows)
+        if g_rows.data_ptr() != d.stage_out.data_ptr():          # the grouped backward writes dX straight into the staging buffer
+            d.stage_out[:plan.rows_total].copy_(g_rows)
         dx, _ = d.combine(plan.slot_loc, None, plan.tokens, plan.topk, keep_rows=False)
-        return dx, None, None
+        return dx, None, None, None
 
 
 class FusedCombine(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ys, weights, plan: _Plan):
         d = plan.disp
-        d.stage_out[:plan.rows_total].copy_(ys)
+        if ys.data_ptr() != d.stage_out.data_ptr():               # the grouped FFN2 writes its output straight into the staging buffer
+            d.stage_out[:plan.rows_total].copy_(ys)
         w32 = weights.reshape(-1).float().contiguous()
         out, rows = d.combine(plan.slot_loc, w32, plan.tokens, plan.topk, keep_rows=weights.requires_grad)
         ctx.plan = plan
@@ -133,7 +162,8 @@ class FusedCombine(torch.autograd.Function):
         g_out = g_out.contiguous()
         # combine-bwd: rows of w[t,k] * g_out[t] travel to the expert owners (shared staging: consumed right away)
         d.dispatch(g_out, w32, plan.gate_flat, plan.slot_rank, plan.counts, d.stage_in, plan.topk)
-        g_ys = d.stage_in[:plan.rows_total].clone()
+        # sync-free: the grouped expert backward runs next in stream order and is the only reader before the next dispatch into stage_in
+        g_ys = d.stage_in[:plan.rows_total] if plan.sync_free else d.stage_in[:plan.rows_total].clone()
         g_w = None
         if ctx.has_rows:
             valid = (plan.slot_loc >= 0).view(plan.tokens, plan.topk, 1)

@@ -5,8 +5,9 @@
 
 ``num_experts`` is the number of experts PER RANK; the expert-parallel world is the ``moe`` = dp x mp group.  The
 reference's latent attribute bug (``self.num_experts`` vs ``self.num_expert``) is not reproduced.
-Local experts run as a loop of tcgen05 GEMMs over contiguous row ranges (expert-major order is what the dispatch
-produces).  With ``Fused.moe_p2p`` the dispatch/combine run as peer-memory kernels (``fused_dispatch.py``).
+With ``fused_p2p`` the dispatch/combine run as peer-memory kernels (``fused_dispatch.py``) and the local experts as GROUPED tcgen05
+GEMMs driven by the device-side segment table (``grouped_experts.py``): the layer never synchronises with the host.  The NCCL path
+keeps the reference's structure (all-to-all + a loop of GEMMs over contiguous row ranges).
 """
 from __future__ import annotations
 
@@ -47,7 +48,8 @@ class MoELayer(nn.Module):
     _instances = 0
 
     def __init__(self, d_model: int, experts: List[nn.Module], gate=None, moe_group=None, mp_group=None, recompute_interval: int = 0,
-                 recompute_ctx=None, top_k: int = 2, dtype=None, device=None, fused_p2p: bool = False, capacity_factor: float = 2.0):
+                 recompute_ctx=None, top_k: int = 2, dtype=None, device=None, fused_p2p: bool = False, capacity_factor: float = 2.0,
+                 grouped_gemm: bool = True):
         super().__init__()
         self.fused_p2p = fused_p2p              # peer-memory dispatch/combine kernels (fused_dispatch.py) instead of NCCL all-to-all
         self.capacity_factor = capacity_factor
@@ -56,6 +58,16 @@ class MoELayer(nn.Module):
         self.d_model = d_model
         self.experts = nn.ModuleList(experts)
         self.num_expert = len(experts)
+        # With the peer-memory dispatch the experts run as grouped tcgen05 GEMMs over the device-side segment table (grouped_experts.py):
+        # their parameters move into four stacked tensors; checkpoints keep the per-expert names through the two hooks below.
+        self.grouped = None
+        if fused_p2p and grouped_gemm:
+            from .grouped_experts import GroupedExperts
+
+            if GroupedExperts.supported(experts):
+                self.grouped = GroupedExperts(experts)
+                self._register_state_dict_hook(MoELayer._split_expert_state)
+                self._register_load_state_dict_pre_hook(self._merge_expert_state)
         self.group = moe_group
         self.world_size = C.group_size(moe_group)
         self.mp_group = mp_group
@@ -78,6 +90,13 @@ class MoELayer(nn.Module):
         else:
             raise TypeError("gate must be a dict or a NaiveGate instance")
         self.gate = gate
+
+    @staticmethod
+    def _split_expert_state(module, state_dict, prefix, local_metadata):
+        module.grouped.split_state(state_dict, prefix + "grouped.", prefix + "experts.")
+
+    def _merge_expert_state(self, state_dict, prefix, *args):
+        self.grouped.merge_state(state_dict, prefix + "grouped.", prefix + "experts.")
 
     def _experts_forward(self, x: torch.Tensor, counts: List[int]) -> torch.Tensor:
         outs, start = [], 0
@@ -107,7 +126,19 @@ class MoELayer(nn.Module):
         if gate_idx.dim() == 1:
             gate_idx = gate_idx.unsqueeze(1)
         plan = make_plan(disp, gate_idx, x.shape[0])
-        xs, seg = FusedDispatch.apply(x, plan, self._layer_key if (self.training and torch.is_grad_enabled()) else None)
+        layer_key = self._layer_key if (self.training and torch.is_grad_enabled()) else None
+        if self.grouped is not None and x.dtype == torch.bfloat16:
+            # sync-free: dispatch -> tile table -> 2 grouped GEMMs -> combine, all sized by the fixed capacity; the host never reads a count
+            from .fused_dispatch import ALIGN
+            from .grouped_experts import grouped_ffn
+
+            xs, _ = FusedDispatch.apply(x, plan, layer_key, True)
+            ys = grouped_ffn(xs, plan.tile_group, plan.seg2, self.grouped, disp, ALIGN, recompute_h=self.recompute_interval > 0 and self.training)
+            disp.poll_overflow()
+            return FusedCombine.apply(ys, value.reshape(x.shape[0], -1), plan)
+        if self.grouped is not None:
+            self.grouped.bind_views()
+        xs, seg = FusedDispatch.apply(x, plan, layer_key, False)
         starts, counts, total = seg[:self.num_expert], seg[self.num_expert:2 * self.num_expert], seg[2 * self.num_expert]
         if self.recompute_interval > 0 and self.training and xs.requires_grad:
             ys = recompute(self._experts_forward_segments, xs, starts, counts, total)
@@ -127,6 +158,8 @@ class MoELayer(nn.Module):
             if mp_world > 1:
                 out = AllGather.apply(out, self.mp_group.rank, mp_world, self.mp_group)
             return out.reshape(origin_shape)
+        if self.grouped is not None:
+            self.grouped.bind_views()
         pos, lec, gec = count_by_gate(gate_idx, self.num_expert, self.world_size, group=self.group)
         fwd_counts = gec.view(self.world_size, self.num_expert).sum(0)
         counts = fwd_counts.tolist()                       # host sync #1 (sizes the expert loop); the P2P path avoids it
@@ -159,4 +192,5 @@ def build_moe_layer(hidden: int, ffn_hidden: int, moe_configs: dict, num_layers:
     gate_cfg = {"type": moe_configs.get("gate", "gshard"), "top_k": int(moe_configs.get("top_k", 2))}
     return MoELayer(hidden, experts, gate=gate_cfg, moe_group=moe_group, mp_group=mp_group if C.group_size(mp_group) > 1 else None,
                     recompute_interval=int(moe_configs.get("recompute_interval", 0)), dtype=dtype, device=device,
-                    fused_p2p=bool(moe_configs.get("fused_p2p", False)), capacity_factor=float(moe_configs.get("p2p_capacity_factor", 2.0)))
+                    fused_p2p=bool(moe_configs.get("fused_p2p", False)), capacity_factor=float(moe_configs.get("p2p_capacity_factor", 2.0)),
+                    grouped_gemm=bool(moe_configs.get("grouped_gemm", True)))

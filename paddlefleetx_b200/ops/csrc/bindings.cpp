@@ -757,6 +757,78 @@ std::vector<at::Tensor> moe_dispatch(const at::Tensor& src, c10::optional<at::Te
                                    dtype_code(src), (int)num_ctas, cur_stream()));
   return {slot_loc, seg};
 }
+// tile table + K segments of the grouped expert GEMMs, from the dispatch kernel's segment table (all on the device)
+std::vector<at::Tensor> moe_tile_table(const at::Tensor& seg, int64_t e_local, int64_t align, int64_t cap_rows, at::Tensor& sticky) {
+  TORCH_CHECK(seg.is_cuda() && seg.scalar_type() == at::kInt && seg.numel() == 2 * e_local + 2 && sticky.scalar_type() == at::kInt, "moe_tile_table: bad seg");
+  at::Tensor tile_group = at::empty({cap_rows / 128}, seg.options()), seg2 = at::empty({2 * e_local}, seg.options());
+  PFX_CUDA_CHECK(pfx::moe_tile_table(seg.data_ptr<int>(), (int)e_local, (int)align, (int)cap_rows, tile_group.data_ptr<int>(), seg2.data_ptr<int>(),
+                                     sticky.data_ptr<int>(), cur_stream()));
+  return {tile_group, seg2};
+}
+
+// Grouped expert GEMM, rows grouped: d[r, :] = a[r, :] . B[g(r)]^T (+ bias[g(r)]) for the expert g(r) that owns row block r / 128.
+//   b: [G, N, K] (b_kmajor: forward) or [G, K, N] (dgrad).  epilogue: EPI_NONE / EPI_BIAS / EPI_BIAS_GELU_DUAL (out2) / EPI_DGELU (aux).
+at::Tensor gemm_grouped(const at::Tensor& a, const at::Tensor& b, c10::optional<at::Tensor> bias, const at::Tensor& tile_group, at::Tensor& out,
+                        bool b_kmajor, int64_t epilogue, c10::optional<at::Tensor> out2, c10::optional<at::Tensor> aux, int64_t row_align) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 3 && a.is_contiguous() && b.is_contiguous() && out.is_contiguous(), "gemm_grouped: a [M,K], b [G,*,*] contiguous");
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16, "gemm_grouped: bf16 only");
+  const int64_t M = a.size(0), K = a.size(1), G = b.size(0);
+  const int64_t N = b_kmajor ? b.size(1) : b.size(2);
+  TORCH_CHECK((b_kmajor ? b.size(2) : b.size(1)) == K, "gemm_grouped: K mismatch");
+  TORCH_CHECK(M % 128 == 0 && tile_group.numel() == M / 128 && tile_group.scalar_type() == at::kInt, "gemm_grouped: tile table must cover M / 128 blocks");
+  TORCH_CHECK(out.dim() == 2 && out.size(0) == M && out.size(1) == N && N % 8 == 0 && K % 64 == 0, "gemm_grouped: out [M, N], N % 8 == 0, K % 64 == 0");
+  const c10::cuda::CUDAGuard guard(a.device());
+  pfx::GemmArgs g{};
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = out.data_ptr();
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == G * N && bias->is_contiguous(), "gemm_grouped: bias [G, N] bf16");
+    g.bias = bias->data_ptr();
+  } else {
+    TORCH_CHECK(epilogue == pfx::EPI_NONE || epilogue == pfx::EPI_DGELU, "gemm_grouped: bias epilogue without bias");
+  }
+  if (epilogue == pfx::EPI_BIAS_GELU_DUAL) {
+    TORCH_CHECK(out2.has_value() && out2->is_contiguous() && out2->sizes() == out.sizes() && out2->scalar_type() == at::kBFloat16, "gemm_grouped: out2 like out");
+    g.d2 = out2->data_ptr();
+  }
+  if (epilogue == pfx::EPI_DGELU) {
+    TORCH_CHECK(aux.has_value() && aux->is_contiguous() && aux->sizes() == out.sizes() && aux->scalar_type() == at::kBFloat16, "gemm_grouped: aux like out");
+    g.aux = aux->data_ptr(); g.ld_aux = (int)N;
+  }
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.lda = (int)K; g.ldb = (int)(b_kmajor ? K : N); g.ldd = (int)N;
+  g.a_kmajor = true; g.b_kmajor = b_kmajor; g.out_mode = 0; g.epilogue = (int)epilogue; g.ab_format = 1; g.num_sms = num_sms(); g.config = 0;
+  g.group.mode = 1; g.group.tile_group = tile_group.data_ptr<int>(); g.group.groups = (int)G; g.group.b_group_stride = (int)(b_kmajor ? N : K);
+  g.group.row_align = (int)row_align;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+  return out;
+}
+
+// Grouped expert wgrad: out[g] = dy[rows of g]^T . x[rows of g]   (dy [R, Mg], x [R, N], out [G, Mg, N] bf16; seg2 = (start, padded count) per expert)
+at::Tensor gemm_grouped_wgrad(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& seg2, at::Tensor& out) {
+  TORCH_CHECK(dy.is_cuda() && dy.dim() == 2 && x.dim() == 2 && out.dim() == 3 && dy.is_contiguous() && x.is_contiguous() && out.is_contiguous(), "gemm_grouped_wgrad: contiguous");
+  TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && x.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16, "gemm_grouped_wgrad: bf16 only");
+  const int64_t R = dy.size(0), Mg = dy.size(1), N = x.size(1), G = out.size(0);
+  TORCH_CHECK(x.size(0) == R && out.size(1) == Mg && out.size(2) == N && seg2.numel() == 2 * G && seg2.scalar_type() == at::kInt, "gemm_grouped_wgrad: shapes");
+  TORCH_CHECK(Mg % 128 == 0 && N % 8 == 0, "gemm_grouped_wgrad: Mg % 128 == 0, N % 8 == 0");
+  const c10::cuda::CUDAGuard guard(dy.device());
+  pfx::GemmArgs g{};
+  g.a = dy.data_ptr(); g.b = x.data_ptr(); g.d = out.data_ptr();
+  g.M = (int)(G * Mg); g.N = (int)N; g.K = (int)R;
+  g.lda = (int)Mg; g.ldb = (int)N; g.ldd = (int)N;
+  g.a_kmajor = false; g.b_kmajor = false; g.out_mode = 0; g.epilogue = pfx::EPI_NONE; g.ab_format = 1; g.num_sms = num_sms(); g.config = 0;
+  g.group.mode = 2; g.group.seg = seg2.data_ptr<int>(); g.group.groups = (int)G; g.group.m_per_group = (int)Mg;
+  PFX_CUDA_CHECK(pfx::gemm_tcgen05(g, cur_stream()));
+  return out;
+}
+
+at::Tensor grouped_colsum(const at::Tensor& x, const at::Tensor& seg2, int64_t groups) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && seg2.numel() == 2 * groups && seg2.scalar_type() == at::kInt, "grouped_colsum: x [R, N], seg2 [2G]");
+  const c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor out = at::empty({groups, x.size(1)}, x.options());
+  PFX_CUDA_CHECK(pfx::grouped_colsum(x.data_ptr(), seg2.data_ptr<int>(), (int)groups, (int)x.size(1), out.data_ptr(), dtype_code(x), cur_stream()));
+  return out;
+}
+
 void moe_combine(const std::vector<int64_t>& peer_src, const at::Tensor& slot_loc, c10::optional<at::Tensor> weights, at::Tensor& out,
                  c10::optional<at::Tensor> rows, const std::vector<int64_t>& peer_flags, int64_t topk, int64_t rank, int64_t epoch,
                  int64_t num_ctas) {
@@ -810,6 +882,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("p2p_all_gather", &p2p_all_gather);
   m.def("attention_fwd", &attention_fwd);
   m.def("probe_tmem_a", &probe_tmem_a);
+  m.def("moe_tile_table", &moe_tile_table);
+  m.def("gemm_grouped", &gemm_grouped, py::arg("a"), py::arg("b"), py::arg("bias"), py::arg("tile_group"), py::arg("out"), py::arg("b_kmajor") = true,
+        py::arg("epilogue") = 0, py::arg("out2") = py::none(), py::arg("aux") = py::none(), py::arg("row_align") = 128);
+  m.def("gemm_grouped_wgrad", &gemm_grouped_wgrad);
+  m.def("grouped_colsum", &grouped_colsum);
   m.def("tmap_cache_stats", []() { uint64_t h = 0, ms = 0; pfx::tmap_cache_stats(&h, &ms); return std::make_pair((int64_t)h, (int64_t)ms); });
   m.def("embedding_fwd", &embedding_fwd);
   m.def("embedding_bwd_", &embedding_bwd_);

@@ -117,7 +117,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float* __restrict__ out_f32, const __nv_bfloat16* __restrict__ bias,
                     int M, int N, int K, int ldd, int epilogue, uint32_t ab_format, const __grid_constant__ GemmComm comm,
                     const __grid_constant__ PeerMaps peer_maps, const __grid_constant__ CUtensorMap tmap_d2,
-                    const __nv_bfloat16* __restrict__ aux, int ld_aux) {
+                    const __nv_bfloat16* __restrict__ aux, int ld_aux, const __grid_constant__ GemmGroup grp) {
   using S = GemmSmem<kCG, kBlockN>;
   constexpr int kStages = S::kStages;
   constexpr int kLoadN = S::kLoadN;
@@ -185,14 +185,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks, m_rotate);
-        const int m_idx = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
+        int m_idx = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
         const int n_idx = tc.n_blk * kBlockN + (int)cta_rank * kLoadN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        int tile_k_blocks = num_k_blocks, k_base = 0, b_row_off = 0;
+        if (grp.mode == 1) {          // the expert that owns this row block selects the slice of the stacked B operand
+          const int g = __ldg(grp.tile_group + tc.m_blk * kCG);
+          if (g < 0) continue;
+          b_row_off = g * grp.b_group_stride;
+        } else if (grp.mode == 2) {   // the tile's expert selects the K (token-row) range; A is addressed inside the expert's [rows, m_per_group]
+          const int g = (tc.m_blk * kUmmaM) / grp.m_per_group;
+          k_base = __ldg(grp.seg + 2 * g);
+          tile_k_blocks = __ldg(grp.seg + 2 * g + 1) / kBlockK;
+          m_idx -= g * grp.m_per_group;
+        }
+        for (int kb = 0; kb < tile_k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_ab + stage * S::kStageBytes;
           const uint32_t sb = sa + S::kABytes;
           const uint32_t fb = full_bar(stage);
-          const int k_idx = kb * kBlockK;
+          const int k_idx = k_base + kb * kBlockK;
           if (kCG == 1 || is_leader) mbar_arrive_expect_tx(fb, S::kStageBytes * kCG);
           if constexpr (kAK) {
             if (comm.ag_world > 1) {
@@ -222,12 +233,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           if constexpr (kBK) {
-            if (kCG == 2) tma_load_2d_2sm(&tmap_b, fb, sb, k_idx, n_idx); else tma_load_2d(&tmap_b, fb, sb, k_idx, n_idx);
+            if (kCG == 2) tma_load_2d_2sm(&tmap_b, fb, sb, k_idx, n_idx + b_row_off); else tma_load_2d(&tmap_b, fb, sb, k_idx, n_idx + b_row_off);
           } else {
 #pragma unroll
             for (int j = 0; j < kLoadN / 64; ++j) {
-              if (kCG == 2) tma_load_2d_2sm(&tmap_b, fb, sb + j * 8192, n_idx + j * 64, k_idx);
-              else tma_load_2d(&tmap_b, fb, sb + j * 8192, n_idx + j * 64, k_idx);
+              if (kCG == 2) tma_load_2d_2sm(&tmap_b, fb, sb + j * 8192, n_idx + j * 64, k_idx + b_row_off);
+              else tma_load_2d(&tmap_b, fb, sb + j * 8192, n_idx + j * 64, k_idx + b_row_off);
             }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -247,10 +258,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tile_k_blocks = num_k_blocks;
+        if (grp.mode != 0) {
+          const int m_blk = tile_coord(tile, num_m_blocks, num_n_blocks, m_rotate).m_blk;
+          if (grp.mode == 1) { if (__ldg(grp.tile_group + m_blk * kCG) < 0) continue; }
+          else tile_k_blocks = __ldg(grp.seg + 2 * ((m_blk * kUmmaM) / grp.m_per_group) + 1) / kBlockK;
+        }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kBlockN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = 0; kb < tile_k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_ab + stage * S::kStageBytes;
@@ -280,6 +297,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const TileCoord tc = tile_coord(tile, num_m_blocks, num_n_blocks, m_rotate);
       const int row0 = tc.m_blk * kUmmaM + (int)cta_rank * kBlockM;
       const int col_tile = tc.n_blk * kBlockN;
+      const __nv_bfloat16* tile_bias = bias;
+      bool empty_k = false;           // K-grouped tile of an expert without tokens: the accumulator was never written, the result is zero
+      if (grp.mode == 1) {
+        const int g = __ldg(grp.tile_group + tc.m_blk * kCG);
+        if (g < 0) continue;
+        if (bias != nullptr) tile_bias = bias + (size_t)g * N;
+      } else if (grp.mode == 2) {
+        empty_k = __ldg(grp.seg + 2 * ((tc.m_blk * kUmmaM) / grp.m_per_group) + 1) < kBlockK;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -298,12 +324,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         float v[64];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i >> 5][i & 31]);
+        for (int i = 0; i < 64; ++i) v[i] = empty_k ? 0.f : __uint_as_float(r[i >> 5][i & 31]);
         if (epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU || epilogue == EPI_BIAS_GELU_DUAL) {
 #pragma unroll
           for (int i = 0; i < 64; i += 8) {
             if (col0 + i < N) {   // N % 8 == 0 is required by the host wrapper
-              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(bias + col0 + i));
+              const uint4 bv = __ldg(reinterpret_cast<const uint4*>(tile_bias + col0 + i));
               const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&bv);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -527,10 +553,22 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   CUtensorMap ta, tb, td;
   const int dt = g.ab_format;  // 0 = fp16, 1 = bf16
   bool ok = true;
+  const GemmGroup& gg = g.group;
+  if (gg.mode == 1) {
+    if (gg.tile_group == nullptr || gg.groups < 1 || gg.row_align % (kBlockM * kCG) != 0 || g.comm.rows_per_rank > 0) return cudaErrorInvalidValue;
+    if (gg.b_group_stride != (kBK ? g.N : g.K) || g.K % kBlockK != 0) return cudaErrorInvalidValue;
+  } else if (gg.mode == 2) {
+    if (kAK || kBK || gg.seg == nullptr || gg.groups < 1 || gg.m_per_group % (kBlockM * kCG) != 0 || g.M != gg.groups * gg.m_per_group ||
+        g.comm.rows_per_rank > 0 || g.epilogue != EPI_NONE) return cudaErrorInvalidValue;
+  }
+  // grouped operands: B stacks the experts along its outer dimension (mode 1); A spans one expert's m_per_group columns (mode 2)
+  const uint64_t a_mn = gg.mode == 2 ? (uint64_t)gg.m_per_group : (uint64_t)g.M;
+  const uint64_t b_outer_k = gg.mode == 1 ? (uint64_t)gg.groups * g.N : (uint64_t)g.N;     // K-major B: rows
+  const uint64_t b_outer_mn = gg.mode == 1 ? (uint64_t)gg.groups * g.K : (uint64_t)g.K;   // MN-major B: k rows
   if (kAK) ok &= make_tmap_2d(&ta, g.a, 2, dt, g.K, g.M, (uint64_t)g.lda * 2, kBlockK, kBlockM);
-  else     ok &= make_tmap_2d(&ta, g.a, 2, dt, g.M, g.K, (uint64_t)g.lda * 2, 64, kBlockK);
-  if (kBK) ok &= make_tmap_2d(&tb, g.b, 2, dt, g.K, g.N, (uint64_t)g.ldb * 2, kBlockK, kLoadN);
-  else     ok &= make_tmap_2d(&tb, g.b, 2, dt, g.N, g.K, (uint64_t)g.ldb * 2, 64, kBlockK);
+  else     ok &= make_tmap_2d(&ta, g.a, 2, dt, a_mn, g.K, (uint64_t)g.lda * 2, 64, kBlockK);
+  if (kBK) ok &= make_tmap_2d(&tb, g.b, 2, dt, g.K, b_outer_k, (uint64_t)g.ldb * 2, kBlockK, kLoadN);
+  else     ok &= make_tmap_2d(&tb, g.b, 2, dt, g.N, b_outer_mn, (uint64_t)g.ldb * 2, 64, kBlockK);
   if (kOutMode == 0) ok &= make_tmap_2d(&td, g.d, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
   else td = ta;
   CUtensorMap td2 = td;
@@ -581,7 +619,7 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   cfg.attrs = attrs; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tal, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
                             g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm, pm, td2,
-                            reinterpret_cast<const __nv_bfloat16*>(g.aux), g.ld_aux);
+                            reinterpret_cast<const __nv_bfloat16*>(g.aux), g.ld_aux, g.group);
 }
 
 template <int kCG, int kBlockN, int kOutMode>
@@ -609,6 +647,9 @@ cudaError_t gemm_tcgen05(const GemmArgs& g, cudaStream_t stream) {
   if (cfg == 0) {
     const long tiles_big = (long)((g.M + 255) / 256) * ((g.N + 255) / 256);
     cfg = (tiles_big >= g.num_sms / 2) ? 2 : ((g.N > 128) ? 1 : 3);
+    // grouped tiles must not straddle two experts: the 2-CTA (256-row) tile needs 256-aligned expert blocks
+    if (g.group.mode == 1 && g.group.row_align % 256 != 0 && cfg == 2) cfg = 1;
+    if (g.group.mode == 2 && g.group.m_per_group % 256 != 0 && cfg == 2) cfg = 1;
   }
   switch (cfg) {
     case 1: return launch_out<1, 256>(g, stream);

@@ -241,6 +241,63 @@ __global__ void __launch_bounds__(256) moe_combine_kernel(CombineArgs a) {
   }
 }
 
+// Tile table of the grouped expert GEMMs, derived on the device from the dispatch kernel's segment table (start[e], count[e], total, overflow):
+//   tile_group[t]  expert that owns rows [128 t, 128 t + 128) of the expert-major receive buffer, -1 = no expert (tile skipped)
+//   seg2[2e..]     (row start, row count padded to the alignment) of expert e, clamped to the buffer: the K ranges of the grouped wgrad
+// A receive-buffer overflow is OR-ed into a sticky flag that the host polls asynchronously (one step late), never on the critical path.
+__global__ void __launch_bounds__(256) moe_tile_table_kernel(const int* __restrict__ seg, int e_local, int align, int cap_rows, int n_tiles,
+                                                             int* __restrict__ tile_group, int* __restrict__ seg2, int* __restrict__ sticky) {
+  __shared__ int s_start[kMoeMaxExperts], s_end[kMoeMaxExperts];
+  for (int e = threadIdx.x; e < e_local; e += blockDim.x) {
+    const int start = min(seg[e], cap_rows);
+    int padded = (seg[e_local + e] + align - 1) / align * align;
+    if (start + padded > cap_rows) padded = (cap_rows - start) / align * align;      // overflow: whole blocks that still fit
+    s_start[e] = start; s_end[e] = start + padded;
+    seg2[2 * e] = start; seg2[2 * e + 1] = padded;
+  }
+  if (threadIdx.x == 0 && seg[2 * e_local + 1] != 0) atomicOr(sticky, 1);
+  __syncthreads();
+  for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+    const int row = t * 128;
+    int g = -1;
+    for (int e = 0; e < e_local; ++e) if (row >= s_start[e] && row + 128 <= s_end[e]) g = e;
+    tile_group[t] = g;
+  }
+}
+
+// Per-expert column sums (bias gradients of the grouped expert linears): out[e, c] = sum over the rows of segment e of x[r, c].
+// grid (column chunks of 256, experts); 32 column vectors x 8 row lanes per CTA, fp32 accumulation, one store per column.
+template <typename T>
+__global__ void __launch_bounds__(256) grouped_colsum_kernel(const T* __restrict__ x, const int* __restrict__ seg2, int N, T* __restrict__ out) {
+  const int e = blockIdx.y;
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cv) * 8;
+  const int r0 = seg2[2 * e], r1 = r0 + seg2[2 * e + 1];
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < N) {
+    for (int r = r0 + rl; r < r1; r += 8) {
+      float v[8];
+      unpack8<T>(ld_stream(reinterpret_cast<const uint4*>(x + (size_t)r * N + c)), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+  __shared__ float part[8][32][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[rl][cv][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && c < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += part[q][cv][j];
+      acc[j] = t;
+    }
+    *reinterpret_cast<uint4*>(out + (size_t)e * N + c) = pack8<T>(acc);
+  }
+}
+
 }  // namespace
 
 cudaError_t moe_route(const int64_t* gate_idx, int num_slots, int total_experts, int* slot_rank, int* counts, cudaStream_t st) {
@@ -286,6 +343,21 @@ cudaError_t moe_combine(void** peer_src, const int* slot_loc, const float* weigh
   a.epoch = epoch;
   if (dtype == 1) moe_combine_kernel<__nv_bfloat16><<<num_ctas, 256, 0, st>>>(a);
   else if (dtype == 0) moe_combine_kernel<__half><<<num_ctas, 256, 0, st>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t moe_tile_table(const int* seg, int e_local, int align, int cap_rows, int* tile_group, int* seg2, int* sticky, cudaStream_t st) {
+  if (e_local > kMoeMaxExperts || align % 128 || cap_rows % 128) return cudaErrorInvalidValue;
+  moe_tile_table_kernel<<<1, 256, 0, st>>>(seg, e_local, align, cap_rows, cap_rows / 128, tile_group, seg2, sticky);
+  return cudaGetLastError();
+}
+
+cudaError_t grouped_colsum(const void* x, const int* seg2, int groups, int N, void* out, int dtype, cudaStream_t st) {
+  if (N % 8 || groups < 1) return cudaErrorInvalidValue;
+  const dim3 grid((unsigned)((N / 8 + 31) / 32), (unsigned)groups);
+  if (dtype == 1) grouped_colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, seg2, N, (__nv_bfloat16*)out);
+  else if (dtype == 0) grouped_colsum_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, seg2, N, (__half*)out);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -25,6 +25,23 @@ struct GemmComm {
   uint32_t epoch;             // AG mode: value that marks "chunk present" for this call
 };
 
+// Grouped (mixture-of-experts) modes: ONE launch covers every expert, and what each tile works on comes from a table in DEVICE memory that the
+// dispatch kernel wrote — the host never learns the per-expert token counts.
+//   mode 1  rows grouped: A / D are the expert-major token buffer [cap_rows, *] whose 128-row blocks each belong to one expert (or to none:
+//           -1, tile skipped); B (and bias) are the experts' weights stacked along their outer dimension, the tile's block picks the slice.
+//           Serves forward (B K-major: [G*N, K]) and dgrad (B MN-major: [G*K, N]).
+//   mode 2  K grouped: D[g] = A_g^T B_g over the token rows of expert g (wgrad).  A [rows, m_per_group] and B [rows, N] are both MN-major,
+//           D is the stacked weight gradient [G*m_per_group, N]; seg = (row start, padded row count) per expert.
+struct GemmGroup {
+  const int* tile_group = nullptr;   // mode 1: [ceil(M / 128)] expert of each 128-row block, -1 = unused
+  const int* seg = nullptr;          // mode 2: [2 * groups]
+  int mode = 0;
+  int groups = 0;
+  int b_group_stride = 0;            // mode 1: rows of stacked B per expert (N if B is K-major, K if MN-major)
+  int m_per_group = 0;               // mode 2: rows of D per expert
+  int row_align = 128;               // mode 1: alignment of the expert blocks (256 allows the 2-CTA tile)
+};
+
 struct GemmArgs {
   const void* a;     // K-major: [M, K] row-major (lda = row stride, elements); MN-major: [K, M]
   const void* b;     // K-major: [N, K] row-major;                              MN-major: [K, N]
@@ -42,6 +59,7 @@ struct GemmArgs {
   int num_sms;
   int config;        // 0 = auto
   GemmComm comm;     // zero-initialised = plain GEMM
+  GemmGroup group;   // mode 0 = plain GEMM
 };
 
 cudaError_t gemm_tcgen05(const GemmArgs& args, cudaStream_t stream);

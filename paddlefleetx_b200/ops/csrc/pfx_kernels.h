@@ -88,6 +88,8 @@ cudaError_t moe_dispatch(const void* src, const float* scale, const int64_t* gat
                          int* seg, void** peer_recv, void** peer_cnt, void** peer_flags, unsigned* block_counter, int num_slots, int src_div,
                          int H, int e_local, int world, int rank, int align, int cap_rows, uint32_t epoch, int dtype, int num_ctas,
                          cudaStream_t st);
+cudaError_t moe_tile_table(const int* seg, int e_local, int align, int cap_rows, int* tile_group, int* seg2, int* sticky, cudaStream_t st);
+cudaError_t grouped_colsum(const void* x, const int* seg2, int groups, int N, void* out, int dtype, cudaStream_t st);
 cudaError_t moe_combine(void** peer_src, const int* slot_loc, const float* weights, void* out, void* rows, void** peer_flags, int T, int topk,
                         int H, int world, int rank, uint32_t epoch, int dtype, int num_ctas, cudaStream_t st);
 

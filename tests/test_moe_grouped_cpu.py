@@ -1,0 +1,54 @@
+"""Stacked expert parameters (``GroupedExperts``): the grouped-GEMM MoE path keeps per-expert checkpoint names and the loop fallback
+computes the same function as a layer with ordinary per-expert parameters (reference layout: moe/moe_layer.py:158-235)."""
+import torch
+
+from paddlefleetx_b200.models.language_model.moe.grouped_experts import GroupedExperts, reference_grouped_ffn
+from paddlefleetx_b200.models.language_model.moe.moe_layer import ExpertLayer, MoELayer
+
+
+def _layer(fused, seed=3):
+    torch.manual_seed(seed)
+    ex = [ExpertLayer(128, 256) for _ in range(3)]
+    return MoELayer(128, ex, gate={"type": "naive", "top_k": 2}, fused_p2p=fused)
+
+
+def test_state_dict_names_and_roundtrip():
+    plain, grouped = _layer(False), _layer(True, seed=4)
+    assert grouped.grouped is not None and plain.grouped is None
+    assert sorted(plain.state_dict().keys()) == sorted(grouped.state_dict().keys())
+    grouped.load_state_dict(plain.state_dict())
+    for k, v in plain.state_dict().items():
+        assert torch.equal(v, grouped.state_dict()[k]), k
+    # and back: a grouped checkpoint loads into per-expert parameters
+    plain2 = _layer(False, seed=5)
+    plain2.load_state_dict(grouped.state_dict())
+    assert torch.equal(plain2.experts[2].h4toh.weight, grouped.grouped.w2[2])
+    names = [n for n, _ in grouped.named_parameters()]
+    assert sum(n.startswith("grouped.") for n in names) == 4 and not any(n.startswith("experts.") for n in names)
+    assert all(getattr(p, "is_expert", False) for n, p in grouped.named_parameters() if n.startswith("grouped."))
+
+
+def test_loop_path_matches_and_grads_land_in_stacks():
+    plain, grouped = _layer(False), _layer(True, seed=4)
+    grouped.load_state_dict(plain.state_dict())
+    x = torch.randn(40, 128)
+    y0 = plain(x)
+    y1 = grouped(x)
+    assert torch.allclose(y0, y1, atol=1e-6)
+    y0.square().sum().backward(); y1.square().sum().backward()
+    for e in range(3):
+        assert torch.allclose(plain.experts[e].htoh4.weight.grad, grouped.grouped.w1.grad[e], atol=1e-5)
+        assert torch.allclose(plain.experts[e].h4toh.bias.grad, grouped.grouped.b2.grad[e], atol=1e-5)
+
+
+def test_views_follow_repointed_storage():
+    """Flat-buffer optimizers re-point ``param.data``; the expert modules must see the new storage after ``bind_views``."""
+    layer = _layer(True)
+    ge: GroupedExperts = layer.grouped
+    new = torch.zeros_like(ge.w1.data)
+    ge.w1.data = new
+    layer(torch.randn(8, 128))          # the loop path re-binds before use
+    assert layer.experts[0].htoh4.weight.data_ptr() == new[0].data_ptr()
+    seg2 = [0, 3, 3, 0, 3, 5]
+    out = reference_grouped_ffn(torch.randn(8, 128), seg2, ge)
+    assert out.shape == (8, 128) and torch.isfinite(out).all()

@@ -249,31 +249,58 @@ def main():
     hc3 = HybridCommunicateGroup(dp=world)
     mg = hc3.get_moe_group()
     hm, e_local, tok = 1024, 2, 8192
-    torch.manual_seed(7 + rank)
-    def make_moe(fused):
+    def make_moe(fused, grouped=True):
         torch.manual_seed(7 + rank)
         ex = [ExpertLayer(hm, 4 * hm, dtype=torch.bfloat16, device="cuda") for _ in range(e_local)]
-        return MoELayer(hm, ex, gate={"type": "naive", "top_k": 2}, moe_group=mg, dtype=torch.bfloat16, device="cuda", fused_p2p=fused)
-    l_ref, l_p2p = make_moe(False), make_moe(True)
-    l_p2p.load_state_dict(l_ref.state_dict())
-    torch.manual_seed(99 + rank)
-    xin = (torch.randn(tok, hm, device="cuda") * 0.5).bfloat16()
-    gout = (torch.randn(tok, hm, device="cuda") * 0.1).bfloat16()
-    outs = []
-    for layer in (l_ref, l_p2p):
-        xi = xin.clone().requires_grad_(True)
-        y = layer(xi)
-        y.backward(gout)
-        outs.append([y.detach(), xi.grad.detach()] + [p.grad.detach().float() for p in layer.parameters()])
-    errs = [relerr(a, b_) for a, b_ in zip(outs[1], outs[0])]
-    def moe_step(layer):
-        def f():
+        return MoELayer(hm, ex, gate={"type": "naive", "top_k": 2}, moe_group=mg, dtype=torch.bfloat16, device="cuda", fused_p2p=fused,
+                        grouped_gemm=grouped)
+
+    def named_grads(layer):      # per-expert names whether the experts' parameters are stacked (grouped path) or not
+        names = {"w1": ("htoh4", "weight"), "b1": ("htoh4", "bias"), "w2": ("h4toh", "weight"), "b2": ("h4toh", "bias")}
+        out = {}
+        for n, p_ in layer.named_parameters():
+            if p_.grad is None:
+                continue
+            if n.startswith("grouped."):
+                lin, attr = names[n.split(".")[1]]
+                for e in range(p_.shape[0]):
+                    out[f"experts.{e}.{lin}.{attr}"] = p_.grad[e].detach().float()
+            else:
+                out[n] = p_.grad.detach().float()
+        return out
+
+    try:
+        l_ref, l_loop, l_grp = make_moe(False), make_moe(True, grouped=False), make_moe(True)
+        sd = l_ref.state_dict()
+        l_loop.load_state_dict(sd); l_grp.load_state_dict(sd)
+        same_names = sorted(l_grp.state_dict().keys()) == sorted(sd.keys())
+        torch.manual_seed(99 + rank)
+        xin = (torch.randn(tok, hm, device="cuda") * 0.5).bfloat16()
+        gout = (torch.randn(tok, hm, device="cuda") * 0.1).bfloat16()
+        outs = []
+        for layer in (l_ref, l_loop, l_grp):
             xi = xin.clone().requires_grad_(True)
-            layer(xi).backward(gout)
-        return f
-    t_ref, t_p2p = timed(moe_step(l_ref), iters=5), timed(moe_step(l_p2p), iters=5)
-    report("moe_p2p_dispatch_combine", errs=[round(e, 5) for e in errs], ok=max(errs) < 3e-2, ms_nccl=t_ref, ms_p2p=t_p2p,
-           shape=dict(tokens=tok, hidden=hm, experts_per_rank=e_local, topk=2))
+            y = layer(xi)
+            y.backward(gout)
+            g = named_grads(layer)
+            outs.append({"y": y.detach(), "dx": xi.grad.detach(), **g})
+        keys = sorted(outs[0].keys())
+        errs_loop = {k: round(relerr(outs[1][k], outs[0][k]), 5) for k in keys}
+        errs_grp = {k: round(relerr(outs[2][k], outs[0][k]), 5) for k in keys}
+
+        def moe_step(layer):
+            def f():
+                xi = xin.clone().requires_grad_(True)
+                layer(xi).backward(gout)
+            return f
+        t_ref, t_loop, t_grp = timed(moe_step(l_ref), iters=5), timed(moe_step(l_loop), iters=5), timed(moe_step(l_grp), iters=5)
+        report("moe_p2p_dispatch_combine", errs=list(errs_loop.values()), ok=max(errs_loop.values()) < 3e-2, ms_nccl=t_ref, ms_p2p=t_loop,
+               shape=dict(tokens=tok, hidden=hm, experts_per_rank=e_local, topk=2))
+        report("moe_grouped_sync_free", errs=errs_grp, ok=max(errs_grp.values()) < 3e-2 and same_names, checkpoint_names_unchanged=same_names,
+               ms_nccl_loop=t_ref, ms_p2p_loop=t_loop, ms_p2p_grouped=t_grp, host_syncs_in_layer=0)
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        report("moe_grouped_sync_free", ok=False, error=repr(e), tb=traceback.format_exc()[-1500:])
 
     dist.barrier()
     finish(res, rank, world)

@@ -747,7 +747,94 @@ def check_gemm_big_sweep():
     return dict(ok=ok, worst=worst, cases=rows)
 
 
+def check_moe_grouped(perf=False):
+    """Grouped expert GEMMs against an fp32 per-expert loop: synthetic segment tables (an expert without tokens, unused blocks at the end, 128-
+    and 256-row alignment = 1-CTA and 2-CTA tiles), the tile-table kernel, forward + backward of the whole grouped FFN."""
+    import torch
+    import torch.nn.functional as F
+    from paddlefleetx_b200.models.language_model.moe.grouped_experts import GroupedExperts, grouped_ffn
+    from paddlefleetx_b200.models.language_model.moe.moe_layer import ExpertLayer
+    from paddlefleetx_b200.ops import _native
+    lib = _native.require()
+    res, ok = {}, True
+    cases = [(4, 256, 512, [300, 0, 129, 700], 256, 4096), (3, 128, 384, [5, 640, 130], 128, 1536), (8, 1024, 4096, [1500, 2100, 1800, 0, 2500, 1900, 2222, 1777], 256, 20480)]
+    if perf:
+        cases = cases[-1:]
+    for (E, hm, ffn, counts, align, cap) in cases:
+        torch.manual_seed(E)
+        ex = [ExpertLayer(hm, ffn, init_std=0.05, dtype=torch.bfloat16, device="cuda") for _ in range(E)]
+        holder = torch.nn.ModuleList(ex)
+        ge = GroupedExperts(ex)
+        with torch.no_grad():
+            ge.b1.normal_(0, 0.1); ge.b2.normal_(0, 0.1)
+        starts, pos = [], 0
+        for c in counts:
+            starts.append(pos)
+            pos += (c + align - 1) // align * align
+        seg = torch.tensor(starts + counts + [pos, 0], dtype=torch.int32, device="cuda")
+        sticky = torch.zeros(1, dtype=torch.int32, device="cuda")
+        tile_group, seg2 = lib.moe_tile_table(seg, E, align, cap, sticky)
+        tg = tile_group.tolist()
+        want = [-1] * (cap // 128)
+        for e, (s0, c) in enumerate(zip(starts, counts)):
+            for t in range(s0 // 128, (s0 + (c + align - 1) // align * align) // 128):
+                want[t] = e
+        table_ok = tg == want and int(sticky) == 0
+        xs = torch.full((cap, hm), float("nan"), device="cuda", dtype=torch.bfloat16)     # unused rows are poisoned: nothing may read them
+        go = torch.full((cap, hm), float("nan"), device="cuda", dtype=torch.bfloat16)
+        for s0, c in zip(starts, counts):
+            pad = (c + align - 1) // align * align
+            xs[s0:s0 + pad] = 0; go[s0:s0 + pad] = 0
+            xs[s0:s0 + c] = (torch.randn(c, hm, device="cuda") * 0.5).bfloat16()
+            go[s0:s0 + c] = (torch.randn(c, hm, device="cuda") * 0.1).bfloat16()
+        xs.requires_grad_(True)
+        ys = grouped_ffn(xs, tile_group, seg2, ge, None, align)
+        ys.backward(go)
+        # fp32 reference over the real rows
+        errs = {}
+        w1, b1, w2, b2 = (t.detach().float() for t in (ge.w1, ge.b1, ge.w2, ge.b2))
+        for e, (s0, c) in enumerate(zip(starts, counts)):
+            dw1 = torch.zeros_like(w1[e]); dw2 = torch.zeros_like(w2[e]); db1 = torch.zeros_like(b1[e]); db2 = torch.zeros_like(b2[e])
+            if c:
+                xe = xs.detach()[s0:s0 + c].float().requires_grad_(True)
+                pw = [t.clone().requires_grad_(True) for t in (w1[e], b1[e], w2[e], b2[e])]
+                ye = F.linear(F.gelu(F.linear(xe, pw[0], pw[1]), approximate="tanh"), pw[2], pw[3])
+                ye.backward(go[s0:s0 + c].float())
+                errs[f"y{e}"] = _relerr(ys.detach()[s0:s0 + c], ye.detach())
+                errs[f"dx{e}"] = _relerr(xs.grad[s0:s0 + c], xe.grad)
+                dw1, db1, dw2, db2 = (t.grad for t in pw)
+                for nm, got, ref in (("dw1", ge.w1.grad[e], dw1), ("db1", ge.b1.grad[e], db1), ("dw2", ge.w2.grad[e], dw2), ("db2", ge.b2.grad[e], db2)):
+                    errs[f"{nm}_{e}"] = _relerr(got, ref)
+            else:   # an expert without tokens: exact zero gradients, written (not left uninitialised)
+                errs[f"empty{e}"] = float(max(ge.w1.grad[e].float().abs().max(), ge.w2.grad[e].float().abs().max(), ge.b1.grad[e].float().abs().max()))
+        worst = max(errs.values())
+        finite = bool(torch.isfinite(ge.w1.grad.float()).all() and torch.isfinite(ge.w2.grad.float()).all())
+        case_ok = table_ok and worst < 2e-2 and finite
+        ok = ok and case_ok
+        r = dict(ok=case_ok, tile_table_ok=table_ok, worst=round(worst, 5), finite=finite)
+        if perf:
+            def step():
+                xs.grad = None
+                grouped_ffn(xs, tile_group, seg2, ge, None, align).backward(go)
+            ms, _ = _time(step)
+            rows = sum(counts)
+            r["fwd_bwd_ms"] = round(ms, 4)
+            r["tflops"] = round(3 * 2 * 2 * rows * hm * ffn / ms / 1e9, 1)
+            def loop():
+                for e, (s0, c) in enumerate(zip(starts, counts)):
+                    if c:
+                        xe = xs.detach()[s0:s0 + c].requires_grad_(True)
+                        ge.bind_views()
+                        ex[e](xe).backward(go[s0:s0 + c])
+            ms_loop, _ = _time(loop)
+            r["per_expert_loop_ms"] = round(ms_loop, 4)
+        res[f"E{E}_h{hm}_ffn{ffn}_align{align}"] = r
+    return dict(ok=ok, cases=res)
+
+
 CHECKS = {
+    "moe_grouped": check_moe_grouped,
+    "moe_grouped_perf": lambda: check_moe_grouped(perf=True),
     "attention_train": check_attention_train,
     "attention_train_perf": lambda: check_attention_train(perf=True),
     "attention_autograd": check_attention_autograd,
