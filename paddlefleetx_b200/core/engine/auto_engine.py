@@ -1,14 +1,18 @@
 """``AutoEngine`` (reference core/engine/auto_engine.py:39-209 wraps Paddle's static-graph semi-auto-parallel engine and its
 ``OptimizationTuner``).
 
-There is no tracing planner here: an "auto" config describes a process mesh (pp, dp, mp) that maps one-to-one onto the hybrid topology, so
-``AutoEngine`` is the eager engine with the mesh validated — ``tools/auto.py`` / ``tools/auto_export.py`` keep working with the same YAML
-files.  ``tune`` covers the two things the reference's ``Tuning`` section drives:
+An "auto" config describes a process mesh (pp, dp, mp) that maps one-to-one onto the hybrid topology, so ``AutoEngine`` is the eager engine
+with the mesh validated — ``tools/auto.py`` / ``tools/auto_export.py`` keep working with the same YAML files.  What the reference's planner
+decides by propagating ``shard_tensor`` annotations is decided here by a cost model over the concrete parallel implementations:
+``Distributed.auto_layout: True`` makes ``utils.config.get_auto_config`` ask ``utils/layout_planner.py`` for the fastest layout that fits
+180 GB per GPU (degrees, ZeRO stage, micro-batch, recompute) and derive the config from it; the chosen plan is recorded under
+``Distributed.plan``.  ``tune`` covers the two things the reference's ``Tuning`` section drives:
 
 * ``Tuning.tuning_recompute`` — a *measured* search: every recompute setting (off / ``core_attn`` / ``full_attn`` / ``full``) is built on the
   configured mesh, steps ``[profile_start_step, profile_end_step]`` are timed (device-synchronised, max over ranks) with the peak allocator
   footprint recorded, and the fastest candidate under the memory limit is written back into the config;
-* otherwise — the analytic ranking of (dp, mp, pp, sharding) factorisations of the world (``utils/layout_planner.py``).
+* otherwise — the planner's ranked table of every feasible (dp, sharding + stage, mp, pp) layout with its predicted step time, memory and
+  time breakdown (compute / TP collectives / pipeline bubble / exposed DP traffic / exposed optimizer).
 """
 from __future__ import annotations
 

@@ -27,6 +27,7 @@
 #include "pfx_ptx.cuh"
 #include "pfx_gemm.h"
 #include <cudaTypedefs.h>
+#include <cstdio>
 
 namespace pfx {
 
@@ -546,6 +547,15 @@ bool make_tmap_bshd(CUtensorMap* map, const void* ptr, int dtype_code, uint64_t 
   });
 }
 
+// An argument combination the kernel family cannot run is a programming error upstream: say which check refused it (the bare
+// "invalid argument" of the CUDA error string does not).
+static cudaError_t gemm_reject(const GemmArgs& g, int cg, int block_n, int line) {
+  fprintf(stderr, "pfx gemm: rejected at gemm_sm100.cu:%d  (M %d N %d K %d lda %d ldb %d ldd %d a_k %d b_k %d out_mode %d epilogue %d cfg %dx%d group mode %d "
+                  "groups %d b_stride %d m_per_group %d row_align %d comm rows %d)\n", line, g.M, g.N, g.K, g.lda, g.ldb, g.ldd, (int)g.a_kmajor, (int)g.b_kmajor,
+          g.out_mode, g.epilogue, cg, block_n, g.group.mode, g.group.groups, g.group.b_group_stride, g.group.m_per_group, g.group.row_align, g.comm.rows_per_rank);
+  return cudaErrorInvalidValue;
+}
+
 template <int kCG, int kBlockN, bool kAK, bool kBK, int kOutMode>
 static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   using S = GemmSmem<kCG, kBlockN>;
@@ -555,11 +565,11 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   bool ok = true;
   const GemmGroup& gg = g.group;
   if (gg.mode == 1) {
-    if (gg.tile_group == nullptr || gg.groups < 1 || gg.row_align % (kBlockM * kCG) != 0 || g.comm.rows_per_rank > 0) return cudaErrorInvalidValue;
-    if (gg.b_group_stride != (kBK ? g.N : g.K) || g.K % kBlockK != 0) return cudaErrorInvalidValue;
+    if (gg.tile_group == nullptr || gg.groups < 1 || gg.row_align % (kBlockM * kCG) != 0 || g.comm.rows_per_rank > 0) return gemm_reject(g, kCG, kBlockN, __LINE__);
+    if (gg.b_group_stride != (kBK ? g.N : g.K) || g.K % kBlockK != 0) return gemm_reject(g, kCG, kBlockN, __LINE__);
   } else if (gg.mode == 2) {
     if (kAK || kBK || gg.seg == nullptr || gg.groups < 1 || gg.m_per_group % (kBlockM * kCG) != 0 || g.M != gg.groups * gg.m_per_group ||
-        g.comm.rows_per_rank > 0 || g.epilogue != EPI_NONE) return cudaErrorInvalidValue;
+        g.comm.rows_per_rank > 0 || g.epilogue != EPI_NONE) return gemm_reject(g, kCG, kBlockN, __LINE__);
   }
   // grouped operands: B stacks the experts along its outer dimension (mode 1); A spans one expert's m_per_group columns (mode 2)
   const uint64_t a_mn = gg.mode == 2 ? (uint64_t)gg.m_per_group : (uint64_t)g.M;
@@ -573,10 +583,10 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   else td = ta;
   CUtensorMap td2 = td;
   if (g.epilogue == EPI_BIAS_GELU_DUAL) {
-    if (kOutMode != 0 || g.d2 == nullptr || g.bias == nullptr) return cudaErrorInvalidValue;
+    if (kOutMode != 0 || g.d2 == nullptr || g.bias == nullptr) return gemm_reject(g, kCG, kBlockN, __LINE__);
     ok &= make_tmap_2d(&td2, g.d2, 2, dt, g.N, g.M, (uint64_t)g.ldd * 2, kStoreCols, kBlockM);
   }
-  if (g.epilogue == EPI_DGELU && (g.aux == nullptr || g.ld_aux % 8 || (reinterpret_cast<uintptr_t>(g.aux) & 15) || dt != 1)) return cudaErrorInvalidValue;
+  if (g.epilogue == EPI_DGELU && (g.aux == nullptr || g.ld_aux % 8 || (reinterpret_cast<uintptr_t>(g.aux) & 15) || dt != 1)) return gemm_reject(g, kCG, kBlockN, __LINE__);
   PeerMaps pm;
   for (int i = 0; i < 8; ++i) pm.m[i] = ta;
   if (kOutMode == 3) {
@@ -586,11 +596,11 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   }
   CUtensorMap tal = ta;
   if (g.comm.ag_world > 1) {
-    if (!kAK) return cudaErrorInvalidValue;
+    if (!kAK) return gemm_reject(g, kCG, kBlockN, __LINE__);
     ok &= make_tmap_2d(&tal, g.comm.a_local, 2, dt, g.K, g.comm.rows_per_rank, (uint64_t)g.K * 2, kBlockK, kBlockM);
   }
-  if (!ok) return cudaErrorInvalidValue;
-  if (g.comm.rows_per_rank > 0 && (g.comm.rows_per_rank % (kBlockM * kCG)) != 0) return cudaErrorInvalidValue;
+  if (!ok) return gemm_reject(g, kCG, kBlockN, __LINE__);
+  if (g.comm.rows_per_rank > 0 && (g.comm.rows_per_rank % (kBlockM * kCG)) != 0) return gemm_reject(g, kCG, kBlockN, __LINE__);
 
   auto kern = gemm_tcgen05_kernel<kCG, kBlockN, kAK, kBK, kOutMode>;
   static bool attr_set = false;
@@ -617,9 +627,14 @@ static cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t stream) {
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kCG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tal, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, tal, reinterpret_cast<float*>(g.d), reinterpret_cast<const __nv_bfloat16*>(g.bias),
                             g.M, g.N, g.K, g.ldd, g.epilogue, (uint32_t)g.ab_format, g.comm, pm, td2,
                             reinterpret_cast<const __nv_bfloat16*>(g.aux), g.ld_aux, g.group);
+  if (le != cudaSuccess) {
+    fprintf(stderr, "pfx gemm: launch failed (%s): grid %d x cluster %d, smem %d B\n", cudaGetErrorString(le), clusters * kCG, kCG, S::kTotal);
+    return gemm_reject(g, kCG, kBlockN, __LINE__);
+  }
+  return le;
 }
 
 template <int kCG, int kBlockN, int kOutMode>

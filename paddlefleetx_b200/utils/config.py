@@ -328,7 +328,29 @@ def get_auto_config(fname: str, overrides: Optional[Iterable[str]] = None, show:
     """Auto-parallel configs (reference: config.py:418-634) share the eager pipeline here: the
     ``ProcessMesh`` the reference hands to its static-graph planner is just our hybrid topology,
     so the mesh is recorded under ``Distributed.mesh`` and the eager engine executes it."""
-    cfg = get_config(fname, overrides, show=False, nranks=nranks)
+    raw = parse_config(fname)
+    override_config(raw, overrides)
+    raw = _wrap(raw)
+    if (raw.get("Distributed") or {}).get("auto_layout", False):
+        # ``Distributed.auto_layout: True``: the planner (utils/layout_planner.py) picks degrees, ZeRO stage, micro-batch and recompute for this
+        # world size and the config is derived with them; the global batch stays what the YAML's per-GPU batch implies
+        from .layout_planner import ModelShape, plan_layouts
+
+        world = nranks or world_size_hint()
+        d0, g0 = raw.Distributed, raw.Global
+        lb0 = int(g0.get("local_batch_size") or g0.get("micro_batch_size") or 1)
+        per_gpu = max(lb0 // (int(d0.get("mp_degree", 1) or 1) * int(d0.get("pp_degree", 1) or 1)), 1)
+        plans = plan_layouts(ModelShape.from_config(raw), world, per_gpu, top=1)
+        if not plans:
+            raise ValueError(f"auto_layout: no layout of this model fits {world} x 180 GB; add GPUs or reduce the batch / sequence length")
+        best = plans[0]
+        extra = best.overrides() + [f"Global.local_batch_size={per_gpu * best.mp * best.pp}", "Global.global_batch_size=None",
+                                    "Distributed.auto_layout=False"]
+        cfg = get_config(fname, list(overrides or []) + extra, show=False, nranks=nranks)
+        cfg.Distributed["plan"] = AttrDict(describe=best.describe(), est_step_ms=best.est_step_s * 1e3, est_mem_gb=best.est_mem_gb,
+                                          breakdown_ms={k: v * 1e3 for k, v in best.breakdown.items()})
+    else:
+        cfg = get_config(fname, overrides, show=False, nranks=nranks)
     d = cfg.Distributed
     cfg.Distributed["mesh"] = AttrDict(
         dim_names=["pp", "dp", "mp"], shape=[d.pp_degree, d.dp_degree * d.sharding.sharding_degree, d.mp_degree])

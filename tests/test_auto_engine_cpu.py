@@ -75,3 +75,13 @@ def test_auto_export_writes_an_inference_bundle(tmp_path):
     assert type(engine).__name__ == "AutoEngine"
     files = [f for _, _, fs in os.walk(tmp_path) for f in fs]
     assert {"model.pdmodel", "model.pdiparams"} <= set(files), files
+
+
+def test_auto_layout_plans_then_trains(tmp_path, capsys):
+    """``Distributed.auto_layout=True``: the planner derives the layout (trivial on one process), records it, and the run trains with it."""
+    import auto
+
+    engine = auto.main(_argv(tmp_path, ["Distributed.auto_layout=True", "Engine.max_steps=2"]))
+    d = engine._configs.Distributed
+    assert d.plan is not None and d.plan.est_mem_gb > 0 and "[auto_layout]" in capsys.readouterr().out
+    assert (d.dp_degree, d.mp_degree, d.pp_degree, d.sharding.sharding_degree) == (1, 1, 1, 1) and d.auto_layout is False

@@ -20,11 +20,13 @@ def main(argv=None):
     env.set_seed(cfg.Global.seed)
     module = build_module(cfg)
     config.print_config(cfg)
+    if cfg.Distributed.get("plan") is not None:
+        print(f"[auto_layout] {cfg.Distributed.plan.describe}")
     engine = AutoEngine(configs=cfg, module=module)
     train_loader = build_dataloader(cfg.Data, "Train")
     if cfg.get("Tuning", {}).get("enable", False):
         for row in engine.tune(train_loader)[:8]:
-            print(row)
+            print(row.get("describe", row) if isinstance(row, dict) else row)
         return engine
     eval_loader = build_dataloader(cfg.Data, "Eval") if cfg.Engine.eval_freq and cfg.Engine.eval_freq > 0 and "Eval" in cfg.Data else None
     if cfg.Engine.save_load.ckpt_dir is not None:

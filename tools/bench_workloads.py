@@ -4,8 +4,10 @@
     vit    ViT-L/16 384^2 fine-tune, ZeRO stage 2 over all ranks, 32 images / GPU                            (images/s)
     ernie  ERNIE 10B-class encoder, mp x ZeRO stage 3                                                        (tokens/s)
 
-Synthetic data of the named shape, random-init weights, bf16.  Same timing contract as bench.py: W warm-up steps, K steps timed
-with CUDA events between barriers, max over ranks, one JSON line on rank 0.
+Synthetic data of the named shape, random-init weights, bf16.  Same contract as bench.py: W warm-up steps, K steps timed with CUDA
+events between barriers, max over ranks, nvidia-smi clocks / throttle reasons sampled during the timed region, the exposed-
+communication meter, the per-step host->device / device->host bytes (every step copies its batch from pinned memory and the harness reads
+the loss back), one JSON line on rank 0.
 
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_workloads.py --workload moe --gpus 8 [--p2p 1]
 """
@@ -122,24 +124,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from bench import ClockSampler          # the headline bench's nvidia-smi sampler (repo root)
+
     for i in range(a.warmup):
         engine.train_step(pool[i % len(pool)])
     barrier()
     OF.reset_launch_count()
+    opt = getattr(engine, "_optimizer", None)
+    if hasattr(opt, "comm_meter_start"):
+        opt.comm_meter_start()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    loss_host = 0.0
     for i in range(a.steps):
         loss = engine.train_step(pool[i % len(pool)])
+        loss_host = float(loss)             # device -> host read of the step's result, inside the timed region
     e1.record()
     barrier()
+    clocks = sampler.stop() if sampler else None
+    exposed = opt.comm_meter_read() / a.steps if hasattr(opt, "comm_meter_read") else None
+    h2d = sum(t.numel() * t.element_size() for t in pool[0])
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t)
     if rank == 0:
         out = {"metric": name, "value": per_step * a.steps / (ms / 1e3), "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-               "ms_per_step": ms / a.steps, "dtype": "bf16", "data": "synthetic, random-init weights, pinned H2D copy inside the timed region",
-               "final_loss": float(loss), "gpu_launches": OF.native_launch_count(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+               "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+               "data": "synthetic, random-init weights; the timed region includes the pinned host->device copy of every batch and the loss read-back",
+               "e2e": {"value": per_step * a.steps / (ms / 1e3), "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "note": "value IS end to end: engine.train_step(pinned host batch) -> float(loss) every step"},
+               "clocks": clocks, "exposed_comm_ms_per_step": exposed,
+               "final_loss": loss_host, "gpu_launches": OF.native_launch_count(), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
                "valid": not a.layers}
         print(json.dumps(out), flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
