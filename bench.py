@@ -91,7 +91,9 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.strip().lower() == "active":
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        pw = sorted(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit())
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": pw[len(pw) // 2] if pw else None}
 
 
 def reference_arm(args):
@@ -305,11 +307,16 @@ def main():
     if hasattr(opt, "comm_meter_start"):
         opt.comm_meter_start()
     e0.record()
+    marks = []
     for i in range(args.steps):
         loss = device_step(i)
+        ev = torch.cuda.Event(enable_timing=True)      # per-step marks: the spread inside the run (power-capped parts wander by several %)
+        ev.record()
+        marks.append(ev)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
     launches = OF.native_launch_count()
     exposed = opt.comm_meter_read() / args.steps if hasattr(opt, "comm_meter_read") else None
     if exposed is not None and world > 1:
@@ -340,6 +347,11 @@ def main():
         e2e = {"value": global_batch * seq * args.steps / (float(t2.item()) / 1e3), "unit": "tokens/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
     clocks = sampler.stop() if sampler else None
+    step_spread = {"median_ms": per_step[len(per_step) // 2], "min_ms": per_step[0], "max_ms": per_step[-1]} if per_step else None
+    energy = None
+    if clocks and clocks.get("power_w"):
+        # energy-normalised throughput (rank 0's GPU): what a power-capped part can be compared on from box to box
+        energy = {"power_w_median": clocks["power_w"], "tokens_per_joule_per_gpu": (global_batch * seq / world) / (ms_total / args.steps / 1e3) / clocks["power_w"]}
     if args.profile > 0:
         _profile_steps(args, device_step, barrier, rank, world)
 
@@ -379,7 +391,7 @@ def main():
                        "micro_batch": lay["micro"], "recompute": lay["recompute"], "dropout": cfg.Model.hidden_dropout_prob,
                        "optimizer": "FusedAdamW fp32 master + clip" + (" (update overlapped with the next forward)" if opt_overlapped else ""), "l2": "working set (>100 GB/step) >> 126 MB L2, no explicit flush"},
             "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "final_loss": final_loss,
-            "collective": collective, "exposed_comm_ms_per_step": exposed, "named_layout": named,
+            "collective": collective, "exposed_comm_ms_per_step": exposed, "step_spread": step_spread, "energy": energy, "named_layout": named,
             "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
         }
         print(json.dumps(out))

@@ -13,7 +13,7 @@ from ..distributed.apis import env
 from ..utils.log import logger
 from . import dataset as _datasets
 from .sampler import batch_sampler as _samplers
-from .sampler import collate as _collate
+from .utils import batch_collate_fn as _collate      # task collate functions + the Stack / Pad / Tuple / Dict primitives
 
 
 def _lookup(mod, name):

@@ -507,8 +507,12 @@ bool make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, int dtype_c
     cuuint64_t strides[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    return fn(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const CUresult r = fn(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      fprintf(stderr, "pfx: cuTensorMapEncodeTiled failed (%d): ptr %p dims {%llu, %llu} stride %llu box {%u, %u} dtype %d\n", (int)r, ptr,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner, box_outer, dtype_code);
+    return r == CUDA_SUCCESS;
   });
 }
 

@@ -32,6 +32,7 @@ import torch.distributed as dist
 from ..ops import _native
 from ..ops import functional as OF
 from ..parallel import comm_ops as C
+from ..parallel import debug_poison as _debug
 from ..parallel.flat_buffer import FlatGroup, attach_grad_views, build_flat_groups
 from ..utils.log import logger
 from .grad_clip import ClipGradByGlobalNorm, ClipGradForMOEByGlobalNorm
@@ -198,7 +199,7 @@ class FusedAdamW:
     def _build_grad_ring(self, grad_dtype, alloc) -> None:
         slots = int(_os.environ.get("PFX_ZERO2_SLOTS", "3"))
         dev = self.groups[0].param_buf.device
-        mk = alloc or (lambda n, dt, d: torch.zeros(n, dtype=dt, device=d))
+        mk = (lambda n, dt, d: alloc(n, dt, d).zero_()) if alloc else (lambda n, dt, d: torch.zeros(n, dtype=dt, device=d))
         ring_groups = [g for g in self.groups if g.key[0] >= 0 and not g.key[3]]          # bucketed, not expert-private
         by_dtype: Dict[torch.dtype, List[FlatGroup]] = {}
         for g in ring_groups:
@@ -470,6 +471,14 @@ class FusedAdamW:
     def step(self) -> None:
         lr = self.get_lr()
         self._step_count += 1
+        if _debug.enabled():
+            # PFX_DEBUG_POISON=1: the previous step's broadcast must have delivered every parameter (fresh symmetric memory is NaN-poisoned,
+            # a consumer that ran ahead of its producer leaves NaN behind) and every rank must have issued the same barriers
+            torch.cuda.synchronize() if self._dev.type == "cuda" else None
+            for g in self.groups:
+                _debug.check_finite(g.param_buf, f"parameter bucket {g.key} before optimizer step {self._step_count}", self.sh_rank)
+            if getattr(self, "_symm", None) is not None and hasattr(self._symm, "_bar_counts"):
+                _debug.barrier_skew_check(self._symm._bar_counts, self._symm.group)
         if self._comm_stream is not None:
             self._wait(self._comm_stream)
         for g in self.groups:

@@ -70,6 +70,8 @@ def build_flat_groups(params: Iterable[torch.nn.Parameter], key_fn: Callable[[to
         total = ((cur + unit - 1) // unit) * unit
         alloc = alloc_fn or (lambda n, dt, dev: torch.zeros(n, dtype=dt, device=dev))
         pbuf = alloc(total, dtype, device)
+        if alloc_fn is not None:
+            pbuf.zero_()                 # symmetric memory is not guaranteed to arrive zeroed; the alignment padding is read by the norm / update kernels
         for p, o in zip(plist, offsets):
             view = pbuf[o:o + p.numel()].view(p.shape)
             view.copy_(p.data)
@@ -78,6 +80,8 @@ def build_flat_groups(params: Iterable[torch.nn.Parameter], key_fn: Callable[[to
         if allocate_grads:
             gd = grad_dtype or dtype
             g.grad_buf = alloc(total, gd, device)
+            if alloc_fn is not None:
+                g.grad_buf.zero_()
             attach_grad_views(g, main_grad=(gd != dtype))
         groups.append(g)
     return groups

@@ -20,6 +20,8 @@ import uuid
 from typing import Dict, List, Optional, Tuple
 
 import torch
+
+from . import debug_poison as _debug
 import torch.distributed as dist
 
 from ..ops import _native
@@ -59,7 +61,9 @@ class SymmetricAllocator:
     def alloc_tensor(self, numel: int, dtype: torch.dtype, device=None) -> torch.Tensor:
         esize = torch.empty(0, dtype=dtype).element_size()
         ptr, _ = self._alloc_raw(numel * esize)
-        return self.lib.tensor_from_ptr(ptr, [numel], dtype, self.device.index or 0)
+        t = self.lib.tensor_from_ptr(ptr, [numel], dtype, self.device.index or 0)
+        _debug.poison(t)                 # PFX_DEBUG_POISON=1: whatever is read before a producer wrote it is NaN, not stale data
+        return t
 
     def empty(self, shape, dtype: torch.dtype) -> torch.Tensor:
         n = 1
@@ -276,7 +280,9 @@ class VmmSymmetricAllocator:
             a = self._cur = self._new_arena(max(nbytes, self.ARENA_BYTES))
         ptr = a["base"] + a["used"]
         a["used"] += nbytes
-        return self.lib.tensor_from_ptr(ptr, [numel], dtype, self.device.index or 0)
+        t = self.lib.tensor_from_ptr(ptr, [numel], dtype, self.device.index or 0)
+        _debug.poison(t)                 # PFX_DEBUG_POISON=1: whatever is read before a producer wrote it is NaN, not stale data
+        return t
 
     def empty(self, shape, dtype: torch.dtype) -> torch.Tensor:
         n = 1

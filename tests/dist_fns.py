@@ -570,3 +570,19 @@ def resume_matches_uninterrupted(rank, world, layout):
     eng2.load()
     resumed = [float(eng2.train_step(b)) for b in batches[3:]]
     assert cont == resumed, (layout, cont, resumed)
+
+
+def barrier_skew_detected(rank, world):
+    """PFX_DEBUG_POISON: equal barrier counts pass, a rank that issued one barrier more on a channel is reported on every rank."""
+    import os
+
+    from paddlefleetx_b200.parallel import debug_poison as D
+
+    os.environ["PFX_DEBUG_POISON"] = "1"
+    D.barrier_skew_check({0: 5, 2: 1})
+    try:
+        D.barrier_skew_check({0: 5, 2: 1 + (rank == 1)})
+    except RuntimeError as e:
+        assert "channel 2" in str(e) and "[1, 2]" in str(e), str(e)
+    else:
+        raise AssertionError("skew not detected")
