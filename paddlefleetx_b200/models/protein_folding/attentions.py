@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ...distributed.protein_folding import dap
+from ...ops.evoformer_attention import evoformer_attention
 
 Attention = None  # set below: the reference's name for the gated attention primitive
 
@@ -34,19 +35,15 @@ class GatedAttention(nn.Module):
         # q_data: [b, g, q, c]; m_data: [b, g, k, c]; bias: [b, g, 1, 1, k]; nonbatched_bias: [b, 1, h, q, k]
         b, g, nq, _ = q_data.shape
         nk = m_data.shape[2]
-        q = self.q(q_data).view(b, g, nq, self.h, self.d).transpose(2, 3)
-        k = self.k(m_data).view(b, g, nk, self.h, self.d).transpose(2, 3)
-        v = self.v(m_data).view(b, g, nk, self.h, self.d).transpose(2, 3)
-        mask = None
-        if bias is not None:
-            mask = bias.to(q.dtype)
-        if nonbatched_bias is not None:
-            mask = nonbatched_bias.to(q.dtype) if mask is None else mask + nonbatched_bias.to(q.dtype)
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
-        o = o.transpose(2, 3).reshape(b, g, nq, self.h * self.d)
-        if self.g is not None:
-            o = o * torch.sigmoid(self.g(q_data))
-        return self.o(o)
+        q = self.q(q_data).view(b * g, nq, self.h, self.d)
+        k = self.k(m_data).view(b * g, nk, self.h, self.d)
+        v = self.v(m_data).view(b * g, nk, self.h, self.d)
+        gate = self.g(q_data).view(b * g, nq, self.h, self.d) if self.g is not None else None
+        mask_bias = bias.expand(b, g, 1, 1, nk).reshape(b * g, nk) if bias is not None else None          # broadcastable over b / g
+        pair_bias = nonbatched_bias.expand(b, 1, self.h, nq, nk).reshape(b, self.h, nq, nk) if nonbatched_bias is not None else None
+        # one fused kernel on B200 (logits, biases, softmax, P V and the gate stay on chip); the same expression in PyTorch elsewhere
+        o = evoformer_attention(q, k, v, mask_bias, pair_bias, gate, groups_per_pair=g)
+        return self.o(o.reshape(b, g, nq, self.h * self.d))
 
 
 class MSARowAttentionWithPairBias(nn.Module):

@@ -22,7 +22,7 @@ CSRC = HERE / "csrc"
 BUILD_DIR = HERE / "csrc" / "build"
 MODULE_NAME = "_pfx_native"
 CUDA_SOURCES = ["gemm_sm100.cu", "norm_act.cu", "loss_optim.cu", "sampling_attn_misc.cu", "comm_p2p.cu",
-                "gemm_lowp_sm100.cu", "quant_kernels.cu", "moe_kernels.cu", "gemv_skinny.cu", "gemm_smallm_sm100.cu", "attention_decode.cu", "attention_fwd_sm100.cu", "comm_nvls.cu", "attention_bwd_sm100.cu", "embedding.cu", "probe_kernels.cu"]
+                "gemm_lowp_sm100.cu", "quant_kernels.cu", "moe_kernels.cu", "gemv_skinny.cu", "gemm_smallm_sm100.cu", "attention_decode.cu", "attention_fwd_sm100.cu", "comm_nvls.cu", "attention_bwd_sm100.cu", "evoformer_attn_sm100.cu", "embedding.cu", "probe_kernels.cu"]
 CPP_SOURCES = ["bindings.cpp", "symm_vmm.cpp"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

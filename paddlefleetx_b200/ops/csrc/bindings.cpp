@@ -757,6 +757,35 @@ std::vector<at::Tensor> moe_dispatch(const at::Tensor& src, c10::optional<at::Te
                                    dtype_code(src), (int)num_ctas, cur_stream()));
   return {slot_loc, seg};
 }
+// Evoformer gated attention forward: q [G, Sq, H, 32], k / v [G, Sk, H, 32]; returns (out [G, Sq, H, 32], lse [G, H, Sq])
+std::vector<at::Tensor> evoformer_attention_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, c10::optional<at::Tensor> mask_bias,
+                                                c10::optional<at::Tensor> pair_bias, c10::optional<at::Tensor> gate, int64_t groups_per_pair, double scale) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous(), "evoformer_attention: contiguous [G, S, H, 32]");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 && k.scalar_type() == at::kBFloat16 && v.scalar_type() == at::kBFloat16, "evoformer_attention: bf16");
+  const int64_t G = q.size(0), Sq = q.size(1), H = q.size(2), Sk = k.size(1);
+  TORCH_CHECK(q.size(3) == 32 && k.size(3) == 32 && v.size(3) == 32 && H % 2 == 0 && k.size(0) == G && v.size(0) == G && k.size(2) == H && v.size(2) == H && v.size(1) == Sk,
+              "evoformer_attention: head width 32, even head count, matching shapes");
+  const c10::cuda::CUDAGuard guard(q.device());
+  const float* mb = nullptr; const void* pb = nullptr; const void* gt = nullptr;
+  if (mask_bias.has_value() && mask_bias->defined()) {
+    TORCH_CHECK(mask_bias->scalar_type() == at::kFloat && mask_bias->is_contiguous() && mask_bias->numel() == G * Sk, "evoformer_attention: mask_bias fp32 [G, Sk]");
+    mb = mask_bias->data_ptr<float>();
+  }
+  if (pair_bias.has_value() && pair_bias->defined()) {
+    TORCH_CHECK(pair_bias->scalar_type() == at::kBFloat16 && pair_bias->is_contiguous() && G % groups_per_pair == 0 &&
+                pair_bias->numel() == (G / groups_per_pair) * H * Sq * Sk, "evoformer_attention: pair_bias bf16 [G / groups_per_pair, H, Sq, Sk]");
+    pb = pair_bias->data_ptr();
+  }
+  if (gate.has_value() && gate->defined()) {
+    TORCH_CHECK(gate->scalar_type() == at::kBFloat16 && gate->is_contiguous() && gate->numel() == q.numel(), "evoformer_attention: gate bf16 like q");
+    gt = gate->data_ptr();
+  }
+  at::Tensor out = at::empty_like(q), lse = at::empty({G, H, Sq}, q.options().dtype(at::kFloat));
+  PFX_CUDA_CHECK(pfx::evoformer_attention_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), mb, pb, gt, (int)G, (int)Sq,
+                                              (int)Sk, (int)H, (int)groups_per_pair, (float)scale, cur_stream()));
+  return {out, lse};
+}
+
 // tile table + K segments of the grouped expert GEMMs, from the dispatch kernel's segment table (all on the device)
 std::vector<at::Tensor> moe_tile_table(const at::Tensor& seg, int64_t e_local, int64_t align, int64_t cap_rows, at::Tensor& sticky) {
   TORCH_CHECK(seg.is_cuda() && seg.scalar_type() == at::kInt && seg.numel() == 2 * e_local + 2 && sticky.scalar_type() == at::kInt, "moe_tile_table: bad seg");
@@ -883,6 +912,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_fwd", &attention_fwd);
   m.def("probe_tmem_a", &probe_tmem_a);
   m.def("moe_tile_table", &moe_tile_table);
+  m.def("evoformer_attention_fwd", &evoformer_attention_fwd);
   m.def("gemm_grouped", &gemm_grouped, py::arg("a"), py::arg("b"), py::arg("bias"), py::arg("tile_group"), py::arg("out"), py::arg("b_kmajor") = true,
         py::arg("epilogue") = 0, py::arg("out2") = py::none(), py::arg("aux") = py::none(), py::arg("row_align") = 128);
   m.def("gemm_grouped_wgrad", &gemm_grouped_wgrad);

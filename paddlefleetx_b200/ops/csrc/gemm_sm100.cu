@@ -476,6 +476,10 @@ inline uint64_t tmap_hash(const TmapKey& k) {
 
 template <typename Encode>
 inline bool tmap_cached(CUtensorMap* out, const TmapKey& key, Encode&& encode) {
+  // cuTensorMapEncodeTiled is a DRIVER call: it fails with CUDA_ERROR_INVALID_CONTEXT on a thread that has not touched the runtime yet
+  // (autograd's backward threads, when the caching allocator served every tensor without a runtime call).  Bind the primary context once.
+  thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   thread_local TmapSlot* slots = new TmapSlot[kTmapCacheSlots]();
   TmapSlot& s = slots[tmap_hash(key) & (kTmapCacheSlots - 1)];
   if (s.valid && s.key == key) { *out = s.map; ++g_tmap_hits; return true; }

@@ -832,7 +832,64 @@ def check_moe_grouped(perf=False):
     return dict(ok=ok, cases=res)
 
 
+def check_evoformer_attention(perf=False):
+    """Evoformer gated attention kernel against the fp32 expression: both biases, gating, ragged lengths, several key tiles, heads 4 / 8; the
+    chunked backward against autograd of the same expression."""
+    import torch
+    from paddlefleetx_b200.ops import evoformer_attention as EA
+    torch.manual_seed(0)
+    res, ok = {}, True
+    #        G   gpp Sq   Sk   H  mask  pair  gate
+    cases = [(4, 4, 128, 128, 4, True, True, True), (6, 3, 200, 200, 8, True, True, True), (2, 1, 300, 77, 2, True, False, True),
+             (3, 3, 64, 384, 4, False, True, False), (8, 8, 256, 256, 8, True, True, True)]
+    if perf:
+        cases = [(256, 256, 256, 256, 8, True, True, True), (128, 128, 384, 384, 8, True, True, True)]
+    for (G, gpp, Sq, Sk, H, wm, wp, wg) in cases:
+        mk = lambda *sh: (torch.randn(*sh, device="cuda") * 0.7).bfloat16()
+        q, k, v = mk(G, Sq, H, 32), mk(G, Sk, H, 32), mk(G, Sk, H, 32)
+        mask = None
+        if wm:
+            keep = (torch.rand(G, Sk, device="cuda") > 0.15).float()
+            keep[:, 0] = 1
+            mask = (keep - 1.0) * 1e9
+        pair = mk(G // gpp, H, Sq, Sk) if wp else None
+        gate = mk(G, Sq, H, 32) if wg else None
+        name = f"G{G}_Sq{Sq}_Sk{Sk}_H{H}" + ("_mask" if wm else "") + ("_pair" if wp else "") + ("_gate" if wg else "")
+        if perf:
+            out = EA.evoformer_attention(q, k, v, mask, pair, gate, gpp)
+            ms, _ = _time(lambda: EA.evoformer_attention(q, k, v, mask, pair, gate, gpp))
+            def eager():
+                return EA.reference(q, k, v, mask, pair, gate, gpp, 32 ** -0.5).to(q.dtype)
+            ms_ref, _ = _time(eager)
+            def sdpa():
+                m = mask.view(G, 1, 1, Sk) + pair.float().repeat_interleave(gpp, 0)
+                o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=m.to(q.dtype))
+                return o.transpose(1, 2) * torch.sigmoid(gate)
+            ms_sdpa, _ = _time(sdpa)
+            flops = 4.0 * G * H * Sq * Sk * 32
+            res[name] = dict(ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), eager_fp32_ms=round(ms_ref, 4), sdpa_masked_ms=round(ms_sdpa, 4),
+                             err=round(_relerr(out, eager()), 5))
+            continue
+        leaves = [t.clone().requires_grad_(True) for t in (q, k, v)] + [t.clone().requires_grad_(True) if t is not None else None for t in (pair, gate)]
+        out = EA.evoformer_attention(leaves[0], leaves[1], leaves[2], mask, leaves[3], leaves[4], gpp)
+        ref_leaves = [t.detach().float().requires_grad_(True) for t in (q, k, v)] + [t.detach().float().requires_grad_(True) if t is not None else None for t in (pair, gate)]
+        ref = EA.reference(ref_leaves[0], ref_leaves[1], ref_leaves[2], mask, ref_leaves[3], ref_leaves[4], gpp, 32 ** -0.5)
+        go = torch.randn_like(ref)
+        out.backward(go.to(out.dtype))
+        ref.backward(go)
+        errs = {"out": _relerr(out, ref)}
+        for nm, a, b in zip(("dq", "dk", "dv", "dpair", "dgate"), leaves, ref_leaves):
+            if a is not None:
+                errs[nm] = _relerr(a.grad, b.grad)
+        case_ok = max(errs.values()) < 2e-2
+        ok = ok and case_ok
+        res[name] = dict(ok=case_ok, **{k_: round(v_, 5) for k_, v_ in errs.items()})
+    return dict(ok=ok, cases=res)
+
+
 CHECKS = {
+    "evoformer_attention": check_evoformer_attention,
+    "evoformer_attention_perf": lambda: check_evoformer_attention(perf=True),
     "moe_grouped": check_moe_grouped,
     "moe_grouped_perf": lambda: check_moe_grouped(perf=True),
     "attention_train": check_attention_train,
