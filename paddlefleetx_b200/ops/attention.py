@@ -2,7 +2,7 @@
 
 ``attention(q, k, v)`` takes ``[b, s, heads, d]`` tensors (views are fine: the slices of a packed QKV projection, sequence-major
 storage).  Path selection on CUDA / bf16:
-  * training and inference at head_dim 128 (forward also 64): our tcgen05 / TMEM flash kernels — ``csrc/attention_fwd_sm100.cu`` and
+  * training and inference at head_dim 128 or 64: our tcgen05 / TMEM flash kernels — ``csrc/attention_fwd_sm100.cu`` and
     ``csrc/attention_bwd_sm100.cu`` — with in-kernel causal masking and counter-hash dropout (the backward regenerates the mask; nothing is
     stored).  ``flash_attention_packed`` is the same pair for the ``[b, s, heads, 3, d]`` output of a fused QKV projection: it reads q / k / v
     in place and writes ONE packed gradient, so no split / cat copies surround the kernels,
@@ -30,7 +30,7 @@ def _native_ok(q, k, v, attn_mask, causal, needs_grad: bool) -> bool:
     if not _NATIVE or attn_mask is not None or not q.is_cuda or q.dtype != torch.bfloat16 or k.dtype != q.dtype or v.dtype != q.dtype:
         return False
     d = q.shape[-1]
-    if d not in (64, 128) or (needs_grad and d != 128) or q.shape[1] < 1 or (causal and k.shape[1] < q.shape[1]):
+    if d not in (64, 128) or q.shape[1] < 1 or (causal and k.shape[1] < q.shape[1]):
         return False
     for t in (q, k, v):
         if t.dim() != 4 or t.stride(3) != 1 or any(t.stride(i) % 8 for i in range(3)) or t.data_ptr() % 16:

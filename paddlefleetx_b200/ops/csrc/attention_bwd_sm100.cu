@@ -41,15 +41,16 @@ namespace {
 constexpr int kBwThreads = 448;
 constexpr int kKv = 128;            // keys per CTA
 constexpr int kQt = 64;             // queries per inner iteration
-constexpr int kHd = 128;            // head dim
 
+template <int kHd>                  // head dim: 128 (two 64-channel panels per tile) or 64 (one)
 struct BwSmem {
-  static constexpr int kKBytes = kKv * kHd * 2;          // 32 KB: two [128 x 64] panels
-  static constexpr int kQBytes = kQt * kHd * 2;          // 16 KB: two [64 x 64] panels
+  static constexpr int kPanels = kHd / 64;
+  static constexpr int kKBytes = kKv * kHd * 2;          // [128 x 64] panels of 16 KB
+  static constexpr int kQBytes = kQt * kHd * 2;          // [64 x 64] panels of 8 KB
   static constexpr int kDsBytes = kKv * kQt * 2;         // 16 KB: one [128 x 64] panel
   static constexpr int kStatBytes = 2 * kQt * 4;         // lse2 + delta of one query tile
   static constexpr int kStages = 3;                      // Q_i / dO_i / stats ring: the MMA warp runs two query tiles ahead of the math warps
-  static constexpr int kDqBytes = kQt * kHd * 4;         // 32 KB: dQ tile [64 q][128 d] fp32, row-major (TMA reduce source)
+  static constexpr int kDqBytes = kQt * kHd * 4;         // dQ tile [64 q][kHd d] fp32, row-major (TMA reduce source)
   static constexpr int kOffK = 0;
   static constexpr int kOffV = kOffK + kKBytes;
   static constexpr int kOffQ = kOffV + kKBytes;
@@ -85,10 +86,12 @@ __device__ __forceinline__ void tma_tile(const CUtensorMap* m, bool swapped, uin
   if (swapped) tma_load_3d(m, bar, dst, col, b, s); else tma_load_3d(m, bar, dst, col, s, b);
 }
 
+template <int kHd>
 __global__ void __launch_bounds__(kBwThreads, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                      const __grid_constant__ CUtensorMap tmap_do, const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ BwParams prm) {
-  using S = BwSmem;
+  using S = BwSmem<kHd>;
+  constexpr int kPanels = S::kPanels;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -149,7 +152,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     // ======================================================================================= TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * S::kKBytes);
-      for (int p = 0; p < 2; ++p) {
+      for (int p = 0; p < kPanels; ++p) {
         tma_tile(&tmap_k, prm.swapped & 2u, kv_full, s_k + p * 16384, h * prm.hs_k + p * 64, k0, b);
         tma_tile(&tmap_v, prm.swapped & 4u, kv_full, s_v + p * 16384, h * prm.hs_v + p * 64, k0, b);
       }
@@ -157,7 +160,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int st = it % S::kStages, q0 = (i_begin + it) * kQt;
         mbar_wait(q_empty(st), (((uint32_t)(it / S::kStages)) & 1u) ^ 1u);
         mbar_arrive_expect_tx(q_full(st), 2 * S::kQBytes + S::kStatBytes);
-        for (int p = 0; p < 2; ++p) {
+        for (int p = 0; p < kPanels; ++p) {
           tma_tile(&tmap_q, prm.swapped & 1u, q_full(st), s_q + st * S::kQBytes + p * 8192, h * prm.hs_q + p * 64, q0, b);
           tma_tile(&tmap_do, prm.swapped & 8u, q_full(st), s_do + st * S::kQBytes + p * 8192, h * prm.hs_do + p * 64, q0, b);
         }
@@ -173,7 +176,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc(1, 1, 1, false, false, kKv, kQt);      // S^T, dP^T: both operands K-major
       const uint32_t idesc_acc = umma_idesc(1, 1, 1, false, true, kKv, kHd);     // dV, dK: A K-major (tensor / shared memory), B MN-major
-      const uint32_t idesc_dq = umma_idesc(1, 1, 1, true, true, kHd, kQt);       // dQ^T: both MN-major
+      // dQ^T: both MN-major.  M is 128 even for a 64-wide head: the A descriptor's second 64-channel chunk (16 KB further) then lands on the
+      // V tile — valid shared memory whose product fills accumulator lanes 64..127, which nobody reads.
+      const uint32_t idesc_dq = umma_idesc(1, 1, 1, true, true, 128, kQt);
       constexpr uint64_t kDescK = umma_desc_hi_lo(16, 1024);
       constexpr uint64_t kDescMN8 = umma_desc_hi_lo(8192, 1024);                 // 64-wide MN chunks 8 KB apart (Q_i / dO_i panels)
       constexpr uint64_t kDescMN16 = umma_desc_hi_lo(16384, 1024);               // ... 16 KB apart (K_j panels; dS^T has a single chunk)
@@ -346,18 +351,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(ds_ready(x));
     }
-    // ---- epilogue: dV and dK of this key tile (this thread: its key row, channels [64*half, 64*half + 64))
+    // ---- epilogue: dV and dK of this key tile (this thread: its key row, one half of the channels)
+    constexpr int kCh = kHd / 2;
     mbar_wait(dkv_full, 0);
     tcgen05_fence_after();
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {
       const BwOut& o = which == 0 ? prm.dv : prm.dk;
       const uint32_t t_acc = which == 0 ? t_dv : t_dk;
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.ptr) + (size_t)b * o.sb + (size_t)kg * o.ss + (size_t)h * o.sh + 64 * half;
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(o.ptr) + (size_t)b * o.sb + (size_t)kg * o.ss + (size_t)h * o.sh + kCh * half;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int c0 = 0; c0 < kCh; c0 += 32) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(t_acc + lane_addr + 64 * half + c0, r);
+        tmem_ld_32x32b_x32(t_acc + lane_addr + kCh * half + c0, r);
         tmem_ld_wait();
         if (k_valid) {
 #pragma unroll
@@ -393,11 +399,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       if (lane == 0) mbar_arrive(dq_free(x));
       if (leader) tma_store_wait_read<0>();                     // the previous tile's reduce has finished reading the staging buffer
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t col = s_dq + (uint32_t)d * 4u;             // staging tile [64 q][128 d] fp32: a warp writes 32 consecutive floats of one row
+      const uint32_t col = s_dq + (uint32_t)d * 4u;             // staging tile [64 q][kHd d] fp32: a warp writes 32 consecutive floats of one row
+      if (d < kHd) {                                            // (64-wide heads: accumulator lanes 64..127 hold the unused second chunk)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + (uint32_t)c * 512u), "r"(r0[c]) : "memory");
+        for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + (uint32_t)c * (kHd * 4u)), "r"(r0[c]) : "memory");
 #pragma unroll
-      for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + (uint32_t)(32 + c) * 512u), "r"(r1[c]) : "memory");
+        for (int c = 0; c < 32; ++c) asm volatile("st.shared.b32 [%0], %1;" ::"r"(col + (uint32_t)(32 + c) * (kHd * 4u)), "r"(r1[c]) : "memory");
+      }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (leader) {
@@ -413,6 +421,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }
 
 // ---- preprocessing: delta = rowsum(dO o O), lse in log2 units; both padded to a multiple of 64 queries per (b, h)
+template <int kHd>
 __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_t o_sb, int64_t o_ss, int64_t o_sh, const __nv_bfloat16* __restrict__ dout,
                                      int64_t d_sb, int64_t d_ss, int64_t d_sh, const float* __restrict__ lse, float* __restrict__ lse2,
                                      float* __restrict__ delta, int B, int Sq, int H, int Sq_pad) {
@@ -427,13 +436,12 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_
     if (lane == 0) { lse2[oi] = INFINITY; delta[oi] = 0.f; }
     return;
   }
-  const uint2 a = *reinterpret_cast<const uint2*>(o + b * o_sb + s * o_ss + h * o_sh + lane * 4);
-  const uint2 g = *reinterpret_cast<const uint2*>(dout + b * d_sb + s * d_ss + h * d_sh + lane * 4);
-  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&g);
+  constexpr int kPer = kHd / 32;                         // channels per lane (4 or 2)
+  const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(o + b * o_sb + s * o_ss + h * o_sh + lane * kPer);
+  const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(dout + b * d_sb + s * d_ss + h * d_sh + lane * kPer);
   float acc = 0.f;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kPer / 2; ++i) {
     const float2 x = __bfloat1622float2(a2[i]), y = __bfloat1622float2(g2[i]);
     acc += x.x * y.x + x.y * y.y;
   }
@@ -445,7 +453,7 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, int64_
 }
 
 // ---- dq: fp32 accumulator -> bf16 view
-__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t sb, int64_t ss, int64_t sh, int B, int Sq, int H) {
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t sb, int64_t ss, int64_t sh, int B, int Sq, int H, int kHd) {
   const int64_t n8 = (int64_t)B * Sq * H * (kHd / 8);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % (kHd / 8));
@@ -471,18 +479,19 @@ bool make_map(CUtensorMap* m, const AttnView& t, int B, int S, int H, int D, uin
 
 }  // namespace
 
-cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& out, const AttnView& dout, const float* lse,
-                          const AttnView& dq, const AttnView& dk, const AttnView& dv, float* dq_acc, float* lse2, float* delta, int B, int Sq,
-                          int Sk, int H, int D, float scale, bool causal, AttnDropout drop, cudaStream_t st) {
-  if (D != kHd || B < 1 || Sq < 1 || Sk < 1 || (causal && Sk < Sq)) return cudaErrorInvalidValue;
-  for (const AttnView* t : {&q, &k, &v, &out, &dout, &dq, &dk, &dv}) if (!view_ok(*t)) return cudaErrorInvalidValue;
+template <int kHd>
+static cudaError_t attention_bwd_impl(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& out, const AttnView& dout, const float* lse,
+                                      const AttnView& dq, const AttnView& dk, const AttnView& dv, float* dq_acc, float* lse2, float* delta, int B, int Sq,
+                                      int Sk, int H, float scale, bool causal, AttnDropout drop, cudaStream_t st) {
+  constexpr int D = kHd;
+  using S = BwSmem<kHd>;
   const int Sq_pad = (Sq + kQt - 1) / kQt * kQt;
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, (size_t)B * Sq * H * kHd * sizeof(float), st);
   if (e != cudaSuccess) return e;
   {
     const int64_t warps = (int64_t)B * Sq_pad * H;
     const int wpb = 8;
-    attn_bwd_prep_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+    attn_bwd_prep_kernel<kHd><<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(
         (const __nv_bfloat16*)out.ptr, out.sb, out.ss, out.sh, (const __nv_bfloat16*)dout.ptr, dout.sb, dout.ss, dout.sh, lse, lse2, delta, B, Sq, H, Sq_pad);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
@@ -506,14 +515,23 @@ cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& 
   prm.seed = drop.seed;
   static bool attr_set = false;
   if (!attr_set) {
-    if ((e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kTotal)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(attention_bwd_kernel<kHd>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal)) != cudaSuccess) return e;
     attr_set = true;
   }
   const int n_kv = (Sk + kKv - 1) / kKv;
-  attention_bwd_kernel<<<(unsigned)(n_kv * B * H), kBwThreads, BwSmem::kTotal, st>>>(tq, tk, tv, tdo, tdq, prm);
+  attention_bwd_kernel<kHd><<<(unsigned)(n_kv * B * H), kBwThreads, S::kTotal, st>>>(tq, tk, tv, tdo, tdq, prm);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
-  attn_bwd_dq_convert_kernel<<<1184, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)const_cast<void*>(dq.ptr), dq.sb, dq.ss, dq.sh, B, Sq, H);
+  attn_bwd_dq_convert_kernel<<<1184, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)const_cast<void*>(dq.ptr), dq.sb, dq.ss, dq.sh, B, Sq, H, kHd);
   return cudaGetLastError();
+}
+
+cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& v, const AttnView& out, const AttnView& dout, const float* lse,
+                          const AttnView& dq, const AttnView& dk, const AttnView& dv, float* dq_acc, float* lse2, float* delta, int B, int Sq,
+                          int Sk, int H, int D, float scale, bool causal, AttnDropout drop, cudaStream_t st) {
+  if ((D != 64 && D != 128) || B < 1 || Sq < 1 || Sk < 1 || (causal && Sk < Sq)) return cudaErrorInvalidValue;
+  for (const AttnView* t : {&q, &k, &v, &out, &dout, &dq, &dk, &dv}) if (!view_ok(*t)) return cudaErrorInvalidValue;
+  if (D == 128) return attention_bwd_impl<128>(q, k, v, out, dout, lse, dq, dk, dv, dq_acc, lse2, delta, B, Sq, Sk, H, scale, causal, drop, st);
+  return attention_bwd_impl<64>(q, k, v, out, dout, lse, dq, dk, dv, dq_acc, lse2, delta, B, Sq, Sk, H, scale, causal, drop, st);
 }
 
 }  // namespace pfx

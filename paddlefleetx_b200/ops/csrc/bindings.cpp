@@ -694,7 +694,7 @@ std::vector<at::Tensor> attention_fwd_v2(const at::Tensor& q, const at::Tensor& 
 void attention_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& out, const at::Tensor& dout, const at::Tensor& lse,
                    at::Tensor& dq, at::Tensor& dk, at::Tensor& dv, bool causal, double scale, double dropout_p, int64_t seed) {
   TORCH_CHECK(q.dim() == 4 && k.sizes() == v.sizes() && q.sizes() == out.sizes() && q.sizes() == dout.sizes() && q.sizes() == dq.sizes() &&
-              k.sizes() == dk.sizes() && k.sizes() == dv.sizes() && q.size(3) == 128, "attention_bwd: shape mismatch (head_dim must be 128)");
+              k.sizes() == dk.sizes() && k.sizes() == dv.sizes() && (q.size(3) == 128 || q.size(3) == 64), "attention_bwd: shape mismatch (head_dim must be 64 or 128)");
   TORCH_CHECK(lse.is_cuda() && lse.is_contiguous() && lse.scalar_type() == at::kFloat && lse.numel() == q.size(0) * q.size(1) * q.size(2), "attention_bwd: lse");
   const c10::cuda::CUDAGuard guard(q.device());
   const int64_t B = q.size(0), Sq = q.size(1), Sk = k.size(1), H = q.size(2), D = q.size(3);

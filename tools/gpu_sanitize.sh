@@ -20,4 +20,4 @@ for t in "${tools[@]}"; do
     summary=$(grep -E "ERROR SUMMARY|RACECHECK SUMMARY" "$log" | tail -1)
     echo "$t $c rc=$rc ${summary:-no summary line}"
   done
-done | tee gpurun_out/sanitize/summary.txt
+done | tee -a gpurun_out/sanitize/summary.txt

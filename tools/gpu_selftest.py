@@ -386,12 +386,14 @@ def check_attention_train(perf=False):
     lib = _lib()
     torch.manual_seed(0)
     res, ok = {}, True
-    cases = [  # B, Sq, Sk, H, causal, p, layout
-        (1, 128, 128, 1, True, 0.0, "plain"), (2, 256, 256, 2, True, 0.0, "plain"), (1, 320, 320, 2, True, 0.1, "plain"),
-        (2, 200, 200, 3, False, 0.0, "plain"), (1, 128, 256, 2, True, 0.0, "plain"), (2, 512, 512, 4, True, 0.1, "packed"),
-        (2, 384, 384, 2, True, 0.1, "seq_major"), (1, 1024, 1024, 4, True, 0.0, "packed")]
-    D = 128
-    for (B, Sq, Sk, H, causal, p, layout) in cases:
+    cases = [  # B, Sq, Sk, H, causal, p, layout, D
+        (1, 128, 128, 1, True, 0.0, "plain", 128), (2, 256, 256, 2, True, 0.0, "plain", 128), (1, 320, 320, 2, True, 0.1, "plain", 128),
+        (2, 200, 200, 3, False, 0.0, "plain", 128), (1, 128, 256, 2, True, 0.0, "plain", 128), (2, 512, 512, 4, True, 0.1, "packed", 128),
+        (2, 384, 384, 2, True, 0.1, "seq_major", 128), (1, 1024, 1024, 4, True, 0.0, "packed", 128),
+        # 64-wide heads (GPT-345M, ViT, ERNIE-base): full and causal, ragged, dropout, packed projection layout
+        (2, 256, 256, 2, True, 0.0, "plain", 64), (2, 577, 577, 4, False, 0.1, "plain", 64), (1, 1024, 1024, 16, True, 0.1, "packed", 64),
+        (2, 197, 197, 3, False, 0.0, "seq_major", 64)]
+    for (B, Sq, Sk, H, causal, p, layout, D) in cases:
         scale = D ** -0.5
         if layout == "plain":
             q = torch.randn(B, Sq, H, D, device="cuda").bfloat16(); k = torch.randn(B, Sk, H, D, device="cuda").bfloat16(); v = torch.randn(B, Sk, H, D, device="cuda").bfloat16()
@@ -416,10 +418,10 @@ def check_attention_train(perf=False):
             errs["keep_rate"] = round(float(keep.float().mean()), 4)
         good = all(errs[n] < 2e-2 for n in ("out", "dq", "dk", "dv"))
         ok = ok and good
-        res[f"B{B}_Sq{Sq}_Sk{Sk}_H{H}_{'causal' if causal else 'full'}_p{p}_{layout}"] = {n: round(float(e), 5) for n, e in errs.items()}
+        res[f"B{B}_Sq{Sq}_Sk{Sk}_H{H}_D{D}_{'causal' if causal else 'full'}_p{p}_{layout}"] = {n: round(float(e), 5) for n, e in errs.items()}
     out_d = dict(ok=ok, shapes=res)
     if perf:
-        for (B, S, H) in [(8, 1024, 32), (2, 4096, 32)]:
+        for (B, S, H, D) in [(8, 1024, 32, 128), (2, 4096, 32, 128), (16, 1024, 16, 64)]:
             mix = torch.randn(B, S, H, 3, D, device="cuda").bfloat16(); q, k, v = mix.unbind(3)
             dmix = torch.empty_like(mix); dq, dk, dv = dmix.unbind(3)
             go = torch.randn(B, S, H, D, device="cuda").bfloat16()
@@ -438,7 +440,7 @@ def check_attention_train(perf=False):
                     qt.grad = kt.grad = vt.grad = None
                 t_sfb, _ = _time(sd_fb)
                 fl = 4.0 * B * H * S * S * D * 0.5
-                out_d[f"perf_B{B}_S{S}_H{H}_p{p}"] = dict(fwd_ms=round(t_f, 4), fwd_tflops=round(fl / t_f / 1e9, 1), bwd_ms=round(t_b, 4),
+                out_d[f"perf_B{B}_S{S}_H{H}{'' if D == 128 else '_D64'}_p{p}"] = dict(fwd_ms=round(t_f, 4), fwd_tflops=round(fl / t_f / 1e9, 1), bwd_ms=round(t_b, 4),
                                                          bwd_tflops=round(2.5 * fl / t_b / 1e9, 1), sdpa_fwd_ms=round(t_sf, 4),
                                                          sdpa_fwd_bwd_ms=round(t_sfb, 4), ours_fwd_bwd_ms=round(t_f + t_b, 4))
     return out_d
