@@ -112,9 +112,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   auto dq_free = [&](int b) { return bar(23 + b); };
 
   const uint32_t warp = warp_id(), lane = lane_id();
-  const int bh_count = prm.B * prm.H;
-  const int j = blockIdx.x / bh_count;            // key tiles in ascending order: under a causal mask the first ones carry the most work
-  const int bh = blockIdx.x - j * bh_count;
+  // CTA order: the key tiles of ONE (batch, head) are neighbours in launch order, so the CTAs that stream the same Q / dO tiles and reduce
+  // into the same dQ rows run at the same time and meet in L2 (ncu of the key-tile-major order: 1.2 GB of DRAM reads for 0.34 GB of
+  // operands, 25 % L2 hit rate).  Within a head the tiles ascend: under a causal mask the first ones carry the most work.
+  const int n_kv_tiles = (prm.Sk + kKv - 1) / kKv;
+  const int bh = blockIdx.x / n_kv_tiles;
+  const int j = blockIdx.x - bh * n_kv_tiles;
   const int h = bh % prm.H, b = bh / prm.H;
   const int k0 = j * kKv;
   const int off = prm.Sk - prm.Sq;                // query q attends keys <= q + off
