@@ -212,6 +212,35 @@ at::Tensor gemm_lowp(const at::Tensor& a, const at::Tensor& b, c10::optional<at:
   return d;
 }
 
+// MX block-scaled fp8: quantiser and GEMM.  quantize_mxfp8(x [R, K]) -> (q e4m3 [R, K], sf uint8 [ceil(R / 128), K / 128, 512])
+std::vector<at::Tensor> quantize_mxfp8(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 2 && x.is_contiguous() && x.size(1) % 128 == 0, "quantize_mxfp8: contiguous [R, K], K % 128 == 0");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int64_t R = x.size(0), K = x.size(1);
+  at::Tensor q = at::empty({R, K}, x.options().dtype(at::kFloat8_e4m3fn));
+  at::Tensor sf = at::zeros({(R + 127) / 128, K / 128, 512}, x.options().dtype(at::kByte));
+  PFX_CUDA_CHECK(pfx::quantize_mxfp8(x.data_ptr(), q.data_ptr(), sf.data_ptr(), (int)R, (int)K, dtype_code(x), cur_stream()));
+  return {q, sf};
+}
+// d [M, N] bf16 = (A_q * 2^(sfa - 127)) (B_q * 2^(sfb - 127))^T (+ bias), the scales applied per 32-element K block by the tensor core
+at::Tensor gemm_mxfp8(const at::Tensor& a, const at::Tensor& sfa, const at::Tensor& b, const at::Tensor& sfb, c10::optional<at::Tensor> bias) {
+  TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 2 && a.is_contiguous() && b.is_contiguous() && a.scalar_type() == at::kFloat8_e4m3fn &&
+              b.scalar_type() == at::kFloat8_e4m3fn, "gemm_mxfp8: contiguous e4m3 operands");
+  const int64_t M = a.size(0), K = a.size(1), N = b.size(0);
+  TORCH_CHECK(b.size(1) == K && K % 128 == 0 && N % 8 == 0, "gemm_mxfp8: K % 128 == 0, N % 8 == 0");
+  TORCH_CHECK(sfa.scalar_type() == at::kByte && sfb.scalar_type() == at::kByte && sfa.is_contiguous() && sfb.is_contiguous() &&
+              sfa.numel() == ((M + 127) / 128) * (K / 128) * 512 && sfb.numel() == ((N + 127) / 128) * (K / 128) * 512, "gemm_mxfp8: scale tensors");
+  const c10::cuda::CUDAGuard guard(a.device());
+  auto d = at::empty({M, N}, a.options().dtype(at::kBFloat16));
+  pfx::LowpGemmArgs g{};
+  g.a = a.data_ptr(); g.b = b.data_ptr(); g.d = d.data_ptr(); g.sfa = sfa.data_ptr(); g.sfb = sfb.data_ptr();
+  if (bias.has_value() && bias->defined()) { TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N); g.bias = bias->data_ptr(); }
+  g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = (int)K; g.ldb = (int)K; g.ldd = (int)N;
+  g.kind = 3; g.num_sms = num_sms(); g.config = 0;
+  PFX_CUDA_CHECK(pfx::gemm_lowp_tcgen05(g, cur_stream()));
+  return d;
+}
+
 // ------------------------------------------------------------------------------- norms
 std::vector<at::Tensor> norm_fwd(const at::Tensor& x, const at::Tensor& w, c10::optional<at::Tensor> b, double eps, bool rms) {
   PFX_CHECK_CUDA_CONTIG(x); PFX_CHECK_CUDA_CONTIG(w);
@@ -912,6 +941,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_fwd", &attention_fwd);
   m.def("probe_tmem_a", &probe_tmem_a);
   m.def("moe_tile_table", &moe_tile_table);
+  m.def("quantize_mxfp8", &quantize_mxfp8);
+  m.def("gemm_mxfp8", &gemm_mxfp8, py::arg("a"), py::arg("sfa"), py::arg("b"), py::arg("sfb"), py::arg("bias") = py::none());
   m.def("evoformer_attention_fwd", &evoformer_attention_fwd);
   m.def("gemm_grouped", &gemm_grouped, py::arg("a"), py::arg("b"), py::arg("bias"), py::arg("tile_group"), py::arg("out"), py::arg("b_kmajor") = true,
         py::arg("epilogue") = 0, py::arg("out2") = py::none(), py::arg("aux") = py::none(), py::arg("row_align") = 128);

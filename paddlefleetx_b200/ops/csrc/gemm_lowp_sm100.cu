@@ -9,6 +9,12 @@
 // converted with I2F in the epilogue and the per-token / per-channel dequantisation scales are applied there, so
 // the int32 / fp32 product never touches HBM.  Reference: L23 in SURVEY §2.6 (Paddle-Inference / TensorRT int8
 // passes — no in-tree kernel in the reference).
+//
+// kKind 3 = MX block-scaled fp8 (kind::mxf8f6f4.block_scale): every 32 K-elements of every row of A and B carry their own E8M0 scale
+// (2^(e - 127)), applied by the tensor core itself.  The quantiser (quant_kernels.cu) writes the scale bytes in the layout the
+// smem -> TMEM copy wants — one 512-byte atom per (128 rows, 128 K): byte (r % 32) * 16 + (r / 32) * 4 + k32 — so a stage needs one
+// 512-byte bulk copy per operand, one tcgen05.cp (32 x 128 b, broadcast to the four lane quarters) into 4 TMEM columns, and the four
+// UMMA K-steps of the stage select their scale byte through the instruction descriptor's a_sf_id / b_sf_id.  1-CTA 128 x 128 tiles.
 #include "pfx_ptx.cuh"
 #include "pfx_gemm.h"
 #include <cudaTypedefs.h>
@@ -23,12 +29,13 @@ constexpr int kNumThreads = 256;
 constexpr int kGroupM = 16;
 constexpr int kStoreCols = 64;
 
-template <int kCG, int kBlockN>
+template <int kCG, int kBlockN, bool kMx = false>
 struct Smem {
   static constexpr int kLoadN = kBlockN / kCG;
   static constexpr int kABytes = kBlockM * kBlockK;
   static constexpr int kBBytes = kLoadN * kBlockK;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSfBytes = 512;                      // one scale-factor atom (128 rows x 4 K-blocks of 32) per operand, MX only
+  static constexpr int kStageBytes = kABytes + kBBytes + (kMx ? 2 * kSfBytes : 0);
   static constexpr int kEpiBytes = kBlockM * kStoreCols * 2;
   static constexpr int kBudget = 227 * 1024 - 1024 - 1024 - 2 * kEpiBytes;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -50,12 +57,15 @@ template <int kCG, int kBlockN, int kKind>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_lowp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_d, const float* __restrict__ row_scale, const float* __restrict__ col_scale,
-                 const __nv_bfloat16* __restrict__ bias, int M, int N, int K) {
-  using S = Smem<kCG, kBlockN>;
+                 const __nv_bfloat16* __restrict__ bias, int M, int N, int K, const uint8_t* __restrict__ sfa, const uint8_t* __restrict__ sfb) {
+  constexpr bool kMx = kKind == 3;
+  static_assert(!kMx || (kCG == 1 && kBlockN == 128), "MX path: 1-CTA 128 x 128 tiles");
+  using S = Smem<kCG, kBlockN, kMx>;
   constexpr int kStages = S::kStages;
   constexpr int kLoadN = S::kLoadN;
   constexpr int kUmmaM = kBlockM * kCG;
-  constexpr int kTmemCols = 2 * kBlockN;
+  constexpr int kTmemCols = kMx ? 512 : 2 * kBlockN;       // MX: accumulators [0, 256), scale factors from column 256
+  constexpr uint32_t kSfCol = 256;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -98,6 +108,10 @@ gemm_lowp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (kCG == 1 || cta_rank == 0) mbar_arrive_expect_tx(fb, S::kStageBytes * kCG);
           if (kCG == 2) { tma_load_2d_2sm(&tmap_a, fb, sa, kb * kBlockK, m_idx); tma_load_2d_2sm(&tmap_b, fb, sb, kb * kBlockK, n_idx); }
           else { tma_load_2d(&tmap_a, fb, sa, kb * kBlockK, m_idx); tma_load_2d(&tmap_b, fb, sb, kb * kBlockK, n_idx); }
+          if constexpr (kMx) {      // the stage's two scale-factor atoms (already in copy order in global memory)
+            bulk_load_1d(sb + S::kBBytes, sfa + ((size_t)m_blk * num_kb + kb) * S::kSfBytes, S::kSfBytes, fb);
+            bulk_load_1d(sb + S::kBBytes + S::kSfBytes, sfb + ((size_t)n_blk * num_kb + kb) * S::kSfBytes, S::kSfBytes, fb);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -116,11 +130,18 @@ gemm_lowp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * S::kStageBytes, sb = sa + S::kABytes;
+          uint32_t tsf = 0;
+          if constexpr (kMx) {      // scale factors of this stage: smem -> 4 + 4 TMEM columns (two alternating sets); cp and mma run in issue order
+            tsf = tmem_base + kSfCol + 8u * (uint32_t)(stage & 1);
+            tmem_cp_32x128b_warpx4(tsf, umma_desc_noswizzle(sb + S::kBBytes, 128));
+            tmem_cp_32x128b_warpx4(tsf + 4, umma_desc_noswizzle(sb + S::kBBytes + S::kSfBytes, 128));
+          }
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t da = umma_desc(sa + k * kUmmaK, kDesc), db = umma_desc(sb + k * kUmmaK, kDesc);   // 32 B per UMMA_K step
-            if (kKind == 1) umma_i8<kCG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f8<kCG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (kKind == 1) umma_i8<kCG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else if constexpr (kKind == 2) umma_f8<kCG>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_mxf8(d_tmem, da, db, umma_idesc_mxf8(kUmmaM, kBlockN, k, k), tsf, tsf + 4, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit<kCG>(empty_bar(stage));
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -207,7 +228,8 @@ gemm_lowp_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int kCG, int kBlockN, int kKind>
 static cudaError_t launch(const LowpGemmArgs& g, cudaStream_t stream) {
-  using S = Smem<kCG, kBlockN>;
+  using S = Smem<kCG, kBlockN, kKind == 3>;
+  if (kKind == 3 && (g.sfa == nullptr || g.sfb == nullptr || g.K % kBlockK != 0)) return cudaErrorInvalidValue;
   CUtensorMap ta, tb, td;
   bool ok = make_tmap_2d(&ta, g.a, 1, 2, g.K, g.M, (uint64_t)g.lda, kBlockK, kBlockM);
   ok &= make_tmap_2d(&tb, g.b, 1, 2, g.K, g.N, (uint64_t)g.ldb, kBlockK, S::kLoadN);
@@ -230,7 +252,8 @@ static cudaError_t launch(const LowpGemmArgs& g, cudaStream_t stream) {
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kCG; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, g.row_scale, g.col_scale, reinterpret_cast<const __nv_bfloat16*>(g.bias), g.M, g.N, g.K);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, td, g.row_scale, g.col_scale, reinterpret_cast<const __nv_bfloat16*>(g.bias), g.M, g.N, g.K,
+                            reinterpret_cast<const uint8_t*>(g.sfa), reinterpret_cast<const uint8_t*>(g.sfb));
 }
 
 }  // namespace lowp
@@ -239,6 +262,7 @@ cudaError_t gemm_lowp_tcgen05(const LowpGemmArgs& g, cudaStream_t stream) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return cudaSuccess;
   const long tiles_big = (long)((g.M + 255) / 256) * ((g.N + 255) / 256);
   const bool pair = g.config == 2 || (g.config == 0 && tiles_big >= g.num_sms / 2);
+  if (g.kind == 3) return lowp::launch<1, 128, 3>(g, stream);
   if (g.kind == 1) return pair ? lowp::launch<2, 256, 1>(g, stream) : lowp::launch<1, 128, 1>(g, stream);
   return pair ? lowp::launch<2, 256, 2>(g, stream) : lowp::launch<1, 128, 2>(g, stream);
 }

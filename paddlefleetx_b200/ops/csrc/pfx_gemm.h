@@ -71,8 +71,10 @@ struct LowpGemmArgs {
   const float* col_scale;   // [N] or nullptr
   const void* bias;         // [N] bf16 or nullptr
   int M, N, K, lda, ldb, ldd;
-  int kind;                 // 1 = int8 (kind::i8), 2 = fp8 e4m3 (kind::f8f6f4)
+  int kind;                 // 1 = int8 (kind::i8), 2 = fp8 e4m3 (kind::f8f6f4), 3 = MX block-scaled fp8 e4m3 (kind::mxf8f6f4.block_scale)
   int num_sms, config;
+  const void* sfa = nullptr;   // kind 3: E8M0 scale bytes of A / B, one 512-byte atom per (128 rows, 128 K): [row_blocks, K / 128, 512]
+  const void* sfb = nullptr;
 };
 cudaError_t gemm_lowp_tcgen05(const LowpGemmArgs& args, cudaStream_t stream);
 

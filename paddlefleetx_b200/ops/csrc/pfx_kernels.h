@@ -38,6 +38,8 @@ cudaError_t rope(const void* x, void* y, const int64_t* positions, size_t tokens
 cudaError_t causal_softmax(const void* a, const void* b, void* out, size_t batch, int sq, int sk, float scale, bool bwd, int dtype,
                            cudaStream_t st);
 
+// MX fp8: e4m3 values + E8M0 scale per 32 K-elements; sf = [ceil(rows / 128), K / 128, 512] bytes in the GEMM copy order (zero-initialised by the caller)
+cudaError_t quantize_mxfp8(const void* x, void* q, void* sf, int rows, int K, int dtype, cudaStream_t st);
 cudaError_t quantize_rows(const void* x, const float* smooth, void* q, float* scale, int rows, int cols, int dtype, bool fp8, cudaStream_t st);
 
 // ---- peer-memory collectives (comm_p2p.cu): every pointer table lives in device memory

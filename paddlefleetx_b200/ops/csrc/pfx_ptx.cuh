@@ -217,6 +217,30 @@ __device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// Block-scaled fp8 (MX: one E8M0 scale per 32 K-elements per row), cta_group::1.  Scale factors live in tensor memory: tsfa / tsfb are
+// the TMEM column addresses of A's and B's scale words (lane = row % 32, replicated in the four lane quarters; column = row / 32; the
+// byte inside the 32-bit word = the idesc's a_sf_id / b_sf_id, i.e. which of the four 32-element K blocks of a 128-wide stage).
+__device__ __forceinline__ void umma_mxf8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t tsfa, uint32_t tsfb,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb) : "memory");
+}
+// Instruction descriptor of kind::mxf8f6f4.block_scale (e4m3 x e4m3, E8M0 scales, both operands K-major):
+//   b_sf_id [4,6)  a_format [7,10)  b_format [10,13)  n_dim [17,23) = N >> 3  scale_format bit 23 (1 = E8M0)  m_dim [24,29) = M >> 4  a_sf_id [29,31)
+__host__ __device__ constexpr uint32_t umma_idesc_mxf8(uint32_t M, uint32_t N, uint32_t a_sf_id, uint32_t b_sf_id) {
+  return (b_sf_id << 4) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24) | (a_sf_id << 29);
+}
+// shared memory -> tensor memory copy of one scale-factor atom: 32 rows x 128 bits, broadcast to the four 32-lane quarters
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t dst_tmem, uint64_t smem_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(dst_tmem), "l"(smem_desc) : "memory");
+}
+// descriptor of an unswizzled K-major region: 8-row groups `sbo_bytes` apart (the scale-factor atoms: 8 x 16 B = 128)
+__device__ __forceinline__ uint64_t umma_desc_noswizzle(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46);
+}
+
 // commit: arrive on `bar` once every MMA issued so far by this thread has retired.
 template <int kCtaGroup>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -889,7 +889,76 @@ def check_evoformer_attention(perf=False):
     return dict(ok=ok, cases=res)
 
 
+def _mx_decode(q, sf):
+    """(e4m3 [R, K], scale atoms) -> fp32 [R, K]: the value the tensor core sees."""
+    import torch
+    R, K = q.shape
+    r = torch.arange(R, device=q.device).view(R, 1)
+    kb = torch.arange(K // 32, device=q.device).view(1, -1)
+    idx = ((r // 128) * (K // 128) + kb // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + (kb % 4)
+    e = sf.reshape(-1)[idx].float()                                   # [R, K / 32]
+    return q.float() * torch.exp2(e - 127).repeat_interleave(32, dim=1)
+
+
+def _mx_encode_sf(e_rows_kb):
+    """[R, K / 32] uint8 exponents -> atom-ordered scale tensor."""
+    import torch
+    R, KB = e_rows_kb.shape
+    sf = torch.full(((R + 127) // 128, KB // 4, 512), 127, dtype=torch.uint8, device=e_rows_kb.device)
+    r = torch.arange(R, device=sf.device).view(R, 1)
+    kb = torch.arange(KB, device=sf.device).view(1, -1)
+    idx = ((r // 128) * (KB // 4) + kb // 4) * 512 + (r % 32) * 16 + ((r % 128) // 32) * 4 + (kb % 4)
+    sf.view(-1)[idx.reshape(-1)] = e_rows_kb.reshape(-1)
+    return sf
+
+
+def check_gemm_mxfp8(perf=False):
+    """MX block-scaled fp8 GEMM (kind::mxf8f6f4.block_scale, scales through TMEM) in stages that isolate each piece of the protocol: unit
+    scales, per-row A scales (lane / column mapping), per-K-block scales (sf_id), B scales, then quantiser + GEMM against fp32."""
+    import torch
+    lib = _lib()
+    torch.manual_seed(0)
+    res, ok = {}, True
+    M, N, K = 300, 384, 512
+    a = (torch.randn(M, K, device="cuda") * 2).to(torch.float8_e4m3fn)
+    b = (torch.randn(N, K, device="cuda") * 2).to(torch.float8_e4m3fn)
+    ones = lambda R: torch.full((R, K // 32), 127, dtype=torch.uint8, device="cuda")
+    rnd = lambda R, per_row, per_k: (127 + torch.randint(-6, 7, (R if per_row else 1, K // 32 if per_k else 1), device="cuda")).to(torch.uint8).expand(R, K // 32).contiguous()
+    stages = {"unit_scales": (ones(M), ones(N)), "a_row_scales": (rnd(M, True, False), ones(N)), "a_kblock_scales": (rnd(M, False, True), ones(N)),
+              "b_row_scales": (ones(M), rnd(N, True, False)), "b_kblock_scales": (ones(M), rnd(N, False, True)), "all_scales": (rnd(M, True, True), rnd(N, True, True))}
+    for name, (ea, eb) in stages.items():
+        sfa, sfb = _mx_encode_sf(ea), _mx_encode_sf(eb)
+        d = lib.gemm_mxfp8(a, sfa, b, sfb)
+        ref = _mx_decode(a, sfa) @ _mx_decode(b, sfb).t()
+        e = _relerr(d, ref)
+        res[name] = round(e, 5)
+        ok = ok and e < 1e-2
+    # quantiser: round trip and layout
+    x = (torch.randn(M, K, device="cuda") * torch.logspace(-2, 2, K // 32, device="cuda").repeat_interleave(32)).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    qx, sx = lib.quantize_mxfp8(x)
+    qw, sw = lib.quantize_mxfp8(w)
+    res["quant_roundtrip"] = round(_relerr(_mx_decode(qx, sx), x), 5)
+    bias = torch.randn(N, device="cuda").bfloat16()
+    d = lib.gemm_mxfp8(qx, sx, qw, sw, bias)
+    res["gemm_vs_dequantised"] = round(_relerr(d, _mx_decode(qx, sx) @ _mx_decode(qw, sw).t() + bias.float()), 5)
+    res["gemm_vs_fp32"] = round(_relerr(d, x.float() @ w.float().t() + bias.float()), 5)
+    ok = ok and res["quant_roundtrip"] < 6e-2 and res["gemm_vs_dequantised"] < 1e-2 and res["gemm_vs_fp32"] < 6e-2
+    out = dict(ok=ok, **res)
+    if perf:
+        M2, N2, K2 = 8192, 8192, 8192
+        x2, w2 = torch.randn(M2, K2, device="cuda").bfloat16(), torch.randn(N2, K2, device="cuda").bfloat16()
+        qx2, sx2 = lib.quantize_mxfp8(x2); qw2, sw2 = lib.quantize_mxfp8(w2)
+        ms, _ = _time(lambda: lib.gemm_mxfp8(qx2, sx2, qw2, sw2))
+        mq, _ = _time(lambda: lib.quantize_mxfp8(x2))
+        out["perf_8192"] = dict(gemm_ms=round(ms, 4), tflops=round(2.0 * M2 * N2 * K2 / ms / 1e9, 1), quantize_ms=round(mq, 4),
+                                quantize_gbs=round(M2 * K2 * 3 / mq / 1e6, 1))
+    return out
+
+
 CHECKS = {
+    "gemm_mxfp8": check_gemm_mxfp8,
+    "gemm_mxfp8_perf": lambda: check_gemm_mxfp8(perf=True),
     "evoformer_attention": check_evoformer_attention,
     "evoformer_attention_perf": lambda: check_evoformer_attention(perf=True),
     "moe_grouped": check_moe_grouped,
