@@ -3,8 +3,9 @@
 ``Int8Linear``  — W8A8 inference layer: int8 weights with per-output-channel scales (from QAT abs-max statistics or from
                   post-training SmoothQuant), activations quantised per token on the fly (``quantize_rows`` kernel, optional
                   SmoothQuant divisor), product dequantised in the GEMM epilogue.
-``fp8_linear``  — scaled fp8-e4m3 forward GEMM for tensor-parallel training layers (activations per-token scale, weights
-                  per-channel scale); backward runs in bf16 (master path) — "fp8 on the TP GEMMs" of BASELINE config #3.
+``fp8_linear``  — fp8-e4m3 forward GEMM for tensor-parallel training layers; backward runs in bf16 (master path) — "fp8 on the TP GEMMs"
+                  of BASELINE config #3.  Two recipes: ``mx`` (OCP MX block scaling: one E8M0 scale per 32 K-elements, applied by the
+                  tensor core, ``kind::mxf8f6f4.block_scale``) and ``rowwise`` (per-token x per-channel fp32 scales in the epilogue).
 
 CPU / no-native fallbacks emulate the same arithmetic with torch ops so exported models are testable anywhere.
 """
@@ -117,8 +118,48 @@ class _Fp8LinearFn(torch.autograd.Function):
         return gx, gw, gb
 
 
-def fp8_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    if x.is_cuda and x.dtype == torch.bfloat16 and _native.use_native(x) and weight.shape[1] % 16 == 0 and weight.shape[0] % 8 == 0:
+def quantize_mx_reference(x: torch.Tensor) -> torch.Tensor:
+    """OCP MX fp8 (e4m3 elements, one power-of-two scale per 32 consecutive elements of the last dim) — returns the DEQUANTISED tensor in
+    fp32, i.e. what the block-scaled tensor-core GEMM multiplies.  The scale is the smallest power of two that brings the block's maximum
+    inside the e4m3 range; ``csrc/quant_kernels.cu: quantize_mxfp8`` makes the same choice."""
+    shape = x.shape
+    blocks = x.float().reshape(-1, 32)
+    amax = blocks.abs().amax(dim=1, keepdim=True)
+    e = torch.where(amax > 0, torch.ceil(torch.log2(amax / 448.0)), torch.full_like(amax, -127.0)).clamp_(-127, 127)
+    scale = torch.exp2(e)
+    q = (blocks / scale).clamp_(-448.0, 448.0).to(torch.float8_e4m3fn).float()
+    return (q * scale).reshape(shape)
+
+
+class _MxFp8LinearFn(torch.autograd.Function):
+    """Forward GEMM on MX block-scaled fp8 operands (scales applied by the tensor core); backward in bf16 on the saved high-precision
+    operands, like the row-wise recipe."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        lib = _native.require()
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        xq, xs = lib.quantize_mxfp8(x2)
+        wq, ws = lib.quantize_mxfp8(weight.contiguous())
+        y = lib.gemm_mxfp8(xq, xs, wq, ws, bias)
+        OF._count(3)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias, ctx.shape = bias is not None, x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    backward = _Fp8LinearFn.backward
+
+
+def fp8_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, recipe: str = "rowwise") -> torch.Tensor:
+    native = x.is_cuda and x.dtype == torch.bfloat16 and _native.use_native(x)
+    if recipe == "mx" and weight.shape[1] % 128 == 0 and weight.shape[0] % 8 == 0:
+        if native:
+            return _MxFp8LinearFn.apply(x, weight, bias)
+        y = quantize_mx_reference(x.reshape(-1, x.shape[-1])) @ quantize_mx_reference(weight).t()
+        y = y.to(x.dtype).view(*x.shape[:-1], weight.shape[0])
+        exact = torch.nn.functional.linear(x, weight, bias)
+        return exact + (y + (0 if bias is None else bias) - exact).detach()
+    if native and weight.shape[1] % 16 == 0 and weight.shape[0] % 8 == 0:
         return _Fp8LinearFn.apply(x, weight, bias)
     xq, xs = quantize_rows_reference(x.reshape(-1, x.shape[-1]), None, True)
     wq, ws = quantize_rows_reference(weight, None, True)

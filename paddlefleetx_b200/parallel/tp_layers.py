@@ -28,14 +28,19 @@ from . import comm_ops as C
 
 # process-wide defaults taken from the YAML ``Fused`` section (``configure`` is called by the task modules before the model is
 # built): ``tp_comm`` = fused all-gather->GEMM / GEMM->reduce-scatter kernels in the SP linears, ``fp8_tp_gemm`` = forward GEMMs of
-# the tensor-parallel linears in scaled fp8-e4m3 (tcgen05 kind::f8f6f4, per-token / per-channel scales; backward stays bf16)
-_OPTIONS = {"tp_comm": False, "fp8_tp_gemm": False}
+# the tensor-parallel linears in fp8-e4m3, backward in bf16; ``fp8_recipe`` = "mx" (default: OCP MX block scaling, one E8M0 scale per 32
+# K-elements applied by the tensor core, tcgen05 kind::mxf8f6f4.block_scale) or "rowwise" (per-token x per-channel fp32 scales in the epilogue)
+_OPTIONS = {"tp_comm": False, "fp8_tp_gemm": False, "fp8_recipe": "mx"}
 
 
 def configure(fused_cfg=None) -> dict:
     fused_cfg = fused_cfg or {}
     _OPTIONS["tp_comm"] = bool(fused_cfg.get("tp_comm", False))
     _OPTIONS["fp8_tp_gemm"] = bool(fused_cfg.get("fp8_tp_gemm", False))
+    recipe = str(fused_cfg.get("fp8_recipe", "mx")).lower()
+    if recipe not in ("mx", "rowwise"):
+        raise ValueError(f"Fused.fp8_recipe must be 'mx' or 'rowwise', got {recipe!r}")
+    _OPTIONS["fp8_recipe"] = recipe
     return dict(_OPTIONS)
 
 
@@ -47,7 +52,7 @@ def _tp_linear(x: torch.Tensor, weight, bias, owner=None) -> torch.Tensor:
     if _OPTIONS["fp8_tp_gemm"] and x.is_cuda:
         from ..ops.quant import fp8_linear
 
-        return fp8_linear(x, weight, bias)
+        return fp8_linear(x, weight, bias, recipe=_OPTIONS["fp8_recipe"])
     return OF.linear(x, weight, bias)
 
 

@@ -13,7 +13,7 @@ import gpu_selftest as st  # noqa: E402
 FAST = ["gemm_nt_1cta", "gemm_nt_1cta_n128", "gemm_nt_2cta", "gemm_nt_2cta_n128", "gemm_nn_1cta", "gemm_tn_1cta", "gemm_tk_1cta",
         "gemm_nn_2cta", "gemm_tn_2cta", "gemm_tail", "gemm_tail_2cta", "gemm_bias_gelu", "gemm_f32_acc", "gemm_f32", "layernorm",
         "rmsnorm", "gelu_dropout", "cross_entropy", "adamw", "topp", "rope_softmax", "gemv_skinny", "gemm_smallm", "attention_decode", "gemv_w8a8", "decode_fused", "attention_fwd", "fused_ffn", "gemm_int8", "gemm_int8_pair", "gemm_fp8", "gemm_fp8_pair",
-        "gemm_big_sweep", "attention_train", "attention_autograd", "embedding", "norm_residual", "probe_tmem_a", "moe_grouped", "evoformer_attention"]
+        "gemm_big_sweep", "attention_train", "attention_autograd", "embedding", "norm_residual", "probe_tmem_a", "moe_grouped", "evoformer_attention", "gemm_mxfp8"]
 
 
 @pytest.mark.parametrize("name", FAST)

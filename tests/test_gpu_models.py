@@ -41,7 +41,9 @@ def _gpt_batches(cfg, n):
 
 @pytest.mark.parametrize("extra", [[], ["Model.use_recompute=True", "Model.recompute_granularity=full"],
                                    ["Model.use_recompute=True", "Model.recompute_granularity=core_attn"], ["Model.use_rope=True"],
-                                   ["Engine.mix_precision.use_main_grad=True"]])
+                                   ["Engine.mix_precision.use_main_grad=True"],
+                                   ["Fused.fp8_tp_gemm=True"],                                   # MX block-scaled fp8 forward GEMMs (kind::mxf8f6f4.block_scale)
+                                   ["Fused.fp8_tp_gemm=True", "Fused.fp8_recipe=rowwise"]])
 def test_gpt_trains_on_gpu_with_native_kernels(extra):
     from paddlefleetx_b200.ops import functional as OF
 
@@ -53,6 +55,8 @@ def test_gpt_trains_on_gpu_with_native_kernels(extra):
     losses = [float(eng.train_step(batch)) for _ in range(12)]          # same batch: the loss must go down
     assert OF.native_launch_count() > 100, "native kernels were not used"
     assert np.isfinite(losses).all() and losses[-1] < losses[0] - 0.3, losses
+    from paddlefleetx_b200.parallel import tp_layers as _tp
+    _tp.configure({})                              # process-wide options: leave the defaults for the next test
 
 
 def test_moe_gpt_trains_on_gpu():

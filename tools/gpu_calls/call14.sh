@@ -11,5 +11,8 @@ echo "rc=$?"; tail -2 gpurun_out/c14_smoke.log | cut -c1-300
 echo "== bench N=1"
 timeout 600 python bench.py --gpus 1 --steps 8 --warmup 3 > gpurun_out/c14_bench_n1.log 2>&1
 echo "rc=$?"; tail -1 gpurun_out/c14_bench_n1.log | cut -c1-2000
+echo "== mx fp8 perf"
+timeout 300 python tools/gpu_selftest.py gemm_mxfp8_perf gemm_fp8_perf > gpurun_out/c14_mx_perf.log 2>&1
+grep -o "\"perf_8192[^}]*}\|\"tflops[^,]*" gpurun_out/c14_mx_perf.log | head
 echo "== reference arm"
 timeout 120 python bench.py --impl reference --gpus 1 --steps 2 --warmup 1 | tail -1 | cut -c1-400
