@@ -1,3 +1,4 @@
+"""CPU checks of op-level reference implementations (quantisation recipes)."""
 
 
 def test_mx_fp8_reference_quantiser_and_linear():
