@@ -190,8 +190,9 @@ def test_ernie_trains_on_gpu(tmp_path):
     assert len(losses) >= 2 and np.isfinite(losses).all()
 
 
-def test_native_flash_forward_is_used_for_short_unmasked_inference():
-    """attention() routes no-grad, unmasked, dropout-free calls with seq <= 256 to the tcgen05 flash forward and matches SDPA."""
+def test_native_flash_attention_serves_inference_and_training():
+    """attention() routes unmasked bf16 calls (head dim 64 / 128) to the tcgen05 flash kernels: forward without grad, forward + backward with
+    grad (no library kernel), a masked call falls back to SDPA; all three match fp32."""
     import torch.nn.functional as F
 
     from paddlefleetx_b200.ops import attention as A
@@ -205,6 +206,20 @@ def test_native_flash_forward_is_used_for_short_unmasked_inference():
     assert OF.native_launch_count() == 1
     ref = F.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(), v.transpose(1, 2).float(), is_causal=True).transpose(1, 2)
     assert float((y.float() - ref).norm() / ref.norm()) < 1e-2
+    # training path: native forward and backward (64-wide heads included since round 2)
     OF.reset_launch_count()
-    y2 = A.attention(q.requires_grad_(True), k, v, causal=True)          # training path: library forward + backward
-    assert OF.native_launch_count() == 0 and y2.requires_grad
+    qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+    y2 = A.attention(qg, kg, vg, causal=True)
+    assert OF.native_launch_count() >= 1 and y2.requires_grad
+    go = torch.randn_like(y2)
+    y2.backward(go)
+    qf, kf, vf = (t.detach().float().requires_grad_(True) for t in (q, k, v))
+    rf = F.scaled_dot_product_attention(qf.transpose(1, 2), kf.transpose(1, 2), vf.transpose(1, 2), is_causal=True).transpose(1, 2)
+    rf.backward(go.float())
+    for got, want in ((qg.grad, qf.grad), (kg.grad, kf.grad), (vg.grad, vf.grad)):
+        assert float((got.float() - want).norm() / want.norm()) < 2e-2
+    # an explicit mask is library territory
+    OF.reset_launch_count()
+    mask = torch.zeros(2, 1, 200, 200, device="cuda", dtype=torch.bfloat16)
+    y3 = A.attention(q, k, v, attn_mask=mask, causal=False)
+    assert OF.native_launch_count() == 0 and y3.shape == y.shape
