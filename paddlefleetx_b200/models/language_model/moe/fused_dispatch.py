@@ -25,13 +25,40 @@ from ....parallel.symmetric_memory import get_allocator
 ALIGN = 256      # expert blocks start on 256-row boundaries: a 2-CTA (256-row) GEMM tile never straddles two experts
 
 
+class _LocalMemory:
+    """The symmetric-allocator surface for an expert group of ONE rank: the dispatch / combine kernels then "exchange" with themselves, and
+    the layer still gets the device-side routing, the expert-major layout and the grouped expert GEMMs (no per-expert loop, no host sync)."""
+
+    def __init__(self, device):
+        self.device = device
+        self._keep = []
+
+    def alloc_tensor(self, numel: int, dtype: torch.dtype, device=None) -> torch.Tensor:
+        t = torch.zeros(numel, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def empty(self, shape, dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        return self.alloc_tensor(n, dtype).view(*shape)
+
+    def peer_ptrs(self, t: torch.Tensor):
+        return [t.data_ptr()]
+
+    def barrier(self, channel: int = 0) -> None:
+        return None
+
+
 class MoEDispatcher:
     def __init__(self, group, hidden: int, e_local: int, dtype: torch.dtype, capacity_factor: float = 2.0, num_ctas: int = 0):
-        self.group, self.world, self.rank = group, group.nranks, group.rank
+        self.group = group
+        self.world, self.rank = (group.nranks, group.rank) if group is not None else (1, 0)
         self.hidden, self.e_local, self.dtype = hidden, e_local, dtype
         self.capacity_factor = capacity_factor
         self.lib = _native.require()
-        self.alloc = get_allocator(group)
+        self.alloc = get_allocator(group) if self.world > 1 else _LocalMemory(torch.device("cuda", torch.cuda.current_device()))
         dev = self.alloc.device
         e_total = self.world * e_local
         self.cnt = self.alloc.alloc_tensor(self.world * e_total, torch.int32)

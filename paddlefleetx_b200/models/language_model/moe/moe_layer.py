@@ -153,7 +153,7 @@ class MoELayer(nn.Module):
         if mp_world > 1:
             x = Slice.apply(x, self.mp_group.rank, mp_world, self.mp_group)
         value, gate_idx = self.gate(x)
-        if self.fused_p2p and x.is_cuda and self.world_size > 1:
+        if self.fused_p2p and x.is_cuda and (self.world_size > 1 or self.grouped is not None):
             out = self._forward_p2p(x, value, gate_idx)
             if mp_world > 1:
                 out = AllGather.apply(out, self.mp_group.rank, mp_world, self.mp_group)

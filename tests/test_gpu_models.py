@@ -59,12 +59,48 @@ def test_gpt_trains_on_gpu_with_native_kernels(extra):
     _tp.configure({})                              # process-wide options: leave the defaults for the next test
 
 
-def test_moe_gpt_trains_on_gpu():
-    cfg = C.get_config(os.path.join(CFG, "nlp/moe/pretrain_moe_345M_single_card.yaml"), SMALL_GPT, nranks=1)
+@pytest.mark.parametrize("fused", [False, True])
+def test_moe_gpt_trains_on_gpu(fused):
+    """fused=True: device-side routing + dispatch kernel + grouped expert GEMMs from the device-side segment table + combine kernel — the
+    sync-free MoE layer, here with an expert group of one rank (the multi-rank exchange is covered by tools/gpu_multi_selftest.py)."""
+    cfg = C.get_config(os.path.join(CFG, "nlp/moe/pretrain_moe_345M_single_card.yaml"), SMALL_GPT + [f"Model.moe_configs.fused_p2p={fused}"], nranks=1)
     eng = _engine(cfg)
+    if fused:
+        from paddlefleetx_b200.models.language_model.moe.moe_layer import MoELayer
+
+        layers = [m for m in eng._module.model.modules() if isinstance(m, MoELayer)]
+        assert layers and all(m.grouped is not None for m in layers), "the grouped expert path was not built"
     batch = _gpt_batches(cfg, 1)[0]
     losses = [float(eng.train_step(batch)) for _ in range(6)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0], losses
+
+
+def test_moe_layer_sync_free_path_matches_the_expert_loop_on_one_gpu():
+    from paddlefleetx_b200.models.language_model.moe.moe_layer import ExpertLayer, MoELayer
+
+    def make(fused):
+        torch.manual_seed(3)
+        ex = [ExpertLayer(256, 1024, dtype=torch.bfloat16, device="cuda") for _ in range(4)]
+        return MoELayer(256, ex, gate={"type": "naive", "top_k": 2}, dtype=torch.bfloat16, device="cuda", fused_p2p=fused)
+
+    ref, fus = make(False), make(True)
+    fus.load_state_dict(ref.state_dict())
+    torch.manual_seed(5)
+    x = (torch.randn(1000, 256, device="cuda") * 0.5).bfloat16()
+    go = (torch.randn(1000, 256, device="cuda") * 0.1).bfloat16()
+    outs = []
+    for layer in (ref, fus):
+        xi = x.clone().requires_grad_(True)
+        y = layer(xi)
+        y.backward(go)
+        sd_grads = {n: p.grad.float() for n, p in layer.named_parameters() if p.grad is not None}
+        outs.append((y.detach().float(), xi.grad.float(), sd_grads))
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-12))
+    assert rel(outs[1][0], outs[0][0]) < 2e-2 and rel(outs[1][1], outs[0][1]) < 2e-2
+    w1 = torch.stack([outs[0][2][f"experts.{e}.htoh4.weight"] for e in range(4)])
+    assert rel(outs[1][2]["grouped.w1"], w1) < 2e-2
+    b2 = torch.stack([outs[0][2][f"experts.{e}.h4toh.bias"] for e in range(4)])
+    assert rel(outs[1][2]["grouped.b2"], b2) < 2e-2
 
 
 def test_generation_cuda_graph_matches_eager_on_gpu():
