@@ -815,6 +815,36 @@ std::vector<at::Tensor> evoformer_attention_fwd(const at::Tensor& q, const at::T
   return {out, lse};
 }
 
+// Evoformer gated attention backward: returns (dq, dk, dv, dgate or empty, dpair fp32 or empty)
+std::vector<at::Tensor> evoformer_attention_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& out, const at::Tensor& dout,
+                                                const at::Tensor& lse, c10::optional<at::Tensor> mask_bias, c10::optional<at::Tensor> pair_bias,
+                                                c10::optional<at::Tensor> gate, int64_t groups_per_pair, double scale, bool need_dpair) {
+  TORCH_CHECK(q.is_cuda() && q.dim() == 4 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous() && out.is_contiguous() && dout.is_contiguous() &&
+              q.scalar_type() == at::kBFloat16 && dout.scalar_type() == at::kBFloat16 && out.sizes() == q.sizes() && dout.sizes() == q.sizes(),
+              "evoformer_attention_bwd: contiguous bf16 [G, S, H, 32] operands");
+  const int64_t G = q.size(0), Sq = q.size(1), H = q.size(2), Sk = k.size(1);
+  TORCH_CHECK(q.size(3) == 32 && H % 2 == 0 && lse.scalar_type() == at::kFloat && lse.numel() == G * H * Sq, "evoformer_attention_bwd: shapes");
+  const c10::cuda::CUDAGuard guard(q.device());
+  const bool has_gate = gate.has_value() && gate->defined(), has_pb = pair_bias.has_value() && pair_bias->defined(), has_mb = mask_bias.has_value() && mask_bias->defined();
+  if (has_mb) TORCH_CHECK(mask_bias->scalar_type() == at::kFloat && mask_bias->is_contiguous() && mask_bias->numel() == G * Sk, "mask_bias fp32 [G, Sk]");
+  if (has_pb) TORCH_CHECK(pair_bias->scalar_type() == at::kBFloat16 && pair_bias->is_contiguous() && pair_bias->numel() == (G / groups_per_pair) * H * Sq * Sk, "pair_bias");
+  if (has_gate) TORCH_CHECK(gate->scalar_type() == at::kBFloat16 && gate->is_contiguous() && gate->numel() == q.numel(), "gate");
+  auto fopt = q.options().dtype(at::kFloat);
+  at::Tensor dq = at::empty_like(q), dk = at::empty_like(k), dv = at::empty_like(v);
+  at::Tensor dgate = has_gate ? at::empty_like(q) : at::empty({0}, q.options());
+  at::Tensor dpair = (has_pb && need_dpair) ? at::zeros({G / groups_per_pair, H, Sq, Sk}, fopt) : at::empty({0}, fopt);
+  at::Tensor do_pre = at::empty_like(q), dq_acc = at::empty({G, Sq, H, 32}, fopt);
+  const int64_t sq_pad = (Sq + 63) / 64 * 64;
+  at::Tensor lse2 = at::empty({G * H, sq_pad}, fopt), delta = at::empty({G * H, sq_pad}, fopt);
+  PFX_CUDA_CHECK(pfx::evoformer_attention_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), has_gate ? gate->data_ptr() : nullptr,
+                                              lse.data_ptr<float>(), has_mb ? mask_bias->data_ptr<float>() : nullptr, has_pb ? pair_bias->data_ptr() : nullptr,
+                                              dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), has_gate ? dgate.data_ptr() : nullptr,
+                                              dpair.numel() ? dpair.data_ptr<float>() : nullptr, do_pre.data_ptr(), dq_acc.data_ptr<float>(),
+                                              lse2.data_ptr<float>(), delta.data_ptr<float>(), (int)G, (int)Sq, (int)Sk, (int)H, (int)groups_per_pair,
+                                              (float)scale, cur_stream()));
+  return {dq, dk, dv, dgate, dpair};
+}
+
 // tile table + K segments of the grouped expert GEMMs, from the dispatch kernel's segment table (all on the device)
 std::vector<at::Tensor> moe_tile_table(const at::Tensor& seg, int64_t e_local, int64_t align, int64_t cap_rows, at::Tensor& sticky) {
   TORCH_CHECK(seg.is_cuda() && seg.scalar_type() == at::kInt && seg.numel() == 2 * e_local + 2 && sticky.scalar_type() == at::kInt, "moe_tile_table: bad seg");
@@ -944,6 +974,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("quantize_mxfp8", &quantize_mxfp8);
   m.def("gemm_mxfp8", &gemm_mxfp8, py::arg("a"), py::arg("sfa"), py::arg("b"), py::arg("sfb"), py::arg("bias") = py::none());
   m.def("evoformer_attention_fwd", &evoformer_attention_fwd);
+  m.def("evoformer_attention_bwd", &evoformer_attention_bwd);
   m.def("gemm_grouped", &gemm_grouped, py::arg("a"), py::arg("b"), py::arg("bias"), py::arg("tile_group"), py::arg("out"), py::arg("b_kmajor") = true,
         py::arg("epilogue") = 0, py::arg("out2") = py::none(), py::arg("aux") = py::none(), py::arg("row_align") = 128);
   m.def("gemm_grouped_wgrad", &gemm_grouped_wgrad);

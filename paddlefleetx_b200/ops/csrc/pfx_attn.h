@@ -32,4 +32,11 @@ cudaError_t attention_bwd(const AttnView& q, const AttnView& k, const AttnView& 
 cudaError_t evoformer_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const float* mask_bias, const void* pair_bias,
                                     const void* gate, int G, int Sq, int Sk, int H, int groups_per_pair, float scale, cudaStream_t st);
 
+// Backward of the above.  do_pre (bf16 like q), dq_acc (fp32 like q), lse2 / delta (fp32 [G*H, round_up(Sq, 64)]) are workspaces; dpair is an
+// fp32 accumulator [G / groups_per_pair, H, Sq, Sk] zeroed by the caller (null = no pair-bias gradient); dgate may be null when gate is.
+cudaError_t evoformer_attention_bwd(const void* q, const void* k, const void* v, const void* out, const void* dout, const void* gate, const float* lse,
+                                    const float* mask_bias, const void* pair_bias, void* dq, void* dk, void* dv, void* dgate, float* dpair,
+                                    void* do_pre, float* dq_acc, float* lse2, float* delta, int G, int Sq, int Sk, int H, int groups_per_pair,
+                                    float scale, cudaStream_t st);
+
 }  // namespace pfx

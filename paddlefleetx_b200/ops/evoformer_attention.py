@@ -3,14 +3,16 @@
     out[g, q, h, :] = softmax_k(scale * q.k + mask_bias[g, k] + pair_bias[g // groups_per_pair, h, q, k]) @ v * sigmoid(gate)
 
 Forward: one tcgen05 kernel (``csrc/evoformer_attn_sm100.cu``) — logits, both biases, softmax, P V and the gate never leave the chip; only the
-output and the row-wise log-sum-exp are written.  Backward: recomputation from (q, k, v, biases, lse) in group chunks with library matmuls —
-the [g, h, q, k] probabilities exist for one chunk at a time instead of being stored for every attention of the trunk (the reference keeps
-logits, probabilities and the gated average of all 48 blocks x 6 attentions alive).
+output and the row-wise log-sum-exp are written.  Backward: a second tcgen05 kernel recomputes the probabilities per tile from (q, k, biases,
+lse) and produces dq / dk / dv / dgate and the pair-bias gradient (fp32 reductions over the groups that share a bias); nothing of size
+[g, h, q, k] is ever stored (the reference keeps logits, probabilities and the gated average of all 48 blocks x 6 attentions alive).
+``PFX_EVO_BWD=torch`` selects the older chunked recomputation with library matmuls (also used when the mask bias needs a gradient).
 
 CPU / unsupported shapes fall back to the plain PyTorch expression, which is also the numerics reference of the tests.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -18,6 +20,7 @@ import torch
 from . import _native
 
 _CHUNK_ELEMS = 1 << 27          # probabilities materialised per backward chunk (fp32 elements)
+_BWD = os.environ.get("PFX_EVO_BWD", "native")      # "native" = tcgen05 backward kernel, "torch" = chunked recomputation with library matmuls
 
 
 def reference(q, k, v, mask_bias, pair_bias, gate, groups_per_pair: int, scale: float):
@@ -51,7 +54,7 @@ class _EvoAttnFn(torch.autograd.Function):
         gt = None if gate is None else gate.contiguous()
         out, lse = lib.evoformer_attention_fwd(q, k, v, mb, pb, gt, groups_per_pair, scale)
         ctx.save_for_backward(q, k, v, mb if mb is not None else q.new_empty(0), pb if pb is not None else q.new_empty(0),
-                              gt if gt is not None else q.new_empty(0), lse)
+                              gt if gt is not None else q.new_empty(0), lse, out)
         ctx.flags = (mask_bias is not None, pair_bias is not None, gate is not None)
         ctx.gpp, ctx.scale = groups_per_pair, scale
         ctx.bias_dtypes = (None if mask_bias is None else mask_bias.dtype, None if pair_bias is None else pair_bias.dtype)
@@ -59,12 +62,22 @@ class _EvoAttnFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, mb, pb, gt, lse = ctx.saved_tensors
+        q, k, v, mb, pb, gt, lse = ctx.saved_tensors[:7]
         has_mb, has_pb, has_gate = ctx.flags
         gpp, scale = ctx.gpp, ctx.scale
         G, Sq, H, D = q.shape
         Sk = k.shape[1]
         dout = dout.contiguous()
+        need_mb = has_mb and ctx.needs_input_grad[3]
+        if _BWD == "native" and q.is_cuda and len(ctx.saved_tensors) == 8 and not need_mb:
+            # one tcgen05 kernel (csrc/evoformer_attn_sm100.cu): five products per (group, head, key tile), pair-bias gradient by fp32 reds
+            lib = _native.require()
+            out = ctx.saved_tensors[7]
+            need_pb = has_pb and ctx.needs_input_grad[4]
+            dq, dk, dv, dgate, dpair = lib.evoformer_attention_bwd(q, k, v, out, dout, lse, mb if has_mb else None, pb if has_pb else None,
+                                                                   gt if has_gate else None, gpp, scale, need_pb)
+            mb_dt, pb_dt = ctx.bias_dtypes
+            return (dq, dk, dv, None, dpair.to(pb_dt) if need_pb else None, dgate if has_gate else None, None, None)
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
         dgate = torch.empty_like(gt) if has_gate else None
         need_pb = has_pb and ctx.needs_input_grad[4]
