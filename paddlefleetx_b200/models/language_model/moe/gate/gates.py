@@ -95,7 +95,7 @@ class SwitchGate(NaiveGate):
         valid = (top1_idx >= 0).sum().clamp(min=1).float()
         frac_expert = torch.zeros(self.tot_expert, dtype=torch.float32, device=inp.device)
         ok = top1_idx.reshape(-1) >= 0
-        frac_expert.index_add_(0, top1_idx.reshape(-1)[ok], torch.ones(int(ok.sum()), dtype=torch.float32, device=inp.device))
+        frac_expert.index_add_(0, top1_idx.reshape(-1).clamp(min=0), ok.float())                     # dropped slots add 0 (no host sync)
         frac_expert = frac_expert / valid
         prob_expert = score.sum(0) / valid
         self.set_loss((frac_expert * prob_expert).sum() * self.tot_expert)
