@@ -869,8 +869,29 @@ def check_evoformer_attention(perf=False):
                 return o.transpose(1, 2) * torch.sigmoid(gate)
             ms_sdpa, _ = _time(sdpa)
             flops = 4.0 * G * H * Sq * Sk * 32
+            # forward + backward through autograd: native kernel pair vs the chunked recomputation vs SDPA autograd with a materialised mask
+            leaves = [t.clone().requires_grad_(True) for t in (q, k, v, pair, gate)]
+            go = torch.randn_like(out)
+
+            def fb():
+                for t in leaves:
+                    t.grad = None
+                EA.evoformer_attention(leaves[0], leaves[1], leaves[2], mask, leaves[3], leaves[4], gpp).backward(go)
+            ms_fb, _ = _time(fb)
+            EA._BWD = "torch"
+            ms_fb_torch, _ = _time(fb)
+            EA._BWD = "native"
+
+            def sdpa_fb():
+                for t in leaves:
+                    t.grad = None
+                m = mask.view(G, 1, 1, Sk) + leaves[3].float().repeat_interleave(gpp, 0)
+                o = torch.nn.functional.scaled_dot_product_attention(leaves[0].transpose(1, 2), leaves[1].transpose(1, 2), leaves[2].transpose(1, 2), attn_mask=m.to(q.dtype))
+                (o.transpose(1, 2) * torch.sigmoid(leaves[4])).backward(go)
+            ms_fb_sdpa, _ = _time(sdpa_fb)
             res[name] = dict(ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), eager_fp32_ms=round(ms_ref, 4), sdpa_masked_ms=round(ms_sdpa, 4),
-                             err=round(_relerr(out, eager()), 5))
+                             err=round(_relerr(out, eager()), 5), fwd_bwd_ms=round(ms_fb, 4), fwd_bwd_chunked_torch_ms=round(ms_fb_torch, 4),
+                             fwd_bwd_sdpa_ms=round(ms_fb_sdpa, 4))
             continue
         leaves = [t.clone().requires_grad_(True) for t in (q, k, v)] + [t.clone().requires_grad_(True) if t is not None else None for t in (pair, gate)]
         out = EA.evoformer_attention(leaves[0], leaves[1], leaves[2], mask, leaves[3], leaves[4], gpp)
