@@ -52,3 +52,23 @@ def test_views_follow_repointed_storage():
     seg2 = [0, 3, 3, 0, 3, 5]
     out = reference_grouped_ffn(torch.randn(8, 128), seg2, ge)
     assert out.shape == (8, 128) and torch.isfinite(out).all()
+
+
+def test_gate_bookkeeping_is_sync_free_and_exact():
+    """number_count / prune_gate_by_capacity without boolean indexing or bincount (both force a device->host wait on CUDA): same results
+    as the obvious formulation, dropped slots (-1) ignored."""
+    from paddlefleetx_b200.models.language_model.moe import utils as U
+
+    torch.manual_seed(0)
+    g = torch.randint(-1, 8, (100, 2))
+    flat = g.reshape(-1)
+    assert torch.equal(U.number_count(g, 8), torch.bincount(flat[flat >= 0], minlength=8))
+    cap = torch.tensor([5, 3, 100, 0, 7, 2, 9, 1])
+    out = U.prune_gate_by_capacity(g, cap, 8, 1).reshape(-1)
+    seen, want = [0] * 8, []
+    for v in flat.tolist():
+        keep = v >= 0 and seen[v] < int(cap[v])
+        if keep:
+            seen[v] += 1
+        want.append(v if keep else -1)
+    assert out.tolist() == want
