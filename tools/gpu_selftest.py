@@ -977,7 +977,45 @@ def check_gemm_mxfp8(perf=False):
     return out
 
 
+def check_sync_audit():
+    """Host <-> device synchronisations inside a training step, found with torch's sync debug mode: steps of a small GPT and of a small
+    GPT-MoE on the sync-free path (expert group of one rank).  Reports every distinct Python call site that made the host wait."""
+    import collections
+    import traceback
+    import warnings
+
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_gpu_models as T                     # reuse the tiny recipes and the engine builder
+    from paddlefleetx_b200.utils import config as C
+
+    out, ok = {}, True
+    for name, recipe, extra in (("gpt", "nlp/gpt/pretrain_gpt_345M_single_card.yaml", []),
+                                ("moe_sync_free", "nlp/moe/pretrain_moe_345M_single_card.yaml", ["Model.moe_configs.fused_p2p=True"])):
+        cfg = C.get_config(os.path.join(T.CFG, recipe), T.SMALL_GPT + extra, nranks=1)
+        eng = T._engine(cfg)
+        batch = [t.cuda() for t in T._gpt_batches(cfg, 1)[0]]
+        for _ in range(3):
+            eng.train_step(batch)                   # warm-up: lazy initialisation may sync
+        torch.cuda.synchronize()
+        sites = collections.Counter()
+        torch.cuda.set_sync_debug_mode(1)
+        try:
+            with warnings.catch_warnings(record=True) as rec:
+                warnings.simplefilter("always")
+                for _ in range(2):
+                    loss = eng.train_step(batch)
+                n_warn = len(rec)
+                for w in rec:
+                    sites[f"{os.path.relpath(w.filename, ROOT) if w.filename.startswith(ROOT) else os.path.basename(w.filename)}:{w.lineno}"] += 1
+        finally:
+            torch.cuda.set_sync_debug_mode(0)
+        out[name] = dict(syncs_in_2_steps=n_warn, sites=dict(sites.most_common(12)), loss=float(loss))
+    return dict(ok=ok, **out)
+
+
 CHECKS = {
+    "sync_audit": check_sync_audit,
     "gemm_mxfp8": check_gemm_mxfp8,
     "gemm_mxfp8_perf": lambda: check_gemm_mxfp8(perf=True),
     "evoformer_attention": check_evoformer_attention,
