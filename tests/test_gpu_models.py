@@ -270,14 +270,14 @@ def test_evoformer_block_runs_on_the_native_attention_kernels(monkeypatch):
 
     torch.manual_seed(0)
     dev = "cuda"
-    blk = EvoformerIteration(c_m=256, c_z=128, msa_heads=8, pair_heads=4, dropout_msa=0.0, dropout_pair=0.0).to(dev).bfloat16()
+    blk = EvoformerIteration(c_m=256, c_z=128, msa_heads=8, pair_heads=4, dropout_msa=0.0, dropout_pair=0.0).to(dev)      # fp32 parameters + bf16 autocast, as the folding recipes run it
     with torch.no_grad():                           # the reference zero-initialises the output projections: give the attention a voice
         for n, p in blk.named_parameters():
             if n.endswith("o.weight") or n.endswith("g.weight"):
                 p.normal_(0, 0.02)
     S, R = 6, 96
-    msa = (torch.randn(1, S, R, 256, device=dev) * 0.5).bfloat16()
-    pair = (torch.randn(1, R, R, 128, device=dev) * 0.5).bfloat16()
+    msa = torch.randn(1, S, R, 256, device=dev) * 0.5
+    pair = torch.randn(1, R, R, 128, device=dev) * 0.5
     msa_mask = (torch.rand(1, S, R, device=dev) > 0.1).float()
     pair_mask = (torch.rand(1, R, R, device=dev) > 0.1).float()
     calls = {"native": 0}
@@ -291,7 +291,8 @@ def test_evoformer_block_runs_on_the_native_attention_kernels(monkeypatch):
 
     def run():
         m, z = msa.clone().requires_grad_(True), pair.clone().requires_grad_(True)
-        mo, zo = blk(m, z, msa_mask, pair_mask)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            mo, zo = blk(m, z, msa_mask, pair_mask)
         (mo.float().square().mean() + zo.float().square().mean()).backward()
         return mo.detach().float(), zo.detach().float(), m.grad.float(), z.grad.float()
 
