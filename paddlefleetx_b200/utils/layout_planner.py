@@ -15,7 +15,7 @@ Cost model (per optimizer step, one GPU's view; every constant is a measurement 
 * attention — flash kernels at their measured rate with dropout (fwd ~315, bwd ~310 TFLOP/s causal, profiles/r2).
 * elementwise / norm / optimizer traffic — bytes over measured HBM copy bandwidth.
 * tensor parallel — 8 collectives per layer per micro-batch of ``tokens x h`` bf16 over NVLink (measured ~620 GB/s per direction);
-  the fused GEMM+collective kernels hide ~65 % of it (profiles: fused 0.125 ms vs GEMM 0.098 + NCCL 0.104), NCCL hides none.
+  in the full step about one wire time stays exposed with the fused GEMM+collective kernels and 1.6 with NCCL (2-GPU 6.7B runs).
 * pipeline — 1F1B bubble ``(pp - 1) / (m + pp - 1)`` plus the boundary activations.
 * data parallel / ZeRO — reduce-scatter + all-gather of the local parameters, overlapped with backward / the next forward; what the
   exposed-communication meter measures at sharding8 (4 ms of a 13 GB exchange) fixes the hidden fraction at 0.9.  Stage 3 adds a
@@ -27,7 +27,6 @@ per layer (calibrated: 6.7B, 8192 tokens, no recompute -> ~20 GB), logits, pipel
 from __future__ import annotations
 
 import json
-import math
 import os
 from dataclasses import asdict, dataclass, field
 from typing import Dict, Iterable, List, Optional
@@ -162,8 +161,13 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
     tp = 0.0
     if mp > 1:
         vol = 8.0 * layers_local * tokens * s.hidden * 2.0 * (mp - 1) / mp
-        tp = vol / hw.link_bw * (0.35 if plan.fused_tp else 1.0) + (0 if plan.fused_tp else 8.0 * layers_local * 12e-6)
+        # exposure calibrated on the 2-GPU 6.7B runs (profiles/r2/bench_c6_mp2_*): +38 ms per step with the fused kernels, +51 ms with NCCL,
+        # for 27.7 ms of wire time — the micro-benchmarks hide 60-70 % of a single collective, the full backward (re-gather + two GEMMs per
+        # collective, smaller N / K) does not
+        tp = vol / hw.link_bw * (1.0 if plan.fused_tp else 1.6) + (0 if plan.fused_tp else 8.0 * layers_local * 12e-6)
     pipe_p2p = 0.0 if pp == 1 else 2.0 * tokens * s.hidden * 2.0 / (mp if plan.sequence_parallel else 1) / hw.link_bw + 4 * 15e-6
+    if pp > 1:
+        per_micro *= 1.15            # blocking stage-to-stage transfers and ~7 k launches per step at micro-batch granularity (c15_bench_n8.json, named_layout)
     compute = n_micro * (per_micro + tp + pipe_p2p)
     bubble = compute * (pp - 1) / max(n_micro, 1) if pp > 1 else 0.0
     # gradient reduce-scatter + parameter all-gather of this rank's parameters over the data ranks (bf16 both ways)
@@ -204,6 +208,8 @@ def _divisors(n: int) -> List[int]:
 
 
 def enumerate_plans(s: ModelShape, world: int, local_batch: int, stages: Iterable[int] = (1, 2, 3), allow_pp: bool = True) -> List[Plan]:
+    """Every (mp, pp, sharding, dp, stage, micro-batch, recompute) combination the parallel layers support for this model and world size.
+    ``local_batch`` is the per-GPU batch: a data rank of an (mp, pp) layout carries ``local_batch * mp * pp`` sequences."""
     out = []
     for mp in _divisors(world):
         if s.heads % mp or s.hidden % mp or s.vocab % mp or mp > 8:
@@ -212,13 +218,14 @@ def enumerate_plans(s: ModelShape, world: int, local_batch: int, stages: Iterabl
             if s.layers % pp or (pp > 1 and not allow_pp):
                 continue
             rest = world // (mp * pp)
+            rank_batch = local_batch * mp * pp
             for sd in _divisors(rest):
                 dp = rest // sd
                 for stage in (stages if sd > 1 else (1,)):
                     if stage == 3 and pp > 1:
                         continue                                           # the stage-3 wrapper and the pipeline schedule are not combined
-                    for mb in _divisors(local_batch * mp * pp if False else local_batch):
-                        n_micro = local_batch // mb
+                    for mb in _divisors(rank_batch):
+                        n_micro = rank_batch // mb
                         if pp > 1 and n_micro < pp:
                             continue
                         for rc in ("none", "core_attn", "full"):
@@ -234,14 +241,10 @@ def plan_layouts(s: ModelShape, world: int, local_batch: int, hw: Optional[Hardw
     hw = hw or Hardware.measured()
     limit = mem_limit_gb if mem_limit_gb is not None else 0.92 * hw.mem_gb
     plans = []
-    for mp_pp_batch in (None,):
-        for p in enumerate_plans(s, world, local_batch, **kw):
-            lb = local_batch * p.mp * p.pp
-            # micro-batch candidates were enumerated over divisors of local_batch; scale the accumulation to the rank's batch
-            p.accumulate = max(lb // p.micro_batch, 1)
-            estimate(s, hw, world, lb, p)
-            if p.est_mem_gb <= limit:
-                plans.append(p)
+    for p in enumerate_plans(s, world, local_batch, **kw):
+        estimate(s, hw, world, local_batch * p.mp * p.pp, p)
+        if p.est_mem_gb <= limit:
+            plans.append(p)
     plans.sort(key=lambda p: (p.est_step_s, p.est_mem_gb))
     seen, uniq = set(), []
     for p in plans:                                                       # one entry per layout: its best micro-batch / recompute
@@ -297,4 +300,3 @@ if __name__ == "__main__":      # python -m paddlefleetx_b200.utils.layout_plann
     shape = ModelShape(layers=L, hidden=h, heads=a, vocab=50304, ffn=4 * h, seq=int(sys.argv[3]) if len(sys.argv) > 3 else 1024)
     print(f"GPT {name}: {shape.params / 1e9:.2f} B parameters, {world} GPUs, 8 sequences / GPU")
     print(explain(plan_layouts(shape, world, 8), 12))
-    _ = math
