@@ -51,6 +51,36 @@ def default_decay_fn(name: str, p: torch.nn.Parameter) -> bool:
     return not (p.ndim <= 1 or lname.endswith("bias") or "norm" in lname)
 
 
+_STACKED_EXPERT = {"w1": ("htoh4", "weight"), "b1": ("htoh4", "bias"), "w2": ("h4toh", "weight"), "b2": ("h4toh", "bias")}
+
+
+def _named_entry(named: dict, name: str) -> dict:
+    """Per-parameter optimizer state by name, across the two spellings of MoE expert parameters: a layer on the grouped-GEMM path owns
+    stacked tensors (``...grouped.w1`` = [E, 4h, h]) while the expert-loop path (and every checkpoint's model file) names them per expert
+    (``...experts.3.htoh4.weight``).  State saved under one spelling loads into the other."""
+    if name in named:
+        return named[name]
+    parts = name.split(".")
+    if len(parts) >= 2 and parts[-2] == "grouped" and parts[-1] in _STACKED_EXPERT:       # want stacked, have per expert
+        lin, attr = _STACKED_EXPERT[parts[-1]]
+        prefix = ".".join(parts[:-2])
+        prefix = prefix + "." if prefix else ""
+        per, e = [], 0
+        while f"{prefix}experts.{e}.{lin}.{attr}" in named:
+            per.append(named[f"{prefix}experts.{e}.{lin}.{attr}"])
+            e += 1
+        if per:
+            return {k: (torch.stack([st[k] for st in per]) if all(st.get(k) is not None for st in per) else None) for k in ("moment1", "moment2", "master")}
+    if len(parts) >= 4 and parts[-4] == "experts" and parts[-3].isdigit():                  # want per expert, have stacked
+        lin, attr = parts[-2], parts[-1]
+        stacked = next((k for k, v in _STACKED_EXPERT.items() if v == (lin, attr)), None)
+        key = ".".join(parts[:-4] + ["grouped", stacked]) if stacked else None
+        if key in named:
+            e = int(parts[-3])
+            return {k: (v[e] if v is not None else None) for k, v in named[key].items() if k in ("moment1", "moment2", "master")}
+    raise KeyError(f"optimizer state has no entry for parameter {name!r}")
+
+
 class FusedAdamW:
     def __init__(self, learning_rate, parameters=None, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8,
                  weight_decay: float = 0.01, grad_clip=None, multi_precision: bool = False, tensor_fusion: bool = True,
@@ -704,7 +734,7 @@ class FusedAdamW:
                 a, b = max(off, lo), min(off + n, hi)
                 if a >= b:
                     continue
-                st = named[self._names[id(p)]]
+                st = _named_entry(named, self._names[id(p)])
                 for key, dst in (("moment1", g.meta["m"]), ("moment2", g.meta["v"]), ("master", g.meta["master"] if g.meta["has_master"] else None)):
                     if dst is None or st.get(key) is None:
                         continue

@@ -72,3 +72,24 @@ def test_gate_bookkeeping_is_sync_free_and_exact():
             seen[v] += 1
         want.append(v if keep else -1)
     assert out.tolist() == want
+
+
+def test_named_optimizer_state_crosses_the_two_expert_spellings():
+    """Universal (named) optimizer checkpoints: state written by an expert-loop run loads into a grouped-GEMM run and back."""
+    from paddlefleetx_b200.optims.optimizer import _named_entry
+
+    E, names = 3, {"w1": ("htoh4", "weight", (3, 8, 4)), "b2": ("h4toh", "bias", (3, 4))}
+    per = {}
+    for e in range(E):
+        per[f"layers.2.moe.experts.{e}.htoh4.weight"] = {"moment1": torch.full((8, 4), float(e)), "moment2": torch.full((8, 4), e + 0.5), "master": None}
+        per[f"layers.2.moe.experts.{e}.h4toh.bias"] = {"moment1": torch.full((4,), float(e)), "moment2": torch.full((4,), e + 0.5), "master": torch.full((4,), e + 0.25)}
+    st = _named_entry(per, "layers.2.moe.grouped.w1")
+    assert st["moment1"].shape == (3, 8, 4) and float(st["moment1"][2, 0, 0]) == 2.0 and st["master"] is None
+    st = _named_entry(per, "layers.2.moe.grouped.b2")
+    assert st["master"].shape == (3, 4) and float(st["master"][1, 0]) == 1.25
+    stacked = {"layers.2.moe.grouped.w1": {"moment1": torch.arange(3.0).view(3, 1, 1).expand(3, 8, 4), "moment2": torch.zeros(3, 8, 4), "master": None}}
+    st = _named_entry(stacked, "layers.2.moe.experts.1.htoh4.weight")
+    assert st["moment1"].shape == (8, 4) and float(st["moment1"][0, 0]) == 1.0
+    import pytest
+    with pytest.raises(KeyError):
+        _named_entry(stacked, "layers.2.moe.experts.1.h4toh.weight")
