@@ -41,6 +41,8 @@ class GroupedExperts(nn.Module):
             par = nn.Parameter(t)
             par.is_expert = True
             par.no_sync = True
+            if attr == "bias":
+                par.no_weight_decay = True      # a stacked bias is 2-D and is not called "...bias": keep it out of weight decay like the per-expert biases
             setattr(self, stacked, par)
         for ex in experts:                      # the stacks are the parameters now
             for _, lin, attr in self.NAMES:

@@ -93,3 +93,13 @@ def test_named_optimizer_state_crosses_the_two_expert_spellings():
     import pytest
     with pytest.raises(KeyError):
         _named_entry(stacked, "layers.2.moe.experts.1.h4toh.weight")
+
+
+def test_stacked_expert_biases_stay_out_of_weight_decay():
+    from paddlefleetx_b200.optims.optimizer import default_decay_fn
+
+    plain, grouped = _layer(False), _layer(True)
+    decayed = lambda layer: sorted(n for n, p in layer.named_parameters() if default_decay_fn(n, p))
+    assert all("bias" not in n for n in decayed(plain))
+    g = decayed(grouped)
+    assert "grouped.w1" in g and "grouped.w2" in g and "grouped.b1" not in g and "grouped.b2" not in g
