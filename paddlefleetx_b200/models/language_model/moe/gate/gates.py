@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .....parallel import comm_ops as C
-from ..utils import limit_by_capacity, random_routing
+from ..utils import limit_by_capacity, number_count, random_routing
 
 
 class BaseGate(nn.Module):
@@ -62,13 +62,14 @@ class GShardGate(NaiveGate):
     def forward(self, x):
         topk_val, topk_idx, score = super().forward(x, return_all_scores=True)
         s = score.shape[0]
-        c_e = torch.zeros(self.tot_expert, dtype=torch.float32, device=x.device)
-        c_e.index_add_(0, topk_idx.reshape(-1), torch.ones(topk_idx.numel(), dtype=torch.float32, device=x.device))
-        c_e = c_e / s
+        # the per-expert slot counts serve both the load-balance loss (fraction of slots routed to each expert) and the capacity limit:
+        # counted once (every op in here is a kernel launch, 24 layers deep: the 8-GPU MoE step is bound by launches, not by math)
+        lec = number_count(topk_idx, self.tot_expert)
+        c_e = lec.float() / s
         m_e = F.softmax(score.float(), dim=1).mean(0)
         self.set_loss((c_e * m_e).mean() * (self.num_expert ** 2))
         cap = math.ceil(self.capacity[0 if self.training else 1] * x.shape[0])
-        _, _, topk_idx = limit_by_capacity(topk_idx, self.num_expert, self.world_size, cap, group=self.group)
+        _, _, topk_idx = limit_by_capacity(topk_idx, self.num_expert, self.world_size, cap, group=self.group, lec=lec)
         if self.random_routing:
             prob = torch.rand(s, dtype=torch.float32, device=x.device)
             topk_idx = random_routing(topk_idx, topk_val, prob)

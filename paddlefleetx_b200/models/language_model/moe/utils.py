@@ -86,10 +86,26 @@ def prune_gate_by_capacity(gate_idx: torch.Tensor, new_lec: torch.Tensor, num_ex
     return torch.where(keep, flat, torch.full_like(flat, -1)).view_as(gate_idx)
 
 
-def limit_by_capacity(topk_idx: torch.Tensor, num_expert: int, world_size: int, capacity: int, group=None):
+_CAP_CACHE = {}
+
+
+def _capacity_tensor(num_expert: int, capacity: int, device) -> torch.Tensor:
+    key = (num_expert, int(capacity), str(device))
+    if key not in _CAP_CACHE:
+        if len(_CAP_CACHE) > 64:
+            _CAP_CACHE.clear()
+        _CAP_CACHE[key] = torch.full((num_expert,), int(capacity), dtype=torch.int64, device=device)
+    return _CAP_CACHE[key]
+
+
+def limit_by_capacity(topk_idx: torch.Tensor, num_expert: int, world_size: int, capacity: int, group=None, lec: torch.Tensor = None):
+    """``lec``: the local per-expert slot counts when the caller has them already (``number_count(topk_idx, num_expert * world_size)``)."""
     with torch.no_grad():
-        cap = torch.full((num_expert,), int(capacity), dtype=torch.int64, device=topk_idx.device)
-        _, lec, gec = count_by_gate(topk_idx, num_expert, world_size, require_pos=False, group=group)
+        cap = _capacity_tensor(num_expert, capacity, topk_idx.device)
+        if lec is None:
+            _, lec, gec = count_by_gate(topk_idx, num_expert, world_size, require_pos=False, group=group)
+        else:
+            gec = alltoall_counts(lec, group) if world_size > 1 else lec
         new_gec = limit_by_capacity_counts(gec, cap, world_size)
         new_lec = alltoall_counts(new_gec, group) if world_size > 1 else new_gec
         topk_idx = prune_gate_by_capacity(topk_idx, new_lec, num_expert, world_size)
