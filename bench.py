@@ -142,15 +142,21 @@ def _profile_steps(args, device_step, barrier, rank, world):
         json.dump({"steps": args.profile, "model": args.model, "n_gpus": world, "columns": ["name", "stream", "ts_us", "dur_us"], "kernels": rows}, f)
 
 
+def child_job_env(parent_env, port_offset: int = 17) -> dict:
+    """Environment of a child job started by every rank of a torchrun job: same ranks, its own rendezvous port.  Under torchrun the env://
+    rendezvous connects to the elastic AGENT's store instead of creating one; nobody serves the child's port, so unless the agent-store
+    marker is removed every child rank waits for a store that never comes up (this is what timed out in profiles/r2/c5_bench_n8)."""
+    env = dict(parent_env)
+    env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + port_offset)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)
+    env.pop("TORCHELASTIC_RUN_ID", None)
+    return env
+
+
 def _run_named_layout(args, rank):
     """BASELINE config #2 (GPT-6.7B, mp2 x pp2 x sharding2) as a child job on the same 8 GPUs: one child per rank, its own rendezvous port, a hard
     timeout; returns the child's JSON line (rank 0) or a dict with the failure reason.  Never raises: the headline line must survive."""
-    env = dict(os.environ)
-    env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 17)
-    # under torchrun the env:// rendezvous connects to the elastic AGENT's store instead of creating one; nobody serves the child's port,
-    # so without this every child rank waits for a store that never comes up (this is what timed out in profiles/r2/c5_bench_n8)
-    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)
-    env.pop("TORCHELASTIC_RUN_ID", None)
+    env = child_job_env(os.environ)
     forced = os.environ.get("PFX_NAMED_LAYOUT_FORCE")      # test hook: exercise the child-job path at another world size / layout (e.g. mp2 on 2 GPUs)
     cmd = [sys.executable, os.path.abspath(__file__), "--gpus", env.get("WORLD_SIZE", "8"), "--layout", forced or "mp2_pp2_sharding2", "--fused-tp", "1", "--steps", str(max(args.steps // 2, 3)),
            "--warmup", "3", "--no-e2e", "--inner", "--model", args.model, "--seq-len", str(args.seq_len), "--local-batch", str(args.local_batch)]

@@ -53,3 +53,24 @@ def test_reference_arm_reports_unavailable_and_exits_zero():
     assert p.returncode == 0, p.stderr[-800:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and "unavailable" in line and "paddle" in line["unavailable"].lower()
+
+
+def test_child_job_of_a_torchrun_job_can_rendezvous(tmp_path):
+    """bench.py --gpus 8 starts BASELINE config #2 as a child job from every rank.  The child must not inherit the elastic agent's store
+    (it would wait forever on a port nobody serves): two gloo ranks under torchrun each start a child with child_job_env and the children
+    complete an all-reduce."""
+    parent = tmp_path / "parent.py"
+    child = tmp_path / "child.py"
+    child.write_text("import torch, torch.distributed as dist\ndist.init_process_group('gloo')\nt = torch.ones(1)\ndist.all_reduce(t)\nprint('CHILD_OK', int(t.item()))\n")
+    parent.write_text(
+        "import os, subprocess, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch.distributed as dist\n"
+        "from bench import child_job_env\n"
+        "dist.init_process_group('gloo')\n"
+        f"p = subprocess.run([sys.executable, {str(child)!r}], env=child_job_env(os.environ), capture_output=True, text=True, timeout=60)\n"
+        "print('PARENT', dist.get_rank(), p.stdout.strip(), p.stderr[-300:])\n")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr=127.0.0.1", "--master-port=29733",
+                        str(parent)], capture_output=True, text=True, timeout=180, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert p.stdout.count("CHILD_OK 2") == 2, p.stdout[-1500:] + p.stderr[-500:]
