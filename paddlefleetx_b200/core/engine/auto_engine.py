@@ -8,8 +8,8 @@ decides by propagating ``shard_tensor`` annotations is decided here by a cost mo
 180 GB per GPU (degrees, ZeRO stage, micro-batch, recompute) and derive the config from it; the chosen plan is recorded under
 ``Distributed.plan``.  ``tune`` covers the two things the reference's ``Tuning`` section drives:
 
-* ``Tuning.tuning_recompute`` — a *measured* search: every recompute setting (off / ``core_attn`` / ``full_attn`` / ``full``) is built on the
-  configured mesh, steps ``[profile_start_step, profile_end_step]`` are timed (device-synchronised, max over ranks) with the peak allocator
+* ``Tuning.tuning_recompute`` / ``Tuning.tuning_micro_batch`` — a *measured* search: every recompute setting (off / ``core_attn`` /
+  ``full_attn`` / ``full``) and / or every micro-batch size that divides the local batch is built on the configured mesh, steps ``[profile_start_step, profile_end_step]`` are timed (device-synchronised, max over ranks) with the peak allocator
   footprint recorded, and the fastest candidate under the memory limit is written back into the config;
 * otherwise — the planner's ranked table of every feasible (dp, sharding + stage, mp, pp) layout with its predicted step time, memory and
   time breakdown (compute / TP collectives / pipeline bubble / exposed DP traffic / exposed optimizer).
@@ -41,10 +41,11 @@ class AutoEngine(EagerEngine):
     # ------------------------------------------------------------------ tuning
     def tune(self, tune_data_loader: Optional[Iterable] = None) -> List[Dict]:
         tuning = self._configs.get("Tuning", {}) or {}
-        if tuning.get("tuning_recompute", False):
-            assert tune_data_loader is not None, "Tuning.tuning_recompute measures real steps: pass the training data loader"
-            return self._tune_recompute(tune_data_loader, int(tuning.get("profile_start_step", 1)), int(tuning.get("profile_end_step", 5)),
-                                        tuning.get("memory_limit_gb"))
+        if tuning.get("tuning_recompute", False) or tuning.get("tuning_micro_batch", False):
+            assert tune_data_loader is not None, "Tuning.tuning_recompute / tuning_micro_batch measure real steps: pass the training data loader"
+            return self._tune_measured(tune_data_loader, int(tuning.get("profile_start_step", 1)), int(tuning.get("profile_end_step", 5)),
+                                       tuning.get("memory_limit_gb"), recompute=bool(tuning.get("tuning_recompute", False)),
+                                       micro_batch=bool(tuning.get("tuning_micro_batch", False)))
         from ...utils.layout_planner import rank_layouts
 
         return rank_layouts(self._configs)
@@ -54,7 +55,13 @@ class AutoEngine(EagerEngine):
         from ...models import build_module
 
         cfg = copy.deepcopy(self._configs)
+        overrides = dict(overrides)
+        micro = overrides.pop("micro_batch_size", None)
         cfg.Model.update(overrides)
+        if micro is not None:                     # the engine accumulates local_batch / micro_batch micro-steps per optimizer step
+            cfg.Global.micro_batch_size = int(micro)
+            cfg.Engine.accumulate_steps = int(cfg.Global.local_batch_size) // int(micro)
+            overrides["micro_batch_size"] = int(micro)
         cfg.Engine.save_load.update({"save_steps": -1, "ckpt_dir": None})
         cuda = torch.cuda.is_available() and str(cfg.Global.get("device", "gpu")) != "cpu"
         row = dict(overrides, status="ok")
@@ -95,7 +102,15 @@ class AutoEngine(EagerEngine):
             torch.cuda.empty_cache()
         return row
 
-    def _tune_recompute(self, loader: Iterable, start: int, end: int, memory_limit_gb: Optional[float]) -> List[Dict]:
+    def _micro_batch_candidates(self) -> List[int]:
+        lb = int(self._configs.Global.local_batch_size)
+        pp = int(self._configs.Distributed.get("pp_degree", 1) or 1)
+        return [m for m in range(1, lb + 1) if lb % m == 0 and (pp == 1 or lb // m >= pp)]
+
+    def _tune_measured(self, loader: Iterable, start: int, end: int, memory_limit_gb: Optional[float], recompute: bool = True,
+                       micro_batch: bool = False) -> List[Dict]:
+        """Build and time every candidate (recompute setting x micro-batch size, whichever the Tuning section asks for) on the configured
+        mesh; the fastest one under the memory limit is written back into the config."""
         assert 0 <= start <= end, "need 0 <= profile_start_step <= profile_end_step"
         batches = []
         for batch in loader:
@@ -105,18 +120,26 @@ class AutoEngine(EagerEngine):
         assert len(batches) > end, f"the loader yields {len(batches)} batches, profiling needs {end + 1}"
         if memory_limit_gb is None and torch.cuda.is_available():
             memory_limit_gb = 0.92 * torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory / 2 ** 30
-        rows = [self._profile_candidate(dict(c), batches, start, end) for c in RECOMPUTE_CANDIDATES]
+        rc = [dict(c) for c in RECOMPUTE_CANDIDATES] if recompute else [{}]
+        mb = [{"micro_batch_size": m} for m in self._micro_batch_candidates()] if micro_batch else [{}]
+        rows = [self._profile_candidate({**a, **b}, batches, start, end) for a in rc for b in mb]
         for r in rows:
             r["fits"] = r["status"] == "ok" and (memory_limit_gb is None or r["peak_mem_gb"] <= memory_limit_gb)
         rows.sort(key=lambda r: (not r["fits"], r["step_s"]))
         best = rows[0]
         if best["fits"]:
             self._configs.Model.update({k: best[k] for k in ("use_recompute", "recompute_granularity") if k in best})
-            logger.info(f"[tune] selected use_recompute={best['use_recompute']} granularity={best.get('recompute_granularity')} "
-                        f"({best['step_s'] * 1e3:.1f} ms/step, peak {best['peak_mem_gb']:.1f} GB)")
+            if "micro_batch_size" in best:
+                self._configs.Global.micro_batch_size = best["micro_batch_size"]
+                self._configs.Engine.accumulate_steps = int(self._configs.Global.local_batch_size) // best["micro_batch_size"]
+            logger.info(f"[tune] selected " + ", ".join(f"{k}={best[k]}" for k in ("use_recompute", "recompute_granularity", "micro_batch_size") if k in best)
+                        + f" ({best['step_s'] * 1e3:.1f} ms/step, peak {best['peak_mem_gb']:.1f} GB)")
         else:
-            logger.warning("[tune] no recompute setting fits the memory limit; configuration left unchanged")
+            logger.warning("[tune] no candidate fits the memory limit; configuration left unchanged")
         return rows
+
+    def _tune_recompute(self, loader: Iterable, start: int, end: int, memory_limit_gb: Optional[float]) -> List[Dict]:
+        return self._tune_measured(loader, start, end, memory_limit_gb, recompute=True, micro_batch=False)
 
     def export_from_prog(self):
         return self.export()

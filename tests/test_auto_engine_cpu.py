@@ -85,3 +85,22 @@ def test_auto_layout_plans_then_trains(tmp_path, capsys):
     d = engine._configs.Distributed
     assert d.plan is not None and d.plan.est_mem_gb > 0 and "[auto_layout]" in capsys.readouterr().out
     assert (d.dp_degree, d.mp_degree, d.pp_degree, d.sharding.sharding_degree) == (1, 1, 1, 1) and d.auto_layout is False
+
+
+def test_auto_tuning_measures_micro_batch_sizes(tmp_path):
+    """``Tuning.tuning_micro_batch``: every micro-batch size that divides the local batch is built and timed; gradient accumulation does not change
+    the numbers, the fastest candidate is written back together with the matching accumulate_steps."""
+    import auto
+
+    extra = ["Tuning.enable=True", "Tuning.tuning_micro_batch=True", "Tuning.profile_start_step=1", "Tuning.profile_end_step=2",
+             "Global.local_batch_size=4", "Global.micro_batch_size=4"]
+    engine = auto.main(_argv(tmp_path, [o for o in extra]))
+    from paddlefleetx_b200.data import build_dataloader
+
+    rows = engine.tune(build_dataloader(engine._configs.Data, "Train"))
+    assert sorted(r["micro_batch_size"] for r in rows) == [1, 2, 4] and all(r["status"] == "ok" for r in rows)
+    losses = [r["final_loss"] for r in rows]
+    assert max(losses) - min(losses) < 1e-4, losses
+    best = rows[0]
+    assert engine._configs.Global.micro_batch_size == best["micro_batch_size"]
+    assert engine._configs.Engine.accumulate_steps == 4 // best["micro_batch_size"]
