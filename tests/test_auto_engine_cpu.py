@@ -104,3 +104,20 @@ def test_auto_tuning_measures_micro_batch_sizes(tmp_path):
     best = rows[0]
     assert engine._configs.Global.micro_batch_size == best["micro_batch_size"]
     assert engine._configs.Engine.accumulate_steps == 4 // best["micro_batch_size"]
+
+
+def test_auto_module_reports_shard_spec_and_rejects_a_wrong_mesh(tmp_path):
+    import auto
+
+    engine = auto.main(_argv(tmp_path, ["Engine.max_steps=1"]))
+    spec = engine._module.shard_spec()
+    assert spec and all(isinstance(v, list) for v in spec.values())
+    assert all(set(v) <= {None} for v in spec.values())                  # one process: nothing is split
+    name, p = next((n, p) for n, p in engine._module.model.named_parameters() if p.dim() == 2)
+    p.tp_sharded, p.split_axis = True, 1                                 # what a column-parallel weight looks like on an mp > 1 mesh
+    assert engine._module.shard_spec()[name] == [None, "mp"]
+    del p.tp_sharded, p.split_axis
+    cfg = engine._configs
+    cfg.Distributed.mesh.shape = [2, 1, 1]
+    with pytest.raises(ValueError, match="mesh"):
+        type(engine._module)(cfg)
