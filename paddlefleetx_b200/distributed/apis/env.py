@@ -111,7 +111,7 @@ def init_dist_env(config) -> HybridCommunicateGroup:
             "pp_degree > 1 with sequence_parallel requires enable_partial_send_recv=False"
     st = DistributedStrategy()
     st.hybrid_configs = dict(dp_degree=d.dp_degree, mp_degree=d.mp_degree, pp_degree=d.pp_degree,
-                             sharding_degree=d.sharding.sharding_degree)
+                             sharding_degree=d.sharding.sharding_degree, cp_degree=int(d.get("cp_degree", 1) or 1))
     st.pipeline_configs = dict(
         accumulate_steps=config.Global.local_batch_size // config.Global.micro_batch_size,
         micro_batch_size=config.Global.micro_batch_size,
@@ -158,14 +158,14 @@ def get_data_world_size() -> int:
     if world_size() == 1:
         return 1
     h = get_hcg()
-    return h.get_data_parallel_world_size() * h.get_sharding_parallel_world_size()
+    return h.get_data_parallel_world_size() * h.get_sharding_parallel_world_size() // getattr(h, "cp", 1)      # a context-parallel group is ONE data replica
 
 
 def get_data_world_rank() -> int:
     if world_size() == 1:
         return 0
     h = get_hcg()
-    return h.get_data_parallel_rank() * h.get_sharding_parallel_world_size() + h.get_sharding_parallel_rank()
+    return (h.get_data_parallel_rank() * h.get_sharding_parallel_world_size() + h.get_sharding_parallel_rank()) // getattr(h, "cp", 1)
 
 
 def work_at_local_rank0(func):

@@ -143,6 +143,16 @@ class MultiHeadAttention(nn.Module):
             self.k_proj = Col(hidden, hidden, **ckw)
             self.v_proj = Col(hidden, hidden, **ckw)
         self.out_proj = Row(hidden, hidden, **rkw)
+        # context parallelism (``Distributed.cp_degree`` > 1): the group comes from the process topology, not from a constructor argument,
+        # because to every other part of the model the members of a cp group are ordinary data-parallel ranks
+        self.cp_group = None
+        from ....distributed.apis import env as _env
+
+        hcg = getattr(_env, "_hcg", None)           # only an already-built topology counts (get_hcg() would build a default one)
+        if hcg is not None and getattr(hcg, "cp", 1) > 1:
+            self.cp_group = hcg.get_context_parallel_group()
+            assert not sequence_parallel, "cp_degree > 1 is not combined with Megatron sequence parallelism"
+            assert self.local_heads % self.cp_group.nranks == 0, f"local heads {self.local_heads} % cp {self.cp_group.nranks}"
 
     # -- projections -------------------------------------------------------------------------
     def _qkv(self, x: torch.Tensor):
@@ -184,8 +194,21 @@ class MultiHeadAttention(nn.Module):
             attn_mask = torch.full((sq, sk), -1e4, device=q.device, dtype=torch.float32).triu(1 + sk - sq)
         return ATT.core_attention(q, k, v, scale, p, self.training, attn_mask=attn_mask, causal=causal)
 
+    def _forward_context_parallel(self, x, attn_mask, positions):
+        """Ulysses context parallelism: this rank holds ``s / c`` positions of every head; one all-to-all turns that into every position
+        of ``H / c`` heads for the attention itself (causal over the FULL sequence), a second one turns it back."""
+        q, k, v = self._qkv(x)                                                   # [b, s/c, H, d]
+        if self.use_rope:
+            q, k = OF.rope(q.contiguous(), positions), OF.rope(k.contiguous(), positions)      # ``positions`` are global (sliced with the tokens)
+        q, k, v = (C.seq_head_all_to_all(t, self.cp_group, 2, 1) for t in (q, k, v))           # [b, s, H/c, d]
+        out = recompute(self._core, q, k, v, attn_mask) if (self.recompute_core and self.training) else self._core(q, k, v, attn_mask)
+        out = C.seq_head_all_to_all(out, self.cp_group, 1, 2)                    # [b, s/c, H, d]
+        return self.out_proj(out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim))
+
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, cache: Optional[KVCache] = None,
                 positions: Optional[torch.Tensor] = None):
+        if self.cp_group is not None and cache is None:
+            return self._forward_context_parallel(x, attn_mask, positions)
         if (self.fuse_attn_qkv and self.use_flash_attn and not self.use_rope and cache is None and attn_mask is None and x.is_cuda
                 and not (self.recompute_core and self.training)):
             # fused projection output [.., heads, 3, d] goes to the flash kernels as it is: q / k / v are read in place (TMA views), the

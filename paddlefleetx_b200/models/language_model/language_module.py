@@ -148,8 +148,21 @@ class LanguageModule(BasicModule):
     def forward(self, tokens, ids):
         return self.model(tokens, ids)
 
+    def _context_parallel_slice(self, batch):
+        """``Distributed.cp_degree`` > 1: the ranks of a context-parallel group receive the same batch; each keeps its contiguous slice of the
+        sequence (tokens, GLOBAL position ids, labels, loss mask).  Attention re-assembles the sequence per head group (Ulysses)."""
+        from ...distributed.apis import env as _env
+
+        hcg = getattr(_env, "_hcg", None)
+        c = getattr(hcg, "cp", 1) if hcg is not None else 1
+        if c == 1:
+            return batch
+        r = hcg.get_context_parallel_rank()
+        assert batch[0].shape[1] % c == 0, f"sequence length {batch[0].shape[1]} % cp_degree {c}"
+        return [t.chunk(c, dim=1)[r].contiguous() for t in batch]
+
     def training_step(self, batch):
-        tokens, position_ids, labels, loss_mask = batch
+        tokens, position_ids, labels, loss_mask = self._context_parallel_slice(batch)
         preds = self(tokens, position_ids)
         return self.loss_fn(preds, labels, loss_mask)
 
@@ -165,7 +178,7 @@ class LanguageModule(BasicModule):
                log_dict["found_inf"]))
 
     def validation_step(self, batch):
-        tokens, position_ids, labels, loss_mask = batch
+        tokens, position_ids, labels, loss_mask = self._context_parallel_slice(batch)
         preds = self(tokens, position_ids)
         return self.loss_fn(preds, labels, loss_mask)
 

@@ -293,3 +293,44 @@ def fused_allreduce_gradients(params, group, scale: Optional[float] = None) -> N
         dist.all_reduce(flat, group=_pg(group))
         for g, synced in zip(gs, torch._utils._unflatten_dense_tensors(flat, gs)):
             g.copy_(synced)
+
+
+# ------------------------------------------------------------------------------------------------ context parallelism (Ulysses)
+def _all_to_all_dims(x: torch.Tensor, group, scatter_dim: int, gather_dim: int) -> torch.Tensor:
+    """Split ``scatter_dim`` over the group, concatenate what arrives (rank order) along ``gather_dim``."""
+    w = group_size(group)
+    if w == 1 or group.process_group is None:
+        return x
+    parts = [p.contiguous() for p in x.chunk(w, dim=scatter_dim)]
+    out = [torch.empty_like(parts[0]) for _ in range(w)]
+    if x.is_cuda:
+        dist.all_to_all(out, parts, group=group.process_group)
+    else:               # gloo has no all_to_all: pairwise exchange
+        reqs = [dist.isend(parts[r], group.ranks[r], group=group.process_group) for r in range(w) if r != group.rank]
+        for r in range(w):
+            if r == group.rank:
+                out[r].copy_(parts[r])
+            else:
+                dist.recv(out[r], group.ranks[r], group=group.process_group)
+        for q in reqs:
+            q.wait()
+    return torch.cat(out, dim=gather_dim)
+
+
+class _SeqHeadAllToAll(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, group, scatter_dim, gather_dim):
+        ctx.args = (group, scatter_dim, gather_dim)
+        return _all_to_all_dims(x, group, scatter_dim, gather_dim)
+
+    @staticmethod
+    def backward(ctx, g):
+        group, s, ga = ctx.args
+        return _all_to_all_dims(g.contiguous(), group, ga, s), None, None, None
+
+
+def seq_head_all_to_all(x: torch.Tensor, group, scatter_dim: int, gather_dim: int) -> torch.Tensor:
+    """The Ulysses exchange around attention: ``[b, s/c, H, d] -> [b, s, H/c, d]`` (scatter heads, gather sequence) and back.  Autograd-aware:
+    the backward is the inverse exchange."""
+    return x if group_size(group) == 1 else _SeqHeadAllToAll.apply(x, group, scatter_dim, gather_dim)
+

@@ -91,7 +91,7 @@ class HybridCommunicateGroup:
     process group (all groups degenerate to size 1), which is what single-card runs use."""
 
     def __init__(self, dp: int = 1, mp: int = 1, pp: int = 1, sharding: int = 1,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, build_groups: bool = True):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, build_groups: bool = True, cp: int = 1):
         initialised = dist.is_available() and dist.is_initialized()
         self.global_rank = rank if rank is not None else (dist.get_rank() if initialised else 0)
         self.nranks = world_size if world_size is not None else (dist.get_world_size() if initialised else 1)
@@ -105,6 +105,22 @@ class HybridCommunicateGroup:
                            ("check", ("mp", "pp")), ("moe", ("dp", "mp")),
                            ("dp_sharding", ("dp", "sharding"))):
             self._groups[name] = self._make(axes, can_build)
+        # context parallelism (beyond the reference): ``cp`` consecutive DATA ranks (data index = dp_rank * sharding + sharding_rank) form a
+        # group that works on one batch, each rank on its slice of the sequence; to the samplers the group is one data replica, to the
+        # gradient reduction its members are ordinary data ranks (different tokens, same parameters)
+        self.cp = int(cp)
+        data = dp * sharding
+        if self.cp < 1 or data % self.cp:
+            raise ValueError(f"cp_degree {cp} must divide dp x sharding = {data}")
+        self._groups["cp"] = _Group([self.global_rank], None, self.global_rank)
+        if self.cp > 1:
+            for ranks in self._topo.groups_along("dp", "sharding"):
+                by_data = sorted(ranks, key=lambda r: self._topo.coord_of(r)["dp"] * sharding + self._topo.coord_of(r)["sharding"])
+                for i in range(0, len(by_data), self.cp):
+                    chunk = by_data[i:i + self.cp]
+                    pg = dist.new_group(chunk) if can_build else None
+                    if self.global_rank in chunk:
+                        self._groups["cp"] = _Group(chunk, pg, self.global_rank)
         # pipeline neighbours
         pp_ranks = self._groups["pp"].ranks
         s = self._coord["pp"]
@@ -166,6 +182,10 @@ class HybridCommunicateGroup:
     def get_sharding_parallel_world_size(self): return self._topo.dims["sharding"]
     def get_sharding_parallel_group(self): return self._groups["sharding"]
     def get_sharding_parallel_group_src_rank(self): return self._groups["sharding"].ranks[0]
+
+    def get_context_parallel_group(self): return self._groups["cp"]
+    def get_context_parallel_world_size(self): return self.cp
+    def get_context_parallel_rank(self): return self._groups["cp"].ranks.index(self.global_rank)
 
     def get_check_parallel_group(self): return self._groups["check"]
     def get_moe_group(self): return self._groups["moe"]

@@ -192,6 +192,14 @@ def process_dist_config(cfg: AttrDict, nranks: Optional[int] = None) -> None:
             f"Mismatched config using {nranks} cards with dp_degree[{dp}], mp_degree[{mp}], "
             f"pp_degree[{pp}] and sharding_degree[{sd}]")
 
+    cp = dist_cfg.setdefault("cp_degree", 1) or 1
+    dist_cfg["cp_degree"] = cp
+    if cp > 1:        # context parallelism: cp consecutive data ranks share a batch and split its sequence (Ulysses all-to-all around attention)
+        if (dp * sd) % cp != 0:
+            raise AssertionError(f"cp_degree[{cp}] must divide dp_degree[{dp}] x sharding_degree[{sd}]")
+        if pp > 1:
+            raise AssertionError("cp_degree > 1 is not combined with pipeline parallelism")
+
     if sd > 1 and (sh.sharding_stage == 3 or sh.sharding_offload):
         for flag in ("reduce_overlap", "broadcast_overlap"):
             if sh[flag]:
@@ -221,7 +229,7 @@ def process_global_configs(cfg: AttrDict) -> None:
         logger.info(f"Environment variable {k} is set {v}.")
 
     gbs, lbs = g.get("global_batch_size"), g.get("local_batch_size")
-    replicas = dp * sd
+    replicas = dp * sd // int(dist_cfg.get("cp_degree", 1) or 1)          # a context-parallel group consumes one batch
     if gbs is None and lbs is None:
         raise ValueError("global_batch_size or local_batch_size should be set.")
     if gbs is not None and lbs is not None:

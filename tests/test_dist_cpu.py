@@ -92,3 +92,11 @@ def test_ernie_tensor_and_sequence_parallel_match_single(sp):
 @pytest.mark.parametrize("layout", ["dp2", "zero2", "zero3"])
 def test_resume_from_checkpoint_matches_uninterrupted_run(layout):
     run_distributed("dist_fns:resume_matches_uninterrupted", 2, layout)
+
+
+def test_context_parallel_cp2_matches_single():          # beyond the reference: Ulysses sequence sharding inside the data-parallel ranks
+    run_distributed("dist_fns:context_parallel_matches_single", 2, 2, 1, 2)
+
+
+def test_context_parallel_cp2_with_zero_sharding_and_rope_matches_single():
+    run_distributed("dist_fns:context_parallel_matches_single", 4, 1, 4, 2, ["Model.use_rope=True"])
