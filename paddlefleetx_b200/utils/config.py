@@ -352,7 +352,7 @@ def get_auto_config(fname: str, overrides: Optional[Iterable[str]] = None, show:
         if not plans:
             raise ValueError(f"auto_layout: no layout of this model fits {world} x 180 GB; add GPUs or reduce the batch / sequence length")
         best = plans[0]
-        extra = best.overrides() + [f"Global.local_batch_size={per_gpu * best.mp * best.pp}", "Global.global_batch_size=None",
+        extra = best.overrides() + [f"Global.local_batch_size={per_gpu * best.mp * best.pp * best.cp}", "Global.global_batch_size=None",
                                     "Distributed.auto_layout=False"]
         cfg = get_config(fname, list(overrides or []) + extra, show=False, nranks=nranks)
         cfg.Distributed["plan"] = AttrDict(describe=best.describe(), est_step_ms=best.est_step_s * 1e3, est_mem_gb=best.est_mem_gb,

@@ -101,6 +101,7 @@ class Plan:
     recompute: str                       # none | core_attn | full_attn | full
     sequence_parallel: bool
     fused_tp: bool
+    cp: int = 1                          # context parallelism: cp of the (dp x sharding) data ranks share a batch and split its sequence (Ulysses)
     est_step_s: float = 0.0
     est_mem_gb: float = 0.0
     tokens_per_s: float = 0.0
@@ -111,13 +112,13 @@ class Plan:
         ov = [f"Distributed.dp_degree={self.dp}", f"Distributed.mp_degree={self.mp}", f"Distributed.pp_degree={self.pp}",
               f"Distributed.sharding.sharding_degree={self.sharding}", f"Distributed.sharding.sharding_stage={self.stage}",
               f"Global.micro_batch_size={self.micro_batch}", f"Model.use_recompute={self.recompute != 'none'}",
-              f"Model.sequence_parallel={self.sequence_parallel}"]
+              f"Model.sequence_parallel={self.sequence_parallel}", f"Distributed.cp_degree={self.cp}"]
         if self.recompute != "none":
             ov.append(f"Model.recompute_granularity={self.recompute}")
         return ov
 
     def describe(self) -> str:
-        return (f"dp{self.dp} x sharding{self.sharding}(stage {self.stage}) x mp{self.mp}{'+sp' if self.sequence_parallel else ''} x pp{self.pp}, "
+        return (f"dp{self.dp} x sharding{self.sharding}(stage {self.stage}){f' [cp{self.cp}]' if self.cp > 1 else ''} x mp{self.mp}{'+sp' if self.sequence_parallel else ''} x pp{self.pp}, "
                 f"micro {self.micro_batch} x {self.accumulate}, recompute {self.recompute}: {self.est_step_s * 1e3:.1f} ms/step, "
                 f"{self.est_mem_gb:.0f} GB, {self.tokens_per_s:,.0f} tok/s")
 
@@ -149,9 +150,10 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
     """Fill in the predicted step time, memory and throughput of ``plan`` (``local_batch`` = sequences per data-parallel rank per step)."""
     mp, pp, sd, dp, stage = plan.mp, plan.pp, plan.sharding, plan.dp, plan.stage
     data_ranks = dp * sd
+    cp = max(int(plan.cp), 1)
     mb = plan.micro_batch
     n_micro = max(local_batch // mb, 1)
-    tokens = float(mb * s.seq)
+    tokens = float(mb * s.seq) / cp                      # a context-parallel rank holds 1 / cp of every sequence
     layers_local = s.layers / pp
     lt = _layer_time(hw, s, tokens, mp, plan.sequence_parallel, plan.recompute)
     per_micro = layers_local * sum(lt.values())
@@ -165,6 +167,8 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
         # for 27.7 ms of wire time — the micro-benchmarks hide 60-70 % of a single collective, the full backward (re-gather + two GEMMs per
         # collective, smaller N / K) does not
         tp = vol / hw.link_bw * (1.0 if plan.fused_tp else 1.6) + (0 if plan.fused_tp else 8.0 * layers_local * 12e-6)
+    if cp > 1:        # Ulysses: 4 all-to-alls per layer forward (q, k, v, out) and 4 backward, each moving (cp - 1) / cp of tokens x h / mp bf16
+        tp += 8.0 * layers_local * tokens * s.hidden / mp * 2.0 * (cp - 1) / cp / hw.link_bw + 8.0 * layers_local * 12e-6
     pipe_p2p = 0.0 if pp == 1 else 2.0 * tokens * s.hidden * 2.0 / (mp if plan.sequence_parallel else 1) / hw.link_bw + 4 * 15e-6
     if pp > 1:
         per_micro *= 1.15            # blocking stage-to-stage transfers and ~7 k launches per step at micro-batch granularity (c15_bench_n8.json, named_layout)
@@ -197,7 +201,7 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
     mem += tokens * s.vocab / mp * 6.0 / (pp if pp > 1 else 1)             # bf16 logits + fp32 softmax workspace (last stage; amortised over stages)
     mem = mem * 1.06 + 2.5e9                                               # allocator slack, CUDA context, NCCL / symmetric buffers
     plan.est_step_s, plan.est_mem_gb = step, mem / 2 ** 30
-    plan.tokens_per_s = local_batch * data_ranks * s.seq / step
+    plan.tokens_per_s = local_batch * (data_ranks // cp) * s.seq / step
     plan.breakdown = {"compute": n_micro * per_micro, "tp_comm": n_micro * tp, "pipeline_bubble": bubble + n_micro * pipe_p2p,
                       "exposed_dp_comm": exposed_dp, "exposed_optimizer": exposed_opt}
     return plan
@@ -224,13 +228,16 @@ def enumerate_plans(s: ModelShape, world: int, local_batch: int, stages: Iterabl
                 for stage in (stages if sd > 1 else (1,)):
                     if stage == 3 and pp > 1:
                         continue                                           # the stage-3 wrapper and the pipeline schedule are not combined
-                    for mb in _divisors(rank_batch):
-                        n_micro = rank_batch // mb
-                        if pp > 1 and n_micro < pp:
-                            continue
-                        for rc in ("none", "core_attn", "full"):
-                            out.append(Plan(dp=dp, sharding=sd, stage=stage, mp=mp, pp=pp, micro_batch=mb, accumulate=n_micro, recompute=rc,
-                                            sequence_parallel=mp > 1, fused_tp=mp > 1))
+                    cps = [1] + [c for c in _divisors(rest) if c > 1 and pp == 1 and mp == 1 and (s.heads // mp) % c == 0 and s.seq % c == 0 and s.seq >= 4096]
+                    for c in cps:                                          # context parallelism only where long sequences make activations the problem
+                        group_batch = rank_batch * c                       # the c ranks of a group pool their share of the global batch
+                        for mb in _divisors(group_batch):
+                            n_micro = group_batch // mb
+                            if pp > 1 and n_micro < pp:
+                                continue
+                            for rc in ("none", "core_attn", "full"):
+                                out.append(Plan(dp=dp, sharding=sd, stage=stage, mp=mp, pp=pp, micro_batch=mb, accumulate=n_micro, recompute=rc,
+                                                sequence_parallel=mp > 1, fused_tp=mp > 1, cp=c))
     return out
 
 
@@ -242,13 +249,13 @@ def plan_layouts(s: ModelShape, world: int, local_batch: int, hw: Optional[Hardw
     limit = mem_limit_gb if mem_limit_gb is not None else 0.92 * hw.mem_gb
     plans = []
     for p in enumerate_plans(s, world, local_batch, **kw):
-        estimate(s, hw, world, local_batch * p.mp * p.pp, p)
+        estimate(s, hw, world, local_batch * p.mp * p.pp * p.cp, p)
         if p.est_mem_gb <= limit:
             plans.append(p)
     plans.sort(key=lambda p: (p.est_step_s, p.est_mem_gb))
     seen, uniq = set(), []
     for p in plans:                                                       # one entry per layout: its best micro-batch / recompute
-        key = (p.dp, p.sharding, p.stage, p.mp, p.pp)
+        key = (p.dp, p.sharding, p.stage, p.mp, p.pp, p.cp)
         if key not in seen:
             seen.add(key)
             uniq.append(p)

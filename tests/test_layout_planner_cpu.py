@@ -66,3 +66,19 @@ def test_auto_layout_rewrites_the_config(monkeypatch):
     assert d.dp_degree * d.sharding.sharding_degree * d.mp_degree * d.pp_degree == 8
     assert d.mp_degree == 1 and d.pp_degree == 1 and "plan" in d and d.plan.est_mem_gb < 170
     assert cfg.Global.global_batch_size == 64
+
+
+def test_long_sequences_bring_in_context_parallelism():
+    """At 32 k tokens per sequence a 13B model's activations no longer fit next to its states without help: the planner may shard the sequence
+    (cp) instead of recomputing; at 1 k tokens it never does.  The group batch keeps the per-GPU token count constant."""
+    hw = Hardware()
+    s = ModelShape(layers=40, hidden=5120, heads=40, vocab=50304, ffn=20480, seq=32768)
+    plans = plan_layouts(s, 8, 1, hw=hw)
+    assert plans and plans[0].cp > 1 and plans[0].est_mem_gb < 0.92 * 180
+    no_cp = [p for p in plans if p.cp == 1 and p.mp == 1 and p.pp == 1]
+    assert all(p.recompute != "none" or p.stage == 3 for p in no_cp[:1]) or not no_cp       # without cp it needs recompute / stage 3 (or does not fit)
+    assert "Distributed.cp_degree=%d" % plans[0].cp in plans[0].overrides()
+    assert all(p.cp == 1 for p in plan_layouts(shape("6.7b"), 8, 8, hw=hw))
+    # same tokens per GPU per step with and without cp
+    a = next(p for p in plans if p.cp == 2)
+    assert a.micro_batch * a.accumulate == 2
