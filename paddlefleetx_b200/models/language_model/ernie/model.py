@@ -193,6 +193,7 @@ class ErnieModel(nn.Module):
         num_hidden_layers = num_layers or num_hidden_layers
         ffn = ffn_hidden_size or intermediate_size or 4 * hidden_size
         self.pad_token_id, self.initializer_range, self.hidden_size, self.mp_group = pad_token_id, initializer_range, hidden_size, mp_group
+        self.vocab_size, self.hidden_act = vocab_size, hidden_act            # read by the heads, as in the reference (single_model.py:464-480)
         self.embeddings = ErnieEmbeddings(vocab_size, hidden_size, hidden_dropout_prob, max_position_embeddings, type_vocab_size,
                                           task_type_vocab_size, task_id, use_task_id, initializer_range, mp_group, dtype, device)
         layers = [TransformerEncoderLayer(hidden_size, num_attention_heads, ffn, hidden_dropout_prob, hidden_act, attention_probs_dropout_prob,
@@ -255,9 +256,11 @@ class ErniePretrainingHeads(nn.Module):
 
 
 class ErnieForPretraining(nn.Module):
-    def __init__(self, ernie: ErnieModel, vocab_size: int, hidden_act: str = "gelu", binary_head: bool = True):
+    def __init__(self, ernie: ErnieModel, vocab_size: Optional[int] = None, hidden_act: Optional[str] = None, binary_head: bool = True):
         super().__init__()
         self.ernie = ernie
+        vocab_size = vocab_size or ernie.vocab_size                  # reference signature: ErnieForPretraining(ernie)
+        hidden_act = hidden_act or ernie.hidden_act
         p = ernie.pooler.dense.weight
         self.cls = ErniePretrainingHeads(ernie.hidden_size, vocab_size, hidden_act, ernie.embeddings.word_embeddings.weight, ernie.mp_group,
                                          ernie.initializer_range, binary_head, p.dtype, p.device)
