@@ -47,15 +47,19 @@ class ErnieEmbeddings(nn.Module):
         self.layer_norm = LayerNorm(hidden, 1e-12, False, dtype, device)
         self.dropout_p = hidden_dropout
 
-    def forward(self, input_ids, token_type_ids=None, position_ids=None, task_type_ids=None):
+    def forward(self, input_ids, token_type_ids=None, position_ids=None, task_type_ids=None, inputs_embeds=None, past_key_values_length=None):
+        """``inputs_embeds`` replaces the word-embedding lookup; ``past_key_values_length`` offsets the default positions when the caller
+        feeds only the new tokens of an incrementally extended sequence (reference single_model.py:71-112)."""
+        words = self.word_embeddings(input_ids) if input_ids is not None else inputs_embeds
+        b, s = words.shape[:2]
         if position_ids is None:
-            position_ids = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0).expand_as(input_ids)
+            position_ids = (torch.arange(s, device=words.device) + int(past_key_values_length or 0)).unsqueeze(0).expand(b, s)
         if token_type_ids is None:
-            token_type_ids = torch.zeros_like(input_ids)
-        x = self.word_embeddings(input_ids) + self.position_embeddings(position_ids) + self.token_type_embeddings(token_type_ids)
+            token_type_ids = torch.zeros(b, s, dtype=torch.long, device=words.device)
+        x = words + self.position_embeddings(position_ids) + self.token_type_embeddings(token_type_ids)
         if self.use_task_id:
             if task_type_ids is None:
-                task_type_ids = torch.full_like(input_ids, self.task_id)
+                task_type_ids = torch.full((b, s), self.task_id, dtype=torch.long, device=words.device)
             x = x + self.task_type_embeddings(task_type_ids)
         return OF.dropout(self.layer_norm(x), self.dropout_p, self.training, "global_seed")
 
@@ -81,6 +85,33 @@ class ErnieSelfAttention(nn.Module):
             self.out_proj = RowParallelLinear(hidden, hidden, input_is_parallel=True, **kw)
         self.attn_dropout = attn_dropout
         self.use_flash_attn = use_flash_attn
+
+    def forward_detailed(self, x, attn_mask=None, cache=None, need_weights=False):
+        """The inspection / incremental path (reference layers/transformer.py:346-436): explicit softmax so that the attention probabilities
+        can be returned, and an optional ``(k, v)`` cache of [b, heads, s_past, d] that the new keys / values are appended to.  Returns
+        ``(out, weights or None, new_cache or None)``.  Not used by training (that is ``forward``: flash kernels, no materialised scores)."""
+        assert not self.sequence_parallel, "attention weights / caches are not available on sequence-parallel activations"
+        b, s, _ = x.shape
+        q, k, v = (p(x).view(b, s, self.local_heads, self.head_dim).transpose(1, 2) for p in (self.q_proj, self.k_proj, self.v_proj))
+        new_cache = None
+        if cache is not None:
+            k, v = torch.cat([cache[0], k], dim=2), torch.cat([cache[1], v], dim=2)
+            new_cache = (k, v)
+        scores = torch.matmul(q * self.head_dim ** -0.5, k.transpose(-1, -2))
+        if attn_mask is not None:
+            scores = scores + attn_mask.to(scores.dtype)
+        weights = torch.softmax(scores.float(), dim=-1).to(q.dtype)
+        probs = weights
+        if self.training and self.attn_dropout > 0:
+            with get_rng_state_tracker().rng_state("local_seed"):
+                probs = F.dropout(weights, self.attn_dropout, True)
+        o = torch.matmul(probs, v).transpose(1, 2).reshape(b, s, self.local_heads * self.head_dim)
+        return self.out_proj(o), (probs if need_weights else None), new_cache
+
+    def gen_cache(self, x):
+        """Empty ``(k, v)`` cache for a batch shaped like ``x`` (reference ``MultiHeadAttention.gen_cache``)."""
+        z = x.new_zeros(x.shape[0], self.local_heads, 0, self.head_dim)
+        return (z, z.clone())
 
     def forward(self, x, attn_mask=None):
         if self.sequence_parallel:
@@ -133,11 +164,18 @@ class TransformerEncoderLayer(nn.Module):
         self.act_dropout_p = dropout if act_dropout is None else act_dropout
         self.activation = activation
 
-    def forward(self, x, attn_mask=None):
+    def forward(self, x, attn_mask=None, cache=None, output_attentions=False):
+        """Plain call: the layer output.  With a ``cache`` and / or ``output_attentions`` the result is a tuple
+        ``(output[, new_cache][, attention_probs])`` like the reference layer (layers/transformer.py:544-620)."""
+        detailed = cache is not None or output_attentions
         res = x
         if self.normalize_before:
             x = self.norm1(x)
-        x = res + OF.dropout(self.self_attn(x, attn_mask), self.dropout_p, self.training, self.rng_name)
+        if detailed:
+            attn, weights, new_cache = self.self_attn.forward_detailed(x, attn_mask, cache, output_attentions)
+        else:
+            attn = self.self_attn(x, attn_mask)
+        x = res + OF.dropout(attn, self.dropout_p, self.training, self.rng_name)
         if not self.normalize_before:
             x = self.norm1(x)
         res = x
@@ -148,7 +186,12 @@ class TransformerEncoderLayer(nn.Module):
         x = res + OF.dropout(self.linear2(h), self.dropout_p, self.training, self.rng_name)
         if not self.normalize_before:
             x = self.norm2(x)
-        return x
+        if not detailed:
+            return x
+        return (x,) + ((new_cache,) if cache is not None else ()) + ((weights,) if output_attentions else ())
+
+    def gen_cache(self, x):
+        return self.self_attn.gen_cache(x)
 
 
 class TransformerEncoder(nn.Module):
@@ -158,13 +201,44 @@ class TransformerEncoder(nn.Module):
         self.norm = norm
         self.use_recompute = use_recompute
 
-    def forward(self, x, attn_mask=None):
-        for layer in self.layers:
-            if self.use_recompute and self.training:
-                x = recompute(layer, x, attn_mask)
-            else:
-                x = layer(x, attn_mask)
-        return x if self.norm is None else self.norm(x)
+    def forward(self, x, attn_mask=None, cache=None, output_attentions=False, output_hidden_states=False, return_dict=False):
+        """Default call: the final hidden states (fast path, flash attention).  ``return_dict=True`` returns a
+        ``BaseModelOutputWithPastAndCrossAttentions`` with whatever of caches / per-layer hidden states (embedding output first) / attention
+        probabilities was asked for; as in the reference (layers/transformer.py:669-760) a non-dict call returns the hidden states only."""
+        use_cache = getattr(self, "_use_cache", None)
+        if cache is None and use_cache:
+            cache = [self.layers[0].gen_cache(x) for _ in self.layers]
+        if cache is None and not output_attentions and not output_hidden_states and not return_dict:
+            for layer in self.layers:
+                if self.use_recompute and self.training:
+                    x = recompute(layer, x, attn_mask)
+                else:
+                    x = layer(x, attn_mask)
+            return x if self.norm is None else self.norm(x)
+        new_caches = [] if cache is not None and (use_cache is None or use_cache) else None
+        attentions = [] if output_attentions else None
+        hidden = [x] if output_hidden_states else None
+        for i, layer in enumerate(self.layers):
+            out = layer(x, attn_mask, None if cache is None else tuple(cache[i]), output_attentions)
+            x, extras = (out[0], out[1:]) if isinstance(out, tuple) else (out, ())
+            if hidden is not None:
+                hidden.append(x)
+            if attentions is not None:
+                attentions.append(extras[-1])
+            if new_caches is not None:
+                new_caches.append(tuple(extras[0]))
+        if self.norm is not None:
+            x = self.norm(x)
+            if hidden is not None:
+                hidden[-1] = x
+        if not return_dict:
+            return x
+        from .model_outputs import BaseModelOutputWithPastAndCrossAttentions
+
+        return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=x, past_key_values=new_caches, hidden_states=hidden, attentions=attentions)
+
+    def gen_cache(self, x):
+        return [layer.gen_cache(x) for layer in self.layers]
 
 
 class ErniePooler(nn.Module):
@@ -202,20 +276,53 @@ class ErnieModel(nn.Module):
         self.encoder = TransformerEncoder(layers, None, use_recompute)
         self.pooler = ErniePooler(hidden_size, initializer_range, dtype, device)
 
-    def forward(self, input_ids, token_type_ids=None, position_ids=None, attention_mask=None, task_type_ids=None):
+    def get_input_embeddings(self):
+        return self.embeddings.word_embeddings
+
+    def set_input_embeddings(self, value):
+        self.embeddings.word_embeddings = value
+
+    def forward(self, input_ids=None, token_type_ids=None, position_ids=None, attention_mask=None, task_type_ids=None, past_key_values=None,
+                inputs_embeds=None, use_cache=None, output_hidden_states=False, output_attentions=False, return_dict=False):
+        """``(sequence_output, pooled_output)``; with ``return_dict=True`` a ``BaseModelOutputWithPoolingAndCrossAttentions`` that also carries
+        the requested ``past_key_values`` / ``hidden_states`` / ``attentions`` (argument list of the reference, single_model.py:241-375).
+        The training recipes use the first five arguments only and stay on the flash-attention path."""
+        if (input_ids is None) == (inputs_embeds is None):
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time." if input_ids is not None
+                             else "You have to specify either input_ids or inputs_embeds")
+        dtype = self.pooler.dense.weight.dtype
+        past_len = past_key_values[0][0].shape[2] if past_key_values is not None else None
         if attention_mask is None:
-            pad = (input_ids == self.pad_token_id)
-            attention_mask = pad[:, None, None, :].to(self.pooler.dense.weight.dtype) * -1e4
+            if input_ids is not None:
+                pad = (input_ids == self.pad_token_id)
+                attention_mask = pad[:, None, None, :].to(dtype) * -1e4
+                if past_len is not None:          # everything already cached is visible
+                    attention_mask = torch.cat([attention_mask.new_zeros(attention_mask.shape[0], 1, 1, past_len), attention_mask], dim=-1)
         elif attention_mask.dim() == 2:
-            attention_mask = (1.0 - attention_mask[:, None, None, :].to(self.pooler.dense.weight.dtype)) * -1e4
-        x = self.embeddings(input_ids, token_type_ids, position_ids, task_type_ids)
-        if self.sequence_parallel:
-            assert x.shape[1] % C.group_size(self.mp_group) == 0, "sequence length must divide by the tensor-parallel degree under sequence parallelism"
-            x = C.scatter_seq(x.transpose(0, 1).contiguous(), self.mp_group)          # [b, s, h] -> [s/n, b, h]
-        seq = self.encoder(x, attention_mask)
-        if self.sequence_parallel:
-            seq = C.gather_seq(seq, self.mp_group).transpose(0, 1).contiguous()       # heads and pooler run replicated on the full sequence
-        return seq, self.pooler(seq)
+            attention_mask = (1.0 - attention_mask[:, None, None, :].to(dtype)) * -1e4
+        x = self.embeddings(input_ids, token_type_ids, position_ids, task_type_ids, inputs_embeds, past_len)
+        detailed = past_key_values is not None or bool(use_cache) or output_hidden_states or output_attentions or return_dict
+        if not detailed:
+            if self.sequence_parallel:
+                assert x.shape[1] % C.group_size(self.mp_group) == 0, "sequence length must divide by the tensor-parallel degree under sequence parallelism"
+                x = C.scatter_seq(x.transpose(0, 1).contiguous(), self.mp_group)          # [b, s, h] -> [s/n, b, h]
+            seq = self.encoder(x, attention_mask)
+            if self.sequence_parallel:
+                seq = C.gather_seq(seq, self.mp_group).transpose(0, 1).contiguous()       # heads and pooler run replicated on the full sequence
+            return seq, self.pooler(seq)
+        assert not self.sequence_parallel, "caches / per-layer outputs are not available with sequence parallelism"
+        self.encoder._use_cache = use_cache
+        try:
+            enc = self.encoder(x, attention_mask, past_key_values, output_attentions, output_hidden_states, return_dict)
+        finally:
+            self.encoder._use_cache = None
+        if isinstance(enc, torch.Tensor):
+            return enc, self.pooler(enc)
+        from .model_outputs import BaseModelOutputWithPoolingAndCrossAttentions
+
+        seq = enc[0]
+        return BaseModelOutputWithPoolingAndCrossAttentions(last_hidden_state=seq, pooler_output=self.pooler(seq), past_key_values=enc.past_key_values,
+                                                            hidden_states=enc.hidden_states, attentions=enc.attentions)
 
 
 class ErnieLMPredictionHead(nn.Module):
@@ -265,9 +372,29 @@ class ErnieForPretraining(nn.Module):
         self.cls = ErniePretrainingHeads(ernie.hidden_size, vocab_size, hidden_act, ernie.embeddings.word_embeddings.weight, ernie.mp_group,
                                          ernie.initializer_range, binary_head, p.dtype, p.device)
 
-    def forward(self, input_ids, token_type_ids=None, position_ids=None, attention_mask=None, masked_positions=None):
-        seq, pooled = self.ernie(input_ids, token_type_ids, position_ids, attention_mask)
-        return self.cls(seq, pooled, masked_positions)
+    def forward(self, input_ids=None, token_type_ids=None, position_ids=None, attention_mask=None, masked_positions=None, inputs_embeds=None,
+                labels=None, next_sentence_label=None, output_hidden_states=False, output_attentions=False, return_dict=False):
+        """``(prediction_scores, seq_relationship_score)`` — what the training module consumes.  With ``labels`` and ``next_sentence_label``
+        the summed MLM + sentence-order loss is prepended; ``return_dict=True`` gives an ``ErnieForPreTrainingOutput``
+        (reference single_model.py:486-560)."""
+        if inputs_embeds is None and labels is None and not (output_hidden_states or output_attentions or return_dict):
+            seq, pooled = self.ernie(input_ids, token_type_ids, position_ids, attention_mask)
+            return self.cls(seq, pooled, masked_positions)
+        outputs = self.ernie(input_ids, token_type_ids, position_ids, attention_mask, inputs_embeds=inputs_embeds,
+                             output_hidden_states=output_hidden_states, output_attentions=output_attentions, return_dict=return_dict)
+        scores, rel = self.cls(outputs[0], outputs[1], masked_positions)
+        loss = None
+        if labels is not None and next_sentence_label is not None:
+            full = C.gather_last_dim(scores, self.ernie.mp_group) if C.group_size(self.ernie.mp_group) > 1 else scores
+            loss = F.cross_entropy(full.reshape(-1, full.shape[-1]).float(), labels.reshape(-1).long()) \
+                + F.cross_entropy(rel.reshape(-1, 2).float(), next_sentence_label.reshape(-1).long())
+        if not return_dict:
+            out = (scores, rel) + tuple(outputs[2:])
+            return ((loss,) + out) if loss is not None else out
+        from .model_outputs import ErnieForPreTrainingOutput
+
+        return ErnieForPreTrainingOutput(loss=loss, prediction_logits=scores, seq_relationship_logits=rel, hidden_states=outputs.hidden_states,
+                                         attentions=outputs.attentions)
 
 
 ErnieForPretrainingHybrid = ErnieForPretraining
@@ -299,10 +426,29 @@ class ErnieForSequenceClassification(nn.Module):
         self.ernie = ernie
         p = ernie.pooler.dense.weight
         self.dropout_p = 0.1 if dropout is None else dropout
+        self.num_classes = num_classes
         self.classifier = nn.Linear(ernie.hidden_size, num_classes, dtype=p.dtype, device=p.device)
         with torch.no_grad():
             self.classifier.weight.normal_(0.0, ernie.initializer_range); self.classifier.bias.zero_()
 
-    def forward(self, input_ids, token_type_ids=None, position_ids=None, attention_mask=None):
-        _, pooled = self.ernie(input_ids, token_type_ids, position_ids, attention_mask)
-        return self.classifier(OF.dropout(pooled, self.dropout_p, self.training, "global_seed"))
+    def forward(self, input_ids=None, token_type_ids=None, position_ids=None, attention_mask=None, inputs_embeds=None, labels=None,
+                output_hidden_states=False, output_attentions=False, return_dict=False):
+        """The logits; ``labels`` adds the loss in front (MSE for one class, cross entropy for integer labels, BCE-with-logits for float
+        multi-label targets) and ``return_dict=True`` gives a ``SequenceClassifierOutput`` (reference single_model.py:672-735)."""
+        outputs = self.ernie(input_ids, token_type_ids, position_ids, attention_mask, inputs_embeds=inputs_embeds,
+                             output_hidden_states=output_hidden_states, output_attentions=output_attentions, return_dict=return_dict)
+        logits = self.classifier(OF.dropout(outputs[1], self.dropout_p, self.training, "global_seed"))
+        loss = None
+        if labels is not None:
+            if self.num_classes == 1:
+                loss = F.mse_loss(logits.float(), labels.to(torch.float32))
+            elif labels.dtype in (torch.int64, torch.int32):
+                loss = F.cross_entropy(logits.reshape(-1, self.num_classes).float(), labels.reshape(-1).long())
+            else:
+                loss = F.binary_cross_entropy_with_logits(logits.float(), labels.to(torch.float32))
+        if not return_dict:
+            out = (logits,) + tuple(outputs[2:])
+            return ((loss,) + out) if loss is not None else (out[0] if len(out) == 1 else out)
+        from .model_outputs import SequenceClassifierOutput
+
+        return SequenceClassifierOutput(loss=loss, logits=logits, hidden_states=outputs.hidden_states, attentions=outputs.attentions)

@@ -20,8 +20,9 @@ _MOVED = {
     f"{_LM}.ernie.dygraph": f"{_LM}.ernie", f"{_LM}.ernie.dygraph.single_model": f"{_LM}.ernie.model", f"{_LM}.ernie.dygraph.hybrid_model": f"{_LM}.ernie.model",
     f"{_LM}.ernie.auto": f"{_LM}.ernie", f"{_LM}.ernie.auto.auto_model": f"{_LM}.ernie.model", f"{_LM}.ernie.auto.auto_module": f"{_LM}.ernie.ernie_module",
     f"{_LM}.ernie.auto.auto_transformer": f"{_LM}.ernie.model", f"{_LM}.ernie.layers": f"{_LM}.ernie.model", f"{_LM}.ernie.layers.transformer": f"{_LM}.ernie.model",
-    f"{_LM}.ernie.layers.distributed_transformer": f"{_LM}.ernie.model",
-    f"{_LM}.t5": f"{_MM}.t5", f"{_LM}.t5.modeling": f"{_MM}.t5.modeling", f"{_LM}.debertav2": f"{_MM}.debertav2", f"{_LM}.debertav2.modeling": f"{_MM}.debertav2.modeling",
+    f"{_LM}.ernie.layers.distributed_transformer": f"{_LM}.ernie.model", f"{_LM}.ernie.layers.model_outputs": f"{_LM}.ernie.model_outputs",
+    f"{_LM}.ernie.layers.utils": f"{_LM}.ernie.utils",
+    f"{_LM}.t5": f"{_MM}.t5", f"{_LM}.t5.modeling": f"{_MM}.t5.modeling", f"{_LM}.t5.utils": f"{_MM}.t5.utils", f"{_LM}.debertav2": f"{_MM}.debertav2", f"{_LM}.debertav2.modeling": f"{_MM}.debertav2.modeling",
     f"{_LM}.utils": f"{_LM}.language_module", f"{_LM}.auto_utils": f"{_LM}.language_module",
     f"{_LM}.moe.gate.base_gate": f"{_LM}.moe.gate.gates", f"{_LM}.moe.gate.naive_gate": f"{_LM}.moe.gate.gates", f"{_LM}.moe.gate.gshard_gate": f"{_LM}.moe.gate.gates",
     f"{_LM}.moe.gate.switch_gate": f"{_LM}.moe.gate.gates", f"{_LM}.moe.comm": f"{_LM}.moe.comm_ops",
@@ -31,6 +32,7 @@ _MOVED = {
     "data.tokenizers.t5_tokenization_utils": "data.tokenizers.tokenization_utils_base",
     "data.data_tools.ernie.preprocess": "data.data_tools.ernie", "data.data_tools.ernie.preprocess.create_pretraining_data": "data.data_tools.ernie.create_pretraining_data",
     "data.data_tools.ernie.preprocess.trans_to_json": "data.data_tools.ernie.trans_to_json", "data.data_tools.ernie.preprocess.words_segmentation": "data.data_tools.ernie.words_segmentation",
+    "data.data_tools.ernie.preprocess.ernie_dataset": "data.dataset.ernie.ernie_dataset", "data.data_tools.ernie.preprocess.dataset_utils": "data.dataset.ernie.dataset_utils",
     "ops.topp_sampling": "ops.functional",
 }
 
