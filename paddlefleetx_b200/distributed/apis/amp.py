@@ -71,6 +71,53 @@ class GradScaler:
         self._scale, self._good, self._bad = sd["scale"], sd.get("good", 0), sd.get("bad", 0)
 
 
+def unscale_method(self, optimizer) -> None:
+    """Explicit unscale for code that drives the scaler by hand (reference amp.py:193-225, bound onto the scaler as ``_unscale``): divides
+    every fp32 ``main_grad`` (or plain ``grad``) of the optimizer's parameters by the loss scale in place, records whether any value was
+    non-finite in ``self._found_inf`` and, when the job has model / pipeline / sharding ranks, agrees on that flag across all ranks.
+    The engine does not come through here: the flat optimizer folds unscale + check + clip into its ``clip_coef`` kernel."""
+    if not self._enable:
+        return
+    params = []
+    groups = getattr(optimizer, "param_groups", None) or getattr(optimizer, "_param_groups", None)
+    if groups and isinstance(groups[0], dict):
+        for g in groups:
+            params.extend(g["params"])
+    else:
+        params = list(getattr(optimizer, "_parameter_list", None) or [])
+    grads = []
+    for prm in params:
+        g = getattr(prm, "main_grad", None)
+        if g is not None:
+            assert g.dtype == torch.float32, "main_grad accumulates in fp32"
+        else:
+            g = prm.grad
+        if g is not None:
+            grads.append(g)
+    found = False
+    if grads:
+        dev = grads[0].device
+        found_inf = torch.zeros(1, dtype=torch.float32, device=dev)
+        inv = torch.full((1,), 1.0 / self._scale, dtype=torch.float32, device=dev)
+        by_dtype = {}
+        for g in grads:
+            by_dtype.setdefault((g.dtype, g.device), []).append(g)
+        for (_, gdev), gl in by_dtype.items():
+            torch._amp_foreach_non_finite_check_and_unscale_(gl, found_inf.to(gdev) if gdev != dev else found_inf, inv.to(gdev))
+        found = bool(found_inf.item() > 0)
+    hcg = self.hcg
+    if hcg is None:
+        from . import env
+
+        hcg = env._hcg if getattr(env, "_hcg", None) is not None else None
+    if hcg is not None and dist.is_available() and dist.is_initialized() and hcg.nranks > hcg.get_data_parallel_world_size():
+        flag = torch.tensor([1.0 if found else 0.0], device=grads[0].device if grads else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        found = bool(flag.item() > 0)
+    self._found_inf = found
+
+
+GradScaler._unscale = unscale_method
 MixPrecisionScaler = GradScaler
 
 

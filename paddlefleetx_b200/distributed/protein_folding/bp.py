@@ -14,6 +14,14 @@ def _grp(group=None):
     return group if group is not None else scg.get_bp_group()
 
 
+def get_world_size() -> int:
+    return scg.get_bp_world_size()
+
+
+def get_rank_in_group() -> int:
+    return scg.get_bp_rank()
+
+
 class _BroadcastGrad(torch.autograd.Function):
     """fwd: broadcast from ``src`` (index in group); bwd: sum grads onto the producer, zero elsewhere."""
 
@@ -46,6 +54,23 @@ class _GradBroadcast(torch.autograd.Function):
         g = g.contiguous().clone()
         dist.broadcast(g, src=ctx.group.ranks[ctx.src], group=ctx.group.process_group)
         return g, None, None
+
+
+class BroadcastGrad(torch.autograd.Function):
+    """Reference class form (bp.py:51-62): ``BroadcastGrad.apply(input, src)`` — identity forward, the gradient of rank ``src`` of the bp
+    group reaches every rank in backward."""
+
+    @staticmethod
+    def forward(ctx, input, src):
+        ctx.src = src
+        return input.clone()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        g, grp = grad_output.contiguous().clone(), _grp()
+        if C.group_size(grp) > 1 and grp.process_group is not None:
+            dist.broadcast(g, src=grp.ranks[ctx.src], group=grp.process_group)
+        return g, None
 
 
 def broadcast_grad_for_backward(x, src: int = 0, group=None):
@@ -113,6 +138,20 @@ class _SyncEvoformerResults(torch.autograd.Function):
         return (g_msa if rank == 0 else zero_m), (g_pair if rank == 1 else zero_p), (g_pair if rank == 0 else zero_p), None
 
 
+class SyncEvoformerResults(torch.autograd.Function):
+    """Reference class form and argument order (bp.py:90-111): ``msa, pair = SyncEvoformerResults.apply(outer, msa, pair)`` on the bp group."""
+
+    @staticmethod
+    def forward(ctx, outer, msa, pair):
+        ctx.group = _grp()
+        return _SyncEvoformerResults.forward(ctx, msa, pair, outer, ctx.group)
+
+    @staticmethod
+    def backward(ctx, g_msa, g_pair):
+        gm, gp, go, _ = _SyncEvoformerResults.backward(ctx, g_msa, g_pair)
+        return go, gm, gp
+
+
 def sync_evoformer_results(msa_act, pair_act, outer=None, group=None):
     """``SyncEvoformerResults`` (reference bp.py:84-113): rank 0 owns the fresh MSA activation and the outer-product-mean update, rank 1 the
     fresh pair activation; every rank leaves with ``(msa, pair + outer)``."""
@@ -125,4 +164,9 @@ def sync_evoformer_results(msa_act, pair_act, outer=None, group=None):
 
 
 def grad_sync(params, group=None) -> None:
-    C.fused_allreduce_gradients(list(params), _grp(group), scale=1.0)
+    """Sum the gradients of parameters replicated across the bp group.  Accepts a parameter list or the reference's optimizer
+    ``param_groups`` (only groups flagged ``bp: True`` take part; bp.py:127-152)."""
+    params = list(params)
+    if params and isinstance(params[0], dict):
+        params = [q for grp in params if grp.get("bp", False) for q in grp["params"] if not getattr(q, "tp_sharded", False)]
+    C.fused_allreduce_gradients(params, _grp(group), scale=1.0)

@@ -11,6 +11,10 @@ import torch.distributed as dist
 from ...parallel.topology import _Group
 
 
+def ensure_divisibility(numerator: int, denominator: int) -> None:
+    assert numerator % denominator == 0, f"{numerator} is not divisible by {denominator}"
+
+
 class SingletonCommunicationGroup:
     def __init__(self):
         self._groups: Dict[str, _Group] = {}
@@ -50,6 +54,25 @@ class SingletonCommunicationGroup:
     def get_rank_in_group(self, name: str) -> int:
         g = self._groups.get(name)
         return 0 if g is None else max(g.rank, 0)
+
+    @property
+    def initialized(self) -> bool:
+        return self._initialised
+
+    def __getattr__(self, name: str):
+        """The reference attaches per-axis attributes at ``init_process_group`` time (scg.py:165-193): ``scg.<axis>_group``,
+        ``scg.get_rank_in_<axis>_group()`` and ``scg.get_<axis>_world_size()`` for whatever axis names the caller chose.  They resolve here
+        for every axis that was built, and — like the reference, where user code probes them with ``hasattr`` — do not exist before."""
+        groups = self.__dict__.get("_groups", {})
+        if name.endswith("_group") and not name.startswith("get_") and name[:-len("_group")] in groups:
+            return groups[name[:-len("_group")]]
+        if name.startswith("get_rank_in_") and name.endswith("_group") and name[len("get_rank_in_"):-len("_group")] in groups:
+            axis = name[len("get_rank_in_"):-len("_group")]
+            return lambda: self.get_rank_in_group(axis)
+        if name.startswith("get_") and name.endswith("_world_size") and name[len("get_"):-len("_world_size")] in groups:
+            axis = name[len("get_"):-len("_world_size")]
+            return lambda: self.get_world_size(axis)
+        raise AttributeError(name)
 
     # convenience accessors used by the model code
     def get_dp_group(self): return self.get_group("dp")

@@ -57,7 +57,7 @@ class MSARowAttentionWithPairBias(nn.Module):
         # msa [b, S(/n), R, c_m]; pair [b, R(/n), R, c_z] sharded on dim 1 under DAP
         m = self.ln_m(msa)
         z = self.pair_bias(self.ln_z(pair))                       # [b, R/n, R, h]
-        z = dap.all_gather(z, axis=1)                             # full [b, R, R, h] on every rank
+        z = dap.gather_full(z, axis=1)                             # full [b, R, R, h] on every rank
         nb = z.permute(0, 3, 1, 2).unsqueeze(1)                   # [b, 1, h, R, R]
         bias = (1e9 * (msa_mask - 1.0))[:, :, None, None, :]
         return self.attn(m, m, bias, nb)
@@ -141,12 +141,12 @@ class TriangleMultiplication(nn.Module):
         a = self.left(z) * mask * torch.sigmoid(self.left_gate(z))
         b_ = self.right(z) * mask * torch.sigmoid(self.right_gate(z))
         if self.outgoing:
-            b_full = dap.all_gather(b_, axis=1)
+            b_full = dap.gather_full(b_, axis=1)
             x = torch.einsum("bikc,bjkc->bijc", a, b_full)
         else:
             # incoming: out[i,j] = sum_k a[k,i] b[k,j]: contraction runs over the sharded axis -> work on column shards
             a_c, b_c = dap.row_to_col(a), dap.row_to_col(b_)         # [b, R, R/n, c]
-            b_full = dap.all_gather(b_c, axis=2)
+            b_full = dap.gather_full(b_c, axis=2)
             x = torch.einsum("bkic,bkjc->bijc", a_c, b_full)          # [b, R/n(i), R, c]
         return self.out(self.ln_out(x)) * torch.sigmoid(self.gate(z))
 
@@ -164,7 +164,7 @@ class TriangleAttention(nn.Module):
         if not self.starting:
             pair, pair_mask = dap.row_to_col(pair).transpose(1, 2), dap.row_to_col(pair_mask.unsqueeze(-1)).squeeze(-1).transpose(1, 2)
         z = self.ln(pair)
-        nb = dap.all_gather(self.bias(z), axis=1).permute(0, 3, 1, 2).unsqueeze(1)
+        nb = dap.gather_full(self.bias(z), axis=1).permute(0, 3, 1, 2).unsqueeze(1)
         bias = (1e9 * (pair_mask - 1.0))[:, :, None, None, :]
         out = self.attn(z, z, bias, nb)
         if not self.starting:

@@ -20,8 +20,8 @@ class OuterProductMean(nn.Module):
         mask = msa_mask.unsqueeze(-1)
         m = self.ln(msa)
         left = self.left(m) * mask
-        right = dap.all_gather(self.right(m) * mask, axis=2)
-        mask_full = dap.all_gather(mask, axis=2)
+        right = dap.gather_full(self.right(m) * mask, axis=2)
+        mask_full = dap.gather_full(mask, axis=2)
         outer = torch.einsum("bsic,bsjd->bijcd", left, right)
         norm = torch.einsum("bsic,bsjd->bijcd", mask, mask_full)
         out = self.out(outer.flatten(-2))

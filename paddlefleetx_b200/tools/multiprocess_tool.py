@@ -18,6 +18,42 @@ def read_commands(path):
         return [line.strip() for line in f if line.strip() and not line.lstrip().startswith("#")]
 
 
+read_command = read_commands          # the reference's spelling (tools/multiprocess_tool.py:60)
+
+
+def process_fn(cmd_list, retries=0, timeout=None):
+    """Run a slice of commands one after another; failures are printed and do not stop the slice (reference multiprocess_tool.py:50-57).
+    Returns the list of ``(cmd, returncode, seconds, error_tail)`` results."""
+    results = []
+    for cmd in cmd_list:
+        res = run_one(cmd, retries, timeout)
+        if res[1] != 0:
+            print(f"execute command: {cmd} failed.")
+        results.append(res)
+    return results
+
+
+def parallel_process(cmd_list, nproc=20, retries=0, timeout=None):
+    """Run ``cmd_list`` with ``nproc`` commands in flight and return the per-command results in completion order
+    (reference multiprocess_tool.py:69-86; here a shared queue instead of fixed slices)."""
+    import os
+    import warnings
+
+    if nproc > (os.cpu_count() or 1):
+        warnings.warn("The set number of processes exceeds the number of cpu cores, please confirm whether it is reasonable.")
+    results = []
+    if not cmd_list:
+        return results
+    # threads are enough: each worker blocks in subprocess.run, the work happens in the child processes
+    with ThreadPoolExecutor(max_workers=max(1, min(nproc, len(cmd_list)))) as pool:
+        futures = [pool.submit(run_one, c, retries, timeout) for c in cmd_list]
+        for done, fut in enumerate(as_completed(futures), 1):
+            res = fut.result()
+            print(f"[{done}/{len(cmd_list)}] rc={res[1]} {res[2]:.1f}s  {res[0]}", flush=True)
+            results.append(res)
+    return results
+
+
 def run_one(cmd, retries=0, timeout=None):
     err = ""
     for attempt in range(retries + 1):
@@ -44,15 +80,8 @@ def main(argv=None):
     if not cmds:
         print("no commands to run")
         return 0
-    t0, failed = time.time(), []
-    # threads are enough: each worker blocks in subprocess.run, the work happens in the child processes
-    with ThreadPoolExecutor(max_workers=max(1, min(a.num_proc, len(cmds)))) as pool:
-        futures = [pool.submit(run_one, c, a.retries, a.timeout) for c in cmds]
-        for done, fut in enumerate(as_completed(futures), 1):
-            cmd, code, dt, err = fut.result()
-            print(f"[{done}/{len(cmds)}] rc={code} {dt:.1f}s  {cmd}", flush=True)
-            if code:
-                failed.append((cmd, code, err))
+    t0 = time.time()
+    failed = [(cmd, code, err) for cmd, code, _, err in parallel_process(cmds, a.num_proc, a.retries, a.timeout) if code]
     print(f"{len(cmds) - len(failed)} succeeded, {len(failed)} failed in {time.time() - t0:.1f}s")
     for cmd, code, err in failed:
         print(f"FAILED rc={code}: {cmd}\n    {err}")

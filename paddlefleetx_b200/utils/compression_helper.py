@@ -151,6 +151,26 @@ def _norm(w: torch.Tensor, criterion: str, dims) -> torch.Tensor:
     return w.float().abs().sum(dims) if criterion.startswith("l1") else w.float().pow(2).sum(dims).sqrt()
 
 
+def get_pruned_params(model: nn.Module) -> list:
+    """Names of the weights structured pruning acts on: 2-D weights of (tensor-parallel) linear layers that are a fused QKV projection
+    (``out = 3 * in``) or a first FFN projection (``out = 4 * in``); their consumers (attention output / second FFN projection) are pruned
+    along with them (reference utils/compression_helper.py:19-42 — there in Paddle's ``[in, out]`` layout, here ``[out, in]``)."""
+    from ..parallel.tp_layers import ColumnParallelLinear, RowParallelLinear
+
+    names = []
+    for mod_name, mod in model.named_modules():
+        if not isinstance(mod, (nn.Linear, ColumnParallelLinear, RowParallelLinear)):
+            continue
+        w = getattr(mod, "weight", None)
+        if w is None or w.dim() != 2:
+            continue
+        world = getattr(mod, "world", None) or 1
+        out_f, in_f = w.shape[0] * (world if isinstance(mod, ColumnParallelLinear) else 1), w.shape[1]
+        if out_f in (3 * in_f, 4 * in_f):
+            names.append(f"{mod_name}.weight" if mod_name else "weight")
+    return names
+
+
 def prune_model(model: nn.Module, cfg: dict) -> nn.Module:
     """Structured pruning of every GPT-style decoder layer: FFN channels (linear1 out / linear2 in) and attention heads
     (qkv rows per head / out_proj columns)."""

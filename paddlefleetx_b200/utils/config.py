@@ -106,6 +106,15 @@ def _load_yaml_tree(path: str, _seen: Optional[set] = None) -> dict:
     return tree
 
 
+def create_attr_dict(yaml_config: dict) -> dict:
+    """In-place: nested plain dicts become ``AttrDict`` and literal-looking strings (``"1e-4"``, ``"[1, 2]"``, ``"True"``) their values
+    (reference utils/config.py:226-240).  ``parse_config`` does the same on a freshly loaded tree; this is the entry point for a config that
+    was assembled by hand."""
+    for key, value in list(yaml_config.items()):
+        yaml_config[key] = _wrap(value)
+    return yaml_config
+
+
 def parse_config(cfg_file: str) -> AttrDict:
     return _wrap(_load_yaml_tree(cfg_file))
 
@@ -145,6 +154,14 @@ def _assign(node: Any, keys: list, value: str) -> None:
         if head not in node:
             print(f"A new field ({head}) detected!")
         node[head] = _wrap(_literal(value))
+
+
+def override(dl, ks: list, v: str) -> None:
+    """Set ``dl[ks[0]][ks[1]]... = v`` on a tree of dicts and lists; list levels take integer keys, unknown dict keys are created with a
+    printed notice, the value string is read as a Python literal when it is one (reference utils/config.py:333-367)."""
+    assert isinstance(dl, (list, dict)), f"{dl} should be a list or a dict"
+    assert len(ks) > 0, "length of keys should be larger than 0"
+    _assign(dl, list(ks), v)
 
 
 def override_config(config: AttrDict, options: Optional[Iterable[str]] = None) -> AttrDict:
@@ -290,29 +307,31 @@ def check_config(cfg: AttrDict) -> None:
             cfg.Global["device"] = "cpu"
 
 
+def print_dict(d: dict, delimiter: int = 0) -> None:
+    """Log a nested dict one key per line, children indented by four columns, a rule after every top-level section
+    (reference utils/config.py:284-301)."""
+    pad = " " * delimiter
+    for k in sorted(d, key=str):
+        v = d[k]
+        if isinstance(v, dict):
+            logger.info(f"{pad}{k} : ")
+            print_dict(v, delimiter + 4)
+        elif isinstance(v, list) and v and isinstance(v[0], dict):
+            logger.info(f"{pad}{k} : ")
+            for item in v:
+                if isinstance(item, dict):
+                    print_dict(item, delimiter + 4)
+                else:          # a bare op name among ``{op: {args}}`` entries (``- ToCHWImage``)
+                    logger.info(f"{pad}    {item}")
+        else:
+            logger.info(f"{pad}{k} : {v}")
+        if delimiter == 0:
+            logger.info("-" * 60)
+
+
 def print_config(cfg: AttrDict) -> None:
     advertise()
-
-    def walk(node: dict, indent: int) -> None:
-        for k in sorted(node, key=str):
-            v = node[k]
-            pad = " " * indent
-            if isinstance(v, dict):
-                logger.info(f"{pad}{k} : ")
-                walk(v, indent + 4)
-            elif isinstance(v, list) and v and isinstance(v[0], dict):
-                logger.info(f"{pad}{k} : ")
-                for item in v:
-                    if isinstance(item, dict):
-                        walk(item, indent + 4)
-                    else:          # a bare op name among ``{op: {args}}`` entries (``- ToCHWImage``)
-                        logger.info(f"{pad}    {item}")
-            else:
-                logger.info(f"{pad}{k} : {v}")
-            if indent == 0:
-                logger.info("-" * 60)
-
-    walk(cfg, 0)
+    print_dict(cfg)
 
 
 def get_config(fname: str, overrides: Optional[Iterable[str]] = None, show: bool = False,
@@ -365,6 +384,118 @@ def get_auto_config(fname: str, overrides: Optional[Iterable[str]] = None, show:
     if show:
         print_config(cfg)
     return cfg
+
+
+# ---- the reference's auto-parallel config steps (utils/config.py:418-613) as individually callable functions.  ``get_auto_config`` above
+# derives the same quantities through the eager pipeline; these serve code that assembles an auto config step by step.
+def process_auto_dist_configs(config: AttrDict, nranks: Optional[int] = None) -> None:
+    """Degrees for the auto engine: ``dp = nranks / (mp * pp)`` — ZeRO sharding lives INSIDE the data dimension here (it is a strategy of the
+    data-parallel ranks, ``Strategy.sharding``), unlike the eager path where it is a topology axis of its own."""
+    d = config["Distributed"]
+    nranks = nranks or world_size_hint()
+    mp, pp = d.setdefault("mp_degree", 1) or 1, d.setdefault("pp_degree", 1) or 1
+    sh = d.setdefault("sharding", AttrDict())
+    sd = sh.setdefault("sharding_degree", 1) or 1
+    other = mp * pp
+    assert nranks % other == 0, "Requires nranks should be divided by mp_degree*pp_degree."
+    dp = d.setdefault("dp_degree", nranks // other) or nranks // other
+    d["dp_degree"] = dp
+    assert nranks == dp * other, (f"Mismatched config using {nranks} cards with dp_degree[{dp}],mp_degree[{mp}], pp_degree[{pp}] and "
+                                  f"sharding_degree[{sd}]")
+
+
+def process_auto_global_configs(config: AttrDict) -> None:
+    d, g = config["Distributed"], config["Global"]
+    dp, pp = d["dp_degree"], d["pp_degree"]
+    g["enable_partial_send_recv"] = True
+    if (config.get("Model") or {}).get("sequence_parallel") and pp > 1:
+        g["enable_partial_send_recv"] = False
+        logger.warning("if config.Distributed.pp_degree > 1 and config.Model.sequence_parallel is True, "
+                       "config.Global.enable_partial_send_recv will be set False.")
+    gbs, lbs = g.get("global_batch_size"), g.get("local_batch_size")
+    if gbs is None and lbs is None:
+        raise ValueError("global_batch_size or local_batch_size should be set.")
+    if gbs is not None and lbs is not None:
+        assert gbs // lbs == dp, f"global_batch_size[{gbs}] should be divided by local_batch_size[{lbs}] when dp_degree is [{dp}]"
+    elif gbs is not None:
+        assert gbs % dp == 0, f"global_batch_size[{gbs}] should be divided by dp_degree[{dp}]"
+        g["local_batch_size"] = gbs // dp
+    else:
+        g["global_batch_size"] = lbs * dp
+    assert g["local_batch_size"] % g["micro_batch_size"] == 0
+
+
+def process_auto_engine_configs(config: AttrDict) -> None:
+    e = config.Engine
+    if e.get("verbose") is None:
+        e["verbose"] = 2
+    if e.get("logging_freq") is None:
+        e["logging_freq"] = 10
+    sl = e.setdefault("save_load", AttrDict())
+    if sl.get("save_steps") in (None, -1):
+        sl["save_steps"] = sys.maxsize
+    if sl.get("save_epoch") in (None, -1):
+        sl["save_epoch"] = 1
+    sl.setdefault("output_dir", "./output")
+    sl.setdefault("ckpt_dir", None)
+    for key, default in (("max_steps", 500000), ("eval_freq", -1), ("eval_iters", 0), ("num_train_epochs", 1)):
+        e.setdefault(key, default)
+    if e.get("test_iters") is None:
+        e["test_iters"] = e["eval_iters"] * 10
+    e["accumulate_steps"] = config.Global.local_batch_size // config.Global.micro_batch_size
+
+
+def process_auto_strategy(config: AttrDict) -> None:
+    """``Engine.strategy``: the knobs the reference hands to ``auto.Strategy`` (amp, recompute, sharding, gradient merge, QAT, tuning) as one
+    plain ``AttrDict`` with the same section / field names — ``AutoEngine`` reads them from here."""
+    e = config.Engine
+    amp_cfg = e.get("mix_precision") or {}
+    st = AttrDict(auto_mode="semi", seed=config.Global.get("seed"))
+    st["amp"] = AttrDict(enable=amp_cfg.get("enable", False), dtype=amp_cfg.get("dtype", "float16"), level=amp_cfg.get("level", "o2"),
+                         init_loss_scaling=amp_cfg.get("scale_loss", 32768), custom_black_list=amp_cfg.get("custom_black_list") or [],
+                         custom_white_list=amp_cfg.get("custom_white_list") or [], use_fp16_guard=amp_cfg.get("use_fp16_guard", False),
+                         use_bf16_guard=amp_cfg.get("use_bf16_guard", False))
+    st["recompute"] = AttrDict(enable=False, no_recompute_segments=[], enable_tuning=False)
+    model = config.get("Model")
+    if model is not None:
+        skip = model.get("no_recompute_layers") or []
+        assert isinstance(skip, list), "no_recompute_layers should be a list"
+        assert all(isinstance(i, int) for i in skip), "all values in no_recompute_layers should be an integer"
+        if skip:
+            assert min(skip) >= 0, "the min value in no_recompute_layers should >= 0"
+            assert max(skip) < model["num_layers"], "the max value in no_recompute_layers should < num_layers"
+        skip = sorted(set(skip))
+        model["no_recompute_layers"] = skip
+        tuning = config.get("Tuning") or {}
+        st["recompute"] = AttrDict(enable=model.get("use_recompute", False), no_recompute_segments=skip,
+                                   enable_tuning=bool(tuning) and bool(tuning.get("tuning_recompute", False)))
+    sh = config.Distributed.get("sharding") or {}
+    st["sharding"] = AttrDict(enable=sh.get("sharding_degree", 1) > 1, degree=sh.get("sharding_degree", 1), stage=sh.get("sharding_stage", 1))
+    k = e.get("accumulate_steps", 1) or 1
+    st["gradient_merge"] = AttrDict(enable=k > 1, k_steps=k)
+    q = config.get("Quantization") or {}
+    st["qat"] = AttrDict(enable=q.get("enable", False), channel_wise_abs_max=q.get("channel_wise_abs_max", True), weight_bits=q.get("weight_bits", 8),
+                         activation_bits=q.get("activation_bits", 8), onnx_format=q.get("onnx_format", True))
+    t = config.get("Tuning") or {}
+    st["tuning"] = AttrDict(enable=t.get("enable", False), profile_start_step=t.get("profile_start_step", 1),
+                            profile_end_step=t.get("profile_end_step", 1), run_after_tuning=t.get("run_after_tuning", True), debug=t.get("debug", True))
+    e["strategy"] = st
+
+
+def process_auto_ckpt_dir(config: AttrDict) -> None:
+    """``Engine.save_load.ckpt_dir`` of an auto run is a ``dirname/prefix`` (files ``<prefix>_dist<rank>.*``), not a directory; a prefix
+    whose parent directory does not exist is dropped with a warning so that training starts from scratch."""
+    sl = config["Engine"]["save_load"]
+    ckpt = sl.get("ckpt_dir")
+    if ckpt is None:
+        return
+    assert not os.path.isdir(ckpt), (f"Wrong setting of ckpt_dir! ckpt_dir can't be a folder, but {ckpt} is a folder. Your `ckpt_dir` should be "
+                                     "`dirname/prefix` like `output/auto` if your model path is `output/auto_dist0.pdparams`")
+    assert not os.path.exists(ckpt), "Wrong setting of ckpt_dir: give the checkpoint prefix (e.g. gpt_auto_model_save/auto), not a file"
+    parent = os.path.split(ckpt)[0]
+    if parent and not os.path.exists(parent):
+        logger.warning(f"{parent} path is not existed! we will set ckpt_dir None.")
+        sl["ckpt_dir"] = None
 
 
 def parse_args(argv: Optional[list] = None) -> argparse.Namespace:

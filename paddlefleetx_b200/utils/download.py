@@ -66,3 +66,25 @@ def cached_path(url_or_path, cache_dir=None, md5sum=None):
     if os.path.exists(url_or_path):
         return url_or_path
     raise FileNotFoundError(url_or_path)
+
+
+def download(url, path):
+    """Fetch ``url`` to the exact file ``path``: local rank 0 downloads, the other ranks of the node wait for the file to appear
+    (reference utils/download.py:117-128)."""
+    rank, world = int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1 and rank != 0:
+        t0 = time.time()
+        while not os.path.exists(path):
+            if time.time() - t0 > 3600:
+                raise TimeoutError(f"waited 1h for local rank 0 to download {url}")
+            time.sleep(1)
+        return path
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    last = None
+    for _ in range(3):                      # the reference retries three times
+        try:
+            _download(url, path)
+            return path
+        except Exception as exc:            # noqa: BLE001 - reported below with the target path
+            last = exc
+    raise RuntimeError(f"cannot fetch {url}: {last}. Place the file at {path} manually (offline environment).") from last

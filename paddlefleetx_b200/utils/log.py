@@ -11,9 +11,12 @@ formatter, no third-party colour packages.
 """
 from __future__ import annotations
 
+import contextlib
+import datetime
 import logging
 import os
 import sys
+import threading
 import time
 
 TRAIN_LEVEL = 21
@@ -74,6 +77,77 @@ def _build() -> FleetLogger:
 logger: FleetLogger = _build()
 
 
+class Logger:
+    """Object-style logger of the reference (utils/log.py:65-150): ``log.info(msg)`` / ``log.TRAIN(msg)`` / ``log(level, msg)``, a global
+    ``disable()`` / ``enable()`` switch, ``use_terminator`` to rewrite one console line, and ``processing(msg)`` — a spinner that runs while
+    the ``with`` body works.  Records go through the same handler / formatter as the module-level ``logger``."""
+
+    LEVELS = {"DEBUG": logging.DEBUG, "INFO": logging.INFO, "TRAIN": TRAIN_LEVEL, "EVAL": EVAL_LEVEL, "WARNING": logging.WARNING,
+              "ERROR": logging.ERROR, "CRITICAL": logging.CRITICAL}
+
+    def __init__(self, name: str = None):
+        self.logger = logging.getLogger(name or "PaddleFleetX")
+        self.handler = logging.StreamHandler(sys.stdout)
+        self.handler.setFormatter(_AnsiFormatter(sys.stdout.isatty() or os.environ.get("PFX_FORCE_COLOR") == "1"))
+        if not self.logger.handlers:
+            self.logger.addHandler(self.handler)
+        else:
+            self.handler = self.logger.handlers[0]
+        self.logLevel = "DEBUG"
+        self.logger.setLevel(logging.DEBUG)
+        self.logger.propagate = False
+        self._is_enable = True
+        for key, level in self.LEVELS.items():
+
+            def emit(msg, _level=level):
+                self(_level, msg)
+
+            self.__dict__[key] = emit
+            self.__dict__[key.lower()] = emit
+
+    def disable(self):
+        self._is_enable = False
+
+    def enable(self):
+        self._is_enable = True
+
+    @property
+    def is_enable(self) -> bool:
+        return self._is_enable
+
+    def __call__(self, log_level, msg: str):
+        if self._is_enable:
+            self.logger.log(self.LEVELS.get(log_level, log_level) if isinstance(log_level, str) else log_level, msg)
+
+    @contextlib.contextmanager
+    def use_terminator(self, terminator: str):
+        old, self.handler.terminator = self.handler.terminator, terminator
+        try:
+            yield
+        finally:
+            self.handler.terminator = old
+
+    @contextlib.contextmanager
+    def processing(self, msg: str, interval: float = 0.1):
+        stop = threading.Event()
+
+        def spin():
+            i = 0
+            while not stop.is_set():
+                with self.use_terminator("\r"):
+                    self.info(f"{msg}: {'\\|/-'[i % 4]}")
+                stop.wait(interval)
+                i += 1
+
+        t = threading.Thread(target=spin, daemon=True)
+        t.start()
+        try:
+            yield
+        finally:
+            stop.set()
+            t.join()
+
+
 def advertise() -> None:
     """Banner shown above the config dump (reference: utils/log.py advertise())."""
     title = "PaddleFleetX-B200"
@@ -91,6 +165,11 @@ def device_synchronize() -> None:
 
     if torch.cuda.is_available():
         torch.cuda.synchronize()
+
+
+def convert_timestamp_to_data(timeStamp) -> str:
+    """Seconds -> ``H:MM:SS`` (the ETA field of the train line; reference utils/log.py:188-189)."""
+    return str(datetime.timedelta(seconds=int(timeStamp)))
 
 
 def get_timestamp() -> float:

@@ -619,3 +619,65 @@ def context_parallel_matches_single(rank, world, dp, sharding, cp, extra=()):
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
     for k, v in eng.module.model.state_dict().items():
         assert torch.allclose(v, ref_state[k], atol=5e-5, rtol=1e-4), k
+
+
+def dap_split_phase_pairs(rank, world):
+    """Reference call style of the DAP collectives: ``y = all_gather(x, axis)`` ... ``z = all_gather_opp(y, axis)`` (and the all-to-all pair),
+    in blocking and asynchronous mode, equal the one-shot ops in value and gradient; the class forms follow the reference signatures."""
+    from paddlefleetx_b200.distributed.protein_folding import dap
+    from paddlefleetx_b200.distributed.protein_folding.scg import scg
+
+    scg.init_process_group([("dp", None), ("dap", world)])
+    assert dap.get_world_size() == world and dap.get_rank_in_group() == rank
+    torch.manual_seed(10 + rank)
+    base = torch.randn(2, 4, 6, 3, dtype=torch.float64)
+    w = torch.randn(2, 4 * world, 6, 3, dtype=torch.float64)          # rank-specific weight: every rank's loss differs
+    for sync in (True, False):
+        dap.set_dap_sync_op(sync)
+        assert dap.get_dap_sync_op() is sync
+        for axis in (0, 1, 2):
+            shape = list(base.shape)
+            shape[axis] *= world
+            wa = torch.randn(shape, dtype=torch.float64, generator=torch.Generator().manual_seed(rank * 7 + axis))
+            x1 = base.clone().requires_grad_(True)
+            y = dap.all_gather(x1, axis=axis)
+            assert y.shape[0] == base.shape[0] * world                 # the rank-major stack, whatever the axis
+            side = (x1 * 2).sum()                                      # independent work between the halves
+            z = dap.all_gather_opp(y, axis=axis)
+            ((z * wa).sum() + side).backward()
+            x2 = base.clone().requires_grad_(True)
+            z2 = dap.gather_full(x2, axis)
+            ((z2 * wa).sum() + (x2 * 2).sum()).backward()
+            torch.testing.assert_close(z, z2)
+            torch.testing.assert_close(x1.grad, x2.grad)
+        # all-to-all pair: rows sharded -> columns sharded
+        x1 = base.clone().requires_grad_(True)
+        y = dap.all_to_all(x1, in_axis=2, out_axis=1)
+        z = dap.all_to_all_opp(y, in_axis=2, out_axis=1)
+        wz = torch.randn(z.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(rank + 99))
+        (z * wz).sum().backward()
+        x2 = base.clone().requires_grad_(True)
+        z2 = dap.row_to_col(x2)
+        (z2 * wz).sum().backward()
+        torch.testing.assert_close(z, z2)
+        torch.testing.assert_close(x1.grad, x2.grad)
+        # without gradients the pair is pure data movement
+        with torch.no_grad():
+            torch.testing.assert_close(dap.all_gather_opp(dap.all_gather(base, axis=1), axis=1), dap.gather_full(base, 1))
+    dap.set_dap_sync_op(True)
+    # class forms (reference signatures: no group argument, the dap group is implied)
+    x = base.clone().requires_grad_(True)
+    full = dap.Gather.apply(x, 1)
+    assert full.shape[1] == base.shape[1] * world
+    back = dap.Scatter.apply(full, 1)
+    torch.testing.assert_close(back, x)
+    (back * w[:, :4]).sum().backward()
+    torch.testing.assert_close(x.grad, w[:, :4])
+    stack = torch.cat((base * (rank + 1)).chunk(world, dim=2), dim=0)
+    out = dap.All2All.apply(stack, 2, 1)
+    torch.testing.assert_close(torch.cat(out.chunk(world, 0), dim=1), dap.row_to_col(base * (rank + 1)))
+    # reference-style optimizer groups in grad_sync
+    p_rep, p_skip = torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(3))
+    p_rep.grad, p_skip.grad = torch.full((3,), float(rank + 1)), torch.full((3,), float(rank + 1))
+    dap.grad_sync([{"params": [p_rep], "dap": True}, {"params": [p_skip]}])
+    assert float(p_rep.grad[0]) == sum(range(1, world + 1)) and float(p_skip.grad[0]) == rank + 1

@@ -215,3 +215,7 @@ def test_template_features_and_embedding():
 @pytest.mark.parametrize("mode", ["dap", "bp"])
 def test_evoformer_with_templates_and_extra_msa_parallel_matches_single(mode):
     run_distributed("dist_fns:evoformer_parallel_matches_single", 2, mode)
+
+
+def test_dap_split_phase_pairs_match_one_shot_ops():
+    run_distributed("dist_fns:dap_split_phase_pairs", 2)
