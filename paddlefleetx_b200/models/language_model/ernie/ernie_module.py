@@ -3,6 +3,8 @@
 ``ErnieSeqClsModule`` (sequence classification fine-tune).  ``*Auto`` names map to the same eager classes."""
 from __future__ import annotations
 
+import os
+
 
 import torch
 
@@ -43,6 +45,50 @@ def process_data_configs(config) -> None:
             col = config.Data[mode].get("loader", {}).get("collate_fn")
             if isinstance(col, dict) and col.get("name") == "ErnieCollateData":
                 col["micro_batch_size"] = g.micro_batch_size
+
+
+def process_model_configs(config) -> None:
+    """``Model.intermediate_size`` defaults to four times the hidden size (reference ernie_module.py:75-78)."""
+    m = config["Model"]
+    m.setdefault("intermediate_size", m["hidden_size"] * 4)
+
+
+def process_auto_model_configs(config) -> None:
+    """Auto variant (reference ernie/auto/auto_module.py:63-68): also records the process mesh under ``Model.mesh``."""
+    from ..auto_module import process_mesh_config
+
+    config["Model"].update({"mesh": process_mesh_config(config["Distributed"])})
+    process_model_configs(config)
+
+
+FINETUNE_CONFIGS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "finetune_configs.yaml")
+
+
+def process_finetune_configs(task: str, config, path: str = FINETUNE_CONFIGS) -> None:
+    """Overlay the per-dataset fine-tuning hyper-parameters of ``finetune_configs.yaml`` (``{task: {dataset_type: {num_train_epochs,
+    learning_rate, max_seq_length, batch_size}}}``) on a recipe (reference ernie_module.py:81-117): epochs go to the engine, the learning rate to
+    ``Optimizer.lr.max_lr``, the sequence length to every dataset section, the batch size to ``Global`` (global = local x dp x pp, as
+    the reference computes it)."""
+    import yaml
+
+    with open(path, encoding="utf-8") as f:
+        table = yaml.safe_load(f)
+    dataset_type = config.Data.Train.dataset.dataset_type
+    assert task in table and dataset_type in table[task], (f"{dataset_type} is an invalid dataset type ! Only support the types of dataset shown "
+                                                           f"in {path}")
+    hp = table[task][dataset_type]
+    if hp.get("num_train_epochs") is not None:
+        config.Engine["num_train_epochs"] = hp["num_train_epochs"]
+    if hp.get("learning_rate") is not None:
+        config.Optimizer["lr"]["max_lr"] = hp["learning_rate"]
+    if hp.get("max_seq_length") is not None:
+        for mode in ("Train", "Eval", "Test"):
+            if mode in config.Data:
+                config.Data[mode]["dataset"]["max_seq_len"] = hp["max_seq_length"]
+    if hp.get("batch_size") is not None:
+        assert hp["batch_size"] % config.Global["micro_batch_size"] == 0
+        config.Global["local_batch_size"] = hp["batch_size"]
+        config.Global["global_batch_size"] = hp["batch_size"] * config.Distributed["dp_degree"] * config.Distributed["pp_degree"]
 
 
 class ErnieModule(BasicModule):

@@ -268,6 +268,7 @@ class ErnieModel(nn.Module):
         ffn = ffn_hidden_size or intermediate_size or 4 * hidden_size
         self.pad_token_id, self.initializer_range, self.hidden_size, self.mp_group = pad_token_id, initializer_range, hidden_size, mp_group
         self.vocab_size, self.hidden_act = vocab_size, hidden_act            # read by the heads, as in the reference (single_model.py:464-480)
+        self.hidden_dropout_prob = hidden_dropout_prob
         self.embeddings = ErnieEmbeddings(vocab_size, hidden_size, hidden_dropout_prob, max_position_embeddings, type_vocab_size,
                                           task_type_vocab_size, task_id, use_task_id, initializer_range, mp_group, dtype, device)
         layers = [TransformerEncoderLayer(hidden_size, num_attention_heads, ffn, hidden_dropout_prob, hidden_act, attention_probs_dropout_prob,
@@ -425,7 +426,7 @@ class ErnieForSequenceClassification(nn.Module):
         super().__init__()
         self.ernie = ernie
         p = ernie.pooler.dense.weight
-        self.dropout_p = 0.1 if dropout is None else dropout
+        self.dropout_p = getattr(ernie, "hidden_dropout_prob", 0.1) if dropout is None else dropout      # reference single_model.py:664-666
         self.num_classes = num_classes
         self.classifier = nn.Linear(ernie.hidden_size, num_classes, dtype=p.dtype, device=p.device)
         with torch.no_grad():
@@ -452,3 +453,50 @@ class ErnieForSequenceClassification(nn.Module):
         from .model_outputs import SequenceClassifierOutput
 
         return SequenceClassifierOutput(loss=loss, logits=logits, hidden_states=outputs.hidden_states, attentions=outputs.attentions)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# Names of the reference's split files (ernie/dygraph/hybrid_model.py, ernie/auto/auto_model.py, ernie/layers/*transformer.py) that resolve
+# to this module: the tensor-parallel / auto-parallel variants are the same classes (the layers are topology-aware).
+ErniePretrainingCriterionHybrid = ErniePretrainingCriterion
+ErnieForSequenceClassificationHybrid = ErnieForSequenceClassification
+ErnieModelAuto = ErnieModel
+ErnieForPretrainingAuto = ErnieForPretraining
+ErniePretrainingCriterionAuto = ErniePretrainingCriterion
+ErnieForSequenceClassificationAuto = ErnieForSequenceClassification
+MultiHeadAttention = ErnieSelfAttention
+
+
+class Embedding(nn.Embedding):
+    """Embedding table with the reference constructor (ernie/auto/auto_model.py:37-95: ``padding_idx`` may be negative, ``sparse`` gradients,
+    validated sizes); the row of ``padding_idx`` stays zero and receives no gradient."""
+
+    def __init__(self, num_embeddings, embedding_dim, padding_idx=None, sparse=False, weight_attr=None, name=None, dtype=None, device=None):
+        if num_embeddings <= 0:
+            raise ValueError("num_embeddings must be gather than 0")
+        if embedding_dim <= 0:
+            raise ValueError("embedding_dim must be gather than 0")
+        if padding_idx is not None and not -num_embeddings <= padding_idx < num_embeddings:
+            raise ValueError(f"padding_idx must be within [-{num_embeddings}, {num_embeddings})")
+        super().__init__(num_embeddings, embedding_dim, padding_idx=padding_idx, sparse=bool(sparse), dtype=dtype, device=device)
+
+
+class LayerNormPipe(LayerNorm):
+    """Final norm as a pipeline stage entry (reference hybrid_model.py:761-765): takes and returns the hidden states only."""
+
+    def forward(self, x, *rest):
+        return super().forward(x)
+
+
+class ErniePoolerPipe(ErniePooler):
+    """Pooler as a pipeline stage entry (reference hybrid_model.py:768-772): ``hidden -> (hidden, pooled)``."""
+
+    def forward(self, hidden_states, *rest):
+        return hidden_states, super().forward(hidden_states)
+
+
+from ....utils.lazy import lazy_exports  # noqa: E402
+
+__getattr__ = lazy_exports(__name__, {
+    "EmbeddingsPipe": ".pipe", "TransformerEncoderLayerPipe": ".pipe", "ErniePretrainingCriterionPipe": ".pipe", "ErnieForPretrainingPipe": ".pipe",
+})

@@ -498,3 +498,55 @@ def vocab_size_with_padding(vocab_size: int, div_unit: int, mp_degree: int) -> i
     """Pad the vocabulary to a multiple of ``div_unit * mp`` (reference language_module.py:62-70)."""
     mult = div_unit * mp_degree
     return ((vocab_size + mult - 1) // mult) * mult
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------------
+# Names of the reference's split files (gpt/dygraph/{single,hybrid}_model.py, gpt/auto/auto_model.py) that resolve to this module.
+def get_attr(layer, name):
+    """Attribute lookup through wrapper layers (``._layer`` / ``._layers``), reference hybrid_model.py:59-63."""
+    while layer is not None:
+        value = getattr(layer, name, None)
+        if value is not None:
+            return value
+        layer = getattr(layer, "_layer", None) or getattr(layer, "_layers", None)
+    raise AttributeError(name)
+
+
+def get_triangle_upper_mask(x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Additive causal mask shaped like the score tensor ``x`` (``-inf`` above the diagonal) unless one is given
+    (reference hybrid_model.py:1681-1688; the training path never builds it: the flash kernels mask by tile)."""
+    if mask is not None:
+        return mask
+    return torch.full_like(x, float("-inf")).triu(1)
+
+
+class ConcatSoftmaxInput(torch.autograd.Function):
+    """All-gather vocabulary-parallel logits along the last axis; backward keeps this rank's slice (reference hybrid_model.py:1691-1708,
+    used by ``GPTForGenerationHybrid`` to sample from the full distribution)."""
+
+    @staticmethod
+    def forward(ctx, inp, group=None):
+        ctx.group = group
+        if C.group_size(group) == 1:
+            return inp.view_as(inp)
+        return C.all_gather_dim(inp.contiguous(), group, inp.dim() - 1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        if C.group_size(ctx.group) == 1:
+            return grad, None
+        return C.split_dim(grad, ctx.group, grad.dim() - 1), None
+
+
+# the auto-parallel variants are the same classes: the sharding the reference annotates with ``auto.shard_tensor`` lives in the layers
+GPTModelAuto = GPTModel
+GPTForPretrainingAuto = GPTForPretraining
+GPTPretrainingCriterionAuto = GPTPretrainingCriterion
+
+from ....utils.lazy import lazy_exports  # noqa: E402
+
+__getattr__ = lazy_exports(__name__, {
+    "GPTForPretrainingPipe": ".pipe", "GPTPretrainingCriterionPipe": ".pipe", "EmbeddingPipe": ".pipe", "LayerNormPipe": ".pipe",
+    "GPTForGeneration": ".generation", "GPTForGenerationHybrid": ".generation", "GPTForGenerationAuto": ".generation:GPTForGeneration",
+    "ExpertLayer": "..moe.moe_layer",
+})

@@ -254,3 +254,13 @@ class GPTModule(LanguageModule):
             for i in range(len(v)):
                 logger.info(f"{k}[{i}]: shape {tuple(v[i].shape)}")
         return outputs
+
+
+# ---- names the reference keeps in this file (language_module.py:228-830) or in auto_utils.py; they live in sibling modules here
+from ...utils.lazy import lazy_exports  # noqa: E402
+from .gpt.model import vocab_size_with_padding  # noqa: E402,F401
+
+__getattr__ = lazy_exports(__name__, {
+    "GPTFinetuneModule": ".finetune_module", "GPTGenerationModule": ".generation_module", "GPTEvalModule": ".eval_module",
+    "MoEModule": ".moe_module", "process_mesh_config": ".auto_module", "ProcessMesh": ".auto_module",
+})

@@ -64,6 +64,17 @@ def count_by_gate(gate_idx: torch.Tensor, num_expert: int, world_size: int, requ
     return pos, lec, gec
 
 
+def prepare_forward(gate, num_expert: int, world_size: int, moe_group=None):
+    """``(pos, local_expert_count, global_expert_count, fwd_expert_count, fwd_batch_size)`` for a top-k gate index tensor (reference
+    moe/utils.py:26-38).  ``fwd_batch_size`` is a Python int, i.e. this call synchronises with the device — the layer's default path does not
+    use it (routing tables stay in device memory, moe/fused_dispatch.py); it serves the NCCL fallback and external callers."""
+    pos, lec, gec = count_by_gate(gate, num_expert, world_size, group=moe_group)
+    with torch.no_grad():
+        fwd_expert_count = gec.view(world_size, num_expert).sum(0)
+        fwd_batch_size = int(fwd_expert_count.sum().item())
+    return pos, lec, gec, fwd_expert_count, fwd_batch_size
+
+
 def limit_by_capacity_counts(gec: torch.Tensor, capacity: torch.Tensor, world_size: int) -> torch.Tensor:
     """gec: [world * E_local] incoming counts ordered (source rank, expert).  Each expert accepts at most ``capacity[e]``
     tokens, granted to source ranks in rank order."""

@@ -279,6 +279,54 @@ def allreduce_sequence_parallel_grads(model: nn.Module) -> None:
         C.fused_allreduce_gradients(params, model._sp_group, scale=1.0)
 
 
+def create_fused_allreduce_gradient_hook(parameter_list, accumulation_steps: int, group=None):
+    """A gradient hook shared by ``parameter_list``: once every parameter has produced its gradient ``accumulation_steps`` times, all of
+    them are all-reduced over the tensor-parallel group in one coalesced call (reference sequence_parallel_utils.py:155-170).  Register it
+    with ``p.register_post_accumulate_grad_hook`` (or ``register_hook``); the engine's default is the equivalent explicit call
+    ``allreduce_sequence_parallel_grads`` after the last micro-batch."""
+    if group is None:
+        from ..distributed.apis import env
+
+        group = env.get_hcg().get_model_parallel_group()
+    parameter_list = list(parameter_list)
+    fire_at, count = accumulation_steps * len(parameter_list), [0]
+
+    def hook(arg=None):
+        count[0] += 1
+        if count[0] == fire_at:
+            count[0] = 0
+            C.fused_allreduce_gradients(parameter_list, group, scale=1.0)
+        return None if isinstance(arg, nn.Parameter) else arg
+
+    return hook
+
+
+def create_non_fused_allreduce_gradient_hook(param, accumulation_steps: int, group=None):
+    """Per-parameter variant: every ``accumulation_steps``-th call all-reduces ``param.main_grad`` (or ``param.grad``) over the
+    tensor-parallel group (reference sequence_parallel_utils.py:173-188)."""
+    if group is None:
+        from ..distributed.apis import env
+
+        group = env.get_hcg().get_model_parallel_group()
+    count = [0]
+
+    @torch.no_grad()
+    def hook(*_):
+        count[0] += 1
+        if count[0] % accumulation_steps == 0:
+            C.fused_allreduce_gradients([param], group, scale=1.0)
+
+    return hook
+
+
+def is_fused_matmul_bias_supported() -> bool:
+    """The reference gates ``fused_linear`` on a cuBLASLt-epilogue capability of the Paddle build (sequence_parallel_utils.py:215-220).  Bias
+    (and bias + GELU) always ride in the tcgen05 GEMM epilogue here when the native library is loaded."""
+    from ..ops import _native
+
+    return _native.available()
+
+
 # sequence-parallel collectives under the reference's names (gpt/dygraph/sequence_parallel_utils.py:30-140)
 from .comm_ops import _AllGatherSeq as AllGatherOp  # noqa: E402,F401
 from .comm_ops import _GatherSeq as GatherOp  # noqa: E402,F401
