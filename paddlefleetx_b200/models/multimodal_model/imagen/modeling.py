@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ....utils.log import logger
 from . import unet as U
 
 
@@ -58,6 +59,20 @@ class GaussianDiffusionContinuousTimes(nn.Module):
         var = sn ** 2 * c
         return mean, var, torch.log(var.clamp(min=1e-20))
 
+    def q_sample_from_to(self, x_from, from_t, to_t, noise=None):
+        """Re-noise a sample from time ``from_t`` to the noisier time ``to_t`` (the resampling step of RePaint-style inpainting): scale by
+        ``alpha_to / alpha_from`` and add exactly the noise that brings the variance up to ``sigma_to^2``, so that the result is distributed like
+        ``q_sample(x0, to_t)``.  The reference (imagen/utils.py:448-469) adds ``(sigma_to * alpha - sigma * alpha_to) / alpha`` instead, which
+        under-shoots that variance; the exact form is used here."""
+        b = x_from.shape[0]
+        from_t = torch.full((b,), from_t, device=x_from.device) if isinstance(from_t, float) else from_t
+        to_t = torch.full((b,), to_t, device=x_from.device) if isinstance(to_t, float) else to_t
+        noise = torch.randn_like(x_from) if noise is None else noise
+        a, s = self.alpha_sigma(self.log_snr(from_t).view(-1, 1, 1, 1))
+        a_to, s_to = self.alpha_sigma(self.log_snr(to_t).view(-1, 1, 1, 1))
+        ratio = a_to / a
+        return x_from * ratio + noise * torch.sqrt((s_to ** 2 - (ratio * s) ** 2).clamp(min=0.0))
+
     def predict_start_from_noise(self, xt, t, noise):
         a, s = self.alpha_sigma(self.log_snr(t).view(-1, 1, 1, 1))
         return (xt - s * noise) / a.clamp(min=1e-8)
@@ -92,7 +107,10 @@ class ImagenModel(nn.Module):
         super().__init__()
         if isinstance(unets, nn.Module):
             unets = [unets]
+        if text_embed_dim is None and text_encoder_name not in (None, "None", ""):
+            text_embed_dim = self._text_tower_width(text_encoder_name)      # reference: default(text_embed_dim, get_encoded_dim(name))
         text_embed_dim = text_embed_dim or 1024
+        self.text_embed_dim = text_embed_dim
         built = [u if isinstance(u, nn.Module) else getattr(U, u["name"])(**{k: v for k, v in u.items() if k != "name"}, text_embed_dim=text_embed_dim)
                  for u in unets]
         in_chans = channels if in_chans is None else in_chans
@@ -123,9 +141,48 @@ class ImagenModel(nn.Module):
         from ....data.tokenizers import get_text_tokenizer
 
         self.tokenizer = get_text_tokenizer(self.text_encoder_name)      # None when the vocabulary is not on this (offline) machine
+        if self.text_encoder is None and self.text_encoder_name is not None:
+            self.text_encoder = self._load_text_encoder(self.text_encoder_name)
         if self.text_encoder is not None:
             for p in self.text_encoder.parameters():
                 p.requires_grad = False
+
+    @staticmethod
+    def _text_tower_width(name: str) -> Optional[int]:
+        try:
+            if "deberta" in str(name).lower():
+                from ..debertav2.modeling import get_debertav2_encoded_dim
+
+                return get_debertav2_encoded_dim(name)
+            from ..t5.modeling import get_encoded_dim
+
+            return get_encoded_dim(name)
+        except (FileNotFoundError, KeyError, ImportError):
+            return None
+
+    @staticmethod
+    def _load_text_encoder(name: str):
+        """The frozen text tower stored under the directory ``name`` (``t5/t5-11b``, ``.../deberta-v2-xxlarge``: ``config.json`` + weights), as
+        the reference builds it at construction time (imagen/modeling.py:221-241).  A name whose directory is not on this machine gives
+        ``None``: training then runs on pre-computed embeddings, and ``sample(texts=...)`` explains what is missing."""
+        import os
+
+        if not os.path.isdir(str(name)):
+            return None
+        low = str(name).lower()
+        try:
+            if "t5" in low:
+                from ..t5.modeling import get_t5_model
+
+                return get_t5_model(name, pretrained=True)
+            if "deberta" in low:
+                from ..debertav2.modeling import get_debertav2_model
+
+                return get_debertav2_model(name, pretrained=True)
+        except FileNotFoundError as exc:
+            logger.warning(f"text encoder {name!r} not loaded: {exc}")
+            return None
+        raise NotImplementedError("Please implement the text encoder.")
 
     def _prev_size(self, k: int) -> Optional[int]:
         """Resolution of the image stage ``k`` is conditioned on (None for an unconditioned base stage)."""
@@ -138,7 +195,16 @@ class ImagenModel(nn.Module):
     def encode_text(self, input_ids, attention_mask):
         with torch.no_grad():
             self.text_encoder.eval()
-            return self.text_encoder(input_ids, attention_mask).detach()
+            out = self.text_encoder(input_ids, attention_mask)
+            return getattr(out, "last_hidden_state", out).detach()
+
+    def encode_captions(self, texts, max_length: int = 256):
+        """captions -> ``(text_embeds, text_masks)`` through the model's own tokenizer and frozen text tower (fp32, no autocast)."""
+        assert self.text_encoder is not None, (f"no text encoder weights for {self.text_encoder_name!r} on this machine: pass text_embeds, or place the "
+                                               "encoder directory (config.json + weights) at that path")
+        input_ids, attention_mask = self.tokenize_captions(texts, max_length)
+        with torch.autocast(device_type=input_ids.device.type, enabled=False):
+            return self.encode_text(input_ids, attention_mask), attention_mask
 
     def tokenize_captions(self, texts, max_length: int = 256):
         """captions -> (input_ids, attention_mask) on the model's device with the text tower's own tokenizer."""
@@ -185,32 +251,122 @@ class ImagenModel(nn.Module):
         s = torch.quantile(x0.flatten(1).abs().float(), self.dt_pct, dim=-1).clamp(min=1.0).view(-1, 1, 1, 1)
         return x0.clamp(-s, s) / s
 
-    @torch.no_grad()
-    def sample(self, text_embeds=None, text_masks=None, batch_size: int = 1, cond_scale: float = 1.0, stop_at_unet_number: Optional[int] = None):
-        dev = next(self.parameters()).device
-        img = None
-        outputs = []
-        for k, (unet, sched, obj, size) in enumerate(zip(self.unets, self.noise_schedulers, self.pred_objectives, self.image_sizes)):
-            lowres, lowres_t = None, None
-            if k > 0:
-                lowres = resize_image_to(img, size) * 2 - 1
-                lt = self.lowres_noise_schedule.get_times(batch_size, self.lowres_sample_noise_level, dev)
-                lowres, _, _, _ = self.lowres_noise_schedule.q_sample(lowres, lt)
-                lowres_t = self.lowres_noise_schedule.log_snr(lt)
-            x = torch.randn(batch_size, self.in_chans, size, size, device=dev)
-            for t, t_next in sched.get_sampling_timesteps(batch_size, dev):
-                pred = unet.forward_with_cond_scale(x, sched.log_snr(t), lowres_cond_img=lowres, lowres_noise_times=lowres_t, text_embeds=text_embeds,
-                                                    text_mask=text_masks, cond_scale=cond_scale)
+    def _p_sample_loop(self, unet, shape, sched, obj, *, text_embeds, text_mask, cond_images, cond_scale, lowres_cond_img, lowres_noise_times,
+                       inpaint_images=None, inpaint_masks=None, inpaint_resample_times=5, init_images=None, skip_steps=None):
+        """Ancestral sampling of one cascade stage (reference imagen/modeling.py:436-538): optional start from ``init_images`` + noise, optional
+        skipped leading steps, self-conditioning on the previous x0 estimate, and RePaint-style inpainting (known pixels are re-imposed at every
+        step, each step is repeated ``inpaint_resample_times`` times with re-noising in between).  Returns images in [-1, 1]."""
+        b, dev = shape[0], next(unet.parameters()).device
+        x = torch.randn(shape, device=dev)
+        if init_images is not None:
+            x = x + init_images
+        x0 = None
+        inpaint = inpaint_images is not None and inpaint_masks is not None
+        resample = inpaint_resample_times if inpaint else 1
+        if inpaint:
+            known = resize_image_to(inpaint_images * 2 - 1 if self.auto_normalize_img else inpaint_images, shape[-1])
+            m = inpaint_masks if inpaint_masks.dim() == 4 else inpaint_masks[:, None]
+            keep = resize_image_to(m.float(), shape[-1]) > 0.5                      # True where the given pixels are kept
+        steps = sched.get_sampling_timesteps(b, dev)[int(skip_steps or 0):]
+        for t, t_next in steps:
+            last = bool((t_next == 0).all())
+            for r in reversed(range(resample)):
+                if inpaint:
+                    noised_known, _, _, _ = sched.q_sample(known, t)
+                    x = torch.where(keep, noised_known, x)
+                kw = {"self_cond": x0} if getattr(unet, "self_cond", False) else {}
+                pred = unet.forward_with_cond_scale(x, sched.log_snr(t), lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
+                                                    text_embeds=text_embeds, text_mask=text_mask, cond_scale=cond_scale,
+                                                    **({"cond_images": cond_images} if cond_images is not None else {}), **kw)
                 x0 = {"noise": sched.predict_start_from_noise, "v": sched.predict_start_from_v}.get(obj, lambda a, b_, c: c)(x, t, pred)
                 x0 = self._threshold(x0)
                 mean, var, _ = sched.q_posterior(x0, x, t, t_next)
                 noise = torch.randn_like(x) * (t_next > 0).float().view(-1, 1, 1, 1)
                 x = mean + var.sqrt() * noise
-            img = (x.clamp(-1, 1) + 1) * 0.5
-            outputs.append(img)
-            if stop_at_unet_number is not None and stop_at_unet_number == k + 1:
-                break
-        return outputs[-1]
+                if inpaint and r > 0 and not last:
+                    x = sched.q_sample_from_to(x, t_next, t)
+        x = x.clamp(-1, 1)
+        if inpaint:
+            x = torch.where(keep, known, x)
+        return x
+
+    @torch.no_grad()
+    def sample(self, texts=None, text_masks=None, text_embeds=None, cond_images=None, inpaint_images=None, inpaint_masks=None,
+               inpaint_resample_times: int = 5, init_images=None, skip_steps=None, batch_size: int = 1, cond_scale=1.0,
+               lowres_sample_noise_level: Optional[float] = None, start_at_unet_number: int = 1, start_image_or_video=None,
+               stop_at_unet_number: Optional[int] = None, return_all_unet_outputs: bool = False, return_pil_images: bool = False):
+        """Run the cascade (reference imagen/modeling.py:541-676).  Conditioning: ``texts`` (encoded by the frozen text tower) or
+        ``text_embeds`` (+ ``text_masks``, default: non-zero rows); ``cond_images`` for U-Nets built with ``cond_images_channels``.  Editing:
+        ``inpaint_images`` + ``inpaint_masks`` (True / 1 = keep the given pixel), ``init_images`` and ``skip_steps`` (one value or one per stage).
+        ``cond_scale`` may be one value or one per stage; ``start_at_unet_number`` > 1 upsamples ``start_image_or_video``.  Returns the last
+        stage's images in [0, 1] — all stages as a list with ``return_all_unet_outputs`` (the reference's default there is True), PIL images
+        with ``return_pil_images``."""
+        was_training = self.training
+        self.eval()
+        try:
+            dev = next(self.parameters()).device
+            if cond_images is not None and cond_images.dtype == torch.uint8:
+                cond_images = cond_images.float() / 255.0
+            if texts is not None and text_embeds is None and self.condition_on_text:
+                text_embeds, text_masks = self.encode_captions(texts)
+            if self.condition_on_text:
+                assert text_embeds is not None, "text or text encodings must be passed into imagen if specified"
+                assert text_embeds.shape[-1] == self.text_embed_dim, f"invalid text embedding dimension being passed in (should be {self.text_embed_dim})"
+                text_embeds = text_embeds.to(dev)
+                text_masks = (text_embeds != 0).any(-1) if text_masks is None else text_masks.to(dev)
+                batch_size = text_embeds.shape[0]
+            else:
+                assert text_embeds is None, "imagen specified not to be conditioned on text, yet it is presented"
+            assert (inpaint_images is None) == (inpaint_masks is None), "inpaint images and masks must be both passed in to do inpainting"
+            if inpaint_images is not None:
+                if not self.condition_on_text and batch_size == 1:
+                    batch_size = inpaint_images.shape[0]
+                assert inpaint_images.shape[0] == batch_size, "number of inpainting images must be equal to the specified batch size on sample"
+            n = len(self.unets)
+            per_stage = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v,) * n      # noqa: E731
+            cond_scales, inits, skips = per_stage(cond_scale), per_stage(init_images), per_stage(skip_steps)
+            noise_level = self.lowres_sample_noise_level if lowres_sample_noise_level is None else lowres_sample_noise_level
+            img = None
+            if start_at_unet_number > 1:
+                assert stop_at_unet_number is None or start_at_unet_number <= stop_at_unet_number
+                assert start_image_or_video is not None, "starting image or video must be supplied if only doing upscaling"
+            if start_image_or_video is not None:          # also feeds a stand-alone super-resolution stage (one low-res-conditioned U-Net)
+                prev = self._prev_size(start_at_unet_number - 1)
+                img = start_image_or_video.to(dev) if prev is None else resize_image_to(start_image_or_video.to(dev), prev)
+            outputs = []
+            for k, (unet, sched, obj, size) in enumerate(zip(self.unets, self.noise_schedulers, self.pred_objectives, self.image_sizes)):
+                if k + 1 < start_at_unet_number:
+                    continue
+                lowres, lowres_t = None, None
+                if unet.lowres_cond:
+                    assert img is not None, "a low-resolution-conditioned stage needs the previous stage's output (or start_image_or_video)"
+                    lowres = resize_image_to(img, size)
+                    lowres = lowres * 2 - 1 if self.auto_normalize_img else lowres
+                    lt = self.lowres_noise_schedule.get_times(batch_size, noise_level, dev)
+                    lowres, _, _, _ = self.lowres_noise_schedule.q_sample(lowres, lt)
+                    lowres_t = self.lowres_noise_schedule.log_snr(lt)
+                init = inits[k]
+                if init is not None:
+                    init = resize_image_to(init.to(dev) * 2 - 1 if self.auto_normalize_img else init.to(dev), size)
+                x = self._p_sample_loop(unet, (batch_size, self.in_chans, size, size), sched, obj, text_embeds=text_embeds, text_mask=text_masks,
+                                        cond_images=None if cond_images is None else cond_images.to(dev), cond_scale=cond_scales[k],
+                                        lowres_cond_img=lowres, lowres_noise_times=lowres_t,
+                                        inpaint_images=None if inpaint_images is None else inpaint_images.to(dev),
+                                        inpaint_masks=None if inpaint_masks is None else inpaint_masks.to(dev),
+                                        inpaint_resample_times=inpaint_resample_times, init_images=init, skip_steps=skips[k])
+                img = (x + 1) * 0.5 if self.auto_normalize_img else x
+                outputs.append(img)
+                if stop_at_unet_number is not None and stop_at_unet_number == k + 1:
+                    break
+        finally:
+            self.train(was_training)
+        if return_pil_images:
+            from PIL import Image
+
+            to_pil = lambda t: Image.fromarray((t.clamp(0, 1).permute(1, 2, 0).float().cpu().numpy() * 255 + 0.5).astype("uint8").squeeze())   # noqa: E731
+            pil = [[to_pil(im) for im in stage] for stage in outputs]
+            return pil if return_all_unet_outputs else pil[-1]
+        return outputs if return_all_unet_outputs else outputs[-1]
 
 
 class ImagenCriterion(nn.Module):

@@ -183,7 +183,7 @@ def test_vision_multimodal_and_text_towers_on_gpu():
     mask = torch.ones(2, 16, dtype=torch.long, device=dev)
     t5 = T5EncoderModel(vocab_size=100, d_model=64, d_kv=16, d_ff=128, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu").to(dev)
     with amp():
-        o = t5(ids, mask)
+        o = t5(ids, mask).last_hidden_state
     o.float().sum().backward()
     deb = DebertaV2Model(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, position_buckets=8,
                          conv_kernel_size=3).to(dev)

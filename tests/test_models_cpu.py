@@ -176,7 +176,7 @@ def test_text_towers_and_evoformer_forward_backward():
     mask = torch.ones(2, 10, dtype=torch.long)
     mask[0, 7:] = 0
     t5 = T5EncoderModel(vocab_size=100, d_model=32, d_kv=8, d_ff=64, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu")
-    assert t5(ids, mask).shape == (2, 10, 32)
+    assert t5(ids, mask).last_hidden_state.shape == (2, 10, 32)
     deb = DebertaV2Model(vocab_size=100, hidden_size=32, num_hidden_layers=2, num_attention_heads=4, intermediate_size=64, position_buckets=8,
                          conv_kernel_size=3)
     deb(ids, mask).sum().backward()

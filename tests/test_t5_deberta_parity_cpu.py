@@ -99,3 +99,6 @@ def test_t5_encoder_matches_reference_constructor(ref_t5, kw):
     mine = T5EncoderModel(device="meta", dropout_rate=0.0, **kw)
     assert sum(_sizes(ref)) == sum(_sizes(mine)), (sum(_sizes(ref)), sum(_sizes(mine)))
     assert _sizes(ref) == _sizes(mine)
+    # same parameter names -> a converted reference checkpoint loads by key (the reference lists the embedding a second time under the encoder)
+    ref_names = {n for n, _ in ref.named_parameters(remove_duplicate=False)} - {"encoder.embed_tokens.weight"}
+    assert ref_names == {n for n, _ in mine.named_parameters()}
