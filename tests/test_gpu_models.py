@@ -188,7 +188,7 @@ def test_vision_multimodal_and_text_towers_on_gpu():
     deb = DebertaV2Model(vocab_size=100, hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128, position_buckets=8,
                          conv_kernel_size=3).to(dev)
     with amp():
-        o = deb(ids, mask)
+        o = deb(ids, mask).last_hidden_state
     o.float().sum().backward()
     evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2,
                                  pair_heads=2, extra_msa_channel=8, extra_msa_blocks=1,

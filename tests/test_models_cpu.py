@@ -179,7 +179,7 @@ def test_text_towers_and_evoformer_forward_backward():
     assert t5(ids, mask).last_hidden_state.shape == (2, 10, 32)
     deb = DebertaV2Model(vocab_size=100, hidden_size=32, num_hidden_layers=2, num_attention_heads=4, intermediate_size=64, position_buckets=8,
                          conv_kernel_size=3)
-    deb(ids, mask).sum().backward()
+    deb(ids, mask).last_hidden_state.sum().backward()
     evo = EmbeddingsAndEvoformer(msa_feat_dim=9, target_feat_dim=6, c_m=16, c_z=8, c_s=12, num_blocks=2, max_relative_feature=4, msa_heads=2, pair_heads=2)
     out = evo(dict(target_feat=torch.randn(1, 10, 6), msa_feat=torch.randn(1, 4, 10, 9), residue_index=torch.arange(10)[None]))
     assert out["single"].shape == (1, 10, 12) and out["pair"].shape == (1, 10, 10, 8)
