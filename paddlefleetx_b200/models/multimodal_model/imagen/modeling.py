@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 from ....utils.log import logger
 from . import unet as U
+from .unet import BaseUnet64, SRUnet256, SRUnet1024, Unet64_397M  # noqa: F401  (the reference defines the presets in this module)
 
 
 def log_snr_cosine(t, s: float = 0.008):

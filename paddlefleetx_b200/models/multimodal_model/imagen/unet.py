@@ -76,6 +76,20 @@ class GainLayerNorm(nn.Module):
 ChanLayerNorm = partial(GainLayerNorm, dim=-3)
 
 
+LayerNorm = GainLayerNorm          # the reference's name (imagen/unet.py:33-54)
+
+
+class Residual(nn.Module):
+    """``fn(x, **kwargs) + x`` (reference imagen/unet.py:60-66)."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x, **kwargs):
+        return self.fn(x, **kwargs) + x
+
+
 class Always(nn.Module):
     def __init__(self, value):
         super().__init__()

@@ -18,6 +18,11 @@ class MultiModalModule(BasicModule):
         super().__init__(configs)
         self.loss_fn = self.get_loss_fn()
 
+    def process_configs(self, configs):
+        from .utils import process_configs
+
+        return process_configs(configs)
+
     def training_step_end(self, log_dict):
         ips = self.configs.Global.global_batch_size / log_dict["train_cost"]
         logger.train("[train] epoch: %d, batch: %d, loss: %.9f, avg_batch_cost: %.5f sec, speed: %.2f step/s, ips: %.2f images/sec, learning rate: %.5e"

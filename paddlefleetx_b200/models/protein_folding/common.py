@@ -21,6 +21,12 @@ def no_autocast(fn: Callable) -> Callable:
     return wrapped
 
 
+def set_tensor_constant(tensor: torch.Tensor, constant) -> None:
+    """Fill a parameter in place (reference common.py:29-30)."""
+    with torch.no_grad():
+        tensor.fill_(constant)
+
+
 def init_gate_linear(linear: nn.Linear) -> None:
     """Gates start open: weight 0, bias 1 (sigmoid(1) ~ 0.73)."""
     nn.init.zeros_(linear.weight)
@@ -116,3 +122,12 @@ class Dropout(nn.Module):
             shape[a] = 1
         keep = torch.bernoulli(torch.full(shape, 1.0 - self.rate, device=x.device, dtype=x.dtype))
         return x * keep / (1.0 - self.rate)
+
+
+def __getattr__(name: str):
+    # ``Transition`` lives with the Evoformer blocks here (evoformer.py); the reference keeps it in this module (common.py:189-249)
+    if name == "Transition":
+        from .evoformer import Transition
+
+        return Transition
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

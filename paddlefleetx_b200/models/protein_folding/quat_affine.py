@@ -158,3 +158,29 @@ def make_transform_from_reference(n_xyz: torch.Tensor, ca_xyz: torch.Tensor, c_x
     ``make_canonical_transform``; this is each residue's backbone frame."""
     translation, rot = make_canonical_transform(n_xyz, ca_xyz, c_xyz)
     return rot.transpose(-1, -2), -translation
+
+
+# ---- NumPy forms used by feature pipelines that run on the host (reference quat_affine.py:162-174, 513-613)
+def apply_rot_to_vec_np(rot, vec, unstack: bool = False):
+    """``rot`` indexable as ``rot[i][j]`` (arrays or scalars), ``vec`` a list ``[x, y, z]`` (or one ``[..., 3]`` array with ``unstack``);
+    returns the rotated coordinates as a list of three arrays."""
+    x, y, z = (vec[..., 0], vec[..., 1], vec[..., 2]) if unstack else vec
+    return [rot[i][0] * x + rot[i][1] * y + rot[i][2] * z for i in range(3)]
+
+
+def make_canonical_transform_np(n_xyz, ca_xyz, c_xyz):
+    """NumPy ``make_canonical_transform``: ``(translation [b, 3], rotation [b, 3, 3])`` moving CA to the origin, C onto +x, N into the xy-plane."""
+    import numpy as np
+
+    assert n_xyz.ndim == 2 and n_xyz.shape[-1] == 3, n_xyz.shape
+    assert n_xyz.shape == ca_xyz.shape == c_xyz.shape, (n_xyz.shape, ca_xyz.shape, c_xyz.shape)
+    t, r = make_canonical_transform(*(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)) for a in (n_xyz, ca_xyz, c_xyz)))
+    return t.numpy().astype(n_xyz.dtype, copy=False), r.numpy().astype(n_xyz.dtype, copy=False)
+
+
+def make_transform_from_reference_np(n_xyz, ca_xyz, c_xyz):
+    """NumPy ``make_transform_from_reference``: ``(rotation, translation)`` of each residue's backbone frame (rotation first, then translation)."""
+    import numpy as np
+
+    translation, rotation = make_canonical_transform_np(n_xyz, ca_xyz, c_xyz)
+    return np.transpose(rotation, (0, 2, 1)), -translation

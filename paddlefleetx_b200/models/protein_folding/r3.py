@@ -111,6 +111,22 @@ def rigids_from_3_points(point_on_neg_x_axis: Vecs, origin: Vecs, point_on_xy_pl
     return Rigids(rot, origin.expand(rot.shape[:-1]) if origin.shape != rot.shape[:-1] else origin)
 
 
+rigids_from_3_points_vecs = rigids_from_3_points      # the reference has a Vecs form and a tensor form; one layout serves both here
+
+
+def squared_difference(x, y):
+    return torch.square(x - y)
+
+
+def broadcast_shape(x_shape, y_shape):
+    """Shape two batch shapes broadcast to (NumPy rules; the reference's hand-rolled version, r3.py:409-424, only handles equal ranks)."""
+    return list(torch.broadcast_shapes(tuple(x_shape), tuple(y_shape)))
+
+
+def broadcast_to(x: torch.Tensor, broadcast_shape) -> torch.Tensor:
+    return x if list(x.shape) == list(broadcast_shape) else x.expand(*broadcast_shape)
+
+
 def invert_rigids(r: Rigids) -> Rigids:
     inv = invert_rots(r.rot)
     return Rigids(inv, -rots_mul_vecs(inv, r.trans))
@@ -144,6 +160,12 @@ def rigids_from_tensor_flat9(m: torch.Tensor) -> Rigids:
     """[..., 9] = two un-normalised frame vectors + translation."""
     assert m.shape[-1] == 9
     return Rigids(rots_from_two_vecs(m[..., 0:3], m[..., 3:6]), m[..., 6:9])
+
+
+def rigids_to_tensor_flat9(r: Rigids) -> torch.Tensor:
+    """[..., 9] = first two COLUMNS of the rotation (the images of e_x and e_y) + translation — what ``rigids_from_tensor_flat9`` rebuilds the
+    frame from by Gram-Schmidt (reference r3.py:352-357)."""
+    return torch.cat([r.rot[..., :, 0], r.rot[..., :, 1], r.trans], dim=-1)
 
 
 def rigids_from_tensor_flat12(m: torch.Tensor) -> Rigids:

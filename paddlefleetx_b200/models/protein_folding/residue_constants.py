@@ -8,7 +8,8 @@ reference: the folding head is in PaddleHelix), and is not included.
 """
 from __future__ import annotations
 
-from typing import Dict, List
+import os
+from typing import Dict, List, NamedTuple
 
 import numpy as np
 
@@ -133,3 +134,111 @@ def sequence_to_onehot(sequence: str, mapping: Dict[str, int] = None, map_unknow
 
 def aatype_to_str_sequence(aatype) -> str:
     return "".join(restypes_with_x[int(i)] for i in aatype)
+
+
+# ---------------------------------------------------------------------------------------------------------------- stereo-chemistry tables
+class Bond(NamedTuple):
+    atom1_name: str
+    atom2_name: str
+    length: float
+    stddev: float
+
+
+class BondAngle(NamedTuple):
+    atom1_name: str
+    atom2_name: str
+    atom3name: str
+    angle_rad: float
+    stddev: float
+
+
+STEREO_CHEMICAL_PROPS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stereo_chemical_props.txt")
+
+
+def load_stereo_chemical_props(path: str = None):
+    """Literature bond lengths and angles per residue type, read from ``stereo_chemical_props.txt`` (the Engh & Huber table that ships with
+    AlphaFold's parameters: a ``Bond Residue Mean StdDev`` block, a line ``-``, an ``Angle Residue Mean StdDev`` block in degrees, a line
+    ``-``).  Returns ``(residue_bonds, residue_virtual_bonds, residue_bond_angles)``; a "virtual bond" is the 1-3 distance an angle implies by
+    the law of cosines, with the error propagated from the two bond lengths and the angle (reference residue_constants.py:403-488).  The table
+    is data, not code, and is not in the reference tree either: put it next to this module or pass ``path``."""
+    path = path or STEREO_CHEMICAL_PROPS
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"{path} not found: copy stereo_chemical_props.txt (AlphaFold parameter release) there, or pass path=")
+    with open(path, "rt") as f:
+        lines = iter(f.read().splitlines())
+    residue_bonds: Dict[str, List[Bond]] = {}
+    next(lines)                                            # header
+    for line in lines:
+        if line.strip() == "-":
+            break
+        bond, resname, length, stddev = line.split()
+        a1, a2 = bond.split("-")
+        residue_bonds.setdefault(resname, []).append(Bond(a1, a2, float(length), float(stddev)))
+    residue_bonds["UNK"] = []
+    residue_bond_angles: Dict[str, List[BondAngle]] = {}
+    next(lines)                                            # blank
+    next(lines)                                            # header
+    for line in lines:
+        if line.strip() == "-":
+            break
+        bond, resname, angle, stddev = line.split()
+        a1, a2, a3 = bond.split("-")
+        residue_bond_angles.setdefault(resname, []).append(BondAngle(a1, a2, a3, float(angle) / 180.0 * np.pi, float(stddev) / 180.0 * np.pi))
+    residue_bond_angles["UNK"] = []
+    residue_virtual_bonds: Dict[str, List[Bond]] = {}
+    for resname, angles in residue_bond_angles.items():
+        by_pair = {"-".join(sorted((b.atom1_name, b.atom2_name))): b for b in residue_bonds.get(resname, [])}
+        virtual = []
+        for ba in angles:
+            b1 = by_pair["-".join(sorted((ba.atom1_name, ba.atom2_name)))]
+            b2 = by_pair["-".join(sorted((ba.atom2_name, ba.atom3name)))]
+            g = ba.angle_rad
+            length = np.sqrt(b1.length ** 2 + b2.length ** 2 - 2 * b1.length * b2.length * np.cos(g))
+            outer = 0.5 / length                                           # d sqrt(u) / du
+            d_gamma = 2 * b1.length * b2.length * np.sin(g) * outer
+            d_b1 = (2 * b1.length - 2 * b2.length * np.cos(g)) * outer
+            d_b2 = (2 * b2.length - 2 * b1.length * np.cos(g)) * outer
+            stddev = np.sqrt((d_gamma * ba.stddev) ** 2 + (d_b1 * b1.stddev) ** 2 + (d_b2 * b2.stddev) ** 2)
+            virtual.append(Bond(ba.atom1_name, ba.atom3name, float(length), float(stddev)))
+        residue_virtual_bonds[resname] = virtual
+    return residue_bonds, residue_virtual_bonds, residue_bond_angles
+
+
+def chi_angle_atom(atom_index: int) -> np.ndarray:
+    """``[21, 37, 4]`` one-hot: for every residue type and chi angle, which atom37 slot holds the ``atom_index``-th of the four atoms defining
+    that torsion (all-zero columns where the residue has fewer chi angles; reference residue_constants.py:757-776)."""
+    out = np.zeros((restype_num + 1, atom_type_num, 4), np.float64)
+    for r, letter in enumerate(restypes):
+        for k, atoms in enumerate(chi_angles_atoms[restype_1to3[letter]]):
+            out[r, atom_order[atoms[atom_index]], k] = 1.0
+    return out
+
+
+chi_atom_1_one_hot = chi_angle_atom(1)
+chi_atom_2_one_hot = chi_angle_atom(2)
+
+
+def make_atom14_dists_bounds(overlap_tolerance: float = 1.5, bond_length_tolerance_factor: float = 15, props=None):
+    """Per residue type, ``[21, 14, 14]`` lower / upper bounds on intra-residue atom distances used to flag structural violations: non-bonded
+    pairs may not come closer than the sum of their van-der-Waals radii minus ``overlap_tolerance``; bonded and 1-3 ("virtual bond") pairs must
+    stay within ``bond_length_tolerance_factor`` standard deviations of the literature length (reference residue_constants.py:908-961).
+    ``props``: the triple from ``load_stereo_chemical_props`` (loaded from the default file when omitted)."""
+    lower = np.zeros((restype_num + 1, 14, 14), np.float32)
+    upper = np.zeros((restype_num + 1, 14, 14), np.float32)
+    stddev = np.zeros((restype_num + 1, 14, 14), np.float32)
+    residue_bonds, residue_virtual_bonds, _ = props if props is not None else load_stereo_chemical_props()
+    for r, letter in enumerate(restypes):
+        resname = restype_1to3[letter]
+        names = restype_name_to_atom14_names[resname]
+        for i, a in enumerate(names):
+            for j, b in enumerate(names):
+                if a and b and i != j:
+                    lower[r, i, j] = van_der_waals_radius[a[0]] + van_der_waals_radius[b[0]] - overlap_tolerance
+                    upper[r, i, j] = 1e10
+        for bond in list(residue_bonds.get(resname, [])) + list(residue_virtual_bonds.get(resname, [])):
+            i, j = names.index(bond.atom1_name), names.index(bond.atom2_name)
+            lo, hi = bond.length - bond_length_tolerance_factor * bond.stddev, bond.length + bond_length_tolerance_factor * bond.stddev
+            lower[r, i, j] = lower[r, j, i] = lo
+            upper[r, i, j] = upper[r, j, i] = hi
+            stddev[r, i, j] = stddev[r, j, i] = bond.stddev
+    return {"lower_bound": lower, "upper_bound": upper, "stddev": stddev}

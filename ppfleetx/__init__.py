@@ -28,7 +28,6 @@ _MOVED = {
     f"{_LM}.moe.gate.switch_gate": f"{_LM}.moe.gate.gates", f"{_LM}.moe.comm": f"{_LM}.moe.comm_ops",
     f"{_VM}.layers.attention": f"{_VM}.vit.vit", f"{_VM}.layers.mlp": f"{_VM}.vit.vit", f"{_VM}.layers.droppath": f"{_VM}.layers", f"{_VM}.layers.embedding": f"{_VM}.layers",
     f"{_VM}.layers.identity": f"{_VM}.layers", f"{_VM}.layers.initializer": f"{_VM}.layers", f"{_VM}.loss.cross_entropy": f"{_VM}.loss", f"{_VM}.metrics.accuracy": f"{_VM}.metrics",
-    f"{_MM}.utils": f"{_MM}.multimodal_module", 
     "data.tokenizers.t5_tokenization_utils": "data.tokenizers.tokenization_utils_base",
     "data.data_tools.ernie.preprocess": "data.data_tools.ernie", "data.data_tools.ernie.preprocess.create_pretraining_data": "data.data_tools.ernie.create_pretraining_data",
     "data.data_tools.ernie.preprocess.trans_to_json": "data.data_tools.ernie.trans_to_json", "data.data_tools.ernie.preprocess.words_segmentation": "data.data_tools.ernie.words_segmentation",

@@ -219,3 +219,53 @@ def test_evoformer_with_templates_and_extra_msa_parallel_matches_single(mode):
 
 def test_dap_split_phase_pairs_match_one_shot_ops():
     run_distributed("dist_fns:dap_split_phase_pairs", 2)
+
+
+def test_geometry_and_chemistry_helpers_of_the_reference(tmp_path):
+    import numpy as np
+
+    from paddlefleetx_b200.models.protein_folding import quat_affine as QA
+    from paddlefleetx_b200.models.protein_folding import r3
+    from paddlefleetx_b200.models.protein_folding import residue_constants as rc
+
+    torch.manual_seed(0)
+    rig = r3.rigids_from_3_points_vecs(torch.randn(5, 3), torch.randn(5, 3), torch.randn(5, 3))
+    back = r3.rigids_from_tensor_flat9(r3.rigids_to_tensor_flat9(rig))
+    torch.testing.assert_close(back.rot, rig.rot, atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(back.trans, rig.trans)
+    assert r3.broadcast_shape([4, 1, 3], [5, 1]) == [4, 5, 3] and r3.broadcast_to(torch.zeros(1, 3), [4, 3]).shape == (4, 3)
+    assert float(r3.squared_difference(torch.tensor(3.0), torch.tensor(1.0))) == 4.0
+    # NumPy forms agree with the tensor forms and put the canonical backbone back where it came from
+    n, ca, c = (np.random.RandomState(i).randn(6, 3) for i in range(3))
+    rot, trans = QA.make_transform_from_reference_np(n, ca, c)
+    rot_t, trans_t = QA.make_transform_from_reference(*(torch.from_numpy(a) for a in (n, ca, c)))
+    np.testing.assert_allclose(rot, rot_t.numpy(), atol=1e-12)
+    np.testing.assert_allclose(trans, trans_t.numpy(), atol=1e-12)
+    t_can, r_can = QA.make_canonical_transform_np(n, ca, c)
+    c_can = np.einsum("bij,bj->bi", r_can, c + t_can)
+    n_can = np.einsum("bij,bj->bi", r_can, n + t_can)
+    assert np.abs(c_can[:, 1:]).max() < 1e-9 and (c_can[:, 0] > 0).all() and np.abs(n_can[:, 2]).max() < 1e-9
+    x, y, z = QA.apply_rot_to_vec_np(np.eye(3) * 2.0, np.array([[1.0, 2.0, 3.0]]), unstack=True)
+    assert (x, y, z) == (2.0, 4.0, 6.0) or np.allclose([x[0], y[0], z[0]], [2, 4, 6])
+    # chi-angle one-hots: ARG chi1 is N-CA-CB-CG, so atom 1 of chi 0 is CA, atom 2 is CB; GLY has none
+    arg, gly = rc.restype_order["R"], rc.restype_order["G"]
+    assert rc.chi_atom_1_one_hot.shape == (21, 37, 4)
+    assert rc.chi_atom_1_one_hot[arg, rc.atom_order["CA"], 0] == 1 and rc.chi_atom_2_one_hot[arg, rc.atom_order["CB"], 0] == 1
+    assert rc.chi_atom_1_one_hot[gly].sum() == 0 and rc.chi_angle_atom(3)[arg, rc.atom_order["CZ"], 3] == 1
+    # stereo-chemistry table in the upstream text format
+    table = tmp_path / "stereo_chemical_props.txt"
+    table.write_text("Bond Residue Mean StdDev\nN-CA ALA 1.459 0.020\nCA-C ALA 1.525 0.026\nCA-CB ALA 1.520 0.021\n-\n\n"
+                     "Angle Residue Mean StdDev\nN-CA-C ALA 111.0 2.7\nN-CA-CB ALA 110.1 1.4\n-\n")
+    bonds, virtual, angles = rc.load_stereo_chemical_props(str(table))
+    assert [b.atom2_name for b in bonds["ALA"]] == ["CA", "C", "CB"] and bonds["UNK"] == [] and len(angles["ALA"]) == 2
+    nc = virtual["ALA"][0]
+    want = np.sqrt(1.459 ** 2 + 1.525 ** 2 - 2 * 1.459 * 1.525 * np.cos(np.deg2rad(111.0)))
+    assert (nc.atom1_name, nc.atom2_name) == ("N", "C") and abs(nc.length - want) < 1e-9 and 0 < nc.stddev < 0.1
+    bounds = rc.make_atom14_dists_bounds(props=(bonds, virtual, angles))
+    ala = rc.restype_order["A"]
+    assert bounds["lower_bound"].shape == (21, 14, 14)
+    assert abs(bounds["lower_bound"][ala, 0, 1] - (1.459 - 15 * 0.020)) < 1e-6 and abs(bounds["upper_bound"][ala, 1, 0] - (1.459 + 15 * 0.020)) < 1e-6
+    assert abs(bounds["lower_bound"][ala, 0, 3] - (1.55 + 1.52 - 1.5)) < 1e-6 and bounds["upper_bound"][ala, 0, 3] == np.float32(1e10)    # N..O: clash bound only
+    assert bounds["lower_bound"][ala, 5, 6] == 0                                                      # empty slots
+    with pytest.raises(FileNotFoundError):
+        rc.load_stereo_chemical_props(str(tmp_path / "missing.txt"))
