@@ -53,6 +53,12 @@ class _CorpusWordPiece:
     def encode(self, text):
         return self.tok.encode_plain(text)
 
+    def tokenize(self, text):
+        return self.tok.tokenize(text)
+
+    def convert_tokens_to_ids(self, tokens):
+        return self.tok.convert_tokens_to_ids(tokens)
+
     def __len__(self):
         return len(self.tok)
 
@@ -84,41 +90,178 @@ def split_sentences(text, chinese):
     return [s for s in (p.strip() for p in parts) if s]
 
 
+# ---- Chinese word segmentation back ends (reference preprocess_data.py:136-165): each factory returns ``text -> list of words``
+def lexical_analysis_fn():
+    """Baidu LAC, lexical-analysis mode (words with part-of-speech tags; the tags are dropped)."""
+    from LAC import LAC
+
+    lac = LAC(mode="lac")
+    return lambda line: lac.run(line)[0]
+
+
+def chinese_segmentation_fn():
+    """Baidu LAC, segmentation-only mode."""
+    from LAC import LAC
+
+    lac = LAC(mode="seg")
+    return lambda line: lac.run(line)
+
+
+def jieba_segmentation_fn():
+    import jieba
+
+    return lambda line: list(jieba.cut(line))
+
+
+CHINESE_SEG_FUNC = {"lac": lexical_analysis_fn, "seg": chinese_segmentation_fn, "jieba": jieba_segmentation_fn}
+_CJK = re.compile("[\u4E00-\u9FA5]")
+
+
+def get_whole_word_mask_tokens(tokens, words, max_word_length=4):
+    """Mark Chinese whole words on a WordPiece sequence: the pieces are single Chinese characters, ``words`` the segmentation of the same text;
+    every character that continues a segmented word gets the ``##`` prefix (``通 过 利 用`` + {通过, 利用} -> ``通 ##过 利 ##用``), so that the
+    masking code, which groups on ``##``, masks whole words.  Longest match first, at most ``max_word_length`` characters; pieces without
+    Chinese characters pass through (they already carry WordPiece's own ``##``).  Reference preprocess_data.py:168-227."""
+    vocabulary = set(words)
+    out, i, n = [], 0, len(tokens)
+    while i < n:
+        piece = tokens[i]
+        if _CJK.search(piece) is None:
+            out.append(piece)
+            i += 1
+            continue
+        span = next((k for k in range(min(max_word_length, n - i), 0, -1) if "".join(tokens[i:i + k]) in vocabulary), 1)
+        out.append(piece)
+        out.extend("##" + t for t in tokens[i + 1:i + span])
+        i += span
+    return out
+
+
+def _join_words(words) -> str:
+    """Re-assemble segmented words into the text the tokenizer sees: nothing between Chinese neighbours, a space between two non-Chinese words
+    (a pre-split corpus has lost the original spaces; gluing ``hello`` and ``world`` together would change their word pieces)."""
+    out = []
+    for w in words:
+        if out and not _CJK.search(out[-1][-1:]) and not _CJK.search(w[:1]) and not out[-1][-1:].isspace() and not w[:1].isspace():
+            out.append(" ")
+        out.append(w)
+    return "".join(out)
+
+
+class IdentitySplitter:
+    """No sentence splitting: the document is one "sentence"."""
+
+    def tokenize(self, *text):
+        return text
+
+
+class NewlineSplitter:
+    """One sentence per line (the convention of the pre-split Chinese corpora)."""
+
+    def tokenize(self, text):
+        return text.split("\n")
+
+
+class _RegexSplitter:
+    """Punctuation-based sentence splitter used when NLTK's punkt model is not on the machine."""
+
+    def __init__(self, chinese):
+        self.chinese = chinese
+
+    def tokenize(self, text):
+        return split_sentences(text, self.chinese)
+
+
 def segment_chinese(text, args):
     if args.cn_splited:
         return text.split(args.cn_split_dimer)
     try:
-        import jieba
-
-        return list(jieba.cut(text))
+        return CHINESE_SEG_FUNC[getattr(args, "cn_seg_func", "jieba")]()(text)
     except ImportError:        # character-level fallback keeps the tool usable without the segmenter
         return list(text)
 
 
+class Converter:
+    """jsonl line -> list of sentences, each a list of token ids (reference preprocess_data.py:240-294).  ``initializer()`` builds the
+    tokenizer, the sentence splitter and the Chinese segmenter once per worker process; ``encode(line)`` returns ``(doc_ids, n_bytes)``."""
+
+    def __init__(self, args):
+        self.args = args
+
+    def initializer(self):
+        a = self.args
+        Converter.tokenizer = build_tokenizer(a)
+        if a.split_sentences:
+            Converter.splitter = _ChineseSplitter() if a.chinese else _english_splitter()
+        else:
+            Converter.splitter = IdentitySplitter()
+        tok = Converter.tokenizer
+        if a.cn_whole_word_segment and hasattr(tok, "tokenize") and hasattr(tok, "convert_tokens_to_ids"):
+            if a.cn_splited:
+                segment = lambda text: text.split(a.cn_split_dimer)      # noqa: E731
+            else:
+                try:
+                    segment = CHINESE_SEG_FUNC[a.cn_seg_func]()
+                except ImportError:
+                    segment = list                                       # no segmenter installed: every character is its own word
+            Converter.segment_func = staticmethod(segment)
+
+            def process(text):
+                words = [w for w in segment(text) if w.strip()]
+                pieces = get_whole_word_mask_tokens(tok.tokenize(_join_words(words)), words)
+                return tok.convert_tokens_to_ids(pieces)
+        else:
+            Converter.segment_func = staticmethod(lambda x: x)
+
+            def process(text):
+                return tok.encode(text)
+        Converter.process = staticmethod(process)
+
+    def encode(self, json_line):
+        text = json.loads(json_line).get(self.args.json_key, "")
+        doc_ids = []
+        for sentence in Converter.splitter.tokenize(text):
+            ids = Converter.process(sentence.strip()) if sentence.strip() else []
+            if len(ids) > 0:
+                doc_ids.append(list(ids))
+        if doc_ids and self.args.append_eos:
+            doc_ids[-1].append(Converter.tokenizer.eos_token_id)
+        return doc_ids, len(text.encode("utf-8"))
+
+
+class _ChineseSplitter:
+    """Newline-separated sentences when the document has them (pre-split corpora), punctuation otherwise."""
+
+    def tokenize(self, text):
+        return [s for s in text.split("\n") if s.strip()] if "\n" in text.strip() else split_sentences(text, True)
+
+
+def _english_splitter():
+    try:
+        import nltk
+
+        return nltk.load("tokenizers/punkt/english.pickle")
+    except Exception:            # noqa: BLE001 - nltk or its punkt data missing (offline): regex splitter
+        return _RegexSplitter(False)
+
+
+_CONVERTER = None
+
+
 def _init(args):
-    global _TOK, _ARGS
+    global _TOK, _ARGS, _CONVERTER
     _ARGS = args
-    _TOK = build_tokenizer(args)
+    _CONVERTER = Converter(args)
+    _CONVERTER.initializer()
+    _TOK = Converter.tokenizer
 
 
 def encode_line(line):
     line = line.strip()
     if not line:
         return [], 0
-    text = json.loads(line).get(_ARGS.json_key, "")
-    if not text:
-        return [], len(line)
-    sents = split_sentences(text, _ARGS.chinese) if _ARGS.split_sentences else [text]
-    out = []
-    for s in sents:
-        if _ARGS.chinese and _ARGS.cn_whole_word_segment:
-            s = " ".join(segment_chinese(s, _ARGS))
-        ids = _TOK.encode(s)
-        if ids:
-            out.append(ids)
-    if out and _ARGS.append_eos:
-        out[-1] = list(out[-1]) + [_TOK.eos_token_id]
-    return out, len(line)
+    sents, _ = _CONVERTER.encode(line)
+    return sents, len(line)
 
 
 def main(argv=None):

@@ -56,6 +56,56 @@ def convert_file(job):
     return path, out_path, n
 
 
+def raw_text_to_json(path, doc_spliter="", json_key="text", min_doc_length=10):
+    """One raw text file -> ``<path>.jsonl``; returns ``(bytes read, output path)`` (``(0, None)`` for a missing file) — the reference's
+    per-file entry point (raw_trans_to_json.py:75-105)."""
+    path = os.path.abspath(path)
+    if not os.path.exists(path):
+        print("No found file %s" % path)
+        return 0, None
+    out_path = path + ".jsonl"
+    convert_file((path, out_path, json_key, doc_spliter, min_doc_length))
+    return os.path.getsize(path), out_path
+
+
+def merge_file(file_paths, output_path):
+    """Concatenate the per-file jsonl parts into ``output_path`` (``.jsonl`` appended when missing) and delete the parts."""
+    if not output_path.endswith(".jsonl"):
+        output_path += ".jsonl"
+    print("Merging files into %s" % output_path)
+    with open(output_path, "wb") as out:
+        for part in file_paths:
+            if part is not None and os.path.exists(part):
+                with open(part, "rb") as f:
+                    shutil.copyfileobj(f, out)
+                os.remove(part)
+    print("File save in %s" % output_path)
+    return output_path
+
+
+def shuffle_file(output_path, seed: int = 1234):
+    """Shuffle the lines of a jsonl file in place (the reference shells out to ``shuf``; here: line offsets shuffled in Python, the file
+    re-written through a temporary — no dependency on coreutils, deterministic under ``seed``)."""
+    if not os.path.exists(output_path):
+        raise ValueError("File not found: %s" % output_path)
+    print("Shuffling the jsonl file...")
+    offsets = []
+    with open(output_path, "rb") as f:
+        pos = 0
+        for line in f:
+            offsets.append((pos, len(line)))
+            pos += len(line)
+    random.Random(seed).shuffle(offsets)
+    tmp = output_path + ".shuf"
+    with open(output_path, "rb") as f, open(tmp, "wb") as out:
+        for pos, n in offsets:
+            f.seek(pos)
+            line = f.read(n)
+            out.write(line if line.endswith(b"\n") else line + b"\n")
+    os.replace(tmp, output_path)
+    print("File shuffled!!!")
+
+
 def main(argv=None):
     a = get_args(argv)
     if os.path.isdir(a.input_path):

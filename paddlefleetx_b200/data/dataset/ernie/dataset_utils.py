@@ -17,6 +17,25 @@ from ....utils.log import logger
 from ..gpt_dataset import _helpers
 
 
+def get_local_rank() -> int:
+    return int(os.environ.get("LOCAL_RANK", os.environ.get("PADDLE_RANK_IN_NODE", 0)))
+
+
+def get_datasets_weights_and_num_samples(data_prefix, train_valid_test_num_samples):
+    """``[w1, prefix1, w2, prefix2, ...]`` -> ``(prefixes, normalised weights, per-dataset [train, valid, test] sample counts)``; each count is
+    the weighted share plus 0.5 % head-room so that a blend that does not draw perfectly evenly never runs dry (reference dataset_utils.py:46-75)."""
+    import math
+
+    assert len(data_prefix) % 2 == 0, "data_prefix must alternate weight, prefix"
+    weights = [float(w) for w in data_prefix[0::2]]
+    prefixes = [str(p).strip() for p in data_prefix[1::2]]
+    total = sum(weights)
+    assert total > 0.0
+    weights = [w / total for w in weights]
+    counts = [[int(math.ceil(n * w * 1.005)) for n in train_valid_test_num_samples] for w in weights]
+    return prefixes, weights, counts
+
+
 class MMapIndexedDataset:
     """Sentence-addressable view of the flat token stream."""
 
@@ -155,6 +174,18 @@ def pad_and_convert_to_numpy(tokens, tokentypes, positions, labels, pad_id: int,
 def make_indexed_dataset(data_prefix, data_impl=None, skip_warmup=False):
     """``<prefix>_ids.npy`` + ``<prefix>_idx.npz`` -> ``MMapIndexedDataset`` (``data_impl`` / ``skip_warmup`` kept for call-site parity)."""
     return MMapIndexedDataset(data_prefix)
+
+
+def get_indexed_dataset_(data_prefix, data_impl=None, skip_warmup=False):
+    """``make_indexed_dataset`` plus the consistency check and the statistics the reference logs (dataset_utils.py:529-545)."""
+    import time
+
+    t0 = time.time()
+    ds = make_indexed_dataset(data_prefix, data_impl, skip_warmup)
+    assert ds.sizes.shape[0] == ds.doc_idx[-1], "the last document boundary must equal the number of sentences"
+    logger.info(f" > indexed dataset {data_prefix}: {ds.doc_idx.shape[0] - 1} documents, {ds.sizes.shape[0]} sentences "
+                f"({time.time() - t0:.4f}s)")
+    return ds
 
 
 def is_start_piece(piece: str) -> bool:

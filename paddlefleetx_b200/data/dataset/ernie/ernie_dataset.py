@@ -18,6 +18,55 @@ from .dataset_utils import (MMapIndexedDataset, create_masked_lm_predictions, cr
                             get_samples_mapping, pad_and_convert_to_numpy, truncate_segments)
 
 
+def get_local_rank() -> int:
+    """Rank inside the node: decides who builds the index caches (the launcher's ``LOCAL_RANK``; Paddle's ``PADDLE_RANK_IN_NODE`` is honoured too)."""
+    return int(os.environ.get("LOCAL_RANK", os.environ.get("PADDLE_RANK_IN_NODE", 0)))
+
+
+def get_train_data_file(input_dir: str):
+    """Corpus prefixes found in ``input_dir`` (same lookup as the GPT dataset; reference ernie_dataset.py)."""
+    from ..gpt_dataset import get_train_data_file as _find
+
+    return _find(input_dir)
+
+
+def get_train_valid_test_split_(splits, size: int):
+    from .dataset_utils import get_train_valid_test_split_ as _split
+
+    return _split(splits, size)
+
+
+def build_training_sample(sample, target_seq_length, max_seq_length, vocab_id_list=None, vocab_id_to_token_dict=None, vocab_token_to_id_dict=None,
+                          cls_id=1, sep_id=2, mask_id=3, pad_id=0, masked_lm_prob=0.15, np_rng=None, binary_head=True, favor_longer_ngram=False,
+                          max_ngrams=3, vocab_size=None):
+    """One pre-training example from a list of sentences (each a sequence of token ids) — reference ernie_dataset.py:156-260: split into
+    segments A / B (swapped half of the time when ``binary_head``), truncate to ``target_seq_length``, add [CLS] / [SEP] and token types,
+    mask n-grams for the MLM objective, pad to ``max_seq_length``.  Random replacement ids are drawn from ``vocab_id_list`` (or
+    ``range(vocab_size)``).  Returns the reference's dict: ``text``, ``types``, ``labels`` (-1 where nothing is predicted), ``is_random``,
+    ``loss_mask``, ``padding_mask``, ``truncated`` — plus ``masked_positions`` / ``masked_labels``, the compact form our collate uses."""
+    np_rng = np_rng if np_rng is not None else np.random.RandomState(1234)
+    if binary_head:
+        assert len(sample) > 1, "The sentence num should be large than 1."
+    assert target_seq_length <= max_seq_length
+    if binary_head:
+        a, b, swapped = get_a_and_b_segments(sample, np_rng)
+    else:
+        a, b, swapped = [int(t) for sent in sample for t in sent], [], False
+    truncated = truncate_segments(a, b, target_seq_length, np_rng)
+    tokens, types = create_tokens_and_tokentypes(a, b, cls_id, sep_id)
+    if vocab_size is None:
+        vocab_size = (max(vocab_id_list) + 1) if vocab_id_list is not None else 40000
+    max_pred = int(masked_lm_prob * max_seq_length) + 1
+    masked, positions, labels = create_masked_lm_predictions(tokens, vocab_size, cls_id, sep_id, mask_id, masked_lm_prob, max_pred, np_rng, max_ngrams,
+                                                             favor_longer_ngram=favor_longer_ngram)
+    tok, typ, pad_mask, pos, lab = pad_and_convert_to_numpy(masked, types, positions, labels, pad_id, max_seq_length)
+    dense_labels = np.full(max_seq_length, -1, dtype=np.int64)
+    loss_mask = np.zeros(max_seq_length, dtype=np.int64)
+    dense_labels[pos], loss_mask[pos] = lab, 1
+    return {"text": tok, "types": typ, "labels": dense_labels, "is_random": int(swapped), "loss_mask": loss_mask, "padding_mask": pad_mask,
+            "truncated": int(truncated), "masked_positions": pos, "masked_labels": lab}
+
+
 class ErnieDataset(torch.utils.data.Dataset):
     def __init__(self, input_dir: str, split: Sequence[float] = (949, 50, 1), max_seq_len: int = 512, max_seq_length: Optional[int] = None,
                  num_samples: Optional[int] = None, mode: str = "Train", masked_lm_prob: float = 0.15, short_seq_prob: float = 0.1, seed: int = 1234,
@@ -46,7 +95,7 @@ class ErnieDataset(torch.utils.data.Dataset):
         bounds = train_valid_test_split(split, n_docs)
         k = {"Train": 0, "Eval": 1, "Test": 2}[mode]
         doc_idx = self.indexed.doc_idx[bounds[k]:bounds[k + 1] + 1]
-        local_rank = int(os.environ.get("LOCAL_RANK", 0))
+        local_rank = get_local_rank()
         self.samples_mapping = get_samples_mapping(self.indexed, doc_idx, prefix, None, num_samples, self.max_seq_length - 3, short_seq_prob, seed,
                                                    "ernie_" + mode, binary_head, build=(local_rank == 0))
 
@@ -57,18 +106,12 @@ class ErnieDataset(torch.utils.data.Dataset):
         start, end, target_len = (int(v) for v in self.samples_mapping[idx])
         sample = [self.indexed[i] for i in range(start, end)]
         rng = np.random.RandomState(seed=((self.seed + idx) % 2 ** 32))
-        if self.binary_head:
-            a, b, swapped = get_a_and_b_segments(sample, rng)
-        else:
-            a, b, swapped = [int(t) for s in sample for t in s], [], False
-        truncate_segments(a, b, min(target_len, self.max_seq_length - 3), rng)
-        tokens, types = create_tokens_and_tokentypes(a, b, self.cls_id, self.sep_id)
-        max_pred = int(self.masked_lm_prob * self.max_seq_length) + 1
-        masked, positions, labels = create_masked_lm_predictions(tokens, self.vocab_size, self.cls_id, self.sep_id, self.mask_id,
-                                                                 self.masked_lm_prob, max_pred, rng, self.max_ngrams,
-                                                                 favor_longer_ngram=self.favor_longer_ngram)
-        tok, typ, mask, pos, lab = pad_and_convert_to_numpy(masked, types, positions, labels, self.pad_id, self.max_seq_length)
-        return [tok, typ, mask, pos, lab, np.asarray([int(swapped)], dtype=np.int64)]
+        ex = build_training_sample(sample, min(target_len, self.max_seq_length - 3), self.max_seq_length, cls_id=self.cls_id, sep_id=self.sep_id,
+                                   mask_id=self.mask_id, pad_id=self.pad_id, masked_lm_prob=self.masked_lm_prob, np_rng=rng,
+                                   binary_head=self.binary_head, favor_longer_ngram=self.favor_longer_ngram, max_ngrams=self.max_ngrams,
+                                   vocab_size=self.vocab_size)
+        return [ex["text"], ex["types"], ex["padding_mask"], ex["masked_positions"], ex["masked_labels"],
+                np.asarray([ex["is_random"]], dtype=np.int64)]
 
 
 class SyntheticErnieDataset(torch.utils.data.Dataset):

@@ -72,6 +72,22 @@ def find_corpus_prefix(input_dir: str) -> str:
     raise RuntimeError(f"no xxx_ids.npy / xxx_idx.npz corpus found in {input_dir!r}")
 
 
+def get_train_data_file(input_dir: str) -> List[str]:
+    """Prefixes of every corpus in ``input_dir`` (``<prefix>_ids.npy`` + ``<prefix>_idx.npz``; falls back to the legacy single-file
+    ``<prefix>_ids.npz``) — the reference's lookup (gpt_dataset.py:220-247); ``find_corpus_prefix`` is "the first of these"."""
+    names = sorted(f for f in os.listdir(input_dir) if f.endswith("_idx.npz") and os.path.isfile(os.path.join(input_dir, f)))
+    if names:
+        return [os.path.join(input_dir, n[:-len("_idx.npz")]) for n in names]
+    logger.warning("Not found dataset with name of xxx_ids.npy and xxx_idx.npz! Try to found old compatible xxx_ids.npz file.")
+    legacy = sorted(f for f in os.listdir(input_dir) if f.endswith("_ids.npz") and os.path.isfile(os.path.join(input_dir, f)))
+    if not legacy:
+        raise RuntimeError(f"Not found dataset with name of xxx_ids.npz in given input_dir '{input_dir}'! ")
+    return [os.path.join(input_dir, n[:-len("_ids.npz")]) for n in legacy]
+
+
+get_train_valid_test_split_ = train_valid_test_split          # reference name (gpt_dataset.py:250-271)
+
+
 class TokenCorpus:
     """Flat token stream + per-document lengths."""
 
@@ -177,6 +193,12 @@ def build_index_files(name: str, prefix: str, documents: np.ndarray, sizes: np.n
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()          # a failing barrier must surface: continuing would leave the ranks with different views of the cache
     return tuple(np.load(p, allow_pickle=True, mmap_mode="r") for p in paths)
+
+
+def construct_samples_and_shuffle_data(name, data_prefix, documents, sizes, num_samples, seq_length, seed, build_data_file):
+    """``(doc_idx, sample_idx, shuffle_idx)`` for one split, built (or awaited) and cached next to the corpus as
+    ``<prefix>_<name>_indexmap_<ns>ns_<sl>sl_{doc,sample,shuffle}_idx.npy`` — the reference entry point (gpt_dataset.py:274-393)."""
+    return build_index_files(name, data_prefix, np.asarray(documents), np.asarray(sizes), num_samples, seq_length, seed, build_data_file)
 
 
 class GPTDataset(torch.utils.data.Dataset):

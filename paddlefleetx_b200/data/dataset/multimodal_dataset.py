@@ -14,15 +14,33 @@ import torch
 from ...distributed.apis import env
 
 
+def get_keys(data_path: str, gpu_num: int, rank: int = None, seed: int = 0):
+    """Shard files of ``data_path`` (one per line) for this rank: the list is padded with randomly re-drawn shards to a multiple of
+    ``gpu_num`` so that every rank gets the same number, then dealt out round-robin (reference multimodal_dataset.py:40-62).  The padding draw
+    is seeded, so all ranks agree on it without communicating."""
+    import random
+
+    with open(data_path) as f:
+        files = [line.strip() for line in f if line.strip()]
+    rank = env.get_data_world_rank() if rank is None else rank
+    extended = list(files)
+    if files and len(files) % gpu_num:
+        need = gpu_num - len(files) % gpu_num
+        rng = random.Random(seed)
+        extended += rng.sample(files, need) if need <= len(files) else [rng.choice(files) for _ in range(need)]
+    return extended[rank::gpu_num]
+
+
 class ImagenDataset(torch.utils.data.Dataset):
     def __init__(self, input_path: str, image_size: int = 64, text_max_len: int = 128, filter_image_resolution: int = 128, image_format: str = "base64",
                  caption_col: int = 2, image_col: int = 5, tokenizer=None, split: bool = True, **unused):
         self.image_size, self.text_max_len, self.min_res = image_size, text_max_len, filter_image_resolution
         self.caption_col, self.image_col = caption_col, image_col
-        with open(input_path) as f:
-            shards = [l.strip() for l in f if l.strip()]
         if split and env.get_data_world_size() > 1:
-            shards = shards[env.get_data_world_rank()::env.get_data_world_size()]
+            shards = get_keys(input_path, env.get_data_world_size())      # padded: every rank reads the same number of shards
+        else:
+            with open(input_path) as f:
+                shards = [l.strip() for l in f if l.strip()]
         self.rows = []
         for shard in shards:
             path = shard if os.path.isabs(shard) else os.path.join(os.path.dirname(input_path), shard)

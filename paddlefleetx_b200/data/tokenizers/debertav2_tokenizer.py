@@ -22,6 +22,15 @@ def _is_punct(ch: str) -> bool:
     return (33 <= cp <= 47) or (58 <= cp <= 64) or (91 <= cp <= 96) or (123 <= cp <= 126) or unicodedata.category(ch).startswith("P")
 
 
+def convert_to_unicode(text):
+    """``str`` as it is, ``bytes`` decoded as UTF-8 (undecodable bytes dropped)."""
+    if isinstance(text, str):
+        return text
+    if isinstance(text, bytes):
+        return text.decode("utf-8", "ignore")
+    raise ValueError(f"Unsupported string type: {type(text)}")
+
+
 class SPMTokenizer:
     def __init__(self, vocab_file: str, special_tokens: List[str], split_by_punct: bool = False):
         import sentencepiece as spm

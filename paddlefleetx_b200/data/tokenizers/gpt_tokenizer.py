@@ -31,6 +31,11 @@ def bytes_to_unicode() -> Dict[int, str]:
 _SPLIT = re.compile(r"""'s|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+""")
 
 
+def get_pairs(word):
+    """Set of adjacent symbol pairs of a word given as a tuple of symbols (the candidates of one BPE merge step)."""
+    return set(zip(word, word[1:]))
+
+
 class GPTTokenizer:
     eos_token = "<|endoftext|>"
 

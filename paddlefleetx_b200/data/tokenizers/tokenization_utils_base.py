@@ -21,6 +21,26 @@ ADDED_TOKENS_FILE = "added_tokens.json"
 TOKENIZER_CONFIG_FILE = "tokenizer_config.json"
 
 
+def is_sentencepiece_available() -> bool:
+    import importlib.util
+
+    return importlib.util.find_spec("sentencepiece") is not None
+
+
+def is_tokenizers_available() -> bool:
+    import importlib.util
+
+    return importlib.util.find_spec("tokenizers") is not None
+
+
+SPECIAL_MODEL_TYPE_TO_MODULE_NAME = {"openai-gpt": "openai", "data2vec-audio": "data2vec", "data2vec-text": "data2vec", "data2vec-vision": "data2vec"}
+
+
+def model_type_to_module_name(key: str) -> str:
+    """``config.json`` model type -> module name (dashes become underscores, a few irregular names are listed)."""
+    return SPECIAL_MODEL_TYPE_TO_MODULE_NAME.get(key, key.replace("-", "_"))
+
+
 class ExplicitEnum(str, Enum):
     @classmethod
     def _missing_(cls, value):

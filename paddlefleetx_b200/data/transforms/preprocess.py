@@ -54,6 +54,39 @@ def _resize(img: np.ndarray, size, interpolation: str = "bilinear") -> np.ndarra
     return out.astype(img.dtype)
 
 
+class OperatorParamError(ValueError):
+    """An image operator was configured with an impossible combination of parameters (reference preprocess.py:34-37)."""
+
+
+class UnifiedResize:
+    """``resize(src, (width, height))`` with the interpolation chosen by name, through OpenCV (``backend="cv2"``, when installed) or PIL
+    (reference preprocess.py:63-104; note the OpenCV-style ``(width, height)`` size order of this call).  Unknown back ends fall back to the
+    first one available; with neither library a NumPy bilinear kernel is used."""
+
+    _CV2 = {"nearest": "INTER_NEAREST", "bilinear": "INTER_LINEAR", "area": "INTER_AREA", "bicubic": "INTER_CUBIC", "lanczos": "INTER_LANCZOS4"}
+
+    def __init__(self, interpolation=None, backend="cv2"):
+        self.interpolation = (interpolation or "bilinear").lower() if isinstance(interpolation, (str, type(None))) else interpolation
+        self.backend = str(backend).lower()
+        self._cv2 = None
+        if self.backend == "cv2":
+            try:
+                import cv2
+
+                self._cv2 = cv2
+            except ImportError:
+                self.backend = "pil"
+        elif self.backend != "pil":
+            self.backend = "pil"
+
+    def __call__(self, src, size):
+        w, h = int(size[0]), int(size[1])
+        if self._cv2 is not None:
+            interp = getattr(self._cv2, self._CV2.get(self.interpolation, "INTER_LINEAR")) if isinstance(self.interpolation, str) else self.interpolation
+            return self._cv2.resize(src, (w, h), interpolation=interp)
+        return _resize(src, (h, w), self.interpolation if isinstance(self.interpolation, str) else "bilinear")
+
+
 class DecodeImage:
     def __init__(self, to_rgb: bool = True, channel_first: bool = False, **unused):
         self.to_rgb, self.channel_first = to_rgb, channel_first
@@ -73,7 +106,9 @@ class DecodeImage:
 
 class ResizeImage:
     def __init__(self, size=None, resize_short=None, interpolation="bilinear", backend="pil", **unused):
-        self.size, self.resize_short, self.interp = size, resize_short, interpolation
+        if not (resize_short and resize_short > 0) and size is None:
+            raise OperatorParamError("invalid params for ResizeImage: both 'size' and 'resize_short' are None")
+        self.size, self.resize_short, self.interp = size, resize_short, interpolation or "bilinear"
 
     def __call__(self, img):
         h, w = img.shape[:2]

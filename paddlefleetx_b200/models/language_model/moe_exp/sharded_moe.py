@@ -16,6 +16,26 @@ import torch.nn.functional as F
 from ....parallel import comm_ops as C
 
 
+def einsum(rule: str, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """The handful of contractions of the einsum-formulated MoE layer (dispatch / combine), each lowered to ONE GEMM or broadcast multiply —
+    ``se,sc->sec`` outer product, ``sec,sm->ecm`` dispatch, ``sec,ecm->sm`` combine, ``se,se->s`` row dot, ``s,se->se`` row scale,
+    ``ks,ksm->sm`` top-k merge — and ``torch.einsum`` for anything else (reference moe_exp/sharded_moe.py:87-117)."""
+    if rule == "s,se->se":
+        return a.reshape(a.shape[0], -1) * b
+    if rule == "se,sc->sec":
+        return a.unsqueeze(2) * b.unsqueeze(1)
+    if rule == "se,se->s":
+        return (a * b).sum(-1)
+    if rule == "sec,sm->ecm":
+        s_, e, c = a.shape
+        return torch.matmul(a.reshape(s_, e * c).t(), b).reshape(e, c, b.shape[1])
+    if rule == "sec,ecm->sm":
+        return torch.matmul(a.reshape(a.shape[0], -1), b.reshape(-1, b.shape[-1]))
+    if rule == "ks,ksm->sm":
+        return torch.bmm(a.t().unsqueeze(1), b.permute(1, 0, 2)).squeeze(1)
+    return torch.einsum(rule, a, b)
+
+
 def multiplicative_jitter(x: torch.Tensor, epsilon: float = 1e-2) -> torch.Tensor:
     if epsilon == 0:
         return x
