@@ -83,4 +83,4 @@ def create_hcg(strategy, hcg_name: str = "HybridCommunicateGroup"):
         raise ValueError(f"unknown hcg {hcg_name}; choose from {sorted(_REGISTRY)}")
     hc = strategy.hybrid_configs
     return _REGISTRY[hcg_name](dp=hc.get("dp_degree", 1), mp=hc.get("mp_degree", 1),
-                               pp=hc.get("pp_degree", 1), sharding=hc.get("sharding_degree", 1), cp=hc.get("cp_degree", 1))
+                               pp=hc.get("pp_degree", 1), sharding=hc.get("sharding_degree", 1), cp=hc.get("cp_degree", 1), cp_mode=hc.get("cp_mode", "ulysses"))

@@ -111,7 +111,7 @@ def init_dist_env(config) -> HybridCommunicateGroup:
             "pp_degree > 1 with sequence_parallel requires enable_partial_send_recv=False"
     st = DistributedStrategy()
     st.hybrid_configs = dict(dp_degree=d.dp_degree, mp_degree=d.mp_degree, pp_degree=d.pp_degree,
-                             sharding_degree=d.sharding.sharding_degree, cp_degree=int(d.get("cp_degree", 1) or 1))
+                             sharding_degree=d.sharding.sharding_degree, cp_degree=int(d.get("cp_degree", 1) or 1), cp_mode=str(d.get("cp_mode", "ulysses") or "ulysses"))
     st.pipeline_configs = dict(
         accumulate_steps=config.Global.local_batch_size // config.Global.micro_batch_size,
         micro_batch_size=config.Global.micro_batch_size,

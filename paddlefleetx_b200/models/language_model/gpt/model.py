@@ -145,14 +145,16 @@ class MultiHeadAttention(nn.Module):
         self.out_proj = Row(hidden, hidden, **rkw)
         # context parallelism (``Distributed.cp_degree`` > 1): the group comes from the process topology, not from a constructor argument,
         # because to every other part of the model the members of a cp group are ordinary data-parallel ranks
-        self.cp_group = None
+        self.cp_group, self.cp_mode = None, "ulysses"
         from ....distributed.apis import env as _env
 
         hcg = getattr(_env, "_hcg", None)           # only an already-built topology counts (get_hcg() would build a default one)
         if hcg is not None and getattr(hcg, "cp", 1) > 1:
             self.cp_group = hcg.get_context_parallel_group()
+            self.cp_mode = getattr(hcg, "cp_mode", "ulysses")
             assert not sequence_parallel, "cp_degree > 1 is not combined with Megatron sequence parallelism"
-            assert self.local_heads % self.cp_group.nranks == 0, f"local heads {self.local_heads} % cp {self.cp_group.nranks}"
+            assert self.cp_mode == "ring" or self.local_heads % self.cp_group.nranks == 0, \
+                f"local heads {self.local_heads} % cp {self.cp_group.nranks} (Ulysses shards heads; cp_mode: ring has no such limit)"
 
     # -- projections -------------------------------------------------------------------------
     def _qkv(self, x: torch.Tensor):
@@ -196,10 +198,22 @@ class MultiHeadAttention(nn.Module):
 
     def _forward_context_parallel(self, x, attn_mask, positions):
         """Ulysses context parallelism: this rank holds ``s / c`` positions of every head; one all-to-all turns that into every position
-        of ``H / c`` heads for the attention itself (causal over the FULL sequence), a second one turns it back."""
+        of ``H / c`` heads for the attention itself (causal over the FULL sequence), a second one turns it back.
+        Ring mode (``Distributed.cp_mode: ring``): every head stays here, K / V blocks travel (parallel/ring_attention.py)."""
         q, k, v = self._qkv(x)                                                   # [b, s/c, H, d]
         if self.use_rope:
             q, k = OF.rope(q.contiguous(), positions), OF.rope(k.contiguous(), positions)      # ``positions`` are global (sliced with the tokens)
+        if self.cp_mode == "ring":
+            assert attn_mask is None, "ring attention builds the causal mask from the zigzag layout; explicit masks are not sharded"
+            from ....parallel.ring_attention import ring_attention
+
+            p = self.attn_dropout if self.training else 0.0
+            if p > 0:
+                with get_rng_state_tracker().rng_state("local_seed"):
+                    out = ring_attention(q, k, v, self.cp_group, True, p, self.head_dim ** -0.5)
+            else:
+                out = ring_attention(q, k, v, self.cp_group, True, 0.0, self.head_dim ** -0.5)
+            return self.out_proj(out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim))
         q, k, v = (C.seq_head_all_to_all(t, self.cp_group, 2, 1) for t in (q, k, v))           # [b, s, H/c, d]
         out = recompute(self._core, q, k, v, attn_mask) if (self.recompute_core and self.training) else self._core(q, k, v, attn_mask)
         out = C.seq_head_all_to_all(out, self.cp_group, 1, 2)                    # [b, s/c, H, d]

@@ -158,6 +158,10 @@ class LanguageModule(BasicModule):
         if c == 1:
             return batch
         r = hcg.get_context_parallel_rank()
+        if getattr(hcg, "cp_mode", "ulysses") == "ring":          # chunks r and 2c-1-r of 2c: equal causal work on every rank at every ring step
+            from ...parallel.ring_attention import zigzag_slice
+
+            return [zigzag_slice(t, c, r, dim=1).contiguous() for t in batch]
         assert batch[0].shape[1] % c == 0, f"sequence length {batch[0].shape[1]} % cp_degree {c}"
         return [t.chunk(c, dim=1)[r].contiguous() for t in batch]
 

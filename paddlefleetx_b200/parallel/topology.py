@@ -91,7 +91,7 @@ class HybridCommunicateGroup:
     process group (all groups degenerate to size 1), which is what single-card runs use."""
 
     def __init__(self, dp: int = 1, mp: int = 1, pp: int = 1, sharding: int = 1,
-                 rank: Optional[int] = None, world_size: Optional[int] = None, build_groups: bool = True, cp: int = 1):
+                 rank: Optional[int] = None, world_size: Optional[int] = None, build_groups: bool = True, cp: int = 1, cp_mode: str = "ulysses"):
         initialised = dist.is_available() and dist.is_initialized()
         self.global_rank = rank if rank is not None else (dist.get_rank() if initialised else 0)
         self.nranks = world_size if world_size is not None else (dist.get_world_size() if initialised else 1)
@@ -109,6 +109,9 @@ class HybridCommunicateGroup:
         # group that works on one batch, each rank on its slice of the sequence; to the samplers the group is one data replica, to the
         # gradient reduction its members are ordinary data ranks (different tokens, same parameters)
         self.cp = int(cp)
+        self.cp_mode = str(cp_mode or "ulysses").lower()      # "ulysses": heads <-> sequence all-to-all; "ring": zigzag shards, K / V blocks on a ring
+        if self.cp_mode not in ("ulysses", "ring"):
+            raise ValueError(f"cp_mode {cp_mode!r}: 'ulysses' or 'ring'")
         data = dp * sharding
         if self.cp < 1 or data % self.cp:
             raise ValueError(f"cp_degree {cp} must divide dp x sharding = {data}")

@@ -211,7 +211,11 @@ def process_dist_config(cfg: AttrDict, nranks: Optional[int] = None) -> None:
 
     cp = dist_cfg.setdefault("cp_degree", 1) or 1
     dist_cfg["cp_degree"] = cp
-    if cp > 1:        # context parallelism: cp consecutive data ranks share a batch and split its sequence (Ulysses all-to-all around attention)
+    mode = str(dist_cfg.setdefault("cp_mode", "ulysses") or "ulysses").lower()
+    if mode not in ("ulysses", "ring"):
+        raise AssertionError(f"cp_mode[{mode}] must be 'ulysses' (all-to-all around attention, cp <= heads / mp) or 'ring' (K / V blocks passed round the group)")
+    dist_cfg["cp_mode"] = mode
+    if cp > 1:        # context parallelism: cp consecutive data ranks share a batch and split its sequence
         if (dp * sd) % cp != 0:
             raise AssertionError(f"cp_degree[{cp}] must divide dp_degree[{dp}] x sharding_degree[{sd}]")
         if pp > 1:

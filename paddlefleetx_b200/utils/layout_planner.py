@@ -101,7 +101,8 @@ class Plan:
     recompute: str                       # none | core_attn | full_attn | full
     sequence_parallel: bool
     fused_tp: bool
-    cp: int = 1                          # context parallelism: cp of the (dp x sharding) data ranks share a batch and split its sequence (Ulysses)
+    cp: int = 1                          # context parallelism: cp of the (dp x sharding) data ranks share a batch and split its sequence
+    cp_mode: str = "ulysses"             # ulysses: all-to-all around attention (cp divides the local heads); ring: K / V blocks on a ring, any cp
     est_step_s: float = 0.0
     est_mem_gb: float = 0.0
     tokens_per_s: float = 0.0
@@ -113,12 +114,14 @@ class Plan:
               f"Distributed.sharding.sharding_degree={self.sharding}", f"Distributed.sharding.sharding_stage={self.stage}",
               f"Global.micro_batch_size={self.micro_batch}", f"Model.use_recompute={self.recompute != 'none'}",
               f"Model.sequence_parallel={self.sequence_parallel}", f"Distributed.cp_degree={self.cp}"]
+        if self.cp > 1:
+            ov.append(f"Distributed.cp_mode={self.cp_mode}")
         if self.recompute != "none":
             ov.append(f"Model.recompute_granularity={self.recompute}")
         return ov
 
     def describe(self) -> str:
-        return (f"dp{self.dp} x sharding{self.sharding}(stage {self.stage}){f' [cp{self.cp}]' if self.cp > 1 else ''} x mp{self.mp}{'+sp' if self.sequence_parallel else ''} x pp{self.pp}, "
+        return (f"dp{self.dp} x sharding{self.sharding}(stage {self.stage}){f' [cp{self.cp} {self.cp_mode}]' if self.cp > 1 else ''} x mp{self.mp}{'+sp' if self.sequence_parallel else ''} x pp{self.pp}, "
                 f"micro {self.micro_batch} x {self.accumulate}, recompute {self.recompute}: {self.est_step_s * 1e3:.1f} ms/step, "
                 f"{self.est_mem_gb:.0f} GB, {self.tokens_per_s:,.0f} tok/s")
 
@@ -167,7 +170,12 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
         # for 27.7 ms of wire time — the micro-benchmarks hide 60-70 % of a single collective, the full backward (re-gather + two GEMMs per
         # collective, smaller N / K) does not
         tp = vol / hw.link_bw * (1.0 if plan.fused_tp else 1.6) + (0 if plan.fused_tp else 8.0 * layers_local * 12e-6)
-    if cp > 1:        # Ulysses: 4 all-to-alls per layer forward (q, k, v, out) and 4 backward, each moving (cp - 1) / cp of tokens x h / mp bf16
+    if cp > 1 and plan.cp_mode == "ring":
+        # ring: (cp - 1) hops per layer of K and V forward (bf16), K / V again plus the fp32 dK / dV accumulators backward = 16 bytes per
+        # token x h / mp per hop; each hop is posted before the block it overlaps, so only what the attention math cannot cover is exposed
+        wire = 16.0 * (cp - 1) * tokens * s.hidden / mp / hw.link_bw
+        tp += layers_local * (max(0.0, wire - lt["attn"]) + 3.0 * (cp - 1) * 12e-6)
+    elif cp > 1:      # Ulysses: 4 all-to-alls per layer forward (q, k, v, out) and 4 backward, each moving (cp - 1) / cp of tokens x h / mp bf16
         tp += 8.0 * layers_local * tokens * s.hidden / mp * 2.0 * (cp - 1) / cp / hw.link_bw + 8.0 * layers_local * 12e-6
     pipe_p2p = 0.0 if pp == 1 else 2.0 * tokens * s.hidden * 2.0 / (mp if plan.sequence_parallel else 1) / hw.link_bw + 4 * 15e-6
     if pp > 1:
@@ -228,8 +236,14 @@ def enumerate_plans(s: ModelShape, world: int, local_batch: int, stages: Iterabl
                 for stage in (stages if sd > 1 else (1,)):
                     if stage == 3 and pp > 1:
                         continue                                           # the stage-3 wrapper and the pipeline schedule are not combined
-                    cps = [1] + [c for c in _divisors(rest) if c > 1 and pp == 1 and mp == 1 and (s.heads // mp) % c == 0 and s.seq % c == 0 and s.seq >= 4096]
-                    for c in cps:                                          # context parallelism only where long sequences make activations the problem
+                    cps = [(1, "ulysses")]                                 # context parallelism only where long sequences make activations the problem
+                    for c in _divisors(rest):
+                        if c > 1 and pp == 1 and mp == 1 and s.seq >= 4096:
+                            if (s.heads // mp) % c == 0 and s.seq % c == 0:
+                                cps.append((c, "ulysses"))
+                            if s.seq % (2 * c) == 0:                       # zigzag shards: two chunks per rank
+                                cps.append((c, "ring"))
+                    for c, cmode in cps:
                         group_batch = rank_batch * c                       # the c ranks of a group pool their share of the global batch
                         for mb in _divisors(group_batch):
                             n_micro = group_batch // mb
@@ -237,7 +251,7 @@ def enumerate_plans(s: ModelShape, world: int, local_batch: int, stages: Iterabl
                                 continue
                             for rc in ("none", "core_attn", "full"):
                                 out.append(Plan(dp=dp, sharding=sd, stage=stage, mp=mp, pp=pp, micro_batch=mb, accumulate=n_micro, recompute=rc,
-                                                sequence_parallel=mp > 1, fused_tp=mp > 1, cp=c))
+                                                sequence_parallel=mp > 1, fused_tp=mp > 1, cp=c, cp_mode=cmode))
     return out
 
 
@@ -255,7 +269,7 @@ def plan_layouts(s: ModelShape, world: int, local_batch: int, hw: Optional[Hardw
     plans.sort(key=lambda p: (p.est_step_s, p.est_mem_gb))
     seen, uniq = set(), []
     for p in plans:                                                       # one entry per layout: its best micro-batch / recompute
-        key = (p.dp, p.sharding, p.stage, p.mp, p.pp, p.cp)
+        key = (p.dp, p.sharding, p.stage, p.mp, p.pp, p.cp, p.cp_mode if p.cp > 1 else "")
         if key not in seen:
             seen.add(key)
             uniq.append(p)

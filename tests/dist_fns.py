@@ -617,8 +617,16 @@ def context_parallel_matches_single(rank, world, dp, sharding, cp, extra=()):
         dist.all_reduce(l)
         losses.append(float(l) / world)
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
+    heads = cfg.Model.num_attention_heads
     for k, v in eng.module.model.state_dict().items():
-        assert torch.allclose(v, ref_state[k], atol=5e-5, rtol=1e-4), k
+        ref = ref_state[k]
+        if k.endswith("qkv_proj.bias"):
+            # softmax is invariant to a shift of the keys: the K-bias gradient is exactly zero in theory and rounding noise in practice, which
+            # Adam normalises to full-size steps — those entries follow the summation order of the attention implementation, not the layout
+            v, ref = v.view(heads, 3, -1), ref.view(heads, 3, -1)
+            assert torch.allclose(v[:, 1], ref[:, 1], atol=1e-3), k
+            v, ref = v[:, [0, 2]], ref[:, [0, 2]]
+        assert torch.allclose(v, ref, atol=5e-5, rtol=1e-4), (k, float((v - ref).abs().max()))
 
 
 def dap_split_phase_pairs(rank, world):
@@ -681,3 +689,60 @@ def dap_split_phase_pairs(rank, world):
     p_rep.grad, p_skip.grad = torch.full((3,), float(rank + 1)), torch.full((3,), float(rank + 1))
     dap.grad_sync([{"params": [p_rep], "dap": True}, {"params": [p_skip]}])
     assert float(p_rep.grad[0]) == sum(range(1, world + 1)) and float(p_skip.grad[0]) == rank + 1
+
+
+def ring_attention_matches_full(rank, world):
+    """parallel/ring_attention.py: zigzag shards + K / V blocks on the ring reproduce attention over the whole sequence — outputs and the
+    gradients of q, k and v — causal and unmasked, and with the kernels' counter-hash dropout the forward / backward pair stays consistent
+    (the gradient of a linear functional equals its finite difference)."""
+    from paddlefleetx_b200.parallel import ring_attention as R
+    from paddlefleetx_b200.parallel.topology import HybridCommunicateGroup
+
+    hcg = HybridCommunicateGroup(dp=world, cp=world, cp_mode="ring")
+    group = hcg.get_context_parallel_group()
+    assert group.nranks == world and group.rank == rank
+    b, s, h, d = 2, 8 * world, 3, 4                                  # 3 heads on 2 / 4 ranks: no Ulysses split exists for this shape
+    gen = torch.Generator().manual_seed(5)
+    full = [torch.randn(b, s, h, d, dtype=torch.float64, generator=gen) for _ in range(3)]
+    w = torch.randn(b, s, h, d, dtype=torch.float64, generator=gen)
+    assert torch.equal(R.zigzag_merge([R.zigzag_slice(w, world, r) for r in range(world)]), w)
+    for causal in (True, False):
+        ref_in = [t.clone().requires_grad_(True) for t in full]
+        qt, kt, vt = (t.transpose(1, 2) for t in ref_in)
+        ref = torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, is_causal=causal).transpose(1, 2)
+        (ref * w).sum().backward()
+        loc = [R.zigzag_slice(t, world, rank).clone().requires_grad_(True) for t in full]
+        out = R.ring_attention(*loc, group, causal=causal)
+        torch.testing.assert_close(out, R.zigzag_slice(ref.detach(), world, rank), atol=1e-10, rtol=1e-8)
+        (out * R.zigzag_slice(w, world, rank)).sum().backward()
+        for a, r_ in zip(loc, ref_in):
+            torch.testing.assert_close(a.grad, R.zigzag_slice(r_.grad, world, rank), atol=1e-10, rtol=1e-8)
+    # dropout: same pattern in forward and backward of every block -> directional derivative matches
+    from paddlefleetx_b200.parallel.rng import get_rng_state_tracker
+
+    tr = get_rng_state_tracker()
+    if not tr.has("local_seed"):
+        tr.add("local_seed", 1234 + rank)
+    loc = [R.zigzag_slice(t, world, rank).clone().requires_grad_(True) for t in full]
+    wl = R.zigzag_slice(w, world, rank)
+
+    def run(q, k, v):
+        state = tr.get_states_tracker()
+        with tr.rng_state("local_seed"):
+            o = R.ring_attention(q, k, v, group, causal=True, dropout_p=0.25)
+        tr.set_states_tracker(state)                                 # replay the same dropout pattern on the next call
+        return (o * wl).sum()
+
+    run(*loc).backward()
+    dirs = [torch.randn(t.shape, dtype=torch.float64, generator=gen) for t in loc]
+    # a perturbation of THIS rank's shards changes every rank's loss: sum the losses over the group to differentiate the same function
+    eps = 1e-6
+    total = []
+    for sign in (1, -1):
+        l = run(*(t.detach() + sign * eps * dd for t, dd in zip(loc, dirs))).detach().clone()
+        dist.all_reduce(l)
+        total.append(float(l))
+    fd = (total[0] - total[1]) / (2 * eps)
+    an = torch.stack([(t.grad * dd).sum() for t, dd in zip(loc, dirs)]).sum()
+    dist.all_reduce(an)
+    assert abs(fd - float(an)) < 1e-5 * max(1.0, abs(fd)), (fd, float(an))

@@ -100,3 +100,18 @@ def test_context_parallel_cp2_matches_single():          # beyond the reference:
 
 def test_context_parallel_cp2_with_zero_sharding_and_rope_matches_single():
     run_distributed("dist_fns:context_parallel_matches_single", 4, 1, 4, 2, ["Model.use_rope=True"])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ring_attention_matches_full_attention(world):          # beyond the reference: zigzag ring attention (Distributed.cp_mode: ring)
+    run_distributed("dist_fns:ring_attention_matches_full", world)
+
+
+def test_context_parallel_ring_cp2_matches_single():
+    run_distributed("dist_fns:context_parallel_matches_single", 2, 2, 1, 2, ["Distributed.cp_mode=ring"])
+
+
+def test_context_parallel_ring_cp4_more_ranks_than_ulysses_allows_with_zero_sharding_and_rope():
+    # 4 heads on mp 1 would allow Ulysses cp 4 too; 3 heads (hidden 48) do not: only the ring runs this layout
+    run_distributed("dist_fns:context_parallel_matches_single", 4, 1, 4, 4,
+                    ["Distributed.cp_mode=ring", "Model.use_rope=True", "Model.num_attention_heads=3", "Model.hidden_size=48", "Model.ffn_hidden_size=96"])

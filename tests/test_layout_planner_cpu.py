@@ -82,3 +82,19 @@ def test_long_sequences_bring_in_context_parallelism():
     # same tokens per GPU per step with and without cp
     a = next(p for p in plans if p.cp == 2)
     assert a.micro_batch * a.accumulate == 2
+
+
+def test_ring_mode_covers_head_counts_ulysses_cannot_split_and_hides_its_transfers():
+    """40 heads leave Ulysses cp in {2, 4, 8}; 25 heads leave it nothing, the ring still offers every cp whose zigzag shards divide the
+    sequence.  At 32 k tokens the ring's K / V hops fit under the attention math (no exposed time), so it is not slower than the all-to-all."""
+    hw = Hardware()
+    odd = ModelShape(layers=40, hidden=5000, heads=25, vocab=50304, ffn=20480, seq=32768)
+    plans = plan_layouts(odd, 8, 1, hw=hw)
+    cp_plans = [p for p in plans if p.cp > 1]
+    assert cp_plans and all(p.cp_mode == "ring" for p in cp_plans)
+    assert "Distributed.cp_mode=ring" in cp_plans[0].overrides()
+    s = ModelShape(layers=40, hidden=5120, heads=40, vocab=50304, ffn=20480, seq=32768)
+    both = plan_layouts(s, 8, 1, hw=hw)
+    ring = next(p for p in both if p.cp == 4 and p.cp_mode == "ring" and p.sharding == 8)
+    uly = next(p for p in both if p.cp == 4 and p.cp_mode == "ulysses" and p.sharding == 8)
+    assert ring.breakdown["tp_comm"] <= uly.breakdown["tp_comm"] and "ring" in ring.describe()

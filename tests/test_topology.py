@@ -34,3 +34,23 @@ def test_hcg_accessors_without_process_group():
     assert h.is_first_stage and not h.is_last_stage and h.next_rank == 7
     assert h.get_rank_from_stage(1) == 7
     assert h.get_parallel_mode() == "pipeline"
+
+
+def test_context_parallel_groups_and_modes_without_process_group():
+    """cp consecutive DATA ranks (dp_rank * sharding + sharding_rank) share a batch; the mode is validated where the topology is built and
+    where the YAML is read."""
+    from helpers import tiny_gpt_config
+
+    for rank in range(8):
+        h = HybridCommunicateGroup(dp=2, sharding=4, cp=4, cp_mode="ring", rank=rank, world_size=8, build_groups=False)
+        ranks = h.get_context_parallel_group().ranks
+        assert len(ranks) == 4 and rank in ranks and h.cp_mode == "ring" and h.get_context_parallel_rank() == ranks.index(rank)
+    with pytest.raises(ValueError):
+        HybridCommunicateGroup(dp=2, sharding=4, cp=3, rank=0, world_size=8, build_groups=False)
+    with pytest.raises(ValueError):
+        HybridCommunicateGroup(dp=8, cp=2, cp_mode="striped", rank=0, world_size=8, build_groups=False)
+    cfg = tiny_gpt_config(["Distributed.dp_degree=4", "Distributed.cp_degree=2", "Distributed.cp_mode=Ring"], nranks=4)
+    assert cfg.Distributed.cp_mode == "ring" and cfg.Distributed.cp_degree == 2
+    assert tiny_gpt_config([], nranks=1).Distributed.cp_mode == "ulysses"
+    with pytest.raises(AssertionError):
+        tiny_gpt_config(["Distributed.dp_degree=4", "Distributed.cp_degree=2", "Distributed.cp_mode=blockwise"], nranks=4)
