@@ -165,10 +165,25 @@ class LanguageModule(BasicModule):
         assert batch[0].shape[1] % c == 0, f"sequence length {batch[0].shape[1]} % cp_degree {c}"
         return [t.chunk(c, dim=1)[r].contiguous() for t in batch]
 
+    def _context_parallel_loss(self, loss, loss_mask):
+        """The criterion divides by THIS rank's mask count; the gradient reduction then averages the cp ranks.  With an uneven mask (padding,
+        masked-out EOS) the mean of the ranks' masked means is not the masked mean over the whole sequences, so rescale by
+        ``local count x c / group count``: the average over the group becomes ``sum(CE x mask) / sum(mask)`` exactly."""
+        from ...distributed.apis import env as _env
+
+        hcg = getattr(_env, "_hcg", None)
+        c = getattr(hcg, "cp", 1) if hcg is not None else 1
+        if c == 1:
+            return loss
+        local = loss_mask.detach().float().sum()
+        total = local.clone()
+        torch.distributed.all_reduce(total, group=hcg.get_context_parallel_group().process_group)
+        return loss * (local * c / total)
+
     def training_step(self, batch):
         tokens, position_ids, labels, loss_mask = self._context_parallel_slice(batch)
         preds = self(tokens, position_ids)
-        return self.loss_fn(preds, labels, loss_mask)
+        return self._context_parallel_loss(self.loss_fn(preds, labels, loss_mask), loss_mask)
 
     def training_step_end(self, log_dict):
         speed = 1.0 / log_dict["train_cost"]
@@ -184,7 +199,7 @@ class LanguageModule(BasicModule):
     def validation_step(self, batch):
         tokens, position_ids, labels, loss_mask = self._context_parallel_slice(batch)
         preds = self(tokens, position_ids)
-        return self.loss_fn(preds, labels, loss_mask)
+        return self._context_parallel_loss(self.loss_fn(preds, labels, loss_mask), loss_mask)
 
     def validation_step_end(self, log_dict):
         speed = 1.0 / log_dict["eval_cost"]

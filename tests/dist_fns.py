@@ -11,7 +11,7 @@ def _slice(batch, rank, world):
     return [t[rank * n:(rank + 1) * n].contiguous() for t in batch]
 
 
-def _reference_losses_and_state(overrides, n_steps, seed=11):
+def _reference_losses_and_state(overrides, n_steps, seed=11, batch_hook=None):
     """Single-process run of the same global batch, executed redundantly on every rank (world-1 topology)."""
     from paddlefleetx_b200.distributed.apis import env
     from paddlefleetx_b200.parallel.topology import HybridCommunicateGroup
@@ -29,6 +29,8 @@ def _reference_losses_and_state(overrides, n_steps, seed=11):
         init = {k: v.detach().clone() for k, v in module.model.state_dict().items()}
         eng = EagerEngine(configs=cfg, module=module)
         batches = synthetic_batches(cfg, n_steps, seed=seed)
+        if batch_hook is not None:
+            batches = [batch_hook(b) for b in batches]
         losses = [float(eng.train_step(b)) for b in batches]
         state = {k: v.detach().clone() for k, v in module.model.state_dict().items()}
     finally:
@@ -588,13 +590,25 @@ def barrier_skew_detected(rank, world):
         raise AssertionError("skew not detected")
 
 
-def context_parallel_matches_single(rank, world, dp, sharding, cp, extra=()):
+def _mask_out_a_ragged_tail(batch):
+    """Loss mask with a different number of live positions in every quarter of the sequence (and per sample)."""
+    tokens, pos, labels, mask = batch
+    mask = mask.clone()
+    s = mask.shape[1]
+    for i in range(mask.shape[0]):
+        mask[i, s - 1 - (i % 3) - s // 4:] = 0          # the tail (mostly the last cp shard) is dead
+        mask[i, 1:3 + i % 2] = 0
+    return tokens, pos, labels, mask
+
+
+def context_parallel_matches_single(rank, world, dp, sharding, cp, extra=(), ragged_mask=False):
     """Ulysses context parallelism (Distributed.cp_degree): the ranks of a cp group take the same batch, each a slice of the sequence; losses
     and weights must equal the single-process run.  Heads 4, seq 16 in the tiny recipe: cp 2 leaves 2 heads x 16 positions per rank."""
     data = dp * sharding // cp
     gb = 4
     _, batches, ref_losses, ref_state, init = _reference_losses_and_state(
-        ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}"] + list(extra), 4)
+        ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={gb}"] + list(extra), 4,
+        batch_hook=_mask_out_a_ragged_tail if ragged_mask else None)
     cfg = tiny_gpt_config([f"Global.global_batch_size={gb}", "Global.local_batch_size=None", f"Global.micro_batch_size={gb // data}",
                            f"Distributed.dp_degree={dp}", f"Distributed.sharding.sharding_degree={sharding}", "Distributed.sharding.sharding_stage=1",
                            f"Distributed.cp_degree={cp}"] + list(extra), nranks=world)

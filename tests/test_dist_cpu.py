@@ -115,3 +115,9 @@ def test_context_parallel_ring_cp4_more_ranks_than_ulysses_allows_with_zero_shar
     # 4 heads on mp 1 would allow Ulysses cp 4 too; 3 heads (hidden 48) do not: only the ring runs this layout
     run_distributed("dist_fns:context_parallel_matches_single", 4, 1, 4, 4,
                     ["Distributed.cp_mode=ring", "Model.use_rope=True", "Model.num_attention_heads=3", "Model.hidden_size=48", "Model.ffn_hidden_size=96"])
+
+
+@pytest.mark.parametrize("mode", ["ulysses", "ring"])
+def test_context_parallel_with_an_uneven_loss_mask_matches_single(mode):
+    # one replica of 2 cp ranks whose sequence shards hold different numbers of live positions: the loss is still sum(CE x mask) / sum(mask)
+    run_distributed("dist_fns:context_parallel_matches_single", 2, 2, 1, 2, [f"Distributed.cp_mode={mode}"], True)
