@@ -152,7 +152,6 @@ class MultiHeadAttention(nn.Module):
         if hcg is not None and getattr(hcg, "cp", 1) > 1:
             self.cp_group = hcg.get_context_parallel_group()
             self.cp_mode = getattr(hcg, "cp_mode", "ulysses")
-            assert not sequence_parallel, "cp_degree > 1 is not combined with Megatron sequence parallelism"
             assert self.cp_mode == "ring" or self.local_heads % self.cp_group.nranks == 0, \
                 f"local heads {self.local_heads} % cp {self.cp_group.nranks} (Ulysses shards heads; cp_mode: ring has no such limit)"
 
@@ -213,11 +212,18 @@ class MultiHeadAttention(nn.Module):
                     out = ring_attention(q, k, v, self.cp_group, True, p, self.head_dim ** -0.5)
             else:
                 out = ring_attention(q, k, v, self.cp_group, True, 0.0, self.head_dim ** -0.5)
-            return self.out_proj(out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim))
+            return self._project_out(out)
         q, k, v = (C.seq_head_all_to_all(t, self.cp_group, 2, 1) for t in (q, k, v))           # [b, s, H/c, d]
         out = recompute(self._core, q, k, v, attn_mask) if (self.recompute_core and self.training) else self._core(q, k, v, attn_mask)
         out = C.seq_head_all_to_all(out, self.cp_group, 1, 2)                    # [b, s/c, H, d]
-        return self.out_proj(out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim))
+        return self._project_out(out)
+
+    def _project_out(self, out):
+        """``[b, s, heads, d]`` -> output projection; Megatron sequence parallelism wants ``[s, b, h / n]`` (GEMM -> reduce-scatter along s)."""
+        out = out.reshape(out.shape[0], out.shape[1], self.local_heads * self.head_dim)
+        if self.sequence_parallel:
+            out = out.transpose(0, 1).contiguous()
+        return self.out_proj(out)
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None, cache: Optional[KVCache] = None,
                 positions: Optional[torch.Tensor] = None):
@@ -480,10 +486,12 @@ class GPTPretrainingCriterion(nn.Module):
         super().__init__()
         self.ce = ParallelCrossEntropy(mp_group)
 
-    def forward(self, logits: torch.Tensor, labels: torch.Tensor, loss_mask: torch.Tensor) -> torch.Tensor:
+    def forward(self, logits: torch.Tensor, labels: torch.Tensor, loss_mask: torch.Tensor, denominator: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``denominator`` (per-sample live-token counts) replaces ``sum(mask)`` when the mask seen here is only a shard of the sequences
+        (context parallelism under the pipeline schedule: language_module.GPTModule.pretreating_batch)."""
         per_tok = self.ce(logits, labels)
         mask = loss_mask.reshape(-1).float()
-        return (per_tok.reshape(-1) * mask).sum() / mask.sum()
+        return (per_tok.reshape(-1) * mask).sum() / (mask.sum() if denominator is None else denominator.float().sum())
 
 
 GPTPretrainingCriterionHybird = GPTPretrainingCriterion  # (sic) name used by the reference module layer

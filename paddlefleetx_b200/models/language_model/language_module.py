@@ -260,7 +260,15 @@ class GPTModule(LanguageModule):
 
     def pretreating_batch(self, batch):
         if self.configs.Distributed.pp_degree > 1:
-            tokens, position_ids, labels, loss_mask = batch
+            tokens, position_ids, labels, loss_mask = self._context_parallel_slice(batch)
+            hcg = getattr(env, "_hcg", None)
+            c = getattr(hcg, "cp", 1) if hcg is not None else 1
+            if c > 1:
+                # the pipeline computes the loss per micro-batch on the last stage: hand it each sample's share of the GROUP's live-token count,
+                # so that the cp ranks' losses average to sum(CE x mask) / sum(mask) over whole sequences (same rule as _context_parallel_loss)
+                rows = loss_mask.float().sum(dim=1)
+                torch.distributed.all_reduce(rows, group=hcg.get_context_parallel_group().process_group)
+                return [(tokens, position_ids), (labels, loss_mask, rows / c)]
             return [(tokens, position_ids), (labels, loss_mask)]
         return batch
 

@@ -218,8 +218,6 @@ def process_dist_config(cfg: AttrDict, nranks: Optional[int] = None) -> None:
     if cp > 1:        # context parallelism: cp consecutive data ranks share a batch and split its sequence
         if (dp * sd) % cp != 0:
             raise AssertionError(f"cp_degree[{cp}] must divide dp_degree[{dp}] x sharding_degree[{sd}]")
-        if pp > 1:
-            raise AssertionError("cp_degree > 1 is not combined with pipeline parallelism")
 
     if sd > 1 and (sh.sharding_stage == 3 or sh.sharding_offload):
         for flag in ("reduce_overlap", "broadcast_overlap"):

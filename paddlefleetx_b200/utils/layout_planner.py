@@ -238,7 +238,7 @@ def enumerate_plans(s: ModelShape, world: int, local_batch: int, stages: Iterabl
                         continue                                           # the stage-3 wrapper and the pipeline schedule are not combined
                     cps = [(1, "ulysses")]                                 # context parallelism only where long sequences make activations the problem
                     for c in _divisors(rest):
-                        if c > 1 and pp == 1 and mp == 1 and s.seq >= 4096:
+                        if c > 1 and pp == 1 and s.seq >= 4096:           # (cp also runs under the pipeline schedule; not searched: RoPE models cannot use it)
                             if (s.heads // mp) % c == 0 and s.seq % c == 0:
                                 cps.append((c, "ulysses"))
                             if s.seq % (2 * c) == 0:                       # zigzag shards: two chunks per rank

@@ -121,3 +121,14 @@ def test_context_parallel_ring_cp4_more_ranks_than_ulysses_allows_with_zero_shar
 def test_context_parallel_with_an_uneven_loss_mask_matches_single(mode):
     # one replica of 2 cp ranks whose sequence shards hold different numbers of live positions: the loss is still sum(CE x mask) / sum(mask)
     run_distributed("dist_fns:context_parallel_matches_single", 2, 2, 1, 2, [f"Distributed.cp_mode={mode}"], True)
+
+
+@pytest.mark.parametrize("sp,mode", [(False, "ulysses"), (True, "ulysses"), (True, "ring")])
+def test_context_parallel_inside_tensor_parallel_matches_single(sp, mode):
+    run_distributed("dist_fns:context_parallel_with_tp_matches_single", 4, 2, 2, sp, mode)
+
+
+@pytest.mark.parametrize("mode", ["ulysses", "ring"])
+def test_context_parallel_under_the_pipeline_schedule_matches_single(mode):
+    # pp2 x (sharding2 = cp2): sequence shards travel through the 1F1B schedule, the last stage normalises by the group's live-token count
+    run_distributed("dist_fns:pipeline_matches_single", 4, 2, 1, 1, 4, False, 2, mode)
