@@ -2,7 +2,8 @@
 (reference ppfleetx/data/sampler/collate.py:27-317): ``Stack`` / ``Pad`` / ``Tuple`` / ``Dict``."""
 from __future__ import annotations
 
-from typing import Callable, Dict, List
+from typing import Callable, List
+from typing import Dict as _Dict          # the combinator below is called ``Dict`` like the reference's
 
 import numpy as np
 import torch
