@@ -69,8 +69,10 @@ class InferenceEngine:
         cfg.setdefault("Distributed", AttrDict(dp_degree=1, mp_degree=self.mp_degree, pp_degree=1, sharding=AttrDict(sharding_degree=1, sharding_stage=1)))
         cfg.setdefault("Optimizer", AttrDict(lr=AttrDict()))
         name = cfg.Model.module
-        module_cls = getattr(importlib.import_module(_REGISTRY[name]), name)
-        module_cls.process_configs = lambda self_, c: c          # the recipe already holds post-processed values
+        base_cls = getattr(importlib.import_module(_REGISTRY[name]), name)
+        # the recipe already holds post-processed values: skip the post-processing in a throw-away subclass (patching the class itself would
+        # switch it off for every later build_module of the same task in this process)
+        module_cls = type(name, (base_cls,), {"process_configs": lambda self_, c: c})
         module = module_cls(cfg)
         model = module.model
         prune = ((recipe.get("Compress") or {}).get("Prune") or {})

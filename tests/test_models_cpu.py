@@ -40,8 +40,10 @@ def test_generation_module_export_and_inference_roundtrip(tmp_path):
     assert sorted(os.listdir(os.path.join(out, "rank_0"))) == ["model.pdiparams", "model.pdmodel"]
     ids = torch.tensor([module.tokenizer.encode("hello world")])
     want, _ = module.model.generate(ids)
+    before = type(module).process_configs
     got = InferenceEngine(out, 1, device="cpu").predict([ids.numpy()])["output_0"]
     assert np.array_equal(got, want.numpy())
+    assert type(module).process_configs is before          # serving must not switch the task's config post-processing off for later builds
 
 
 def test_sampling_is_seed_reproducible_and_respects_eos():
