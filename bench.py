@@ -243,6 +243,9 @@ def build_config(args, world: int):
 
 
 def main():
+    """Run one arm of the headline benchmark (``--impl``: ours, ``reference`` or ``torch_library``) on this rank and, on rank 0, print the ONE
+    JSON line of the driver contract: W untimed warm-up steps, exactly K device-timed steps between barriers (max over ranks), clocks sampled
+    during the timed region, the end-to-end arm through the public engine API, launch and exposed-communication counts."""
     args = parse()
     if args.impl == "reference":
         return reference_arm(args)

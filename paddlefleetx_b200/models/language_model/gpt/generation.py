@@ -113,6 +113,10 @@ class GPTForGeneration(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_ids, attention_mask=None, position_ids=None, seed: Optional[int] = None):
+        """Decode ``max_length`` new tokens for a batch of (left-padded) prompts: prefill once into the static KV cache, then one token per step —
+        logits processors (min length, repetition penalty, forced BOS / EOS), temperature, top-k / top-p sampling (native radix-descent sampler on
+        CUDA) or greedy search; the single-token step is replayed from a CUDA graph when enabled.  Returns ``(generated ids, scores)``
+        (reference single_model.py:898-1320)."""
         self.gpt.eval()
         if self.num_return_sequences > 1:
             input_ids = input_ids.repeat_interleave(self.num_return_sequences, 0)

@@ -699,6 +699,9 @@ class Unet(nn.Module):
 
     def forward(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None, self_cond=None,
                 cond_images=None, cond_drop_prob=0.0, use_recompute=False):
+        """Predict the noise (or ``x0`` / ``v``) for noisy images ``x`` at continuous ``time``: time (+ low-resolution noise level) conditioning
+        tokens, text conditioning through the Perceiver / attention pooling with classifier-free dropout of probability ``cond_drop_prob``, then the
+        down path, the middle blocks and the up path with skip connections (reference unet.py:1371-1562)."""
         b = x.shape[0]
         if self.self_cond:
             x = torch.cat((x, _default(self_cond, lambda: torch.zeros_like(x))), dim=1)

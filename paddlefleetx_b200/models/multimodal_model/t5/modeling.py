@@ -487,6 +487,9 @@ class T5Stack(nn.Module):
     def forward(self, input_ids=None, attention_mask=None, encoder_hidden_states=None, encoder_attention_mask=None, inputs_embeds=None, head_mask=None,
                 cross_attn_head_mask=None, past_key_values=None, use_cache=False, output_attentions=False, output_hidden_states=False,
                 return_dict=True):
+        """Run the stack (encoder, or decoder with cross-attention over ``encoder_hidden_states``) on ids or ready embeddings.  The relative-position
+        bias is computed by the first block and shared by the others; ``past_key_values`` / ``use_cache`` extend a decoder incrementally; the
+        optional tuples of hidden states / attention probabilities follow the reference's output classes (reference t5/modeling.py:880-1075)."""
         prefix = "decoder_" if self.is_decoder else ""
         if use_cache:
             assert self.is_decoder, f"`use_cache` can only be set to `True` if {type(self).__name__} is used as a decoder"

@@ -179,6 +179,9 @@ class EmbeddingsAndEvoformer(nn.Module):
         return msa, pair
 
     def forward(self, batch, prev=None):
+        """Features -> ``{single, pair, msa}`` representations: target / MSA embedding, relative-position and recycling (``prev``) terms, template
+        pair stack + template attention, the extra-MSA stack, the Evoformer blocks, template torsion-angle rows and the single projection
+        (reference evoformer.py:504-760)."""
         from .common import dgram_from_positions
 
         tf, mf = batch["target_feat"], batch["msa_feat"]

@@ -62,6 +62,9 @@ class _EvoAttnFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        """Gradients of the gated attention w.r.t. q / k / v, the two additive biases and the gate: the native kernel recomputes the probabilities
+        from the saved log-sum-exp tile by tile (dK / dV in tensor memory, dQ through an fp32 workspace); bias gradients are reduced over the axes
+        the biases were broadcast along."""
         q, k, v, mb, pb, gt, lse = ctx.saved_tensors[:7]
         has_mb, has_pb, has_gate = ctx.flags
         gpp, scale = ctx.gpp, ctx.scale

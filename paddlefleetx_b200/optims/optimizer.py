@@ -499,6 +499,10 @@ class FusedAdamW:
     # ------------------------------------------------------------------ step
     @torch.no_grad()
     def step(self) -> None:
+        """One optimizer step over every flat group: finish the outstanding gradient reductions, global gradient norm (local shards + the mp / pp /
+        sharding / expert groups) and clip coefficient on the device, found-inf check for fp16, then the fused multi-precision AdamW on this rank's
+        shard — under ZeRO the same kernel delivers the new low-precision weights to every rank (NVLS / peer stores, or an NCCL all-gather) — on the
+        side stream when ``step_overlap`` is on, so that the update of the later layers runs beneath the next forward pass."""
         lr = self.get_lr()
         self._step_count += 1
         if _debug.enabled():

@@ -426,6 +426,9 @@ class PipelineParallel(nn.Module):
 
     # -- 1F1B ---------------------------------------------------------------------------------------
     def forward_backward_pipeline(self, data, scaler=None):
+        """One training step under the 1F1B schedule (interleaved when virtual stages are configured): ``warm`` forward micro-batches, then
+        forward / backward pairs with the stage-boundary activations and gradients exchanged by ``batch_isend_irecv``, then the remaining backwards;
+        returns the mean loss over the micro-batches, broadcast from the last stage (reference contract: eager_engine.py:507-517)."""
         if self._num_virtual > 1:
             return self._interleaved(data, scaler)
         M = self.accumulate_steps

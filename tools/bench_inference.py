@@ -23,6 +23,7 @@ REF_FP16_MS = {"gpt-345m": {1: 18.91, 2: 20.01, 4: 20.83, 8: 24.06, 16: 29.32}, 
 
 
 def main():
+    """Time prompt + generation for each batch size with CUDA events after warm-up and write one JSON record (latency per batch, tokens / s)."""
     p = argparse.ArgumentParser()
     p.add_argument("--model", default="gpt-6.7b")
     p.add_argument("--batches", default="1,2,4,8,16")

@@ -42,6 +42,7 @@ def parse():
 
 
 def main():
+    """Build the selected workload through the public engine, run warm-up + timed steps under the bench.py timing rules and print one JSON line."""
     a = parse()
     from paddlefleetx_b200.core import EagerEngine
     from paddlefleetx_b200.distributed.apis import env

@@ -34,6 +34,7 @@ def timed(fn, iters=10, warmup=3):
 
 
 def main():
+    """Run every multi-GPU check on this rank and print one ``RESULT {json}`` line per check (rank 0); exit status 1 if any check failed."""
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))

@@ -12,6 +12,7 @@ import torch  # noqa: E402
 
 
 def main():
+    """Validate this process's environment (device, architecture, native library, one GEMM) and, under a launcher, the collectives between ranks."""
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     ok = True
 

@@ -53,6 +53,7 @@ class _GPT(nn.Module):
 
 
 def run(args, spec, ClockSampler) -> int:
+    """Train the headline config on stock PyTorch under the same timing rules as our arm and print the same JSON line with ``impl: torch_library``."""
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
