@@ -44,6 +44,9 @@ class Hardware:
     attn_bwd_flops: float = 3.1e14
     launch_s: float = 4e-6
     mem_gb: float = HBM_GB
+    # inside the whole training step the GEMMs run ~7 % below the stand-alone cuBLAS rate: the step sits at the power cap (1.3-1.46 GHz) with
+    # memory-bound kernels in between.  Calibrated on the 1-GPU 6.7B step (313.8 ms, profiles/r2/c14_bench_n1.json)
+    step_efficiency: float = 0.925
 
     @staticmethod
     def measured() -> "Hardware":
@@ -159,7 +162,7 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
     tokens = float(mb * s.seq) / cp                      # a context-parallel rank holds 1 / cp of every sequence
     layers_local = s.layers / pp
     lt = _layer_time(hw, s, tokens, mp, plan.sequence_parallel, plan.recompute)
-    per_micro = layers_local * sum(lt.values())
+    per_micro = layers_local * sum(lt.values()) / hw.step_efficiency
     head = 3.0 * _gemm_time(hw, tokens, s.vocab / mp, s.hidden) + 10.0 * tokens * s.vocab / mp / hw.hbm_bw     # LM head + fused CE (last stage)
     per_micro += head / pp
     # tensor-parallel collectives: 4 forward + 4 backward per layer, (mp - 1) / mp of tokens x h bf16 each
@@ -169,7 +172,9 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
         # exposure calibrated on the 2-GPU 6.7B runs (profiles/r2/bench_c6_mp2_*): +38 ms per step with the fused kernels, +51 ms with NCCL,
         # for 27.7 ms of wire time — the micro-benchmarks hide 60-70 % of a single collective, the full backward (re-gather + two GEMMs per
         # collective, smaller N / K) does not
-        tp = vol / hw.link_bw * (1.0 if plan.fused_tp else 1.6) + (0 if plan.fused_tp else 8.0 * layers_local * 12e-6)
+        # (353 / 367 ms at mp2 against 314 ms on one GPU: 1.6 wire times with the fused kernels, 2.1 with NCCL — this term also carries the
+        # lower efficiency of GEMMs with halved N / K, which the per-GEMM roofline does not see at these sizes)
+        tp = vol / hw.link_bw * (1.6 if plan.fused_tp else 2.1) + (0 if plan.fused_tp else 8.0 * layers_local * 12e-6)
     if cp > 1 and plan.cp_mode == "ring":
         # ring: (cp - 1) hops per layer of K and V forward (bf16), K / V again plus the fp32 dK / dV accumulators backward = 16 bytes per
         # token x h / mp per hop; each hop is posted before the block it overlaps, so only what the attention math cannot cover is exposed
@@ -189,7 +194,10 @@ def estimate(s: ModelShape, hw: Hardware, world: int, local_batch: int, plan: Pl
         dp_comm = 2.0 * p_local * 2.0 * (data_ranks - 1) / data_ranks / hw.link_bw
         if stage == 3:
             dp_comm += 2.0 * n_micro * p_local * 2.0 * (sd - 1) / sd / hw.link_bw     # per-layer gathers in forward and backward
-    exposed_dp = 0.1 * dp_comm + (0.0 if data_ranks == 1 else 1.5e-3)
+    # 10 % of the exchange is exposed outright (first / last bucket); the hidden 90 % still costs about half its duration because the
+    # collective kernels take SMs, HBM bandwidth and power from the GEMMs they run beside (sharding8: 325 ms vs 314 ms on one GPU with an
+    # optimizer 8x smaller — profiles/r2/c15_bench_n8.json)
+    exposed_dp = (0.1 + 0.5) * dp_comm + (0.0 if data_ranks == 1 else 1.5e-3)
     # AdamW over the local shard: 2 (bf16 w) + 4 (grad) + 12 (master, m, v read) + 12 (write) bytes per parameter; overlapped with the next forward
     opt = p_local / (sd if stage >= 1 else 1) * 30.0 / hw.hbm_bw
     exposed_opt = 0.6 * opt            # "overlapped" still costs: the forward GEMMs it runs beside slow down 2-3x (trace, profiles/r2)

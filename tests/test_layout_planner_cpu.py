@@ -98,3 +98,22 @@ def test_ring_mode_covers_head_counts_ulysses_cannot_split_and_hides_its_transfe
     ring = next(p for p in both if p.cp == 4 and p.cp_mode == "ring" and p.sharding == 8)
     uly = next(p for p in both if p.cp == 4 and p.cp_mode == "ulysses" and p.sharding == 8)
     assert ring.breakdown["tp_comm"] <= uly.breakdown["tp_comm"] and "ring" in ring.describe()
+
+
+def test_cost_model_reproduces_the_measured_6p7b_layouts():
+    """The five GPT-6.7B layouts measured on B200s in round 2 (profiles/r2: c14_bench_n1, c15_bench_n8 + its named_layout, bench_c6_mp2_*): the
+    default hardware constants predict each step within 4 %, and rank them in the measured order."""
+    s, hw = shape("6.7b"), Hardware()
+    base = dict(dp=1, sharding=1, stage=1, mp=1, pp=1, micro_batch=8, accumulate=1, recompute="none", sequence_parallel=False, fused_tp=False)
+    cases = [  # world, sequences per data rank, plan, measured ms / step
+        (1, 8, dict(), 313.8),
+        (8, 8, dict(sharding=8), 325.1),
+        (2, 16, dict(mp=2, micro_batch=16, sequence_parallel=True, fused_tp=True), 353.2),
+        (2, 16, dict(mp=2, micro_batch=16, sequence_parallel=True, fused_tp=False), 366.9),
+        (8, 32, dict(mp=2, pp=2, sharding=2, micro_batch=4, accumulate=8, sequence_parallel=True, fused_tp=True), 448.0)]
+    pred = []
+    for world, lb, kw, measured in cases:
+        p = estimate(s, hw, world, lb, Plan(**{**base, **kw}))
+        assert abs(p.est_step_s * 1e3 / measured - 1.0) < 0.04, (kw, p.est_step_s * 1e3, measured)
+        pred.append(p.est_step_s)
+    assert pred == sorted(pred)
