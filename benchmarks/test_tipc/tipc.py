@@ -35,7 +35,7 @@ def flag(name, default=False):
 
 def common(world, dp, sharding):
     bs, micro = env("bs_item", 16, int), env("micro_bs", None, int)
-    local = max(bs // max(dp * sharding, 1), 1)
+    local = max(bs // max(dp * sharding // env("cp_degree", 1, int), 1), 1)      # a context-parallel group consumes one batch
     amp = env("fp_item", "fp16") != "fp32"
     return local, micro or local, [
         "Global.seed=1234", f"Global.local_batch_size={local}", f"Global.micro_batch_size={micro or local}", "Global.global_batch_size=None",
@@ -48,7 +48,8 @@ def degrees():
     sh = env("sharding_degree", 1, int)
     return dp, mp, pp, sh, [f"Distributed.dp_degree={dp}", f"Distributed.mp_degree={mp}", f"Distributed.pp_degree={pp}",
                             f"Distributed.sharding.sharding_degree={sh}", f"Distributed.sharding.sharding_stage={env('sharding_stage', 1, int)}",
-                            f"Distributed.sharding.sharding_offload={flag('sharding_offload')}"]
+                            f"Distributed.sharding.sharding_offload={flag('sharding_offload')}",
+                            f"Distributed.cp_degree={env('cp_degree', 1, int)}", f"Distributed.cp_mode={env('cp_mode', 'ulysses')}"]
 
 
 def family_gpt(kind):
