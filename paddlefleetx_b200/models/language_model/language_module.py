@@ -175,10 +175,15 @@ class LanguageModule(BasicModule):
         c = getattr(hcg, "cp", 1) if hcg is not None else 1
         if c == 1:
             return loss
+        pg = hcg.get_context_parallel_group().process_group
         local = loss_mask.detach().float().sum()
         total = local.clone()
-        torch.distributed.all_reduce(total, group=hcg.get_context_parallel_group().process_group)
-        return loss * (local * c / total)
+        torch.distributed.all_reduce(total, group=pg)
+        scaled = loss * (local * c / total)
+        # report the loss of the whole sequences on every rank of the group (what a run without cp logs); the gradient stays this shard's
+        mean = scaled.detach().clone()
+        torch.distributed.all_reduce(mean, group=pg)
+        return scaled + (mean / c - scaled.detach())
 
     def training_step(self, batch):
         tokens, position_ids, labels, loss_mask = self._context_parallel_slice(batch)

@@ -642,8 +642,11 @@ def context_parallel_matches_single(rank, world, dp, sharding, cp, extra=(), rag
     losses = []
     for b in batches:
         l = eng.train_step(_slice(b, dr, dw)).detach().clone()        # the module keeps this rank's slice of the sequence
+        if data == 1:
+            mine = float(l)                                           # every rank of a cp group reports the loss of the whole sequences
         dist.all_reduce(l)
         losses.append(float(l) / world)
+        assert data > 1 or abs(mine - losses[-1]) < 1e-5, (mine, losses[-1])
     assert max(abs(a - b) for a, b in zip(losses, ref_losses)) < 2e-4, (losses, ref_losses)
     heads = cfg.Model.num_attention_heads
     for k, v in eng.module.model.state_dict().items():
