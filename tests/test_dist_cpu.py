@@ -132,3 +132,8 @@ def test_context_parallel_inside_tensor_parallel_matches_single(sp, mode):
 def test_context_parallel_under_the_pipeline_schedule_matches_single(mode):
     # pp2 x (sharding2 = cp2): sequence shards travel through the 1F1B schedule, the last stage normalises by the group's live-token count
     run_distributed("dist_fns:pipeline_matches_single", 4, 2, 1, 1, 4, False, 2, mode)
+
+
+@pytest.mark.parametrize("stage", [2, 3])
+def test_context_parallel_ring_with_zero_stage_2_and_3_matches_single(stage):
+    run_distributed("dist_fns:context_parallel_matches_single", 2, 1, 2, 2, ["Distributed.cp_mode=ring", f"Distributed.sharding.sharding_stage={stage}"], True)
