@@ -201,6 +201,10 @@ class MultiHeadAttention(nn.Module):
         Ring mode (``Distributed.cp_mode: ring``): every head stays here, K / V blocks travel (parallel/ring_attention.py)."""
         q, k, v = self._qkv(x)                                                   # [b, s/c, H, d]
         if self.use_rope:
+            if positions is None:     # pipeline stages > 0 receive activations only: the shard's positions follow from the layout (default ids)
+                from ....parallel.ring_attention import local_positions
+
+                positions = local_positions(q.shape[1], self.cp_group.nranks, self.cp_group.rank, self.cp_mode, q.device).expand(q.shape[0], -1)
             q, k = OF.rope(q.contiguous(), positions), OF.rope(k.contiguous(), positions)      # ``positions`` are global (sliced with the tokens)
         if self.cp_mode == "ring":
             assert attn_mask is None, "ring attention builds the causal mask from the zigzag layout; explicit masks are not sharded"

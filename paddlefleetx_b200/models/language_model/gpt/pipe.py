@@ -63,9 +63,6 @@ class GPTForPretrainingPipe(PipelineLayer):
                  **unused):
         ffn_hidden_size = ffn_hidden_size or 4 * hidden_size
         recompute_granularity = recompute_granularity or "full"
-        if use_rope and getattr(hcg, "cp", 1) > 1:
-            # a stage boundary carries ONE tensor: later stages rebuild default (0..s-1) positions, which is wrong for a sequence shard
-            raise ValueError("context parallelism under pipeline parallelism needs learned position embeddings (Model.use_rope=False)")
         sp = sequence_parallel and C.group_size(mp_group) > 1
         embed_args = dict(vocab_size=vocab_size, hidden=hidden_size, max_position=max_position_embeddings,
                           hidden_dropout=hidden_dropout_prob, init_std=initializer_range, sequence_parallel=sp, mp_group=mp_group,

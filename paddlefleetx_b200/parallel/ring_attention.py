@@ -37,6 +37,16 @@ def zigzag_slice(t: torch.Tensor, c: int, r: int, dim: int = 1) -> torch.Tensor:
     return torch.cat([parts[r], parts[2 * c - 1 - r]], dim=dim)
 
 
+def local_positions(s_local: int, c: int, r: int, mode: str, device=None) -> torch.Tensor:
+    """Global positions ``[s_local]`` of rank ``r``'s sequence shard when the data carries the default ``0 .. s-1`` position ids: a contiguous
+    slice (Ulysses) or the two zigzag chunks (ring).  Used where position ids do not travel with the activations (pipeline stages > 0)."""
+    if mode == "ring":
+        half = s_local // 2
+        a = torch.arange(half, device=device)
+        return torch.cat([r * half + a, (2 * c - 1 - r) * half + a])
+    return r * s_local + torch.arange(s_local, device=device)
+
+
 def zigzag_merge(parts, dim: int = 1) -> torch.Tensor:
     """Inverse of ``zigzag_slice`` over the rank-ordered list of local tensors."""
     c = len(parts)

@@ -184,7 +184,7 @@ def tp_shards_differ_across_ranks(rank, world):
         assert torch.equal(parts[0], parts[1]), n
 
 
-def pipeline_matches_single(rank, world, pp, mp, vpp, acc, sp=False, cp=1, cp_mode="ulysses"):
+def pipeline_matches_single(rank, world, pp, mp, vpp, acc, sp=False, cp=1, cp_mode="ulysses", extra=()):
     """pp (x mp, optionally with Megatron sequence parallelism) pipeline with tied embeddings reproduces the single-process loss curve
     AND the single-process weights (sequence-partial LayerNorm / bias gradients must be summed over the mp group on every stage)."""
     from paddlefleetx_b200.core import EagerEngine
@@ -193,7 +193,7 @@ def pipeline_matches_single(rank, world, pp, mp, vpp, acc, sp=False, cp=1, cp_mo
 
     gb = acc
     L = 4
-    common = [f"Model.num_layers={L}", "Model.use_flash_attn=False"]
+    common = [f"Model.num_layers={L}", "Model.use_flash_attn=False"] + list(extra)
     _, batches, ref_losses, ref_state, init = _reference_losses_and_state(
         # with an uneven mask the mean of per-micro-batch means is not the mean over the batch: the reference accumulates the same micro-batches
         common + ["Global.global_batch_size=None", f"Global.local_batch_size={gb}", f"Global.micro_batch_size={1 if cp > 1 else gb}"], 3, seed=31,

@@ -134,6 +134,12 @@ def test_context_parallel_under_the_pipeline_schedule_matches_single(mode):
     run_distributed("dist_fns:pipeline_matches_single", 4, 2, 1, 1, 4, False, 2, mode)
 
 
+@pytest.mark.parametrize("mode", ["ulysses", "ring"])
+def test_context_parallel_under_the_pipeline_schedule_with_rope_matches_single(mode):
+    # stages > 0 receive activations only: the rotary positions of a sequence shard are rebuilt from the cp layout
+    run_distributed("dist_fns:pipeline_matches_single", 4, 2, 1, 1, 4, False, 2, mode, ["Model.use_rope=True"])
+
+
 @pytest.mark.parametrize("stage", [2, 3])
 def test_context_parallel_ring_with_zero_stage_2_and_3_matches_single(stage):
     run_distributed("dist_fns:context_parallel_matches_single", 2, 1, 2, 2, ["Distributed.cp_mode=ring", f"Distributed.sharding.sharding_stage={stage}"], True)
